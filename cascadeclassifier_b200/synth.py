@@ -1,0 +1,162 @@
+"""Synthetic positives (.vec layout) and background images for benchmarks and parity tests.
+
+Stands in for `opencv_createsamples` on a generated pattern: the reference tool
+needs OpenCV C++, which is not in this image, so the positives are rendered here and stored in
+the identical .vec layout (tools/createsamples/utility.cpp:128-153, reader
+traincascade/lib/src/imagestorage.cpp:138-182).  Everything is seeded (numpy PCG64) so that the
+CPU oracle and the CUDA path see byte-identical inputs on any box.
+"""
+import os
+import struct
+
+import numpy as np
+
+
+def _pattern(size=96):
+    """High-contrast glyph on a flat background (a crude face: brow band, eyes, nose, mouth)."""
+    p = np.full((size, size), 170.0, np.float32)
+    s = size / 24.0
+    def box(x0, y0, x1, y1, v):
+        p[int(y0 * s):int(y1 * s), int(x0 * s):int(x1 * s)] = v
+    box(3, 5, 21, 8, 60)      # brow band
+    box(5, 8, 9, 11, 30)      # left eye
+    box(15, 8, 19, 11, 30)    # right eye
+    box(10, 8, 14, 16, 215)   # nose ridge
+    box(7, 17, 17, 20, 70)    # mouth
+    box(3, 11, 6, 16, 200)    # cheeks
+    box(18, 11, 21, 16, 200)
+    return p
+
+
+def _warp(pat, W, H, rng):
+    """Random affine jitter + contrast/brightness + noise; bilinear sampling with numpy only."""
+    size = pat.shape[0]
+    ang = rng.uniform(-0.18, 0.18)
+    sc = rng.uniform(0.85, 1.15)
+    tx, ty = rng.uniform(-0.08, 0.08, 2) * size
+    ca, sa = np.cos(ang) / sc, np.sin(ang) / sc
+    ys, xs = np.meshgrid((np.arange(H) + 0.5) / H * size, (np.arange(W) + 0.5) / W * size, indexing="ij")
+    cx = cy = size / 2.0
+    u = ca * (xs - cx) - sa * (ys - cy) + cx + tx
+    v = sa * (xs - cx) + ca * (ys - cy) + cy + ty
+    u = np.clip(u, 0, size - 1.001)
+    v = np.clip(v, 0, size - 1.001)
+    u0, v0 = u.astype(np.int32), v.astype(np.int32)
+    fu, fv = u - u0, v - v0
+    img = (pat[v0, u0] * (1 - fu) * (1 - fv) + pat[v0, u0 + 1] * fu * (1 - fv) +
+           pat[v0 + 1, u0] * (1 - fu) * fv + pat[v0 + 1, u0 + 1] * fu * fv)
+    gain = rng.uniform(0.6, 1.3)
+    bias = rng.uniform(-40, 40)
+    img = (img - 128.0) * gain + 128.0 + bias + rng.normal(0, rng.uniform(2, 12), img.shape)
+    if rng.random() < 0.5:  # illumination gradient
+        img += np.linspace(-1, 1, W)[None, :] * rng.uniform(-25, 25)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_positives(count, W, H, seed=12345):
+    rng = np.random.default_rng(seed)
+    pat = _pattern(96)
+    if W != H:  # stretch the glyph to the window aspect (e.g. 48x96 pedestrian-shaped windows)
+        pat = np.repeat(pat, 1, axis=0)
+    out = np.empty((count, H, W), np.uint8)
+    for i in range(count):
+        out[i] = _warp(pat, W, H, rng)
+    return out
+
+
+def make_background(w, h, seed):
+    """8-bit gray: multi-octave value noise + random rectangles / gradients (non-zero window variance)."""
+    rng = np.random.default_rng(seed)
+    img = np.zeros((h, w), np.float32)
+    amp = 1.0
+    for octave in range(6):
+        gh, gw = max(2, h >> (7 - octave)), max(2, w >> (7 - octave))
+        g = rng.random((gh + 1, gw + 1)).astype(np.float32)
+        ys = np.linspace(0, gh, h, endpoint=False)
+        xs = np.linspace(0, gw, w, endpoint=False)
+        y0, x0 = ys.astype(np.int32), xs.astype(np.int32)
+        fy, fx = (ys - y0)[:, None], (xs - x0)[None, :]
+        a = g[y0][:, x0]; b = g[y0][:, x0 + 1]; c = g[y0 + 1][:, x0]; d = g[y0 + 1][:, x0 + 1]
+        img += amp * (a * (1 - fx) * (1 - fy) + b * fx * (1 - fy) + c * (1 - fx) * fy + d * fx * fy)
+        amp *= 0.6
+    img = (img - img.min()) / max(1e-6, img.max() - img.min()) * 255.0
+    for _ in range(int(rng.integers(8, 24))):
+        x0, y0 = int(rng.integers(0, w - 8)), int(rng.integers(0, h - 8))
+        x1, y1 = min(w, x0 + int(rng.integers(8, max(9, w // 3)))), min(h, y0 + int(rng.integers(8, max(9, h // 3))))
+        kind = rng.random()
+        if kind < 0.5:
+            img[y0:y1, x0:x1] = img[y0:y1, x0:x1] * 0.3 + rng.uniform(0, 255) * 0.7
+        else:
+            img[y0:y1, x0:x1] += np.linspace(-60, 60, x1 - x0)[None, :] * rng.uniform(-1, 1)
+    img += rng.normal(0, 3.0, img.shape)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def make_backgrounds(count, w, h, seed0=1000):
+    return [make_background(w, h, seed0 + i) for i in range(count)]
+
+
+# ---- on-disk formats -------------------------------------------------------------------------
+def write_vec(path, samples):
+    """.vec: int32 count, int32 vecSize, int16 0, int16 0; per sample 1 pad byte + vecSize int16."""
+    n, H, W = samples.shape
+    with open(path, "wb") as f:
+        f.write(struct.pack("<iihh", n, W * H, 0, 0))
+        for i in range(n):
+            f.write(b"\x00")
+            f.write(samples[i].astype("<i2").tobytes())
+
+
+def read_vec(path, W, H):
+    with open(path, "rb") as f:
+        count, vec_size, _, _ = struct.unpack("<iihh", f.read(12))
+        if vec_size != W * H:
+            raise ValueError("vec sample size %d does not match %dx%d" % (vec_size, W, H))
+        raw = np.frombuffer(f.read(), np.uint8)
+    rec = 1 + 2 * vec_size
+    n = min(count, raw.size // rec)
+    body = raw[: n * rec].reshape(n, rec)[:, 1:]
+    vals = body.view("<i2").reshape(n, vec_size)
+    return vals.astype(np.uint8).reshape(n, H, W)
+
+
+def write_pgm(path, img):
+    h, w = img.shape
+    with open(path, "wb") as f:
+        f.write(b"P5\n%d %d\n255\n" % (w, h))
+        f.write(np.ascontiguousarray(img, np.uint8).tobytes())
+
+
+def read_pgm(path):
+    with open(path, "rb") as f:
+        data = f.read()
+    tokens, pos = [], 0
+    while len(tokens) < 4:
+        while data[pos:pos + 1].isspace():
+            pos += 1
+        if data[pos:pos + 1] == b"#":
+            while data[pos:pos + 1] != b"\n":
+                pos += 1
+            continue
+        start = pos
+        while not data[pos:pos + 1].isspace():
+            pos += 1
+        tokens.append(data[start:pos])
+    pos += 1
+    if tokens[0] != b"P5":
+        raise ValueError("only binary PGM (P5) is supported: %s" % path)
+    w, h, _ = int(tokens[1]), int(tokens[2]), int(tokens[3])
+    return np.frombuffer(data, np.uint8, w * h, pos).reshape(h, w).copy()
+
+
+def write_dataset(directory, positives, backgrounds):
+    os.makedirs(directory, exist_ok=True)
+    write_vec(os.path.join(directory, "pos.vec"), positives)
+    names = []
+    for i, bg in enumerate(backgrounds):
+        name = os.path.join(directory, "bg_%05d.pgm" % i)
+        write_pgm(name, bg)
+        names.append(name)
+    with open(os.path.join(directory, "bg.txt"), "w") as f:
+        f.write("\n".join(names) + "\n")
+    return os.path.join(directory, "pos.vec"), os.path.join(directory, "bg.txt")
