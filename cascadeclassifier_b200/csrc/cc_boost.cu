@@ -1,0 +1,1098 @@
+// K4: the boosted-tree stage trainer.  Device restatement of CvCascadeBoost::train and everything
+// under it (src/boost.cpp:168-518, src/o_cvboost.cpp:67-139, src/o_cvboostree.cpp:71-516,657-732,
+// src/o_cvdtree.cpp:95-187,296-357,1247-1320, src/o_cvcascadeboosttree.cpp:16-39,167-347).
+//
+// State lives in HBM for the whole stage; per weak tree the host only reads a few small structs
+// (node statistics, the winning split, the stage summary).  The split search — one pass over the
+// sorted-value / sorted-index rows of every local variable per tree node — is the dominant kernel.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+
+#include "cc_internal.h"
+
+namespace cc {
+
+struct EvalView {
+  int ftype, P, ns_pad;
+  const int32_t* sum;
+  const int32_t* tilted;
+  const float* nf;
+  const float* hog;
+  const HaarTaps* haar_taps;
+  const LbpTaps* lbp_taps;
+  const HogTaps* hog_taps;
+};
+EvalView make_eval_view(const cc_ctx* ctx);
+int traindata_free(cc_ctx* ctx);
+
+// ---- device copies of the evaluator (kept in sync with cc_eval.cu) --------------------------------
+__device__ __forceinline__ float d_haar_value(const HaarTaps& t, const EvalView& e, int s) {
+  const int32_t* base = (t.tilted() ? e.tilted : e.sum) + (size_t)(s >> 5) * e.P * TILE + (s & 31);
+  int acc = 0;
+  const int nt = t.ntaps();
+  for (int k = 0; k < nt; ++k) acc += tap_coef(t.w[k]) * base[(size_t)tap_off(t.w[k]) * TILE];
+  const float n = e.nf[s];
+  return n == 0.f ? 0.f : __fdiv_rn((float)acc, n);
+}
+__device__ __forceinline__ int d_lbp_code(const LbpTaps& t, const EvalView& e, int s) {
+  const int32_t* base = e.sum + (size_t)(s >> 5) * e.P * TILE + (s & 31);
+  int v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = base[(size_t)t.off[k] * TILE];
+  auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
+  const int c = cell(1, 1);
+  return (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
+         (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
+         (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
+}
+__device__ __forceinline__ float d_hog_value(const HogTaps& t, const EvalView& e, int comp, int s) {
+  const int bin = comp % 9, cell = comp / 9;
+  const size_t np = (size_t)e.ns_pad;
+  const float* ph = e.hog + (size_t)bin * e.P * np + s;
+  const float* pn = e.hog + (size_t)9 * e.P * np + s;
+  float res = __fadd_rn(__fsub_rn(__fsub_rn(ph[t.off[cell][0] * np], ph[t.off[cell][1] * np]), ph[t.off[cell][2] * np]), ph[t.off[cell][3] * np]);
+  float nrm = __fadd_rn(__fsub_rn(__fsub_rn(pn[t.off[0][0] * np], pn[t.off[1][1] * np]), pn[t.off[2][2] * np]), pn[t.off[3][3] * np]);
+  return res > 0.001f ? __fdiv_rn(res, __fadd_rn(nrm, 0.001f)) : 0.f;
+}
+__device__ __forceinline__ float d_eval_var(const EvalView& e, int var, int s) {
+  if (e.ftype == CC_FEATURE_HAAR) return d_haar_value(e.haar_taps[var], e, s);
+  if (e.ftype == CC_FEATURE_LBP) return (float)d_lbp_code(e.lbp_taps[var], e, s);
+  return d_hog_value(e.hog_taps[var / 36], e, var % 36, s);
+}
+
+// ---- small structs shared with the host ------------------------------------------------------------
+enum Crit { CRIT_GINI = 0, CRIT_MISCLASS = 1, CRIT_SQERR = 2 };
+
+struct NodeStats {
+  int n;
+  int cls_count[2];
+  int pad;
+  double rcw[2];      // regression: rcw[0] = sum of weights
+  double value, risk;
+  double rsum0;       // regression: node value * rcw[0] (initial right sum of find_split_ord_reg)
+};
+
+struct RowBest { float q; float c; float vleft; int pos; };
+struct RowBestCat { float q; int subset[8]; };
+
+struct BestSplit {
+  float q;
+  int var;            // global variable index
+  float c, vleft;
+  int pos;
+  int subset[8];
+  int valid;
+  int pad[2];
+};
+
+struct TreeSummary {
+  double scaleC;      // DAB: tree->scale(C)
+  double sumW;
+  int nz_count, have_subsample;
+  float threshold, hit_rate, false_alarm;
+  int num_pos, num_neg;
+};
+
+struct BoostBuffers {
+  int cap_n = 0;
+  size_t cap_rows = 0;
+  double *weights = nullptr, *weak_eval = nullptr, *stage_sum = nullptr, *sum_response = nullptr, *wnode = nullptr, *treeval = nullptr;
+  float *responses = nullptr, *ynode = nullptr;
+  int* orig_response = nullptr;
+  uint8_t* mask = nullptr;
+  int* node_of = nullptr;
+  RowBest* rowbest = nullptr;
+  RowBestCat* rowbest_cat = nullptr;
+  NodeStats* d_stats = nullptr;       // [CC_MAX_TREE_NODES]
+  BestSplit* d_best = nullptr;        // [1] (+ world candidates)
+  TreeSummary* d_summary = nullptr;
+  DevNode* d_tree = nullptr;          // [CC_MAX_TREE_NODES]
+  NodeStats* h_stats = nullptr;       // pinned
+  BestSplit* h_best = nullptr;
+  TreeSummary* h_summary = nullptr;
+  // stage state
+  int boost_type = CC_BOOST_GENTLE, crit = CRIT_SQERR, is_classifier = 0, have_subsample = 0;
+  cc_boost_params params;
+  bool row_quality_valid = false;
+};
+
+int boost_free(cc_ctx* ctx) {
+  BoostBuffers* b = ctx->boost;
+  if (b) {
+    cudaFree(b->weights); cudaFree(b->weak_eval); cudaFree(b->stage_sum); cudaFree(b->sum_response); cudaFree(b->wnode);
+    cudaFree(b->treeval); cudaFree(b->responses); cudaFree(b->ynode); cudaFree(b->orig_response); cudaFree(b->mask);
+    cudaFree(b->node_of); cudaFree(b->rowbest); cudaFree(b->rowbest_cat); cudaFree(b->d_stats); cudaFree(b->d_best);
+    cudaFree(b->d_summary); cudaFree(b->d_tree);
+    cudaFreeHost(b->h_stats); cudaFreeHost(b->h_best); cudaFreeHost(b->h_summary);
+    delete b;
+    ctx->boost = nullptr;
+  }
+  traindata_free(ctx);
+  return CC_OK;
+}
+
+static int ensure_boost(cc_ctx* ctx, int N, size_t nrows) {
+  if (!ctx->boost) ctx->boost = new BoostBuffers();
+  BoostBuffers* b = ctx->boost;
+  if (!b->d_stats) {
+    CC_CUDA(cudaMalloc(&b->d_stats, sizeof(NodeStats) * CC_MAX_TREE_NODES));
+    CC_CUDA(cudaMalloc(&b->d_best, sizeof(BestSplit) * 16));
+    CC_CUDA(cudaMalloc(&b->d_summary, sizeof(TreeSummary)));
+    CC_CUDA(cudaMalloc(&b->d_tree, sizeof(DevNode) * CC_MAX_TREE_NODES));
+    CC_CUDA(cudaMallocHost(&b->h_stats, sizeof(NodeStats) * CC_MAX_TREE_NODES));
+    CC_CUDA(cudaMallocHost(&b->h_best, sizeof(BestSplit) * 16));
+    CC_CUDA(cudaMallocHost(&b->h_summary, sizeof(TreeSummary)));
+  }
+  if (N > b->cap_n) {
+    cudaFree(b->weights); cudaFree(b->weak_eval); cudaFree(b->stage_sum); cudaFree(b->sum_response); cudaFree(b->wnode);
+    cudaFree(b->treeval); cudaFree(b->responses); cudaFree(b->ynode); cudaFree(b->orig_response); cudaFree(b->mask); cudaFree(b->node_of);
+    const size_t n = (size_t)N;
+    CC_CUDA(cudaMalloc(&b->weights, n * 8)); CC_CUDA(cudaMalloc(&b->weak_eval, n * 8)); CC_CUDA(cudaMalloc(&b->stage_sum, n * 8));
+    CC_CUDA(cudaMalloc(&b->sum_response, n * 8)); CC_CUDA(cudaMalloc(&b->wnode, n * 8)); CC_CUDA(cudaMalloc(&b->treeval, n * 8));
+    CC_CUDA(cudaMalloc(&b->responses, n * 4)); CC_CUDA(cudaMalloc(&b->ynode, n * 4)); CC_CUDA(cudaMalloc(&b->orig_response, n * 4));
+    CC_CUDA(cudaMalloc(&b->mask, n)); CC_CUDA(cudaMalloc(&b->node_of, n * 4));
+    b->cap_n = N;
+  }
+  if (nrows > b->cap_rows) {
+    cudaFree(b->rowbest); cudaFree(b->rowbest_cat);
+    b->rowbest = nullptr; b->rowbest_cat = nullptr;
+    if (ctx->ftype == CC_FEATURE_LBP) CC_CUDA(cudaMalloc(&b->rowbest_cat, nrows * sizeof(RowBestCat)));
+    else CC_CUDA(cudaMalloc(&b->rowbest, nrows * sizeof(RowBest)));
+    b->cap_rows = nrows;
+  }
+  return CC_OK;
+}
+
+// ---- block-level helpers (single-CTA kernels, blockDim = 1024) ---------------------------------------
+constexpr int ONE_CTA = 1024;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+__device__ __forceinline__ double block_sum(double v, double* scratch /*[32]*/) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double r = (lane < (int)(blockDim.x >> 5)) ? scratch[lane] : 0.0;
+  r = warp_sum(r);
+  return r;     // every thread holds the total
+}
+__device__ __forceinline__ long long block_sum_ll(long long v, double* scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  long long* sc = reinterpret_cast<long long*>(scratch);
+  __syncthreads();
+  if (lane == 0) sc[warp] = v;
+  __syncthreads();
+  long long r = (lane < (int)(blockDim.x >> 5)) ? sc[lane] : 0;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) r += __shfl_xor_sync(0xffffffffu, r, d);
+  return r;
+}
+
+__device__ __forceinline__ double d_log_ratio(double val) {   // boost.cpp:27-36
+  const double eps = 1e-5;
+  val = fmax(val, eps);
+  val = fmin(val, 1. - eps);
+  return log(val / (1. - val));
+}
+
+// ---- CvCascadeBoost::update_weights(nullptr), src/boost.cpp:190-265 ---------------------------------
+__global__ void k_boost_init(int N, const uint8_t* __restrict__ labels, int boost_type, double* weights, double* weak_eval,
+                             double* stage_sum, double* sum_response, float* responses, int* orig_response, uint8_t* mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int label = labels[i];
+  const int o = label * 2 - 1;
+  orig_response[i] = o;
+  weights[i] = 1. / N;
+  weak_eval[i] = 0.;
+  stage_sum[i] = 0.;
+  sum_response[i] = 0.;
+  mask[i] = 1;
+  float r = (float)label;
+  if (boost_type == CC_BOOST_LOGIT) r = o > 0 ? 2.f : -2.f;
+  else if (boost_type == CC_BOOST_GENTLE) r = (float)o;
+  responses[i] = r;
+}
+
+__global__ void k_tree_begin(int N, const uint8_t* __restrict__ mask, int* node_of) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) node_of[i] = mask[i] ? 0 : -1;
+}
+
+// ---- CvBoostTree::calc_node_value, src/o_cvboostree.cpp:657-732 (single CTA) -------------------------
+// Also writes the per-sample operand of the split search for this node:
+//   regression, +-1 targets (GAB): wnode = y*w (sign carries the target), 0 for non-members
+//   regression, free targets (LB): wnode = w, ynode = y
+//   classification (DAB/RAB)     : wnode = +w for class 1, -w for class 0
+// and weak_eval[s] = node value for every member (leaf assignment of CvBoostTree::try_split_node,
+// :74-84; children overwrite it when the node is split).
+__global__ void __launch_bounds__(ONE_CTA, 1)
+k_node_prepare(int N, int nid, int is_classifier, int boost_type, const int* __restrict__ node_of, const double* __restrict__ weights,
+               const float* __restrict__ responses, double* wnode, float* ynode, double* weak_eval, NodeStats* stats) {
+  __shared__ double scratch[32];
+  double a0 = 0, a1 = 0, a2 = 0;
+  long long c0 = 0, c1 = 0;
+  for (int s = threadIdx.x; s < N; s += blockDim.x) {
+    if (node_of[s] != nid) { wnode[s] = 0.0; continue; }
+    const double w = weights[s];
+    const float y = responses[s];
+    if (is_classifier) {
+      const int r = (int)y;
+      if (r) { a1 += w; c1++; wnode[s] = w; } else { a0 += w; c0++; wnode[s] = -w; }
+    } else {
+      const double t = (double)y;
+      a0 += w; a1 += t * w; a2 += t * t * w; c0++;
+      if (boost_type == CC_BOOST_LOGIT) { wnode[s] = w; ynode[s] = y; } else wnode[s] = t * w;
+    }
+  }
+  a0 = block_sum(a0, scratch); a1 = block_sum(a1, scratch); a2 = block_sum(a2, scratch);
+  c0 = block_sum_ll(c0, scratch); c1 = block_sum_ll(c1, scratch);
+  NodeStats st;
+  st.pad = 0;
+  if (is_classifier) {
+    st.n = (int)(c0 + c1); st.cls_count[0] = (int)c0; st.cls_count[1] = (int)c1;
+    st.rcw[0] = a0; st.rcw[1] = a1; st.risk = 0; st.rsum0 = 0;
+    const int class_idx = a1 > a0;
+    if (boost_type == CC_BOOST_DISCRETE) st.value = class_idx * 2 - 1;
+    else { const double p = a1 / (a0 + a1); st.value = 0.5 * d_log_ratio(p); }
+  } else {
+    st.n = (int)c0; st.cls_count[0] = st.cls_count[1] = 0;
+    st.rcw[0] = a0; st.rcw[1] = 0;
+    const double iw = 1. / a0;
+    st.value = a1 * iw;
+    double risk = a2 - (a1 * iw) * a1;
+    const double n = (double)st.n;
+    risk *= n * iw * n * iw;
+    st.risk = risk;
+    st.rsum0 = st.value * a0;
+  }
+  if (threadIdx.x == 0) stats[nid] = st;
+  const double value = st.value;
+  for (int s = threadIdx.x; s < N; s += blockDim.x)
+    if (node_of[s] == nid) weak_eval[s] = value;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split search, ordered variables: CvBoostTree::find_split_ord_reg / find_split_ord_class
+// (src/o_cvboostree.cpp:361-426, :151-247).
+//
+// One warp scans one row: 256 sorted positions per step (8 per lane, 128-bit loads of the u16 index
+// row and the f32 sorted-value row), per-sample operand gathered from shared memory, two running
+// sums carried as warp-level exclusive scans in f64.  Samples that are not in the node (trimmed out,
+// or in another node) carry operand 0 and are skipped, which is the stable compaction that
+// CvCascadeBoostTrainData::subsample_data / split_node_data perform on the index rows
+// (src/o_cvcascadeboosttraindata.cpp:80-121, src/o_cvcascadeboosttree.cpp:192-253).  A split between
+// consecutive node samples p < j is admissible iff v[p] + 2*FLT_EPSILON < v[j] (f32).  Per row the
+// first position attaining the maximal f64 criterion wins (strict '<' of the reference).
+// ------------------------------------------------------------------------------------------------
+constexpr int SS_THREADS = 512;
+constexpr int SS_WARPS = SS_THREADS / 32;
+constexpr int SS_EPT = 8;
+constexpr int SS_TILE = 32 * SS_EPT;
+
+template <int CRIT>
+__device__ __forceinline__ double criterion(double A, double B, double totA, double totB) {
+  if (CRIT == CRIT_SQERR) {         // A = L (sum w), B = lsum (sum w*y); totA = sum w, totB = value*sum w
+    const double L = A, R = totA - A, lsum = B, rsum = totB - B;
+    if (!(L > 0.0) || !(R > 0.0)) return -DBL_MAX;
+    return (lsum * lsum * R + rsum * rsum * L) / (L * R);
+  } else if (CRIT == CRIT_GINI) {   // A = lcw[0], B = lcw[1]
+    const double r0 = totA - A, r1 = totB - B, L = A + B, R = r0 + r1;
+    if (!(L > 0.0) || !(R > 0.0)) return -DBL_MAX;
+    const double lsum2 = A * A + B * B, rsum2 = r0 * r0 + r1 * r1;
+    return (lsum2 * R + rsum2 * L) / (L * R);
+  } else {                          // misclassification
+    const double r0 = totA - A, r1 = totB - B;
+    return fmax(A + r1, B + r0);
+  }
+}
+
+template <int CRIT, bool HAS_Y>
+__global__ void __launch_bounds__(SS_THREADS, 1)
+k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ sval, int n_stride, int N, int nrows,
+                   const double* __restrict__ wnode, const float* __restrict__ ynode, const NodeStats* __restrict__ stats,
+                   RowBest* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sw = reinterpret_cast<double*>(smem_raw);
+  float* sy = reinterpret_cast<float*>(sw + N);
+  for (int i = threadIdx.x; i < N; i += SS_THREADS) { sw[i] = wnode[i]; if (HAS_Y) sy[i] = ynode[i]; }
+  __syncthreads();
+  const NodeStats st = *stats;
+  const double totA = st.rcw[0];
+  const double totB = (CRIT == CRIT_SQERR) ? st.rsum0 : st.rcw[1];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const float eps = FLT_EPSILON * 2;
+
+  for (int row = blockIdx.x * SS_WARPS + warp; row < nrows; row += gridDim.x * SS_WARPS) {
+    const uint16_t* ri = sidx + (size_t)row * n_stride;
+    const float* rv = sval + (size_t)row * n_stride;
+    double carryA = 0, carryB = 0;
+    float carryV = 0.f;
+    int carryHas = 0, carryCnt = 0;
+    double bestVal = -1.0;
+    int bestPos = -1;
+    float bestVl = 0.f, bestVr = 0.f;
+
+    uint4 nxt_i = *reinterpret_cast<const uint4*>(ri + lane * SS_EPT);
+    float4 nxt_v0 = *reinterpret_cast<const float4*>(rv + lane * SS_EPT);
+    float4 nxt_v1 = *reinterpret_cast<const float4*>(rv + lane * SS_EPT + 4);
+    for (int base = 0; base < N; base += SS_TILE) {
+      const uint4 ci = nxt_i;
+      const float4 cv0 = nxt_v0, cv1 = nxt_v1;
+      if (base + SS_TILE < N) {      // prefetch the next tile while this one is processed
+        nxt_i = *reinterpret_cast<const uint4*>(ri + base + SS_TILE + lane * SS_EPT);
+        nxt_v0 = *reinterpret_cast<const float4*>(rv + base + SS_TILE + lane * SS_EPT);
+        nxt_v1 = *reinterpret_cast<const float4*>(rv + base + SS_TILE + lane * SS_EPT + 4);
+      }
+      const int i0 = base + lane * SS_EPT;
+      const uint32_t iw[4] = {ci.x, ci.y, ci.z, ci.w};
+      const float v[SS_EPT] = {cv0.x, cv0.y, cv0.z, cv0.w, cv1.x, cv1.y, cv1.z, cv1.w};
+      double a[SS_EPT], b[SS_EPT];
+      unsigned act = 0;
+      double ta = 0, tb = 0;
+      float lastv = 0.f;
+#pragma unroll
+      for (int j = 0; j < SS_EPT; ++j) {
+        const int idx = (int)((iw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
+        double w = 0.0;
+        float y = 0.f;
+        if (i0 + j < N) { w = sw[idx]; if (HAS_Y) y = sy[idx]; }
+        if (w != 0.0) {
+          act |= 1u << j;
+          lastv = v[j];
+          if (CRIT == CRIT_SQERR) {
+            if (HAS_Y) { a[j] = w; b[j] = (double)y * w; } else { a[j] = fabs(w); b[j] = w; }
+          } else {
+            a[j] = w < 0.0 ? -w : 0.0;
+            b[j] = w > 0.0 ? w : 0.0;
+          }
+          ta += a[j]; tb += b[j];
+        } else { a[j] = 0.0; b[j] = 0.0; }
+      }
+      const int cnt = __popc(act);
+      // warp exclusive scans of (ta, tb, cnt)
+      double ia = ta, ib = tb;
+      int ic = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double xa = __shfl_up_sync(0xffffffffu, ia, d), xb = __shfl_up_sync(0xffffffffu, ib, d);
+        const int xc = __shfl_up_sync(0xffffffffu, ic, d);
+        if (lane >= d) { ia += xa; ib += xb; ic += xc; }
+      }
+      double pa = carryA + (ia - ta), pb = carryB + (ib - tb);
+      int pc = carryCnt + (ic - cnt);
+      // value of the last node sample before this lane's chunk
+      const uint32_t has_mask = __ballot_sync(0xffffffffu, act != 0);
+      const uint32_t before = has_mask & lt_mask;
+      const int src = before ? (31 - __clz(before)) : 0;
+      const float pv_other = __shfl_sync(0xffffffffu, lastv, src);
+      float pv = before ? pv_other : carryV;
+      int pHas = before ? 1 : carryHas;
+#pragma unroll
+      for (int j = 0; j < SS_EPT; ++j) {
+        if (act & (1u << j)) {
+          if (pHas && __fadd_rn(pv, eps) < v[j]) {
+            const double val = criterion<CRIT>(pa, pb, totA, totB);
+            if (val > bestVal) { bestVal = val; bestPos = pc - 1; bestVl = pv; bestVr = v[j]; }
+          }
+          pa += a[j]; pb += b[j]; pc += 1;
+          pv = v[j]; pHas = 1;
+        }
+      }
+      // carries for the next tile
+      carryA += __shfl_sync(0xffffffffu, ia, 31);
+      carryB += __shfl_sync(0xffffffffu, ib, 31);
+      carryCnt += __shfl_sync(0xffffffffu, ic, 31);
+      if (has_mask) {
+        const int lastLane = 31 - __clz(has_mask);
+        carryV = __shfl_sync(0xffffffffu, lastv, lastLane);
+        carryHas = 1;
+      }
+    }
+    // warp argmax: larger value first, then smaller position (first maximum of the sequential scan)
+    int owner = lane;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bestVal, d);
+      const int op = __shfl_xor_sync(0xffffffffu, bestPos, d);
+      const int oo = __shfl_xor_sync(0xffffffffu, owner, d);
+      const bool take = op >= 0 && (bestPos < 0 || ov > bestVal || (ov == bestVal && op < bestPos));
+      if (take) { bestVal = ov; bestPos = op; owner = oo; }
+    }
+    const float vl = __shfl_sync(0xffffffffu, bestVl, owner), vr = __shfl_sync(0xffffffffu, bestVr, owner);
+    if (lane == 0) {
+      RowBest rb;
+      rb.q = bestPos >= 0 ? (float)bestVal : -1.f;
+      rb.c = __fmul_rn(__fadd_rn(vl, vr), 0.5f);
+      rb.vleft = vl;
+      rb.pos = bestPos;
+      out[row] = rb;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Split search, categorical variables (LBP codes): CvBoostTree::find_split_cat_reg / _cat_class
+// (src/o_cvboostree.cpp:428-516, :249-359).  One warp per variable.  The 256 per-category sums are
+// accumulated in node order (ascending sample index) exactly like the reference: for every sample
+// the lane owning bin (code & 31) performs the two f64 additions, so the order of additions inside a
+// bin is the sequential one.  Categories are then ranked by (key, category) — the stable order —
+// and the prefix scan over the ranked categories is done sequentially by lane 0 with un-fused f64
+// operations.
+// ------------------------------------------------------------------------------------------------
+constexpr int CAT_THREADS = 256;
+constexpr int CAT_WARPS = CAT_THREADS / 32;
+
+__global__ void __launch_bounds__(CAT_THREADS, 1)
+k_split_search_cat(const uint8_t* __restrict__ codes, int n_stride, int N, int nrows, const double* __restrict__ wnode,
+                   const float* __restrict__ ynode, int is_classifier, int crit, int has_y, RowBestCat* __restrict__ out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sw = reinterpret_cast<double*>(smem_raw);                   // [N]
+  float* sy = reinterpret_cast<float*>(sw + N);                        // [N] (LB only, else unused but allocated)
+  double* bins = reinterpret_cast<double*>(sy + ((N + 1) & ~1));       // [CAT_WARPS][3][256]: s0, s1, key
+  int* order_all = reinterpret_cast<int*>(bins + CAT_WARPS * 3 * 256); // [CAT_WARPS][256]
+  for (int i = threadIdx.x; i < N; i += CAT_THREADS) { sw[i] = wnode[i]; sy[i] = has_y ? ynode[i] : 0.f; }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* s0 = bins + warp * 3 * 256;     // regression: sum of y*w ; classification: class-0 weight
+  double* s1 = s0 + 256;                  // regression: sum of w   ; classification: class-1 weight
+  double* key = s1 + 256;
+  int* order = order_all + warp * 256;
+
+  for (int row = blockIdx.x * CAT_WARPS + warp; row < nrows; row += gridDim.x * CAT_WARPS) {
+    const uint8_t* rc = codes + (size_t)row * n_stride;
+    for (int i = lane; i < 256; i += 32) { s0[i] = 0.0; s1[i] = 0.0; }
+    __syncwarp();
+    for (int base = 0; base < N; base += 32) {
+      const int i = base + lane;
+      const int mycode = i < N ? rc[i] : 0;
+      const int lim = min(32, N - base);
+      for (int j = 0; j < lim; ++j) {
+        const int code = __shfl_sync(0xffffffffu, mycode, j);
+        const double w = sw[base + j];
+        if (w != 0.0 && (code & 31) == lane) {
+          if (is_classifier) {
+            if (w > 0.0) s1[code] = __dadd_rn(s1[code], w); else s0[code] = __dadd_rn(s0[code], -w);
+          } else if (has_y) {
+            s0[code] = __dadd_rn(s0[code], __dmul_rn((double)sy[base + j], w));
+            s1[code] = __dadd_rn(s1[code], w);
+          } else {
+            s0[code] = __dadd_rn(s0[code], w);            // w already carries the +-1 target
+            s1[code] = __dadd_rn(s1[code], fabs(w));
+          }
+        }
+      }
+    }
+    __syncwarp();
+    // sort key per category, totals (sequential over categories, as the reference)
+    double R = 0, rsum = 0, rc0 = 0, rc1 = 0;
+    if (lane == 0) {
+      if (!is_classifier) {
+        for (int i = 0; i < 256; ++i) {
+          R = __dadd_rn(R, s1[i]);
+          rsum = __dadd_rn(rsum, s0[i]);
+          key[i] = fabs(s1[i]) > DBL_EPSILON ? __ddiv_rn(s0[i], s1[i]) : 0.0;
+        }
+      } else {
+        for (int i = 0; i < 256; ++i) { rc0 = __dadd_rn(rc0, s0[i]); rc1 = __dadd_rn(rc1, s1[i]); key[i] = s1[i]; }
+      }
+    }
+    __syncwarp();
+    // stable rank by counting
+    for (int j = lane; j < 256; j += 32) {
+      const double kj = key[j];
+      int rank = 0;
+      for (int k = 0; k < 256; ++k) { const double kk = key[k]; rank += (kk < kj) || (kk == kj && k < j); }
+      order[rank] = j;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      double best_val = -1.0;
+      int best_subset = -1;
+      if (!is_classifier) {
+        double L = 0, lsum = 0;
+        for (int si = 0; si < 255; ++si) {
+          const int idx = order[si];
+          const double ni = s1[idx];
+          if (ni > FLT_EPSILON) {
+            const double s = __dmul_rn(key[idx], ni);       // "revert back to unnormalized sums"
+            lsum = __dadd_rn(lsum, s); L = __dadd_rn(L, ni);
+            rsum = __dsub_rn(rsum, s); R = __dsub_rn(R, ni);
+            if (L > FLT_EPSILON && R > FLT_EPSILON) {
+              const double num = __dadd_rn(__dmul_rn(__dmul_rn(lsum, lsum), R), __dmul_rn(__dmul_rn(rsum, rsum), L));
+              const double val = __ddiv_rn(num, __dmul_rn(L, R));
+              if (best_val < val) { best_val = val; best_subset = si; }
+            }
+          }
+        }
+      } else {
+        double lcw0 = 0, lcw1 = 0, L = 0;
+        R = __dadd_rn(rc0, rc1);
+        for (int si = 0; si < 255; ++si) {
+          const int idx = order[si];
+          const double w0 = s0[idx], w1 = s1[idx];
+          const double weight = __dadd_rn(w0, w1);
+          if (weight < FLT_EPSILON) continue;
+          lcw0 = __dadd_rn(lcw0, w0); rc0 = __dsub_rn(rc0, w0); lcw1 = __dadd_rn(lcw1, w1); rc1 = __dsub_rn(rc1, w1);
+          if (crit == CRIT_GINI) {
+            const double lsum2 = __dadd_rn(__dmul_rn(lcw0, lcw0), __dmul_rn(lcw1, lcw1));
+            const double rsum2 = __dadd_rn(__dmul_rn(rc0, rc0), __dmul_rn(rc1, rc1));
+            L = __dadd_rn(L, weight); R = __dsub_rn(R, weight);
+            if (L > FLT_EPSILON && R > FLT_EPSILON) {
+              const double val = __ddiv_rn(__dadd_rn(__dmul_rn(lsum2, R), __dmul_rn(rsum2, L)), __dmul_rn(L, R));
+              if (best_val < val) { best_val = val; best_subset = si; }
+            }
+          } else {
+            const double val = fmax(__dadd_rn(lcw0, rc1), __dadd_rn(lcw1, rc0));
+            if (best_val < val) { best_val = val; best_subset = si; }
+          }
+        }
+      }
+      RowBestCat rb;
+      rb.q = best_subset >= 0 ? (float)best_val : -1.f;
+      for (int k = 0; k < 8; ++k) rb.subset[k] = 0;
+      for (int i = 0; i <= best_subset; ++i) { const int idx = order[i]; rb.subset[idx >> 5] |= 1 << (idx & 31); }
+      out[row] = rb;
+    }
+    __syncwarp();
+  }
+}
+
+// ---- CvDTree::find_best_split over the local rows (src/o_cvdtree.cpp:313-357): highest f32 quality,
+//      lowest variable index on ties, accepted only if quality > 0.  Single CTA. ---------------------
+__global__ void __launch_bounds__(ONE_CTA, 1)
+k_argmax_rows(const RowBest* __restrict__ rows, const RowBestCat* __restrict__ rows_cat, int nrows, int row_base, BestSplit* out) {
+  __shared__ float sq[32];
+  __shared__ int sr[32];
+  float q = -1.f;
+  int r = 0x7fffffff;
+  for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+    const float qi = rows ? rows[i].q : rows_cat[i].q;
+    if (qi > q) { q = qi; r = i; }    // i increases within a thread, so ties keep the lower index
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) {
+    const float oq = __shfl_xor_sync(0xffffffffu, q, d);
+    const int orr = __shfl_xor_sync(0xffffffffu, r, d);
+    if (oq > q || (oq == q && orr < r)) { q = oq; r = orr; }
+  }
+  if (lane == 0) { sq[warp] = q; sr[warp] = r; }
+  __syncthreads();
+  if (warp == 0) {
+    q = sq[lane]; r = sr[lane];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const float oq = __shfl_xor_sync(0xffffffffu, q, d);
+      const int orr = __shfl_xor_sync(0xffffffffu, r, d);
+      if (oq > q || (oq == q && orr < r)) { q = oq; r = orr; }
+    }
+    if (lane == 0) {
+      BestSplit b;
+      memset(&b, 0, sizeof(b));
+      b.q = q;
+      b.valid = (q > 0.f) && r != 0x7fffffff;
+      if (r != 0x7fffffff) {
+        b.var = row_base + r;
+        if (rows) { b.c = rows[r].c; b.vleft = rows[r].vleft; b.pos = rows[r].pos; }
+        else for (int k = 0; k < 8; ++k) b.subset[k] = rows_cat[r].subset[k];
+      }
+      *out = b;
+    }
+  }
+}
+
+// winner among the per-rank candidates (feature sharding): same ordering rule, variable indices are global
+__global__ void k_argmax_candidates(const BestSplit* __restrict__ cands, int n, BestSplit* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  BestSplit best = cands[0];
+  for (int i = 1; i < n; ++i) {
+    const BestSplit c = cands[i];
+    if (!c.valid) continue;
+    if (!best.valid || c.q > best.q || (c.q == best.q && c.var < best.var)) best = c;
+  }
+  *out = best;
+}
+
+// ---- calc_node_dir + split_node_data (src/o_cvboostree.cpp:87-149, src/o_cvcascadeboosttree.cpp:167-347):
+//      node samples left of the split point are exactly those with value <= v[split_point], because a
+//      split never separates equal values; categorical: subset bit set -> left. -------------------------
+__global__ void k_apply_split(EvalView e, int N, int nid, int lid, int rid, const BestSplit* __restrict__ best, int* node_of) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= N || node_of[s] != nid) return;
+  const BestSplit b = *best;
+  const float val = d_eval_var(e, b.var, s);
+  bool left;
+  if (e.ftype == CC_FEATURE_LBP) { const int c = (int)val; left = (b.subset[c >> 5] & (1 << (c & 31))) != 0; }
+  else left = val <= b.vleft;
+  node_of[s] = left ? lid : rid;
+}
+
+// ---- tree prediction for one sample, CvCascadeBoostTree::predict (src/o_cvcascadeboosttree.cpp:16-39)
+__device__ __forceinline__ double d_tree_predict(const EvalView& e, const DevNode* __restrict__ tree, int s) {
+  int n = 0;
+  while (tree[n].left >= 0) {
+    const float val = d_eval_var(e, tree[n].var_idx, s);
+    bool left;
+    if (e.ftype == CC_FEATURE_LBP) { const int c = (int)val; left = (tree[n].subset[c >> 5] & (1 << (c & 31))) != 0; }
+    else left = val <= tree[n].c;
+    n = left ? tree[n].left : tree[n].right;
+  }
+  return tree[n].value;
+}
+
+__device__ __forceinline__ uint32_t f2key(float v) {
+  uint32_t u = __float_as_uint(v);
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu)); }
+
+// ------------------------------------------------------------------------------------------------
+// Everything that follows a finished weak tree, in one single-CTA kernel:
+//   update_weights(tree)  src/boost.cpp:266-406     trim_weights  src/o_cvboost.cpp:101-139
+//   isErrDesired          src/boost.cpp:479-518
+// The two order statistics (trim threshold = first sorted weight at which the running remainder
+// 1-rate-sum drops to <= 0; stage threshold = eval[thresholdIdx] of the sorted positive sums) are
+// found by bisection over the value bits instead of by sorting.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ONE_CTA, 1)
+k_tree_finish(EvalView e, int N, int boost_type, int have_subsample, double trim_rate, float min_hit_rate,
+              const DevNode* __restrict__ tree, const uint8_t* __restrict__ labels, const int* __restrict__ orig_response,
+              double* weights, double* weak_eval, double* treeval, double* stage_sum, double* sum_response, float* responses,
+              uint8_t* mask, TreeSummary* summary) {
+  __shared__ double scratch[32];
+  __shared__ unsigned long long s_u64;
+  // (a) responses of the samples that did not take part in the tree, and the threshold-rule output for everyone
+  for (int s = threadIdx.x; s < N; s += blockDim.x) {
+    const double tv = d_tree_predict(e, tree, s);
+    treeval[s] = tv;
+    if (have_subsample && !mask[s]) weak_eval[s] = tv;
+  }
+  __syncthreads();
+  // (b) weight update
+  double scaleC = 1.0;
+  double sumW = 0;
+  if (boost_type == CC_BOOST_DISCRETE) {
+    double sw = 0, err = 0;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) {
+      const double w = weights[s];
+      sw += w;
+      err += w * (weak_eval[s] != (double)orig_response[s]);
+    }
+    sw = block_sum(sw, scratch); err = block_sum(err, scratch);
+    if (sw != 0) err /= sw;
+    const double C = -d_log_ratio(err);
+    scaleC = C;
+    const double sc1 = exp(C);
+    double acc = 0;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) {
+      const double w = weights[s] * ((weak_eval[s] != (double)orig_response[s]) ? sc1 : 1.0);
+      acc += w;
+      weights[s] = w;
+    }
+    sumW = block_sum(acc, scratch);
+  } else if (boost_type == CC_BOOST_LOGIT) {
+    double acc = 0;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) {
+      const double sr = sum_response[s] + 0.5 * weak_eval[s];
+      sum_response[s] = sr;
+      const double ex = exp(-2 * sr);
+      const double p = 1. / (1. + ex);
+      double w = p * (1 - p);
+      w = fmax(w, (double)FLT_EPSILON);
+      weights[s] = w;
+      acc += w;
+      if (orig_response[s] > 0) { const double z = 1. / p; responses[s] = (float)fmin(z, 10.); }
+      else { const double z = 1. / (1 - p); responses[s] = (float)-fmin(z, 10.); }
+    }
+    sumW = block_sum(acc, scratch);
+  } else {   // REAL and GENTLE share the update w *= exp(-y f)
+    double acc = 0;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) {
+      const double we = weak_eval[s] * (double)(-orig_response[s]);
+      const double w = weights[s] * exp(we);
+      weights[s] = w;
+      acc += w;
+    }
+    sumW = block_sum(acc, scratch);
+  }
+  if (sumW > FLT_EPSILON) {
+    const double inv = 1. / sumW;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) weights[s] *= inv;
+  }
+  __syncthreads();
+  // (c) trim_weights
+  int nz = N, hs = 0;
+  if (trim_rate > 0. && trim_rate < 1.) {
+    const double target = 1. - trim_rate;
+    // smallest weight value v with  (sum of weights <= v) - v >= target ; DBL_MAX if none
+    unsigned long long lo = 0, hi = 0x7FF0000000000000ull;     // bit patterns of non-negative doubles are ordered
+    // predicate(v) true for hi (inf) trivially false if total - ... ; handle "none" below
+    bool any = false;
+    {
+      double tot = 0, mx = 0;
+      for (int s = threadIdx.x; s < N; s += blockDim.x) { tot += weights[s]; mx = fmax(mx, weights[s]); }
+      tot = block_sum(tot, scratch);
+      // block max
+      for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = mx;
+      __syncthreads();
+      mx = scratch[threadIdx.x & 31];
+      for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      any = (tot - mx) >= target;
+      hi = (unsigned long long)__double_as_longlong(mx);
+    }
+    double threshold = DBL_MAX;
+    if (any) {
+      // Q(x) = [ sum{w <= x} - max{w <= x} >= target ] is a monotone step function of x whose first
+      // true point is the wanted weight value (the sorted prefix before the last copy of that value).
+      while (lo < hi) {
+        const unsigned long long mid = lo + ((hi - lo) >> 1);
+        const double v = __longlong_as_double((long long)mid);
+        double acc = 0, top = 0;
+        for (int s = threadIdx.x; s < N; s += blockDim.x) { const double w = weights[s]; if (w <= v) { acc += w; top = fmax(top, w); } }
+        acc = block_sum(acc, scratch);
+        for (int d = 16; d > 0; d >>= 1) top = fmax(top, __shfl_xor_sync(0xffffffffu, top, d));
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = top;
+        __syncthreads();
+        top = scratch[threadIdx.x & 31];
+        for (int d = 16; d > 0; d >>= 1) top = fmax(top, __shfl_xor_sync(0xffffffffu, top, d));
+        if (acc - top >= target) hi = mid; else lo = mid + 1;
+      }
+      // snap to the smallest actual weight >= bound
+      const double bound = __longlong_as_double((long long)lo);
+      double mn = DBL_MAX;
+      for (int s = threadIdx.x; s < N; s += blockDim.x) { const double w = weights[s]; if (w >= bound) mn = fmin(mn, w); }
+      for (int d = 16; d > 0; d >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = mn;
+      __syncthreads();
+      mn = scratch[threadIdx.x & 31];
+      for (int d = 16; d > 0; d >>= 1) mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      threshold = mn;
+    }
+    long long cnt = 0;
+    for (int s = threadIdx.x; s < N; s += blockDim.x) {
+      const int f = weights[s] >= threshold;
+      mask[s] = (uint8_t)f;
+      cnt += f;
+    }
+    nz = (int)block_sum_ll(cnt, scratch);
+    hs = nz < N;
+  } else {
+    // mask is left as it is (all ones: have_subsample can never become true)
+    hs = 0;
+  }
+  // (d) stage sums and isErrDesired
+  long long npos = 0;
+  for (int s = threadIdx.x; s < N; s += blockDim.x) {
+    stage_sum[s] += treeval[s] * scaleC;
+    npos += labels[s] == 1;
+  }
+  const int numPos = (int)block_sum_ll(npos, scratch);
+  const int numNeg = N - numPos;
+  const int thresholdIdx = (int)((1.0F - min_hit_rate) * numPos);
+  // k-th smallest (k = thresholdIdx) of the float stage sums of the positives
+  uint32_t klo = 0, khi = 0xFFFFFFFFu;
+  while (klo < khi) {
+    const uint32_t mid = klo + ((khi - klo) >> 1);
+    long long c = 0;
+    for (int s = threadIdx.x; s < N; s += blockDim.x)
+      if (labels[s] == 1 && f2key((float)stage_sum[s]) <= mid) c++;
+    c = block_sum_ll(c, scratch);
+    if (c >= thresholdIdx + 1) khi = mid; else klo = mid + 1;
+  }
+  const float thr = key2f(klo);
+  long long below = 0, nfalse = 0;
+  const float thr_eps = thr - 0.00001F;
+  for (int s = threadIdx.x; s < N; s += blockDim.x) {
+    const double sum = stage_sum[s];
+    if (labels[s] == 1) {
+      const float ev = (float)sum;
+      if (ev < thr && !(fabsf(ev - thr) < FLT_EPSILON)) below++;
+    } else {
+      if (!(sum < (double)thr_eps)) nfalse++;
+    }
+  }
+  below = block_sum_ll(below, scratch);
+  nfalse = block_sum_ll(nfalse, scratch);
+  if (threadIdx.x == 0) {
+    TreeSummary ts;
+    ts.scaleC = scaleC; ts.sumW = sumW; ts.nz_count = nz; ts.have_subsample = hs;
+    ts.threshold = thr;
+    ts.num_pos = numPos; ts.num_neg = numNeg;
+    ts.hit_rate = ((float)(numPos - (int)below)) / ((float)numPos);
+    ts.false_alarm = ((float)nfalse) / ((float)numNeg);
+    *summary = ts;
+  }
+  (void)s_u64;
+}
+
+__global__ void k_row_quality(const RowBest* rows, const RowBestCat* rows_cat, int nrows, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nrows) { const float q = rows ? rows[i].q : rows_cat[i].q; out[i] = q > 0.f ? q : 0.f; }
+}
+
+// stage sums for arbitrary stages (cc_stage_predict)
+__global__ void k_stage_predict(EvalView e, const DevNode* __restrict__ nodes, const int* __restrict__ tree_first, int ntrees, int s0,
+                                int ns, float threshold, int return_sum, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ns) return;
+  double sum = 0;
+  for (int t = 0; t < ntrees; ++t) sum += d_tree_predict(e, nodes + tree_first[t], s0 + i);
+  if (!return_sum) sum = sum < (double)(threshold - 0.00001F) ? 0.0 : 1.0;
+  out[i] = (float)sum;
+}
+
+// ---- host side ----------------------------------------------------------------------------------------
+static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
+  const int N = ctx->N;
+  ScopedTimer tm(ctx, "split_search", 2);
+  if (ctx->ftype == CC_FEATURE_LBP) {
+    const size_t smem = (size_t)N * 8 + (size_t)((N + 1) & ~1) * 4 + (size_t)CAT_WARPS * 3 * 256 * 8 + CAT_WARPS * 256 * 4;
+    CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED, "split search: numSamples %d needs %zu B of shared memory (limit 227 KB)", N, smem);
+    CC_CUDA(cudaFuncSetAttribute(k_split_search_cat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = std::min((ctx->nrows + CAT_WARPS - 1) / CAT_WARPS, ctx->sm_count * std::max(1, (int)((220 * 1024) / smem)));
+    k_split_search_cat<<<blocks, CAT_THREADS, smem, ctx->stream>>>(ctx->d_fcode, ctx->n_stride, N, ctx->nrows, b->wnode, b->ynode,
+                                                                   b->is_classifier, b->crit, b->boost_type == CC_BOOST_LOGIT, b->rowbest_cat);
+    CC_CUDA(cudaGetLastError());
+    k_argmax_rows<<<1, ONE_CTA, 0, ctx->stream>>>(nullptr, b->rowbest_cat, ctx->nrows, ctx->row0, b->d_best);
+  } else {
+    const bool has_y = b->boost_type == CC_BOOST_LOGIT;
+    const size_t smem = (size_t)N * 8 + (has_y ? (size_t)N * 4 : 0) + 16;
+    CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED, "split search: numSamples %d needs %zu B of shared memory (limit 227 KB)", N, smem);
+    const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
+    const int blocks = std::min((ctx->nrows + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
+#define LAUNCH_SS(CR, HY)                                                                                                   \
+  {                                                                                                                         \
+    CC_CUDA(cudaFuncSetAttribute(k_split_search_ord<CR, HY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+    k_split_search_ord<CR, HY><<<blocks, SS_THREADS, smem, ctx->stream>>>(ctx->d_sidx, ctx->d_sval, ctx->n_stride, N, ctx->nrows, \
+                                                                          b->wnode, b->ynode, b->d_stats + nid, b->rowbest); \
+  }
+    if (b->crit == CRIT_SQERR) { if (has_y) LAUNCH_SS(CRIT_SQERR, true) else LAUNCH_SS(CRIT_SQERR, false) }
+    else if (b->crit == CRIT_GINI) LAUNCH_SS(CRIT_GINI, false)
+    else LAUNCH_SS(CRIT_MISCLASS, false)
+#undef LAUNCH_SS
+    CC_CUDA(cudaGetLastError());
+    k_argmax_rows<<<1, ONE_CTA, 0, ctx->stream>>>(b->rowbest, nullptr, ctx->nrows, ctx->row0, b->d_best);
+  }
+  CC_CUDA(cudaGetLastError());
+  b->row_quality_valid = true;
+  return CC_OK;
+}
+
+int exchange_candidates(cc_ctx* ctx, void* d_best_buf);   // cc_comm.cu: all-gather + argmax when sharded
+static_assert(sizeof(BestSplit) == 64, "candidate record is exchanged as 64 raw bytes (cc_comm.cu)");
+int launch_argmax_candidates(cc_ctx* ctx, const void* cands, int n, void* out) {
+  k_argmax_candidates<<<1, 32, 0, ctx->stream>>>((const BestSplit*)cands, n, (BestSplit*)out);
+  CC_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return CC_OK;
+}
+
+struct HostNode { int left = -1, right = -1, depth = 0, var = -1, pos = -1, n = 0; float c = 0, q = 0; int subset[8] = {0}; double value = 0; };
+
+// CvDTree::try_split_node for one node, depth-first like the reference (the order of nodes does not
+// affect results: nodes own disjoint samples)
+static int grow_node(cc_ctx* ctx, BoostBuffers* b, std::vector<HostNode>& nodes, int nid) {
+  const int N = ctx->N;
+  {
+    ScopedTimer tm(ctx, "boost_small", 1);
+    k_node_prepare<<<1, ONE_CTA, 0, ctx->stream>>>(N, nid, b->is_classifier, b->boost_type, b->node_of, b->weights, b->responses,
+                                                   b->wnode, b->ynode, b->weak_eval, b->d_stats);
+    CC_CUDA(cudaGetLastError());
+  }
+  CC_CUDA(cudaMemcpyAsync(b->h_stats + nid, b->d_stats + nid, sizeof(NodeStats), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const NodeStats st = b->h_stats[nid];
+  nodes[nid].value = st.value;
+  nodes[nid].n = st.n;
+  bool can_split = true;
+  if (st.n <= b->params.min_sample_count || nodes[nid].depth >= b->params.max_depth) can_split = false;
+  if (can_split && b->is_classifier) {
+    const int nz = (st.cls_count[0] != 0) + (st.cls_count[1] != 0);
+    if (nz == 1) can_split = false;
+  } else if (can_split) {
+    if (std::sqrt(st.risk) / st.n < b->params.regression_accuracy) can_split = false;
+  }
+  if (!can_split) return CC_OK;
+  CC_CHECK(launch_split_search(ctx, b, nid));
+  CC_CHECK(exchange_candidates(ctx, b->d_best));
+  CC_CUDA(cudaMemcpyAsync(b->h_best, b->d_best, sizeof(BestSplit), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const BestSplit bs = *b->h_best;
+  if (!bs.valid) return CC_OK;
+  CC_REQUIRE((int)nodes.size() + 2 <= CC_MAX_TREE_NODES, CC_ERR_UNSUPPORTED, "tree grew beyond %d nodes (max_depth too large)", CC_MAX_TREE_NODES);
+  const int lid = (int)nodes.size(), rid = lid + 1;
+  HostNode l, r;
+  l.depth = r.depth = nodes[nid].depth + 1;
+  nodes.push_back(l); nodes.push_back(r);
+  nodes[nid].left = lid; nodes[nid].right = rid;
+  nodes[nid].var = bs.var; nodes[nid].c = bs.c; nodes[nid].q = bs.q; nodes[nid].pos = bs.pos;
+  std::memcpy(nodes[nid].subset, bs.subset, sizeof(bs.subset));
+  {
+    ScopedTimer tm(ctx, "boost_small", 1);
+    k_apply_split<<<(N + 255) / 256, 256, 0, ctx->stream>>>(make_eval_view(ctx), N, nid, lid, rid, b->d_best, b->node_of);
+    CC_CUDA(cudaGetLastError());
+  }
+  CC_CHECK(grow_node(ctx, b, nodes, lid));
+  CC_CHECK(grow_node(ctx, b, nodes, rid));
+  return CC_OK;
+}
+
+}  // namespace cc
+
+using namespace cc;
+
+extern "C" {
+
+int cc_boost_train(cc_ctx* ctx, int num_samples, const cc_boost_params* p, cc_stage* out) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_boost_train: evaluator not initialised");
+  CC_REQUIRE(p && out && out->trees && out->log, CC_ERR_BAD_ARG, "cc_boost_train: null params / output arrays");
+  CC_REQUIRE(p->boost_type >= CC_BOOST_DISCRETE && p->boost_type <= CC_BOOST_GENTLE, CC_ERR_BAD_ARG, "Unknown/unsupported boosting type");
+  CC_REQUIRE(p->min_hit_rate > 0 && p->min_hit_rate < 1 && p->max_false_alarm > 0 && p->max_false_alarm < 1, CC_ERR_BAD_ARG,
+             "cc_boost_train: minHitRate / maxFalseAlarm must be in (0,1) (src/boost.cpp:534-541)");
+  CC_REQUIRE(p->max_depth >= 1 && p->max_depth <= 5, CC_ERR_UNSUPPORTED, "cc_boost_train: max_depth %d outside [1,5]", p->max_depth);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->precalc_valid || ctx->N != num_samples) CC_CHECK(cc_boost_precalc(ctx, num_samples));
+  const int N = ctx->N;
+  CC_CHECK(ensure_boost(ctx, N, (size_t)ctx->nrows));
+  BoostBuffers* b = ctx->boost;
+  // CvBoost::set_params, src/o_cvboost.cpp:67-99
+  b->params = *p;
+  b->params.weak_count = std::max(p->weak_count, 1);
+  double trim = std::min(std::max(p->weight_trim_rate, 0.), 1.);
+  if (trim < FLT_EPSILON) trim = 1.f;
+  b->params.weight_trim_rate = trim;
+  b->boost_type = p->boost_type;
+  b->crit = p->boost_type == CC_BOOST_DISCRETE ? CRIT_MISCLASS : p->boost_type == CC_BOOST_REAL ? CRIT_GINI : CRIT_SQERR;
+  b->is_classifier = (p->boost_type == CC_BOOST_DISCRETE || p->boost_type == CC_BOOST_REAL) ? 1 : 0;
+  b->have_subsample = 0;
+
+  {
+    ScopedTimer tm(ctx, "boost_small", 1);
+    k_boost_init<<<(N + 255) / 256, 256, 0, ctx->stream>>>(N, ctx->d_labels, b->boost_type, b->weights, b->weak_eval, b->stage_sum,
+                                                           b->sum_response, b->responses, b->orig_response, b->mask);
+    CC_CUDA(cudaGetLastError());
+  }
+  out->num_weak = 0; out->num_log = 0; out->threshold = 0.f; out->trained = 0;
+  const EvalView ev = make_eval_view(ctx);
+  for (;;) {
+    {
+      ScopedTimer tm(ctx, "boost_small", 1);
+      k_tree_begin<<<(N + 255) / 256, 256, 0, ctx->stream>>>(N, b->mask, b->node_of);
+      CC_CUDA(cudaGetLastError());
+    }
+    std::vector<HostNode> nodes(1);
+    CC_CHECK(grow_node(ctx, b, nodes, 0));
+    if (nodes[0].left < 0) break;      // tree->train() returned false (root not split), boost.cpp:436-440
+    // upload the tree for the threshold-rule pass
+    DevNode dn[CC_MAX_TREE_NODES];
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      dn[i].left = nodes[i].left; dn[i].right = nodes[i].right; dn[i].var_idx = nodes[i].var; dn[i].c = nodes[i].c;
+      std::memcpy(dn[i].subset, nodes[i].subset, sizeof(dn[i].subset));
+      dn[i].value = nodes[i].value;
+    }
+    CC_CUDA(cudaMemcpyAsync(b->d_tree, dn, sizeof(DevNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    {
+      ScopedTimer tm(ctx, "boost_small", 1);
+      k_tree_finish<<<1, ONE_CTA, 0, ctx->stream>>>(ev, N, b->boost_type, b->have_subsample, b->params.weight_trim_rate, p->min_hit_rate,
+                                                    b->d_tree, ctx->d_labels, b->orig_response, b->weights, b->weak_eval, b->treeval,
+                                                    b->stage_sum, b->sum_response, b->responses, b->mask, b->d_summary);
+      CC_CUDA(cudaGetLastError());
+    }
+    CC_CUDA(cudaMemcpyAsync(b->h_summary, b->d_summary, sizeof(TreeSummary), cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const TreeSummary ts = *b->h_summary;
+    b->have_subsample = ts.have_subsample;
+    // record the tree (DAB: tree->scale(C), src/boost.cpp:316)
+    cc_tree& t = out->trees[out->num_weak];
+    t.num_nodes = (int)nodes.size(); t.pad = 0;
+    for (size_t i = 0; i < nodes.size(); ++i) {
+      cc_node& n = t.nodes[i];
+      n.left = nodes[i].left; n.right = nodes[i].right; n.var_idx = nodes[i].var; n.split_point = nodes[i].pos;
+      n.c = nodes[i].c; n.quality = nodes[i].q; std::memcpy(n.subset, nodes[i].subset, sizeof(n.subset));
+      n.value = nodes[i].value * ts.scaleC; n.depth = nodes[i].depth; n.sample_count = nodes[i].n;
+    }
+    out->num_weak++;
+    if (ts.nz_count == 0) break;       // cvCountNonZero(subsample_mask) == 0, boost.cpp:444
+    // isErrDesired (prints one table row in the reference)
+    out->threshold = ts.threshold;
+    out->log[out->num_log].n = out->num_weak;
+    out->log[out->num_log].hit_rate = ts.hit_rate;
+    out->log[out->num_log].false_alarm = ts.false_alarm;
+    out->num_log++;
+    if (ts.false_alarm <= p->max_false_alarm) break;
+    if (out->num_weak >= b->params.weak_count) break;
+  }
+  out->trained = out->num_weak > 0;
+  return CC_OK;
+}
+
+int cc_boost_get_weights(cc_ctx* ctx, double* weights, uint8_t* mask) {
+  CC_REQUIRE(ctx && ctx->boost && ctx->boost->weights, CC_ERR_STATE, "cc_boost_get_weights: no stage has been trained");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  if (weights) CC_CUDA(cudaMemcpyAsync(weights, ctx->boost->weights, sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+  if (mask) CC_CUDA(cudaMemcpyAsync(mask, ctx->boost->mask, ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
+int cc_boost_get_row_quality(cc_ctx* ctx, int row0, int nrows, float* out) {
+  CC_REQUIRE(ctx && ctx->boost && ctx->boost->row_quality_valid, CC_ERR_STATE, "cc_boost_get_row_quality: no split search has run");
+  CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows, CC_ERR_BAD_ARG, "cc_boost_get_row_quality: rows out of range");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  float* tmp = nullptr;
+  CC_CUDA(cudaMallocAsync(&tmp, sizeof(float) * nrows, ctx->stream));
+  BoostBuffers* b = ctx->boost;
+  k_row_quality<<<(nrows + 255) / 256, 256, 0, ctx->stream>>>(b->rowbest ? b->rowbest + row0 : nullptr, b->rowbest_cat ? b->rowbest_cat + row0 : nullptr, nrows, tmp);
+  CC_CUDA(cudaGetLastError());
+  CC_CUDA(cudaMemcpyAsync(out, tmp, sizeof(float) * nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  CC_CUDA(cudaFreeAsync(tmp, ctx->stream));
+  return CC_OK;
+}
+
+int cc_stage_predict(cc_ctx* ctx, const cc_stage* stage, int s0, int ns, int return_sum, float* out) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_stage_predict: evaluator not initialised");
+  CC_REQUIRE(stage && out && ns > 0 && s0 >= 0 && s0 + ns <= ctx->max_samples, CC_ERR_BAD_ARG, "cc_stage_predict: bad arguments");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  std::vector<DevNode> nodes;
+  std::vector<int> first;
+  for (int t = 0; t < stage->num_weak; ++t) {
+    first.push_back((int)nodes.size());
+    for (int i = 0; i < stage->trees[t].num_nodes; ++i) {
+      const cc_node& n = stage->trees[t].nodes[i];
+      DevNode d;
+      d.left = n.left; d.right = n.right; d.var_idx = n.var_idx; d.c = n.c; std::memcpy(d.subset, n.subset, sizeof(d.subset)); d.value = n.value;
+      nodes.push_back(d);
+    }
+  }
+  DevNode* dn = nullptr; int* df = nullptr; float* dout = nullptr;
+  CC_CUDA(cudaMallocAsync(&dn, sizeof(DevNode) * std::max<size_t>(1, nodes.size()), ctx->stream));
+  CC_CUDA(cudaMallocAsync(&df, sizeof(int) * std::max<size_t>(1, first.size()), ctx->stream));
+  CC_CUDA(cudaMallocAsync(&dout, sizeof(float) * ns, ctx->stream));
+  if (!nodes.empty()) CC_CUDA(cudaMemcpyAsync(dn, nodes.data(), sizeof(DevNode) * nodes.size(), cudaMemcpyHostToDevice, ctx->stream));
+  if (!first.empty()) CC_CUDA(cudaMemcpyAsync(df, first.data(), sizeof(int) * first.size(), cudaMemcpyHostToDevice, ctx->stream));
+  k_stage_predict<<<(ns + 127) / 128, 128, 0, ctx->stream>>>(make_eval_view(ctx), dn, df, stage->num_weak, s0, ns, stage->threshold, return_sum, dout);
+  CC_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  CC_CUDA(cudaMemcpyAsync(out, dout, sizeof(float) * ns, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  CC_CUDA(cudaFreeAsync(dn, ctx->stream)); CC_CUDA(cudaFreeAsync(df, ctx->stream)); CC_CUDA(cudaFreeAsync(dout, ctx->stream));
+  return CC_OK;
+}
+
+}  // extern "C"

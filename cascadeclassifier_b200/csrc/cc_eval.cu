@@ -1,0 +1,573 @@
+// K1: batched integral images (sum / squared / tilted) and HOG integral histograms, plus the
+// evaluator half of the C ABI (init / setImage / operator()).
+//
+// Device layout.  Haar/LBP integrals are stored as tiles of 32 samples, [tile][P][32] int32 with the
+// sample index fastest, so that (a) the precalc kernel pulls one tile into shared memory with a single
+// bulk copy and reads it bank-conflict-free with lane == sample, and (b) any per-sample gather is a
+// coalesced 128-byte line.  HOG planes are [plane][P][ns_pad] float, also sample-fastest.
+#include <algorithm>
+#include <cstring>
+
+#include "cc_internal.h"
+
+namespace cc {
+
+// ------------------------------------------------------------------------------------------------
+// Haar / LBP integral kernel: one CTA per tile of 32 samples, one warp per sample.
+//   sum   : row prefix by warp-shuffle inclusive scan (32 columns per step, carry between chunks),
+//           column accumulation in a per-lane register.
+//   nf    : sums of I and I^2 over the inner (1,1,W-2,H-2) rectangle, warp-reduced, one f64 sqrt
+//           (calcNormFactor, src/features.cpp:13-25).  The f64 sqsum integral of the reference holds
+//           exact integers, so the direct sum is identical.
+//   tilted: T(Y,X) = T(Y-1,X) + D1(Y-1,X-1) + D2(Y-1,X-1) - I(Y-1,X-1) with the two diagonal running
+//           sums D1(y,x)=D1(y-1,x-1)+I(y,x), D2(y,x)=D2(y-1,x+1)+I(y,x) (cv::integral tilted definition).
+// Results are staged in shared memory as [P][33] and written out as full 128-byte lines.
+// ------------------------------------------------------------------------------------------------
+template <int NCHUNK>
+__global__ void __launch_bounds__(1024, 1)
+k_integral_tiles(const uint8_t* __restrict__ imgs, int W, int H, int first, int last /*exclusive*/,
+                 int32_t* __restrict__ sum_tiles, int32_t* __restrict__ tilted_tiles, float* __restrict__ nf_out,
+                 int want_tilted, int want_nf, int staged) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int S = W + 1, P = S * (H + 1);
+  // staged: results go to smem [P][33] first and leave as full 128-byte lines; otherwise (windows whose
+  // staging buffer does not fit) each warp writes its sample column of the tile directly.
+  int32_t* stage = reinterpret_cast<int32_t*>(smem_raw);
+  uint8_t* simg = smem_raw + (staged ? (size_t)P * 33 * sizeof(int32_t) : 0);           // [32][H*W]
+  int32_t* diag = reinterpret_cast<int32_t*>(simg + (((size_t)32 * W * H + 15) & ~(size_t)15));   // [32][2][W+2]
+
+  const int tile = first / TILE + blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sample = tile * TILE + warp;
+  const bool active = sample >= first && sample < last;
+  const int npx = W * H;
+  const int lo = max(first - tile * TILE, 0), hi = min(last - tile * TILE, TILE);
+
+  for (int i = threadIdx.x; i < TILE * npx; i += blockDim.x) {
+    int s = i / npx;
+    int g = tile * TILE + s;
+    simg[i] = (g >= first && g < last) ? imgs[(size_t)g * npx + (i - s * npx)] : 0;
+  }
+  __syncthreads();
+
+  const uint8_t* img = simg + warp * npx;
+  const bool compute = staged || active;
+  // ---------------- sum plane + norm factor ----------------
+  if (compute) {
+    int32_t* out = staged ? stage + warp : sum_tiles + (size_t)tile * P * TILE + warp;
+    const int ostride = staged ? 33 : TILE;
+    int32_t colacc[NCHUNK];
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) colacc[c] = 0;
+    for (int x = lane; x <= W; x += 32) out[x * ostride] = 0;              // first row
+    long long s1 = 0, s2 = 0;
+    for (int y = 0; y < H; ++y) {
+      int carry = 0;
+      if (lane == 0) out[((y + 1) * S) * ostride] = 0;                     // first column
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        const int x = c * 32 + lane;
+        int v = (x < W) ? img[y * W + x] : 0;
+        if (x >= 1 && x <= W - 2 && y >= 1 && y <= H - 2) { s1 += v; s2 += v * v; }
+        int pre = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          int t = __shfl_up_sync(0xffffffffu, pre, d);
+          if (lane >= d) pre += t;
+        }
+        pre += carry;
+        carry = __shfl_sync(0xffffffffu, pre, 31);
+        colacc[c] += pre;
+        if (x < W) out[((y + 1) * S + x + 1) * ostride] = colacc[c];
+      }
+    }
+    if (want_nf) {
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+      }
+      if (lane == 0 && active) {
+        double area = (double)((W - 2) * (H - 2));
+        double vs = (double)s1;
+        nf_out[sample] = (float)sqrt(area * (double)s2 - vs * vs);
+      }
+    }
+  }
+  if (staged) {
+    __syncthreads();
+    int32_t* dst = sum_tiles + (size_t)tile * P * TILE;
+    for (int i = threadIdx.x; i < P * TILE; i += blockDim.x) {
+      int p = i >> 5, s = i & 31;
+      if (s >= lo && s < hi) dst[i] = stage[p * 33 + s];
+    }
+  }
+  if (!want_tilted) return;
+  __syncthreads();
+  // ---------------- tilted plane ----------------
+  if (compute) {
+    int32_t* out = staged ? stage + warp : tilted_tiles + (size_t)tile * P * TILE + warp;
+    const int ostride = staged ? 33 : TILE;
+    int32_t* d1 = diag + warp * 2 * (W + 2);     // index j = x + 1, x in [-1, W-1]
+    int32_t* d2 = d1 + (W + 2);
+    for (int j = lane; j < W + 2; j += 32) { d1[j] = 0; d2[j] = 0; }
+    for (int X = lane; X <= W; X += 32) out[X * ostride] = 0;               // T(0, X) = 0
+    __syncwarp();
+    for (int y = 0; y < H; ++y) {
+      int32_t nd1[NCHUNK + 1], nd2[NCHUNK + 1];
+#pragma unroll
+      for (int c = 0; c <= NCHUNK; ++c) {
+        const int j = c * 32 + lane;           // column X = j, pixel x = j - 1
+        nd1[c] = nd2[c] = 0;
+        if (j <= W) {
+          const int x = j - 1;
+          const int iv = (x >= 0) ? img[y * W + x] : 0;
+          const int a = (x >= 1) ? d1[j - 1] : 0;            // D1(y-1, x-1)
+          const int b = (x + 1 <= W - 1) ? d2[j + 1] : 0;    // D2(y-1, x+1)
+          nd1[c] = a + iv;
+          nd2[c] = b + iv;
+          const int prev = out[(y * S + j) * ostride];
+          out[((y + 1) * S + j) * ostride] = prev + nd1[c] + nd2[c] - iv;
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int c = 0; c <= NCHUNK; ++c) {
+        const int j = c * 32 + lane;
+        if (j <= W) { d1[j] = nd1[c]; d2[j] = nd2[c]; }
+      }
+      __syncwarp();
+    }
+  }
+  if (staged) {
+    __syncthreads();
+    int32_t* dst = tilted_tiles + (size_t)tile * P * TILE;
+    for (int i = threadIdx.x; i < P * TILE; i += blockDim.x) {
+      int p = i >> 5, s = i & 31;
+      if (s >= lo && s < hi) dst[i] = stage[p * 33 + s];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HOG integral histograms (CvHOGEvaluator::integralHistogram, src/HOGfeatures.cpp:163-256)
+// ------------------------------------------------------------------------------------------------
+// cv::fastAtan32f polynomial (OpenCV 4.x core/mathfuncs_core.simd.hpp), radians; explicit _rn
+// intrinsics keep the operation order free of FMA contraction.
+__device__ __forceinline__ float cv_atan2_rad(float y, float x) {
+  const float deg = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * deg, p3 = -0.3258083974640975f * deg, p5 = 0.1555786518463281f * deg,
+              p7 = -0.04432655554792128f * deg;
+  float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+  const float eps = (float)2.2204460492503131e-16;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return __fmul_rn(a, (float)(3.14159265358979323846 / 180.0));
+}
+
+// gradient magnitude + orientation bin per pixel; outputs are [pixel][ns_pad] (sample-fastest)
+__global__ void k_hog_gradient(const uint8_t* __restrict__ imgs, int W, int H, int first, int n, int ns_pad,
+                               float* __restrict__ grad, uint8_t* __restrict__ qangle) {
+  const long long total = (long long)n * W * H;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int s = (int)(t % n);
+    const int px = (int)(t / n);
+    const int y = px / W, x = px - y * W;
+    const uint8_t* img = imgs + (size_t)(first + s) * W * H;
+    const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+    const float dx = (float)((int)img[y * W + xp] - (int)img[y * W + xm]);
+    const float dy = (float)((int)img[yp * W + x] - (int)img[ym * W + x]);
+    const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+    float angle = cv_atan2_rad(dy, dx);
+    angle = __fsub_rn(__fmul_rn(angle, (float)(9 / 3.14159265358979323846)), 0.5f);
+    int b = (int)floorf(angle);
+    if (b < 0) b += 9; else if (b >= 9) b -= 9;
+    grad[(size_t)px * ns_pad + first + s] = mag;
+    qangle[(size_t)px * ns_pad + first + s] = (uint8_t)b;
+  }
+}
+
+// row pass: thread per (plane, y, sample); sequential float prefix along x, same order as the reference
+__global__ void k_hog_rows(const float* __restrict__ grad, const uint8_t* __restrict__ qangle, int W, int H,
+                           int first, int n, int ns_pad, float* __restrict__ planes) {
+  const int S = W + 1, P = S * (H + 1);
+  const long long total = (long long)10 * H * n;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int s = first + (int)(t % n);
+    const int y = (int)((t / n) % H);
+    const int b = (int)(t / ((long long)n * H));
+    float* out = planes + (size_t)b * P * ns_pad;
+    float run = 0.f;
+    out[(size_t)((y + 1) * S) * ns_pad + s] = 0.f;
+    for (int x = 0; x < W; ++x) {
+      const size_t px = (size_t)(y * W + x) * ns_pad + s;
+      if (b == 9 || qangle[px] == b) run = __fadd_rn(run, grad[px]);
+      out[(size_t)((y + 1) * S + x + 1) * ns_pad + s] = run;
+    }
+  }
+}
+
+// column pass: thread per (plane, x, sample); plane[y+1][x+1] = plane[y][x+1] + rowprefix
+__global__ void k_hog_cols(int W, int H, int first, int n, int ns_pad, float* __restrict__ planes) {
+  const int S = W + 1, P = S * (H + 1);
+  const long long total = (long long)10 * S * n;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int s = first + (int)(t % n);
+    const int X = (int)((t / n) % S);
+    const int b = (int)(t / ((long long)n * S));
+    float* out = planes + (size_t)b * P * ns_pad;
+    out[(size_t)X * ns_pad + s] = 0.f;
+    if (X == 0) continue;
+    float prev = 0.f;
+    for (int y = 0; y < H; ++y) {
+      const size_t o = (size_t)((y + 1) * S + X) * ns_pad + s;
+      prev = __fadd_rn(prev, out[o]);
+      out[o] = prev;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// operator()(var, sample) for arbitrary pairs (debug / drop-in queries; not the precalc hot path)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float haar_value(const HaarTaps& t, const int32_t* __restrict__ sum_tiles,
+                                            const int32_t* __restrict__ tilted_tiles, const float* __restrict__ nf,
+                                            int P, int s) {
+  const int32_t* base = (t.tilted() ? tilted_tiles : sum_tiles) + (size_t)(s >> 5) * P * TILE + (s & 31);
+  int acc = 0;
+  const int nt = t.ntaps();
+  for (int k = 0; k < nt; ++k) acc += tap_coef(t.w[k]) * base[(size_t)tap_off(t.w[k]) * TILE];
+  const float n = nf[s];
+  return n == 0.f ? 0.f : __fdiv_rn((float)acc, n);
+}
+
+__device__ __forceinline__ int lbp_code(const LbpTaps& t, const int32_t* __restrict__ sum_tiles, int P, int s) {
+  const int32_t* base = sum_tiles + (size_t)(s >> 5) * P * TILE + (s & 31);
+  int v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = base[(size_t)t.off[k] * TILE];
+  auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
+  const int c = cell(1, 1);
+  return (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
+         (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
+         (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
+}
+
+__device__ __forceinline__ float hog_value(const HogTaps& t, const float* __restrict__ planes, int P, int ns_pad,
+                                           int comp, int s) {
+  const int bin = comp % 9, cell = comp / 9;
+  const float* ph = planes + (size_t)bin * P * ns_pad + s;
+  const float* pn = planes + (size_t)9 * P * ns_pad + s;
+  float res = __fadd_rn(__fsub_rn(__fsub_rn(ph[(size_t)t.off[cell][0] * ns_pad], ph[(size_t)t.off[cell][1] * ns_pad]),
+                                  ph[(size_t)t.off[cell][2] * ns_pad]), ph[(size_t)t.off[cell][3] * ns_pad]);
+  float nrm = __fadd_rn(__fsub_rn(__fsub_rn(pn[(size_t)t.off[0][0] * ns_pad], pn[(size_t)t.off[1][1] * ns_pad]),
+                                  pn[(size_t)t.off[2][2] * ns_pad]), pn[(size_t)t.off[3][3] * ns_pad]);
+  return res > 0.001f ? __fdiv_rn(res, __fadd_rn(nrm, 0.001f)) : 0.f;
+}
+
+struct EvalView {
+  int ftype, P, ns_pad;
+  const int32_t* sum;
+  const int32_t* tilted;
+  const float* nf;
+  const float* hog;
+  const HaarTaps* haar_taps;
+  const LbpTaps* lbp_taps;
+  const HogTaps* hog_taps;
+};
+
+__device__ __forceinline__ float eval_var(const EvalView& e, int var, int s) {
+  if (e.ftype == CC_FEATURE_HAAR) return haar_value(e.haar_taps[var], e.sum, e.tilted, e.nf, e.P, s);
+  if (e.ftype == CC_FEATURE_LBP) return (float)lbp_code(e.lbp_taps[var], e.sum, e.P, s);
+  return hog_value(e.hog_taps[var / 36], e.hog, e.P, e.ns_pad, var % 36, s);
+}
+
+__global__ void k_eval_values(EvalView e, const int* __restrict__ vars, int nv, int s0, int ns, float* __restrict__ out) {
+  const long long total = (long long)nv * ns;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int a = (int)(t / ns), b = (int)(t - (long long)a * ns);
+    out[t] = eval_var(e, vars[a], s0 + b);
+  }
+}
+
+EvalView make_eval_view(const cc_ctx* ctx) {
+  EvalView e;
+  e.ftype = ctx->ftype; e.P = ctx->P; e.ns_pad = ctx->ns_pad;
+  e.sum = ctx->d_sum; e.tilted = ctx->d_tilted; e.nf = ctx->d_nf; e.hog = ctx->d_hog;
+  e.haar_taps = ctx->d_haar_taps; e.lbp_taps = ctx->d_lbp_taps; e.hog_taps = ctx->d_hog_taps;
+  return e;
+}
+
+int eval_free(cc_ctx* ctx) {
+  cudaFree(ctx->d_imgs); cudaFree(ctx->d_labels); cudaFree(ctx->d_sum); cudaFree(ctx->d_tilted);
+  cudaFree(ctx->d_nf); cudaFree(ctx->d_hog); cudaFree(ctx->d_haar_taps); cudaFree(ctx->d_lbp_taps);
+  cudaFree(ctx->d_hog_taps); cudaFree(ctx->d_upright_rows); cudaFree(ctx->d_tilted_rows);
+  ctx->d_imgs = ctx->d_labels = nullptr; ctx->d_sum = ctx->d_tilted = nullptr; ctx->d_nf = nullptr; ctx->d_hog = nullptr;
+  ctx->d_haar_taps = nullptr; ctx->d_lbp_taps = nullptr; ctx->d_hog_taps = nullptr;
+  ctx->d_upright_rows = ctx->d_tilted_rows = nullptr;
+  ctx->ftype = -1;
+  return CC_OK;
+}
+
+// shared by setImage and by mining (windows already in d_imgs)
+int launch_integrals(cc_ctx* ctx, int first, int n) {
+  if (n <= 0) return CC_OK;
+  const int last = first + n;
+  if (ctx->ftype == CC_FEATURE_HOG) {
+    ScopedTimer tm(ctx, "integral", 3);
+    const size_t npx = (size_t)ctx->W * ctx->H;
+    float* grad = nullptr; uint8_t* qa = nullptr;
+    CC_CUDA(cudaMallocAsync(&grad, npx * ctx->ns_pad * sizeof(float), ctx->stream));
+    CC_CUDA(cudaMallocAsync(&qa, npx * ctx->ns_pad, ctx->stream));
+    const int threads = 256;
+    auto blocks = [&](long long total) { return (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->sm_count * 32); };
+    k_hog_gradient<<<blocks((long long)n * npx), threads, 0, ctx->stream>>>(ctx->d_imgs, ctx->W, ctx->H, first, n, ctx->ns_pad, grad, qa);
+    k_hog_rows<<<blocks((long long)10 * ctx->H * n), threads, 0, ctx->stream>>>(grad, qa, ctx->W, ctx->H, first, n, ctx->ns_pad, ctx->d_hog);
+    k_hog_cols<<<blocks((long long)10 * (ctx->W + 1) * n), threads, 0, ctx->stream>>>(ctx->W, ctx->H, first, n, ctx->ns_pad, ctx->d_hog);
+    CC_CUDA(cudaGetLastError());
+    CC_CUDA(cudaFreeAsync(grad, ctx->stream));
+    CC_CUDA(cudaFreeAsync(qa, ctx->stream));
+    return CC_OK;
+  }
+  const int W = ctx->W, H = ctx->H, P = ctx->P;
+  const int tile0 = first / TILE, tile1 = (last - 1) / TILE;
+  const size_t smem_img = (((size_t)32 * W * H + 15) & ~(size_t)15) + (size_t)32 * 2 * (W + 2) * 4;
+  const int staged = (size_t)P * 33 * 4 + smem_img <= 200 * 1024;
+  const size_t smem = smem_img + (staged ? (size_t)P * 33 * 4 : 0);
+  const int want_tilted = ctx->ftype == CC_FEATURE_HAAR && ctx->haar_mode == CC_HAAR_ALL;
+  const int want_nf = ctx->ftype == CC_FEATURE_HAAR;
+  const int nchunk = (W + 31) / 32;
+  CC_REQUIRE(nchunk <= 4 && smem <= 227 * 1024, CC_ERR_UNSUPPORTED,
+             "integral kernel: window %dx%d needs %zu B of shared memory (limit 227 KB, width <= 128)", W, H, smem);
+  ScopedTimer tm(ctx, "integral", 1);
+#define LAUNCH_INT(NC)                                                                                         \
+  {                                                                                                            \
+    CC_CUDA(cudaFuncSetAttribute(k_integral_tiles<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    k_integral_tiles<NC><<<tile1 - tile0 + 1, 1024, smem, ctx->stream>>>(ctx->d_imgs, W, H, first, last, ctx->d_sum, \
+                                                                         ctx->d_tilted, ctx->d_nf, want_tilted, want_nf, staged); \
+  }
+  switch (nchunk) {
+    case 1: LAUNCH_INT(1); break;
+    case 2: LAUNCH_INT(2); break;
+    case 3: LAUNCH_INT(3); break;
+    default: LAUNCH_INT(4); break;
+  }
+#undef LAUNCH_INT
+  CC_CUDA(cudaGetLastError());
+  return CC_OK;
+}
+
+}  // namespace cc
+
+using namespace cc;
+
+extern "C" {
+
+int cc_eval_init(cc_ctx* ctx, int feature_type, int haar_mode, int win_w, int win_h, int max_samples) {
+  CC_REQUIRE(ctx, CC_ERR_BAD_ARG, "cc_eval_init: null ctx");
+  CC_REQUIRE(max_samples > 0, CC_ERR_BAD_ARG, "cc_eval_init: _maxSampleCount > 0 required (src/features.cpp:75)");
+  CC_REQUIRE(feature_type >= CC_FEATURE_HAAR && feature_type <= CC_FEATURE_HOG, CC_ERR_BAD_ARG, "cc_eval_init: unknown feature type %d", feature_type);
+  CC_REQUIRE(win_w >= 4 && win_h >= 4 && win_w <= 255 && win_h <= 255, CC_ERR_BAD_ARG, "cc_eval_init: window %dx%d out of range [4,255]", win_w, win_h);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  cc::mine_free(ctx);
+  cc::boost_free(ctx);
+  cc::eval_free(ctx);
+  ctx->ftype = feature_type; ctx->haar_mode = haar_mode; ctx->W = win_w; ctx->H = win_h;
+  ctx->P = (win_w + 1) * (win_h + 1);
+  ctx->max_samples = max_samples;
+  ctx->ntiles = (max_samples + TILE - 1) / TILE;
+  ctx->ns_pad = ctx->ntiles * TILE;
+  const int S = win_w + 1;
+  const size_t npx = (size_t)win_w * win_h;
+  CC_CUDA(cudaMalloc(&ctx->d_imgs, (size_t)ctx->ns_pad * npx));
+  CC_CUDA(cudaMemsetAsync(ctx->d_imgs, 0, (size_t)ctx->ns_pad * npx, ctx->stream));
+  CC_CUDA(cudaMalloc(&ctx->d_labels, ctx->ns_pad));
+  CC_CUDA(cudaMemsetAsync(ctx->d_labels, 0, ctx->ns_pad, ctx->stream));
+  if (feature_type == CC_FEATURE_HAAR) {
+    CC_REQUIRE(haar_mode >= CC_HAAR_BASIC && haar_mode <= CC_HAAR_ALL, CC_ERR_BAD_ARG, "cc_eval_init: unknown Haar mode %d", haar_mode);
+    ctx->haar = make_haar_catalog(win_w, win_h, haar_mode);
+    ctx->num_features = (int)ctx->haar.size(); ctx->feat_size = 1; ctx->max_cat = 0;
+    std::vector<HaarTaps> taps(ctx->haar.size());
+    ctx->upright_rows.clear(); ctx->tilted_rows.clear();
+    for (size_t i = 0; i < ctx->haar.size(); ++i) {
+      taps[i] = make_haar_taps(ctx->haar[i], S);
+      (ctx->haar[i].tilted ? ctx->tilted_rows : ctx->upright_rows).push_back((int)i);
+    }
+    CC_CUDA(cudaMalloc(&ctx->d_haar_taps, taps.size() * sizeof(HaarTaps)));
+    CC_CUDA(cudaMemcpyAsync(ctx->d_haar_taps, taps.data(), taps.size() * sizeof(HaarTaps), cudaMemcpyHostToDevice, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t tile_bytes = (size_t)ctx->ntiles * ctx->P * TILE * sizeof(int32_t);
+    CC_CUDA(cudaMalloc(&ctx->d_sum, tile_bytes));
+    CC_CUDA(cudaMemsetAsync(ctx->d_sum, 0, tile_bytes, ctx->stream));
+    if (haar_mode == CC_HAAR_ALL) {
+      CC_CUDA(cudaMalloc(&ctx->d_tilted, tile_bytes));
+      CC_CUDA(cudaMemsetAsync(ctx->d_tilted, 0, tile_bytes, ctx->stream));
+    }
+    CC_CUDA(cudaMalloc(&ctx->d_nf, ctx->ns_pad * sizeof(float)));
+    CC_CUDA(cudaMemsetAsync(ctx->d_nf, 0, ctx->ns_pad * sizeof(float), ctx->stream));
+  } else if (feature_type == CC_FEATURE_LBP) {
+    ctx->lbp = make_lbp_catalog(win_w, win_h);
+    ctx->num_features = (int)ctx->lbp.size(); ctx->feat_size = 1; ctx->max_cat = 256;
+    std::vector<LbpTaps> taps(ctx->lbp.size());
+    for (size_t i = 0; i < ctx->lbp.size(); ++i) taps[i] = make_lbp_taps(ctx->lbp[i], S);
+    CC_CUDA(cudaMalloc(&ctx->d_lbp_taps, taps.size() * sizeof(LbpTaps)));
+    CC_CUDA(cudaMemcpyAsync(ctx->d_lbp_taps, taps.data(), taps.size() * sizeof(LbpTaps), cudaMemcpyHostToDevice, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t tile_bytes = (size_t)ctx->ntiles * ctx->P * TILE * sizeof(int32_t);
+    CC_CUDA(cudaMalloc(&ctx->d_sum, tile_bytes));
+    CC_CUDA(cudaMemsetAsync(ctx->d_sum, 0, tile_bytes, ctx->stream));
+  } else {
+    ctx->hog = make_hog_catalog(win_w, win_h);
+    ctx->num_features = (int)ctx->hog.size(); ctx->feat_size = 36; ctx->max_cat = 0;
+    std::vector<HogTaps> taps(ctx->hog.size());
+    for (size_t i = 0; i < ctx->hog.size(); ++i) taps[i] = make_hog_taps(ctx->hog[i], S);
+    CC_CUDA(cudaMalloc(&ctx->d_hog_taps, std::max<size_t>(1, taps.size()) * sizeof(HogTaps)));
+    CC_CUDA(cudaMemcpyAsync(ctx->d_hog_taps, taps.data(), taps.size() * sizeof(HogTaps), cudaMemcpyHostToDevice, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    const size_t bytes = (size_t)10 * ctx->P * ctx->ns_pad * sizeof(float);
+    CC_CUDA(cudaMalloc(&ctx->d_hog, bytes));
+    CC_CUDA(cudaMemsetAsync(ctx->d_hog, 0, bytes, ctx->stream));
+  }
+  ctx->var_count = ctx->num_features * ctx->feat_size;
+  ctx->precalc_valid = false;
+  CC_CHECK(cc_boost_set_shard(ctx, ctx->shard_rank, ctx->shard_world));
+  return CC_OK;
+}
+
+int cc_eval_num_features(cc_ctx* ctx) { return ctx ? ctx->num_features : 0; }
+int cc_eval_feature_size(cc_ctx* ctx) { return ctx ? ctx->feat_size : 0; }
+int cc_eval_max_cat_count(cc_ctx* ctx) { return ctx ? ctx->max_cat : 0; }
+
+int cc_eval_get_feature(cc_ctx* ctx, int fi, int32_t rects[12], float weights[3], int32_t* tilted) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_eval_get_feature: evaluator not initialised");
+  CC_REQUIRE(fi >= 0 && fi < ctx->num_features, CC_ERR_BAD_ARG, "cc_eval_get_feature: index %d out of range", fi);
+  std::memset(rects, 0, sizeof(int32_t) * 12);
+  weights[0] = weights[1] = weights[2] = 0.f;
+  *tilted = 0;
+  if (ctx->ftype == CC_FEATURE_HAAR) {
+    const HaarFeatureH& f = ctx->haar[fi];
+    for (int j = 0; j < 3; ++j) {
+      rects[j * 4] = f.r[j].x; rects[j * 4 + 1] = f.r[j].y; rects[j * 4 + 2] = f.r[j].w; rects[j * 4 + 3] = f.r[j].h;
+      weights[j] = f.wt[j];
+    }
+    *tilted = f.tilted;
+  } else {
+    const RectI& r = ctx->ftype == CC_FEATURE_LBP ? ctx->lbp[fi].r : ctx->hog[fi].cell0;
+    rects[0] = r.x; rects[1] = r.y; rects[2] = r.w; rects[3] = r.h;
+  }
+  return CC_OK;
+}
+
+int cc_eval_set_images_device(cc_ctx* ctx, const uint8_t* dev_imgs, const uint8_t* dev_labels, int first, int n) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_eval_set_images: evaluator not initialised");
+  CC_REQUIRE(first >= 0 && n >= 0 && first + n <= ctx->max_samples, CC_ERR_BAD_ARG,
+             "cc_eval_set_images: slots [%d,%d) exceed maxSampleCount %d (CV_Assert(idx < cls.rows), src/features.cpp:87)", first, first + n, ctx->max_samples);
+  if (n == 0) return CC_OK;
+  CC_CUDA(cudaSetDevice(ctx->device));
+  const size_t npx = (size_t)ctx->W * ctx->H;
+  if (dev_imgs != ctx->d_imgs + (size_t)first * npx)
+    CC_CUDA(cudaMemcpyAsync(ctx->d_imgs + (size_t)first * npx, dev_imgs, (size_t)n * npx, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (dev_labels && dev_labels != ctx->d_labels + first)
+    CC_CUDA(cudaMemcpyAsync(ctx->d_labels + first, dev_labels, n, cudaMemcpyDeviceToDevice, ctx->stream));
+  ctx->precalc_valid = false;
+  return launch_integrals(ctx, first, n);
+}
+
+int cc_eval_set_images(cc_ctx* ctx, const uint8_t* host_imgs, const uint8_t* host_labels, int first, int n) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_eval_set_images: evaluator not initialised");
+  CC_REQUIRE(host_imgs && host_labels, CC_ERR_BAD_ARG, "cc_eval_set_images: null buffer");
+  CC_REQUIRE(first >= 0 && n >= 0 && first + n <= ctx->max_samples, CC_ERR_BAD_ARG,
+             "cc_eval_set_images: slots [%d,%d) exceed maxSampleCount %d (CV_Assert(idx < cls.rows), src/features.cpp:87)", first, first + n, ctx->max_samples);
+  if (n == 0) return CC_OK;
+  CC_CUDA(cudaSetDevice(ctx->device));
+  const size_t npx = (size_t)ctx->W * ctx->H;
+  CC_CUDA(cudaMemcpyAsync(ctx->d_imgs + (size_t)first * npx, host_imgs, (size_t)n * npx, cudaMemcpyHostToDevice, ctx->stream));
+  CC_CUDA(cudaMemcpyAsync(ctx->d_labels + first, host_labels, n, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->precalc_valid = false;
+  return launch_integrals(ctx, first, n);
+}
+
+int cc_eval_values(cc_ctx* ctx, const int32_t* var_idx, int nv, int s0, int ns, float* out) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_eval_values: evaluator not initialised");
+  CC_REQUIRE(var_idx && out && nv > 0 && ns > 0, CC_ERR_BAD_ARG, "cc_eval_values: bad arguments");
+  CC_REQUIRE(s0 >= 0 && s0 + ns <= ctx->max_samples, CC_ERR_BAD_ARG, "cc_eval_values: sample range out of bounds");
+  for (int i = 0; i < nv; ++i)
+    CC_REQUIRE(var_idx[i] >= 0 && var_idx[i] < ctx->var_count, CC_ERR_BAD_ARG, "cc_eval_values: variable %d out of range", var_idx[i]);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  int* dv = nullptr; float* dout = nullptr;
+  CC_CUDA(cudaMallocAsync(&dv, nv * sizeof(int), ctx->stream));
+  CC_CUDA(cudaMallocAsync(&dout, (size_t)nv * ns * sizeof(float), ctx->stream));
+  CC_CUDA(cudaMemcpyAsync(dv, var_idx, nv * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  const long long total = (long long)nv * ns;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, (long long)ctx->sm_count * 16);
+  k_eval_values<<<blocks, 256, 0, ctx->stream>>>(make_eval_view(ctx), dv, nv, s0, ns, dout);
+  CC_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  CC_CUDA(cudaMemcpyAsync(out, dout, (size_t)nv * ns * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  CC_CUDA(cudaFreeAsync(dv, ctx->stream));
+  CC_CUDA(cudaFreeAsync(dout, ctx->stream));
+  return CC_OK;
+}
+
+int cc_eval_value(cc_ctx* ctx, int var_idx, int sample_idx, float* out) {
+  int32_t v = var_idx;
+  return cc_eval_values(ctx, &v, 1, sample_idx, 1, out);
+}
+
+int cc_eval_get_integrals(cc_ctx* ctx, int si, int32_t* sum, int32_t* tilted, float* nf) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_eval_get_integrals: evaluator not initialised");
+  CC_REQUIRE(si >= 0 && si < ctx->max_samples, CC_ERR_BAD_ARG, "cc_eval_get_integrals: sample %d out of range", si);
+  CC_REQUIRE(ctx->ftype != CC_FEATURE_HOG, CC_ERR_BAD_ARG, "cc_eval_get_integrals: HOG evaluator has no integer integrals");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  const size_t tile_off = (size_t)(si / TILE) * ctx->P * TILE + (si % TILE);
+  if (sum)
+    CC_CUDA(cudaMemcpy2DAsync(sum, sizeof(int32_t), ctx->d_sum + tile_off, TILE * sizeof(int32_t), sizeof(int32_t), ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+  if (tilted && ctx->d_tilted)
+    CC_CUDA(cudaMemcpy2DAsync(tilted, sizeof(int32_t), ctx->d_tilted + tile_off, TILE * sizeof(int32_t), sizeof(int32_t), ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+  if (nf && ctx->d_nf) CC_CUDA(cudaMemcpyAsync(nf, ctx->d_nf + si, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
+int cc_eval_get_hog_planes(cc_ctx* ctx, int si, float* planes10) {
+  CC_REQUIRE(ctx && ctx->ftype == CC_FEATURE_HOG, CC_ERR_STATE, "cc_eval_get_hog_planes: not a HOG evaluator");
+  CC_REQUIRE(si >= 0 && si < ctx->max_samples, CC_ERR_BAD_ARG, "cc_eval_get_hog_planes: sample %d out of range", si);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  CC_CUDA(cudaMemcpy2DAsync(planes10, sizeof(float), ctx->d_hog + si, (size_t)ctx->ns_pad * sizeof(float), sizeof(float),
+                            (size_t)10 * ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
+int cc_eval_get_labels(cc_ctx* ctx, int first, int n, float* cls) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_eval_get_labels: evaluator not initialised");
+  CC_REQUIRE(first >= 0 && n >= 0 && first + n <= ctx->max_samples, CC_ERR_BAD_ARG, "cc_eval_get_labels: range out of bounds");
+  std::vector<uint8_t> tmp(n);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  CC_CUDA(cudaMemcpyAsync(tmp.data(), ctx->d_labels + first, n, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n; ++i) cls[i] = (float)tmp[i];
+  return CC_OK;
+}
+
+int cc_eval_get_images(cc_ctx* ctx, int first, int n, uint8_t* imgs) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_eval_get_images: evaluator not initialised");
+  CC_REQUIRE(first >= 0 && n >= 0 && first + n <= ctx->max_samples, CC_ERR_BAD_ARG, "cc_eval_get_images: range out of bounds");
+  const size_t npx = (size_t)ctx->W * ctx->H;
+  CC_CUDA(cudaSetDevice(ctx->device));
+  CC_CUDA(cudaMemcpyAsync(imgs, ctx->d_imgs + (size_t)first * npx, (size_t)n * npx, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
+}  // extern "C"

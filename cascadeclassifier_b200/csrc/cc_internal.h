@@ -1,0 +1,167 @@
+// Internal declarations shared by the translation units of libcascade_cuda.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/cascade_cuda.h"
+
+namespace cc {
+
+void set_error(const char* fmt, ...);
+
+#define CC_CUDA(expr)                                                                     \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      cc::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return CC_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define CC_CHECK(expr)              \
+  do {                              \
+    int _s = (expr);                \
+    if (_s != CC_OK) return _s;     \
+  } while (0)
+
+#define CC_REQUIRE(cond, status, ...)  \
+  do {                                 \
+    if (!(cond)) {                     \
+      cc::set_error(__VA_ARGS__);      \
+      return status;                   \
+    }                                  \
+  } while (0)
+
+constexpr int TILE = 32;   // samples per integral tile (one warp lane per sample)
+
+// ---- host-side catalogs -------------------------------------------------------------------
+struct RectI { int x, y, w, h; };
+struct HaarFeatureH { int tilted; RectI r[3]; float wt[3]; };
+struct LbpFeatureH { RectI r; };
+struct HogFeatureH { RectI cell0; };
+
+// A Haar feature flattened to unique integral-image taps: value = sum coef[k] * I[off[k]].
+// Packed for warp-uniform 128-bit loads: tap k = off (bits 0-15) | coef as int8 (bits 16-23);
+// word 0 additionally carries ntaps in bits 24-27 and the tilted flag in bit 28.
+constexpr int HAAR_MAX_TAPS = 12;
+struct __align__(16) HaarTaps {
+  uint32_t w[HAAR_MAX_TAPS];
+#if defined(__CUDACC__)
+  __host__ __device__
+#endif
+  int ntaps() const { return (int)((w[0] >> 24) & 15u); }
+#if defined(__CUDACC__)
+  __host__ __device__
+#endif
+  int tilted() const { return (int)((w[0] >> 28) & 1u); }
+};
+static_assert(sizeof(HaarTaps) == 48, "HaarTaps layout");
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int tap_off(uint32_t w) { return (int)(w & 0xFFFFu); }
+#if defined(__CUDACC__)
+__host__ __device__
+#endif
+inline int tap_coef(uint32_t w) { return (int)(int8_t)((w >> 16) & 0xFFu); }
+
+struct LbpTaps { uint16_t off[16]; };           // 4x4 corner grid
+struct HogTaps { uint16_t off[4][4]; };         // 4 cells x 4 corners
+
+std::vector<HaarFeatureH> make_haar_catalog(int W, int H, int mode);
+std::vector<LbpFeatureH> make_lbp_catalog(int W, int H);
+std::vector<HogFeatureH> make_hog_catalog(int W, int H);
+HaarTaps make_haar_taps(const HaarFeatureH& f, int stride);
+LbpTaps make_lbp_taps(const LbpFeatureH& f, int stride);
+HogTaps make_hog_taps(const HogFeatureH& f, int stride);
+
+// ---- timing -------------------------------------------------------------------------------
+struct TimerSlot { double ms = 0; int64_t launches = 0; };
+
+// flat device-side tree used by predict kernels
+struct DevNode {
+  int left, right, var_idx;
+  float c;
+  int subset[8];
+  double value;
+};
+
+struct DevStageRef { int first_tree, num_trees; float threshold; };
+
+struct BoostBuffers;
+struct MineState;
+
+}  // namespace cc
+
+struct cc_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::map<std::string, cc::TimerSlot> timers;
+  int64_t launches = 0;
+  bool timing_enabled = true;
+
+  // ---- evaluator ----
+  int ftype = -1, haar_mode = 0, W = 0, H = 0, P = 0, max_samples = 0, ntiles = 0;
+  int num_features = 0, feat_size = 1, max_cat = 0, var_count = 0;
+  std::vector<cc::HaarFeatureH> haar;
+  std::vector<cc::LbpFeatureH> lbp;
+  std::vector<cc::HogFeatureH> hog;
+  uint8_t* d_imgs = nullptr;       // [max_samples][H][W]
+  uint8_t* d_labels = nullptr;     // [max_samples]
+  int32_t* d_sum = nullptr;        // tiles [ntiles][P][32]
+  int32_t* d_tilted = nullptr;     // tiles (Haar ALL only)
+  float* d_nf = nullptr;           // [ntiles*32]
+  float* d_hog = nullptr;          // [10][P][ns_pad]  sample-fastest
+  int ns_pad = 0;                  // ntiles*32
+  cc::HaarTaps* d_haar_taps = nullptr;   // [num_features]
+  cc::LbpTaps* d_lbp_taps = nullptr;
+  cc::HogTaps* d_hog_taps = nullptr;
+  std::vector<int> upright_rows, tilted_rows;   // global feature indices by plane (Haar)
+  int* d_upright_rows = nullptr;
+  int* d_tilted_rows = nullptr;
+
+  // ---- train data ----
+  int shard_rank = 0, shard_world = 1;
+  int row0 = 0, nrows = 0;         // local variable slice
+  int N = 0, n_stride = 0;         // samples of the current stage, padded row stride
+  bool precalc_valid = false;
+  float* d_fval = nullptr;         // [nrows][n_stride] (Haar / HOG)
+  uint8_t* d_fcode = nullptr;      // [nrows][n_stride] (LBP)
+  uint16_t* d_sidx = nullptr;      // [nrows][n_stride]
+  float* d_sval = nullptr;         // [nrows][n_stride] values in sorted order
+  size_t cap_rows = 0, cap_stride = 0;
+
+  // ---- boosting state (device) ----
+  cc::BoostBuffers* boost = nullptr;
+
+  // ---- mining ----
+  cc::MineState* mine = nullptr;
+
+  // ---- NCCL ----
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
+};
+
+namespace cc {
+// timing helpers: bracket a kernel family with events on ctx->stream
+struct ScopedTimer {
+  cc_ctx* ctx;
+  const char* name;
+  int n;
+  ScopedTimer(cc_ctx* c, const char* nm, int launches);
+  ~ScopedTimer();
+};
+
+int eval_free(cc_ctx* ctx);
+int boost_free(cc_ctx* ctx);
+int mine_free(cc_ctx* ctx);
+}  // namespace cc

@@ -1,0 +1,483 @@
+// K2 (feature precalc into the fval matrix) and K3 (per-feature segmented radix sort).
+// Replaces CvCascadeBoostTrainData::setData / precalculate and the three Feature*Precalc bodies
+// (src/o_cvcascadeboosttraindata.cpp:214-368, :490-596); every row is cached in HBM, so the
+// reference's -precalcValBufSize / -precalcIdxBufSize become advisory.
+#include <algorithm>
+
+#include "cc_internal.h"
+
+namespace cc {
+
+struct EvalView;
+EvalView make_eval_view(const cc_ctx* ctx);
+
+// ---- mbarrier / bulk-copy (TMA 1-D) helpers -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 / Haar.  CTA = TILES_PER_CTA tiles of 32 samples resident in shared memory as [tile][P][32]
+// (one cp.async.bulk each), lane == sample, so every tap is a conflict-free 128-byte LDS.  A warp
+// walks the features of its chunk; the tap words of a feature are warp-uniform 128-bit loads, reused
+// for all tiles.  value = (float)(sum coef*I) / nf with IEEE division (haarfeatures.h:108-112).
+// Stores are one full 128-byte line per (feature, tile).
+// ------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ int haar_acc(const uint32_t (&w)[HAAR_MAX_TAPS], const int32_t* __restrict__ tile_lane) {
+  int acc = 0;
+#pragma unroll
+  for (int k = 0; k < NT; ++k) acc += tap_coef(w[k]) * tile_lane[tap_off(w[k]) * TILE];
+  return acc;
+}
+
+constexpr int PRECALC_THREADS = 256;
+
+template <int TILES_PER_CTA>
+__global__ void __launch_bounds__(PRECALC_THREADS, 1)
+k_precalc_haar(const int32_t* __restrict__ plane_tiles, const float* __restrict__ nf, const HaarTaps* __restrict__ taps,
+               const int* __restrict__ rows, int nrows_launch, int rows_per_chunk, int row_base, float* __restrict__ fval,
+               int n_stride, int P, int ntiles_used) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  int32_t* stile = reinterpret_cast<int32_t*>(smem_raw);                      // [TILES][P][32]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TILES_PER_CTA * P * TILE * sizeof(int32_t));
+
+  const int tile0 = blockIdx.x * TILES_PER_CTA;
+  const int ntl = min(TILES_PER_CTA, ntiles_used - tile0);
+  const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, tile_bytes * ntl);
+    for (int k = 0; k < ntl; ++k) bulk_g2s(stile + (size_t)k * P * TILE, plane_tiles + (size_t)(tile0 + k) * P * TILE, tile_bytes, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PRECALC_THREADS / 32;
+  float nfv[TILES_PER_CTA];
+#pragma unroll
+  for (int k = 0; k < TILES_PER_CTA; ++k) nfv[k] = (k < ntl) ? nf[(tile0 + k) * TILE + lane] : 0.f;
+
+  const int r_begin = blockIdx.y * rows_per_chunk;
+  const int r_end = min(r_begin + rows_per_chunk, nrows_launch);
+  for (int r = r_begin + warp; r < r_end; r += nwarps) {
+    const int f = rows[r];
+    const uint4* tp = reinterpret_cast<const uint4*>(taps + f);
+    const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+    const uint32_t w[HAAR_MAX_TAPS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+    const int nt = (int)((a.x >> 24) & 15u);
+    float* out = fval + (size_t)(f - row_base) * n_stride + tile0 * TILE + lane;
+#pragma unroll
+    for (int k = 0; k < TILES_PER_CTA; ++k) {
+      if (k < ntl) {
+        const int32_t* tl = stile + (size_t)k * P * TILE + lane;
+        int acc;
+        switch (nt) {
+          case 6: acc = haar_acc<6>(w, tl); break;
+          case 8: acc = haar_acc<8>(w, tl); break;
+          case 9: acc = haar_acc<9>(w, tl); break;
+          default: {
+            acc = 0;
+#pragma unroll
+            for (int q = 0; q < HAAR_MAX_TAPS; ++q)
+              if (q < nt) acc += tap_coef(w[q]) * tl[tap_off(w[q]) * TILE];
+          }
+        }
+        const float v = nfv[k] == 0.f ? 0.f : __fdiv_rn((float)acc, nfv[k]);
+        out[k * TILE] = v;
+      }
+    }
+  }
+}
+
+// K2 / LBP: same tiling; 16 corner taps -> 9 cell sums -> 8-bit code (lbpfeatures.h:70-83).
+template <int TILES_PER_CTA>
+__global__ void __launch_bounds__(PRECALC_THREADS, 1)
+k_precalc_lbp(const int32_t* __restrict__ sum_tiles, const LbpTaps* __restrict__ taps, int row_first, int nrows_launch,
+              int rows_per_chunk, uint8_t* __restrict__ fcode, int n_stride, int P, int ntiles_used) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  int32_t* stile = reinterpret_cast<int32_t*>(smem_raw);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TILES_PER_CTA * P * TILE * sizeof(int32_t));
+  const int tile0 = blockIdx.x * TILES_PER_CTA;
+  const int ntl = min(TILES_PER_CTA, ntiles_used - tile0);
+  const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, tile_bytes * ntl);
+    for (int k = 0; k < ntl; ++k) bulk_g2s(stile + (size_t)k * P * TILE, sum_tiles + (size_t)(tile0 + k) * P * TILE, tile_bytes, bar);
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PRECALC_THREADS / 32;
+  const int r_begin = blockIdx.y * rows_per_chunk;
+  const int r_end = min(r_begin + rows_per_chunk, nrows_launch);
+  for (int r = r_begin + warp; r < r_end; r += nwarps) {
+    const int f = row_first + r;
+    const uint4* tp = reinterpret_cast<const uint4*>(taps + f);
+    const uint4 a = __ldg(tp), b = __ldg(tp + 1);
+    const uint32_t pw[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint8_t* out = fcode + (size_t)r * n_stride + tile0 * TILE + lane;
+#pragma unroll
+    for (int k = 0; k < TILES_PER_CTA; ++k) {
+      if (k < ntl) {
+        const int32_t* tl = stile + (size_t)k * P * TILE + lane;
+        int v[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[2 * q] = tl[(pw[q] & 0xFFFFu) * TILE];
+          v[2 * q + 1] = tl[(pw[q] >> 16) * TILE];
+        }
+        auto cell = [&](int gx, int gy) { const int i = gy * 4 + gx; return v[i] - v[i + 1] - v[i + 4] + v[i + 5]; };
+        const int c = cell(1, 1);
+        const int code = (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
+                         (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
+                         (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
+        out[k * TILE] = (uint8_t)code;
+      }
+    }
+  }
+}
+
+// K2 / HOG: planes are [plane][P][ns_pad] (sample-fastest), so lane == sample gives coalesced 128-byte
+// loads straight from L2/HBM; one warp handles one block feature (36 variables) of one sample tile.
+__global__ void __launch_bounds__(256)
+k_precalc_hog(const float* __restrict__ planes, const HogTaps* __restrict__ taps, int var_first, int nvars, float* __restrict__ fval,
+              int n_stride, int P, int ns_pad, int ntiles_used) {
+  const int lane = threadIdx.x & 31;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps_total = (gridDim.x * blockDim.x) >> 5;
+  const int f_first = var_first / 36, f_last = (var_first + nvars - 1) / 36;
+  const int nblocks = f_last - f_first + 1;
+  const long long work = (long long)nblocks * ntiles_used;
+  for (long long wi = warp_global; wi < work; wi += nwarps_total) {
+    const int fb = f_first + (int)(wi / ntiles_used);
+    const int s = (int)(wi % ntiles_used) * TILE + lane;
+    const HogTaps t = taps[fb];
+    const float* pn = planes + (size_t)9 * P * ns_pad + s;
+    const float nrm = __fadd_rn(__fsub_rn(__fsub_rn(pn[(size_t)t.off[0][0] * ns_pad], pn[(size_t)t.off[1][1] * ns_pad]),
+                                          pn[(size_t)t.off[2][2] * ns_pad]), pn[(size_t)t.off[3][3] * ns_pad]);
+    const float den = __fadd_rn(nrm, 0.001f);
+    for (int comp = 0; comp < 36; ++comp) {
+      const int var = fb * 36 + comp;
+      if (var < var_first || var >= var_first + nvars) continue;
+      const int bin = comp % 9, cell = comp / 9;
+      const float* ph = planes + (size_t)bin * P * ns_pad + s;
+      const float res = __fadd_rn(__fsub_rn(__fsub_rn(ph[(size_t)t.off[cell][0] * ns_pad], ph[(size_t)t.off[cell][1] * ns_pad]),
+                                            ph[(size_t)t.off[cell][2] * ns_pad]), ph[(size_t)t.off[cell][3] * ns_pad]);
+      fval[(size_t)(var - var_first) * n_stride + s] = res > 0.001f ? __fdiv_rn(res, den) : 0.f;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: per-feature segmented sort.  One CTA sorts one row of N (value, sample index) pairs held in
+// shared memory: stable LSD radix sort, 4 passes of 8 bits over the order-preserving float->uint
+// transform.  Stability is kept by giving every warp a contiguous segment and ranking inside a warp
+// with __match_any_sync; ties therefore come out in ascending sample index, which is the canonical
+// order the oracle's stable mode produces (std::sort + LessThanIdx in the reference leaves tie order
+// unspecified, o_utils.h:18-23, test_o_utils.cpp:111-128).
+// ------------------------------------------------------------------------------------------------
+constexpr int SORT_THREADS = 512;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+
+__device__ __forceinline__ uint32_t float_to_key(float v) {
+  uint32_t u = __float_as_uint(v + 0.0f);          // -0 -> +0
+  return u ^ ((u >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+
+__global__ void __launch_bounds__(SORT_THREADS, 1)
+k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint16_t* __restrict__ sidx, float* __restrict__ sval) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* keyA = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* keyB = keyA + N;
+  uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + N);
+  uint16_t* idxB = idxA + ((N + 1) & ~1);
+  uint32_t* hist = reinterpret_cast<uint32_t*>(idxB + ((N + 1) & ~1));     // [SORT_WARPS][256]
+  uint32_t* dig_total = hist + SORT_WARPS * 256;                            // [256]
+  __shared__ uint32_t warp_sums[8];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = ((N + SORT_WARPS - 1) / SORT_WARPS + 31) & ~31;           // per-warp contiguous segment (multiple of 32)
+  const int seg_begin = min(warp * seg, N), seg_end = min(seg_begin + seg, N);
+  const uint32_t lt_mask = (1u << lane) - 1u;
+
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const float* src = fval + (size_t)row * n_stride;
+    for (int i = threadIdx.x; i < N; i += SORT_THREADS) { keyA[i] = float_to_key(src[i]); idxA[i] = (uint16_t)i; }
+    uint32_t* kin = keyA; uint32_t* kout = keyB; uint16_t* iin = idxA; uint16_t* iout = idxB;
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = pass * 8;
+      for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) hist[i] = 0;
+      __syncthreads();
+      uint32_t* wh = hist + warp * 256;
+      for (int base = seg_begin; base < seg_end; base += 32) {
+        const int i = base + lane;
+        const bool ok = i < seg_end;
+        const uint32_t d = ok ? ((kin[i] >> shift) & 255u) : (256u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        if (ok && (peers & lt_mask) == 0) wh[d] += __popc(peers);
+        __syncwarp();
+      }
+      __syncthreads();
+      // exclusive offsets: digit-major, warp-minor
+      int same_digit = 0;
+      if (threadIdx.x < 256) {
+        uint32_t run = 0;
+        for (int w = 0; w < SORT_WARPS; ++w) { uint32_t t = hist[w * 256 + threadIdx.x]; hist[w * 256 + threadIdx.x] = run; run += t; }
+        same_digit = run == (uint32_t)N;             // every key has the same digit: the pass is the identity
+        uint32_t incl = run;
+#pragma unroll
+        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, dlt); if (lane >= dlt) incl += t; }
+        if (lane == 31) warp_sums[warp] = incl;
+        dig_total[threadIdx.x] = incl - run;         // exclusive within the warp of 32 digits
+      }
+      if (__syncthreads_or(same_digit)) continue;
+      if (threadIdx.x < 256) {
+        uint32_t add = 0;
+        for (int w = 0; w < warp; ++w) add += warp_sums[w];
+        dig_total[threadIdx.x] += add;
+      }
+      __syncthreads();
+      for (int base = seg_begin; base < seg_end; base += 32) {
+        const int i = base + lane;
+        const bool ok = i < seg_end;
+        const uint32_t k = ok ? kin[i] : 0u;
+        const uint32_t d = ok ? ((k >> shift) & 255u) : (256u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, d);
+        uint32_t pos = 0;
+        if (ok) pos = dig_total[d] + wh[d] + __popc(peers & lt_mask);
+        __syncwarp();
+        if (ok && (peers & lt_mask) == 0) wh[d] += __popc(peers);
+        __syncwarp();
+        if (ok) { kout[pos] = k; iout[pos] = iin[i]; }
+      }
+      __syncthreads();
+      { uint32_t* t = kin; kin = kout; kout = t; uint16_t* u = iin; iin = iout; iout = u; }
+    }
+    uint16_t* drow = sidx + (size_t)row * n_stride;
+    float* vrow = sval + (size_t)row * n_stride;
+    for (int i = threadIdx.x; i < N; i += SORT_THREADS) { drow[i] = iin[i]; vrow[i] = key_to_float(kin[i]); }
+    __syncthreads();
+  }
+}
+
+// widen LBP codes / copy rows for the parity getters
+__global__ void k_codes_to_float(const uint8_t* __restrict__ codes, int n_stride, int N, int nrows, float* __restrict__ out) {
+  const long long total = (long long)nrows * N;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(t / N), s = (int)(t - (long long)r * N);
+    out[t] = (float)codes[(size_t)r * n_stride + s];
+  }
+}
+
+int traindata_free(cc_ctx* ctx) {
+  cudaFree(ctx->d_fval); cudaFree(ctx->d_fcode); cudaFree(ctx->d_sidx); cudaFree(ctx->d_sval);
+  ctx->d_fval = nullptr; ctx->d_fcode = nullptr; ctx->d_sidx = nullptr; ctx->d_sval = nullptr;
+  ctx->cap_rows = ctx->cap_stride = 0;
+  ctx->precalc_valid = false;
+  return CC_OK;
+}
+
+static int ensure_traindata(cc_ctx* ctx, int nrows, int n_stride) {
+  if ((size_t)nrows <= ctx->cap_rows && (size_t)n_stride <= ctx->cap_stride) return CC_OK;
+  traindata_free(ctx);
+  const size_t cells = (size_t)nrows * n_stride;
+  if (ctx->ftype == CC_FEATURE_LBP) {
+    CC_CUDA(cudaMalloc(&ctx->d_fcode, cells));
+  } else {
+    CC_CUDA(cudaMalloc(&ctx->d_fval, cells * sizeof(float)));
+    CC_CUDA(cudaMalloc(&ctx->d_sidx, cells * sizeof(uint16_t)));
+    CC_CUDA(cudaMalloc(&ctx->d_sval, cells * sizeof(float)));
+  }
+  ctx->cap_rows = nrows; ctx->cap_stride = n_stride;
+  return CC_OK;
+}
+
+}  // namespace cc
+
+using namespace cc;
+
+extern "C" {
+
+int cc_boost_set_shard(cc_ctx* ctx, int rank, int world) {
+  CC_REQUIRE(ctx, CC_ERR_BAD_ARG, "cc_boost_set_shard: null ctx");
+  CC_REQUIRE(world >= 1 && rank >= 0 && rank < world, CC_ERR_BAD_ARG, "cc_boost_set_shard: rank %d of %d", rank, world);
+  ctx->shard_rank = rank; ctx->shard_world = world;
+  if (ctx->ftype >= 0) {
+    const long long F = ctx->var_count;
+    ctx->row0 = (int)(F * rank / world);
+    ctx->nrows = (int)(F * (rank + 1) / world) - ctx->row0;
+    ctx->precalc_valid = false;
+    // per-plane row lists of this shard (Haar): upright rows read `sum`, tilted rows read `tilted`
+    if (ctx->ftype == CC_FEATURE_HAAR) {
+      std::vector<int> up, tl;
+      for (int f = ctx->row0; f < ctx->row0 + ctx->nrows; ++f) (ctx->haar[f].tilted ? tl : up).push_back(f);
+      ctx->upright_rows = up; ctx->tilted_rows = tl;
+      cudaFree(ctx->d_upright_rows); cudaFree(ctx->d_tilted_rows);
+      ctx->d_upright_rows = ctx->d_tilted_rows = nullptr;
+      CC_CUDA(cudaSetDevice(ctx->device));
+      if (!up.empty()) {
+        CC_CUDA(cudaMalloc(&ctx->d_upright_rows, up.size() * sizeof(int)));
+        CC_CUDA(cudaMemcpy(ctx->d_upright_rows, up.data(), up.size() * sizeof(int), cudaMemcpyHostToDevice));
+      }
+      if (!tl.empty()) {
+        CC_CUDA(cudaMalloc(&ctx->d_tilted_rows, tl.size() * sizeof(int)));
+        CC_CUDA(cudaMemcpy(ctx->d_tilted_rows, tl.data(), tl.size() * sizeof(int), cudaMemcpyHostToDevice));
+      }
+    }
+  }
+  return CC_OK;
+}
+
+int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_boost_precalc: evaluator not initialised");
+  CC_REQUIRE(num_samples > 0 && num_samples <= ctx->max_samples, CC_ERR_BAD_ARG, "cc_boost_precalc: numSamples %d not in (0, %d]", num_samples, ctx->max_samples);
+  CC_REQUIRE(num_samples < 65536, CC_ERR_UNSUPPORTED, "cc_boost_precalc: numSamples %d >= 65536 needs 32-bit sorted indices (is_buf_16u == false), not implemented", num_samples);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  const int N = num_samples;
+  const int n_stride = (N + 255) & ~255;   // rows padded to the split-search tile (256 elements)
+  CC_CHECK(ensure_traindata(ctx, ctx->nrows, n_stride));
+  ctx->N = N; ctx->n_stride = n_stride;
+  const int ntiles_used = (N + TILE - 1) / TILE;
+  const int P = ctx->P;
+
+  if (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) {
+    const size_t tile_bytes = (size_t)P * TILE * sizeof(int32_t);
+    const int tiles_per_cta = (2 * tile_bytes + 64 <= 200 * 1024) ? 2 : 1;
+    CC_REQUIRE(tile_bytes + 64 <= 227 * 1024, CC_ERR_UNSUPPORTED,
+               "precalc: one 32-sample integral tile of a %dx%d window (%zu B) exceeds shared memory", ctx->W, ctx->H, tile_bytes);
+    const size_t smem = tiles_per_cta * tile_bytes + 64;
+    const int gx = (ntiles_used + tiles_per_cta - 1) / tiles_per_cta;
+    auto chunks_for = [&](int nrows_launch) {
+      // enough CTAs for >= ~8 waves, but >= 512 rows per CTA so the tile load is amortised
+      int want = std::max(1, (ctx->sm_count * 8 + gx - 1) / gx);
+      int max_chunks = std::max(1, nrows_launch / 512);
+      int chunks = std::min(want, max_chunks);
+      return std::max(1, chunks);
+    };
+    if (ctx->ftype == CC_FEATURE_HAAR) {
+      struct Launch { const int32_t* plane; const int* rows; int n; };
+      Launch ls[2] = {{ctx->d_sum, ctx->d_upright_rows, (int)ctx->upright_rows.size()},
+                      {ctx->d_tilted, ctx->d_tilted_rows, (int)ctx->tilted_rows.size()}};
+      for (const Launch& l : ls) {
+        if (l.n == 0) continue;
+        ScopedTimer tm(ctx, "precalc", 1);
+        const int chunks = chunks_for(l.n);
+        const int rpc = (l.n + chunks - 1) / chunks;
+        dim3 grid(gx, (l.n + rpc - 1) / rpc);
+        if (tiles_per_cta == 2) {
+          CC_CUDA(cudaFuncSetAttribute(k_precalc_haar<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_precalc_haar<2><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, ctx->d_haar_taps, l.rows, l.n, rpc, ctx->row0,
+                                                                          ctx->d_fval, n_stride, P, ntiles_used);
+        } else {
+          CC_CUDA(cudaFuncSetAttribute(k_precalc_haar<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_precalc_haar<1><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, ctx->d_haar_taps, l.rows, l.n, rpc, ctx->row0,
+                                                                          ctx->d_fval, n_stride, P, ntiles_used);
+        }
+        CC_CUDA(cudaGetLastError());
+      }
+    } else {
+      ScopedTimer tm(ctx, "precalc", 1);
+      const int chunks = chunks_for(ctx->nrows);
+      const int rpc = (ctx->nrows + chunks - 1) / chunks;
+      dim3 grid(gx, (ctx->nrows + rpc - 1) / rpc);
+      if (tiles_per_cta == 2) {
+        CC_CUDA(cudaFuncSetAttribute(k_precalc_lbp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_precalc_lbp<2><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
+                                                                       n_stride, P, ntiles_used);
+      } else {
+        CC_CUDA(cudaFuncSetAttribute(k_precalc_lbp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_precalc_lbp<1><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
+                                                                       n_stride, P, ntiles_used);
+      }
+      CC_CUDA(cudaGetLastError());
+    }
+  } else {
+    ScopedTimer tm(ctx, "precalc", 1);
+    const int blocks = ctx->sm_count * 8;
+    k_precalc_hog<<<blocks, 256, 0, ctx->stream>>>(ctx->d_hog, ctx->d_hog_taps, ctx->row0, ctx->nrows, ctx->d_fval, n_stride, P, ctx->ns_pad,
+                                                   ntiles_used);
+    CC_CUDA(cudaGetLastError());
+  }
+
+  if (ctx->ftype != CC_FEATURE_LBP) {   // categorical variables are not sorted (numPrecalcIdx = 0, :267-273)
+    const size_t smem = (size_t)N * 8 + (size_t)((N + 1) & ~1) * 4 + (SORT_WARPS * 256 + 256) * 4 + 16;
+    CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED,
+               "sort: numSamples %d needs %zu B of shared memory per row (limit 227 KB, about 18900 samples)", N, smem);
+    ScopedTimer tm(ctx, "sort", 1);
+    CC_CUDA(cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int blocks = std::min(ctx->nrows, ctx->sm_count * std::max(1, (int)((227 * 1024) / (smem + 1024))));
+    k_sort_rows<<<blocks, SORT_THREADS, smem, ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx, ctx->d_sval);
+    CC_CUDA(cudaGetLastError());
+  }
+  ctx->precalc_valid = true;
+  return CC_OK;
+}
+
+int cc_boost_get_fval(cc_ctx* ctx, int row0, int nrows, float* out) {
+  CC_REQUIRE(ctx && ctx->precalc_valid, CC_ERR_STATE, "cc_boost_get_fval: precalc has not run");
+  CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows, CC_ERR_BAD_ARG, "cc_boost_get_fval: rows [%d,%d) outside local slice of %d rows", row0, row0 + nrows, ctx->nrows);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->ftype == CC_FEATURE_LBP) {
+    float* tmp = nullptr;
+    CC_CUDA(cudaMallocAsync(&tmp, (size_t)nrows * ctx->N * sizeof(float), ctx->stream));
+    k_codes_to_float<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(ctx->d_fcode + (size_t)row0 * ctx->n_stride, ctx->n_stride, ctx->N, nrows, tmp);
+    CC_CUDA(cudaGetLastError());
+    CC_CUDA(cudaMemcpyAsync(out, tmp, (size_t)nrows * ctx->N * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    CC_CUDA(cudaFreeAsync(tmp, ctx->stream));
+    return CC_OK;
+  }
+  CC_CUDA(cudaMemcpy2DAsync(out, (size_t)ctx->N * sizeof(float), ctx->d_fval + (size_t)row0 * ctx->n_stride, (size_t)ctx->n_stride * sizeof(float),
+                            (size_t)ctx->N * sizeof(float), nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
+int cc_boost_get_sorted_idx(cc_ctx* ctx, int row0, int nrows, uint16_t* out) {
+  CC_REQUIRE(ctx && ctx->precalc_valid && ctx->d_sidx, CC_ERR_STATE, "cc_boost_get_sorted_idx: no sorted-index buffer (precalc not run, or categorical features)");
+  CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows, CC_ERR_BAD_ARG, "cc_boost_get_sorted_idx: rows out of range");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  CC_CUDA(cudaMemcpy2DAsync(out, (size_t)ctx->N * sizeof(uint16_t), ctx->d_sidx + (size_t)row0 * ctx->n_stride, (size_t)ctx->n_stride * sizeof(uint16_t),
+                            (size_t)ctx->N * sizeof(uint16_t), nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
+int cc_boost_get_sorted_val(cc_ctx* ctx, int row0, int nrows, float* out) {
+  CC_REQUIRE(ctx && ctx->precalc_valid && ctx->d_sval, CC_ERR_STATE, "cc_boost_get_sorted_val: no sorted-value buffer");
+  CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows, CC_ERR_BAD_ARG, "cc_boost_get_sorted_val: rows out of range");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  CC_CUDA(cudaMemcpy2DAsync(out, (size_t)ctx->N * sizeof(float), ctx->d_sval + (size_t)row0 * ctx->n_stride, (size_t)ctx->n_stride * sizeof(float),
+                            (size_t)ctx->N * sizeof(float), nrows, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,36 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def make_samples(n_pos, n_neg, W=24, H=24, seed=7):
+    """Seeded training set: distorted glyph positives + windows cut from generated backgrounds."""
+    from cascadeclassifier_b200 import synth
+    pos = synth.make_positives(n_pos, W, H, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    bgs = synth.make_backgrounds(4, 320, 240, seed0=seed * 100)
+    neg = np.empty((n_neg, H, W), np.uint8)
+    for i in range(n_neg):
+        b = bgs[i % len(bgs)]
+        y = int(rng.integers(0, b.shape[0] - H))
+        x = int(rng.integers(0, b.shape[1] - W))
+        neg[i] = b[y:y + H, x:x + W]
+    imgs = np.concatenate([pos, neg])
+    labels = np.concatenate([np.ones(n_pos, np.uint8), np.zeros(n_neg, np.uint8)])
+    return imgs, labels
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    import cascadeclassifier_b200 as ccb
+    return ccb.Context(0)

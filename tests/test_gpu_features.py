@@ -1,0 +1,149 @@
+"""GPU parity: K1 integral images, operator(), K2 precalc, K3 sort — through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+import orc
+from conftest import make_samples
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu_eval(ftype, mode, W, H, n, ctx):
+    import cascadeclassifier_b200 as ccb
+    ev = ccb.CvFeatureEvaluator.create(ftype, ctx)
+    params = ccb.CvFeatureParams.create(ftype)
+    if ftype == ccb.CvFeatureParams.HAAR:
+        params.mode = mode
+    ev.init(params, n, (W, H))
+    return ev
+
+
+@pytest.mark.parametrize("mode", [orc.BASIC, orc.ALL])
+def test_haar_integrals_bit_exact(gpu_ctx, mode):
+    imgs, labels = make_samples(40, 61)     # 101 samples: partial last tile
+    n = len(imgs)
+    ev = _gpu_eval(orc.HAAR, mode, 24, 24, n, gpu_ctx)
+    ev.setImages(imgs, labels)
+    o = orc.Evaluator(orc.HAAR, mode, 24, 24, n)
+    o.set_images(imgs, labels)
+    for si in [0, 1, 31, 32, 63, 64, 100]:
+        s, t, nf = ev.integrals(si)
+        os_, ot, onf = o.integrals(si)
+        assert (s == os_).all()
+        if mode == orc.ALL:
+            assert (t == ot).all()
+        assert np.float32(nf) == np.float32(onf)
+    assert (ev.getCls()[:n] == labels).all()
+
+
+def test_set_image_single_slot_isolated(gpu_ctx):
+    """setImage(img, label, idx) touches only slot idx (test_features.cpp:364-392)."""
+    imgs, labels = make_samples(10, 30)
+    ev = _gpu_eval(orc.HAAR, orc.ALL, 24, 24, 40, gpu_ctx)
+    ev.setImages(imgs, labels)
+    before = [ev.integrals(si) for si in (4, 5, 6)]
+    new = (255 - imgs[5])
+    ev.setImage(new, 1, 5)
+    s4, t4, n4 = ev.integrals(4)
+    assert (s4 == before[0][0]).all() and (t4 == before[0][1]).all() and n4 == before[0][2]
+    s6, t6, n6 = ev.integrals(6)
+    assert (s6 == before[2][0]).all() and (t6 == before[2][1]).all() and n6 == before[2][2]
+    s5, t5, n5 = ev.integrals(5)
+    rs, _, rt = orc.integral(new, tilted=True)
+    assert (s5 == rs.ravel()).all() and (t5 == rt.ravel()).all()
+    assert ev.getCls(5) == 1.0
+
+
+def test_wide_window_integrals(gpu_ctx):
+    """75x32 (the reference's barcode window): multi-chunk rows, unstaged output path."""
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (37, 32, 75), dtype=np.uint8)
+    labels = np.zeros(37, np.uint8)
+    ev = _gpu_eval(orc.HAAR, orc.ALL, 75, 32, 37, gpu_ctx)
+    ev.setImages(imgs, labels)
+    for si in [0, 17, 36]:
+        s, t, nf = ev.integrals(si)
+        rs, rq, rt = orc.integral(imgs[si], tilted=True, sq=True)
+        assert (s == rs.ravel()).all() and (t == rt.ravel()).all()
+        assert np.float32(nf) == np.float32(orc.norm_factor(imgs[si]))
+
+
+@pytest.mark.parametrize("ftype,mode,W,H", [(orc.HAAR, orc.BASIC, 24, 24), (orc.HAAR, orc.ALL, 24, 24),
+                                            (orc.LBP, 0, 24, 24), (orc.HOG, 0, 48, 96), (orc.HAAR, orc.CORE, 20, 16)])
+def test_operator_call_matches_oracle(gpu_ctx, ftype, mode, W, H):
+    imgs, labels = make_samples(20, 45, W, H)
+    n = len(imgs)
+    ev = _gpu_eval(ftype, mode, W, H, n, gpu_ctx)
+    ev.setImages(imgs, labels)
+    o = orc.Evaluator(ftype, mode, W, H, n)
+    o.set_images(imgs, labels)
+    rng = np.random.default_rng(1)
+    nv = o.var_count
+    vis = np.unique(np.concatenate([rng.integers(0, nv, 400), [0, nv - 1]])).astype(np.int32)
+    g = ev.values(vis, 0, n)
+    r = o.values(vis, 0, n)
+    if ftype == orc.HOG:
+        # f32 planes built in the same sequential order: expected bit-exact vs the oracle
+        assert np.array_equal(g, r)
+    else:
+        assert np.array_equal(g.view(np.uint32), r.view(np.uint32))   # bit-exact incl. Haar division
+    assert ev(int(vis[3]), 7) == r[3, 7]
+
+
+def test_flat_image_invariants(gpu_ctx):
+    """Haar == 0, LBP == 255, HOG == 0 on a constant image (test_features.cpp:252-340,394-417)."""
+    import cascadeclassifier_b200 as ccb
+    flat = np.full((1, 24, 24), 128, np.uint8)
+    for ftype, expect in [(orc.HAAR, 0.0), (orc.LBP, 255.0)]:
+        ev = _gpu_eval(ftype, orc.ALL, 24, 24, 1, gpu_ctx)
+        ev.setImages(flat, np.ones(1, np.uint8))
+        vals = ev.values(np.arange(0, ev.getNumFeatures(), 97, dtype=np.int32), 0, 1)
+        assert (vals == expect).all()
+    flat = np.full((1, 96, 48), 77, np.uint8)
+    ev = _gpu_eval(orc.HOG, 0, 48, 96, 1, gpu_ctx)
+    ev.setImages(flat, np.ones(1, np.uint8))
+    vals = ev.values(np.arange(0, ev.getNumFeatures() * 36, 53, dtype=np.int32), 0, 1)
+    assert (vals == 0.0).all()
+    assert isinstance(ev, ccb.CvFeatureEvaluator)
+
+
+def test_hog_planes_match_oracle(gpu_ctx):
+    imgs, labels = make_samples(3, 4, 48, 96)
+    ev = _gpu_eval(orc.HOG, 0, 48, 96, 7, gpu_ctx)
+    ev.setImages(imgs, labels)
+    for si in (0, 6):
+        g = ev.hogPlanes(si)
+        r = orc.hog_planes(imgs[si]).reshape(10, -1)
+        assert np.array_equal(g, r)
+
+
+@pytest.mark.parametrize("ftype,mode,W,H,npos,nneg", [(orc.HAAR, orc.BASIC, 24, 24, 150, 317), (orc.HAAR, orc.ALL, 24, 24, 90, 200),
+                                                      (orc.LBP, 0, 24, 24, 100, 233), (orc.HOG, 0, 48, 96, 40, 60)])
+def test_precalc_and_sort_match_oracle(gpu_ctx, ftype, mode, W, H, npos, nneg):
+    import ctypes as C
+    from cascadeclassifier_b200._lib import check
+    imgs, labels = make_samples(npos, nneg, W, H)
+    n = len(imgs)
+    ev = _gpu_eval(ftype, mode, W, H, n, gpu_ctx)
+    ev.setImages(imgs, labels)
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    check(lib.cc_boost_precalc(h, n), "precalc")
+    o = orc.Evaluator(ftype, mode, W, H, n)
+    o.set_images(imgs, labels)
+    F = o.var_count
+    rng = np.random.default_rng(5)
+    starts = sorted(set([0, max(0, F - 64)] + [int(x) for x in rng.integers(0, max(1, F - 64), 6)]))
+    for r0 in starts:
+        nr = min(64, F - r0)
+        rows = np.arange(r0, r0 + nr, dtype=np.int32)
+        td = orc.TrainData(o, n, orc.SORT_STABLE, 8, subset=rows)
+        g = np.zeros((nr, n), np.float32)
+        check(lib.cc_boost_get_fval(h, r0, nr, g.ctypes.data_as(C.c_void_p)), "get_fval")
+        assert np.array_equal(g.view(np.uint32), td.fval().view(np.uint32)), "fval rows %d.." % r0
+        if ftype != orc.LBP:
+            gi = np.zeros((nr, n), np.uint16)
+            check(lib.cc_boost_get_sorted_idx(h, r0, nr, gi.ctypes.data_as(C.c_void_p)), "get_sidx")
+            assert np.array_equal(gi, td.sidx()), "sorted idx rows %d.." % r0
+            gv = np.zeros((nr, n), np.float32)
+            check(lib.cc_boost_get_sorted_val(h, r0, nr, gv.ctypes.data_as(C.c_void_p)), "get_sval")
+            assert np.array_equal(gv, np.take_along_axis(td.fval(), td.sidx().astype(np.int64), axis=1))
