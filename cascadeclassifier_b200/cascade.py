@@ -1,0 +1,293 @@
+"""Host-side mirror of CvCascadeParams / CvCascadeClassifier (training half) over the C ABI
+(traincascade/lib/include/cascadeclassifier.h:84-204, traincascade/lib/src/cascadeclassifier.cpp:24-578).
+
+The stage loop, the stdout text and the files written (params.xml, stage<i>.xml, cascade.xml) follow the
+reference; the two hot calls — updateTrainingSet (mining) and CvCascadeBoost::train — run on the GPU.
+"""
+import ctypes as C
+import math
+import os
+import sys
+import time
+
+import numpy as np
+
+from . import _lib, synth
+from ._lib import CascadeCudaError, check
+from .boost import CvCascadeBoost, CvCascadeBoostParams
+from .evaluator import Context, CvFeatureEvaluator, CvFeatureParams, CvHaarFeatureParams, _p
+from .xml_io import XmlWriter
+
+
+class CvCascadeParams:
+    BOOST = 0
+    defaultStageType = BOOST
+    defaultFeatureType = CvFeatureParams.HAAR
+    _FT = {0: "HAAR", 1: "LBP", 2: "HOG"}
+
+    def __init__(self, stageType=0, featureType=0, winSize=(24, 24)):
+        self.stageType = stageType
+        self.featureType = featureType
+        self.winSize = (int(winSize[0]), int(winSize[1]))     # (width, height)
+        self.name = "cascadeParams"
+
+    def write(self, fs):      # src/cascadeclassifier.cpp:33-46
+        fs.write("stageType", "BOOST")
+        fs.write("featureType", self._FT[self.featureType])
+        fs.write("height", self.winSize[1])
+        fs.write("width", self.winSize[0])
+
+    def printAttrs(self, out):
+        out.write("stageType: BOOST\n")
+        out.write("featureType: %s\n" % self._FT[self.featureType])
+        out.write("sampleWidth: %d\n" % self.winSize[0])
+        out.write("sampleHeight: %d\n" % self.winSize[1])
+
+
+def _fmt(v):
+    """std::cout << float/double with default precision 6."""
+    return "%g" % v
+
+
+def load_backgrounds(bg_filename):
+    """CvCascadeImageReader::NegReader::create (src/imagestorage.cpp:35-55) + cv::imread(path, 0)."""
+    names = []
+    with open(bg_filename, "r") as f:
+        for line in f:
+            s = line.rstrip(" \n\r\t")
+            if not s:
+                break
+            if s[0] == "#":
+                continue
+            names.append(s)
+    images = []
+    for n in names:
+        if n.lower().endswith(".pgm"):
+            images.append(synth.read_pgm(n))
+        else:
+            import cv2
+            im = cv2.imread(n, 0)
+            images.append(im if im is not None else np.zeros((0, 0), np.uint8))
+    return images
+
+
+class CvCascadeClassifier:
+    def __init__(self, ctx=None, out=None):
+        self.ctx = ctx
+        self.out = out or sys.stdout
+        self.stageClassifiers = []
+        self.featureEvaluator = None
+        self.cascadeParams = None
+        self.featureParams = None
+        self.stageParams = None
+        self.numPos = self.numNeg = self.numStages = self.curNumSamples = 0
+        self.reports = []
+        self.timings = []
+        self._reader = _lib.ReaderState()
+        self._vec_pos = C.c_int32(0)
+        self._vec = None
+
+    # -- data sources (imgReader.create) --
+    def _create_readers(self, positives, backgrounds):
+        W, H = self.cascadeParams.winSize
+        self._vec = np.ascontiguousarray(positives, np.uint8)
+        if self._vec.ndim != 3 or self._vec.shape[1:] != (H, W):
+            raise CascadeCudaError("vec samples must be [count,%d,%d]" % (H, W))
+        lib, h = self.ctx.lib, self.ctx.h
+        check(lib.cc_bg_clear(h), "cc_bg_clear")
+        for im in backgrounds:
+            im = np.ascontiguousarray(im, np.uint8)
+            if im.size == 0:
+                continue
+            check(lib.cc_bg_register(h, _p(im), im.shape[1], im.shape[0]), "cc_bg_register")
+        self._reader = _lib.ReaderState()
+        self._vec_pos = C.c_int32(0)
+
+    def _sync_cascade(self):
+        n = len(self.stageClassifiers)
+        arr = (_lib.Stage * max(n, 1))()
+        for i, st in enumerate(self.stageClassifiers):
+            cs = st.c_stage()
+            arr[i] = cs
+        self._stage_arr = arr
+        check(self.ctx.lib.cc_cascade_set_stages(self.ctx.h, arr, n), "cc_cascade_set_stages")
+
+    # -- fillPassedSamples (src/cascadeclassifier.cpp:329-357) --
+    def fillPassedSamples(self, first, count, isPositive, minimumAcceptanceRatio):
+        lib, h = self.ctx.lib, self.ctx.h
+        consumed, got = C.c_int64(0), C.c_int32(0)
+        if isPositive:
+            check(lib.cc_mine_positives(h, _p(self._vec), self._vec.shape[0], int(count), C.byref(self._vec_pos),
+                                        C.byref(consumed), C.byref(got)), "cc_mine_positives")
+        else:
+            check(lib.cc_mine_negatives(h, int(first), int(count), float(minimumAcceptanceRatio),
+                                        C.byref(self._reader), C.byref(consumed), C.byref(got)), "cc_mine_negatives")
+        return got.value, consumed.value
+
+    # -- updateTrainingSet (src/cascadeclassifier.cpp:308-327) --
+    def updateTrainingSet(self, minimumAcceptanceRatio):
+        self._vec_pos = C.c_int32(0)          # imgReader.restart(): rewinds the .vec only
+        self._sync_cascade()
+        posCount, posConsumed = self.fillPassedSamples(0, self.numPos, True, 0)
+        rep = dict(pos_count=posCount, pos_consumed=posConsumed, neg_count=0, neg_consumed=0, acceptance_ratio=0.0)
+        if not posCount:
+            return False, 0.0, rep
+        self.out.write("POS count : consumed   %d : %d\n" % (posCount, int(posConsumed)))
+        proNumNeg = int(np.rint((float(self.numNeg) * float(posCount)) / self.numPos))      # cvRound
+        negCount, negConsumed = self.fillPassedSamples(posCount, proNumNeg, False, minimumAcceptanceRatio)
+        rep.update(neg_count=negCount, neg_consumed=negConsumed)
+        if not negCount:
+            if not (negConsumed > 0 and (float(negCount) + 1) / float(negConsumed) <= minimumAcceptanceRatio):
+                return False, 0.0, rep
+        self.curNumSamples = posCount + negCount
+        acceptanceRatio = 0.0 if negConsumed == 0 else float(negCount) / float(negConsumed)
+        rep["acceptance_ratio"] = acceptanceRatio
+        self.out.write("NEG count : acceptanceRatio    %d : %s\n" % (negCount, _fmt(acceptanceRatio)))
+        return True, acceptanceRatio, rep
+
+    # -- train (src/cascadeclassifier.cpp:137-295) --
+    def train(self, cascadeDirName, posFilename, negFilename, numPos, numNeg, precalcValBufSize, precalcIdxBufSize,
+              numStages, cascadeParams, featureParams, stageParams, baseFormatSave=False,
+              acceptanceRatioBreakValue=-1.0, positives=None, backgrounds=None):
+        t_start = time.time()
+        out = self.out
+        if not cascadeDirName or (positives is None and not posFilename) or (backgrounds is None and not negFilename):
+            raise CascadeCudaError("_cascadeDirName or _bgfileName or _vecFileName is NULL")
+        dirName = cascadeDirName if cascadeDirName[-1] in "/\\" else cascadeDirName + "/"
+        self.numPos, self.numNeg, self.numStages = numPos, numNeg, numStages
+        self.cascadeParams, self.featureParams, self.stageParams = cascadeParams, featureParams, stageParams
+        if self.ctx is None:
+            self.ctx = Context(0)
+        W, H = cascadeParams.winSize
+        try:
+            if positives is None:
+                positives = synth.read_vec(posFilename, W, H)
+            if backgrounds is None:
+                backgrounds = load_backgrounds(negFilename)
+        except (IOError, OSError, ValueError):
+            out.write("Image reader can not be created from -vec %s and -bg %s.\n" % (posFilename, negFilename))
+            return False
+        self.featureEvaluator = CvFeatureEvaluator.create(cascadeParams.featureType, self.ctx)
+        self.featureEvaluator.init(featureParams, numPos + numNeg, cascadeParams.winSize)
+        self._create_readers(positives, backgrounds)
+        self.stageClassifiers = []
+        out.write("PARAMETERS:\ncascadeDirName: %s\nvecFileName: %s\nbgFileName: %s\n" % (cascadeDirName, posFilename, negFilename))
+        out.write("numPos: %d\nnumNeg: %d\nnumStages: %d\n" % (numPos, numNeg, numStages))
+        out.write("precalcValBufSize[Mb] : %d\nprecalcIdxBufSize[Mb] : %d\n" % (precalcValBufSize, precalcIdxBufSize))
+        out.write("acceptanceRatioBreakValue : %s\n" % _fmt(acceptanceRatioBreakValue))
+        cascadeParams.printAttrs(out)
+        out.write("boostType: %s\nminHitRate: %s\nmaxFalseAlarmRate: %s\nweightTrimRate: %s\nmaxDepth: %d\nmaxWeakCount: %d\n" % (
+            stageParams.boostTypeStr(), _fmt(stageParams.minHitRate), _fmt(stageParams.maxFalseAlarm),
+            _fmt(stageParams.weight_trim_rate), stageParams.max_depth, stageParams.weak_count))
+        if isinstance(featureParams, CvHaarFeatureParams):
+            out.write("mode: %s\n" % featureParams.modeStr())
+        out.write("Number of unique features given windowSize [%d,%d] : %d\n" % (W, H, self.featureEvaluator.getNumFeatures()))
+
+        requiredLeafFARate = math.pow(float(stageParams.maxFalseAlarm), float(numStages)) / float(stageParams.max_depth)
+        for i in range(numStages):
+            out.write("\n===== TRAINING %d-stage =====\n<BEGIN\n" % i)
+            t0 = time.time()
+            ok, tempLeafFARate, rep = self.updateTrainingSet(requiredLeafFARate)
+            t1 = time.time()
+            self.reports.append(rep)
+            if not ok:
+                out.write("Train dataset for temp stage can not be filled. Branch training terminated.\n")
+                break
+            if tempLeafFARate <= requiredLeafFARate:
+                out.write("Required leaf false alarm rate achieved. Branch training terminated.\n")
+                break
+            if tempLeafFARate <= acceptanceRatioBreakValue and acceptanceRatioBreakValue >= 0:
+                out.write("The required acceptanceRatio for the model has been reached to avoid overfitting of "
+                          "trainingdata. Branch training terminated.\n")
+                break
+            tempStage = CvCascadeBoost()
+            out.write("+----+---------+---------+\n|  N |    HR   |    FA   |\n+----+---------+---------+\n")
+            isStageTrained = tempStage.train(self.featureEvaluator, self.curNumSamples, precalcValBufSize,
+                                             precalcIdxBufSize, stageParams)
+            for n, hr, fa in tempStage.log:
+                out.write("|%4d|%9s|%9s|\n+----+---------+---------+\n" % (n, _fmt(hr), _fmt(fa)))
+            out.write("END>\n")
+            t2 = time.time()
+            self.timings.append(dict(stage=i, mine_s=t1 - t0, train_s=t2 - t1, weak=len(tempStage.trees),
+                                     neg_consumed=rep["neg_consumed"]))
+            if not isStageTrained:
+                break
+            self.stageClassifiers.append(tempStage)
+            os.makedirs(dirName, exist_ok=True)
+            if i == 0:
+                fs = XmlWriter(dirName + "params.xml")
+                fs.start_map("params")
+                self.writeParams(fs)
+                fs.end_map()
+                fs.release()
+            fs = XmlWriter(dirName + "stage%d.xml" % i)
+            fs.start_map("stage%d" % i)
+            tempStage.write(fs, None, self.featureEvaluator.getMaxCatCount())
+            fs.end_map()
+            fs.release()
+            seconds = int(time.time() - t_start)
+            out.write("Training until now has taken %d days %d hours %d minutes %d seconds.\n" % (
+                seconds // 86400, (seconds // 3600) % 24, (seconds // 60) % 60, seconds % 60))
+        if not self.stageClassifiers:
+            out.write("Cascade classifier can't be trained. Check the used training parameters.\n")
+            return False
+        self.save(dirName + "cascade.xml", baseFormatSave)
+        return True
+
+    def predict(self, sampleIdx):
+        for st in self.stageClassifiers:
+            if st.predict(self.featureEvaluator, sampleIdx) == 0.0:
+                return 0
+        return 1
+
+    # -- XML (src/cascadeclassifier.cpp:359-386, 439-456, 566-578) --
+    def writeParams(self, fs):
+        self.cascadeParams.write(fs)
+        sp = self.stageParams
+        fs.start_map("stageParams")
+        fs.write("boostType", sp.boostTypeStr())
+        fs.write("minHitRate", float(np.float32(sp.minHitRate)))
+        fs.write("maxFalseAlarm", float(np.float32(sp.maxFalseAlarm)))
+        fs.write("weightTrimRate", float(sp.weight_trim_rate))
+        fs.write("maxDepth", int(sp.max_depth))
+        fs.write("maxWeakCount", int(sp.weak_count))
+        fs.end_map()
+        fp = self.featureParams
+        fs.start_map("featureParams")
+        fs.write("maxCatCount", int(fp.maxCatCount))
+        fs.write("featSize", int(fp.featSize))
+        if isinstance(fp, CvHaarFeatureParams):
+            fs.write("mode", fp.modeStr())
+        fs.end_map()
+
+    def getUsedFeaturesIdxMap(self):
+        varCount = self.featureEvaluator.getNumFeatures() * self.featureEvaluator.getFeatureSize()
+        fmap = np.full(varCount, -1, np.int32)
+        for st in self.stageClassifiers:
+            st.markUsedFeaturesInMap(fmap)
+        idx = 0
+        for fi in range(varCount):
+            if fmap[fi] >= 0:
+                fmap[fi] = idx
+                idx += 1
+        return fmap
+
+    def save(self, filename, baseFormat=False):
+        if baseFormat:
+            raise CascadeCudaError("old file format (-baseFormatSave) is written by the unchanged reference host code; "
+                                   "not part of the GPU path")
+        fs = XmlWriter(filename)
+        fmap = self.getUsedFeaturesIdxMap()
+        fs.start_map("cascade")
+        self.writeParams(fs)
+        fs.write("stageNum", len(self.stageClassifiers))
+        fs.start_seq("stages")
+        for i, st in enumerate(self.stageClassifiers):
+            fs.comment("stage %d" % i)
+            fs.start_map(None)
+            st.write(fs, fmap, self.featureEvaluator.getMaxCatCount())
+            fs.end_map()
+        fs.end_seq()
+        self.featureEvaluator.writeFeatures(fs, fmap)
+        fs.end_map()
+        fs.release()

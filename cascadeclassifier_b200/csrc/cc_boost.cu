@@ -316,11 +316,28 @@ __device__ __forceinline__ double criterion(double A, double B, double totA, dou
   }
 }
 
+// f32 estimate of the same criterion, used only to decide whether a candidate can possibly beat the
+// running best; every candidate that survives the filter is re-evaluated with criterion<>() in f64,
+// so the selected split is the one full-f64 evaluation would select.
+template <int CRIT>
+__device__ __forceinline__ float criterion32(float A, float B, float totA, float totB) {
+  if (CRIT == CRIT_SQERR) {
+    const float L = A, R = totA - A, lsum = B, rsum = totB - B;
+    return __fdividef(lsum * lsum * R + rsum * rsum * L, L * R);
+  } else if (CRIT == CRIT_GINI) {
+    const float r0 = totA - A, r1 = totB - B, L = A + B, R = r0 + r1;
+    return __fdividef((A * A + B * B) * R + (r0 * r0 + r1 * r1) * L, L * R);
+  } else {
+    const float r0 = totA - A, r1 = totB - B;
+    return fmaxf(A + r1, B + r0);
+  }
+}
+
 template <int CRIT, bool HAS_Y>
 __global__ void __launch_bounds__(SS_THREADS, 1)
 k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ sval, int n_stride, int N, int nrows,
                    const double* __restrict__ wnode, const float* __restrict__ ynode, const NodeStats* __restrict__ stats,
-                   RowBest* __restrict__ out) {
+                   float filter_abs, RowBest* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sw = reinterpret_cast<double*>(smem_raw);
   float* sy = reinterpret_cast<float*>(sw + N);
@@ -329,7 +346,10 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
   const NodeStats st = *stats;
   const double totA = st.rcw[0];
   const double totB = (CRIT == CRIT_SQERR) ? st.rsum0 : st.rcw[1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float ftotA = (float)totA, ftotB = (float)totB;
+  // broadcast from lane 0 so that the compiler knows the row loop is warp-uniform (no collective-sync
+  // wrappers around the shuffles inside it)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
   const float eps = FLT_EPSILON * 2;
 
@@ -342,6 +362,8 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
     double bestVal = -1.0;
     int bestPos = -1;
     float bestVl = 0.f, bestVr = 0.f;
+    float best32 = -1.f;          // lane-local f32 image of bestVal
+    float thr32 = -3.0e38f;       // warp-uniform filter threshold, refreshed once per tile
 
     uint4 nxt_i = *reinterpret_cast<const uint4*>(ri + lane * SS_EPT);
     float4 nxt_v0 = *reinterpret_cast<const float4*>(rv + lane * SS_EPT);
@@ -358,26 +380,29 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
       const uint32_t iw[4] = {ci.x, ci.y, ci.z, ci.w};
       const float v[SS_EPT] = {cv0.x, cv0.y, cv0.z, cv0.w, cv1.x, cv1.y, cv1.z, cv1.w};
       double a[SS_EPT], b[SS_EPT];
+      float af[SS_EPT], bf[SS_EPT];
       unsigned act = 0;
       double ta = 0, tb = 0;
       float lastv = 0.f;
 #pragma unroll
       for (int j = 0; j < SS_EPT; ++j) {
         const int idx = (int)((iw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
-        double w = 0.0;
-        float y = 0.f;
-        if (i0 + j < N) { w = sw[idx]; if (HAS_Y) y = sy[idx]; }
-        if (w != 0.0) {
-          act |= 1u << j;
-          lastv = v[j];
-          if (CRIT == CRIT_SQERR) {
-            if (HAS_Y) { a[j] = w; b[j] = (double)y * w; } else { a[j] = fabs(w); b[j] = w; }
-          } else {
-            a[j] = w < 0.0 ? -w : 0.0;
-            b[j] = w > 0.0 ? w : 0.0;
-          }
-          ta += a[j]; tb += b[j];
-        } else { a[j] = 0.0; b[j] = 0.0; }
+        const bool inb = i0 + j < N;
+        const double w = inb ? sw[idx] : 0.0;          // 0 marks "not in this node"
+        const float wf = (float)w;
+        const bool on = w != 0.0;
+        act |= on ? (1u << j) : 0u;
+        lastv = on ? v[j] : lastv;
+        if (CRIT == CRIT_SQERR) {
+          if (HAS_Y) {
+            const float y = inb ? sy[idx] : 0.f;
+            a[j] = w; b[j] = (double)y * w; af[j] = wf; bf[j] = y * wf;
+          } else { a[j] = fabs(w); b[j] = w; af[j] = fabsf(wf); bf[j] = wf; }
+        } else {
+          a[j] = w < 0.0 ? -w : 0.0; b[j] = w > 0.0 ? w : 0.0;
+          af[j] = wf < 0.f ? -wf : 0.f; bf[j] = wf > 0.f ? wf : 0.f;
+        }
+        ta += a[j]; tb += b[j];
       }
       const int cnt = __popc(act);
       // warp exclusive scans of (ta, tb, cnt)
@@ -390,6 +415,7 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
         if (lane >= d) { ia += xa; ib += xb; ic += xc; }
       }
       double pa = carryA + (ia - ta), pb = carryB + (ib - tb);
+      float fa = (float)pa, fb = (float)pb;
       int pc = carryCnt + (ic - cnt);
       // value of the last node sample before this lane's chunk
       const uint32_t has_mask = __ballot_sync(0xffffffffu, act != 0);
@@ -397,27 +423,40 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
       const int src = before ? (31 - __clz(before)) : 0;
       const float pv_other = __shfl_sync(0xffffffffu, lastv, src);
       float pv = before ? pv_other : carryV;
-      int pHas = before ? 1 : carryHas;
+      bool pHas = before ? true : (carryHas != 0);
+      const float marg = 1e-5f * fabsf(best32) + filter_abs;
+      float lim = fmaxf(thr32, best32 - marg);       // candidates estimated below this cannot win
 #pragma unroll
       for (int j = 0; j < SS_EPT; ++j) {
-        if (act & (1u << j)) {
-          if (pHas && __fadd_rn(pv, eps) < v[j]) {
-            const double val = criterion<CRIT>(pa, pb, totA, totB);
-            if (val > bestVal) { bestVal = val; bestPos = pc - 1; bestVl = pv; bestVr = v[j]; }
+        const bool on = (act >> j) & 1u;
+        const bool cand = on && pHas && (__fadd_rn(pv, eps) < v[j]);
+        const float est = criterion32<CRIT>(fa, fb, ftotA, ftotB);
+        if (cand && !(est < lim)) {                    // rare: exact f64 evaluation
+          const double val = criterion<CRIT>(pa, pb, totA, totB);
+          if (val > bestVal) {
+            bestVal = val; bestPos = pc - 1; bestVl = pv; bestVr = v[j]; best32 = (float)val;
+            lim = fmaxf(lim, best32 - (1e-5f * fabsf(best32) + filter_abs));
           }
-          pa += a[j]; pb += b[j]; pc += 1;
-          pv = v[j]; pHas = 1;
         }
+        pa += a[j]; pb += b[j]; fa += af[j]; fb += bf[j];
+        pc += on ? 1 : 0;
+        pv = on ? v[j] : pv;
+        pHas = pHas || on;
       }
       // carries for the next tile
       carryA += __shfl_sync(0xffffffffu, ia, 31);
       carryB += __shfl_sync(0xffffffffu, ib, 31);
       carryCnt += __shfl_sync(0xffffffffu, ic, 31);
-      if (has_mask) {
-        const int lastLane = 31 - __clz(has_mask);
-        carryV = __shfl_sync(0xffffffffu, lastv, lastLane);
-        carryHas = 1;
+      {
+        const int lastLane = has_mask ? 31 - __clz(has_mask) : 0;
+        const float lv = __shfl_sync(0xffffffffu, lastv, lastLane);
+        if (has_mask) { carryV = lv; carryHas = 1; }
       }
+      // share the best estimate across the warp: anything clearly below it cannot win the row
+      float wb = best32;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) wb = fmaxf(wb, __shfl_xor_sync(0xffffffffu, wb, d));
+      thr32 = wb - (1e-5f * fabsf(wb) + filter_abs);
     }
     // warp argmax: larger value first, then smaller position (first maximum of the sequential scan)
     int owner = lane;
@@ -463,7 +502,7 @@ k_split_search_cat(const uint8_t* __restrict__ codes, int n_stride, int N, int n
   int* order_all = reinterpret_cast<int*>(bins + CAT_WARPS * 3 * 256); // [CAT_WARPS][256]
   for (int i = threadIdx.x; i < N; i += CAT_THREADS) { sw[i] = wnode[i]; sy[i] = has_y ? ynode[i] : 0.f; }
   __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   double* s0 = bins + warp * 3 * 256;     // regression: sum of y*w ; classification: class-0 weight
   double* s1 = s0 + 256;                  // regression: sum of w   ; classification: class-1 weight
   double* key = s1 + 256;
@@ -874,12 +913,16 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
     const size_t smem = (size_t)N * 8 + (has_y ? (size_t)N * 4 : 0) + 16;
     CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED, "split search: numSamples %d needs %zu B of shared memory (limit 227 KB)", N, smem);
     const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
+    // absolute slack of the f32 pre-filter: the f32 prefix sums carry ~1e-6 * (node weight) * |y|max^2
+    // of absolute error (see criterion32); LogitBoost targets are clipped to |z| <= 10 (boost.cpp:347).
+    const double ymax2 = has_y ? 100.0 : 1.0;
+    const float filter_abs = (float)(8e-6 * (b->h_stats[nid].rcw[0] + b->h_stats[nid].rcw[1]) * ymax2 + 1e-30);
     const int blocks = std::min((ctx->nrows + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
 #define LAUNCH_SS(CR, HY)                                                                                                   \
   {                                                                                                                         \
     CC_CUDA(cudaFuncSetAttribute(k_split_search_ord<CR, HY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     k_split_search_ord<CR, HY><<<blocks, SS_THREADS, smem, ctx->stream>>>(ctx->d_sidx, ctx->d_sval, ctx->n_stride, N, ctx->nrows, \
-                                                                          b->wnode, b->ynode, b->d_stats + nid, b->rowbest); \
+                                                                          b->wnode, b->ynode, b->d_stats + nid, filter_abs, b->rowbest); \
   }
     if (b->crit == CRIT_SQERR) { if (has_y) LAUNCH_SS(CRIT_SQERR, true) else LAUNCH_SS(CRIT_SQERR, false) }
     else if (b->crit == CRIT_GINI) LAUNCH_SS(CRIT_GINI, false)

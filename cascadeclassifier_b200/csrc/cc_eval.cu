@@ -299,40 +299,84 @@ __global__ void k_eval_values(EvalView e, const int* __restrict__ vars, int nv, 
   }
 }
 
-EvalView make_eval_view(const cc_ctx* ctx) {
+EvalView make_eval_view_store(const cc_ctx* ctx, const EvalStore& st) {
   EvalView e;
-  e.ftype = ctx->ftype; e.P = ctx->P; e.ns_pad = ctx->ns_pad;
-  e.sum = ctx->d_sum; e.tilted = ctx->d_tilted; e.nf = ctx->d_nf; e.hog = ctx->d_hog;
+  e.ftype = ctx->ftype; e.P = ctx->P; e.ns_pad = st.ns_pad;
+  e.sum = st.d_sum; e.tilted = st.d_tilted; e.nf = st.d_nf; e.hog = st.d_hog;
   e.haar_taps = ctx->d_haar_taps; e.lbp_taps = ctx->d_lbp_taps; e.hog_taps = ctx->d_hog_taps;
   return e;
+}
+EvalView make_eval_view(const cc_ctx* ctx) { return make_eval_view_store(ctx, main_store(ctx)); }
+
+EvalStore main_store(const cc_ctx* ctx) {
+  EvalStore s;
+  s.max_samples = ctx->max_samples; s.ntiles = ctx->ntiles; s.ns_pad = ctx->ns_pad;
+  s.d_imgs = ctx->d_imgs; s.d_labels = ctx->d_labels; s.d_sum = ctx->d_sum; s.d_tilted = ctx->d_tilted;
+  s.d_nf = ctx->d_nf; s.d_hog = ctx->d_hog;
+  return s;
+}
+
+void store_free(EvalStore& st) {
+  cudaFree(st.d_imgs); cudaFree(st.d_labels); cudaFree(st.d_sum); cudaFree(st.d_tilted); cudaFree(st.d_nf); cudaFree(st.d_hog);
+  st = EvalStore();
+}
+
+int store_alloc(cc_ctx* ctx, EvalStore& st, int max_samples) {
+  st.max_samples = max_samples;
+  st.ntiles = (max_samples + TILE - 1) / TILE;
+  st.ns_pad = st.ntiles * TILE;
+  const size_t npx = (size_t)ctx->W * ctx->H;
+  CC_CUDA(cudaMalloc(&st.d_imgs, (size_t)st.ns_pad * npx));
+  CC_CUDA(cudaMemsetAsync(st.d_imgs, 0, (size_t)st.ns_pad * npx, ctx->stream));
+  CC_CUDA(cudaMalloc(&st.d_labels, st.ns_pad));
+  CC_CUDA(cudaMemsetAsync(st.d_labels, 0, st.ns_pad, ctx->stream));
+  const size_t tile_bytes = (size_t)st.ntiles * ctx->P * TILE * sizeof(int32_t);
+  if (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) {
+    CC_CUDA(cudaMalloc(&st.d_sum, tile_bytes));
+    CC_CUDA(cudaMemsetAsync(st.d_sum, 0, tile_bytes, ctx->stream));
+  }
+  if (ctx->ftype == CC_FEATURE_HAAR) {
+    if (ctx->haar_mode == CC_HAAR_ALL) {
+      CC_CUDA(cudaMalloc(&st.d_tilted, tile_bytes));
+      CC_CUDA(cudaMemsetAsync(st.d_tilted, 0, tile_bytes, ctx->stream));
+    }
+    CC_CUDA(cudaMalloc(&st.d_nf, st.ns_pad * sizeof(float)));
+    CC_CUDA(cudaMemsetAsync(st.d_nf, 0, st.ns_pad * sizeof(float), ctx->stream));
+  }
+  if (ctx->ftype == CC_FEATURE_HOG) {
+    const size_t bytes = (size_t)10 * ctx->P * st.ns_pad * sizeof(float);
+    CC_CUDA(cudaMalloc(&st.d_hog, bytes));
+    CC_CUDA(cudaMemsetAsync(st.d_hog, 0, bytes, ctx->stream));
+  }
+  return CC_OK;
 }
 
 int eval_free(cc_ctx* ctx) {
   cudaFree(ctx->d_imgs); cudaFree(ctx->d_labels); cudaFree(ctx->d_sum); cudaFree(ctx->d_tilted);
   cudaFree(ctx->d_nf); cudaFree(ctx->d_hog); cudaFree(ctx->d_haar_taps); cudaFree(ctx->d_lbp_taps);
-  cudaFree(ctx->d_hog_taps); cudaFree(ctx->d_upright_rows); cudaFree(ctx->d_tilted_rows);
+  cudaFree(ctx->d_hog_taps); cudaFree(ctx->d_taps_upright); cudaFree(ctx->d_taps_tilted);
   ctx->d_imgs = ctx->d_labels = nullptr; ctx->d_sum = ctx->d_tilted = nullptr; ctx->d_nf = nullptr; ctx->d_hog = nullptr;
   ctx->d_haar_taps = nullptr; ctx->d_lbp_taps = nullptr; ctx->d_hog_taps = nullptr;
-  ctx->d_upright_rows = ctx->d_tilted_rows = nullptr;
+  ctx->d_taps_upright = ctx->d_taps_tilted = nullptr;
   ctx->ftype = -1;
   return CC_OK;
 }
 
 // shared by setImage and by mining (windows already in d_imgs)
-int launch_integrals(cc_ctx* ctx, int first, int n) {
+int launch_integrals(cc_ctx* ctx, const EvalStore& st, int first, int n) {
   if (n <= 0) return CC_OK;
   const int last = first + n;
   if (ctx->ftype == CC_FEATURE_HOG) {
     ScopedTimer tm(ctx, "integral", 3);
     const size_t npx = (size_t)ctx->W * ctx->H;
     float* grad = nullptr; uint8_t* qa = nullptr;
-    CC_CUDA(cudaMallocAsync(&grad, npx * ctx->ns_pad * sizeof(float), ctx->stream));
-    CC_CUDA(cudaMallocAsync(&qa, npx * ctx->ns_pad, ctx->stream));
+    CC_CUDA(cudaMallocAsync(&grad, npx * st.ns_pad * sizeof(float), ctx->stream));
+    CC_CUDA(cudaMallocAsync(&qa, npx * st.ns_pad, ctx->stream));
     const int threads = 256;
     auto blocks = [&](long long total) { return (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->sm_count * 32); };
-    k_hog_gradient<<<blocks((long long)n * npx), threads, 0, ctx->stream>>>(ctx->d_imgs, ctx->W, ctx->H, first, n, ctx->ns_pad, grad, qa);
-    k_hog_rows<<<blocks((long long)10 * ctx->H * n), threads, 0, ctx->stream>>>(grad, qa, ctx->W, ctx->H, first, n, ctx->ns_pad, ctx->d_hog);
-    k_hog_cols<<<blocks((long long)10 * (ctx->W + 1) * n), threads, 0, ctx->stream>>>(ctx->W, ctx->H, first, n, ctx->ns_pad, ctx->d_hog);
+    k_hog_gradient<<<blocks((long long)n * npx), threads, 0, ctx->stream>>>(st.d_imgs, ctx->W, ctx->H, first, n, st.ns_pad, grad, qa);
+    k_hog_rows<<<blocks((long long)10 * ctx->H * n), threads, 0, ctx->stream>>>(grad, qa, ctx->W, ctx->H, first, n, st.ns_pad, st.d_hog);
+    k_hog_cols<<<blocks((long long)10 * (ctx->W + 1) * n), threads, 0, ctx->stream>>>(ctx->W, ctx->H, first, n, st.ns_pad, st.d_hog);
     CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaFreeAsync(grad, ctx->stream));
     CC_CUDA(cudaFreeAsync(qa, ctx->stream));
@@ -352,8 +396,8 @@ int launch_integrals(cc_ctx* ctx, int first, int n) {
 #define LAUNCH_INT(NC)                                                                                         \
   {                                                                                                            \
     CC_CUDA(cudaFuncSetAttribute(k_integral_tiles<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    k_integral_tiles<NC><<<tile1 - tile0 + 1, 1024, smem, ctx->stream>>>(ctx->d_imgs, W, H, first, last, ctx->d_sum, \
-                                                                         ctx->d_tilted, ctx->d_nf, want_tilted, want_nf, staged); \
+    k_integral_tiles<NC><<<tile1 - tile0 + 1, 1024, smem, ctx->stream>>>(st.d_imgs, W, H, first, last, st.d_sum, \
+                                                                         st.d_tilted, st.d_nf, want_tilted, want_nf, staged); \
   }
   switch (nchunk) {
     case 1: LAUNCH_INT(1); break;
@@ -387,33 +431,15 @@ int cc_eval_init(cc_ctx* ctx, int feature_type, int haar_mode, int win_w, int wi
   ctx->ntiles = (max_samples + TILE - 1) / TILE;
   ctx->ns_pad = ctx->ntiles * TILE;
   const int S = win_w + 1;
-  const size_t npx = (size_t)win_w * win_h;
-  CC_CUDA(cudaMalloc(&ctx->d_imgs, (size_t)ctx->ns_pad * npx));
-  CC_CUDA(cudaMemsetAsync(ctx->d_imgs, 0, (size_t)ctx->ns_pad * npx, ctx->stream));
-  CC_CUDA(cudaMalloc(&ctx->d_labels, ctx->ns_pad));
-  CC_CUDA(cudaMemsetAsync(ctx->d_labels, 0, ctx->ns_pad, ctx->stream));
   if (feature_type == CC_FEATURE_HAAR) {
     CC_REQUIRE(haar_mode >= CC_HAAR_BASIC && haar_mode <= CC_HAAR_ALL, CC_ERR_BAD_ARG, "cc_eval_init: unknown Haar mode %d", haar_mode);
     ctx->haar = make_haar_catalog(win_w, win_h, haar_mode);
     ctx->num_features = (int)ctx->haar.size(); ctx->feat_size = 1; ctx->max_cat = 0;
     std::vector<HaarTaps> taps(ctx->haar.size());
-    ctx->upright_rows.clear(); ctx->tilted_rows.clear();
-    for (size_t i = 0; i < ctx->haar.size(); ++i) {
-      taps[i] = make_haar_taps(ctx->haar[i], S);
-      (ctx->haar[i].tilted ? ctx->tilted_rows : ctx->upright_rows).push_back((int)i);
-    }
+    for (size_t i = 0; i < ctx->haar.size(); ++i) taps[i] = make_haar_taps(ctx->haar[i], S);
     CC_CUDA(cudaMalloc(&ctx->d_haar_taps, taps.size() * sizeof(HaarTaps)));
     CC_CUDA(cudaMemcpyAsync(ctx->d_haar_taps, taps.data(), taps.size() * sizeof(HaarTaps), cudaMemcpyHostToDevice, ctx->stream));
     CC_CUDA(cudaStreamSynchronize(ctx->stream));
-    const size_t tile_bytes = (size_t)ctx->ntiles * ctx->P * TILE * sizeof(int32_t);
-    CC_CUDA(cudaMalloc(&ctx->d_sum, tile_bytes));
-    CC_CUDA(cudaMemsetAsync(ctx->d_sum, 0, tile_bytes, ctx->stream));
-    if (haar_mode == CC_HAAR_ALL) {
-      CC_CUDA(cudaMalloc(&ctx->d_tilted, tile_bytes));
-      CC_CUDA(cudaMemsetAsync(ctx->d_tilted, 0, tile_bytes, ctx->stream));
-    }
-    CC_CUDA(cudaMalloc(&ctx->d_nf, ctx->ns_pad * sizeof(float)));
-    CC_CUDA(cudaMemsetAsync(ctx->d_nf, 0, ctx->ns_pad * sizeof(float), ctx->stream));
   } else if (feature_type == CC_FEATURE_LBP) {
     ctx->lbp = make_lbp_catalog(win_w, win_h);
     ctx->num_features = (int)ctx->lbp.size(); ctx->feat_size = 1; ctx->max_cat = 256;
@@ -422,9 +448,6 @@ int cc_eval_init(cc_ctx* ctx, int feature_type, int haar_mode, int win_w, int wi
     CC_CUDA(cudaMalloc(&ctx->d_lbp_taps, taps.size() * sizeof(LbpTaps)));
     CC_CUDA(cudaMemcpyAsync(ctx->d_lbp_taps, taps.data(), taps.size() * sizeof(LbpTaps), cudaMemcpyHostToDevice, ctx->stream));
     CC_CUDA(cudaStreamSynchronize(ctx->stream));
-    const size_t tile_bytes = (size_t)ctx->ntiles * ctx->P * TILE * sizeof(int32_t);
-    CC_CUDA(cudaMalloc(&ctx->d_sum, tile_bytes));
-    CC_CUDA(cudaMemsetAsync(ctx->d_sum, 0, tile_bytes, ctx->stream));
   } else {
     ctx->hog = make_hog_catalog(win_w, win_h);
     ctx->num_features = (int)ctx->hog.size(); ctx->feat_size = 36; ctx->max_cat = 0;
@@ -433,9 +456,12 @@ int cc_eval_init(cc_ctx* ctx, int feature_type, int haar_mode, int win_w, int wi
     CC_CUDA(cudaMalloc(&ctx->d_hog_taps, std::max<size_t>(1, taps.size()) * sizeof(HogTaps)));
     CC_CUDA(cudaMemcpyAsync(ctx->d_hog_taps, taps.data(), taps.size() * sizeof(HogTaps), cudaMemcpyHostToDevice, ctx->stream));
     CC_CUDA(cudaStreamSynchronize(ctx->stream));
-    const size_t bytes = (size_t)10 * ctx->P * ctx->ns_pad * sizeof(float);
-    CC_CUDA(cudaMalloc(&ctx->d_hog, bytes));
-    CC_CUDA(cudaMemsetAsync(ctx->d_hog, 0, bytes, ctx->stream));
+  }
+  {
+    EvalStore st;
+    CC_CHECK(store_alloc(ctx, st, max_samples));
+    ctx->d_imgs = st.d_imgs; ctx->d_labels = st.d_labels; ctx->d_sum = st.d_sum; ctx->d_tilted = st.d_tilted;
+    ctx->d_nf = st.d_nf; ctx->d_hog = st.d_hog;
   }
   ctx->var_count = ctx->num_features * ctx->feat_size;
   ctx->precalc_valid = false;
@@ -479,7 +505,7 @@ int cc_eval_set_images_device(cc_ctx* ctx, const uint8_t* dev_imgs, const uint8_
   if (dev_labels && dev_labels != ctx->d_labels + first)
     CC_CUDA(cudaMemcpyAsync(ctx->d_labels + first, dev_labels, n, cudaMemcpyDeviceToDevice, ctx->stream));
   ctx->precalc_valid = false;
-  return launch_integrals(ctx, first, n);
+  return launch_integrals(ctx, main_store(ctx), first, n);
 }
 
 int cc_eval_set_images(cc_ctx* ctx, const uint8_t* host_imgs, const uint8_t* host_labels, int first, int n) {
@@ -493,7 +519,7 @@ int cc_eval_set_images(cc_ctx* ctx, const uint8_t* host_imgs, const uint8_t* hos
   CC_CUDA(cudaMemcpyAsync(ctx->d_imgs + (size_t)first * npx, host_imgs, (size_t)n * npx, cudaMemcpyHostToDevice, ctx->stream));
   CC_CUDA(cudaMemcpyAsync(ctx->d_labels + first, host_labels, n, cudaMemcpyHostToDevice, ctx->stream));
   ctx->precalc_valid = false;
-  return launch_integrals(ctx, first, n);
+  return launch_integrals(ctx, main_store(ctx), first, n);
 }
 
 int cc_eval_values(cc_ctx* ctx, const int32_t* var_idx, int nv, int s0, int ns, float* out) {

@@ -97,6 +97,17 @@ struct DevStageRef { int first_tree, num_trees; float threshold; };
 struct BoostBuffers;
 struct MineState;
 
+// Device storage of one set of evaluator slots (the training set, or the mining scratch batch)
+struct EvalStore {
+  int max_samples = 0, ntiles = 0, ns_pad = 0;
+  uint8_t* d_imgs = nullptr;       // [ns_pad][H][W]
+  uint8_t* d_labels = nullptr;     // [ns_pad]
+  int32_t* d_sum = nullptr;        // tiles [ntiles][P][32]
+  int32_t* d_tilted = nullptr;     // tiles (Haar ALL only)
+  float* d_nf = nullptr;           // [ns_pad]
+  float* d_hog = nullptr;          // [10][P][ns_pad]
+};
+
 }  // namespace cc
 
 struct cc_ctx {
@@ -126,8 +137,8 @@ struct cc_ctx {
   cc::LbpTaps* d_lbp_taps = nullptr;
   cc::HogTaps* d_hog_taps = nullptr;
   std::vector<int> upright_rows, tilted_rows;   // global feature indices by plane (Haar)
-  int* d_upright_rows = nullptr;
-  int* d_tilted_rows = nullptr;
+  cc::HaarTaps* d_taps_upright = nullptr;   // compact per-plane tap lists of the local shard
+  cc::HaarTaps* d_taps_tilted = nullptr;
 
   // ---- train data ----
   int shard_rank = 0, shard_world = 1;
@@ -164,4 +175,8 @@ struct ScopedTimer {
 int eval_free(cc_ctx* ctx);
 int boost_free(cc_ctx* ctx);
 int mine_free(cc_ctx* ctx);
+EvalStore main_store(const cc_ctx* ctx);
+int store_alloc(cc_ctx* ctx, EvalStore& st, int max_samples);
+void store_free(EvalStore& st);
+int launch_integrals(cc_ctx* ctx, const EvalStore& st, int first, int n);
 }  // namespace cc

@@ -1,15 +1,770 @@
-// K5: hard-negative mining (placeholder until the kernels land; see cc_mine.cu history).
+// K5: hard-negative mining.  CvCascadeClassifier::updateTrainingSet / fillPassedSamples / predict
+// (src/cascadeclassifier.cpp:297-357) with the window stream of CvCascadeImageReader::NegReader
+// (src/imagestorage.cpp:23-126) and PosReader (:138-189).
+//
+// The reference consumes one window at a time: copy the crop, build its integral images in slot i,
+// run the cascade, keep the slot if it passes.  Here the same stream is evaluated speculatively in
+// batches: the host enumerates pyramid levels arithmetically (the NegReader state machine without the
+// pixels), the GPU (1) builds the INTER_LINEAR_EXACT levels, (2) gathers every window of the batch into
+// scratch evaluator slots, (3) builds their integral images with the training kernels (K1) — i.e. with
+// exactly the per-window arithmetic of setImage — and (4) runs the cascade with early exit, appending
+// surviving stream ordinals.  The host then applies the serial stopping rule to the ordered survivors,
+// copies the accepted windows into the training slots and leaves the reader state right behind the last
+// consumed window.  Evaluating windows past the stopping point is harmless: they are simply not consumed.
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstring>
+
 #include "cc_internal.h"
+
 namespace cc {
-int mine_free(cc_ctx*) { return CC_OK; }
+
+struct EvalView {
+  int ftype, P, ns_pad;
+  const int32_t* sum;
+  const int32_t* tilted;
+  const float* nf;
+  const float* hog;
+  const HaarTaps* haar_taps;
+  const LbpTaps* lbp_taps;
+  const HogTaps* hog_taps;
+};
+EvalView make_eval_view_store(const cc_ctx* ctx, const EvalStore& st);
+
+// ---- device-side feature evaluation (same arithmetic as cc_eval.cu / cc_boost.cu) ----------------
+__device__ __forceinline__ float m_haar_value(const HaarTaps& t, const EvalView& e, int s) {
+  const int32_t* base = (t.tilted() ? e.tilted : e.sum) + (size_t)(s >> 5) * e.P * TILE + (s & 31);
+  int acc = 0;
+  const int nt = t.ntaps();
+  for (int k = 0; k < nt; ++k) acc += tap_coef(t.w[k]) * base[(size_t)tap_off(t.w[k]) * TILE];
+  const float n = e.nf[s];
+  return n == 0.f ? 0.f : __fdiv_rn((float)acc, n);
 }
+__device__ __forceinline__ int m_lbp_code(const LbpTaps& t, const EvalView& e, int s) {
+  const int32_t* base = e.sum + (size_t)(s >> 5) * e.P * TILE + (s & 31);
+  int v[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) v[k] = base[(size_t)t.off[k] * TILE];
+  auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
+  const int c = cell(1, 1);
+  return (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
+         (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
+         (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
+}
+__device__ __forceinline__ float m_hog_value(const HogTaps& t, const EvalView& e, int comp, int s) {
+  const int bin = comp % 9, cell = comp / 9;
+  const size_t np = (size_t)e.ns_pad;
+  const float* ph = e.hog + (size_t)bin * e.P * np + s;
+  const float* pn = e.hog + (size_t)9 * e.P * np + s;
+  float res = __fadd_rn(__fsub_rn(__fsub_rn(ph[t.off[cell][0] * np], ph[t.off[cell][1] * np]), ph[t.off[cell][2] * np]), ph[t.off[cell][3] * np]);
+  float nrm = __fadd_rn(__fsub_rn(__fsub_rn(pn[t.off[0][0] * np], pn[t.off[1][1] * np]), pn[t.off[2][2] * np]), pn[t.off[3][3] * np]);
+  return res > 0.001f ? __fdiv_rn(res, __fadd_rn(nrm, 0.001f)) : 0.f;
+}
+__device__ __forceinline__ float m_eval_var(const EvalView& e, int var, int s) {
+  if (e.ftype == CC_FEATURE_HAAR) return m_haar_value(e.haar_taps[var], e, s);
+  if (e.ftype == CC_FEATURE_LBP) return (float)m_lbp_code(e.lbp_taps[var], e, s);
+  return m_hog_value(e.hog_taps[var / 36], e, var % 36, s);
+}
+
+// ---- batch description ------------------------------------------------------------------------------
+struct LevelDesc {
+  const uint8_t* src;      // background image in HBM
+  int sw, sh;              // source size
+  int lw, lh;              // level size
+  double scale_x, scale_y; // 1.0 / (lw / (double)sw), as cv::resize computes it
+  long long px_off;        // offset of this level in the batch level-pixel pool
+  int x0, y0, step_x, step_y, nx, ny;
+  long long w_skip;        // windows of this level that precede the batch (partial first level)
+  long long w_base;        // batch ordinal of the first window taken from this level
+  long long w_count;       // windows taken
+};
+
+// cv::resize(src, dst, INTER_LINEAR_EXACT), 8-bit single channel: 8.8 fixed-point coefficients per axis,
+// horizontal pass to 8.8, vertical to 16.16, round by +32768 >> 16.  Un-fused f64.
+__device__ __forceinline__ void lin_coef(double scale, int v, int src, int& ofs, int& c0, int& c1, int& mode) {
+  double f = __dsub_rn(__dmul_rn(scale, (double)v + 0.5), 0.5);
+  const int i = (int)floor(f);
+  f = __dsub_rn(f, (double)i);
+  if (i >= 0 && src > 1) {
+    if (i < src - 1) { ofs = i; c1 = __double2int_rn(__dmul_rn(f, 256.0)); c0 = 256 - c1; mode = 0; }
+    else { ofs = src - 1; c0 = 256; c1 = 0; mode = 2; }
+  } else { ofs = 0; c0 = 256; c1 = 0; mode = 1; }
+}
+
+__global__ void k_resize_levels(const LevelDesc* __restrict__ levels, int nlevels, long long total_px, uint8_t* __restrict__ pool) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total_px; p += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nlevels - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].px_off <= p) lo = mid; else hi = mid - 1; }
+    const LevelDesc& L = levels[lo];
+    const int q = (int)(p - L.px_off);
+    const int y = q / L.lw, x = q - y * L.lw;
+    int ox, cx0, cx1, mx, oy, cy0, cy1, my;
+    lin_coef(L.scale_x, x, L.sw, ox, cx0, cx1, mx);
+    lin_coef(L.scale_y, y, L.sh, oy, cy0, cy1, my);
+    auto hrow = [&](int row) -> uint32_t {
+      const uint8_t* s = L.src + (size_t)row * L.sw;
+      if (mx == 1) return (uint32_t)s[0] * 256u;
+      if (mx == 2) return (uint32_t)s[L.sw - 1] * 256u;
+      return (uint32_t)s[ox] * cx0 + (uint32_t)s[ox + 1] * cx1;
+    };
+    uint32_t val;
+    if (my == 1) val = hrow(0) * 256u;
+    else if (my == 2) val = hrow(L.sh - 1) * 256u;
+    else val = hrow(oy) * cy0 + hrow(oy + 1) * cy1;
+    pool[p] = (uint8_t)((val + 32768u) >> 16);
+  }
+}
+
+// copy every window of the batch out of its pyramid level into consecutive slots dst[first .. first+n)
+__global__ void k_gather_windows(const LevelDesc* __restrict__ levels, int nlevels, const uint8_t* __restrict__ pool, int W, int H,
+                                 long long nwin, uint8_t* __restrict__ dst) {
+  const int npx = W * H;
+  const long long total = nwin * npx;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long b = t / npx;
+    const int r = (int)(t - b * npx);
+    int lo = 0, hi = nlevels - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= b) lo = mid; else hi = mid - 1; }
+    const LevelDesc& L = levels[lo];
+    const long long k = b - L.w_base + L.w_skip;
+    const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
+    const int wy = r / W, wx = r - wy * W;
+    dst[t] = pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.lw + (L.x0 + ix * L.step_x + wx)];
+  }
+}
+
+// CvCascadeClassifier::predict(sampleIdx): every stage's CvCascadeBoost::predict with early exit
+// (src/cascadeclassifier.cpp:297-306, src/boost.cpp:461-477, src/o_cvcascadeboosttree.cpp:16-39)
+__global__ void k_cascade_eval(EvalView e, const DevNode* __restrict__ nodes, const int* __restrict__ tree_first,
+                               const DevStageRef* __restrict__ stages, int nstages, int n, unsigned int* __restrict__ surv_count,
+                               unsigned int* __restrict__ surv, unsigned int surv_cap) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  bool pass = true;
+  for (int st = 0; st < nstages && pass; ++st) {
+    const DevStageRef sr = stages[st];
+    double sum = 0;
+    for (int t = 0; t < sr.num_trees; ++t) {
+      const DevNode* tree = nodes + tree_first[sr.first_tree + t];
+      int nd = 0;
+      while (tree[nd].left >= 0) {
+        const float val = m_eval_var(e, tree[nd].var_idx, s);
+        bool left;
+        if (e.ftype == CC_FEATURE_LBP) { const int c = (int)val; left = (tree[nd].subset[c >> 5] & (1 << (c & 31))) != 0; }
+        else left = val <= tree[nd].c;
+        nd = left ? tree[nd].left : tree[nd].right;
+      }
+      sum += tree[nd].value;
+    }
+    if (sum < (double)(sr.threshold - 0.00001F)) pass = false;
+  }
+  // ordered compaction inside the warp (ballot), one atomic per warp; the host sorts the short list
+  const unsigned m = __ballot_sync(__activemask(), pass);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(surv_count, (unsigned)__popc(m));
+    base = __shfl_sync(__activemask(), base, leader);
+    if (pass) {
+      const unsigned pos = base + __popc(m & ((1u << lane) - 1u));
+      if (pos < surv_cap) surv[pos] = (unsigned)s;
+    }
+  }
+}
+
+__global__ void k_copy_slots(const uint8_t* __restrict__ src, const unsigned int* __restrict__ which, int n, int npx, uint8_t* __restrict__ dst,
+                             uint8_t* __restrict__ labels, int label) {
+  const long long total = (long long)n * npx;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / npx);
+    const int r = (int)(t - (long long)i * npx);
+    dst[t] = src[(size_t)which[i] * npx + r];
+    if (r == 0) labels[i] = (uint8_t)label;
+  }
+}
+
+// ---- host-side state ----------------------------------------------------------------------------------
+struct BgImage { int w = 0, h = 0; uint8_t* d_px = nullptr; };
+
+struct MineState {
+  std::vector<BgImage> bgs;
+  // cascade
+  std::vector<DevNode> nodes;
+  std::vector<int> tree_first;
+  std::vector<DevStageRef> stages;
+  DevNode* d_nodes = nullptr;
+  int* d_tree_first = nullptr;
+  DevStageRef* d_stages = nullptr;
+  // scratch
+  EvalStore scratch;
+  int scratch_cap = 0;
+  uint8_t* d_pool = nullptr;
+  size_t pool_cap = 0;
+  LevelDesc* d_levels = nullptr;
+  int levels_cap = 0;
+  unsigned int* d_surv = nullptr;      // [0] = counter, [1..cap] = list
+  unsigned int surv_cap = 0;
+  unsigned int* h_surv = nullptr;      // pinned mirror
+};
+
+static void free_cascade(MineState* m) {
+  cudaFree(m->d_nodes); cudaFree(m->d_tree_first); cudaFree(m->d_stages);
+  m->d_nodes = nullptr; m->d_tree_first = nullptr; m->d_stages = nullptr;
+  m->nodes.clear(); m->tree_first.clear(); m->stages.clear();
+}
+static void free_scratch(MineState* m) {
+  store_free(m->scratch);
+  m->scratch_cap = 0;
+  cudaFree(m->d_pool); m->d_pool = nullptr; m->pool_cap = 0;
+  cudaFree(m->d_levels); m->d_levels = nullptr; m->levels_cap = 0;
+  cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
+  cudaFreeHost(m->h_surv); m->h_surv = nullptr;
+}
+
+int mine_free(cc_ctx* ctx) {
+  MineState* m = ctx->mine;
+  if (!m) return CC_OK;
+  for (auto& b : m->bgs) cudaFree(b.d_px);
+  free_cascade(m);
+  free_scratch(m);
+  delete m;
+  ctx->mine = nullptr;
+  return CC_OK;
+}
+
+static MineState* mine_state(cc_ctx* ctx) {
+  if (!ctx->mine) ctx->mine = new MineState();
+  return ctx->mine;
+}
+
+static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, int nlevels) {
+  if (nwin > m->scratch_cap) {
+    store_free(m->scratch);
+    CC_CHECK(store_alloc(ctx, m->scratch, nwin));
+    m->scratch_cap = nwin;
+  }
+  if (pool_px > m->pool_cap) {
+    cudaFree(m->d_pool);
+    CC_CUDA(cudaMalloc(&m->d_pool, pool_px));
+    m->pool_cap = pool_px;
+  }
+  if (nlevels > m->levels_cap) {
+    cudaFree(m->d_levels);
+    CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * nlevels));
+    m->levels_cap = nlevels;
+  }
+  if ((unsigned)nwin > m->surv_cap) {
+    cudaFree(m->d_surv); cudaFreeHost(m->h_surv);
+    CC_CUDA(cudaMalloc(&m->d_surv, sizeof(unsigned) * ((size_t)nwin + 1)));
+    CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * ((size_t)nwin + 1)));
+    m->surv_cap = (unsigned)nwin;
+  }
+  return CC_OK;
+}
+
+// ---- NegReader state machine without the pixels (src/imagestorage.cpp:57-126) -------------------------
+struct NegStream {
+  const std::vector<BgImage>* bgs;
+  int W, H;
+  long long last = 0, round = 0;
+  int src = -1;                 // index of the current source image
+  int pointX = 0, pointY = 0, offX = 0, offY = 0;
+  int lw = 0, lh = 0;           // current level size (0: no image loaded yet)
+  float scale = 1.0f;
+  static constexpr float scaleFactor = 1.4142135623730950488016887242097F;
+  static constexpr float stepFactor = 0.5F;
+
+  bool nextImg() {
+    const long long count = (long long)bgs->size();
+    int ox = 0, oy = 0;
+    bool found = false;
+    for (long long i = 0; i < count; ++i) {
+      src = (int)last;
+      last++;
+      const BgImage& im = (*bgs)[src];
+      round += last / count;
+      round = round % ((long long)W * H);
+      last %= count;
+      ox = std::min((int)round % W, im.w - W);
+      oy = std::min((int)round / W, im.h - H);
+      if (ox >= 0 && oy >= 0) { found = true; break; }
+    }
+    if (!found) return false;    // the reference would read out of bounds here; refuse instead
+    pointX = offX = ox; pointY = offY = oy;
+    const BgImage& im = (*bgs)[src];
+    scale = std::max(((float)W + pointX) / ((float)im.w), ((float)H + pointY) / ((float)im.h));
+    lw = (int)(scale * im.w + 0.5F);
+    lh = (int)(scale * im.h + 0.5F);
+    return true;
+  }
+  int stepX() const { return (int)(stepFactor * W); }
+  int stepY() const { return (int)(stepFactor * H); }
+  bool canStepX(int x) const { return (int)(x + (1.0F + stepFactor) * W) < lw; }
+  bool canStepY(int y) const { return (int)(y + (1.0F + stepFactor) * H) < lh; }
+  int countX() const { int n = 1, x = offX; while (canStepX(x)) { x += stepX(); ++n; } return n; }
+  int countY() const { int n = 1, y = offY; while (canStepY(y)) { y += stepY(); ++n; } return n; }
+  // after the last window of the current level: next level of the same image or the next image
+  bool nextLevel() {
+    pointX = offX; pointY = offY;
+    scale *= scaleFactor;
+    if (scale <= 1.0F) {
+      const BgImage& im = (*bgs)[src];
+      lw = (int)(scale * im.w);
+      lh = (int)(scale * im.h);
+      return true;
+    }
+    return nextImg();
+  }
+};
+
+static void stream_from_state(NegStream& ns, const cc_reader_state& st, int nimg) {
+  ns.last = st.last; ns.round = st.round;
+  ns.pointX = st.point_x; ns.pointY = st.point_y; ns.offX = st.offset_x; ns.offY = st.offset_y;
+  ns.lw = st.level_w; ns.lh = st.level_h; ns.scale = st.scale;
+  ns.src = nimg > 0 ? (int)((st.last + nimg - 1) % nimg) : -1;
+}
+static void state_from_stream(const NegStream& ns, cc_reader_state* st) {
+  st->last = ns.last; st->round = ns.round;
+  st->point_x = ns.pointX; st->point_y = ns.pointY; st->offset_x = ns.offX; st->offset_y = ns.offY;
+  st->level_w = ns.lw; st->level_h = ns.lh; st->scale = ns.scale; st->pad = 0;
+}
+
+static void fill_level(const NegStream& ns, LevelDesc& L) {
+  const BgImage& im = (*ns.bgs)[ns.src];
+  L.src = im.d_px; L.sw = im.w; L.sh = im.h; L.lw = ns.lw; L.lh = ns.lh;
+  L.scale_x = 1.0 / ((double)ns.lw / (double)im.w);
+  L.scale_y = 1.0 / ((double)ns.lh / (double)im.h);
+  L.x0 = ns.offX; L.y0 = ns.offY; L.step_x = ns.stepX(); L.step_y = ns.stepY();
+  L.nx = ns.countX(); L.ny = ns.countY();
+}
+
+// upload the cascade as flat arrays
+static int upload_cascade(cc_ctx* ctx, MineState* m, const cc_stage* stages, int n) {
+  free_cascade(m);
+  for (int s = 0; s < n; ++s) {
+    DevStageRef sr;
+    sr.first_tree = (int)m->tree_first.size();
+    sr.num_trees = stages[s].num_weak;
+    sr.threshold = stages[s].threshold;
+    for (int t = 0; t < stages[s].num_weak; ++t) {
+      m->tree_first.push_back((int)m->nodes.size());
+      const cc_tree& tr = stages[s].trees[t];
+      for (int i = 0; i < tr.num_nodes; ++i) {
+        DevNode d;
+        d.left = tr.nodes[i].left; d.right = tr.nodes[i].right; d.var_idx = tr.nodes[i].var_idx; d.c = tr.nodes[i].c;
+        std::memcpy(d.subset, tr.nodes[i].subset, sizeof(d.subset));
+        d.value = tr.nodes[i].value;
+        m->nodes.push_back(d);
+      }
+    }
+    m->stages.push_back(sr);
+  }
+  if (!m->nodes.empty()) {
+    CC_CUDA(cudaMalloc(&m->d_nodes, sizeof(DevNode) * m->nodes.size()));
+    CC_CUDA(cudaMalloc(&m->d_tree_first, sizeof(int) * m->tree_first.size()));
+    CC_CUDA(cudaMalloc(&m->d_stages, sizeof(DevStageRef) * m->stages.size()));
+    CC_CUDA(cudaMemcpyAsync(m->d_nodes, m->nodes.data(), sizeof(DevNode) * m->nodes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CC_CUDA(cudaMemcpyAsync(m->d_tree_first, m->tree_first.data(), sizeof(int) * m->tree_first.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CC_CUDA(cudaMemcpyAsync(m->d_stages, m->stages.data(), sizeof(DevStageRef) * m->stages.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return CC_OK;
+}
+
+static int grid_for(cc_ctx* ctx, long long total, int threads) {
+  return (int)std::max<long long>(1, std::min<long long>((total + threads - 1) / threads, (long long)ctx->sm_count * 32));
+}
+
+// Evaluate `n` windows that sit in scratch slots [0, n): integrals + cascade; returns sorted survivors.
+static int eval_scratch(cc_ctx* ctx, MineState* m, int n, std::vector<unsigned>& survivors) {
+  survivors.clear();
+  if (n == 0) return CC_OK;
+  if (m->stages.empty()) {
+    survivors.resize(n);
+    for (int i = 0; i < n; ++i) survivors[i] = (unsigned)i;
+    return CC_OK;
+  }
+  CC_CHECK(launch_integrals(ctx, m->scratch, 0, n));
+  {
+    ScopedTimer tm(ctx, "mine", 1);
+    CC_CUDA(cudaMemsetAsync(m->d_surv, 0, sizeof(unsigned), ctx->stream));
+    k_cascade_eval<<<(n + 127) / 128, 128, 0, ctx->stream>>>(make_eval_view_store(ctx, m->scratch), m->d_nodes, m->d_tree_first, m->d_stages,
+                                                             (int)m->stages.size(), n, m->d_surv, m->d_surv + 1, m->surv_cap);
+    CC_CUDA(cudaGetLastError());
+  }
+  CC_CUDA(cudaMemcpyAsync(m->h_surv, m->d_surv, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const unsigned cnt = std::min(m->h_surv[0], m->surv_cap);
+  if (cnt) {
+    CC_CUDA(cudaMemcpyAsync(m->h_surv + 1, m->d_surv + 1, sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    survivors.assign(m->h_surv + 1, m->h_surv + 1 + cnt);
+    std::sort(survivors.begin(), survivors.end());
+  }
+  return CC_OK;
+}
+
+// copy accepted scratch windows into training slots [first, first+n) and build their integrals
+static int accept_windows(cc_ctx* ctx, MineState* m, const unsigned* which, int n, int first, int label) {
+  if (n == 0) return CC_OK;
+  const int npx = ctx->W * ctx->H;
+  // reuse the survivor device buffer as the index list
+  CC_CUDA(cudaMemcpyAsync(m->d_surv + 1, which, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    ScopedTimer tm(ctx, "mine", 1);
+    k_copy_slots<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(m->scratch.d_imgs, m->d_surv + 1, n, npx,
+                                                                                 ctx->d_imgs + (size_t)first * npx, ctx->d_labels + first, label);
+    CC_CUDA(cudaGetLastError());
+  }
+  ctx->precalc_valid = false;
+  CC_CHECK(launch_integrals(ctx, main_store(ctx), first, n));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));   // `which` (host) and d_surv are reused by the caller
+  return CC_OK;
+}
+
+// build one batch: whole levels (or a bounded part of one) starting at the stream position
+struct Batch {
+  std::vector<LevelDesc> levels;
+  std::vector<NegStream> after;     // stream state right after the last window of each level part (level granularity)
+  long long nwin = 0;
+  size_t pool_px = 0;
+};
+
+}  // namespace cc
+
 using namespace cc;
+
 extern "C" {
-int cc_bg_clear(cc_ctx*) { set_error("mining not built yet"); return CC_ERR_UNSUPPORTED; }
-int cc_bg_register(cc_ctx*, const uint8_t*, int, int) { set_error("mining not built yet"); return CC_ERR_UNSUPPORTED; }
-int cc_bg_count(cc_ctx*) { return 0; }
-int cc_cascade_set_stages(cc_ctx*, const cc_stage*, int) { set_error("mining not built yet"); return CC_ERR_UNSUPPORTED; }
-int cc_mine_negatives(cc_ctx*, int, int, double, cc_reader_state*, int64_t*, int32_t*) { set_error("mining not built yet"); return CC_ERR_UNSUPPORTED; }
-int cc_mine_positives(cc_ctx*, const uint8_t*, int, int, int32_t*, int64_t*, int32_t*) { set_error("mining not built yet"); return CC_ERR_UNSUPPORTED; }
-int cc_mine_scan(cc_ctx*, int, int, int64_t*, int64_t*) { set_error("mining not built yet"); return CC_ERR_UNSUPPORTED; }
+
+int cc_bg_clear(cc_ctx* ctx) {
+  CC_REQUIRE(ctx, CC_ERR_BAD_ARG, "cc_bg_clear: null ctx");
+  MineState* m = mine_state(ctx);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  for (auto& b : m->bgs) cudaFree(b.d_px);
+  m->bgs.clear();
+  return CC_OK;
 }
+
+int cc_bg_register(cc_ctx* ctx, const uint8_t* host_gray, int w, int h) {
+  CC_REQUIRE(ctx && host_gray && w > 0 && h > 0, CC_ERR_BAD_ARG, "cc_bg_register: bad arguments");
+  MineState* m = mine_state(ctx);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  BgImage b;
+  b.w = w; b.h = h;
+  CC_CUDA(cudaMalloc(&b.d_px, (size_t)w * h));
+  CC_CUDA(cudaMemcpyAsync(b.d_px, host_gray, (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  m->bgs.push_back(b);
+  return CC_OK;
+}
+
+int cc_bg_count(cc_ctx* ctx) { return ctx && ctx->mine ? (int)ctx->mine->bgs.size() : 0; }
+
+int cc_cascade_set_stages(cc_ctx* ctx, const cc_stage* stages, int n) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_cascade_set_stages: evaluator not initialised");
+  CC_REQUIRE(n >= 0 && (n == 0 || stages), CC_ERR_BAD_ARG, "cc_cascade_set_stages: bad arguments");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  return upload_cascade(ctx, mine_state(ctx), stages, n);
+}
+
+int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, cc_reader_state* state, int64_t* consumed_out, int32_t* got_out) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_mine_negatives: evaluator not initialised");
+  CC_REQUIRE(state && consumed_out && got_out, CC_ERR_BAD_ARG, "cc_mine_negatives: null argument");
+  CC_REQUIRE(first_slot >= 0 && count >= 0 && first_slot + count <= ctx->max_samples, CC_ERR_BAD_ARG,
+             "cc_mine_negatives: slots [%d,%d) exceed maxSampleCount %d", first_slot, first_slot + count, ctx->max_samples);
+  MineState* m = mine_state(ctx);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  *consumed_out = 0; *got_out = 0;
+  if (count == 0) return CC_OK;
+  CC_REQUIRE(!m->bgs.empty(), CC_ERR_STATE, "cc_mine_negatives: no background images registered");
+  const int W = ctx->W, H = ctx->H, npx = W * H;
+  NegStream ns;
+  ns.bgs = &m->bgs; ns.W = W; ns.H = H;
+  stream_from_state(ns, *state, (int)m->bgs.size());
+
+  long long consumed = 0;
+  int got = 0;
+  double accept_rate = m->stages.empty() ? 1.0 : 0.0;   // running estimate
+  const long long max_batch = ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  bool stream_ok = true;
+  if (ns.lw == 0) stream_ok = ns.nextImg();             // first get(): img.empty() -> nextImg()
+  std::vector<unsigned> survivors, accepted;
+
+  while (got < count && stream_ok) {
+    // serial rule, checked before every window: stop when (getcount+1)/consumed <= minRatio
+    if (consumed != 0 && ((double)got + 1) / (double)consumed <= min_ratio) break;
+    // ---- assemble a batch ----
+    long long want = 32768;
+    if (accept_rate > 0) want = (long long)std::min<double>((double)max_batch, std::max(4096.0, 1.25 * (count - got) / accept_rate + 1024));
+    else want = std::min<long long>(max_batch, 65536);
+    want = std::min(want, max_batch);
+    Batch bt;
+    NegStream cur = ns;
+    bool more = true;
+    while (bt.nwin < want && more) {
+      LevelDesc L;
+      fill_level(cur, L);
+      const int ix0 = (cur.pointX - cur.offX) / std::max(1, L.step_x), iy0 = (cur.pointY - cur.offY) / std::max(1, L.step_y);
+      L.w_skip = (long long)iy0 * L.nx + ix0;
+      const long long avail = (long long)L.nx * L.ny - L.w_skip;
+      L.w_count = std::min(avail, max_batch - bt.nwin);
+      L.w_base = bt.nwin;
+      L.px_off = (long long)bt.pool_px;
+      bt.pool_px += (size_t)L.lw * L.lh;
+      bt.nwin += L.w_count;
+      NegStream nxt = cur;
+      if (L.w_count == avail) {
+        more = nxt.nextLevel();
+      } else {
+        const long long k = L.w_skip + L.w_count;      // first window not taken
+        nxt.pointY = cur.offY + (int)(k / L.nx) * L.step_y;
+        nxt.pointX = cur.offX + (int)(k % L.nx) * L.step_x;
+      }
+      bt.levels.push_back(L);
+      bt.after.push_back(nxt);
+      cur = nxt;
+      if (L.w_count < avail) break;
+    }
+    const int nwin = (int)bt.nwin;
+    // ---- GPU: levels, gather, integrals, cascade ----
+    const bool direct = m->stages.empty();       // stage 0: every window passes, gather straight into the training slots
+    CC_CHECK(ensure_scratch(ctx, m, direct ? 1 : nwin, bt.pool_px, (int)bt.levels.size()));
+    CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
+    long long take_direct = 0;
+    {
+      ScopedTimer tm(ctx, "mine", 2);
+      k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
+      CC_CUDA(cudaGetLastError());
+      if (direct) {
+        // how many windows does the serial rule consume?  all pass, so got grows with consumed
+        take_direct = std::min<long long>(nwin, count - got);
+        k_gather_windows<<<grid_for(ctx, take_direct * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, take_direct,
+                                                                                       ctx->d_imgs + (size_t)(first_slot + got) * npx);
+      } else {
+        k_gather_windows<<<grid_for(ctx, (long long)nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
+      }
+      CC_CUDA(cudaGetLastError());
+    }
+    long long stop_after = -1;     // batch ordinal of the last consumed window (-1: none consumed)
+    if (direct) {
+      // with no stages every window passes; the ratio rule can only trigger if minRatio >= 1
+      long long taken = 0;
+      while (taken < take_direct) {
+        if (consumed != 0 && ((double)got + 1) / (double)consumed <= min_ratio) break;
+        consumed++; got++; taken++;
+      }
+      CC_CUDA(cudaMemsetAsync(ctx->d_labels + first_slot + got - taken, 0, (size_t)taken, ctx->stream));
+      ctx->precalc_valid = false;
+      CC_CHECK(launch_integrals(ctx, main_store(ctx), first_slot + got - (int)taken, (int)taken));
+      CC_CUDA(cudaStreamSynchronize(ctx->stream));
+      stop_after = taken - 1;
+      if (taken < take_direct) { /* ratio rule fired */ }
+      if (got < count && taken == nwin) { ns = bt.after.back(); stream_ok = more; continue; }
+    } else {
+      CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
+      // ---- serial stopping rule over the ordered survivors ----
+      accepted.clear();
+      long long pos = 0;            // next unconsumed batch ordinal
+      bool stopped = false;
+      size_t si = 0;
+      // smallest value c >= max(c_from, 1) of `consumed` at which the reference's check
+      // (getcount+1)/consumed <= minimumAcceptanceRatio holds (cascadeclassifier.cpp:337)
+      auto first_fire = [&](int g, long long c_from) -> long long {
+        if (!(min_ratio > 0)) return INT64_MAX;
+        long long c = std::max<long long>(1, c_from);
+        const double c0 = std::ceil(((double)g + 1) / min_ratio);
+        if (c0 > 9e18) return INT64_MAX;
+        const long long guess = (long long)c0 - 2;
+        if (guess > c) c = guess;
+        while (!(((double)g + 1) / (double)c <= min_ratio)) ++c;
+        return c;
+      };
+      while (pos < nwin) {
+        const long long nextPass = si < survivors.size() ? (long long)survivors[si] : (long long)nwin;
+        const long long gap = nextPass - pos;               // failing windows before the next survivor
+        const long long fire = first_fire(got, consumed);
+        if (fire <= consumed + gap) {                       // the rule fires before a window of this gap (or before the survivor)
+          const long long adv = fire - consumed;
+          consumed += adv; pos += adv;
+          stopped = true;
+          break;
+        }
+        consumed += gap;
+        pos = nextPass;
+        if (pos >= nwin) break;
+        consumed++; got++;                                  // window `pos` passes the cascade
+        accepted.push_back((unsigned)pos);
+        pos++; si++;
+        if (got == count) { stopped = true; break; }
+      }
+      stop_after = pos - 1;
+      CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
+      if (nwin > 0) accept_rate = std::max((double)survivors.size() / (double)nwin, 1e-9);
+      if (!stopped) { ns = bt.after.back(); stream_ok = more; continue; }
+    }
+    // ---- stopped inside this batch: reader state right after window `stop_after` ----
+    if (stop_after < 0) {
+      // nothing consumed from this batch: state unchanged
+    } else {
+      // find the level part containing stop_after
+      size_t li = 0;
+      while (li + 1 < bt.levels.size() && bt.levels[li + 1].w_base <= stop_after) ++li;
+      const LevelDesc& L = bt.levels[li];
+      const long long k = stop_after - L.w_base + L.w_skip + 1;          // index (within the level) of the next window
+      if (k >= (long long)L.nx * L.ny) {
+        ns = bt.after[li];                                               // next level / image (already advanced)
+        if (li + 1 == bt.levels.size()) stream_ok = more;
+      } else {
+        // same level: rebuild the state of that level, then position the point
+        NegStream st = li == 0 ? ns : bt.after[li - 1];
+        st.pointY = st.offY + (int)(k / L.nx) * L.step_y;
+        st.pointX = st.offX + (int)(k % L.nx) * L.step_x;
+        ns = st;
+      }
+    }
+    break;
+  }
+  state_from_stream(ns, state);
+  *consumed_out = consumed;
+  *got_out = got;
+  return CC_OK;
+}
+
+int cc_mine_positives(cc_ctx* ctx, const uint8_t* host_vec, int vec_count, int count, int32_t* vec_pos, int64_t* consumed_out, int32_t* got_out) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_mine_positives: evaluator not initialised");
+  CC_REQUIRE(host_vec && vec_pos && consumed_out && got_out, CC_ERR_BAD_ARG, "cc_mine_positives: null argument");
+  CC_REQUIRE(count >= 0 && count <= ctx->max_samples, CC_ERR_BAD_ARG, "cc_mine_positives: count %d exceeds maxSampleCount %d", count, ctx->max_samples);
+  MineState* m = mine_state(ctx);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  const int npx = ctx->W * ctx->H;
+  long long consumed = 0;
+  int got = 0;
+  int pos = *vec_pos;
+  const int max_batch = ctx->ftype == CC_FEATURE_HOG ? 8192 : 65536;
+  std::vector<unsigned> survivors, accepted;
+  while (got < count) {
+    if (pos >= vec_count) {
+      *vec_pos = pos; *consumed_out = consumed; *got_out = got;
+      set_error("Can not get new positive sample. The most possible reason is insufficient count of samples in given vec-file.");
+      return CC_ERR_BAD_ARG;
+    }
+    const int nwin = std::min(std::min(max_batch, vec_count - pos), std::max(1024, (count - got) + (count - got) / 8 + 64));
+    CC_CHECK(ensure_scratch(ctx, m, nwin, 1, 1));
+    CC_CUDA(cudaMemcpyAsync(m->scratch.d_imgs, host_vec + (size_t)pos * npx, (size_t)nwin * npx, cudaMemcpyHostToDevice, ctx->stream));
+    CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
+    accepted.clear();
+    long long last_consumed = -1;
+    for (size_t si = 0; si < survivors.size() && got < count; ++si) {
+      accepted.push_back(survivors[si]);
+      got++;
+      last_consumed = survivors[si];
+    }
+    if (got < count) last_consumed = nwin - 1;          // everything in the batch was consumed
+    consumed += last_consumed + 1;
+    pos += (int)(last_consumed + 1);
+    CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), got - (int)accepted.size(), 1));
+  }
+  *vec_pos = pos; *consumed_out = consumed; *got_out = got;
+  return CC_OK;
+}
+
+// Host-only: advance the NegReader state machine by `nwindows` windows over images of the given sizes
+// (no pixels, no GPU).  Used by the CPU tests to pin the stream enumeration against the oracle, and by
+// callers that need to skip ahead.  window_xywh (optional) receives x, y, level_w, level_h and the source
+// image index of the last consumed window.
+int cc_reader_advance(const int32_t* img_w, const int32_t* img_h, int nimg, int win_w, int win_h, cc_reader_state* state,
+                      int64_t nwindows, int32_t* window_xywh) {
+  CC_REQUIRE(img_w && img_h && nimg > 0 && state && nwindows >= 0, CC_ERR_BAD_ARG, "cc_reader_advance: bad arguments");
+  std::vector<BgImage> imgs(nimg);
+  for (int i = 0; i < nimg; ++i) { imgs[i].w = img_w[i]; imgs[i].h = img_h[i]; }
+  NegStream ns;
+  ns.bgs = &imgs; ns.W = win_w; ns.H = win_h;
+  stream_from_state(ns, *state, nimg);
+  bool ok = true;
+  if (ns.lw == 0 && nwindows > 0) ok = ns.nextImg();
+  int64_t left = nwindows;
+  while (left > 0 && ok) {
+    const int nx = ns.countX(), ny = ns.countY();
+    const int sx = std::max(1, ns.stepX()), sy = std::max(1, ns.stepY());
+    const int64_t k0 = (int64_t)((ns.pointY - ns.offY) / sy) * nx + (ns.pointX - ns.offX) / sx;
+    const int64_t avail = (int64_t)nx * ny - k0;
+    const int64_t take = std::min(avail, left);
+    const int64_t klast = k0 + take - 1;
+    if (window_xywh) {
+      window_xywh[0] = ns.offX + (int)(klast % nx) * sx; window_xywh[1] = ns.offY + (int)(klast / nx) * sy;
+      window_xywh[2] = ns.lw; window_xywh[3] = ns.lh; window_xywh[4] = ns.src;
+    }
+    left -= take;
+    if (take == avail) ok = ns.nextLevel();
+    else { const int64_t k = k0 + take; ns.pointY = ns.offY + (int)(k / nx) * sy; ns.pointX = ns.offX + (int)(k % nx) * sx; }
+  }
+  state_from_stream(ns, state);
+  CC_REQUIRE(left == 0, CC_ERR_BAD_ARG, "cc_reader_advance: no usable background image (stream ended with %lld windows left)", (long long)left);
+  return CC_OK;
+}
+
+int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* survivors_out) {
+  CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_mine_scan: evaluator not initialised");
+  MineState* m = mine_state(ctx);
+  CC_REQUIRE(img0 >= 0 && nimg > 0 && img0 + nimg <= (int)m->bgs.size(), CC_ERR_BAD_ARG, "cc_mine_scan: image range out of bounds");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  const int W = ctx->W, H = ctx->H, npx = W * H;
+  const long long max_batch = ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  long long total = 0, surv = 0;
+  std::vector<unsigned> survivors;
+  // every image from its first level (round 0 offsets), independent of the reader state
+  std::vector<BgImage> one(1);
+  Batch bt;
+  auto flush = [&]() -> int {
+    if (bt.nwin == 0) return CC_OK;
+    const int nwin = (int)bt.nwin;
+    CC_CHECK(ensure_scratch(ctx, m, nwin, bt.pool_px, (int)bt.levels.size()));
+    CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
+    {
+      ScopedTimer tm(ctx, "mine", 2);
+      k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
+      k_gather_windows<<<grid_for(ctx, (long long)nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
+      CC_CUDA(cudaGetLastError());
+    }
+    CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
+    total += nwin; surv += (long long)survivors.size();
+    bt = Batch();
+    return CC_OK;
+  };
+  for (int i = img0; i < img0 + nimg; ++i) {
+    one[0] = m->bgs[i];
+    NegStream s;
+    s.bgs = &one; s.W = W; s.H = H;
+    if (!s.nextImg()) continue;
+    bool more = true;
+    while (more) {
+      LevelDesc L;
+      fill_level(s, L);
+      long long done = 0;
+      const long long all = (long long)L.nx * L.ny;
+      while (done < all) {
+        if (bt.nwin >= max_batch) CC_CHECK(flush());
+        LevelDesc part = L;
+        part.w_skip = done;
+        part.w_count = std::min(all - done, max_batch - bt.nwin);
+        part.w_base = bt.nwin;
+        part.px_off = (long long)bt.pool_px;
+        bt.pool_px += (size_t)L.lw * L.lh;
+        bt.nwin += part.w_count;
+        bt.levels.push_back(part);
+        done += part.w_count;
+      }
+      // next level of the same image only
+      s.scale *= s.scaleFactor;
+      if (s.scale <= 1.0F) { s.lw = (int)(s.scale * one[0].w); s.lh = (int)(s.scale * one[0].h); } else more = false;
+    }
+  }
+  CC_CHECK(flush());
+  if (windows) *windows = total;
+  if (survivors_out) *survivors_out = surv;
+  return CC_OK;
+}
+
+}  // extern "C"

@@ -51,13 +51,13 @@ __device__ __forceinline__ int haar_acc(const uint32_t (&w)[HAAR_MAX_TAPS], cons
   return acc;
 }
 
-constexpr int PRECALC_THREADS = 256;
+constexpr int PRECALC_THREADS = 1024;
 
+// taps: compact list of this launch (one plane), w[11] of every entry = global feature index
 template <int TILES_PER_CTA>
 __global__ void __launch_bounds__(PRECALC_THREADS, 1)
 k_precalc_haar(const int32_t* __restrict__ plane_tiles, const float* __restrict__ nf, const HaarTaps* __restrict__ taps,
-               const int* __restrict__ rows, int nrows_launch, int rows_per_chunk, int row_base, float* __restrict__ fval,
-               int n_stride, int P, int ntiles_used) {
+               int nrows_launch, int rows_per_chunk, int row_base, float* __restrict__ fval, int n_stride, int P, int ntiles_used) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   int32_t* stile = reinterpret_cast<int32_t*>(smem_raw);                      // [TILES][P][32]
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TILES_PER_CTA * P * TILE * sizeof(int32_t));
@@ -72,21 +72,24 @@ k_precalc_haar(const int32_t* __restrict__ plane_tiles, const float* __restrict_
     for (int k = 0; k < ntl; ++k) bulk_g2s(stile + (size_t)k * P * TILE, plane_tiles + (size_t)(tile0 + k) * P * TILE, tile_bytes, bar);
   }
   __syncthreads();
-  mbar_wait(bar, 0);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PRECALC_THREADS / 32;
+  const int r_begin = blockIdx.y * rows_per_chunk;
+  const int r_end = min(r_begin + rows_per_chunk, nrows_launch);
+  int r = r_begin + warp;
+  // software pipeline: the tap words of the next feature are in flight while this one is evaluated
+  uint4 a = make_uint4(0, 0, 0, 0), b = a, c = a;
+  if (r < r_end) { const uint4* tp = reinterpret_cast<const uint4*>(taps + r); a = __ldg(tp); b = __ldg(tp + 1); c = __ldg(tp + 2); }
   float nfv[TILES_PER_CTA];
 #pragma unroll
   for (int k = 0; k < TILES_PER_CTA; ++k) nfv[k] = (k < ntl) ? nf[(tile0 + k) * TILE + lane] : 0.f;
+  mbar_wait(bar, 0);
 
-  const int r_begin = blockIdx.y * rows_per_chunk;
-  const int r_end = min(r_begin + rows_per_chunk, nrows_launch);
-  for (int r = r_begin + warp; r < r_end; r += nwarps) {
-    const int f = rows[r];
-    const uint4* tp = reinterpret_cast<const uint4*>(taps + f);
-    const uint4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+  for (; r < r_end; r += nwarps) {
     const uint32_t w[HAAR_MAX_TAPS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
-    const int nt = (int)((a.x >> 24) & 15u);
+    if (r + nwarps < r_end) { const uint4* tp = reinterpret_cast<const uint4*>(taps + r + nwarps); a = __ldg(tp); b = __ldg(tp + 1); c = __ldg(tp + 2); }
+    const int nt = (int)((w[0] >> 24) & 15u);
+    const int f = (int)w[11];
     float* out = fval + (size_t)(f - row_base) * n_stride + tile0 * TILE + lane;
 #pragma unroll
     for (int k = 0; k < TILES_PER_CTA; ++k) {
@@ -100,20 +103,21 @@ k_precalc_haar(const int32_t* __restrict__ plane_tiles, const float* __restrict_
           default: {
             acc = 0;
 #pragma unroll
-            for (int q = 0; q < HAAR_MAX_TAPS; ++q)
+            for (int q = 0; q < 10; ++q)
               if (q < nt) acc += tap_coef(w[q]) * tl[tap_off(w[q]) * TILE];
           }
         }
         const float v = nfv[k] == 0.f ? 0.f : __fdiv_rn((float)acc, nfv[k]);
-        out[k * TILE] = v;
+        __stcs(out + k * TILE, v);      // streaming store: the fval matrix is not re-read by this kernel
       }
     }
   }
 }
 
 // K2 / LBP: same tiling; 16 corner taps -> 9 cell sums -> 8-bit code (lbpfeatures.h:70-83).
+constexpr int LBP_THREADS = 512;
 template <int TILES_PER_CTA>
-__global__ void __launch_bounds__(PRECALC_THREADS, 1)
+__global__ void __launch_bounds__(LBP_THREADS, 1)
 k_precalc_lbp(const int32_t* __restrict__ sum_tiles, const LbpTaps* __restrict__ taps, int row_first, int nrows_launch,
               int rows_per_chunk, uint8_t* __restrict__ fcode, int n_stride, int P, int ntiles_used) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -130,7 +134,7 @@ k_precalc_lbp(const int32_t* __restrict__ sum_tiles, const LbpTaps* __restrict__
   }
   __syncthreads();
   mbar_wait(bar, 0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PRECALC_THREADS / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = LBP_THREADS / 32;
   const int r_begin = blockIdx.y * rows_per_chunk;
   const int r_end = min(r_begin + rows_per_chunk, nrows_launch);
   for (int r = r_begin + warp; r < r_end; r += nwarps) {
@@ -201,6 +205,9 @@ k_precalc_hog(const float* __restrict__ planes, const HogTaps* __restrict__ taps
 // ------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 512;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_RADIX = 16;      // 4-bit digits, 8 passes
+constexpr int SORT_CNT_STRIDE = SORT_THREADS + SORT_THREADS / 16;   // one pad word per 16 counters
+__device__ __forceinline__ int cnt_index(int d, int t) { return d * SORT_CNT_STRIDE + t + (t >> 4); }
 
 __device__ __forceinline__ uint32_t float_to_key(float v) {
   uint32_t u = __float_as_uint(v + 0.0f);          // -0 -> +0
@@ -210,6 +217,11 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
   return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
 }
 
+// Every thread owns a contiguous segment of the row and a private set of 16 digit counters, laid out
+// [digit][thread] so that the flattened exclusive scan yields, for (digit d, thread t), the first output
+// slot of t's elements with digit d: elements keep their relative order (stable) without any cross-lane
+// ranking.  Warp w of the scan owns digit w, so a digit total is one warp reduction; a pass in which a
+// single digit holds all N keys is the identity and is skipped.
 __global__ void __launch_bounds__(SORT_THREADS, 1)
 k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint16_t* __restrict__ sidx, float* __restrict__ sval) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -217,72 +229,54 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
   uint32_t* keyB = keyA + N;
   uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + N);
   uint16_t* idxB = idxA + ((N + 1) & ~1);
-  uint32_t* hist = reinterpret_cast<uint32_t*>(idxB + ((N + 1) & ~1));     // [SORT_WARPS][256]
-  uint32_t* dig_total = hist + SORT_WARPS * 256;                            // [256]
-  __shared__ uint32_t warp_sums[8];
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(idxB + ((N + 1) & ~1));       // [16][SORT_THREADS]
+  __shared__ uint32_t warp_tot[SORT_WARPS];
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int seg = ((N + SORT_WARPS - 1) / SORT_WARPS + 31) & ~31;           // per-warp contiguous segment (multiple of 32)
-  const int seg_begin = min(warp * seg, N), seg_end = min(seg_begin + seg, N);
-  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int seg = ((N + SORT_THREADS - 1) / SORT_THREADS) | 1;               // odd length: conflict-free strided reads
+  const int s_begin = min(t * seg, N), s_end = min(s_begin + seg, N);
 
   for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
     const float* src = fval + (size_t)row * n_stride;
-    for (int i = threadIdx.x; i < N; i += SORT_THREADS) { keyA[i] = float_to_key(src[i]); idxA[i] = (uint16_t)i; }
+    for (int i = t; i < N; i += SORT_THREADS) { keyA[i] = float_to_key(src[i]); idxA[i] = (uint16_t)i; }
     uint32_t* kin = keyA; uint32_t* kout = keyB; uint16_t* iin = idxA; uint16_t* iout = idxB;
     __syncthreads();
-    for (int pass = 0; pass < 4; ++pass) {
-      const int shift = pass * 8;
-      for (int i = threadIdx.x; i < SORT_WARPS * 256; i += SORT_THREADS) hist[i] = 0;
-      __syncthreads();
-      uint32_t* wh = hist + warp * 256;
-      for (int base = seg_begin; base < seg_end; base += 32) {
-        const int i = base + lane;
-        const bool ok = i < seg_end;
-        const uint32_t d = ok ? ((kin[i] >> shift) & 255u) : (256u + lane);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if (ok && (peers & lt_mask) == 0) wh[d] += __popc(peers);
-        __syncwarp();
-      }
-      __syncthreads();
-      // exclusive offsets: digit-major, warp-minor
-      int same_digit = 0;
-      if (threadIdx.x < 256) {
-        uint32_t run = 0;
-        for (int w = 0; w < SORT_WARPS; ++w) { uint32_t t = hist[w * 256 + threadIdx.x]; hist[w * 256 + threadIdx.x] = run; run += t; }
-        same_digit = run == (uint32_t)N;             // every key has the same digit: the pass is the identity
-        uint32_t incl = run;
+    for (int pass = 0; pass < 8; ++pass) {
+      const int shift = pass * 4;
 #pragma unroll
-        for (int dlt = 1; dlt < 32; dlt <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, incl, dlt); if (lane >= dlt) incl += t; }
-        if (lane == 31) warp_sums[warp] = incl;
-        dig_total[threadIdx.x] = incl - run;         // exclusive within the warp of 32 digits
-      }
-      if (__syncthreads_or(same_digit)) continue;
-      if (threadIdx.x < 256) {
-        uint32_t add = 0;
-        for (int w = 0; w < warp; ++w) add += warp_sums[w];
-        dig_total[threadIdx.x] += add;
+      for (int d = 0; d < SORT_RADIX; ++d) cnt[cnt_index(d, t)] = 0;
+      for (int i = s_begin; i < s_end; ++i) cnt[cnt_index((kin[i] >> shift) & 15u, t)] += 1;
+      __syncthreads();
+      // flattened exclusive scan of cnt[16*512]: thread t scans entries [16t, 16t+16) (all of digit `warp`)
+      uint32_t loc[16];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { loc[k] = cnt[cnt_index(warp, lane * 16 + k)]; sum += loc[k]; }   // 17*lane + k: conflict-free
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += x; }
+      const uint32_t digit_total = __shfl_sync(0xffffffffu, incl, 31);
+      if (lane == 31) warp_tot[warp] = incl;
+      if (__syncthreads_or(digit_total == (uint32_t)N)) continue;            // identity pass
+      uint32_t run = incl - sum;
+      for (int w = 0; w < warp; ++w) run += warp_tot[w];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) { const uint32_t c = loc[k]; cnt[cnt_index(warp, lane * 16 + k)] = run; run += c; }
+      __syncthreads();
+      for (int i = s_begin; i < s_end; ++i) {
+        const uint32_t k = kin[i];
+        uint32_t* slot = cnt + cnt_index((k >> shift) & 15u, t);
+        const uint32_t pos = *slot;
+        *slot = pos + 1;
+        kout[pos] = k;
+        iout[pos] = iin[i];
       }
       __syncthreads();
-      for (int base = seg_begin; base < seg_end; base += 32) {
-        const int i = base + lane;
-        const bool ok = i < seg_end;
-        const uint32_t k = ok ? kin[i] : 0u;
-        const uint32_t d = ok ? ((k >> shift) & 255u) : (256u + lane);
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t pos = 0;
-        if (ok) pos = dig_total[d] + wh[d] + __popc(peers & lt_mask);
-        __syncwarp();
-        if (ok && (peers & lt_mask) == 0) wh[d] += __popc(peers);
-        __syncwarp();
-        if (ok) { kout[pos] = k; iout[pos] = iin[i]; }
-      }
-      __syncthreads();
-      { uint32_t* t = kin; kin = kout; kout = t; uint16_t* u = iin; iin = iout; iout = u; }
+      { uint32_t* tk = kin; kin = kout; kout = tk; uint16_t* ti = iin; iin = iout; iout = ti; }
     }
     uint16_t* drow = sidx + (size_t)row * n_stride;
     float* vrow = sval + (size_t)row * n_stride;
-    for (int i = threadIdx.x; i < N; i += SORT_THREADS) { drow[i] = iin[i]; vrow[i] = key_to_float(kin[i]); }
+    for (int i = t; i < N; i += SORT_THREADS) { drow[i] = iin[i]; vrow[i] = key_to_float(kin[i]); }
     __syncthreads();
   }
 }
@@ -334,21 +328,28 @@ int cc_boost_set_shard(cc_ctx* ctx, int rank, int world) {
     ctx->row0 = (int)(F * rank / world);
     ctx->nrows = (int)(F * (rank + 1) / world) - ctx->row0;
     ctx->precalc_valid = false;
-    // per-plane row lists of this shard (Haar): upright rows read `sum`, tilted rows read `tilted`
+    // per-plane compact tap lists of this shard (Haar): upright rows read `sum`, tilted rows read `tilted`;
+    // word 11 of every entry carries the global feature index
     if (ctx->ftype == CC_FEATURE_HAAR) {
       std::vector<int> up, tl;
-      for (int f = ctx->row0; f < ctx->row0 + ctx->nrows; ++f) (ctx->haar[f].tilted ? tl : up).push_back(f);
-      ctx->upright_rows = up; ctx->tilted_rows = tl;
-      cudaFree(ctx->d_upright_rows); cudaFree(ctx->d_tilted_rows);
-      ctx->d_upright_rows = ctx->d_tilted_rows = nullptr;
-      CC_CUDA(cudaSetDevice(ctx->device));
-      if (!up.empty()) {
-        CC_CUDA(cudaMalloc(&ctx->d_upright_rows, up.size() * sizeof(int)));
-        CC_CUDA(cudaMemcpy(ctx->d_upright_rows, up.data(), up.size() * sizeof(int), cudaMemcpyHostToDevice));
+      std::vector<HaarTaps> tu, tt;
+      const int S = ctx->W + 1;
+      for (int f = ctx->row0; f < ctx->row0 + ctx->nrows; ++f) {
+        HaarTaps t = make_haar_taps(ctx->haar[f], S);
+        t.w[11] = (uint32_t)f;
+        if (ctx->haar[f].tilted) { tl.push_back(f); tt.push_back(t); } else { up.push_back(f); tu.push_back(t); }
       }
-      if (!tl.empty()) {
-        CC_CUDA(cudaMalloc(&ctx->d_tilted_rows, tl.size() * sizeof(int)));
-        CC_CUDA(cudaMemcpy(ctx->d_tilted_rows, tl.data(), tl.size() * sizeof(int), cudaMemcpyHostToDevice));
+      ctx->upright_rows = up; ctx->tilted_rows = tl;
+      cudaFree(ctx->d_taps_upright); cudaFree(ctx->d_taps_tilted);
+      ctx->d_taps_upright = ctx->d_taps_tilted = nullptr;
+      CC_CUDA(cudaSetDevice(ctx->device));
+      if (!tu.empty()) {
+        CC_CUDA(cudaMalloc(&ctx->d_taps_upright, tu.size() * sizeof(HaarTaps)));
+        CC_CUDA(cudaMemcpy(ctx->d_taps_upright, tu.data(), tu.size() * sizeof(HaarTaps), cudaMemcpyHostToDevice));
+      }
+      if (!tt.empty()) {
+        CC_CUDA(cudaMalloc(&ctx->d_taps_tilted, tt.size() * sizeof(HaarTaps)));
+        CC_CUDA(cudaMemcpy(ctx->d_taps_tilted, tt.data(), tt.size() * sizeof(HaarTaps), cudaMemcpyHostToDevice));
       }
     }
   }
@@ -375,16 +376,16 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
     const size_t smem = tiles_per_cta * tile_bytes + 64;
     const int gx = (ntiles_used + tiles_per_cta - 1) / tiles_per_cta;
     auto chunks_for = [&](int nrows_launch) {
-      // enough CTAs for >= ~8 waves, but >= 512 rows per CTA so the tile load is amortised
+      // enough CTAs for >= ~8 waves, but >= 4096 rows (128 per warp) per CTA so the tile load is amortised
       int want = std::max(1, (ctx->sm_count * 8 + gx - 1) / gx);
-      int max_chunks = std::max(1, nrows_launch / 512);
+      int max_chunks = std::max(1, nrows_launch / 4096);
       int chunks = std::min(want, max_chunks);
       return std::max(1, chunks);
     };
     if (ctx->ftype == CC_FEATURE_HAAR) {
-      struct Launch { const int32_t* plane; const int* rows; int n; };
-      Launch ls[2] = {{ctx->d_sum, ctx->d_upright_rows, (int)ctx->upright_rows.size()},
-                      {ctx->d_tilted, ctx->d_tilted_rows, (int)ctx->tilted_rows.size()}};
+      struct Launch { const int32_t* plane; const HaarTaps* taps; int n; };
+      Launch ls[2] = {{ctx->d_sum, ctx->d_taps_upright, (int)ctx->upright_rows.size()},
+                      {ctx->d_tilted, ctx->d_taps_tilted, (int)ctx->tilted_rows.size()}};
       for (const Launch& l : ls) {
         if (l.n == 0) continue;
         ScopedTimer tm(ctx, "precalc", 1);
@@ -393,11 +394,11 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
         dim3 grid(gx, (l.n + rpc - 1) / rpc);
         if (tiles_per_cta == 2) {
           CC_CUDA(cudaFuncSetAttribute(k_precalc_haar<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_precalc_haar<2><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, ctx->d_haar_taps, l.rows, l.n, rpc, ctx->row0,
+          k_precalc_haar<2><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, l.taps, l.n, rpc, ctx->row0,
                                                                           ctx->d_fval, n_stride, P, ntiles_used);
         } else {
           CC_CUDA(cudaFuncSetAttribute(k_precalc_haar<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_precalc_haar<1><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, ctx->d_haar_taps, l.rows, l.n, rpc, ctx->row0,
+          k_precalc_haar<1><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, l.taps, l.n, rpc, ctx->row0,
                                                                           ctx->d_fval, n_stride, P, ntiles_used);
         }
         CC_CUDA(cudaGetLastError());
@@ -409,11 +410,11 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
       dim3 grid(gx, (ctx->nrows + rpc - 1) / rpc);
       if (tiles_per_cta == 2) {
         CC_CUDA(cudaFuncSetAttribute(k_precalc_lbp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_precalc_lbp<2><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
+        k_precalc_lbp<2><<<grid, LBP_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
                                                                        n_stride, P, ntiles_used);
       } else {
         CC_CUDA(cudaFuncSetAttribute(k_precalc_lbp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_precalc_lbp<1><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
+        k_precalc_lbp<1><<<grid, LBP_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
                                                                        n_stride, P, ntiles_used);
       }
       CC_CUDA(cudaGetLastError());
@@ -427,9 +428,9 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
   }
 
   if (ctx->ftype != CC_FEATURE_LBP) {   // categorical variables are not sorted (numPrecalcIdx = 0, :267-273)
-    const size_t smem = (size_t)N * 8 + (size_t)((N + 1) & ~1) * 4 + (SORT_WARPS * 256 + 256) * 4 + 16;
+    const size_t smem = (size_t)N * 8 + (size_t)((N + 1) & ~1) * 4 + (size_t)SORT_RADIX * SORT_CNT_STRIDE * 4 + 16;
     CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED,
-               "sort: numSamples %d needs %zu B of shared memory per row (limit 227 KB, about 18900 samples)", N, smem);
+               "sort: numSamples %d needs %zu B of shared memory per row (limit 227 KB, about 16600 samples)", N, smem);
     ScopedTimer tm(ctx, "sort", 1);
     CC_CUDA(cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = std::min(ctx->nrows, ctx->sm_count * std::max(1, (int)((227 * 1024) / (smem + 1024))));

@@ -174,6 +174,10 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_accepta
  * (PosReader, src/imagestorage.cpp:138-189): host_vec = vec_count windows; *vec_pos = PosReader::last */
 int cc_mine_positives(cc_ctx* ctx, const uint8_t* host_vec, int vec_count, int count,
                       int32_t* vec_pos, int64_t* consumed, int32_t* got);
+/* NegReader::get() x nwindows without pixels (host only, no GPU needed): advances *state over images of
+ * the given sizes; window5 (optional) = x, y, level_w, level_h, source image of the last consumed window. */
+int cc_reader_advance(const int32_t* img_w, const int32_t* img_h, int nimg, int win_w, int win_h,
+                      cc_reader_state* state, int64_t nwindows, int32_t* window5);
 /* throughput probe used by bench.py: evaluate the cascade on every window of backgrounds
  * [img0, img0+nimg) at round 0 without touching evaluator slots; returns windows and survivors */
 int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* survivors);

@@ -1,0 +1,121 @@
+"""GPU parity: K5 mining (fillPassedSamples / NegReader / PosReader) and the whole cascade loop vs the oracle."""
+import ctypes as C
+import io
+import os
+
+import numpy as np
+import pytest
+
+import orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _data(n_pos_vec, n_bg, W=24, H=24, bw=160, bh=120, seed=3):
+    from cascadeclassifier_b200 import synth
+    pos = synth.make_positives(n_pos_vec, W, H, seed=seed)
+    bgs = synth.make_backgrounds(n_bg, bw, bh, seed0=seed * 50)
+    return pos, bgs
+
+
+def _state_dict(st):
+    return dict(last=st.last, round=st.round, point=(st.point_x, st.point_y), offset=(st.offset_x, st.offset_y),
+                img_size=(st.level_w, st.level_h), scale=st.scale)
+
+
+@pytest.mark.parametrize("ftype,mode", [(orc.HAAR, orc.ALL), (orc.LBP, 0)])
+def test_stage0_mining_matches_reader_stream(gpu_ctx, ftype, mode):
+    """No stages yet: fillPassedSamples accepts the first `count` windows of the NegReader stream."""
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import _lib
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    pos, bgs = _data(50, 3, bw=100, bh=70)
+    cc = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
+    cc.cascadeParams = CvCascadeParams(0, ftype, (24, 24))
+    fp = ccb.CvFeatureParams.create(ftype)
+    if ftype == orc.HAAR:
+        fp.mode = mode
+    cc.featureEvaluator = ccb.CvFeatureEvaluator.create(ftype, gpu_ctx)
+    cc.featureEvaluator.init(fp, 40 + 700, (24, 24))
+    cc._create_readers(pos, bgs)
+    cc.numPos, cc.numNeg = 40, 700
+    cc.stageClassifiers = []
+    cc._sync_cascade()
+    got, consumed = cc.fillPassedSamples(0, 40, True, 0)
+    assert (got, consumed) == (40, 40)
+    got, consumed = cc.fillPassedSamples(40, 333, False, 1e-9)
+    assert (got, consumed) == (333, 333)
+    got2, consumed2 = cc.fillPassedSamples(373, 367, False, 1e-9)     # resumes mid-level, crosses images
+    assert (got2, consumed2) == (367, 367)
+    rd = orc.NegReader(24, 24, bgs)
+    ref = np.stack([rd.get() for _ in range(700)])
+    imgs = cc.featureEvaluator.images(0, 740)
+    assert np.array_equal(imgs[:40], pos[:40])
+    assert np.array_equal(imgs[40:], ref)
+    assert _state_dict(cc._reader) == rd.state()
+    # integrals of mined slots are those of the window
+    o = orc.Evaluator(ftype, mode, 24, 24, 1)
+    for si in (40, 41, 372, 373, 739):
+        o.set_images(imgs[si:si + 1], np.zeros(1, np.uint8))
+        s, t, nf = cc.featureEvaluator.integrals(si)
+        os_, ot, onf = o.integrals(0)
+        assert (s == os_).all()
+        if ftype == orc.HAAR:
+            assert (t == ot).all() and np.float32(nf) == np.float32(onf)
+    labels = cc.featureEvaluator.getCls()
+    assert (labels[:40] == 1).all() and (labels[40:740] == 0).all()
+
+
+def _run_cascade(gpu_ctx, tmp_path, ftype, mode, W, H, numPos, numNeg, numStages, pos, bgs, **kw):
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    out = io.StringIO()
+    cc = CvCascadeClassifier(gpu_ctx, out=out)
+    fp = ccb.CvFeatureParams.create(ftype)
+    if ftype == orc.HAAR:
+        fp.mode = mode
+    sp = ccb.CvCascadeBoostParams(maxFalseAlarm=kw.get("max_false_alarm", 0.5), minHitRate=kw.get("min_hit_rate", 0.995),
+                                  maxWeakCount=kw.get("weak_count", 100))
+    ok = cc.train(str(tmp_path), "pos.vec", "bg.txt", numPos, numNeg, 1024, 1024, numStages,
+                  CvCascadeParams(0, ftype, (W, H)), fp, sp, positives=pos, backgrounds=bgs)
+    o = orc.Cascade(ftype, mode, W, H, numPos, numNeg, numStages,
+                    orc.boost_params(max_false_alarm=kw.get("max_false_alarm", 0.5), min_hit_rate=kw.get("min_hit_rate", 0.995),
+                                     weak_count=kw.get("weak_count", 100)), sort_mode=orc.SORT_STABLE, threads=8)
+    o.set_pos(pos)
+    for b in bgs:
+        o.add_bg(b)
+    o.train()
+    return ok, cc, o, out.getvalue()
+
+
+@pytest.mark.parametrize("ftype,mode", [(orc.HAAR, orc.BASIC), (orc.LBP, 0)])
+def test_cascade_training_matches_oracle(gpu_ctx, tmp_path, ftype, mode):
+    pos, bgs = _data(260, 6)
+    ok, cc, o, log = _run_cascade(gpu_ctx, tmp_path, ftype, mode, 24, 24, 200, 300, 4, pos, bgs)
+    assert ok
+    ref_stages = o.stages()
+    ref_reports = o.reports()
+    assert len(cc.stageClassifiers) == len(ref_stages), log
+    from test_gpu_boost import compare_stage
+
+    class _R:
+        pass
+    for s, (g, r) in enumerate(zip(cc.stageClassifiers, ref_stages)):
+        rr = _R()
+        rr.trees = r["trees"]
+        agreed = compare_stage(g, rr)
+        assert agreed == len(r["trees"]), "stage %d diverged at tree %d (tie)" % (s, agreed)
+        assert g.threshold == pytest.approx(r["threshold"], rel=1e-6, abs=1e-7)
+    for g, r in zip(cc.reports, ref_reports):
+        for k in ("pos_count", "pos_consumed", "neg_count", "neg_consumed"):
+            assert g[k] == r[k], (k, g, r)
+        assert g["acceptance_ratio"] == pytest.approx(r["acceptance_ratio"])
+    assert _state_dict(cc._reader) == o.neg_state()
+    # files exist and OpenCV's own detector can load the result (test_integration.cpp:125-127)
+    assert os.path.exists(os.path.join(str(tmp_path), "params.xml"))
+    assert os.path.exists(os.path.join(str(tmp_path), "stage0.xml"))
+    import cv2
+    det = cv2.CascadeClassifier(os.path.join(str(tmp_path), "cascade.xml"))
+    if ftype != orc.HOG:
+        assert not det.empty()
+    assert "===== TRAINING 0-stage =====" in log and "POS count : consumed" in log
