@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py — one "step" = one complete stage training (CvCascadeBoost::train) of BASELINE.json configs[2]:
+Haar ALL 24x24, numPos=5000 numNeg=10000 (N=15000 samples, F=261600 features), reference default boosting
+flags, on the stage-0 sample set (synthetic positives + the first 10000 windows of generated backgrounds).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+`value`  : feature evals/s through a whole stage = F*N / step time, samples already resident in HBM.
+`e2e`    : same, through the C ABI with HOST buffers (H2D of the windows + D2H of the trained stage timed).
+N > 1    : feature-sharded (each rank owns F/N variables; one NCCL all-gather of 64-byte candidates per node),
+           total work fixed => "strong" scaling.
+--impl reference : the CPU oracle (port of the reference; OpenCV C++ is not installable here) on a bounded
+           sample (every k-th feature), all host threads for precalc/sort, serial split search like the reference.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_POS, NUM_NEG, WIN = 5000, 10000, 24
+HAAR_MODE_ALL = 2
+WORKLOAD = "traincascade Haar ALL 24x24 stage train, numPos=5000 numNeg=10000 (BASELINE configs[2])"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+def make_sources():
+    from cascadeclassifier_b200 import synth
+    pos = synth.make_positives(NUM_POS, WIN, WIN, seed=12345)
+    bgs = synth.make_backgrounds(6, 640, 480, seed0=1000, clutter=2.5)
+    return pos, bgs
+
+
+def make_training_set_gpu(ctx, ev):
+    """Stage-0 sample set built by the product's own mining path (K5): positives from the .vec block, negatives =
+    the first NUM_NEG windows of the NegReader stream over the generated backgrounds.  Returned to the host only
+    for the e2e / cpu_baseline legs."""
+    from cascadeclassifier_b200 import _lib
+    pos, bgs = make_sources()
+    lib, h = ctx.lib, ctx.h
+    _lib.check(lib.cc_bg_clear(h), "cc_bg_clear")
+    for b in bgs:
+        b = np.ascontiguousarray(b)
+        _lib.check(lib.cc_bg_register(h, b.ctypes.data_as(C.c_void_p), b.shape[1], b.shape[0]), "cc_bg_register")
+    _lib.check(lib.cc_cascade_set_stages(h, None, 0), "cc_cascade_set_stages")
+    consumed, got, vec_pos = C.c_int64(0), C.c_int32(0), C.c_int32(0)
+    _lib.check(lib.cc_mine_positives(h, pos.ctypes.data_as(C.c_void_p), len(pos), NUM_POS, C.byref(vec_pos), C.byref(consumed), C.byref(got)), "mine_pos")
+    st = _lib.ReaderState()
+    _lib.check(lib.cc_mine_negatives(h, NUM_POS, NUM_NEG, 0.0, C.byref(st), C.byref(consumed), C.byref(got)), "mine_neg")
+    assert got.value == NUM_NEG
+    imgs = ev.images(0, NUM_POS + NUM_NEG)
+    labels = np.concatenate([np.ones(NUM_POS, np.uint8), np.zeros(NUM_NEG, np.uint8)])
+    return imgs, labels
+
+
+def make_training_set_oracle():
+    """Same set for the CPU arm, from the oracle's own PosReader / NegReader (bit-identical stream; see tests)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    pos, bgs = make_sources()
+    rd = orc.NegReader(WIN, WIN, bgs)
+    neg = np.stack([rd.get() for _ in range(NUM_NEG)])
+    imgs = np.concatenate([pos[:NUM_POS], neg])
+    labels = np.concatenate([np.ones(NUM_POS, np.uint8), np.zeros(NUM_NEG, np.uint8)])
+    return imgs, labels
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[2 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except (ValueError, IndexError):
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import _lib
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+
+    N = NUM_POS + NUM_NEG
+    stream = torch.cuda.Stream(device=dev)
+    ctx = ccb.Context(local, stream=stream.cuda_stream)
+    lib, h = ctx.lib, ctx.h
+    ev = ccb.CvFeatureEvaluator.create(ccb.CvFeatureParams.HAAR, ctx)
+    ev.init(ccb.CvHaarFeatureParams(HAAR_MODE_ALL), N, (WIN, WIN))
+    F = ev.getNumFeatures()
+    imgs, labels = make_training_set_gpu(ctx, ev)
+    if world > 1:
+        from cascadeclassifier_b200.dist import init_comm
+        init_comm(ctx, dist, dev)
+
+    params = ccb.CvCascadeBoostParams()          # reference defaults: GAB, 0.995 / 0.5, trim 0.95, depth 1, 100 weak
+    cparams = params.to_c()
+    cap = params.weak_count
+    trees = (_lib.Tree * cap)()
+    logrows = (_lib.LogRow * cap)()
+    stage = _lib.Stage(0.0, 0, 0, 0, trees, logrows)
+
+    d_imgs = torch.from_numpy(imgs).to(dev)
+    d_labels = torch.from_numpy(labels).to(dev)
+    h_imgs = torch.from_numpy(imgs).pin_memory()
+    h_labels = torch.from_numpy(labels).pin_memory()
+    torch.cuda.synchronize(dev)
+
+    def step_device():
+        _lib.check(lib.cc_eval_set_images_device(h, C.c_void_p(d_imgs.data_ptr()), C.c_void_p(d_labels.data_ptr()), 0, N), "set_images_device")
+        _lib.check(lib.cc_boost_train(h, N, C.byref(cparams), C.byref(stage)), "cc_boost_train")
+
+    def step_host():
+        _lib.check(lib.cc_eval_set_images(h, C.c_void_p(h_imgs.data_ptr()), C.c_void_p(h_labels.data_ptr()), 0, N), "set_images")
+        _lib.check(lib.cc_boost_train(h, N, C.byref(cparams), C.byref(stage)), "cc_boost_train")
+        return stage.num_weak, stage.threshold          # the trained stage is already on the host (D2H inside the call)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                fn()
+            e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    ctx.timing_reset()
+    ms_total = timed(step_device, args.steps)
+    launches = ctx.launch_count()
+    fam = {}
+    for name in ["integral", "precalc", "sort", "split_search", "boost_small"]:
+        m, k = ctx.timing(name)
+        fam[name] = {"ms_per_step": m / args.steps, "launches_per_step": k / args.steps}
+    nweak = stage.num_weak
+    clocks = sampler.finish() if sampler else None
+    for _ in range(2):
+        step_host()
+    ms_e2e = timed(step_host, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    ms_step = ms_total / args.steps
+    value = F * N / (ms_step * 1e-3)
+    e2e_value = F * N / (ms_e2e / args.steps * 1e-3)
+    peak, peak_kind = peaks()
+    # dominant kernel: split search (one launch per tree node over the local rows): 6 B per (feature, sample)
+    ss = fam["split_search"]
+    n_search = ss["launches_per_step"] / 2.0          # every search = 1 search kernel + 1 argmax kernel
+    ss_ms = ss["ms_per_step"] / max(n_search, 1e-9)
+    rows_local = F // world if world > 1 else F
+    alg_bytes = 6.0 * rows_local * N
+    achieved = alg_bytes / (ss_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("split_search_dram_bytes_per_launch")
+    pre_ms = fam["precalc"]["ms_per_step"]
+    out = {
+        "metric": "Haar stage-train feature evals/s (F*N per complete stage train)", "value": value, "unit": "evals/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32 integral taps, f32 values, f64 split criteria",
+        "data": "synthetic (generated glyph positives, generated backgrounds with distractors)",
+        "config": {"workload": WORKLOAD, "N": N, "F": F, "weak_trees_in_stage": int(nweak), "timing": "inputs larger than L2 (fval 15.7 GB, sorted rows 23.5 GB per pass)",
+                   "parallelism": "feature-sharded x%d" % world},
+        "stage_train_s": ms_step * 1e-3,
+        "kernels": {"precalc_evals_per_s": rows_local * N / (pre_ms * 1e-3), "precalc_frac_of_hbm": rows_local * N * 4 / (pre_ms * 1e-3) / 1e9 / peak,
+                    "sort_ms": fam["sort"]["ms_per_step"], "split_search_ms_per_node": ss_ms, "families": fam},
+        "roofline": {"kernel": "k_split_search_ord", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(imgs.nbytes + labels.nbytes),
+                "d2h_bytes_per_step": int(C.sizeof(_lib.Tree) * nweak + C.sizeof(_lib.LogRow) * nweak + 16), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(imgs, labels, F, budget_s=20.0)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(imgs, labels, F, budget_s=20.0):
+    """The oracle (a port of the reference's CPU path) on a bounded sample of the same workload: all N samples,
+    every k-th feature, precalc+sort on all host threads (cv::parallel_for_ shape), serial split search."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import orc
+    N = len(imgs)
+    cores = os.cpu_count() or 1
+    o = orc.Evaluator(orc.HAAR, orc.ALL, WIN, WIN, N)
+    t0 = time.time()
+    o.set_images(imgs, labels, threads=cores)
+    t_int = time.time() - t0
+    # calibrate the stride so that the sample takes roughly budget_s
+    stride = 64
+    rows = np.arange(0, F, stride, dtype=np.int32)
+    t0 = time.time()
+    td = orc.TrainData(o, N, orc.SORT_STD, cores, subset=rows)
+    t_pre = time.time() - t0
+    res = orc.boost_train(td, orc.boost_params(), cat_sort=orc.SORT_STD)
+    t_boost = res.seconds
+    total = t_int + t_pre + t_boost
+    return {"value": len(rows) * N / total, "unit": "evals/s", "cores": cores, "kind": "port",
+            "sample": "all %d samples, every %dth feature (%d of %d); integral %.2fs + precalc/sort %.2fs (%d threads) + boosting %.2fs serial, %d weak trees"
+                      % (N, stride, len(rows), F, t_int, t_pre, cores, t_boost, len(res.trees)),
+            "seconds": total}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    imgs, labels = make_training_set_oracle()
+    N = len(imgs)
+    import orc
+    F = orc.lib().orc_catalog_count(orc.HAAR, orc.ALL, WIN, WIN)
+    best = None
+    times = []
+    for i in range(args.warmup + args.steps):
+        cb = cpu_baseline(imgs, labels, F)
+        if i >= args.warmup:
+            times.append(cb["seconds"])
+            best = cb
+    ms = float(np.mean(times)) * 1e3
+    stride_rows = int(best["sample"].split("(")[1].split(" of")[0])
+    value = stride_rows * N / (ms * 1e-3)
+    best["value"] = value
+    out = {"impl": "reference", "metric": "Haar stage-train feature evals/s (F*N per complete stage train)", "value": value, "unit": "evals/s",
+           "n_gpus": int(os.environ.get("WORLD_SIZE", "1")), "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+           "scaling": "strong", "vs_baseline": None, "dtype": "int32/f32/f64 (CPU)", "data": "synthetic (same generator as the GPU arm)",
+           "config": {"workload": WORKLOAD, "N": N, "F": F, "note": "each step is a bounded sample: " + best["sample"]},
+           "cpu_baseline": best, "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

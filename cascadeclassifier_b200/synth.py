@@ -45,11 +45,15 @@ def _warp(pat, W, H, rng):
     fu, fv = u - u0, v - v0
     img = (pat[v0, u0] * (1 - fu) * (1 - fv) + pat[v0, u0 + 1] * fu * (1 - fv) +
            pat[v0 + 1, u0] * (1 - fu) * fv + pat[v0 + 1, u0 + 1] * fu * fv)
-    gain = rng.uniform(0.6, 1.3)
-    bias = rng.uniform(-40, 40)
-    img = (img - 128.0) * gain + 128.0 + bias + rng.normal(0, rng.uniform(2, 12), img.shape)
+    gain = rng.uniform(0.3, 1.3)
+    bias = rng.uniform(-50, 50)
+    img = (img - 128.0) * gain + 128.0 + bias + rng.normal(0, rng.uniform(3, 40), img.shape)
     if rng.random() < 0.5:  # illumination gradient
-        img += np.linspace(-1, 1, W)[None, :] * rng.uniform(-25, 25)
+        img += np.linspace(-1, 1, W)[None, :] * rng.uniform(-35, 35)
+    if rng.random() < 0.35:  # occluding patch
+        ph, pw = int(rng.integers(H // 5, H // 2)), int(rng.integers(W // 5, W // 2))
+        py, px = int(rng.integers(0, H - ph)), int(rng.integers(0, W - pw))
+        img[py:py + ph, px:px + pw] = rng.uniform(40, 220)
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
 
@@ -64,8 +68,43 @@ def make_positives(count, W, H, seed=12345):
     return out
 
 
-def make_background(w, h, seed):
-    """8-bit gray: multi-octave value noise + random rectangles / gradients (non-zero window variance)."""
+def _distractor(size, rng):
+    """A glyph-like patch that is NOT the positive pattern: scrambled / flipped / inverted variants."""
+    pat = _pattern(48)
+    kind = int(rng.integers(0, 8))
+    if kind >= 5:                                # near miss: the glyph with half of it flattened
+        pat = pat.copy()
+        half = int(rng.integers(0, 4))
+        if half == 0:
+            pat[:24, :] = pat[:24, :].mean()
+        elif half == 1:
+            pat[24:, :] = pat[24:, :].mean()
+        elif half == 2:
+            pat[:, :24] = pat[:, :24].mean()
+        else:
+            pat[:, 24:] = pat[:, 24:].mean()
+    elif kind == 0:
+        pat = pat[::-1, :]                       # upside down
+    elif kind == 1:
+        pat = 255.0 - pat                        # inverted contrast
+    elif kind == 2:
+        q = 24
+        blocks = [pat[i:i + q, j:j + q].copy() for i in (0, q) for j in (0, q)]
+        order = rng.permutation(4)
+        pat = np.block([[blocks[order[0]], blocks[order[1]]], [blocks[order[2]], blocks[order[3]]]])
+    elif kind == 3:
+        pat = np.roll(pat, int(rng.integers(8, 40)), axis=int(rng.integers(0, 2)))
+    else:
+        pat = pat.T.copy()                       # transposed
+    idx = (np.arange(size) * (48.0 / size)).astype(np.int32)
+    patch = pat[idx][:, idx]
+    gain = rng.uniform(0.5, 1.3)
+    return (patch - 128.0) * gain + 128.0 + rng.uniform(-40, 40)
+
+
+def make_background(w, h, seed, clutter=0.0):
+    """8-bit gray: multi-octave value noise + random rectangles / gradients (non-zero window variance).
+    clutter > 0 pastes that many glyph-like distractors per 10^4 pixels (hard negatives)."""
     rng = np.random.default_rng(seed)
     img = np.zeros((h, w), np.float32)
     amp = 1.0
@@ -88,12 +127,19 @@ def make_background(w, h, seed):
             img[y0:y1, x0:x1] = img[y0:y1, x0:x1] * 0.3 + rng.uniform(0, 255) * 0.7
         else:
             img[y0:y1, x0:x1] += np.linspace(-60, 60, x1 - x0)[None, :] * rng.uniform(-1, 1)
+    if clutter > 0:
+        for _ in range(int(clutter * w * h / 1e4)):
+            size = int(rng.integers(20, max(21, min(w, h) // 2)))
+            if size >= min(w, h):
+                continue
+            x0, y0 = int(rng.integers(0, w - size)), int(rng.integers(0, h - size))
+            img[y0:y0 + size, x0:x0 + size] = _distractor(size, rng)
     img += rng.normal(0, 3.0, img.shape)
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
 
-def make_backgrounds(count, w, h, seed0=1000):
-    return [make_background(w, h, seed0 + i) for i in range(count)]
+def make_backgrounds(count, w, h, seed0=1000, clutter=0.0):
+    return [make_background(w, h, seed0 + i, clutter) for i in range(count)]
 
 
 # ---- on-disk formats -------------------------------------------------------------------------

@@ -1,0 +1,133 @@
+"""CPU: the C-ABI library loads, exports every symbol declared in include/cascade_cuda.h, fails loudly without a
+GPU, and its host-only logic (NegReader state machine, catalogs via the header contract) matches the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    src = open(os.path.join(ROOT, "include", "cascade_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cc_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from cascadeclassifier_b200 import _lib
+    lib = _lib.load()
+    declared = _header_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(lib, name), "libcascade_cuda.so does not export %s" % name
+    assert set(_lib.exported_symbols()) <= set(declared)
+    assert b"sm_100a" in lib.cc_version()
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device cc_create must fail (the product path never falls back to the CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import cascadeclassifier_b200 as ccb
+    with pytest.raises(ccb.CascadeCudaError) as e:
+        ccb.Context(0)
+    assert "no CPU fallback" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "cascadeclassifier_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "liborc" not in text and "import orc" not in text and "oracle/" not in text, f
+
+
+def test_reader_state_machine_matches_oracle():
+    from cascadeclassifier_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(11)
+    sizes = [(100, 80), (64, 48), (20, 20), (57, 33), (24, 24), (130, 25), (31, 200)]
+    imgs = [rng.integers(0, 256, (h, w), dtype=np.uint8) for (w, h) in sizes]
+    rd = orc.NegReader(24, 24, imgs)
+    w = np.array([s[0] for s in sizes], np.int32)
+    h = np.array([s[1] for s in sizes], np.int32)
+    st = _lib.ReaderState()
+    win = np.zeros(5, np.int32)
+    for step in [1, 1, 2, 5, 40, 1, 300, 777, 4000, 9000]:
+        last = None
+        for _ in range(step):
+            last = rd.get()
+            assert last is not None
+        _lib.check(lib.cc_reader_advance(w.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), len(sizes), 24, 24,
+                                         C.byref(st), step, win.ctypes.data_as(C.c_void_p)))
+        o = rd.state()
+        mine = dict(last=st.last, round=st.round, point=(st.point_x, st.point_y), offset=(st.offset_x, st.offset_y),
+                    img_size=(st.level_w, st.level_h), scale=st.scale)
+        assert mine == o
+        # the window the library says was consumed last is the one the oracle returned
+        x, y, lw, lh, src = [int(v) for v in win]
+        level = orc.resize_linear_exact(imgs[src], lw, lh)
+        assert np.array_equal(level[y:y + 24, x:x + 24], last)
+
+
+def test_reader_1080p_level_table():
+    """1920x1080, 24x24, round 0 -> 11 levels, 13584 windows."""
+    from cascadeclassifier_b200 import _lib
+    lib = _lib.load()
+    w = np.array([1920, 1920], np.int32)       # two images: the first one is scanned at round 0 (last/count == 0)
+    h = np.array([1080, 1080], np.int32)
+    st = _lib.ReaderState()
+    _lib.check(lib.cc_reader_advance(w.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), 2, 24, 24, C.byref(st), 13584, None))
+    # image 0 fully consumed: the reader has loaded image 1, which closes the list cycle (round 1, offset (1,0))
+    assert (st.last, st.round, st.point_x, st.point_y, st.level_w, st.level_h) == (0, 1, 1, 0, 43, 24)
+    st2 = _lib.ReaderState()
+    _lib.check(lib.cc_reader_advance(w.ctypes.data_as(C.c_void_p), h.ctypes.data_as(C.c_void_p), 2, 24, 24, C.byref(st2), 13583, None))
+    assert (st2.last, st2.round, st2.level_w, st2.level_h) == (1, 0, 1365, 768)
+
+
+def test_tree_xml_encoding(tmp_path):
+    """CvCascadeBoostTree::write (o_cvcascadeboosttree.cpp:41-93): BFS internal nodes, leaves 0,-1,-2.."""
+    import cv2
+    from cascadeclassifier_b200.boost import CvCascadeBoost
+    from cascadeclassifier_b200.xml_io import XmlWriter
+    leaf = lambda v: dict(left=-1, right=-1, var_idx=-1, value=v)
+    depth2 = [dict(left=1, right=2, var_idx=7, c=0.5, value=0.0), dict(left=3, right=4, var_idx=9, c=-0.25, value=0.0), leaf(0.3),
+              leaf(-0.7), leaf(0.9)]
+    stump = [dict(left=1, right=2, var_idx=3, c=0.125, value=0.0), leaf(-1.0), leaf(1.0)]
+    st = CvCascadeBoost.from_trees(-0.5, [stump, depth2]) if False else CvCascadeBoost()
+    st.threshold, st.trees = -0.5, [stump, depth2]
+    fmap = np.full(16, -1, np.int32)
+    st.markUsedFeaturesInMap(fmap)
+    assert sorted(np.nonzero(fmap >= 0)[0].tolist()) == [3, 7, 9]
+    k = 0
+    for i in range(16):
+        if fmap[i] >= 0:
+            fmap[i] = k
+            k += 1
+    path = str(tmp_path / "stage.xml")
+    fs = XmlWriter(path)
+    fs.start_map("stage")
+    st.write(fs, fmap, 0)
+    fs.end_map()
+    fs.release()
+    rd = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)
+    node = rd.getNode("stage")
+    assert int(node.getNode("maxWeakCount").real()) == 2
+    wc = node.getNode("weakClassifiers")
+    t0 = wc.at(0)
+    inn = [t0.getNode("internalNodes").at(i).real() for i in range(4)]
+    assert inn == [0.0, -1.0, 0.0, 0.125]                       # leaf 0, leaf -1, mapped feature 0, threshold
+    lv = [t0.getNode("leafValues").at(i).real() for i in range(2)]
+    assert lv == [-1.0, 1.0]
+    t1 = wc.at(1)
+    inn = [t1.getNode("internalNodes").at(i).real() for i in range(8)]
+    assert inn == [1.0, 0.0, 1.0, 0.5, -1.0, -2.0, 2.0, -0.25]  # root: child node 1, leaf 0; node 1: leaves -1,-2
+    lv = [t1.getNode("leafValues").at(i).real() for i in range(3)]
+    assert lv == [np.float32(0.3), np.float32(-0.7), np.float32(0.9)]
