@@ -97,3 +97,34 @@ def test_stage_predict_matches_training_decision(gpu_ctx):
     pos = sums[:100]
     assert (dec[:100] == 1).mean() >= 0.99
     assert np.isfinite(pos).all()
+
+
+def test_feature_sharded_search_single_gpu(gpu_ctx):
+    """Feature sharding without NCCL: train the first weak tree on each of 2 slices (one context each, run one after
+    the other on the same GPU), merge with the library's rule -> must equal the unsharded first tree."""
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200._lib import check
+    from cascadeclassifier_b200.dist import select_winner, shard_range
+    imgs, labels = make_samples(150, 250)
+    n = len(imgs)
+    params = ccb.CvCascadeBoostParams(maxWeakCount=1)
+    full = None
+    cands = []
+    for rank, world in [(0, 1), (0, 2), (1, 2)]:
+        ctx = ccb.Context(0)
+        ev = ccb.CvFeatureEvaluator.create(0, ctx)
+        ev.init(ccb.CvHaarFeatureParams(2), n, (24, 24))
+        check(ctx.lib.cc_boost_set_shard(ctx.h, rank, world), "set_shard")
+        ev.setImages(imgs, labels)
+        st = ccb.CvCascadeBoost()
+        assert st.train(ev, n, 1024, 1024, params)
+        root = st.trees[0][0]
+        if world == 1:
+            full = root
+        else:
+            lo, hi = shard_range(ev.getNumFeatures(), rank, world)
+            assert lo <= root["var_idx"] < hi
+            cands.append(dict(valid=True, quality=root["quality"], var_idx=root["var_idx"], c=root["c"]))
+        ctx.close()
+    win = select_winner(cands)
+    assert win["var_idx"] == full["var_idx"] and win["c"] == full["c"] and win["quality"] == full["quality"]
