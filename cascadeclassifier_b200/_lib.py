@@ -96,6 +96,7 @@ def _signatures():
         "cc_timing_reset": (i32, [vp]),
         "cc_timing_get": (i32, [vp, C.c_char_p, P(f64), P(i64)]),
         "cc_launch_count": (i64, [vp]),
+        "cc_debug_div_check": (i32, [vp, i32, C.c_uint64, i64, P(C.c_uint64)]),
     }
 
 

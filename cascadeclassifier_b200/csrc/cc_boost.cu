@@ -333,16 +333,146 @@ __device__ __forceinline__ float criterion32(float A, float B, float totA, float
   }
 }
 
+// exact numerator / denominator of the criterion (f64, the reference's formula); criteria without a division use den = 1
+template <int CRIT>
+__device__ __forceinline__ bool criterion_frac(double A, double B, double totA, double totB, double& num, double& den) {
+  if (CRIT == CRIT_SQERR) {
+    const double L = A, R = totA - A, lsum = B, rsum = totB - B;
+    if (!(L > 0.0) || !(R > 0.0)) return false;
+    num = lsum * lsum * R + rsum * rsum * L; den = L * R;
+  } else if (CRIT == CRIT_GINI) {
+    const double r0 = totA - A, r1 = totB - B, L = A + B, R = r0 + r1;
+    if (!(L > 0.0) || !(R > 0.0)) return false;
+    num = (A * A + B * B) * R + (r0 * r0 + r1 * r1) * L; den = L * R;
+  } else {
+    const double r0 = totA - A, r1 = totB - B;
+    num = fmax(A + r1, B + r0); den = 1.0;
+  }
+  return true;
+}
+
+// per-tile state saved by the estimate pass so that the exact pass can resume at any tile
+struct TileCarry { double a, b; float v; int cnt_has; };     // cnt_has = (count << 1) | has
+
+// One 256-position tile of one row.  EXACT == false: f32 estimate of every admissible split, returns the lane's
+// maximum.  EXACT == true: re-evaluates candidates whose estimate reaches `lim` with the reference's f64 formula,
+// in position order, keeping the first maximum (compared as exact fractions).
+template <int CRIT, bool HAS_Y, bool EXACT>
+__device__ __forceinline__ float ss_tile(const uint4 ci, const float4 cv0, const float4 cv1, uint32_t sw_addr, uint32_t sy_addr,
+                                         int lane, uint32_t lt_mask, double totA, double totB, float ftotA, float ftotB,
+                                         double& carryA, double& carryB, float& carryV, int& carryHas, int& carryCnt, float lim,
+                                         double& bestNum, double& bestDen, int& bestPos, float& bestVl, float& bestVr) {
+  const float eps = FLT_EPSILON * 2;
+  const uint32_t iw[4] = {ci.x, ci.y, ci.z, ci.w};
+  const float v[SS_EPT] = {cv0.x, cv0.y, cv0.z, cv0.w, cv1.x, cv1.y, cv1.z, cv1.w};
+  // ---- gather operands, lane totals, "previous node sample" values, candidate mask ----
+  double a[SS_EPT], b[SS_EPT];
+  float af[SS_EPT], bf[SS_EPT], pvv[SS_EPT];
+  unsigned act = 0, inner = 0;      // inner: candidate whose left neighbour lies in this lane's chunk
+  double ta = 0, tb = 0;
+  float lastv = 0.f;
+#pragma unroll
+  for (int j = 0; j < SS_EPT; ++j) {
+    const uint32_t idx = (iw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu;   // row padding holds index N (operand 0)
+    double w;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(w) : "r"(sw_addr + idx * 8u));   // 0 marks "not in this node"
+    const float wf = (float)w;
+    const bool on = w != 0.0;
+    pvv[j] = lastv;
+    if (on && act != 0 && __fadd_rn(lastv, eps) < v[j]) inner |= 1u << j;
+    act |= on ? (1u << j) : 0u;
+    lastv = on ? v[j] : lastv;
+    if (CRIT == CRIT_SQERR) {
+      if (HAS_Y) {
+        float y;
+        asm("ld.shared.f32 %0, [%1];" : "=f"(y) : "r"(sy_addr + idx * 4u));
+        a[j] = w; b[j] = (double)y * w; af[j] = wf; bf[j] = y * wf;
+      } else { a[j] = fabs(w); b[j] = w; af[j] = fabsf(wf); bf[j] = wf; }
+    } else {
+      a[j] = w < 0.0 ? -w : 0.0; b[j] = w > 0.0 ? w : 0.0;
+      af[j] = wf < 0.f ? -wf : 0.f; bf[j] = wf > 0.f ? wf : 0.f;
+    }
+    ta += a[j]; tb += b[j];
+  }
+  const int cnt = __popc(act);
+  // ---- warp exclusive scans of (ta, tb, cnt) ----
+  double ia = ta, ib = tb;
+  int ic = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const double xa = __shfl_up_sync(0xffffffffu, ia, d), xb = __shfl_up_sync(0xffffffffu, ib, d);
+    const int xc = __shfl_up_sync(0xffffffffu, ic, d);
+    if (lane >= d) { ia += xa; ib += xb; ic += xc; }
+  }
+  const double pa0 = carryA + (ia - ta), pb0 = carryB + (ib - tb);    // sums over node samples before this chunk
+  const int pc0 = carryCnt + (ic - cnt);
+  // value of the last node sample before this lane's chunk (for the first node sample of the chunk)
+  const uint32_t has_mask = __ballot_sync(0xffffffffu, act != 0);
+  const uint32_t before = has_mask & lt_mask;
+  const int src = before ? (31 - __clz(before)) : 0;
+  const float pv_other = __shfl_sync(0xffffffffu, lastv, src);
+  const float pv_in = before ? pv_other : carryV;
+  const bool pHas_in = before ? true : (carryHas != 0);
+  unsigned cand = inner;
+  const int first = act ? (__ffs(act) - 1) : 0;
+  if (act && pHas_in && __fadd_rn(pv_in, eps) < v[first]) cand |= 1u << first;
+  // ---- f32 estimate of the criterion at every candidate ----
+  float fa = (float)pa0, fb = (float)pb0;
+  float tmax = -3.0e38f;
+  unsigned pass = 0;
+#pragma unroll
+  for (int j = 0; j < SS_EPT; ++j) {
+    const float est = criterion32<CRIT>(fa, fb, ftotA, ftotB);
+    if (EXACT) { if (!(est < lim)) pass |= 1u << j; }
+    else tmax = ((cand >> j) & 1u) ? fmaxf(tmax, est == est ? est : 3.0e38f) : tmax;     // NaN (0/0 at the ends) counts as "unknown, maybe large"
+    fa += af[j]; fb += bf[j];
+  }
+  if (EXACT) {
+    pass &= cand;
+    double pa = pa0, pb = pb0;
+    int pc = pc0;
+#pragma unroll
+    for (int j = 0; j < SS_EPT; ++j) {
+      if (pass & (1u << j)) {
+        double num, den;
+        if (criterion_frac<CRIT>(pa, pb, totA, totB, num, den) && num * bestDen > bestNum * den) {
+          bestNum = num; bestDen = den; bestPos = pc - 1;
+          bestVl = (j == first) ? pv_in : pvv[j];
+          bestVr = v[j];
+        }
+      }
+      pa += a[j]; pb += b[j];
+      pc += (act >> j) & 1u;
+    }
+  }
+  // ---- carries for the next tile ----
+  carryA += __shfl_sync(0xffffffffu, ia, 31);
+  carryB += __shfl_sync(0xffffffffu, ib, 31);
+  carryCnt += __shfl_sync(0xffffffffu, ic, 31);
+  {
+    const int lastLane = has_mask ? 31 - __clz(has_mask) : 0;
+    const float lv = __shfl_sync(0xffffffffu, lastv, lastLane);
+    if (has_mask) { carryV = lv; carryHas = 1; }
+  }
+  return tmax;
+}
+
 template <int CRIT, bool HAS_Y>
 __global__ void __launch_bounds__(SS_THREADS, 1)
 k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ sval, int n_stride, int N, int nrows,
                    const double* __restrict__ wnode, const float* __restrict__ ynode, const NodeStats* __restrict__ stats,
                    float filter_abs, RowBest* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double* sw = reinterpret_cast<double*>(smem_raw);
-  float* sy = reinterpret_cast<float*>(sw + N);
-  for (int i = threadIdx.x; i < N; i += SS_THREADS) { sw[i] = wnode[i]; if (HAS_Y) sy[i] = ynode[i]; }
+  const int ntile = (N + SS_TILE - 1) / SS_TILE;
+  double* sw = reinterpret_cast<double*>(smem_raw);          // [N+1]; entry N = 0 is what the row padding points at
+  TileCarry* carries_all = reinterpret_cast<TileCarry*>(sw + N + 1);                 // [SS_WARPS][ntile]
+  float* tilemax_all = reinterpret_cast<float*>(carries_all + (size_t)SS_WARPS * ntile);   // [SS_WARPS][ntile]
+  float* sy = tilemax_all + (size_t)SS_WARPS * ntile;        // [N+1] (LogitBoost only)
+  for (int i = threadIdx.x; i <= N; i += SS_THREADS) { sw[i] = i < N ? wnode[i] : 0.0; if (HAS_Y) sy[i] = i < N ? ynode[i] : 0.f; }
   __syncthreads();
+  // 32-bit shared-window addresses: the per-sample gathers become plain LDS with one address add
+  const uint32_t sw_addr = (uint32_t)__cvta_generic_to_shared(sw);
+  const uint32_t sy_addr = (uint32_t)__cvta_generic_to_shared(sy);
   const NodeStats st = *stats;
   const double totA = st.rcw[0];
   const double totB = (CRIT == CRIT_SQERR) ? st.rsum0 : st.rcw[1];
@@ -351,7 +481,8 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
   // wrappers around the shuffles inside it)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const uint32_t lt_mask = (1u << lane) - 1u;
-  const float eps = FLT_EPSILON * 2;
+  TileCarry* carries = carries_all + (size_t)warp * ntile;
+  float* tilemax = tilemax_all + (size_t)warp * ntile;
 
   for (int row = blockIdx.x * SS_WARPS + warp; row < nrows; row += gridDim.x * SS_WARPS) {
     const uint16_t* ri = sidx + (size_t)row * n_stride;
@@ -359,106 +490,49 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
     double carryA = 0, carryB = 0;
     float carryV = 0.f;
     int carryHas = 0, carryCnt = 0;
-    double bestVal = -1.0;
+    double bestNum = -1.0, bestDen = 1.0;      // running best as an exact fraction
     int bestPos = -1;
     float bestVl = 0.f, bestVr = 0.f;
-    float best32 = -1.f;          // lane-local f32 image of bestVal
-    float thr32 = -3.0e38f;       // warp-uniform filter threshold, refreshed once per tile
+    float rmax = -3.0e38f;
 
+    // ---------------- pass 1: f32 estimates, per-tile maxima, per-tile carries ----------------
     uint4 nxt_i = *reinterpret_cast<const uint4*>(ri + lane * SS_EPT);
     float4 nxt_v0 = *reinterpret_cast<const float4*>(rv + lane * SS_EPT);
     float4 nxt_v1 = *reinterpret_cast<const float4*>(rv + lane * SS_EPT + 4);
-    for (int base = 0; base < N; base += SS_TILE) {
+    for (int t = 0; t < ntile; ++t) {
       const uint4 ci = nxt_i;
       const float4 cv0 = nxt_v0, cv1 = nxt_v1;
-      if (base + SS_TILE < N) {      // prefetch the next tile while this one is processed
-        nxt_i = *reinterpret_cast<const uint4*>(ri + base + SS_TILE + lane * SS_EPT);
-        nxt_v0 = *reinterpret_cast<const float4*>(rv + base + SS_TILE + lane * SS_EPT);
-        nxt_v1 = *reinterpret_cast<const float4*>(rv + base + SS_TILE + lane * SS_EPT + 4);
+      if (t + 1 < ntile) {           // prefetch the next tile while this one is processed
+        const int o = (t + 1) * SS_TILE + lane * SS_EPT;
+        nxt_i = *reinterpret_cast<const uint4*>(ri + o);
+        nxt_v0 = *reinterpret_cast<const float4*>(rv + o);
+        nxt_v1 = *reinterpret_cast<const float4*>(rv + o + 4);
       }
-      const int i0 = base + lane * SS_EPT;
-      const uint32_t iw[4] = {ci.x, ci.y, ci.z, ci.w};
-      const float v[SS_EPT] = {cv0.x, cv0.y, cv0.z, cv0.w, cv1.x, cv1.y, cv1.z, cv1.w};
-      double a[SS_EPT], b[SS_EPT];
-      float af[SS_EPT], bf[SS_EPT];
-      unsigned act = 0;
-      double ta = 0, tb = 0;
-      float lastv = 0.f;
+      if (lane == 0) { carries[t].a = carryA; carries[t].b = carryB; carries[t].v = carryV; carries[t].cnt_has = (carryCnt << 1) | carryHas; }
+      float tm = ss_tile<CRIT, HAS_Y, false>(ci, cv0, cv1, sw_addr, sy_addr, lane, lt_mask, totA, totB, ftotA, ftotB, carryA, carryB, carryV,
+                                             carryHas, carryCnt, 0.f, bestNum, bestDen, bestPos, bestVl, bestVr);
 #pragma unroll
-      for (int j = 0; j < SS_EPT; ++j) {
-        const int idx = (int)((iw[j >> 1] >> ((j & 1) * 16)) & 0xFFFFu);
-        const bool inb = i0 + j < N;
-        const double w = inb ? sw[idx] : 0.0;          // 0 marks "not in this node"
-        const float wf = (float)w;
-        const bool on = w != 0.0;
-        act |= on ? (1u << j) : 0u;
-        lastv = on ? v[j] : lastv;
-        if (CRIT == CRIT_SQERR) {
-          if (HAS_Y) {
-            const float y = inb ? sy[idx] : 0.f;
-            a[j] = w; b[j] = (double)y * w; af[j] = wf; bf[j] = y * wf;
-          } else { a[j] = fabs(w); b[j] = w; af[j] = fabsf(wf); bf[j] = wf; }
-        } else {
-          a[j] = w < 0.0 ? -w : 0.0; b[j] = w > 0.0 ? w : 0.0;
-          af[j] = wf < 0.f ? -wf : 0.f; bf[j] = wf > 0.f ? wf : 0.f;
-        }
-        ta += a[j]; tb += b[j];
-      }
-      const int cnt = __popc(act);
-      // warp exclusive scans of (ta, tb, cnt)
-      double ia = ta, ib = tb;
-      int ic = cnt;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const double xa = __shfl_up_sync(0xffffffffu, ia, d), xb = __shfl_up_sync(0xffffffffu, ib, d);
-        const int xc = __shfl_up_sync(0xffffffffu, ic, d);
-        if (lane >= d) { ia += xa; ib += xb; ic += xc; }
-      }
-      double pa = carryA + (ia - ta), pb = carryB + (ib - tb);
-      float fa = (float)pa, fb = (float)pb;
-      int pc = carryCnt + (ic - cnt);
-      // value of the last node sample before this lane's chunk
-      const uint32_t has_mask = __ballot_sync(0xffffffffu, act != 0);
-      const uint32_t before = has_mask & lt_mask;
-      const int src = before ? (31 - __clz(before)) : 0;
-      const float pv_other = __shfl_sync(0xffffffffu, lastv, src);
-      float pv = before ? pv_other : carryV;
-      bool pHas = before ? true : (carryHas != 0);
-      const float marg = 1e-5f * fabsf(best32) + filter_abs;
-      float lim = fmaxf(thr32, best32 - marg);       // candidates estimated below this cannot win
-#pragma unroll
-      for (int j = 0; j < SS_EPT; ++j) {
-        const bool on = (act >> j) & 1u;
-        const bool cand = on && pHas && (__fadd_rn(pv, eps) < v[j]);
-        const float est = criterion32<CRIT>(fa, fb, ftotA, ftotB);
-        if (cand && !(est < lim)) {                    // rare: exact f64 evaluation
-          const double val = criterion<CRIT>(pa, pb, totA, totB);
-          if (val > bestVal) {
-            bestVal = val; bestPos = pc - 1; bestVl = pv; bestVr = v[j]; best32 = (float)val;
-            lim = fmaxf(lim, best32 - (1e-5f * fabsf(best32) + filter_abs));
-          }
-        }
-        pa += a[j]; pb += b[j]; fa += af[j]; fb += bf[j];
-        pc += on ? 1 : 0;
-        pv = on ? v[j] : pv;
-        pHas = pHas || on;
-      }
-      // carries for the next tile
-      carryA += __shfl_sync(0xffffffffu, ia, 31);
-      carryB += __shfl_sync(0xffffffffu, ib, 31);
-      carryCnt += __shfl_sync(0xffffffffu, ic, 31);
-      {
-        const int lastLane = has_mask ? 31 - __clz(has_mask) : 0;
-        const float lv = __shfl_sync(0xffffffffu, lastv, lastLane);
-        if (has_mask) { carryV = lv; carryHas = 1; }
-      }
-      // share the best estimate across the warp: anything clearly below it cannot win the row
-      float wb = best32;
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) wb = fmaxf(wb, __shfl_xor_sync(0xffffffffu, wb, d));
-      thr32 = wb - (1e-5f * fabsf(wb) + filter_abs);
+      for (int d = 16; d > 0; d >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, d));
+      if (lane == 0) tilemax[t] = tm;
+      rmax = fmaxf(rmax, tm);
     }
+    __syncwarp();
+    // ---------------- pass 2: exact evaluation of the few tiles that can hold the maximum ----------------
+    const float lim = rmax - (1e-5f * fabsf(rmax) + filter_abs);
+    for (int t = 0; t < ntile; ++t) {
+      if (!(tilemax[t] >= lim)) continue;           // warp-uniform (shared memory broadcast)
+      const int o = t * SS_TILE + lane * SS_EPT;
+      const uint4 ci = *reinterpret_cast<const uint4*>(ri + o);
+      const float4 cv0 = *reinterpret_cast<const float4*>(rv + o), cv1 = *reinterpret_cast<const float4*>(rv + o + 4);
+      double cA = carries[t].a, cB = carries[t].b;
+      float cV = carries[t].v;
+      int cH = carries[t].cnt_has & 1, cC = carries[t].cnt_has >> 1;
+      ss_tile<CRIT, HAS_Y, true>(ci, cv0, cv1, sw_addr, sy_addr, lane, lt_mask, totA, totB, ftotA, ftotB, cA, cB, cV, cH, cC, lim, bestNum,
+                                 bestDen, bestPos, bestVl, bestVr);
+    }
+    __syncwarp();
     // warp argmax: larger value first, then smaller position (first maximum of the sequential scan)
+    double bestVal = bestPos >= 0 ? bestNum / bestDen : -1.0;
     int owner = lane;
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
@@ -910,13 +984,14 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
     k_argmax_rows<<<1, ONE_CTA, 0, ctx->stream>>>(nullptr, b->rowbest_cat, ctx->nrows, ctx->row0, b->d_best);
   } else {
     const bool has_y = b->boost_type == CC_BOOST_LOGIT;
-    const size_t smem = (size_t)N * 8 + (has_y ? (size_t)N * 4 : 0) + 16;
+    const int ntile = (N + SS_TILE - 1) / SS_TILE;
+    const size_t smem = (size_t)(N + 1) * 8 + (size_t)SS_WARPS * ntile * (sizeof(TileCarry) + 4) + (has_y ? (size_t)(N + 1) * 4 : 0) + 16;
     CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED, "split search: numSamples %d needs %zu B of shared memory (limit 227 KB)", N, smem);
     const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
     // absolute slack of the f32 pre-filter: the f32 prefix sums carry ~1e-6 * (node weight) * |y|max^2
     // of absolute error (see criterion32); LogitBoost targets are clipped to |z| <= 10 (boost.cpp:347).
     const double ymax2 = has_y ? 100.0 : 1.0;
-    const float filter_abs = (float)(8e-6 * (b->h_stats[nid].rcw[0] + b->h_stats[nid].rcw[1]) * ymax2 + 1e-30);
+    const float filter_abs = (float)(4e-6 * (b->h_stats[nid].rcw[0] + b->h_stats[nid].rcw[1]) * ymax2 + 1e-30);
     const int blocks = std::min((ctx->nrows + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
 #define LAUNCH_SS(CR, HY)                                                                                                   \
   {                                                                                                                         \

@@ -50,7 +50,9 @@ std::vector<HaarFeatureH> make_haar_catalog(int W, int H, int mode) {
     for (int y = 0; y < H; ++y)
       for (int dx = 1; dx <= W; ++dx)
         for (int dy = 1; dy <= H; ++dy) {
+          int shape = -1;
           for (const UprightSpec& s : kUpright) {
+            ++shape;
             if (mode < s.min_mode) continue;
             if (x + dx * s.mx > W || y + dy * s.my > H) continue;
             HaarFeatureH f;
@@ -63,13 +65,17 @@ std::vector<HaarFeatureH> make_haar_catalog(int W, int H, int mode) {
               f.r[k + 1] = {x + in.ox * dx, y + in.oy * dy, in.sx * dx, in.sy * dy};
               f.wt[k + 1] = in.wt;
             }
+            f.shape = shape; f.x = x; f.y = y; f.dx = dx; f.dy = dy;
             out.push_back(f);
           }
           if (mode != CC_HAAR_ALL) continue;
+          shape = 7;
           for (const TiltedSpec& s : kTilted) {
+            ++shape;
             HaarFeatureH f;
             std::memset(&f, 0, sizeof(f));
             f.tilted = 1;
+            f.shape = shape; f.x = x; f.y = y; f.dx = dx; f.dy = dy;
             f.wt[0] = -1.f;
             f.wt[1] = s.wt;
             if (s.along_x) {

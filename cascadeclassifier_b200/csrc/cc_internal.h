@@ -42,7 +42,7 @@ constexpr int TILE = 32;   // samples per integral tile (one warp lane per sampl
 
 // ---- host-side catalogs -------------------------------------------------------------------
 struct RectI { int x, y, w, h; };
-struct HaarFeatureH { int tilted; RectI r[3]; float wt[3]; };
+struct HaarFeatureH { int tilted; RectI r[3]; float wt[3]; int shape, x, y, dx, dy; };   // shape: 0..7 upright (x2,y2,x3,y3,x4,y4,x2y2,cs), 8..13 tilted
 struct LbpFeatureH { RectI r; };
 struct HogFeatureH { RectI cell0; };
 
@@ -70,6 +70,10 @@ inline int tap_off(uint32_t w) { return (int)(w & 0xFFFFu); }
 __host__ __device__
 #endif
 inline int tap_coef(uint32_t w) { return (int)(int8_t)((w >> 16) & 0xFFu); }
+
+// Work item of the separable upright-Haar precalc: all features sharing (x, dx) [kind 0] or (y, dy) [kind 1]
+struct SepPattern { uint8_t kind, p, d, flags; uint8_t lo, hi, pad0, pad1; };   // flags: bit t set = shape t has local features
+static_assert(sizeof(SepPattern) == 8, "SepPattern layout");
 
 struct LbpTaps { uint16_t off[16]; };           // 4x4 corner grid
 struct HogTaps { uint16_t off[4][4]; };         // 4 cells x 4 corners
@@ -139,6 +143,12 @@ struct cc_ctx {
   std::vector<int> upright_rows, tilted_rows;   // global feature indices by plane (Haar)
   cc::HaarTaps* d_taps_upright = nullptr;   // compact per-plane tap lists of the local shard
   cc::HaarTaps* d_taps_tilted = nullptr;
+  // separable upright precalc (cc_traindata.cu): feature-index tables and pattern list of the local shard
+  int32_t* d_sep_tab_row = nullptr;     // [5][W][W][H][HP]
+  int32_t* d_sep_tab_col = nullptr;     // [3][H][H][W][WP]
+  cc::SepPattern* d_sep_patterns = nullptr;
+  int n_sep_patterns = 0;
+  bool use_sep = false;
 
   // ---- train data ----
   int shard_rank = 0, shard_world = 1;

@@ -114,6 +114,228 @@ k_precalc_haar(const int32_t* __restrict__ plane_tiles, const float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Correctly rounded (int)acc / nf without the generic IEEE division sequence.
+// With r = RN(1/nf) precomputed per sample: q0 = RN(a*r); e0 = fma(-q0, nf, a) (exact); q1 = RN(q0 + e0*r);
+// e1 = fma(-q1, nf, a); q = RN(q1 + e1*r).  |a| < 2^24 is an integer, so a/nf is never a rounding tie and the
+// two correction steps land on RN(a/nf) (Markstein-style iteration; validated against __fdiv_rn on the GPU by
+// cc_debug_div_check / tests/test_gpu_features.py::test_fast_division_is_exact).  nf == 0 is handled by r = 0
+// (all terms vanish and the result is +0, as the reference returns).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float haar_recip(float nfv) { return nfv == 0.f ? 0.f : __frcp_rn(nfv); }
+template <int STEPS>
+__device__ __forceinline__ float haar_div(float a, float nfv, float r) {
+  float q = __fmul_rn(a, r);
+#pragma unroll
+  for (int k = 0; k < STEPS; ++k) {
+    const float e = __fmaf_rn(-q, nfv, a);
+    q = __fmaf_rn(e, r, q);
+  }
+  return q;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 / upright Haar, separable form.  Every upright shape of the catalog is a difference of a "row
+// function" (or, for the y-shapes, a "column function") of the integral image:
+//   x2   : acc = gA(y+dy) - gA(y)                 gA(r) = I(r,x) - 2 I(r,x+dx) + I(r,x+2dx)
+//   x3   : acc = gB(y+dy) - gB(y)                 gB(r) = I(r,x) - 2 I(r,x+dx) + 2 I(r,x+2dx) - I(r,x+3dx)
+//   x4   : acc = gC(y+dy) - gC(y)                 gC(r) = I(r,x) - 2 I(r,x+dx) + 2 I(r,x+3dx) - I(r,x+4dx)
+//   x2y2 : acc = gA(y) - 2 gA(y+dy) + gA(y+2dy)
+//   3x3  : acc = -(gW(y+3dy) - gW(y)) + 9 (gM(y+2dy) - gM(y+dy)),  gW(r) = I(r,x+3dx) - I(r,x), gM(r) = I(r,x+2dx) - I(r,x+dx)
+//   y2/y3/y4 : the transposes (column functions hA/hB/hC of c for fixed (y,dy); acc = h(x+dx) - h(x))
+// (expand -1*rect0 + 2*rect1 [+ 2*rect2 | 9*rect1] of src/haarfeatures.cpp:135-195 into corner terms).
+// All of it is exact int32 arithmetic, so (float)acc / nf equals the reference's value bit for bit.
+// A work item is one (x,dx) [or (y,dy)] pattern: the function is evaluated once per row into a per-warp
+// scratch column (lane == sample) and every feature of the pattern then costs ~1 shared load and a subtract,
+// instead of 6-9 tap loads and multiply-adds.  The feature -> fval row mapping comes from dense index tables
+// (-1 = shape absent from this mode / not in this rank's shard).
+// ------------------------------------------------------------------------------------------------
+constexpr int SEP_THREADS = 512;
+constexpr int SEP_WARPS = SEP_THREADS / 32;
+
+__device__ __forceinline__ void sep_store(float* __restrict__ out_col, int f, int n_stride, int acc, float nf, float rnf) {
+  __stcs(out_col + (size_t)f * n_stride, haar_div<2>((float)acc, nf, rnf));
+}
+
+__global__ void __launch_bounds__(SEP_THREADS, 1)
+k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restrict__ nf, const SepPattern* __restrict__ patterns,
+                   int npatterns, int patterns_per_chunk, const int32_t* __restrict__ tab_row, const int32_t* __restrict__ tab_col,
+                   int W, int H, int row_base, float* __restrict__ fval, int n_stride, int ntiles_used) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int S = W + 1, P = S * (H + 1);
+  const int HP = (H + 3) & ~3, WP = (W + 3) & ~3;
+  const int L = max(W, H) + 1;                                               // scratch column length
+  int32_t* stile = reinterpret_cast<int32_t*>(smem_raw);                      // [P][32]
+  int32_t* scratch_all = stile + (size_t)P * TILE;                            // [SEP_WARPS][2][L][32]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(scratch_all + (size_t)SEP_WARPS * 2 * L * TILE);
+  int* s_next = reinterpret_cast<int*>(bar + 1);
+
+  const int tile = blockIdx.x;
+  const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
+  if (threadIdx.x == 0) {
+    *s_next = 0;
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, tile_bytes);
+    bulk_g2s(stile, sum_tiles + (size_t)tile * P * TILE, tile_bytes, bar);
+  }
+  __syncthreads();
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  int32_t* sA = scratch_all + (size_t)warp * 2 * L * TILE + lane;             // element r at sA[r * 32]
+  int32_t* sB = sA + (size_t)L * TILE;
+  const float nfv = nf[tile * TILE + lane];
+  const float rnf = haar_recip(nfv);
+  float* out_col = fval + (tile * TILE + lane) - (size_t)row_base * n_stride;     // + f * n_stride = this sample's cell of row f
+  const int32_t* tl = stile + lane;
+  const int p_begin = blockIdx.y * patterns_per_chunk;
+  const int p_end = min(p_begin + patterns_per_chunk, npatterns);
+  mbar_wait(bar, 0);
+
+  for (;;) {
+    int pi = 0;
+    if (lane == 0) pi = p_begin + atomicAdd(s_next, 1);
+    pi = __shfl_sync(0xffffffffu, pi, 0);
+    if (pi >= p_end) break;
+    const SepPattern pat = patterns[pi];
+    const int p = pat.p, d = pat.d, lo = pat.lo, hi = pat.hi, flags = pat.flags;
+    if (pat.kind == 0) {
+      // ---------------- row pattern: x = p, dx = d; functions of the row r = 0..H ----------------
+      const int x = p, dx = d;
+      const bool has3 = x + 3 * dx <= W, has4 = x + 4 * dx <= W;
+      auto tabp = [&](int t, int y) { return tab_row + ((((size_t)t * W + x) * W + (dx - 1)) * H + y) * HP; };
+      if (flags & 0x09) {                      // gA: x2 (bit 0), x2y2 (bit 3)
+        for (int r = 0; r <= H; ++r) {
+          const int32_t* row = tl + (size_t)(r * S + x) * TILE;
+          sA[r * TILE] = row[0] - 2 * row[dx * TILE] + row[2 * dx * TILE];
+        }
+        __syncwarp();
+        for (int y = lo; y <= hi; ++y) {
+          const int gy = sA[y * TILE];
+          if (flags & 0x01) {
+            const int32_t* tp = tabp(0, y);
+            for (int dy0 = 1; dy0 <= H - y; dy0 += 4) {
+              const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
+              const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                if (fs[k] >= 0) sep_store(out_col, fs[k], n_stride, sA[(y + dy0 + k) * TILE] - gy, nfv, rnf);
+            }
+          }
+          if (flags & 0x08) {
+            const int32_t* tp = tabp(3, y);
+            for (int dy0 = 1; 2 * dy0 <= H - y; dy0 += 4) {
+              const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
+              const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int dy = dy0 + k;
+                if (fs[k] >= 0)
+                  sep_store(out_col, fs[k], n_stride, gy - 2 * sA[(y + dy) * TILE] + sA[(y + 2 * dy) * TILE], nfv, rnf);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (has3 && (flags & 0x02)) {            // gB: x3
+        for (int r = 0; r <= H; ++r) {
+          const int32_t* row = tl + (size_t)(r * S + x) * TILE;
+          sA[r * TILE] = row[0] - 2 * row[dx * TILE] + 2 * row[2 * dx * TILE] - row[3 * dx * TILE];
+        }
+        __syncwarp();
+        for (int y = lo; y <= hi; ++y) {
+          const int gy = sA[y * TILE];
+          const int32_t* tp = tabp(1, y);
+          for (int dy0 = 1; dy0 <= H - y; dy0 += 4) {
+            const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
+            const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (fs[k] >= 0) sep_store(out_col, fs[k], n_stride, sA[(y + dy0 + k) * TILE] - gy, nfv, rnf);
+          }
+        }
+        __syncwarp();
+      }
+      if (has3 && (flags & 0x10)) {            // gW, gM: centre-surround
+        for (int r = 0; r <= H; ++r) {
+          const int32_t* row = tl + (size_t)(r * S + x) * TILE;
+          sA[r * TILE] = row[3 * dx * TILE] - row[0];
+          sB[r * TILE] = row[2 * dx * TILE] - row[dx * TILE];
+        }
+        __syncwarp();
+        for (int y = lo; y <= hi; ++y) {
+          const int wy = sA[y * TILE];
+          const int32_t* tp = tabp(4, y);
+          for (int dy0 = 1; 3 * dy0 <= H - y; dy0 += 4) {
+            const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
+            const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int dy = dy0 + k;
+              if (fs[k] >= 0)
+                sep_store(out_col, fs[k], n_stride,
+                          wy - sA[(y + 3 * dy) * TILE] + 9 * (sB[(y + 2 * dy) * TILE] - sB[(y + dy) * TILE]), nfv, rnf);
+            }
+          }
+        }
+        __syncwarp();
+      }
+      if (has4 && (flags & 0x04)) {            // gC: x4
+        for (int r = 0; r <= H; ++r) {
+          const int32_t* row = tl + (size_t)(r * S + x) * TILE;
+          sA[r * TILE] = row[0] - 2 * row[dx * TILE] + 2 * row[3 * dx * TILE] - row[4 * dx * TILE];
+        }
+        __syncwarp();
+        for (int y = lo; y <= hi; ++y) {
+          const int gy = sA[y * TILE];
+          const int32_t* tp = tabp(2, y);
+          for (int dy0 = 1; dy0 <= H - y; dy0 += 4) {
+            const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
+            const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (fs[k] >= 0) sep_store(out_col, fs[k], n_stride, sA[(y + dy0 + k) * TILE] - gy, nfv, rnf);
+          }
+        }
+        __syncwarp();
+      }
+    } else {
+      // ---------------- column pattern: y = p, dy = d; functions of the column c = 0..W ----------------
+      const int y = p, dy = d;
+      auto tabp = [&](int t, int x) { return tab_col + ((((size_t)t * H + y) * H + (dy - 1)) * W + x) * WP; };
+      for (int t = 0; t < 3; ++t) {
+        if (!(flags & (1 << t))) continue;
+        if (y + (t + 2) * dy > H) continue;
+        const int32_t* r0 = tl + (size_t)(y * S) * TILE;
+        const int32_t* r1 = tl + (size_t)((y + dy) * S) * TILE;
+        const int32_t* r2 = tl + (size_t)((y + 2 * dy) * S) * TILE;
+        const int32_t* r3 = tl + (size_t)((y + min(3 * dy, H - y)) * S) * TILE;
+        const int32_t* r4 = tl + (size_t)((y + min(4 * dy, H - y)) * S) * TILE;
+        for (int c = 0; c <= W; ++c) {
+          int v;
+          if (t == 0) v = r0[c * TILE] - 2 * r1[c * TILE] + r2[c * TILE];
+          else if (t == 1) v = r0[c * TILE] - 2 * r1[c * TILE] + 2 * r2[c * TILE] - r3[c * TILE];
+          else v = r0[c * TILE] - 2 * r1[c * TILE] + 2 * r3[c * TILE] - r4[c * TILE];
+          sA[c * TILE] = v;
+        }
+        __syncwarp();
+        for (int x = lo; x <= hi; ++x) {
+          const int hx = sA[x * TILE];
+          const int32_t* tp = tabp(t, x);
+          for (int dx0 = 1; dx0 <= W - x; dx0 += 4) {
+            const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dx0 - 1));
+            const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (fs[k] >= 0) sep_store(out_col, fs[k], n_stride, sA[(x + dx0 + k) * TILE] - hx, nfv, rnf);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+}
+
 // K2 / LBP: same tiling; 16 corner taps -> 9 cell sums -> 8-bit code (lbpfeatures.h:70-83).
 constexpr int LBP_THREADS = 512;
 template <int TILES_PER_CTA>
@@ -277,8 +499,31 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
     uint16_t* drow = sidx + (size_t)row * n_stride;
     float* vrow = sval + (size_t)row * n_stride;
     for (int i = t; i < N; i += SORT_THREADS) { drow[i] = iin[i]; vrow[i] = key_to_float(kin[i]); }
+    // row padding up to the split-search tile: index N (an always-zero operand), value +max
+    for (int i = N + t; i < n_stride; i += SORT_THREADS) { drow[i] = (uint16_t)N; vrow[i] = 3.402823466e+38f; }
     __syncthreads();
   }
+}
+
+__global__ void k_div_check(int steps, unsigned long long seed, long long n, unsigned long long* mismatches) {
+  unsigned long long bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // splitmix64
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+    const int acc = (int)(z & 0x3FFFFF) - 0x200000;                       // [-2^21, 2^21)
+    // nf: positive float with exponent in [2^0, 2^23) and arbitrary mantissa; every 64th sample forces special mantissas
+    unsigned mant = (unsigned)(z >> 22) & 0x7FFFFFu;
+    const unsigned ex = 127u + (unsigned)((z >> 45) % 23);
+    if ((i & 63) == 0) mant = 0x7FFFFFu - (unsigned)((z >> 50) & 7u);
+    if ((i & 63) == 1) mant = (unsigned)((z >> 50) & 7u);
+    const float nfv = __uint_as_float((ex << 23) | mant);
+    const float r = haar_recip(nfv);
+    const float ref = __fdiv_rn((float)acc, nfv);
+    const float got = steps == 1 ? haar_div<1>((float)acc, nfv, r) : haar_div<2>((float)acc, nfv, r);
+    bad += __float_as_uint(ref + 0.0f) != __float_as_uint(got + 0.0f);
+  }
+  if (bad) atomicAdd(mismatches, bad);
 }
 
 // widen LBP codes / copy rows for the parity getters
@@ -351,6 +596,55 @@ int cc_boost_set_shard(cc_ctx* ctx, int rank, int world) {
         CC_CUDA(cudaMalloc(&ctx->d_taps_tilted, tt.size() * sizeof(HaarTaps)));
         CC_CUDA(cudaMemcpy(ctx->d_taps_tilted, tt.data(), tt.size() * sizeof(HaarTaps), cudaMemcpyHostToDevice));
       }
+      // ---- separable upright precalc: index tables + pattern list (only if one tile + scratch fit in smem) ----
+      cudaFree(ctx->d_sep_tab_row); cudaFree(ctx->d_sep_tab_col); cudaFree(ctx->d_sep_patterns);
+      ctx->d_sep_tab_row = ctx->d_sep_tab_col = nullptr; ctx->d_sep_patterns = nullptr; ctx->n_sep_patterns = 0; ctx->use_sep = false;
+      const int W = ctx->W, H = ctx->H;
+      const size_t sep_smem = (size_t)ctx->P * TILE * 4 + (size_t)SEP_WARPS * 2 * (std::max(W, H) + 1) * TILE * 4 + 64;
+      if (sep_smem <= 227 * 1024 && W <= 255 && H <= 255 && !up.empty()) {
+        const int HP = (H + 3) & ~3, WP = (W + 3) & ~3;
+        std::vector<int32_t> trow((size_t)5 * W * W * H * HP, -1), tcol((size_t)3 * H * H * W * WP, -1);
+        // per pattern: which shapes occur and the range of the outer loop variable that has local features
+        struct Acc { int flags = 0, lo = 1 << 30, hi = -1; };
+        std::vector<Acc> prow((size_t)W * W), pcol((size_t)H * H);
+        static const int row_t[8] = {0, -1, 1, -1, 2, -1, 3, 4};   // shape -> row-table type
+        static const int col_t[8] = {-1, 0, -1, 1, -1, 2, -1, -1}; // shape -> column-table type
+        for (int f : up) {
+          const HaarFeatureH& hf = ctx->haar[f];
+          if (row_t[hf.shape] >= 0) {
+            const int t = row_t[hf.shape];
+            trow[((((size_t)t * W + hf.x) * W + (hf.dx - 1)) * H + hf.y) * HP + (hf.dy - 1)] = f;
+            Acc& a = prow[(size_t)hf.x * W + (hf.dx - 1)];
+            a.flags |= 1 << t; a.lo = std::min(a.lo, hf.y); a.hi = std::max(a.hi, hf.y);
+          } else {
+            const int t = col_t[hf.shape];
+            tcol[((((size_t)t * H + hf.y) * H + (hf.dy - 1)) * W + hf.x) * WP + (hf.dx - 1)] = f;
+            Acc& a = pcol[(size_t)hf.y * H + (hf.dy - 1)];
+            a.flags |= 1 << t; a.lo = std::min(a.lo, hf.x); a.hi = std::max(a.hi, hf.x);
+          }
+        }
+        std::vector<SepPattern> pats;
+        for (int x = 0; x < W; ++x)
+          for (int dx = 1; dx <= W; ++dx) {
+            const Acc& a = prow[(size_t)x * W + (dx - 1)];
+            if (a.flags) pats.push_back({0, (uint8_t)x, (uint8_t)dx, (uint8_t)a.flags, (uint8_t)a.lo, (uint8_t)a.hi, 0, 0});
+          }
+        for (int y = 0; y < H; ++y)
+          for (int dy = 1; dy <= H; ++dy) {
+            const Acc& a = pcol[(size_t)y * H + (dy - 1)];
+            if (a.flags) pats.push_back({1, (uint8_t)y, (uint8_t)dy, (uint8_t)a.flags, (uint8_t)a.lo, (uint8_t)a.hi, 0, 0});
+          }
+        // heavy patterns (small d: most features) first, so that the dynamic per-CTA queue ends with light ones
+        std::stable_sort(pats.begin(), pats.end(), [](const SepPattern& a, const SepPattern& b) { return a.d < b.d; });
+        CC_CUDA(cudaMalloc(&ctx->d_sep_tab_row, trow.size() * sizeof(int32_t)));
+        CC_CUDA(cudaMemcpy(ctx->d_sep_tab_row, trow.data(), trow.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CC_CUDA(cudaMalloc(&ctx->d_sep_tab_col, tcol.size() * sizeof(int32_t)));
+        CC_CUDA(cudaMemcpy(ctx->d_sep_tab_col, tcol.data(), tcol.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+        CC_CUDA(cudaMalloc(&ctx->d_sep_patterns, pats.size() * sizeof(SepPattern)));
+        CC_CUDA(cudaMemcpy(ctx->d_sep_patterns, pats.data(), pats.size() * sizeof(SepPattern), cudaMemcpyHostToDevice));
+        ctx->n_sep_patterns = (int)pats.size();
+        ctx->use_sep = true;
+      }
     }
   }
   return CC_OK;
@@ -386,6 +680,20 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
       struct Launch { const int32_t* plane; const HaarTaps* taps; int n; };
       Launch ls[2] = {{ctx->d_sum, ctx->d_taps_upright, (int)ctx->upright_rows.size()},
                       {ctx->d_tilted, ctx->d_taps_tilted, (int)ctx->tilted_rows.size()}};
+      if (ctx->use_sep && ls[0].n > 0) {
+        ScopedTimer tm(ctx, "precalc", 1);
+        const size_t sep_smem = (size_t)P * TILE * 4 + (size_t)SEP_WARPS * 2 * (std::max(ctx->W, ctx->H) + 1) * TILE * 4 + 64;
+        // the list is sorted heavy-first; every CTA drains its chunk through a shared counter, the grid has many CTAs per SM
+        const int nchunks = std::max(1, std::min(ctx->n_sep_patterns / (SEP_WARPS * 2), (ctx->sm_count * 6 + ntiles_used - 1) / ntiles_used));
+        const int ppc = (ctx->n_sep_patterns + nchunks - 1) / nchunks;
+        CC_CUDA(cudaFuncSetAttribute(k_precalc_haar_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_smem));
+        dim3 grid(ntiles_used, (ctx->n_sep_patterns + ppc - 1) / ppc);
+        k_precalc_haar_sep<<<grid, SEP_THREADS, sep_smem, ctx->stream>>>(ctx->d_sum, ctx->d_nf, ctx->d_sep_patterns, ctx->n_sep_patterns, ppc,
+                                                                        ctx->d_sep_tab_row, ctx->d_sep_tab_col, ctx->W, ctx->H, ctx->row0,
+                                                                        ctx->d_fval, n_stride, ntiles_used);
+        CC_CUDA(cudaGetLastError());
+        ls[0].n = 0;      // upright rows are done
+      }
       for (const Launch& l : ls) {
         if (l.n == 0) continue;
         ScopedTimer tm(ctx, "precalc", 1);
@@ -438,6 +746,22 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
     CC_CUDA(cudaGetLastError());
   }
   ctx->precalc_valid = true;
+  return CC_OK;
+}
+
+int cc_debug_div_check(cc_ctx* ctx, int steps, uint64_t seed, int64_t n, uint64_t* mismatches) {
+  CC_REQUIRE(ctx && mismatches && (steps == 1 || steps == 2) && n > 0, CC_ERR_BAD_ARG, "cc_debug_div_check: bad arguments");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  unsigned long long* d = nullptr;
+  CC_CUDA(cudaMallocAsync(&d, sizeof(unsigned long long), ctx->stream));
+  CC_CUDA(cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+  k_div_check<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(steps, seed, n, d);
+  CC_CUDA(cudaGetLastError());
+  unsigned long long h = 0;
+  CC_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  CC_CUDA(cudaFreeAsync(d, ctx->stream));
+  *mismatches = h;
   return CC_OK;
 }
 

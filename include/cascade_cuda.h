@@ -188,6 +188,9 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
 int cc_timing_reset(cc_ctx* ctx);
 int cc_timing_get(cc_ctx* ctx, const char* name, double* ms, int64_t* launches);
 int64_t cc_launch_count(cc_ctx* ctx);
+/* self-check of the reciprocal-based Haar division used by K2 against IEEE division on n pseudo-random
+ * (integer numerator, normalisation factor) pairs; steps = number of correction iterations (1 or 2) */
+int cc_debug_div_check(cc_ctx* ctx, int steps, uint64_t seed, int64_t n, uint64_t* mismatches);
 
 #ifdef __cplusplus
 }

@@ -147,3 +147,12 @@ def test_precalc_and_sort_match_oracle(gpu_ctx, ftype, mode, W, H, npos, nneg):
             gv = np.zeros((nr, n), np.float32)
             check(lib.cc_boost_get_sorted_val(h, r0, nr, gv.ctypes.data_as(C.c_void_p)), "get_sval")
             assert np.array_equal(gv, np.take_along_axis(td.fval(), td.sidx().astype(np.int64), axis=1))
+
+
+def test_fast_division_is_exact(gpu_ctx):
+    """The reciprocal-based Haar division of K2 equals IEEE division on 2e9 (integer, norm-factor) pairs."""
+    import ctypes as C
+    from cascadeclassifier_b200._lib import check
+    m = C.c_uint64(1)
+    check(gpu_ctx.lib.cc_debug_div_check(gpu_ctx.h, 2, 12345, 2_000_000_000, C.byref(m)), "div_check")
+    assert m.value == 0
