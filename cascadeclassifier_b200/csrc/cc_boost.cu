@@ -95,6 +95,9 @@ struct TreeSummary {
   int num_pos, num_neg;
 };
 
+// control block of one pruned search: packed argmax keys (quality bits << 32 | ~row) and the flagged-row counter
+struct SearchCtl { unsigned long long key; unsigned int nflag; unsigned int pad; };
+
 struct BoostBuffers {
   int cap_n = 0;
   size_t cap_rows = 0;
@@ -116,6 +119,14 @@ struct BoostBuffers {
   int boost_type = CC_BOOST_GENTLE, crit = CRIT_SQERR, is_classifier = 0, have_subsample = 0;
   cc_boost_params params;
   bool row_quality_valid = false;
+  // pruned ordered split search (k_ss_bound): control block, seed / flagged row lists, statistics
+  struct SearchCtl* d_ctl = nullptr;
+  int* d_seed_rows = nullptr;
+  int* d_flag_rows = nullptr;
+  std::vector<int> seed_rows;         // strided sample of the local rows + the winners of this stage so far
+  int seed_cap = 0, n_seed_static = 0;
+  int search_mode = 0;                // 0 = pruned (default), 1 = exhaustive (every row evaluated exactly)
+  long long stat_searches = 0, stat_seed_rows = 0, stat_flag_rows = 0;
 };
 
 int boost_free(cc_ctx* ctx) {
@@ -124,7 +135,7 @@ int boost_free(cc_ctx* ctx) {
     cudaFree(b->weights); cudaFree(b->weak_eval); cudaFree(b->stage_sum); cudaFree(b->sum_response); cudaFree(b->wnode);
     cudaFree(b->treeval); cudaFree(b->responses); cudaFree(b->ynode); cudaFree(b->orig_response); cudaFree(b->mask);
     cudaFree(b->node_of); cudaFree(b->rowbest); cudaFree(b->rowbest_cat); cudaFree(b->d_stats); cudaFree(b->d_best);
-    cudaFree(b->d_summary); cudaFree(b->d_tree);
+    cudaFree(b->d_summary); cudaFree(b->d_tree); cudaFree(b->d_ctl); cudaFree(b->d_seed_rows); cudaFree(b->d_flag_rows);
     cudaFreeHost(b->h_stats); cudaFreeHost(b->h_best); cudaFreeHost(b->h_summary);
     delete b;
     ctx->boost = nullptr;
@@ -132,6 +143,8 @@ int boost_free(cc_ctx* ctx) {
   traindata_free(ctx);
   return CC_OK;
 }
+
+constexpr int SEED_TARGET = 2048;      // rows evaluated exactly up front to obtain the pruning threshold
 
 static int ensure_boost(cc_ctx* ctx, int N, size_t nrows) {
   if (!ctx->boost) ctx->boost = new BoostBuffers();
@@ -141,6 +154,7 @@ static int ensure_boost(cc_ctx* ctx, int N, size_t nrows) {
     CC_CUDA(cudaMalloc(&b->d_best, sizeof(BestSplit) * 16));
     CC_CUDA(cudaMalloc(&b->d_summary, sizeof(TreeSummary)));
     CC_CUDA(cudaMalloc(&b->d_tree, sizeof(DevNode) * CC_MAX_TREE_NODES));
+    CC_CUDA(cudaMalloc(&b->d_ctl, sizeof(SearchCtl)));
     CC_CUDA(cudaMallocHost(&b->h_stats, sizeof(NodeStats) * CC_MAX_TREE_NODES));
     CC_CUDA(cudaMallocHost(&b->h_best, sizeof(BestSplit) * 16));
     CC_CUDA(cudaMallocHost(&b->h_summary, sizeof(TreeSummary)));
@@ -156,10 +170,15 @@ static int ensure_boost(cc_ctx* ctx, int N, size_t nrows) {
     b->cap_n = N;
   }
   if (nrows > b->cap_rows) {
-    cudaFree(b->rowbest); cudaFree(b->rowbest_cat);
-    b->rowbest = nullptr; b->rowbest_cat = nullptr;
+    cudaFree(b->rowbest); cudaFree(b->rowbest_cat); cudaFree(b->d_flag_rows); cudaFree(b->d_seed_rows);
+    b->rowbest = nullptr; b->rowbest_cat = nullptr; b->d_flag_rows = nullptr; b->d_seed_rows = nullptr;
     if (ctx->ftype == CC_FEATURE_LBP) CC_CUDA(cudaMalloc(&b->rowbest_cat, nrows * sizeof(RowBestCat)));
-    else CC_CUDA(cudaMalloc(&b->rowbest, nrows * sizeof(RowBest)));
+    else {
+      CC_CUDA(cudaMalloc(&b->rowbest, nrows * sizeof(RowBest)));
+      CC_CUDA(cudaMalloc(&b->d_flag_rows, nrows * sizeof(int)));
+      b->seed_cap = SEED_TARGET + 256;
+      CC_CUDA(cudaMalloc(&b->d_seed_rows, b->seed_cap * sizeof(int)));
+    }
     b->cap_rows = nrows;
   }
   return CC_OK;
@@ -461,8 +480,12 @@ template <int CRIT, bool HAS_Y>
 __global__ void __launch_bounds__(SS_THREADS, 1)
 k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ sval, int n_stride, int N, int nrows,
                    const double* __restrict__ wnode, const float* __restrict__ ynode, const NodeStats* __restrict__ stats,
-                   float filter_abs, RowBest* __restrict__ out) {
+                   float filter_abs, RowBest* __restrict__ out, const int* __restrict__ row_list,
+                   const unsigned int* __restrict__ list_count, SearchCtl* __restrict__ ctl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  // rows to search: all local rows, or the entries of row_list (seed rows / rows flagged by k_ss_bound)
+  const int nwork = row_list ? (list_count ? (int)min(*list_count, (unsigned int)nrows) : nrows) : nrows;
+  if (blockIdx.x * SS_WARPS >= nwork) return;
   const int ntile = (N + SS_TILE - 1) / SS_TILE;
   double* sw = reinterpret_cast<double*>(smem_raw);          // [N+1]; entry N = 0 is what the row padding points at
   TileCarry* carries_all = reinterpret_cast<TileCarry*>(sw + N + 1);                 // [SS_WARPS][ntile]
@@ -484,7 +507,8 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
   TileCarry* carries = carries_all + (size_t)warp * ntile;
   float* tilemax = tilemax_all + (size_t)warp * ntile;
 
-  for (int row = blockIdx.x * SS_WARPS + warp; row < nrows; row += gridDim.x * SS_WARPS) {
+  for (int wi = blockIdx.x * SS_WARPS + warp; wi < nwork; wi += gridDim.x * SS_WARPS) {
+    const int row = row_list ? row_list[wi] : wi;
     const uint16_t* ri = sidx + (size_t)row * n_stride;
     const float* rv = sval + (size_t)row * n_stride;
     double carryA = 0, carryB = 0;
@@ -550,8 +574,121 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
       rb.vleft = vl;
       rb.pos = bestPos;
       out[row] = rb;
+      // running argmax over rows: highest f32 quality, lowest row on ties (CvDTree::find_best_split, o_cvdtree.cpp:340)
+      if (rb.q > 0.f) {
+        const unsigned long long k = ((unsigned long long)__float_as_uint(rb.q) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)row);
+        if (k > *reinterpret_cast<volatile unsigned long long*>(&ctl->key)) atomicMax(&ctl->key, k);
+      }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pruning pass of the ordered split search (all criteria over two class weights: GAB squared error with
+// +-1 targets, Gini, misclassification).
+//
+// Write the state of the reference's running sums after a prefix of the sorted node samples as
+// (L, D) = (sum |x|, sum x) with the signed per-sample operand x (y*w for GAB, +-w by class otherwise).
+// Every criterion is a convex function of (L, D):
+//   squared error  C(L,D) = D^2/L + (S-D)^2/(T-L)            (o_cvboostree.cpp:398-414)
+//   Gini           (lsum2*R + rsum2*L)/(L*R) = T/2 + C/2      (:205-225, with lsum2 = (L^2+D^2)/2)
+//   misclass       max(T1 - D, T0 + D)                        (:226-243)
+// While the scan walks through a chunk of consecutive sorted positions, (L, D) moves by steps (|x|, x), so
+// it stays inside the parallelogram spanned by P*(1,1) and M*(1,-1) (P, M = sums of the positive / negative
+// operands of the chunk).  A convex function attains its maximum over that parallelogram at a corner, hence
+//   max over the chunk's split candidates <= max over 3 corners (the 4th is the previous chunk's end).
+// A row none of whose chunks can beat the best quality already known (the exact result over the seed rows,
+// minus a margin that covers the f32 arithmetic of this pass) cannot hold the winning split and is dropped;
+// the others are appended to the flagged list and evaluated exactly by k_split_search_ord.  The pass reads
+// only the u16 index row (2 B per element) and needs no sorted values: the bound holds for admissible and
+// inadmissible (tied) positions alike, and samples outside the node carry operand 0.
+// ------------------------------------------------------------------------------------------------
+constexpr int SB_THREADS = 512;
+constexpr int SB_WARPS = SB_THREADS / 32;
+constexpr int SB_EPT = 16;
+constexpr int SB_TILE = 32 * SB_EPT;
+
+template <bool MISCLASS>
+__device__ __forceinline__ bool sb_corner(float L, float D, float T, float S, float Gp, float eps) {
+  if (MISCLASS) return fmaxf(S - D, T + D) > Gp;          // T = T0, S = T1
+  const float Lc = fmaxf(L, eps), Rc = fmaxf(T - L, eps), Dr = S - D;
+  const float num = fmaf(D * D, Rc, (Dr * Dr) * Lc), den = Lc * Rc;
+  return fmaf(-Gp, den, num) > 0.f;
+}
+
+template <bool MISCLASS>
+__global__ void __launch_bounds__(SB_THREADS, 3)
+k_ss_bound(const uint16_t* __restrict__ sidx, int n_stride, int N, int nrows, const double* __restrict__ wnode,
+           const NodeStats* __restrict__ stats, int crit, SearchCtl* __restrict__ ctl, int* __restrict__ flag_rows) {
+  extern __shared__ __align__(16) float sx[];                // [N+1]; entry N = 0 is what the row padding points at
+  for (int i = threadIdx.x; i <= N; i += SB_THREADS) sx[i] = i < N ? (float)wnode[i] : 0.f;
+  __syncthreads();
+  const NodeStats st = *stats;
+  const float g0 = __uint_as_float((unsigned)(ctl->key >> 32));   // best exact quality so far (0: none)
+  float T, S, Gp, eps;
+  {
+    const double W = crit == CRIT_SQERR ? st.rcw[0] : st.rcw[0] + st.rcw[1];     // total node weight
+    // margin: f32 prefix sums (<= 1.5e-6 W abs. error on L and D, |dC/dL| <= 1, |dC/dD| <= 4), clamping of L, R at
+    // eps = 4e-6 W (<= 2 eps), f32 evaluation of the test (<= 1e-6 C) -- see DESIGN.md
+    const double m = 1e-5 * fabs((double)g0) + 2.4e-5 * W;
+    eps = (float)(4e-6 * W);
+    if (MISCLASS) { T = (float)st.rcw[0]; S = (float)st.rcw[1]; Gp = (float)((double)g0 - m); }
+    else if (crit == CRIT_GINI) { T = (float)W; S = (float)(st.rcw[1] - st.rcw[0]); Gp = (float)(2.0 * ((double)g0 - m) - W); }
+    else { T = (float)W; S = (float)st.rsum0; Gp = (float)((double)g0 - m); }
+  }
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int ntile = (n_stride + SB_TILE - 1) / SB_TILE;
+  const uint32_t padw = (uint32_t)N | ((uint32_t)N << 16);
+  const uint4 pad4 = make_uint4(padw, padw, padw, padw);
+
+  for (int row = blockIdx.x * SB_WARPS + warp; row < nrows; row += gridDim.x * SB_WARPS) {
+    const uint16_t* ri = sidx + (size_t)row * n_stride;
+    double carryL = 0.0, carryD = 0.0;
+    bool fire = false;
+    uint4 n0 = pad4, n1 = pad4;
+    { const int o = lane * SB_EPT; if (o < n_stride) { n0 = __ldcs(reinterpret_cast<const uint4*>(ri + o)); n1 = __ldcs(reinterpret_cast<const uint4*>(ri + o + 8)); } }
+    for (int t = 0; t < ntile; ++t) {
+      const uint4 c0 = n0, c1 = n1;
+      { const int o = (t + 1) * SB_TILE + lane * SB_EPT;
+        if (o < n_stride) { n0 = __ldcs(reinterpret_cast<const uint4*>(ri + o)); n1 = __ldcs(reinterpret_cast<const uint4*>(ri + o + 8)); } else { n0 = pad4; n1 = pad4; } }
+      const uint32_t iw[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+      float ta = 0.f, td = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float x0 = sx[iw[j] & 0xFFFFu], x1 = sx[iw[j] >> 16];
+        ta += fabsf(x0); td += x0;
+        ta += fabsf(x1); td += x1;
+      }
+      float ia = ta, id = td;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const float xa = __shfl_up_sync(0xffffffffu, ia, d), xd = __shfl_up_sync(0xffffffffu, id, d);
+        if (lane >= d) { ia += xa; id += xd; }
+      }
+      const float L0 = (float)carryL + (ia - ta), D0 = (float)carryD + (id - td);
+      const float P = 0.5f * (ta + td), M = 0.5f * (ta - td);
+      fire = sb_corner<MISCLASS>(L0 + P, D0 + P, T, S, Gp, eps) | sb_corner<MISCLASS>(L0 + M, D0 - M, T, S, Gp, eps) |
+             sb_corner<MISCLASS>(L0 + ta, D0 + td, T, S, Gp, eps);
+      if (__any_sync(0xffffffffu, fire)) { fire = true; break; }
+      carryL += (double)__shfl_sync(0xffffffffu, ia, 31);
+      carryD += (double)__shfl_sync(0xffffffffu, id, 31);
+    }
+    if (fire && lane == 0) flag_rows[atomicAdd(&ctl->nflag, 1u)] = row;
+  }
+}
+
+// winner of the search from the packed key (pruned path; replaces k_argmax_rows)
+__global__ void k_finalize_best(const SearchCtl* __restrict__ ctl, const RowBest* __restrict__ rows, int row_base, BestSplit* out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  BestSplit b;
+  memset(&b, 0, sizeof(b));
+  const unsigned long long k = ctl->key;
+  if (k != 0ull) {
+    const int r = (int)(0xFFFFFFFFu - (unsigned)(k & 0xFFFFFFFFull));
+    b.q = rows[r].q; b.valid = b.q > 0.f; b.var = row_base + r; b.c = rows[r].c; b.vleft = rows[r].vleft; b.pos = rows[r].pos;
+  } else { b.q = -1.f; b.valid = 0; }
+  b.pad[0] = (int)ctl->nflag;
+  *out = b;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -993,21 +1130,56 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
     const double ymax2 = has_y ? 100.0 : 1.0;
     const float filter_abs = (float)(4e-6 * (b->h_stats[nid].rcw[0] + b->h_stats[nid].rcw[1]) * ymax2 + 1e-30);
     const int blocks = std::min((ctx->nrows + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
-#define LAUNCH_SS(CR, HY)                                                                                                   \
+    const bool pruned = b->search_mode == 0 && !has_y && ctx->nrows >= 4 * SEED_TARGET;
+    CC_CUDA(cudaMemsetAsync(b->d_ctl, 0, sizeof(SearchCtl), ctx->stream));
+#define LAUNCH_SS(CR, HY, BLOCKS, NWORK, LIST, COUNT)                                                                       \
   {                                                                                                                         \
     CC_CUDA(cudaFuncSetAttribute(k_split_search_ord<CR, HY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-    k_split_search_ord<CR, HY><<<blocks, SS_THREADS, smem, ctx->stream>>>(ctx->d_sidx, ctx->d_sval, ctx->n_stride, N, ctx->nrows, \
-                                                                          b->wnode, b->ynode, b->d_stats + nid, filter_abs, b->rowbest); \
+    k_split_search_ord<CR, HY><<<BLOCKS, SS_THREADS, smem, ctx->stream>>>(ctx->d_sidx, ctx->d_sval, ctx->n_stride, N, NWORK, \
+                                                                          b->wnode, b->ynode, b->d_stats + nid, filter_abs, b->rowbest, \
+                                                                          LIST, COUNT, b->d_ctl);                           \
   }
-    if (b->crit == CRIT_SQERR) { if (has_y) LAUNCH_SS(CRIT_SQERR, true) else LAUNCH_SS(CRIT_SQERR, false) }
-    else if (b->crit == CRIT_GINI) LAUNCH_SS(CRIT_GINI, false)
-    else LAUNCH_SS(CRIT_MISCLASS, false)
+#define LAUNCH_SS_CRIT(BLOCKS, NWORK, LIST, COUNT)                                                             \
+  {                                                                                                            \
+    if (b->crit == CRIT_SQERR) { if (has_y) LAUNCH_SS(CRIT_SQERR, true, BLOCKS, NWORK, LIST, COUNT) else LAUNCH_SS(CRIT_SQERR, false, BLOCKS, NWORK, LIST, COUNT) } \
+    else if (b->crit == CRIT_GINI) LAUNCH_SS(CRIT_GINI, false, BLOCKS, NWORK, LIST, COUNT)                     \
+    else LAUNCH_SS(CRIT_MISCLASS, false, BLOCKS, NWORK, LIST, COUNT)                                           \
+    CC_CUDA(cudaGetLastError());                                                                               \
+  }
+    if (!pruned) {
+      LAUNCH_SS_CRIT(blocks, ctx->nrows, (const int*)nullptr, (const unsigned int*)nullptr)
+      k_argmax_rows<<<1, ONE_CTA, 0, ctx->stream>>>(b->rowbest, nullptr, ctx->nrows, ctx->row0, b->d_best);
+      b->row_quality_valid = true;
+    } else {
+      // (1) exact search over the seed rows -> pruning threshold, (2) bound pass over every row, (3) exact search
+      // over the flagged rows, (4) winner from the packed key
+      const int nseed = (int)b->seed_rows.size();
+      const int seed_blocks = std::min((nseed + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
+      LAUNCH_SS_CRIT(seed_blocks, nseed, b->d_seed_rows, (const unsigned int*)nullptr)
+      const size_t bsmem = (size_t)(N + 1) * sizeof(float);
+      const int bper_sm = std::max(1, std::min(3, (int)((220 * 1024) / (bsmem + 1024))));
+      const int bblocks = std::min((ctx->nrows + SB_WARPS - 1) / SB_WARPS, ctx->sm_count * bper_sm);
+      if (b->crit == CRIT_MISCLASS) {
+        CC_CUDA(cudaFuncSetAttribute(k_ss_bound<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        k_ss_bound<true><<<bblocks, SB_THREADS, bsmem, ctx->stream>>>(ctx->d_sidx, ctx->n_stride, N, ctx->nrows, b->wnode, b->d_stats + nid, b->crit,
+                                                                     b->d_ctl, b->d_flag_rows);
+      } else {
+        CC_CUDA(cudaFuncSetAttribute(k_ss_bound<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem));
+        k_ss_bound<false><<<bblocks, SB_THREADS, bsmem, ctx->stream>>>(ctx->d_sidx, ctx->n_stride, N, ctx->nrows, b->wnode, b->d_stats + nid, b->crit,
+                                                                      b->d_ctl, b->d_flag_rows);
+      }
+      CC_CUDA(cudaGetLastError());
+      LAUNCH_SS_CRIT(blocks, ctx->nrows, b->d_flag_rows, &b->d_ctl->nflag)
+      k_finalize_best<<<1, 32, 0, ctx->stream>>>(b->d_ctl, b->rowbest, ctx->row0, b->d_best);
+      b->row_quality_valid = false;
+      b->stat_searches++; b->stat_seed_rows += nseed;
+      ctx->launches += 3;
+    }
+#undef LAUNCH_SS_CRIT
 #undef LAUNCH_SS
-    CC_CUDA(cudaGetLastError());
-    k_argmax_rows<<<1, ONE_CTA, 0, ctx->stream>>>(b->rowbest, nullptr, ctx->nrows, ctx->row0, b->d_best);
   }
   CC_CUDA(cudaGetLastError());
-  b->row_quality_valid = true;
+  if (ctx->ftype == CC_FEATURE_LBP) b->row_quality_valid = true;
   return CC_OK;
 }
 
@@ -1051,7 +1223,16 @@ static int grow_node(cc_ctx* ctx, BoostBuffers* b, std::vector<HostNode>& nodes,
   CC_CUDA(cudaMemcpyAsync(b->h_best, b->d_best, sizeof(BestSplit), cudaMemcpyDeviceToHost, ctx->stream));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
   const BestSplit bs = *b->h_best;
+  if (b->d_seed_rows && !b->row_quality_valid) b->stat_flag_rows += bs.pad[0];
   if (!bs.valid) return CC_OK;
+  if (b->d_seed_rows && bs.var >= ctx->row0 && bs.var < ctx->row0 + ctx->nrows && (int)b->seed_rows.size() < b->seed_cap) {
+    // the winner of this search stays a strong candidate for the next ones: evaluate it exactly up front
+    const int lr = bs.var - ctx->row0;
+    if (std::find(b->seed_rows.begin(), b->seed_rows.end(), lr) == b->seed_rows.end()) {
+      b->seed_rows.push_back(lr);
+      CC_CUDA(cudaMemcpyAsync(b->d_seed_rows + b->seed_rows.size() - 1, &b->seed_rows.back(), sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
   CC_REQUIRE((int)nodes.size() + 2 <= CC_MAX_TREE_NODES, CC_ERR_UNSUPPORTED, "tree grew beyond %d nodes (max_depth too large)", CC_MAX_TREE_NODES);
   const int lid = (int)nodes.size(), rid = lid + 1;
   HostNode l, r;
@@ -1104,6 +1285,14 @@ int cc_boost_train(cc_ctx* ctx, int num_samples, const cc_boost_params* p, cc_st
     k_boost_init<<<(N + 255) / 256, 256, 0, ctx->stream>>>(N, ctx->d_labels, b->boost_type, b->weights, b->weak_eval, b->stage_sum,
                                                            b->sum_response, b->responses, b->orig_response, b->mask);
     CC_CUDA(cudaGetLastError());
+  }
+  if (b->d_seed_rows) {     // seed rows of the pruned split search: a strided sample of the local rows
+    const int stride = std::max(1, ctx->nrows / SEED_TARGET);
+    b->seed_rows.clear();
+    b->seed_rows.reserve(b->seed_cap);
+    for (int r = stride / 2; r < ctx->nrows && (int)b->seed_rows.size() < SEED_TARGET; r += stride) b->seed_rows.push_back(r);
+    b->n_seed_static = (int)b->seed_rows.size();
+    CC_CUDA(cudaMemcpyAsync(b->d_seed_rows, b->seed_rows.data(), sizeof(int) * b->seed_rows.size(), cudaMemcpyHostToDevice, ctx->stream));
   }
   out->num_weak = 0; out->num_log = 0; out->threshold = 0.f; out->trained = 0;
   const EvalView ev = make_eval_view(ctx);
@@ -1168,8 +1357,24 @@ int cc_boost_get_weights(cc_ctx* ctx, double* weights, uint8_t* mask) {
   return CC_OK;
 }
 
+int cc_boost_set_search_mode(cc_ctx* ctx, int mode) {
+  CC_REQUIRE(ctx && (mode == 0 || mode == 1), CC_ERR_BAD_ARG, "cc_boost_set_search_mode: mode must be 0 (pruned) or 1 (exhaustive)");
+  if (!ctx->boost) ctx->boost = new BoostBuffers();
+  ctx->boost->search_mode = mode;
+  return CC_OK;
+}
+
+int cc_boost_get_search_stats(cc_ctx* ctx, int64_t* searches, int64_t* seed_rows, int64_t* flagged_rows) {
+  CC_REQUIRE(ctx && ctx->boost, CC_ERR_STATE, "cc_boost_get_search_stats: no stage has been trained");
+  if (searches) *searches = ctx->boost->stat_searches;
+  if (seed_rows) *seed_rows = ctx->boost->stat_seed_rows;
+  if (flagged_rows) *flagged_rows = ctx->boost->stat_flag_rows;
+  return CC_OK;
+}
+
 int cc_boost_get_row_quality(cc_ctx* ctx, int row0, int nrows, float* out) {
-  CC_REQUIRE(ctx && ctx->boost && ctx->boost->row_quality_valid, CC_ERR_STATE, "cc_boost_get_row_quality: no split search has run");
+  CC_REQUIRE(ctx && ctx->boost && ctx->boost->row_quality_valid, CC_ERR_STATE,
+             "cc_boost_get_row_quality: no exhaustive split search has run (cc_boost_set_search_mode(ctx, 1) keeps every row's quality)");
   CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows, CC_ERR_BAD_ARG, "cc_boost_get_row_quality: rows out of range");
   CC_CUDA(cudaSetDevice(ctx->device));
   float* tmp = nullptr;

@@ -49,6 +49,15 @@ class Context:
     def launch_count(self):
         return int(self.lib.cc_launch_count(self.h))
 
+    def set_search_mode(self, mode):
+        """0 = pruned split search (default), 1 = exhaustive (every variable searched exactly)."""
+        check(self.lib.cc_boost_set_search_mode(self.h, int(mode)), "cc_boost_set_search_mode")
+
+    def search_stats(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        check(self.lib.cc_boost_get_search_stats(self.h, C.byref(a), C.byref(b), C.byref(c)), "cc_boost_get_search_stats")
+        return dict(searches=a.value, seed_rows=b.value, flagged_rows=c.value)
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.cc_destroy(self.h)

@@ -142,7 +142,14 @@ int cc_boost_train(cc_ctx* ctx, int num_samples, const cc_boost_params* params, 
 /* state after training, for parity tests: AdaBoost weights and subsample mask (src/boost.cpp:168-407,
  * src/o_cvboost.cpp:101-139) */
 int cc_boost_get_weights(cc_ctx* ctx, double* weights, uint8_t* mask);
-/* per-variable best split quality of the LAST root-node search (0 where no split), local rows */
+/* Ordered-variable split search strategy.  0 (default) = pruned: a bound pass over the u16 index rows drops every
+ * variable that cannot beat the best split already known, the rest is searched exactly -- same winner as the
+ * serial loop of DTreeBestSplitFinder (src/o_cvdtree.cpp:313-357), whose init_quality threading prunes in the
+ * same spirit.  1 = exhaustive: every variable searched exactly (keeps per-variable qualities for the getter). */
+int cc_boost_set_search_mode(cc_ctx* ctx, int mode);
+/* counters since cc_create: pruned searches run, rows searched exactly as seeds, rows flagged by the bound pass */
+int cc_boost_get_search_stats(cc_ctx* ctx, int64_t* searches, int64_t* seed_rows, int64_t* flagged_rows);
+/* per-variable best split quality of the LAST root-node search (0 where no split), local rows; exhaustive mode only */
 int cc_boost_get_row_quality(cc_ctx* ctx, int row0, int nrows, float* out);
 
 /* CvCascadeBoost::predict(sampleIdx), src/boost.cpp:461-477, for stages given as flat arrays */

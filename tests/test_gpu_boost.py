@@ -128,3 +128,32 @@ def test_feature_sharded_search_single_gpu(gpu_ctx):
         ctx.close()
     win = select_winner(cands)
     assert win["var_idx"] == full["var_idx"] and win["c"] == full["c"] and win["quality"] == full["quality"]
+
+
+@pytest.mark.parametrize("bt,depth", [(orc.GAB, 1), (orc.GAB, 2), (orc.RAB, 1), (orc.DAB, 1)])
+def test_pruned_search_equals_exhaustive(gpu_ctx, bt, depth):
+    """The bound pass (k_ss_bound) may only drop variables that cannot win: the pruned search must grow exactly the
+    trees of the exhaustive search (bitwise: same feature, threshold, quality, leaf values), and it must actually prune."""
+    import cascadeclassifier_b200 as ccb
+    imgs, labels = make_samples(300, 500)
+    n = len(imgs)
+    ev = ccb.CvFeatureEvaluator.create(orc.HAAR, gpu_ctx)
+    ev.init(ccb.CvHaarFeatureParams(orc.ALL), n, (24, 24))
+    ev.setImages(imgs, labels)
+    params = ccb.CvCascadeBoostParams(boostType=bt, maxFalseAlarm=0.02, maxDepth=depth, maxWeakCount=10)
+    stages = []
+    for mode in (1, 0):
+        gpu_ctx.set_search_mode(mode)
+        st = ccb.CvCascadeBoost()
+        assert st.train(ev, n, 1024, 1024, params)
+        stages.append(st)
+    gpu_ctx.set_search_mode(0)
+    ex, pr = stages
+    assert len(ex.trees) == len(pr.trees) and ex.threshold == pr.threshold
+    for a, b in zip(ex.trees, pr.trees):
+        assert a == b
+    stats = gpu_ctx.search_stats()
+    assert stats["searches"] >= len(pr.trees)
+    F = ev.getNumFeatures()
+    # far fewer rows searched exactly than an exhaustive search would touch
+    assert stats["flagged_rows"] + stats["seed_rows"] < 0.25 * F * stats["searches"], stats

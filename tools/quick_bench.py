@@ -19,6 +19,7 @@ n = len(imgs)
 ev.init(fp, n, (24, 24))
 for rep in range(3):
     ctx.timing_reset()
+    st0 = ctx.search_stats() if rep else dict(searches=0, seed_rows=0, flagged_rows=0)
     t0 = time.time()
     ev.setImages(imgs, labels)
     ctx.synchronize()
@@ -36,7 +37,11 @@ for rep in range(3):
         if name == "sort":
             extra = " -> %.1f%% of HBM roofline (6 B/elem)" % (F * n * 6 / (ms * 1e-3) / 6547.8e9 * 100)
         if name == "split_search" and k:
-            per = ms / (k / 2)
+            st1 = ctx.search_stats()
+            ns = max(1, st1["searches"] - st0["searches"])
+            extra0 = " searches %d flagged/search %.0f seeds/search %.0f" % (ns, (st1["flagged_rows"] - st0["flagged_rows"]) / ns, (st1["seed_rows"] - st0["seed_rows"]) / ns)
+            print("  ", extra0)
+            per = ms / ns
             extra = " -> %.2f ms/node, %.1f%% of HBM roofline (6 B/elem)" % (per, F * n * 6 / (per * 1e-3) / 6547.8e9 * 100)
         print("   %-13s %9.3f ms  launches %d%s" % (name, ms, k, extra))
     print("   log", st.log[:3], "...", st.log[-1] if st.log else None, "thr", st.threshold)
