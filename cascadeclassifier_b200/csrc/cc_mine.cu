@@ -78,6 +78,10 @@ struct LevelDesc {
   long long w_skip;        // windows of this level that precede the batch (partial first level)
   long long w_base;        // batch ordinal of the first window taken from this level
   long long w_count;       // windows taken
+  // whole-level integral planes (Haar / LBP fast path): element offset of this level's (lh+1) x (lw+1) plane in
+  // each plane pool, and cumulative line counts that map a thread to (level, row | column | diagonal)
+  long long ip_off;
+  int rows_base, cols_base, diag_base, pad0;
 };
 
 // cv::resize(src, dst, INTER_LINEAR_EXACT), 8-bit single channel: 8.8 fixed-point coefficients per axis,
@@ -185,6 +189,225 @@ __global__ void k_copy_slots(const uint8_t* __restrict__ src, const unsigned int
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Haar / LBP fast path: integral images of whole pyramid levels instead of one per window.
+//
+// Sums over a window's rectangles taken from the integral image of the whole level equal those taken
+// from the integral image of the 24x24 crop (exact integers; for tilted rectangles the 4-corner
+// combination cancels every pixel outside the rectangle point-wise, so it does not matter that the
+// level's tilted integral also covers pixels outside the crop) -- SURVEY.md App. A.2, re-checked
+// against cv2.integral3 in tests/test_oracle_golden.py.  Planes hold uint32 with wrap-around: every
+// window-level difference is < 2^32, so modular arithmetic returns the exact value (sqsum included,
+// which the reference keeps in f64).  Per window the arithmetic after the rectangle sums is that of
+// setImage + operator(): nf = (float)sqrt(area*sq - s*s) in f64 (src/features.cpp:13-25), value =
+// (float)acc / nf in IEEE f32 (include/haarfeatures.h:108-112), LBP code from 9 cell sums.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int level_of_line(const LevelDesc* __restrict__ levels, int nlevels, int line, int which) {
+  int lo = 0, hi = nlevels - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    const int b = which == 0 ? levels[mid].rows_base : which == 1 ? levels[mid].cols_base : levels[mid].diag_base;
+    if (b <= line) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+// row prefix sums of I and I^2 into rows 1..lh of the sum / sqsum planes (one warp per level row); row 0 and column 0 = 0
+__global__ void __launch_bounds__(256)
+k_lvl_rows(const LevelDesc* __restrict__ levels, int nlevels, int total_rows, const uint8_t* __restrict__ pool,
+           uint32_t* __restrict__ sum, uint32_t* __restrict__ sq) {
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int gr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gr < total_rows; gr += nwarps) {
+    const LevelDesc& L = levels[level_of_line(levels, nlevels, gr, 0)];
+    const int y = gr - L.rows_base, pitch = L.lw + 1;
+    const uint8_t* src = pool + L.px_off + (size_t)y * L.lw;
+    uint32_t* S = sum + L.ip_off + (size_t)(y + 1) * pitch;
+    uint32_t* Q = sq ? sq + L.ip_off + (size_t)(y + 1) * pitch : nullptr;
+    if (y == 0) for (int x = lane; x < pitch; x += 32) { S[x - pitch] = 0; if (Q) Q[x - pitch] = 0; }
+    if (lane == 0) { S[0] = 0; if (Q) Q[0] = 0; }
+    uint32_t c1 = 0, c2 = 0;
+    for (int x0 = 0; x0 < L.lw; x0 += 32) {
+      const int x = x0 + lane;
+      const uint32_t v = x < L.lw ? src[x] : 0u;
+      uint32_t p1 = v, p2 = v * v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t1 = __shfl_up_sync(0xffffffffu, p1, d), t2 = __shfl_up_sync(0xffffffffu, p2, d);
+        if (lane >= d) { p1 += t1; p2 += t2; }
+      }
+      p1 += c1; p2 += c2;
+      if (x < L.lw) { S[x + 1] = p1; if (Q) Q[x + 1] = p2; }
+      c1 = __shfl_sync(0xffffffffu, p1, 31); c2 = __shfl_sync(0xffffffffu, p2, 31);
+    }
+  }
+}
+
+// tilted plane, step 1: E(y, x) = D1(y,x) + D2(y,x) - I(y,x) stored at plane row y+1, column x+1 (x = -1 .. lw-1), with
+// D1(y,x) = I(y,x) + D1(y-1,x-1), D2(y,x) = I(y,x) + D2(y-1,x+1) (the two diagonal running sums of cv::integral's tilted
+// definition).  One thread walks one diagonal; pass 0 writes D1, pass 1 adds D2 - I.  The plane is zeroed beforehand.
+__global__ void __launch_bounds__(256)
+k_lvl_diag(const LevelDesc* __restrict__ levels, int nlevels, int total_diag, const uint8_t* __restrict__ pool,
+           uint32_t* __restrict__ tilted, int pass) {
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_diag; g += gridDim.x * blockDim.x) {
+    const LevelDesc& L = levels[level_of_line(levels, nlevels, g, 2)];
+    const int k = g - L.diag_base, lw = L.lw, lh = L.lh, pitch = lw + 1;
+    const uint8_t* img = pool + L.px_off;
+    uint32_t* T = tilted + L.ip_off;
+    // diagonals start on the top row (k < lw: column k) or on a side column (k >= lw: row k - lw + 1)
+    int y = k < lw ? 0 : k - lw + 1;
+    uint32_t run = 0;
+    if (pass == 0) {
+      int x = k < lw ? k : 0;
+      for (; y < lh && x < lw; ++y, ++x) { run += img[(size_t)y * lw + x]; T[(size_t)(y + 1) * pitch + x + 1] = run; }
+    } else {
+      int x = k < lw ? k : lw - 1;
+      for (; y < lh && x >= 0; ++y, --x) {
+        const uint32_t v = img[(size_t)y * lw + x];
+        run += v;
+        T[(size_t)(y + 1) * pitch + x + 1] += run - v;
+      }
+      if (y < lh) T[(size_t)(y + 1) * pitch] += run;        // virtual column x = -1: D2(y,-1) = D2(y-1,0), I = 0
+    }
+  }
+}
+
+// column prefix sums in place (one thread per plane column): turns row prefixes into integrals, and E into
+// T(Y,X) = T(Y-1,X) + E(Y-1,X-1)
+__global__ void __launch_bounds__(256)
+k_lvl_cols(const LevelDesc* __restrict__ levels, int nlevels, int total_cols, uint32_t* __restrict__ p0, uint32_t* __restrict__ p1,
+           uint32_t* __restrict__ p2) {
+  uint32_t* plane = blockIdx.y == 0 ? p0 : blockIdx.y == 1 ? p1 : p2;
+  if (!plane) return;
+  for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_cols; g += gridDim.x * blockDim.x) {
+    const LevelDesc& L = levels[level_of_line(levels, nlevels, g, 1)];
+    const int j = g - L.cols_base, pitch = L.lw + 1;
+    uint32_t* c = plane + L.ip_off + j;
+    uint32_t acc = 0;
+    int y = 1;
+    for (; y + 3 <= L.lh; y += 4) {
+      const uint32_t a0 = c[(size_t)y * pitch], a1 = c[(size_t)(y + 1) * pitch], a2 = c[(size_t)(y + 2) * pitch], a3 = c[(size_t)(y + 3) * pitch];
+      acc += a0; c[(size_t)y * pitch] = acc;
+      acc += a1; c[(size_t)(y + 1) * pitch] = acc;
+      acc += a2; c[(size_t)(y + 2) * pitch] = acc;
+      acc += a3; c[(size_t)(y + 3) * pitch] = acc;
+    }
+    for (; y <= L.lh; ++y) { acc += c[(size_t)y * pitch]; c[(size_t)y * pitch] = acc; }
+  }
+}
+
+// A tree node's feature flattened for level planes: tap = dx | dy << 8 | (int8 coef) << 16 relative to the window origin
+struct LvlFeat { uint32_t hdr; uint32_t tap[16]; };      // hdr = ntaps | tilted << 8
+
+struct LvlPlanes { const uint32_t* sum; const uint32_t* sq; const uint32_t* tilted; };
+
+// CvCascadeClassifier::predict over the windows of the batch, stages [s_begin, s_end), early exit; the survivors'
+// batch ordinals are appended to out_list (warp-ballot compaction, one atomic per warp).  in_list == nullptr:
+// every window of the batch; otherwise the survivors of the previous stage group (count read on the device).
+__global__ void __launch_bounds__(256)
+k_lvl_cascade(const LevelDesc* __restrict__ levels, int nlevels, LvlPlanes pl, int ftype, int W, int H,
+              const DevNode* __restrict__ nodes, const LvlFeat* __restrict__ feats, const int* __restrict__ tree_first,
+              const DevStageRef* __restrict__ stages, int s_begin, int s_end, const unsigned int* __restrict__ in_list,
+              const unsigned int* __restrict__ in_count, long long nwin_all, unsigned int* __restrict__ out_count,
+              unsigned int* __restrict__ out_list) {
+  const long long n = in_list ? (long long)*in_count : nwin_all;
+  const int lane = threadIdx.x & 31;
+  const long long nround = (n + 31) & ~31ll;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nround; i += (long long)gridDim.x * blockDim.x) {
+    bool pass = i < n;
+    unsigned int b = 0;
+    if (pass) {
+      b = in_list ? in_list[i] : (unsigned int)i;
+      int lo = 0, hi = nlevels - 1;
+      while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= (long long)b) lo = mid; else hi = mid - 1; }
+      const LevelDesc& L = levels[lo];
+      const long long k = (long long)b - L.w_base + L.w_skip;
+      const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
+      const int pitch = L.lw + 1;
+      const size_t org = (size_t)L.ip_off + (size_t)(L.y0 + iy * L.step_y) * pitch + (L.x0 + ix * L.step_x);
+      const uint32_t* S = pl.sum + org;
+      float nf = 0.f;
+      if (ftype == CC_FEATURE_HAAR) {
+        const uint32_t* Q = pl.sq + org;
+        const int o0 = pitch + 1, o1 = pitch + (W - 1), o2 = (H - 1) * pitch + 1, o3 = (H - 1) * pitch + (W - 1);
+        const uint32_t vs = __ldg(S + o0) - __ldg(S + o1) - __ldg(S + o2) + __ldg(S + o3);
+        const uint32_t vq = __ldg(Q + o0) - __ldg(Q + o1) - __ldg(Q + o2) + __ldg(Q + o3);
+        const double area = (double)((W - 2) * (H - 2));
+        const double dvs = (double)(int)vs;
+        nf = (float)sqrt(area * (double)vq - dvs * dvs);
+      }
+      const uint32_t* Tt = pl.tilted ? pl.tilted + org : nullptr;
+      for (int st = s_begin; st < s_end && pass; ++st) {
+        const DevStageRef sr = stages[st];
+        double sum = 0;
+        for (int t = 0; t < sr.num_trees; ++t) {
+          const int first = tree_first[sr.first_tree + t];
+          int nd = 0;
+          while (nodes[first + nd].left >= 0) {
+            const DevNode& node = nodes[first + nd];
+            const LvlFeat& f = feats[first + nd];
+            bool left;
+            if (ftype == CC_FEATURE_HAAR) {
+              const uint32_t hdr = f.hdr;
+              const uint32_t* P = (hdr >> 8) ? Tt : S;
+              const int nt = (int)(hdr & 0xFFu);
+              int acc = 0;
+              for (int q = 0; q < nt; ++q) {
+                const uint32_t tp = f.tap[q];
+                acc += (int)(int8_t)(tp >> 16) * (int)__ldg(P + (int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu));
+              }
+              const float val = nf == 0.f ? 0.f : __fdiv_rn((float)acc, nf);
+              left = val <= node.c;
+            } else {
+              int v[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) { const uint32_t tp = f.tap[q]; v[q] = (int)__ldg(S + (int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)); }
+              auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
+              const int c = cell(1, 1);
+              const int code = (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
+                               (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
+                               (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
+              left = (node.subset[code >> 5] & (1 << (code & 31))) != 0;
+            }
+            nd = left ? node.left : node.right;
+          }
+          sum += nodes[first + nd].value;
+        }
+        if (sum < (double)(sr.threshold - 0.00001F)) pass = false;
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      unsigned base = 0;
+      if (lane == leader) base = atomicAdd(out_count, (unsigned)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (pass) out_list[base + __popc(m & ((1u << lane) - 1u))] = b;
+    }
+  }
+}
+
+// copy the listed windows (batch ordinals) out of their pyramid levels into consecutive slots
+__global__ void k_gather_list(const LevelDesc* __restrict__ levels, int nlevels, const uint8_t* __restrict__ pool, int W, int H,
+                              const unsigned int* __restrict__ which, int n, uint8_t* __restrict__ dst, uint8_t* __restrict__ labels, int label) {
+  const int npx = W * H;
+  const long long total = (long long)n * npx;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / npx);
+    const int r = (int)(t - (long long)i * npx);
+    const long long b = which[i];
+    int lo = 0, hi = nlevels - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= b) lo = mid; else hi = mid - 1; }
+    const LevelDesc& L = levels[lo];
+    const long long k = b - L.w_base + L.w_skip;
+    const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
+    const int wy = r / W, wx = r - wy * W;
+    dst[t] = pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.lw + (L.x0 + ix * L.step_x + wx)];
+    if (r == 0) labels[i] = (uint8_t)label;
+  }
+}
+
 // ---- host-side state ----------------------------------------------------------------------------------
 struct BgImage { int w = 0, h = 0; uint8_t* d_px = nullptr; };
 
@@ -207,12 +430,21 @@ struct MineState {
   unsigned int* d_surv = nullptr;      // [0] = counter, [1..cap] = list
   unsigned int surv_cap = 0;
   unsigned int* h_surv = nullptr;      // pinned mirror
+  // whole-level fast path (Haar / LBP)
+  std::vector<LvlFeat> lfeats;         // parallel to `nodes`
+  LvlFeat* d_lfeats = nullptr;
+  bool cascade_tilted = false;         // some node uses a tilted feature
+  uint32_t *d_psum = nullptr, *d_psq = nullptr, *d_ptilt = nullptr;
+  size_t plane_cap = 0;
+  unsigned int *d_list[2] = {nullptr, nullptr}, *d_counts = nullptr;
+  size_t list_cap = 0;
 };
 
 static void free_cascade(MineState* m) {
-  cudaFree(m->d_nodes); cudaFree(m->d_tree_first); cudaFree(m->d_stages);
-  m->d_nodes = nullptr; m->d_tree_first = nullptr; m->d_stages = nullptr;
-  m->nodes.clear(); m->tree_first.clear(); m->stages.clear();
+  cudaFree(m->d_nodes); cudaFree(m->d_tree_first); cudaFree(m->d_stages); cudaFree(m->d_lfeats);
+  m->d_nodes = nullptr; m->d_tree_first = nullptr; m->d_stages = nullptr; m->d_lfeats = nullptr;
+  m->nodes.clear(); m->tree_first.clear(); m->stages.clear(); m->lfeats.clear();
+  m->cascade_tilted = false;
 }
 static void free_scratch(MineState* m) {
   store_free(m->scratch);
@@ -221,6 +453,10 @@ static void free_scratch(MineState* m) {
   cudaFree(m->d_levels); m->d_levels = nullptr; m->levels_cap = 0;
   cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
   cudaFreeHost(m->h_surv); m->h_surv = nullptr;
+  cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
+  m->d_psum = m->d_psq = m->d_ptilt = nullptr; m->plane_cap = 0;
+  cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts);
+  m->d_list[0] = m->d_list[1] = m->d_counts = nullptr; m->list_cap = 0;
 }
 
 int mine_free(cc_ctx* ctx) {
@@ -357,6 +593,27 @@ static int upload_cascade(cc_ctx* ctx, MineState* m, const cc_stage* stages, int
         std::memcpy(d.subset, tr.nodes[i].subset, sizeof(d.subset));
         d.value = tr.nodes[i].value;
         m->nodes.push_back(d);
+        LvlFeat lf;
+        std::memset(&lf, 0, sizeof(lf));
+        if (d.left >= 0 && ctx->ftype != CC_FEATURE_HOG) {
+          CC_REQUIRE(d.var_idx >= 0 && d.var_idx < ctx->num_features, CC_ERR_BAD_ARG, "cc_cascade_set_stages: feature index %d out of range", d.var_idx);
+          const int S = ctx->W + 1;
+          if (ctx->ftype == CC_FEATURE_HAAR) {
+            const HaarTaps t = make_haar_taps(ctx->haar[d.var_idx], S);
+            const int nt = t.ntaps();
+            lf.hdr = (uint32_t)nt | ((uint32_t)t.tilted() << 8);
+            for (int q = 0; q < nt; ++q) {
+              const int off = tap_off(t.w[q]);
+              lf.tap[q] = (uint32_t)(off % S) | ((uint32_t)(off / S) << 8) | ((uint32_t)(uint8_t)(int8_t)tap_coef(t.w[q]) << 16);
+            }
+            if (t.tilted()) m->cascade_tilted = true;
+          } else {
+            const LbpTaps t = make_lbp_taps(ctx->lbp[d.var_idx], S);
+            lf.hdr = 16;
+            for (int q = 0; q < 16; ++q) lf.tap[q] = (uint32_t)(t.off[q] % S) | ((uint32_t)(t.off[q] / S) << 8);
+          }
+        }
+        m->lfeats.push_back(lf);
       }
     }
     m->stages.push_back(sr);
@@ -368,6 +625,8 @@ static int upload_cascade(cc_ctx* ctx, MineState* m, const cc_stage* stages, int
     CC_CUDA(cudaMemcpyAsync(m->d_nodes, m->nodes.data(), sizeof(DevNode) * m->nodes.size(), cudaMemcpyHostToDevice, ctx->stream));
     CC_CUDA(cudaMemcpyAsync(m->d_tree_first, m->tree_first.data(), sizeof(int) * m->tree_first.size(), cudaMemcpyHostToDevice, ctx->stream));
     CC_CUDA(cudaMemcpyAsync(m->d_stages, m->stages.data(), sizeof(DevStageRef) * m->stages.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CC_CUDA(cudaMalloc(&m->d_lfeats, sizeof(LvlFeat) * m->lfeats.size()));
+    CC_CUDA(cudaMemcpyAsync(m->d_lfeats, m->lfeats.data(), sizeof(LvlFeat) * m->lfeats.size(), cudaMemcpyHostToDevice, ctx->stream));
     CC_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   return CC_OK;
@@ -432,6 +691,117 @@ struct Batch {
   size_t pool_px = 0;
 };
 
+// windows the fast path may put in one batch (pyramid pixels ~ 154 per window at 1920x1080 -> ~2 GB of planes)
+constexpr long long LEVEL_PATH_MAX_BATCH = 1 << 20;
+
+static bool use_level_path(const cc_ctx* ctx, const MineState* m) {
+  return !m->stages.empty() && (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) && ctx->W <= 255 && ctx->H <= 255;
+}
+
+// Fast path: build the levels and their integral planes, run the cascade in stage groups over the shrinking survivor
+// list, return the sorted surviving batch ordinals.  The level pixels stay in m->d_pool for gather_accepted().
+static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigned>& survivors) {
+  survivors.clear();
+  const int nlv = (int)bt.levels.size();
+  if (bt.nwin == 0) return CC_OK;
+  size_t plane_elems = 0;
+  int rows = 0, cols = 0, diag = 0;
+  for (LevelDesc& L : bt.levels) {
+    L.ip_off = (long long)plane_elems; L.rows_base = rows; L.cols_base = cols; L.diag_base = diag; L.pad0 = 0;
+    plane_elems += (size_t)(L.lw + 1) * (L.lh + 1);
+    rows += L.lh; cols += L.lw + 1; diag += L.lw + L.lh - 1;
+  }
+  const bool haar = ctx->ftype == CC_FEATURE_HAAR;
+  const bool tilted = haar && m->cascade_tilted;
+  if (bt.pool_px > m->pool_cap) { cudaFree(m->d_pool); CC_CUDA(cudaMalloc(&m->d_pool, bt.pool_px)); m->pool_cap = bt.pool_px; }
+  if (nlv > m->levels_cap) { cudaFree(m->d_levels); CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * nlv)); m->levels_cap = nlv; }
+  if (plane_elems > m->plane_cap) {
+    cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
+    m->d_psum = m->d_psq = m->d_ptilt = nullptr;
+    const size_t cap = plane_elems + plane_elems / 4;
+    CC_CUDA(cudaMalloc(&m->d_psum, cap * 4));
+    if (haar) { CC_CUDA(cudaMalloc(&m->d_psq, cap * 4)); CC_CUDA(cudaMalloc(&m->d_ptilt, cap * 4)); }
+    m->plane_cap = cap;
+  }
+  if ((size_t)bt.nwin > m->list_cap) {
+    cudaFree(m->d_list[0]); cudaFree(m->d_list[1]);
+    const size_t cap = (size_t)bt.nwin + (size_t)bt.nwin / 4;
+    CC_CUDA(cudaMalloc(&m->d_list[0], cap * 4)); CC_CUDA(cudaMalloc(&m->d_list[1], cap * 4));
+    m->list_cap = cap;
+    cudaFreeHost(m->h_surv); m->h_surv = nullptr;
+    CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (cap + 1)));
+  }
+  if (!m->h_surv) CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (m->list_cap + 1)));
+  if (!m->d_counts) CC_CUDA(cudaMalloc(&m->d_counts, sizeof(unsigned) * 16));
+  CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * nlv, cudaMemcpyHostToDevice, ctx->stream));
+  int ngroups = 0;
+  {
+    ScopedTimer tm(ctx, "mine", 0);
+    int launches = 0;
+    k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, (long long)bt.pool_px, m->d_pool);
+    k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
+    launches += 2;
+    if (tilted) {
+      CC_CUDA(cudaMemsetAsync(m->d_ptilt, 0, plane_elems * 4, ctx->stream));
+      k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, diag, m->d_pool, m->d_ptilt, 0);
+      k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, diag, m->d_pool, m->d_ptilt, 1);
+      launches += 2;
+    }
+    dim3 cgrid(grid_for(ctx, cols, 256), 3);
+    k_lvl_cols<<<cgrid, 256, 0, ctx->stream>>>(m->d_levels, nlv, cols, m->d_psum, haar ? m->d_psq : nullptr, tilted ? m->d_ptilt : nullptr);
+    launches += 1;
+    CC_CUDA(cudaGetLastError());
+    CC_CUDA(cudaMemsetAsync(m->d_counts, 0, sizeof(unsigned) * 16, ctx->stream));
+    // stage groups [0,2) [2,4) [4,8) [8,16) ...: each group runs on the survivors of the previous one
+    const int ns = (int)m->stages.size();
+    LvlPlanes pl{m->d_psum, m->d_psq, tilted ? m->d_ptilt : nullptr};
+    int s0 = 0, width = 2;
+    while (s0 < ns) {
+      const int s1 = std::min(ns, s0 + width);
+      const unsigned* in_list = ngroups == 0 ? nullptr : m->d_list[(ngroups - 1) & 1];
+      const int grid = ngroups == 0 ? grid_for(ctx, bt.nwin, 256) : ctx->sm_count * 8;
+      k_lvl_cascade<<<grid, 256, 0, ctx->stream>>>(m->d_levels, nlv, pl, ctx->ftype, ctx->W, ctx->H, m->d_nodes, m->d_lfeats, m->d_tree_first,
+                                                    m->d_stages, s0, s1, in_list, ngroups == 0 ? nullptr : m->d_counts + ngroups - 1, bt.nwin,
+                                                    m->d_counts + ngroups, m->d_list[ngroups & 1]);
+      ++ngroups; ++launches;
+      s0 = s1;
+      if (ngroups >= 2) width *= 2;
+      if (ngroups == 15) { width = ns; }
+    }
+    CC_CUDA(cudaGetLastError());
+    ctx->launches += launches;
+    if (ctx->timing_enabled) ctx->timers["mine"].launches += launches;
+  }
+  CC_CUDA(cudaMemcpyAsync(m->h_surv, m->d_counts + ngroups - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const unsigned cnt = m->h_surv[0];
+  if (cnt) {
+    CC_CUDA(cudaMemcpyAsync(m->h_surv + 1, m->d_list[(ngroups - 1) & 1], sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    survivors.assign(m->h_surv + 1, m->h_surv + 1 + cnt);
+    std::sort(survivors.begin(), survivors.end());
+  }
+  return CC_OK;
+}
+
+// fast path: copy accepted windows (batch ordinals) from the level pool into training slots [first, first+n), build integrals
+static int gather_accepted(cc_ctx* ctx, MineState* m, const Batch& bt, const unsigned* which, int n, int first, int label) {
+  if (n == 0) return CC_OK;
+  const int npx = ctx->W * ctx->H;
+  CC_CUDA(cudaMemcpyAsync(m->d_list[0], which, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    ScopedTimer tm(ctx, "mine", 1);
+    k_gather_list<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, ctx->W, ctx->H,
+                                                                                  m->d_list[0], n, ctx->d_imgs + (size_t)first * npx,
+                                                                                  ctx->d_labels + first, label);
+    CC_CUDA(cudaGetLastError());
+  }
+  ctx->precalc_valid = false;
+  CC_CHECK(launch_integrals(ctx, main_store(ctx), first, n));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
 }  // namespace cc
 
 using namespace cc;
@@ -487,7 +857,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   long long consumed = 0;
   int got = 0;
   double accept_rate = m->stages.empty() ? 1.0 : 0.0;   // running estimate
-  const long long max_batch = ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  const bool level_path = use_level_path(ctx, m);
+  const long long max_batch = level_path ? LEVEL_PATH_MAX_BATCH : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
   bool stream_ok = true;
   if (ns.lw == 0) stream_ok = ns.nextImg();             // first get(): img.empty() -> nextImg()
   std::vector<unsigned> survivors, accepted;
@@ -530,10 +901,12 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     const int nwin = (int)bt.nwin;
     // ---- GPU: levels, gather, integrals, cascade ----
     const bool direct = m->stages.empty();       // stage 0: every window passes, gather straight into the training slots
-    CC_CHECK(ensure_scratch(ctx, m, direct ? 1 : nwin, bt.pool_px, (int)bt.levels.size()));
-    CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     long long take_direct = 0;
-    {
+    if (!level_path) {
+      CC_CHECK(ensure_scratch(ctx, m, direct ? 1 : nwin, bt.pool_px, (int)bt.levels.size()));
+      CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (!level_path) {
       ScopedTimer tm(ctx, "mine", 2);
       k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
       CC_CUDA(cudaGetLastError());
@@ -563,7 +936,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       if (taken < take_direct) { /* ratio rule fired */ }
       if (got < count && taken == nwin) { ns = bt.after.back(); stream_ok = more; continue; }
     } else {
-      CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
+      if (level_path) CC_CHECK(eval_levels(ctx, m, bt, survivors));
+      else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
       // ---- serial stopping rule over the ordered survivors ----
       accepted.clear();
       long long pos = 0;            // next unconsumed batch ordinal
@@ -600,7 +974,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
         if (got == count) { stopped = true; break; }
       }
       stop_after = pos - 1;
-      CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
+      if (level_path) CC_CHECK(gather_accepted(ctx, m, bt, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
+      else CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
       if (nwin > 0) accept_rate = std::max((double)survivors.size() / (double)nwin, 1e-9);
       if (!stopped) { ns = bt.after.back(); stream_ok = more; continue; }
     }
@@ -711,7 +1086,8 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
   CC_REQUIRE(img0 >= 0 && nimg > 0 && img0 + nimg <= (int)m->bgs.size(), CC_ERR_BAD_ARG, "cc_mine_scan: image range out of bounds");
   CC_CUDA(cudaSetDevice(ctx->device));
   const int W = ctx->W, H = ctx->H, npx = W * H;
-  const long long max_batch = ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  const bool level_path = use_level_path(ctx, m);
+  const long long max_batch = level_path ? LEVEL_PATH_MAX_BATCH : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
   long long total = 0, surv = 0;
   std::vector<unsigned> survivors;
   // every image from its first level (round 0 offsets), independent of the reader state
@@ -720,6 +1096,12 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
   auto flush = [&]() -> int {
     if (bt.nwin == 0) return CC_OK;
     const int nwin = (int)bt.nwin;
+    if (level_path) {
+      CC_CHECK(eval_levels(ctx, m, bt, survivors));
+      total += nwin; surv += (long long)survivors.size();
+      bt = Batch();
+      return CC_OK;
+    }
     CC_CHECK(ensure_scratch(ctx, m, nwin, bt.pool_px, (int)bt.levels.size()));
     CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     {
