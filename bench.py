@@ -200,8 +200,13 @@ def run_ours(args):
         sampler.start()
         time.sleep(0.3)
     ctx.timing_reset()
+    st0 = ctx.search_stats()
+    launches0 = ctx.launch_count()
     ms_total = timed(step_device, args.steps)
-    launches = ctx.launch_count()
+    launches = ctx.launch_count() - launches0
+    st1 = ctx.search_stats()
+    searches_per_step = (st1["searches"] - st0["searches"]) / args.steps
+    exact_rows_per_search = (st1["seed_rows"] + st1["flagged_rows"] - st0["seed_rows"] - st0["flagged_rows"]) / max(1, st1["searches"] - st0["searches"])
     fam = {}
     for name in ["integral", "precalc", "sort", "split_search", "boost_small"]:
         m, k = ctx.timing(name)
@@ -220,19 +225,27 @@ def run_ours(args):
     value = F * N / (ms_step * 1e-3)
     e2e_value = F * N / (ms_e2e / args.steps * 1e-3)
     peak, peak_kind = peaks()
-    # dominant kernel: split search (one launch per tree node over the local rows): 6 B per (feature, sample)
-    ss = fam["split_search"]
-    n_search = ss["launches_per_step"] / 2.0          # every search = 1 search kernel + 1 argmax kernel
-    ss_ms = ss["ms_per_step"] / max(n_search, 1e-9)
     rows_local = F // world if world > 1 else F
-    alg_bytes = 6.0 * rows_local * N
-    achieved = alg_bytes / (ss_ms * 1e-3) / 1e9
-    traffic = None
+    cells = float(rows_local) * N                      # (feature, sample) pairs of the local shard
+    n_search = max(searches_per_step, 1e-9)
+    ss_ms = fam["split_search"]["ms_per_step"] / n_search
+    pre_ms, sort_ms = fam["precalc"]["ms_per_step"], fam["sort"]["ms_per_step"]
+    traffic = {}
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("split_search_dram_bytes_per_launch")
-    pre_ms = fam["precalc"]["ms_per_step"]
+            traffic = json.load(f)
+    # algorithmic bytes per (feature, sample) pair (SURVEY.md 8d / DESIGN.md 4): precalc 4 B written; sort 4 B key read +
+    # 2 B index written; split search: the pruned search reads the 2 B index row once per tree node (the f32 value row
+    # is only read for the ~0.1 % of rows searched exactly)
+    def roof(kernel, bytes_per_cell, ms, tkey):
+        ach = bytes_per_cell * cells / (ms * 1e-3) / 1e9
+        return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get(tkey), "algorithmic_bytes_per_launch": bytes_per_cell * cells, "ms_per_launch": ms}
+    rooflines = {"precalc": roof("k_precalc_haar_sep + k_precalc_haar", 4.0, pre_ms, "precalc_dram_bytes_per_step"),
+                 "sort": roof("k_sort_rows", 6.0, sort_ms, "sort_dram_bytes_per_launch"),
+                 "split_search": roof("k_ss_bound (+ exact search of seed / flagged rows)", 2.0, ss_ms, "split_search_dram_bytes_per_search")}
+    dominant = max(("precalc", pre_ms), ("sort", sort_ms), ("split_search", fam["split_search"]["ms_per_step"]), key=lambda kv: kv[1])[0]
     out = {
         "metric": "Haar stage-train feature evals/s (F*N per complete stage train)", "value": value, "unit": "evals/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
@@ -241,19 +254,62 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "N": N, "F": F, "weak_trees_in_stage": int(nweak), "timing": "inputs larger than L2 (fval 15.7 GB, sorted rows 23.5 GB per pass)",
                    "parallelism": "feature-sharded x%d" % world},
         "stage_train_s": ms_step * 1e-3,
-        "kernels": {"precalc_evals_per_s": rows_local * N / (pre_ms * 1e-3), "precalc_frac_of_hbm": rows_local * N * 4 / (pre_ms * 1e-3) / 1e9 / peak,
-                    "sort_ms": fam["sort"]["ms_per_step"], "split_search_ms_per_node": ss_ms, "families": fam},
-        "roofline": {"kernel": "k_split_search_ord", "bound": "hbm", "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": traffic},
+        "kernels": {"precalc_evals_per_s": cells / (pre_ms * 1e-3), "precalc_frac_of_hbm": rooflines["precalc"]["frac"],
+                    "sort_ms": sort_ms, "split_search_ms_per_node": ss_ms, "split_searches_per_step": searches_per_step,
+                    "rows_searched_exactly_per_node": exact_rows_per_search, "families": fam, "rooflines": rooflines},
+        "roofline": rooflines[dominant],
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(imgs.nbytes + labels.nbytes),
                 "d2h_bytes_per_step": int(C.sizeof(_lib.Tree) * nweak + C.sizeof(_lib.LogRow) * nweak + 16), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks,
     }
+    if world == 1 and not args.no_mining:
+        out["mining"] = mining_leg(local)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(imgs, labels, F, budget_s=20.0)
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def mining_leg(device):
+    """neg-mining windows/s (BASELINE configs[4] shape): a small Haar-ALL cascade trained on the spot, then
+    fillPassedSamples' cascade evaluation over every window of generated 1920x1080 backgrounds (13584 windows per
+    image at round 0).  Wall-clock through the C ABI (host batching + device work), backgrounds resident in HBM."""
+    import io
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import synth, _lib
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    ctx = ccb.Context(device)
+    lib, h = ctx.lib, ctx.h
+    pos = synth.make_positives(1400, WIN, WIN)
+    small = synth.make_backgrounds(12, 480, 360, seed0=500, clutter=2.5)
+    cc = CvCascadeClassifier(ctx, out=io.StringIO())
+    cc.train("/tmp/bench_mining_cascade", "pos.vec", "bg.txt", 1000, 2000, 1024, 1024, 8, CvCascadeParams(0, 0, (WIN, WIN)),
+             ccb.CvHaarFeatureParams(HAAR_MODE_ALL), ccb.CvCascadeBoostParams(), positives=pos, backgrounds=small)
+    nimg = 256
+    big = [synth.make_background(1920, 1080, 9000 + i, clutter=0.3) for i in range(4)]
+    _lib.check(lib.cc_bg_clear(h), "cc_bg_clear")
+    for i in range(nimg):
+        b = big[i % len(big)]
+        _lib.check(lib.cc_bg_register(h, b.ctypes.data_as(C.c_void_p), b.shape[1], b.shape[0]), "cc_bg_register")
+    cc._sync_cascade()
+    win, surv = C.c_int64(0), C.c_int64(0)
+    _lib.check(lib.cc_mine_scan(h, 0, nimg, C.byref(win), C.byref(surv)), "cc_mine_scan")      # warm-up (allocations)
+    ctx.synchronize()
+    ctx.timing_reset()
+    t0 = time.time()
+    reps = 3
+    for _ in range(reps):
+        _lib.check(lib.cc_mine_scan(h, 0, nimg, C.byref(win), C.byref(surv)), "cc_mine_scan")
+    ctx.synchronize()
+    dt = (time.time() - t0) / reps
+    ms_dev, k = ctx.timing("mine")
+    res = {"windows_per_s": win.value / dt, "windows": int(win.value), "survivors": int(surv.value), "images": nimg,
+           "image_size": "1920x1080", "stages": len(cc.stageClassifiers), "weak_per_stage": [len(s.trees) for s in cc.stageClassifiers],
+           "wall_ms_per_sweep": dt * 1e3, "device_ms_per_sweep": ms_dev / reps, "launches_per_sweep": k / reps,
+           "windows_per_s_device": win.value / (ms_dev / reps * 1e-3)}
+    ctx.close()
+    return res
 
 
 def cpu_baseline(imgs, labels, F, budget_s=20.0):
@@ -316,6 +372,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mining", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -213,6 +213,128 @@ __device__ __forceinline__ int level_of_line(const LevelDesc* __restrict__ level
   return lo;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused pyramid builder of the fast path: one CTA per level walks the level row by row and produces, in one
+// pass over the source image, the INTER_LINEAR_EXACT pixels (same fixed-point arithmetic as k_resize_levels),
+// the sum and sqsum integral rows (block-wide row scan + per-column running sums held in registers) and the
+// tilted integral row (D1/D2 diagonal recurrences with the previous row's values in shared memory).  Thread t
+// owns pixel columns 2t, 2t+1 and plane columns 2t, 2t+1; one __syncthreads per row (all per-row shared
+// buffers are double-buffered).  Levels wider or taller than 2047 take the multi-kernel path below.
+// ------------------------------------------------------------------------------------------------
+constexpr int LB_THREADS = 1024;
+constexpr int LB_MAXDIM = 2 * LB_THREADS - 1;      // lw + 1 <= 2048 plane columns, lh <= 2047 rows of y coefficients
+
+__global__ void __launch_bounds__(LB_THREADS, 1)
+k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order, uint8_t* __restrict__ pool, uint32_t* __restrict__ sum,
+            uint32_t* __restrict__ sq, uint32_t* __restrict__ tilted) {
+  __shared__ uint8_t s_pix[2][2 * LB_THREADS + 8];         // pixel row, index j = x + 1 (j = 0: virtual column x = -1)
+  __shared__ uint32_t s_d1[2][2 * LB_THREADS + 2], s_d2[2][2 * LB_THREADS + 2];
+  __shared__ int s_yo[LB_MAXDIM + 1];                       // source row | c1 << 16
+  __shared__ uint32_t s_wt[2][2][32];
+  const LevelDesc L = levels[order[blockIdx.x]];      // tallest levels first: a level is one serial chain of rows
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int lw = L.lw, lh = L.lh, sw = L.sw, sh = L.sh, pitch = lw + 1;
+  const uint8_t* __restrict__ src = L.src;
+  // per-column x coefficients (registers), per-row y coefficients (shared)
+  int xo[2], xc1[2];
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    int o = 0, c0 = 256, c1 = 0, md = 0;
+    const int x = 2 * t + k;
+    if (x < lw) lin_coef(L.scale_x, x, sw, o, c0, c1, md);
+    xo[k] = o; xc1[k] = c1;
+  }
+  for (int y = t; y < lh; y += LB_THREADS) {
+    int o, c0, c1, md;
+    lin_coef(L.scale_y, y, sh, o, c0, c1, md);
+    s_yo[y] = o | (c1 << 16);
+  }
+  for (int j = t; j < 2 * LB_THREADS + 2; j += LB_THREADS) { s_pix[0][j] = s_pix[1][j] = 0; s_d1[0][j] = s_d1[1][j] = 0; s_d2[0][j] = s_d2[1][j] = 0; }
+  uint32_t* S = sum + L.ip_off;
+  uint32_t* Q = sq ? sq + L.ip_off : nullptr;
+  uint32_t* T = tilted ? tilted + L.ip_off : nullptr;
+  for (int j = t; j < pitch; j += LB_THREADS) { S[j] = 0; if (Q) Q[j] = 0; if (T) T[j] = 0; }
+  __syncthreads();
+  uint8_t* dst = pool + L.px_off;
+  uint32_t colS[2] = {0, 0}, colQ[2] = {0, 0}, Tprev[2] = {0, 0};
+  const int x0 = 2 * t, x1 = 2 * t + 1;
+  const int xa0 = xo[0], xb0 = min(xo[0] + 1, sw - 1), xa1 = xo[1], xb1 = min(xo[1] + 1, sw - 1);
+  // source bytes of row y are fetched one row ahead
+  auto fetch = [&](int y, uint32_t (&p)[8]) {
+    const int yo = s_yo[y];
+    const int r0 = yo & 0xFFFF, r1 = min(r0 + 1, sh - 1);
+    const uint8_t* a = src + (size_t)r0 * sw;
+    const uint8_t* b = src + (size_t)r1 * sw;
+    if (x0 < lw) { p[0] = a[xa0]; p[1] = a[xb0]; p[2] = b[xa0]; p[3] = b[xb0]; }
+    if (x1 < lw) { p[4] = a[xa1]; p[5] = a[xb1]; p[6] = b[xa1]; p[7] = b[xb1]; }
+  };
+  uint32_t nxt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (lh > 0) fetch(0, nxt);
+  for (int y = 0; y < lh; ++y) {
+    const int buf = y & 1;
+    uint32_t cur[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
+    const uint32_t cy1 = (uint32_t)(s_yo[y] >> 16), cy0 = 256u - cy1;
+    if (y + 1 < lh) fetch(y + 1, nxt);
+    uint32_t v[2] = {0, 0};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const uint32_t c1 = (uint32_t)xc1[k], c0 = 256u - c1;
+      const uint32_t h0 = cur[4 * k] * c0 + cur[4 * k + 1] * c1, h1 = cur[4 * k + 2] * c0 + cur[4 * k + 3] * c1;
+      v[k] = (h0 * cy0 + h1 * cy1 + 32768u) >> 16;
+    }
+    if (x0 < lw) { dst[(size_t)y * lw + x0] = (uint8_t)v[0]; s_pix[buf][x0 + 1] = (uint8_t)v[0]; }
+    if (x1 < lw) { dst[(size_t)y * lw + x1] = (uint8_t)v[1]; s_pix[buf][x1 + 1] = (uint8_t)v[1]; } else v[1] = 0;
+    if (x0 >= lw) v[0] = 0;
+    // block-wide exclusive scan of the per-thread row totals (pixels and squares)
+    const uint32_t tot1 = v[0] + v[1], tot2 = v[0] * v[0] + v[1] * v[1];
+    uint32_t i1 = tot1, i2 = tot2;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t a = __shfl_up_sync(0xffffffffu, i1, d), b = __shfl_up_sync(0xffffffffu, i2, d);
+      if (lane >= d) { i1 += a; i2 += b; }
+    }
+    if (lane == 31) { s_wt[buf][0][warp] = i1; s_wt[buf][1][warp] = i2; }
+    __syncthreads();
+    uint32_t w1 = s_wt[buf][0][lane], w2 = s_wt[buf][1][lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t a = __shfl_up_sync(0xffffffffu, w1, d), b = __shfl_up_sync(0xffffffffu, w2, d);
+      if (lane >= d) { w1 += a; w2 += b; }
+    }
+    const uint32_t b1 = __shfl_sync(0xffffffffu, w1, (warp + 31) & 31), b2 = __shfl_sync(0xffffffffu, w2, (warp + 31) & 31);
+    const uint32_t e1 = (warp ? b1 : 0u) + i1 - tot1, e2 = (warp ? b2 : 0u) + i2 - tot2;    // row sums left of this thread's columns
+    uint32_t* Srow = S + (size_t)(y + 1) * pitch;
+    if (t == 0) Srow[0] = 0;
+    if (x0 < lw) { colS[0] += e1 + v[0]; Srow[x0 + 1] = colS[0]; }
+    if (x1 < lw) { colS[1] += e1 + v[0] + v[1]; Srow[x1 + 1] = colS[1]; }
+    if (Q) {
+      uint32_t* Qrow = Q + (size_t)(y + 1) * pitch;
+      if (t == 0) Qrow[0] = 0;
+      if (x0 < lw) { colQ[0] += e2 + v[0] * v[0]; Qrow[x0 + 1] = colQ[0]; }
+      if (x1 < lw) { colQ[1] += e2 + tot2; Qrow[x1 + 1] = colQ[1]; }
+    }
+    if (T) {
+      uint32_t* Trow = T + (size_t)(y + 1) * pitch;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int j = 2 * t + k;              // plane column X = j, pixel x = j - 1
+        if (j <= lw) {
+          const int x = j - 1;
+          const uint32_t iv = s_pix[buf][j];
+          const uint32_t a = (x >= 1) ? s_d1[buf ^ 1][j - 1] : 0u;           // D1(y-1, x-1)
+          const uint32_t b = (x + 1 <= lw - 1) ? s_d2[buf ^ 1][j + 1] : 0u;   // D2(y-1, x+1)
+          const uint32_t nd1 = a + iv, nd2 = b + iv;
+          s_d1[buf][j] = nd1; s_d2[buf][j] = nd2;
+          Tprev[k] += nd1 + nd2 - iv;
+          Trow[j] = Tprev[k];
+        }
+      }
+    }
+  }
+}
+
 // row prefix sums of I and I^2 into rows 1..lh of the sum / sqsum planes (one warp per level row); row 0 and column 0 = 0
 __global__ void __launch_bounds__(256)
 k_lvl_rows(const LevelDesc* __restrict__ levels, int nlevels, int total_rows, const uint8_t* __restrict__ pool,
@@ -434,10 +556,14 @@ struct MineState {
   std::vector<LvlFeat> lfeats;         // parallel to `nodes`
   LvlFeat* d_lfeats = nullptr;
   bool cascade_tilted = false;         // some node uses a tilted feature
+  bool force_unfused = false;          // cc_mine_set_mode 1: build the planes with the multi-kernel path (k_lvl_rows/diag/cols)
+  bool force_slots = false;            // cc_mine_set_mode 2: per-window scratch slots (the generic path HOG always takes)
   uint32_t *d_psum = nullptr, *d_psq = nullptr, *d_ptilt = nullptr;
   size_t plane_cap = 0;
   unsigned int *d_list[2] = {nullptr, nullptr}, *d_counts = nullptr;
   size_t list_cap = 0;
+  int* d_order = nullptr;
+  int order_cap = 0;
 };
 
 static void free_cascade(MineState* m) {
@@ -455,8 +581,8 @@ static void free_scratch(MineState* m) {
   cudaFreeHost(m->h_surv); m->h_surv = nullptr;
   cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
   m->d_psum = m->d_psq = m->d_ptilt = nullptr; m->plane_cap = 0;
-  cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts);
-  m->d_list[0] = m->d_list[1] = m->d_counts = nullptr; m->list_cap = 0;
+  cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts); cudaFree(m->d_order);
+  m->d_list[0] = m->d_list[1] = m->d_counts = nullptr; m->list_cap = 0; m->d_order = nullptr; m->order_cap = 0;
 }
 
 int mine_free(cc_ctx* ctx) {
@@ -695,7 +821,7 @@ struct Batch {
 constexpr long long LEVEL_PATH_MAX_BATCH = 1 << 20;
 
 static bool use_level_path(const cc_ctx* ctx, const MineState* m) {
-  return !m->stages.empty() && (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) && ctx->W <= 255 && ctx->H <= 255;
+  return !m->force_slots && !m->stages.empty() && (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) && ctx->W <= 255 && ctx->H <= 255;
 }
 
 // Fast path: build the levels and their integral planes, run the cascade in stage groups over the shrinking survivor
@@ -738,18 +864,30 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
   {
     ScopedTimer tm(ctx, "mine", 0);
     int launches = 0;
-    k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, (long long)bt.pool_px, m->d_pool);
-    k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
-    launches += 2;
-    if (tilted) {
-      CC_CUDA(cudaMemsetAsync(m->d_ptilt, 0, plane_elems * 4, ctx->stream));
-      k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, diag, m->d_pool, m->d_ptilt, 0);
-      k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, diag, m->d_pool, m->d_ptilt, 1);
+    bool fused = !m->force_unfused;
+    for (const LevelDesc& L : bt.levels) fused = fused && L.lw <= LB_MAXDIM && L.lh <= LB_MAXDIM && L.sh <= 65535;
+    if (fused) {
+      std::vector<int> order(nlv);
+      for (int i = 0; i < nlv; ++i) order[i] = i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bt.levels[a].lh > bt.levels[b].lh; });
+      if (nlv > m->order_cap) { cudaFree(m->d_order); CC_CUDA(cudaMalloc(&m->d_order, sizeof(int) * nlv * 2)); m->order_cap = nlv * 2; }
+      CC_CUDA(cudaMemcpyAsync(m->d_order, order.data(), sizeof(int) * nlv, cudaMemcpyHostToDevice, ctx->stream));
+      k_lvl_build<<<nlv, LB_THREADS, 0, ctx->stream>>>(m->d_levels, m->d_order, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr, tilted ? m->d_ptilt : nullptr);
+      launches += 1;
+    } else {
+      k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, (long long)bt.pool_px, m->d_pool);
+      k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
       launches += 2;
+      if (tilted) {
+        CC_CUDA(cudaMemsetAsync(m->d_ptilt, 0, plane_elems * 4, ctx->stream));
+        k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, diag, m->d_pool, m->d_ptilt, 0);
+        k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, diag, m->d_pool, m->d_ptilt, 1);
+        launches += 2;
+      }
+      dim3 cgrid(grid_for(ctx, cols, 256), 3);
+      k_lvl_cols<<<cgrid, 256, 0, ctx->stream>>>(m->d_levels, nlv, cols, m->d_psum, haar ? m->d_psq : nullptr, tilted ? m->d_ptilt : nullptr);
+      launches += 1;
     }
-    dim3 cgrid(grid_for(ctx, cols, 256), 3);
-    k_lvl_cols<<<cgrid, 256, 0, ctx->stream>>>(m->d_levels, nlv, cols, m->d_psum, haar ? m->d_psq : nullptr, tilted ? m->d_ptilt : nullptr);
-    launches += 1;
     CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaMemsetAsync(m->d_counts, 0, sizeof(unsigned) * 16, ctx->stream));
     // stage groups [0,2) [2,4) [4,8) [8,16) ...: each group runs on the survivors of the previous one
@@ -827,6 +965,14 @@ int cc_bg_register(cc_ctx* ctx, const uint8_t* host_gray, int w, int h) {
   CC_CUDA(cudaMemcpyAsync(b.d_px, host_gray, (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
   m->bgs.push_back(b);
+  return CC_OK;
+}
+
+int cc_mine_set_mode(cc_ctx* ctx, int mode) {
+  CC_REQUIRE(ctx && mode >= 0 && mode <= 2, CC_ERR_BAD_ARG, "cc_mine_set_mode: mode must be 0 (auto), 1 (level planes, unfused kernels) or 2 (per-window slots)");
+  MineState* m = mine_state(ctx);
+  m->force_unfused = mode == 1;
+  m->force_slots = mode == 2;
   return CC_OK;
 }
 

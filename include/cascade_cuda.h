@@ -181,6 +181,11 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_accepta
  * (PosReader, src/imagestorage.cpp:138-189): host_vec = vec_count windows; *vec_pos = PosReader::last */
 int cc_mine_positives(cc_ctx* ctx, const uint8_t* host_vec, int vec_count, int count,
                       int32_t* vec_pos, int64_t* consumed, int32_t* got);
+/* How predict() is evaluated over the window stream.  0 (default): Haar / LBP windows are evaluated from integral
+ * planes of whole pyramid levels built by one fused kernel (same integers as the per-crop cv::integral of setImage,
+ * src/haarfeatures.cpp:100-114), HOG from per-window slots.  1: same planes, built by separate row / diagonal /
+ * column kernels.  2: per-window slots for every feature type (literal setImage + predict per window). */
+int cc_mine_set_mode(cc_ctx* ctx, int mode);
 /* NegReader::get() x nwindows without pixels (host only, no GPU needed): advances *state over images of
  * the given sizes; window5 (optional) = x, y, level_w, level_h, source image of the last consumed window. */
 int cc_reader_advance(const int32_t* img_w, const int32_t* img_h, int nimg, int win_w, int win_h,

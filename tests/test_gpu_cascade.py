@@ -119,3 +119,53 @@ def test_cascade_training_matches_oracle(gpu_ctx, tmp_path, ftype, mode):
     if ftype != orc.HOG:
         assert not det.empty()
     assert "===== TRAINING 0-stage =====" in log and "POS count : consumed" in log
+
+
+@pytest.mark.parametrize("ftype,mode", [(orc.HAAR, orc.ALL), (orc.LBP, 0)])
+def test_mining_paths_agree(gpu_ctx, tmp_path, ftype, mode):
+    """The whole-level integral planes (fused builder, and the separate row/diagonal/column kernels) must select
+    exactly the windows the literal per-window path (setImage + predict on a scratch slot) selects: same consumed
+    count, same reader state, same accepted pixels, same integrals."""
+    import copy
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import _lib
+    from cascadeclassifier_b200._lib import check
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    pos, bgs = _data(300, 5, bw=230, bh=170)
+    cc = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
+    fp = ccb.CvFeatureParams.create(ftype)
+    if ftype == orc.HAAR:
+        fp.mode = mode
+    ok = cc.train(str(tmp_path), "pos.vec", "bg.txt", 200, 300, 1024, 1024, 3, CvCascadeParams(0, ftype, (24, 24)), fp,
+                  ccb.CvCascadeBoostParams(), positives=pos, backgrounds=bgs)
+    assert len(cc.stageClassifiers) >= 1
+    if ftype == orc.HAAR:
+        # the point of this case: tilted features evaluated from a whole-level tilted integral.  The trained stages may
+        # not use one, so a hand-made stage of three tilted stumps (one per tilted shape family) is appended.
+        tilted = [fi for fi in range(0, cc.featureEvaluator.getNumFeatures(), 997) if cc.featureEvaluator.feature(fi)[2]][:3]
+        assert len(tilted) == 3
+        trees = [[dict(left=1, right=2, var_idx=fi, c=0.01 * (k - 1), value=0.0), dict(left=-1, right=-1, var_idx=-1, value=1.0),
+                  dict(left=-1, right=-1, var_idx=-1, value=-1.0)] for k, fi in enumerate(tilted)]
+        cc.stageClassifiers.append(ccb.CvCascadeBoost.from_trees(-0.5, trees))
+    cc._sync_cascade()
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    start = copy.copy(cc._reader)
+    results = []
+    for m in (2, 1, 0):
+        check(lib.cc_mine_set_mode(h, m), "cc_mine_set_mode")
+        st = _lib.ReaderState.from_buffer_copy(bytes(start))
+        consumed, got = C.c_int64(0), C.c_int32(0)
+        check(lib.cc_mine_negatives(h, 200, 250, 1e-7, C.byref(st), C.byref(consumed), C.byref(got)), "cc_mine_negatives")
+        imgs = cc.featureEvaluator.images(200, got.value)
+        ints = [cc.featureEvaluator.integrals(200 + k) for k in (0, got.value // 2, got.value - 1)]
+        results.append((got.value, consumed.value, _state_dict(st), imgs, ints))
+    check(lib.cc_mine_set_mode(h, 0), "cc_mine_set_mode")
+    ref = results[0]
+    assert ref[0] == 250 and ref[1] > 250
+    for r in results[1:]:
+        assert r[0] == ref[0] and r[1] == ref[1] and r[2] == ref[2]
+        assert np.array_equal(r[3], ref[3])
+        for a, b in zip(r[4], ref[4]):
+            assert (a[0] == b[0]).all() and np.float32(a[2]) == np.float32(b[2])
+            if a[1] is not None and b[1] is not None:
+                assert (np.asarray(a[1]) == np.asarray(b[1])).all()
