@@ -150,57 +150,49 @@ __device__ __forceinline__ float haar_div(float a, float nfv, float r) {
 // instead of 6-9 tap loads and multiply-adds.  The feature -> fval row mapping comes from dense index tables
 // (-1 = shape absent from this mode / not in this rank's shard).
 // ------------------------------------------------------------------------------------------------
-constexpr int SEP_THREADS = 512;
+constexpr int SEP_THREADS = 1024;
 constexpr int SEP_WARPS = SEP_THREADS / 32;
 
-__device__ __forceinline__ void sep_store(float* __restrict__ out_col, int f, int n_stride, int acc, float nf, float rnf) {
-  __stcs(out_col + (size_t)f * n_stride, haar_div<2>((float)acc, nf, rnf));
+// one fval cell: row f of this sample's column.  The byte stride of a row fits 32 bits, so the address is one IMAD.WIDE.
+template <int STEPS>
+__device__ __forceinline__ void sep_store(char* __restrict__ out_bytes, int f, uint32_t stride_bytes, int acc, float nf, float rnf) {
+  float* p = reinterpret_cast<float*>(out_bytes + (unsigned long long)(uint32_t)f * stride_bytes);
+  __stcs(p, haar_div<STEPS>((float)acc, nf, rnf));
 }
 
-__global__ void __launch_bounds__(SEP_THREADS, 1)
-k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restrict__ nf, const SepPattern* __restrict__ patterns,
-                   int npatterns, int patterns_per_chunk, const int32_t* __restrict__ tab_row, const int32_t* __restrict__ tab_col,
-                   int W, int H, int row_base, float* __restrict__ fval, int n_stride, int ntiles_used) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const int S = W + 1, P = S * (H + 1);
-  const int HP = (H + 3) & ~3, WP = (W + 3) & ~3;
-  const int L = max(W, H) + 1;                                               // scratch column length
-  int32_t* stile = reinterpret_cast<int32_t*>(smem_raw);                      // [P][32]
-  int32_t* scratch_all = stile + (size_t)P * TILE;                            // [SEP_WARPS][2][L][32]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(scratch_all + (size_t)SEP_WARPS * 2 * L * TILE);
-  int* s_next = reinterpret_cast<int*>(bar + 1);
-
-  const int tile = blockIdx.x;
-  const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
-  if (threadIdx.x == 0) {
-    *s_next = 0;
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar, tile_bytes);
-    bulk_g2s(stile, sum_tiles + (size_t)tile * P * TILE, tile_bytes, bar);
+// Walk the feature-index table row tp[0 .. nd) (groups of 4, -1 = absent, prefetched one group ahead) and emit
+// ACC(d) for every present entry; d = 1-based step (dy or dx).
+#define SEP_EMIT(tp, nd, ACC)                                                                              \
+  {                                                                                                        \
+    int4 cur4 = __ldg(reinterpret_cast<const int4*>(tp));                                                  \
+    for (int d0_ = 0; d0_ < (nd); d0_ += 4) {                                                              \
+      const int4 f4_ = cur4;                                                                               \
+      if (d0_ + 4 < (nd)) cur4 = __ldg(reinterpret_cast<const int4*>((tp) + d0_ + 4));                     \
+      const int fs_[4] = {f4_.x, f4_.y, f4_.z, f4_.w};                                                     \
+      _Pragma("unroll") for (int k_ = 0; k_ < 4; ++k_) {                                                   \
+        const int d = d0_ + k_ + 1;                                                                        \
+        if (fs_[k_] >= 0) sep_store<STEPS>(out_bytes, fs_[k_], stride_bytes, (ACC), nfv, rnf);             \
+      }                                                                                                    \
+    }                                                                                                      \
   }
-  __syncthreads();
-  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  int32_t* sA = scratch_all + (size_t)warp * 2 * L * TILE + lane;             // element r at sA[r * 32]
-  int32_t* sB = sA + (size_t)L * TILE;
-  const float nfv = nf[tile * TILE + lane];
-  const float rnf = haar_recip(nfv);
-  float* out_col = fval + (tile * TILE + lane) - (size_t)row_base * n_stride;     // + f * n_stride = this sample's cell of row f
-  const int32_t* tl = stile + lane;
-  const int p_begin = blockIdx.y * patterns_per_chunk;
-  const int p_end = min(p_begin + patterns_per_chunk, npatterns);
-  mbar_wait(bar, 0);
 
+template <int STEPS>
+__device__ __forceinline__ void sep_body(const int32_t* __restrict__ tl, int32_t* __restrict__ sA, int* s_next, int p_begin, int p_end,
+                                         const SepPattern* __restrict__ patterns, const int32_t* __restrict__ tab_row,
+                                         const int32_t* __restrict__ tab_col, int W, int H, char* __restrict__ out_bytes,
+                                         uint32_t stride_bytes, float nfv, float rnf, int lane) {
+  const int S = W + 1;
+  const int HP = (H + 3) & ~3, WP = (W + 3) & ~3;
   for (;;) {
     int pi = 0;
     if (lane == 0) pi = p_begin + atomicAdd(s_next, 1);
     pi = __shfl_sync(0xffffffffu, pi, 0);
     if (pi >= p_end) break;
     const SepPattern pat = patterns[pi];
-    const int p = pat.p, d = pat.d, lo = pat.lo, hi = pat.hi, flags = pat.flags;
+    const int p = pat.p, d_ = pat.d, lo = pat.lo, hi = pat.hi, flags = pat.flags;
     if (pat.kind == 0) {
       // ---------------- row pattern: x = p, dx = d; functions of the row r = 0..H ----------------
-      const int x = p, dx = d;
+      const int x = p, dx = d_;
       const bool has3 = x + 3 * dx <= W, has4 = x + 4 * dx <= W;
       auto tabp = [&](int t, int y) { return tab_row + ((((size_t)t * W + x) * W + (dx - 1)) * H + y) * HP; };
       if (flags & 0x09) {                      // gA: x2 (bit 0), x2y2 (bit 3)
@@ -211,29 +203,9 @@ k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restric
         __syncwarp();
         for (int y = lo; y <= hi; ++y) {
           const int gy = sA[y * TILE];
-          if (flags & 0x01) {
-            const int32_t* tp = tabp(0, y);
-            for (int dy0 = 1; dy0 <= H - y; dy0 += 4) {
-              const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
-              const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k)
-                if (fs[k] >= 0) sep_store(out_col, fs[k], n_stride, sA[(y + dy0 + k) * TILE] - gy, nfv, rnf);
-            }
-          }
-          if (flags & 0x08) {
-            const int32_t* tp = tabp(3, y);
-            for (int dy0 = 1; 2 * dy0 <= H - y; dy0 += 4) {
-              const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
-              const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int dy = dy0 + k;
-                if (fs[k] >= 0)
-                  sep_store(out_col, fs[k], n_stride, gy - 2 * sA[(y + dy) * TILE] + sA[(y + 2 * dy) * TILE], nfv, rnf);
-              }
-            }
-          }
+          const int32_t* sy = sA + y * TILE;
+          if (flags & 0x01) SEP_EMIT(tabp(0, y), H - y, sy[d * TILE] - gy)
+          if (flags & 0x08) SEP_EMIT(tabp(3, y), (H - y) >> 1, gy - 2 * sy[d * TILE] + sy[2 * d * TILE])
         }
         __syncwarp();
       }
@@ -245,38 +217,26 @@ k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restric
         __syncwarp();
         for (int y = lo; y <= hi; ++y) {
           const int gy = sA[y * TILE];
-          const int32_t* tp = tabp(1, y);
-          for (int dy0 = 1; dy0 <= H - y; dy0 += 4) {
-            const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
-            const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (fs[k] >= 0) sep_store(out_col, fs[k], n_stride, sA[(y + dy0 + k) * TILE] - gy, nfv, rnf);
-          }
+          const int32_t* sy = sA + y * TILE;
+          SEP_EMIT(tabp(1, y), H - y, sy[d * TILE] - gy)
         }
         __syncwarp();
       }
-      if (has3 && (flags & 0x10)) {            // gW, gM: centre-surround
+      if (has3 && (flags & 0x10)) {            // centre-surround: gW from the scratch column, gM straight from the tile
         for (int r = 0; r <= H; ++r) {
           const int32_t* row = tl + (size_t)(r * S + x) * TILE;
           sA[r * TILE] = row[3 * dx * TILE] - row[0];
-          sB[r * TILE] = row[2 * dx * TILE] - row[dx * TILE];
         }
         __syncwarp();
+        const int32_t* c1 = tl + (size_t)(x + dx) * TILE;
+        const int32_t* c2 = tl + (size_t)(x + 2 * dx) * TILE;
         for (int y = lo; y <= hi; ++y) {
           const int wy = sA[y * TILE];
-          const int32_t* tp = tabp(4, y);
-          for (int dy0 = 1; 3 * dy0 <= H - y; dy0 += 4) {
-            const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
-            const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int dy = dy0 + k;
-              if (fs[k] >= 0)
-                sep_store(out_col, fs[k], n_stride,
-                          wy - sA[(y + 3 * dy) * TILE] + 9 * (sB[(y + 2 * dy) * TILE] - sB[(y + dy) * TILE]), nfv, rnf);
-            }
-          }
+          const int32_t* sy = sA + y * TILE;
+          const int32_t* m1 = c1 + (size_t)y * S * TILE;
+          const int32_t* m2 = c2 + (size_t)y * S * TILE;
+          SEP_EMIT(tabp(4, y), (H - y) / 3,
+                   wy - sy[3 * d * TILE] + 9 * ((m2[2 * d * S * TILE] - m1[2 * d * S * TILE]) - (m2[d * S * TILE] - m1[d * S * TILE])))
         }
         __syncwarp();
       }
@@ -288,20 +248,14 @@ k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restric
         __syncwarp();
         for (int y = lo; y <= hi; ++y) {
           const int gy = sA[y * TILE];
-          const int32_t* tp = tabp(2, y);
-          for (int dy0 = 1; dy0 <= H - y; dy0 += 4) {
-            const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dy0 - 1));
-            const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (fs[k] >= 0) sep_store(out_col, fs[k], n_stride, sA[(y + dy0 + k) * TILE] - gy, nfv, rnf);
-          }
+          const int32_t* sy = sA + y * TILE;
+          SEP_EMIT(tabp(2, y), H - y, sy[d * TILE] - gy)
         }
         __syncwarp();
       }
     } else {
       // ---------------- column pattern: y = p, dy = d; functions of the column c = 0..W ----------------
-      const int y = p, dy = d;
+      const int y = p, dy = d_;
       auto tabp = [&](int t, int x) { return tab_col + ((((size_t)t * H + y) * H + (dy - 1)) * W + x) * WP; };
       for (int t = 0; t < 3; ++t) {
         if (!(flags & (1 << t))) continue;
@@ -321,19 +275,60 @@ k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restric
         __syncwarp();
         for (int x = lo; x <= hi; ++x) {
           const int hx = sA[x * TILE];
-          const int32_t* tp = tabp(t, x);
-          for (int dx0 = 1; dx0 <= W - x; dx0 += 4) {
-            const int4 f4 = __ldg(reinterpret_cast<const int4*>(tp + dx0 - 1));
-            const int fs[4] = {f4.x, f4.y, f4.z, f4.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (fs[k] >= 0) sep_store(out_col, fs[k], n_stride, sA[(x + dx0 + k) * TILE] - hx, nfv, rnf);
-          }
+          const int32_t* sx = sA + x * TILE;
+          SEP_EMIT(tabp(t, x), W - x, sx[d * TILE] - hx)
         }
         __syncwarp();
       }
     }
   }
+}
+#undef SEP_EMIT
+
+__global__ void __launch_bounds__(SEP_THREADS, 1)
+k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restrict__ nf, const SepPattern* __restrict__ patterns,
+                   int npatterns, int patterns_per_chunk, const int32_t* __restrict__ tab_row, const int32_t* __restrict__ tab_col,
+                   int W, int H, int row_base, float* __restrict__ fval, int n_stride, int ntiles_used) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int S = W + 1, P = S * (H + 1);
+  const int L = max(W, H) + 1;                                               // scratch column length
+  int32_t* stile = reinterpret_cast<int32_t*>(smem_raw);                      // [P][32]
+  int32_t* scratch_all = stile + (size_t)P * TILE;                            // [SEP_WARPS][L][32]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(scratch_all + (size_t)SEP_WARPS * L * TILE);
+  int* s_next = reinterpret_cast<int*>(bar + 1);
+
+  const int tile = blockIdx.x;
+  const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
+  if (threadIdx.x == 0) {
+    *s_next = 0;
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_expect_tx(bar, tile_bytes);
+    bulk_g2s(stile, sum_tiles + (size_t)tile * P * TILE, tile_bytes, bar);
+  }
+  __syncthreads();
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  int32_t* sA = scratch_all + (size_t)warp * L * TILE + lane;                 // element r at sA[r * 32]
+  const float nfv = nf[tile * TILE + lane];
+  const float rnf = haar_recip(nfv);
+  // + f * stride_bytes = this sample's cell of row f
+  char* out_bytes = reinterpret_cast<char*>(fval) + ((long long)(tile * TILE + lane) - (long long)row_base * n_stride) * (long long)sizeof(float);
+  {   // keep the per-lane base as one opaque 64-bit register so that a cell address is a single IMAD.WIDE
+    unsigned long long ob = reinterpret_cast<unsigned long long>(out_bytes);
+    asm volatile("" : "+l"(ob));
+    out_bytes = reinterpret_cast<char*>(ob);
+  }
+  const uint32_t stride_bytes = (uint32_t)n_stride * (uint32_t)sizeof(float);
+  const int32_t* tl = stile + lane;
+  const int p_begin = blockIdx.y * patterns_per_chunk;
+  const int p_end = min(p_begin + patterns_per_chunk, npatterns);
+  // One correction step of haar_div is exact when 1/nf is correctly rounded, except (Markstein) for divisors whose
+  // significand is all ones; a warp holding such a sample takes the two-step variant.
+  const bool odd_nf = (__float_as_uint(nfv) & 0x7FFFFFu) == 0x7FFFFFu;
+  const bool two_steps = __any_sync(0xffffffffu, odd_nf);
+  mbar_wait(bar, 0);
+  if (two_steps) sep_body<2>(tl, sA, s_next, p_begin, p_end, patterns, tab_row, tab_col, W, H, out_bytes, stride_bytes, nfv, rnf, lane);
+  else sep_body<1>(tl, sA, s_next, p_begin, p_end, patterns, tab_row, tab_col, W, H, out_bytes, stride_bytes, nfv, rnf, lane);
 }
 
 // K2 / LBP: same tiling; 16 corner taps -> 9 cell sums -> 8-bit code (lbpfeatures.h:70-83).
@@ -600,7 +595,7 @@ int cc_boost_set_shard(cc_ctx* ctx, int rank, int world) {
       cudaFree(ctx->d_sep_tab_row); cudaFree(ctx->d_sep_tab_col); cudaFree(ctx->d_sep_patterns);
       ctx->d_sep_tab_row = ctx->d_sep_tab_col = nullptr; ctx->d_sep_patterns = nullptr; ctx->n_sep_patterns = 0; ctx->use_sep = false;
       const int W = ctx->W, H = ctx->H;
-      const size_t sep_smem = (size_t)ctx->P * TILE * 4 + (size_t)SEP_WARPS * 2 * (std::max(W, H) + 1) * TILE * 4 + 64;
+      const size_t sep_smem = (size_t)ctx->P * TILE * 4 + (size_t)SEP_WARPS * (std::max(W, H) + 1) * TILE * 4 + 64;
       if (sep_smem <= 227 * 1024 && W <= 255 && H <= 255 && !up.empty()) {
         const int HP = (H + 3) & ~3, WP = (W + 3) & ~3;
         std::vector<int32_t> trow((size_t)5 * W * W * H * HP, -1), tcol((size_t)3 * H * H * W * WP, -1);
@@ -682,7 +677,7 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
                       {ctx->d_tilted, ctx->d_taps_tilted, (int)ctx->tilted_rows.size()}};
       if (ctx->use_sep && ls[0].n > 0) {
         ScopedTimer tm(ctx, "precalc", 1);
-        const size_t sep_smem = (size_t)P * TILE * 4 + (size_t)SEP_WARPS * 2 * (std::max(ctx->W, ctx->H) + 1) * TILE * 4 + 64;
+        const size_t sep_smem = (size_t)P * TILE * 4 + (size_t)SEP_WARPS * (std::max(ctx->W, ctx->H) + 1) * TILE * 4 + 64;
         // the list is sorted heavy-first; every CTA drains its chunk through a shared counter, the grid has many CTAs per SM
         const int nchunks = std::max(1, std::min(ctx->n_sep_patterns / (SEP_WARPS * 2), (ctx->sm_count * 6 + ntiles_used - 1) / ntiles_used));
         const int ppc = (ctx->n_sep_patterns + nchunks - 1) / nchunks;
