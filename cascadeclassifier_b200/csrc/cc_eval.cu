@@ -354,10 +354,10 @@ int store_alloc(cc_ctx* ctx, EvalStore& st, int max_samples) {
 int eval_free(cc_ctx* ctx) {
   cudaFree(ctx->d_imgs); cudaFree(ctx->d_labels); cudaFree(ctx->d_sum); cudaFree(ctx->d_tilted);
   cudaFree(ctx->d_nf); cudaFree(ctx->d_hog); cudaFree(ctx->d_haar_taps); cudaFree(ctx->d_lbp_taps);
-  cudaFree(ctx->d_hog_taps); cudaFree(ctx->d_taps_upright); cudaFree(ctx->d_taps_tilted); cudaFree(ctx->d_sep_tab_row); cudaFree(ctx->d_sep_tab_col); cudaFree(ctx->d_sep_patterns);
+  cudaFree(ctx->d_hog_taps); cudaFree(ctx->d_taps_upright); cudaFree(ctx->d_taps_tilted); cudaFree(ctx->d_sep_tab_row); cudaFree(ctx->d_sep_tab_col); cudaFree(ctx->d_sep_patterns); cudaFree(ctx->d_sep_tab_t1); cudaFree(ctx->d_sep_tab_t2);
   ctx->d_imgs = ctx->d_labels = nullptr; ctx->d_sum = ctx->d_tilted = nullptr; ctx->d_nf = nullptr; ctx->d_hog = nullptr;
   ctx->d_haar_taps = nullptr; ctx->d_lbp_taps = nullptr; ctx->d_hog_taps = nullptr;
-  ctx->d_taps_upright = ctx->d_taps_tilted = nullptr; ctx->d_sep_tab_row = ctx->d_sep_tab_col = nullptr; ctx->d_sep_patterns = nullptr; ctx->n_sep_patterns = 0; ctx->use_sep = false;
+  ctx->d_taps_upright = ctx->d_taps_tilted = nullptr; ctx->d_sep_tab_row = ctx->d_sep_tab_col = ctx->d_sep_tab_t1 = ctx->d_sep_tab_t2 = nullptr; ctx->d_sep_patterns = nullptr; ctx->n_sep_patterns = 0; ctx->n_sep_tilted = 0; ctx->use_sep = false;
   ctx->ftype = -1;
   return CC_OK;
 }

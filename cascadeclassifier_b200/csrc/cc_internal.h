@@ -71,7 +71,8 @@ __host__ __device__
 #endif
 inline int tap_coef(uint32_t w) { return (int)(int8_t)((w >> 16) & 0xFFu); }
 
-// Work item of the separable upright-Haar precalc: all features sharing (x, dx) [kind 0] or (y, dy) [kind 1]
+// Work item of the separable Haar precalc: all features sharing (x, dx) [kind 0], (y, dy) [kind 1], or, for tilted
+// features in rotated coordinates a = x + y, b = y - x, (a0, dx) [kind 2] or (b0 + W, dy) [kind 3]
 struct SepPattern { uint8_t kind, p, d, flags; uint8_t lo, hi, pad0, pad1; };   // flags: bit t set = shape t has local features
 static_assert(sizeof(SepPattern) == 8, "SepPattern layout");
 
@@ -146,8 +147,11 @@ struct cc_ctx {
   // separable upright precalc (cc_traindata.cu): feature-index tables and pattern list of the local shard
   int32_t* d_sep_tab_row = nullptr;     // [5][W][W][H][HP]
   int32_t* d_sep_tab_col = nullptr;     // [3][H][H][W][WP]
-  cc::SepPattern* d_sep_patterns = nullptr;
-  int n_sep_patterns = 0;
+  int32_t* d_sep_tab_t1 = nullptr;      // tilted, long side along a: [3][W+H][W][W][HP]
+  int32_t* d_sep_tab_t2 = nullptr;      // tilted, long side along b: [3][W+H+1][H][W][WP]
+  cc::SepPattern* d_sep_patterns = nullptr;   // upright patterns, then tilted patterns
+  int n_sep_patterns = 0;               // upright
+  int n_sep_tilted = 0;
   bool use_sep = false;
 
   // ---- train data ----

@@ -179,7 +179,8 @@ __device__ __forceinline__ void sep_store(char* __restrict__ out_bytes, int f, u
 template <int STEPS>
 __device__ __forceinline__ void sep_body(const int32_t* __restrict__ tl, int32_t* __restrict__ sA, int* s_next, int p_begin, int p_end,
                                          const SepPattern* __restrict__ patterns, const int32_t* __restrict__ tab_row,
-                                         const int32_t* __restrict__ tab_col, int W, int H, char* __restrict__ out_bytes,
+                                         const int32_t* __restrict__ tab_col, const int32_t* __restrict__ tab_t1,
+                                         const int32_t* __restrict__ tab_t2, int W, int H, char* __restrict__ out_bytes,
                                          uint32_t stride_bytes, float nfv, float rnf, int lane) {
   const int S = W + 1;
   const int HP = (H + 3) & ~3, WP = (W + 3) & ~3;
@@ -253,6 +254,68 @@ __device__ __forceinline__ void sep_body(const int32_t* __restrict__ tl, int32_t
         }
         __syncwarp();
       }
+    } else if (pat.kind >= 2) {
+      // ---------------- tilted patterns (the tile is the tilted integral) ----------------
+      // In rotated coordinates a = X + Y, b = Y - X a tilted rectangle (x, y, w, h) is the axis-aligned box
+      // [a0, a0 + 2w] x [b0, b0 + 2h] with (a0, b0) = (x + y, y - x) (corners of CV_TILTED_OFFSETS), so the tilted
+      // shapes separate exactly like the upright ones:
+      //   kind 2 (long side along +a: tilted x2/x3/x4):  acc = G(b0) - G(b0 + 2 dy), G a function of b for fixed (a0, dx)
+      //   kind 3 (long side along +b: tilted y2/y3/y4):  acc = G(a0) - G(a0 + 2 dx), G a function of a for fixed (b0, dy)
+      //   G = T0 - 2 T1 + T2 | -T0 + 3 T1 - 3 T2 + T3 | -T0 + 2 T1 - 2 T3 + T4 at the pattern's 3..5 equidistant points
+      // (expand -1*outer + wt*inner of src/haarfeatures.cpp:197-247).  One tile cell step: a += 2 -> off += S + 1,
+      // b += 2 -> off += S - 1.
+      const bool along_a = pat.kind == 2;
+      const int c0 = along_a ? p : p - W;                 // a0, or b0 (stored + W)
+      const int LT = ((W + H) >> 1) + 1;
+      const int par = along_a ? ((c0 + W) & 1) : (c0 & 1);
+      const int step = along_a ? d_ * (S + 1) : d_ * (S - 1);
+      for (int t = 0; t < 3; ++t) {
+        if (!(flags & (1 << t))) continue;
+        const int mmax = t + 2;
+        // only the cells the pattern's features read: b in [a0 - 2 hi, a0] (dy <= x), a in [b0 + 2 lo, b0 + 2 W] (x + dx <= W)
+        const int jlo = along_a ? max(0, (c0 - 2 * hi + W) >> 1) : max(0, (c0 + 2 * lo) >> 1);
+        const int jhi = along_a ? min(LT - 1, (c0 + W) >> 1) : min(LT - 1, (c0 + 2 * W) >> 1);
+        for (int j = jlo; j <= jhi; ++j) {
+          const int free_c = along_a ? 2 * j - W + par : 2 * j + par;       // b (kind 2) or a (kind 3)
+          const int a = along_a ? c0 : free_c, b = along_a ? free_c : c0;
+          const int X0 = (a - b) >> 1, Y0 = (a + b) >> 1;
+          const int Xe = along_a ? X0 + mmax * d_ : X0 - mmax * d_, Ye = Y0 + mmax * d_;
+          int v = 0;
+          if (X0 >= 0 && X0 <= W && Y0 >= 0 && Xe >= 0 && Xe <= W && Ye <= H) {
+            const int32_t* q = tl + (size_t)(Y0 * S + X0) * TILE;
+            const int st = step * TILE;
+            if (t == 0) v = q[0] - 2 * q[st] + q[2 * st];
+            else if (t == 1) v = -q[0] + 3 * q[st] - 3 * q[2 * st] + q[3 * st];
+            else v = -q[0] + 2 * q[st] - 2 * q[3 * st] + q[4 * st];
+          }
+          sA[j * TILE] = v;
+        }
+        __syncwarp();
+        if (along_a) {
+          const int A = W + H;
+          for (int x = lo; x <= hi; ++x) {
+            const int jb = (c0 - 2 * x + W) >> 1;
+            const int gy = sA[jb * TILE];
+            const int32_t* sy = sA + jb * TILE;
+            const int32_t* tp = tab_t1 + ((((size_t)t * A + c0) * W + (d_ - 1)) * W + x) * HP;
+            // catalog bounds (fits iff x+k*dx<=W, y+k*dx+dy<=H, x-dy>=0): dy = 1 .. min(x, H - y - k*dx), y = a0 - x
+            const int nd = min(x, H - (c0 - x) - mmax * d_);
+            if (nd > 0 && x + mmax * d_ <= W) SEP_EMIT(tp, nd, gy - sy[d * TILE])
+          }
+        } else {
+          const int B = W + H + 1;
+          for (int x = lo; x <= hi; ++x) {
+            const int ja = (c0 + 2 * x) >> 1;
+            const int gy = sA[ja * TILE];
+            const int32_t* sy = sA + ja * TILE;
+            const int32_t* tp = tab_t2 + ((((size_t)t * B + p) * H + (d_ - 1)) * W + x) * WP;
+            // catalog bounds (fits iff x+dx<=W, y+dx+k*dy<=H, x-k*dy>=0): dx = 1 .. min(W - x, H - y - k*dy), y = b0 + x
+            const int nd = min(W - x, H - (c0 + x) - mmax * d_);
+            if (nd > 0 && x - mmax * d_ >= 0) SEP_EMIT(tp, nd, gy - sy[d * TILE])
+          }
+        }
+        __syncwarp();
+      }
     } else {
       // ---------------- column pattern: y = p, dy = d; functions of the column c = 0..W ----------------
       const int y = p, dy = d_;
@@ -288,7 +351,8 @@ __device__ __forceinline__ void sep_body(const int32_t* __restrict__ tl, int32_t
 __global__ void __launch_bounds__(SEP_THREADS, 1)
 k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restrict__ nf, const SepPattern* __restrict__ patterns,
                    int npatterns, int patterns_per_chunk, const int32_t* __restrict__ tab_row, const int32_t* __restrict__ tab_col,
-                   int W, int H, int row_base, float* __restrict__ fval, int n_stride, int ntiles_used) {
+                   const int32_t* __restrict__ tab_t1, const int32_t* __restrict__ tab_t2, int W, int H, int row_base,
+                   float* __restrict__ fval, int n_stride, int ntiles_used) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int S = W + 1, P = S * (H + 1);
   const int L = max(W, H) + 1;                                               // scratch column length
@@ -327,8 +391,8 @@ k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restric
   const bool odd_nf = (__float_as_uint(nfv) & 0x7FFFFFu) == 0x7FFFFFu;
   const bool two_steps = __any_sync(0xffffffffu, odd_nf);
   mbar_wait(bar, 0);
-  if (two_steps) sep_body<2>(tl, sA, s_next, p_begin, p_end, patterns, tab_row, tab_col, W, H, out_bytes, stride_bytes, nfv, rnf, lane);
-  else sep_body<1>(tl, sA, s_next, p_begin, p_end, patterns, tab_row, tab_col, W, H, out_bytes, stride_bytes, nfv, rnf, lane);
+  if (two_steps) sep_body<2>(tl, sA, s_next, p_begin, p_end, patterns, tab_row, tab_col, tab_t1, tab_t2, W, H, out_bytes, stride_bytes, nfv, rnf, lane);
+  else sep_body<1>(tl, sA, s_next, p_begin, p_end, patterns, tab_row, tab_col, tab_t1, tab_t2, W, H, out_bytes, stride_bytes, nfv, rnf, lane);
 }
 
 // K2 / LBP: same tiling; 16 corner taps -> 9 cell sums -> 8-bit code (lbpfeatures.h:70-83).
@@ -592,16 +656,19 @@ int cc_boost_set_shard(cc_ctx* ctx, int rank, int world) {
         CC_CUDA(cudaMemcpy(ctx->d_taps_tilted, tt.data(), tt.size() * sizeof(HaarTaps), cudaMemcpyHostToDevice));
       }
       // ---- separable upright precalc: index tables + pattern list (only if one tile + scratch fit in smem) ----
-      cudaFree(ctx->d_sep_tab_row); cudaFree(ctx->d_sep_tab_col); cudaFree(ctx->d_sep_patterns);
-      ctx->d_sep_tab_row = ctx->d_sep_tab_col = nullptr; ctx->d_sep_patterns = nullptr; ctx->n_sep_patterns = 0; ctx->use_sep = false;
+      cudaFree(ctx->d_sep_tab_row); cudaFree(ctx->d_sep_tab_col); cudaFree(ctx->d_sep_patterns); cudaFree(ctx->d_sep_tab_t1); cudaFree(ctx->d_sep_tab_t2);
+      ctx->d_sep_tab_row = ctx->d_sep_tab_col = ctx->d_sep_tab_t1 = ctx->d_sep_tab_t2 = nullptr;
+      ctx->d_sep_patterns = nullptr; ctx->n_sep_patterns = 0; ctx->n_sep_tilted = 0; ctx->use_sep = false;
       const int W = ctx->W, H = ctx->H;
       const size_t sep_smem = (size_t)ctx->P * TILE * 4 + (size_t)SEP_WARPS * (std::max(W, H) + 1) * TILE * 4 + 64;
-      if (sep_smem <= 227 * 1024 && W <= 255 && H <= 255 && !up.empty()) {
+      if (sep_smem <= 227 * 1024 && W + H <= 255 && (!up.empty() || !tl.empty())) {
         const int HP = (H + 3) & ~3, WP = (W + 3) & ~3;
+        const int A = W + H, B = W + H + 1;
         std::vector<int32_t> trow((size_t)5 * W * W * H * HP, -1), tcol((size_t)3 * H * H * W * WP, -1);
+        std::vector<int32_t> tt1(tl.empty() ? 4 : (size_t)3 * A * W * W * HP, -1), tt2(tl.empty() ? 4 : (size_t)3 * B * H * W * WP, -1);
         // per pattern: which shapes occur and the range of the outer loop variable that has local features
         struct Acc { int flags = 0, lo = 1 << 30, hi = -1; };
-        std::vector<Acc> prow((size_t)W * W), pcol((size_t)H * H);
+        std::vector<Acc> prow((size_t)W * W), pcol((size_t)H * H), pt1((size_t)A * W), pt2((size_t)B * H);
         static const int row_t[8] = {0, -1, 1, -1, 2, -1, 3, 4};   // shape -> row-table type
         static const int col_t[8] = {-1, 0, -1, 1, -1, 2, -1, -1}; // shape -> column-table type
         for (int f : up) {
@@ -618,7 +685,22 @@ int cc_boost_set_shard(cc_ctx* ctx, int rank, int world) {
             a.flags |= 1 << t; a.lo = std::min(a.lo, hf.x); a.hi = std::max(a.hi, hf.x);
           }
         }
-        std::vector<SepPattern> pats;
+        for (int f : tl) {       // tilted shapes 8..13: even = long side along a (x2, x3, x4), odd = along b (y2, y3, y4)
+          const HaarFeatureH& hf = ctx->haar[f];
+          const int t = (hf.shape - 8) >> 1;
+          if (((hf.shape - 8) & 1) == 0) {
+            const int a0 = hf.x + hf.y;
+            tt1[((((size_t)t * A + a0) * W + (hf.dx - 1)) * W + hf.x) * HP + (hf.dy - 1)] = f;
+            Acc& a = pt1[(size_t)a0 * W + (hf.dx - 1)];
+            a.flags |= 1 << t; a.lo = std::min(a.lo, hf.x); a.hi = std::max(a.hi, hf.x);
+          } else {
+            const int b0w = hf.y - hf.x + W;
+            tt2[((((size_t)t * B + b0w) * H + (hf.dy - 1)) * W + hf.x) * WP + (hf.dx - 1)] = f;
+            Acc& a = pt2[(size_t)b0w * H + (hf.dy - 1)];
+            a.flags |= 1 << t; a.lo = std::min(a.lo, hf.x); a.hi = std::max(a.hi, hf.x);
+          }
+        }
+        std::vector<SepPattern> pats, patt;
         for (int x = 0; x < W; ++x)
           for (int dx = 1; dx <= W; ++dx) {
             const Acc& a = prow[(size_t)x * W + (dx - 1)];
@@ -629,15 +711,34 @@ int cc_boost_set_shard(cc_ctx* ctx, int rank, int world) {
             const Acc& a = pcol[(size_t)y * H + (dy - 1)];
             if (a.flags) pats.push_back({1, (uint8_t)y, (uint8_t)dy, (uint8_t)a.flags, (uint8_t)a.lo, (uint8_t)a.hi, 0, 0});
           }
+        for (int a0 = 0; a0 < A; ++a0)
+          for (int dx = 1; dx <= W; ++dx) {
+            const Acc& a = pt1[(size_t)a0 * W + (dx - 1)];
+            if (a.flags) patt.push_back({2, (uint8_t)a0, (uint8_t)dx, (uint8_t)a.flags, (uint8_t)a.lo, (uint8_t)a.hi, 0, 0});
+          }
+        for (int b0w = 0; b0w < B; ++b0w)
+          for (int dy = 1; dy <= H; ++dy) {
+            const Acc& a = pt2[(size_t)b0w * H + (dy - 1)];
+            if (a.flags) patt.push_back({3, (uint8_t)b0w, (uint8_t)dy, (uint8_t)a.flags, (uint8_t)a.lo, (uint8_t)a.hi, 0, 0});
+          }
         // heavy patterns (small d: most features) first, so that the dynamic per-CTA queue ends with light ones
-        std::stable_sort(pats.begin(), pats.end(), [](const SepPattern& a, const SepPattern& b) { return a.d < b.d; });
-        CC_CUDA(cudaMalloc(&ctx->d_sep_tab_row, trow.size() * sizeof(int32_t)));
-        CC_CUDA(cudaMemcpy(ctx->d_sep_tab_row, trow.data(), trow.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        CC_CUDA(cudaMalloc(&ctx->d_sep_tab_col, tcol.size() * sizeof(int32_t)));
-        CC_CUDA(cudaMemcpy(ctx->d_sep_tab_col, tcol.data(), tcol.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-        CC_CUDA(cudaMalloc(&ctx->d_sep_patterns, pats.size() * sizeof(SepPattern)));
-        CC_CUDA(cudaMemcpy(ctx->d_sep_patterns, pats.data(), pats.size() * sizeof(SepPattern), cudaMemcpyHostToDevice));
+        auto by_d = [](const SepPattern& a, const SepPattern& b) { return a.d < b.d; };
+        std::stable_sort(pats.begin(), pats.end(), by_d);
+        std::stable_sort(patt.begin(), patt.end(), by_d);
         ctx->n_sep_patterns = (int)pats.size();
+        ctx->n_sep_tilted = (int)patt.size();
+        pats.insert(pats.end(), patt.begin(), patt.end());
+        auto upload = [&](int32_t** dst, const std::vector<int32_t>& v) -> int {
+          CC_CUDA(cudaMalloc(dst, v.size() * sizeof(int32_t)));
+          CC_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+          return CC_OK;
+        };
+        CC_CHECK(upload(&ctx->d_sep_tab_row, trow));
+        CC_CHECK(upload(&ctx->d_sep_tab_col, tcol));
+        CC_CHECK(upload(&ctx->d_sep_tab_t1, tt1));
+        CC_CHECK(upload(&ctx->d_sep_tab_t2, tt2));
+        CC_CUDA(cudaMalloc(&ctx->d_sep_patterns, std::max<size_t>(1, pats.size()) * sizeof(SepPattern)));
+        CC_CUDA(cudaMemcpy(ctx->d_sep_patterns, pats.data(), pats.size() * sizeof(SepPattern), cudaMemcpyHostToDevice));
         ctx->use_sep = true;
       }
     }
@@ -675,19 +776,26 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
       struct Launch { const int32_t* plane; const HaarTaps* taps; int n; };
       Launch ls[2] = {{ctx->d_sum, ctx->d_taps_upright, (int)ctx->upright_rows.size()},
                       {ctx->d_tilted, ctx->d_taps_tilted, (int)ctx->tilted_rows.size()}};
-      if (ctx->use_sep && ls[0].n > 0) {
-        ScopedTimer tm(ctx, "precalc", 1);
+      if (ctx->use_sep) {
+        // separable kernels: upright patterns on the sum tiles, tilted patterns on the tilted tiles
         const size_t sep_smem = (size_t)P * TILE * 4 + (size_t)SEP_WARPS * (std::max(ctx->W, ctx->H) + 1) * TILE * 4 + 64;
-        // the list is sorted heavy-first; every CTA drains its chunk through a shared counter, the grid has many CTAs per SM
-        const int nchunks = std::max(1, std::min(ctx->n_sep_patterns / (SEP_WARPS * 2), (ctx->sm_count * 6 + ntiles_used - 1) / ntiles_used));
-        const int ppc = (ctx->n_sep_patterns + nchunks - 1) / nchunks;
         CC_CUDA(cudaFuncSetAttribute(k_precalc_haar_sep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sep_smem));
-        dim3 grid(ntiles_used, (ctx->n_sep_patterns + ppc - 1) / ppc);
-        k_precalc_haar_sep<<<grid, SEP_THREADS, sep_smem, ctx->stream>>>(ctx->d_sum, ctx->d_nf, ctx->d_sep_patterns, ctx->n_sep_patterns, ppc,
-                                                                        ctx->d_sep_tab_row, ctx->d_sep_tab_col, ctx->W, ctx->H, ctx->row0,
-                                                                        ctx->d_fval, n_stride, ntiles_used);
-        CC_CUDA(cudaGetLastError());
-        ls[0].n = 0;      // upright rows are done
+        struct SepLaunch { const int32_t* plane; const SepPattern* pats; int n; int which; };
+        SepLaunch sl[2] = {{ctx->d_sum, ctx->d_sep_patterns, ctx->n_sep_patterns, 0},
+                           {ctx->d_tilted, ctx->d_sep_patterns + ctx->n_sep_patterns, ctx->n_sep_tilted, 1}};
+        for (const SepLaunch& L : sl) {
+          if (L.n == 0 || ls[L.which].n == 0) continue;
+          ScopedTimer tm(ctx, "precalc", 1);
+          // the list is sorted heavy-first; every CTA drains its chunk through a shared counter, the grid has many CTAs per SM
+          const int nchunks = std::max(1, std::min(L.n / (SEP_WARPS * 2), (ctx->sm_count * 6 + ntiles_used - 1) / ntiles_used));
+          const int ppc = (L.n + nchunks - 1) / nchunks;
+          dim3 grid(ntiles_used, (L.n + ppc - 1) / ppc);
+          k_precalc_haar_sep<<<grid, SEP_THREADS, sep_smem, ctx->stream>>>(L.plane, ctx->d_nf, L.pats, L.n, ppc, ctx->d_sep_tab_row, ctx->d_sep_tab_col,
+                                                                          ctx->d_sep_tab_t1, ctx->d_sep_tab_t2, ctx->W, ctx->H, ctx->row0,
+                                                                          ctx->d_fval, n_stride, ntiles_used);
+          CC_CUDA(cudaGetLastError());
+          ls[L.which].n = 0;      // these rows are done
+        }
       }
       for (const Launch& l : ls) {
         if (l.n == 0) continue;

@@ -153,6 +153,30 @@ def test_fast_division_is_exact(gpu_ctx):
     """The reciprocal-based Haar division of K2 equals IEEE division on 2e9 (integer, norm-factor) pairs."""
     import ctypes as C
     from cascadeclassifier_b200._lib import check
-    m = C.c_uint64(1)
-    check(gpu_ctx.lib.cc_debug_div_check(gpu_ctx.h, 2, 12345, 2_000_000_000, C.byref(m)), "div_check")
-    assert m.value == 0
+    for steps in (2, 1):     # 1 step is what the separable kernels use (2 for warps holding an all-ones-significand divisor)
+        m = C.c_uint64(1)
+        check(gpu_ctx.lib.cc_debug_div_check(gpu_ctx.h, steps, 12345 + steps, 2_000_000_000, C.byref(m)), "div_check")
+        assert m.value == 0
+
+
+@pytest.mark.parametrize("mode,W,H", [(orc.ALL, 24, 24), (orc.ALL, 20, 28), (orc.CORE, 30, 18)])
+def test_separable_precalc_equals_operator_call_everywhere(gpu_ctx, mode, W, H):
+    """Every row of the fval matrix written by the separable kernels (upright row/column patterns, tilted a/b patterns)
+    equals operator()(featureIdx, sampleIdx) evaluated tap by tap (k_eval_values, itself pinned to the oracle above):
+    all features, non-square windows included."""
+    import ctypes as C
+    from cascadeclassifier_b200._lib import check
+    imgs, labels = make_samples(30, 45, W, H)
+    n = len(imgs)
+    ev = _gpu_eval(orc.HAAR, mode, W, H, n, gpu_ctx)
+    ev.setImages(imgs, labels)
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    check(lib.cc_boost_precalc(h, n), "precalc")
+    F = ev.getNumFeatures()
+    step = 8192
+    for r0 in range(0, F, step):
+        nr = min(step, F - r0)
+        got = np.zeros((nr, n), np.float32)
+        check(lib.cc_boost_get_fval(h, r0, nr, got.ctypes.data_as(C.c_void_p)), "get_fval")
+        ref = ev.values(np.arange(r0, r0 + nr, dtype=np.int32), 0, n)
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), "rows %d..%d differ" % (r0, r0 + nr)
