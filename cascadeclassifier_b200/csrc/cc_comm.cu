@@ -20,6 +20,7 @@ typedef void* ncclComm_t_;
 typedef int (*fn_GetUniqueId)(ncclUniqueId_t*);
 typedef int (*fn_CommInitRank)(ncclComm_t_*, int, ncclUniqueId_t, int);
 typedef int (*fn_AllGather)(const void*, void*, size_t, int, ncclComm_t_, cudaStream_t);
+typedef int (*fn_AllReduce)(const void*, void*, size_t, int, int, ncclComm_t_, cudaStream_t);
 typedef int (*fn_CommDestroy)(ncclComm_t_);
 typedef const char* (*fn_GetErrorString)(int);
 
@@ -28,6 +29,7 @@ struct NcclApi {
   fn_GetUniqueId GetUniqueId = nullptr;
   fn_CommInitRank CommInitRank = nullptr;
   fn_AllGather AllGather = nullptr;
+  fn_AllReduce AllReduce = nullptr;
   fn_CommDestroy CommDestroy = nullptr;
   fn_GetErrorString GetErrorString = nullptr;
 } g_nccl;
@@ -43,9 +45,10 @@ int load_nccl() {
   g_nccl.GetUniqueId = (fn_GetUniqueId)dlsym(g_nccl.handle, "ncclGetUniqueId");
   g_nccl.CommInitRank = (fn_CommInitRank)dlsym(g_nccl.handle, "ncclCommInitRank");
   g_nccl.AllGather = (fn_AllGather)dlsym(g_nccl.handle, "ncclAllGather");
+  g_nccl.AllReduce = (fn_AllReduce)dlsym(g_nccl.handle, "ncclAllReduce");
   g_nccl.CommDestroy = (fn_CommDestroy)dlsym(g_nccl.handle, "ncclCommDestroy");
   g_nccl.GetErrorString = (fn_GetErrorString)dlsym(g_nccl.handle, "ncclGetErrorString");
-  CC_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.CommDestroy, CC_ERR_NCCL,
+  CC_REQUIRE(g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllGather && g_nccl.AllReduce && g_nccl.CommDestroy, CC_ERR_NCCL,
              "libnccl is missing required symbols");
   return CC_OK;
 }
@@ -60,6 +63,16 @@ int exchange_candidates(cc_ctx* ctx, void* d_best_buf) {
   int rc = g_nccl.AllGather(base, base + kCandBytes, kCandBytes, /*ncclChar*/ 0, (ncclComm_t_)ctx->nccl_comm, ctx->stream);
   CC_REQUIRE(rc == 0, CC_ERR_NCCL, "ncclAllGather failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
   return launch_argmax_candidates(ctx, base + kCandBytes, ctx->comm_world, base);
+}
+
+// Image-sharded mining: in-place sum over the ranks of a survivor bitmap (uint32 words) or of accepted-window pixels
+// (uint8); the contributions are disjoint, so the sum is the union.
+int allreduce_sum(cc_ctx* ctx, void* d_buf, size_t count, int elem_bytes) {
+  if (ctx->comm_world <= 1 || !ctx->nccl_comm) return CC_OK;
+  const int dtype = elem_bytes == 1 ? /*ncclUint8*/ 1 : /*ncclUint32*/ 3;
+  int rc = g_nccl.AllReduce(d_buf, d_buf, count, dtype, /*ncclSum*/ 0, (ncclComm_t_)ctx->nccl_comm, ctx->stream);
+  CC_REQUIRE(rc == 0, CC_ERR_NCCL, "ncclAllReduce failed: %s", g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+  return CC_OK;
 }
 
 }  // namespace cc

@@ -31,6 +31,7 @@ struct EvalView {
   const HogTaps* hog_taps;
 };
 EvalView make_eval_view_store(const cc_ctx* ctx, const EvalStore& st);
+int allreduce_sum(cc_ctx* ctx, void* d_buf, size_t count, int elem_bytes);   // cc_comm.cu: in-place NCCL sum of uint8 / uint32 on ctx->stream
 
 // ---- device-side feature evaluation (same arithmetic as cc_eval.cu / cc_boost.cu) ----------------
 __device__ __forceinline__ float m_haar_value(const HaarTaps& t, const EvalView& e, int s) {
@@ -81,7 +82,8 @@ struct LevelDesc {
   // whole-level integral planes (Haar / LBP fast path): element offset of this level's (lh+1) x (lw+1) plane in
   // each plane pool, and cumulative line counts that map a thread to (level, row | column | diagonal)
   long long ip_off;
-  int rows_base, cols_base, diag_base, pad0;
+  int rows_base, cols_base, diag_base;
+  int owned;               // image-sharded mining: this rank builds and evaluates the level (1) or skips it (0)
 };
 
 // cv::resize(src, dst, INTER_LINEAR_EXACT), 8-bit single channel: 8.8 fixed-point coefficients per axis,
@@ -444,13 +446,14 @@ k_lvl_cascade(const LevelDesc* __restrict__ levels, int nlevels, LvlPlanes pl, i
       int lo = 0, hi = nlevels - 1;
       while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= (long long)b) lo = mid; else hi = mid - 1; }
       const LevelDesc& L = levels[lo];
+      if (!L.owned) pass = false;          // another rank evaluates this level (image-sharded mining)
       const long long k = (long long)b - L.w_base + L.w_skip;
       const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
       const int pitch = L.lw + 1;
       const size_t org = (size_t)L.ip_off + (size_t)(L.y0 + iy * L.step_y) * pitch + (L.x0 + ix * L.step_x);
       const uint32_t* S = pl.sum + org;
       float nf = 0.f;
-      if (ftype == CC_FEATURE_HAAR) {
+      if (ftype == CC_FEATURE_HAAR && pass) {
         const uint32_t* Q = pl.sq + org;
         const int o0 = pitch + 1, o1 = pitch + (W - 1), o2 = (H - 1) * pitch + 1, o3 = (H - 1) * pitch + (W - 1);
         const uint32_t vs = __ldg(S + o0) - __ldg(S + o1) - __ldg(S + o2) + __ldg(S + o3);
@@ -525,8 +528,18 @@ __global__ void k_gather_list(const LevelDesc* __restrict__ levels, int nlevels,
     const long long k = b - L.w_base + L.w_skip;
     const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
     const int wy = r / W, wx = r - wy * W;
-    dst[t] = pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.lw + (L.x0 + ix * L.step_x + wx)];
+    dst[t] = L.owned ? pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.lw + (L.x0 + ix * L.step_x + wx)] : (uint8_t)0;
     if (r == 0) labels[i] = (uint8_t)label;
+  }
+}
+
+// survivor list -> bitmap over the batch ordinals (image-sharded mining: the bitmaps of the ranks are disjoint, so
+// their element-wise sum is their union)
+__global__ void k_list_to_bitmap(const unsigned int* __restrict__ list, const unsigned int* __restrict__ count, unsigned int* __restrict__ bitmap) {
+  const unsigned int n = *count;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned int b = list[i];
+    atomicOr(bitmap + (b >> 5), 1u << (b & 31));
   }
 }
 
@@ -564,6 +577,10 @@ struct MineState {
   size_t list_cap = 0;
   int* d_order = nullptr;
   int order_cap = 0;
+  unsigned int* d_bitmap = nullptr;    // image-sharded mining: survivor bitmap, summed over the ranks
+  unsigned int* h_bitmap = nullptr;
+  size_t bitmap_cap = 0;
+  bool shard_images = true;            // when an NCCL communicator is attached
 };
 
 static void free_cascade(MineState* m) {
@@ -583,6 +600,7 @@ static void free_scratch(MineState* m) {
   m->d_psum = m->d_psq = m->d_ptilt = nullptr; m->plane_cap = 0;
   cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts); cudaFree(m->d_order);
   m->d_list[0] = m->d_list[1] = m->d_counts = nullptr; m->list_cap = 0; m->d_order = nullptr; m->order_cap = 0;
+  cudaFree(m->d_bitmap); cudaFreeHost(m->h_bitmap); m->d_bitmap = nullptr; m->h_bitmap = nullptr; m->bitmap_cap = 0;
 }
 
 int mine_free(cc_ctx* ctx) {
@@ -833,9 +851,21 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
   size_t plane_elems = 0;
   int rows = 0, cols = 0, diag = 0;
   for (LevelDesc& L : bt.levels) {
-    L.ip_off = (long long)plane_elems; L.rows_base = rows; L.cols_base = cols; L.diag_base = diag; L.pad0 = 0;
+    L.ip_off = (long long)plane_elems; L.rows_base = rows; L.cols_base = cols; L.diag_base = diag;
     plane_elems += (size_t)(L.lw + 1) * (L.lh + 1);
     rows += L.lh; cols += L.lw + 1; diag += L.lw + L.lh - 1;
+  }
+  // image-sharded mining: the background images of the batch go round-robin to the ranks; every rank
+  // builds and evaluates only the levels of its images, the survivor bitmaps are summed over NVLink, and every rank
+  // then applies the same serial stopping rule to the same ordered survivor list
+  const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
+  {
+    int img_ord = -1;
+    const uint8_t* prev = nullptr;
+    for (LevelDesc& L : bt.levels) {
+      if (L.src != prev) { ++img_ord; prev = L.src; }
+      L.owned = sharded ? ((img_ord % ctx->comm_world) == ctx->comm_rank) : 1;
+    }
   }
   const bool haar = ctx->ftype == CC_FEATURE_HAAR;
   const bool tilted = haar && m->cascade_tilted;
@@ -867,13 +897,16 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
     bool fused = !m->force_unfused;
     for (const LevelDesc& L : bt.levels) fused = fused && L.lw <= LB_MAXDIM && L.lh <= LB_MAXDIM && L.sh <= 65535;
     if (fused) {
-      std::vector<int> order(nlv);
-      for (int i = 0; i < nlv; ++i) order[i] = i;
+      std::vector<int> order;
+      for (int i = 0; i < nlv; ++i) if (bt.levels[i].owned) order.push_back(i);
       std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bt.levels[a].lh > bt.levels[b].lh; });
       if (nlv > m->order_cap) { cudaFree(m->d_order); CC_CUDA(cudaMalloc(&m->d_order, sizeof(int) * nlv * 2)); m->order_cap = nlv * 2; }
-      CC_CUDA(cudaMemcpyAsync(m->d_order, order.data(), sizeof(int) * nlv, cudaMemcpyHostToDevice, ctx->stream));
-      k_lvl_build<<<nlv, LB_THREADS, 0, ctx->stream>>>(m->d_levels, m->d_order, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr, tilted ? m->d_ptilt : nullptr);
-      launches += 1;
+      if (!order.empty()) {
+        CC_CUDA(cudaMemcpyAsync(m->d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
+        k_lvl_build<<<(int)order.size(), LB_THREADS, 0, ctx->stream>>>(m->d_levels, m->d_order, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr,
+                                                                       tilted ? m->d_ptilt : nullptr);
+        launches += 1;
+      }
     } else {
       k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, (long long)bt.pool_px, m->d_pool);
       k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
@@ -910,6 +943,27 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
     ctx->launches += launches;
     if (ctx->timing_enabled) ctx->timers["mine"].launches += launches;
   }
+  if (sharded) {
+    const size_t words = ((size_t)bt.nwin + 31) / 32;
+    if (words > m->bitmap_cap) {
+      cudaFree(m->d_bitmap); cudaFreeHost(m->h_bitmap);
+      const size_t cap = words + words / 4 + 64;
+      CC_CUDA(cudaMalloc(&m->d_bitmap, cap * 4)); CC_CUDA(cudaMallocHost(&m->h_bitmap, cap * 4));
+      m->bitmap_cap = cap;
+    }
+    CC_CUDA(cudaMemsetAsync(m->d_bitmap, 0, words * 4, ctx->stream));
+    k_list_to_bitmap<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1, m->d_bitmap);
+    CC_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    CC_CHECK(allreduce_sum(ctx, m->d_bitmap, words, /*uint32*/ 4));
+    CC_CUDA(cudaMemcpyAsync(m->h_bitmap, m->d_bitmap, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t w = 0; w < words; ++w) {
+      unsigned int bits = m->h_bitmap[w];
+      while (bits) { const int k = __builtin_ctz(bits); bits &= bits - 1; survivors.push_back((unsigned)(w * 32 + k)); }
+    }
+    return CC_OK;
+  }
   CC_CUDA(cudaMemcpyAsync(m->h_surv, m->d_counts + ngroups - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
   const unsigned cnt = m->h_surv[0];
@@ -934,6 +988,8 @@ static int gather_accepted(cc_ctx* ctx, MineState* m, const Batch& bt, const uns
                                                                                   ctx->d_labels + first, label);
     CC_CUDA(cudaGetLastError());
   }
+  // image-sharded mining: only the owner of a level holds its pixels; the others wrote zeros
+  if (ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images) CC_CHECK(allreduce_sum(ctx, ctx->d_imgs + (size_t)first * npx, (size_t)n * npx, /*uint8*/ 1));
   ctx->precalc_valid = false;
   CC_CHECK(launch_integrals(ctx, main_store(ctx), first, n));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
