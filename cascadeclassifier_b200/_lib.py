@@ -95,6 +95,7 @@ def _signatures():
         "cc_mine_positives": (i32, [vp, vp, i32, i32, P(C.c_int32), P(i64), P(C.c_int32)]),
         "cc_mine_scan": (i32, [vp, i32, i32, P(i64), P(i64)]),
         "cc_mine_set_mode": (i32, [vp, i32]),
+        "cc_mine_serial_cut": (i32, [vp, i64, i64, i32, f64, P(i64), P(C.c_int32), P(i64), P(C.c_int32), vp, P(C.c_int32)]),
         "cc_reader_advance": (i32, [vp, vp, i32, i32, i32, P(ReaderState), i64, vp]),
         "cc_timing_reset": (i32, [vp]),
         "cc_timing_get": (i32, [vp, C.c_char_p, P(f64), P(i64)]),

@@ -996,6 +996,50 @@ static int gather_accepted(cc_ctx* ctx, MineState* m, const Batch& bt, const uns
   return CC_OK;
 }
 
+// The serial part of fillPassedSamples (src/cascadeclassifier.cpp:333-355) applied to a batch that has already been
+// evaluated: walk the windows in stream order, stop at the count-th acceptance or as soon as the reference's check
+// (getcount+1)/consumed <= minimumAcceptanceRatio holds before a window.  `surv` = ascending batch ordinals that pass
+// the cascade.  Returns the ordinal of the first unconsumed window; consumed / got are updated, accepted ordinals
+// appended.
+static long long serial_cut(const unsigned* surv, size_t nsurv, long long nwin, int count, double min_ratio, long long& consumed, int& got,
+                            std::vector<unsigned>& accepted, bool& stopped) {
+  accepted.clear();
+  stopped = false;
+  long long pos = 0;            // next unconsumed batch ordinal
+  size_t si = 0;
+  // smallest value c >= max(c_from, 1) of `consumed` at which the check holds
+  auto first_fire = [&](int g, long long c_from) -> long long {
+    if (!(min_ratio > 0)) return INT64_MAX;
+    long long c = std::max<long long>(1, c_from);
+    const double c0 = std::ceil(((double)g + 1) / min_ratio);
+    if (c0 > 9e18) return INT64_MAX;
+    const long long guess = (long long)c0 - 2;
+    if (guess > c) c = guess;
+    while (!(((double)g + 1) / (double)c <= min_ratio)) ++c;
+    return c;
+  };
+  if (got >= count) { stopped = true; return 0; }
+  while (pos < nwin) {
+    const long long nextPass = si < nsurv ? (long long)surv[si] : nwin;
+    const long long gap = nextPass - pos;               // failing windows before the next survivor
+    const long long fire = first_fire(got, consumed);
+    if (fire <= consumed + gap) {                       // the rule fires before a window of this gap (or before the survivor)
+      const long long adv = fire - consumed;
+      consumed += adv; pos += adv;
+      stopped = true;
+      break;
+    }
+    consumed += gap;
+    pos = nextPass;
+    if (pos >= nwin) break;
+    consumed++; got++;                                  // window `pos` passes the cascade
+    accepted.push_back((unsigned)pos);
+    pos++; si++;
+    if (got == count) { stopped = true; break; }
+  }
+  return pos;
+}
+
 }  // namespace cc
 
 using namespace cc;
@@ -1141,40 +1185,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       if (level_path) CC_CHECK(eval_levels(ctx, m, bt, survivors));
       else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
       // ---- serial stopping rule over the ordered survivors ----
-      accepted.clear();
-      long long pos = 0;            // next unconsumed batch ordinal
       bool stopped = false;
-      size_t si = 0;
-      // smallest value c >= max(c_from, 1) of `consumed` at which the reference's check
-      // (getcount+1)/consumed <= minimumAcceptanceRatio holds (cascadeclassifier.cpp:337)
-      auto first_fire = [&](int g, long long c_from) -> long long {
-        if (!(min_ratio > 0)) return INT64_MAX;
-        long long c = std::max<long long>(1, c_from);
-        const double c0 = std::ceil(((double)g + 1) / min_ratio);
-        if (c0 > 9e18) return INT64_MAX;
-        const long long guess = (long long)c0 - 2;
-        if (guess > c) c = guess;
-        while (!(((double)g + 1) / (double)c <= min_ratio)) ++c;
-        return c;
-      };
-      while (pos < nwin) {
-        const long long nextPass = si < survivors.size() ? (long long)survivors[si] : (long long)nwin;
-        const long long gap = nextPass - pos;               // failing windows before the next survivor
-        const long long fire = first_fire(got, consumed);
-        if (fire <= consumed + gap) {                       // the rule fires before a window of this gap (or before the survivor)
-          const long long adv = fire - consumed;
-          consumed += adv; pos += adv;
-          stopped = true;
-          break;
-        }
-        consumed += gap;
-        pos = nextPass;
-        if (pos >= nwin) break;
-        consumed++; got++;                                  // window `pos` passes the cascade
-        accepted.push_back((unsigned)pos);
-        pos++; si++;
-        if (got == count) { stopped = true; break; }
-      }
+      const long long pos = serial_cut(survivors.data(), survivors.size(), nwin, count, min_ratio, consumed, got, accepted, stopped);
       stop_after = pos - 1;
       if (level_path) CC_CHECK(gather_accepted(ctx, m, bt, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
       else CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
@@ -1279,6 +1291,21 @@ int cc_reader_advance(const int32_t* img_w, const int32_t* img_h, int nimg, int 
   }
   state_from_stream(ns, state);
   CC_REQUIRE(left == 0, CC_ERR_BAD_ARG, "cc_reader_advance: no usable background image (stream ended with %lld windows left)", (long long)left);
+  return CC_OK;
+}
+
+int cc_mine_serial_cut(const uint32_t* survivors, int64_t nsurv, int64_t nwin, int32_t count, double min_ratio, int64_t* consumed, int32_t* got,
+                       int64_t* next_window, int32_t* stopped, uint32_t* accepted, int32_t* n_accepted) {
+  CC_REQUIRE((survivors || nsurv == 0) && nsurv >= 0 && nwin >= 0 && consumed && got && next_window && stopped && n_accepted, CC_ERR_BAD_ARG,
+             "cc_mine_serial_cut: bad arguments");
+  std::vector<unsigned> acc;
+  long long c = *consumed;
+  int g = *got;
+  bool st = false;
+  const long long pos = serial_cut(survivors, (size_t)nsurv, nwin, count, min_ratio, c, g, acc, st);
+  *consumed = c; *got = g; *next_window = pos; *stopped = st ? 1 : 0;
+  *n_accepted = (int32_t)acc.size();
+  if (accepted) std::memcpy(accepted, acc.data(), acc.size() * sizeof(unsigned));
   return CC_OK;
 }
 

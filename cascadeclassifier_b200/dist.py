@@ -43,3 +43,38 @@ def init_comm(ctx, dist, device=None):
     raw = (C.c_ubyte * 128)(*t.cpu().tolist())
     _lib.check(ctx.lib.cc_comm_init(ctx.h, raw, rank, world), "cc_comm_init")
     return rank, world
+
+
+# ---- image-sharded mining --------------------------------------------------------------------------
+def image_owner(image_ordinal, world):
+    """Rank that builds and evaluates the pyramid of the image_ordinal-th background of a mining batch (round-robin,
+    matches eval_levels in csrc/cc_mine.cu)."""
+    return image_ordinal % world
+
+
+def survivors_to_bitmap(ordinals, nwin):
+    """uint32 bitmap over the batch ordinals; the ranks' bitmaps are disjoint, so their sum is their union."""
+    import numpy as np
+    bm = np.zeros((nwin + 31) // 32, np.uint32)
+    o = np.asarray(ordinals, np.int64)
+    np.bitwise_or.at(bm, o >> 5, (np.uint32(1) << (o & 31).astype(np.uint32)))
+    return bm
+
+
+def bitmap_to_survivors(bitmap):
+    """Ascending batch ordinals of the set bits (the ordered survivor list every rank feeds to the serial cut)."""
+    import numpy as np
+    bits = np.unpackbits(np.asarray(bitmap, np.uint32).view(np.uint8), bitorder="little")
+    return np.nonzero(bits)[0].astype(np.uint32)
+
+
+def serial_cut(survivors, nwin, count, min_ratio, consumed=0, got=0):
+    """cc_mine_serial_cut: the reference's serial stopping rule over an evaluated batch (host only)."""
+    import numpy as np
+    lib = _lib.load()
+    surv = np.ascontiguousarray(survivors, np.uint32)
+    c, g, nxt, st, na = C.c_int64(consumed), C.c_int32(got), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+    acc = np.zeros(max(1, count), np.uint32)
+    _lib.check(lib.cc_mine_serial_cut(surv.ctypes.data_as(C.c_void_p), len(surv), int(nwin), int(count), float(min_ratio), C.byref(c),
+                                      C.byref(g), C.byref(nxt), C.byref(st), acc.ctypes.data_as(C.c_void_p), C.byref(na)), "cc_mine_serial_cut")
+    return dict(consumed=c.value, got=g.value, next_window=nxt.value, stopped=bool(st.value), accepted=acc[:na.value].copy())

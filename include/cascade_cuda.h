@@ -190,6 +190,14 @@ int cc_mine_set_mode(cc_ctx* ctx, int mode);
  * the given sizes; window5 (optional) = x, y, level_w, level_h, source image of the last consumed window. */
 int cc_reader_advance(const int32_t* img_w, const int32_t* img_h, int nimg, int win_w, int win_h,
                       cc_reader_state* state, int64_t nwindows, int32_t* window5);
+/* The serial part of fillPassedSamples (src/cascadeclassifier.cpp:333-355) for a batch whose windows have already been
+ * evaluated (host only, no GPU needed): survivors = ascending batch ordinals that pass the cascade, nwin = windows in
+ * the batch.  Walks the stream order, stops at the count-th acceptance or when (getcount+1)/consumed <=
+ * minimumAcceptanceRatio holds before a window.  consumed / got are in-out; next_window = first unconsumed ordinal;
+ * accepted (capacity >= count) receives the accepted ordinals.  With image-sharded mining every rank runs this on the
+ * union of the ranks' survivors, which is what makes the ordered cut identical on all GPUs. */
+int cc_mine_serial_cut(const uint32_t* survivors, int64_t nsurv, int64_t nwin, int32_t count, double min_ratio, int64_t* consumed,
+                       int32_t* got, int64_t* next_window, int32_t* stopped, uint32_t* accepted, int32_t* n_accepted);
 /* throughput probe used by bench.py: evaluate the cascade on every window of backgrounds
  * [img0, img0+nimg) at round 0 without touching evaluator slots; returns windows and survivors */
 int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* survivors);
