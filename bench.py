@@ -217,6 +217,9 @@ def run_ours(args):
         step_host()
     ms_e2e = timed(step_host, args.steps)
 
+    mining = None
+    if not args.no_mining:
+        mining = mining_leg(local, dist if world > 1 else None, dev, world)      # image-sharded across the ranks when N > 1
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -262,8 +265,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(C.sizeof(_lib.Tree) * nweak + C.sizeof(_lib.LogRow) * nweak + 16), "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "clocks": clocks,
     }
-    if world == 1 and not args.no_mining:
-        out["mining"] = mining_leg(local)
+    if mining is not None:
+        out["mining"] = mining
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(imgs, labels, F, budget_s=20.0)
     print(json.dumps(out))
@@ -271,7 +274,7 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def mining_leg(device):
+def mining_leg(device, dist=None, dev=None, world=1):
     """neg-mining windows/s (BASELINE configs[4] shape): a small Haar-ALL cascade trained on the spot, then
     fillPassedSamples' cascade evaluation over every window of generated 1920x1080 backgrounds (13584 windows per
     image at round 0).  Wall-clock through the C ABI (host batching + device work), backgrounds resident in HBM."""
@@ -281,10 +284,13 @@ def mining_leg(device):
     from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
     ctx = ccb.Context(device)
     lib, h = ctx.lib, ctx.h
+    if dist is not None:
+        from cascadeclassifier_b200.dist import init_comm
+        init_comm(ctx, dist, dev)
     pos = synth.make_positives(1400, WIN, WIN)
     small = synth.make_backgrounds(12, 480, 360, seed0=500, clutter=2.5)
     cc = CvCascadeClassifier(ctx, out=io.StringIO())
-    cc.train("/tmp/bench_mining_cascade", "pos.vec", "bg.txt", 1000, 2000, 1024, 1024, 8, CvCascadeParams(0, 0, (WIN, WIN)),
+    cc.train("/tmp/bench_mining_cascade_r%d" % device, "pos.vec", "bg.txt", 1000, 2000, 1024, 1024, 8, CvCascadeParams(0, 0, (WIN, WIN)),
              ccb.CvHaarFeatureParams(HAAR_MODE_ALL), ccb.CvCascadeBoostParams(), positives=pos, backgrounds=small)
     nimg = 256
     big = [synth.make_background(1920, 1080, 9000 + i, clutter=0.3) for i in range(4)]
@@ -297,17 +303,22 @@ def mining_leg(device):
     _lib.check(lib.cc_mine_scan(h, 0, nimg, C.byref(win), C.byref(surv)), "cc_mine_scan")      # warm-up (allocations)
     ctx.synchronize()
     ctx.timing_reset()
+    if dist is not None:
+        dist.barrier()
     t0 = time.time()
     reps = 3
     for _ in range(reps):
         _lib.check(lib.cc_mine_scan(h, 0, nimg, C.byref(win), C.byref(surv)), "cc_mine_scan")
     ctx.synchronize()
+    if dist is not None:
+        dist.barrier()          # every sweep ends with a collective, so all ranks finish together; the barrier makes it explicit
     dt = (time.time() - t0) / reps
     ms_dev, k = ctx.timing("mine")
     res = {"windows_per_s": win.value / dt, "windows": int(win.value), "survivors": int(surv.value), "images": nimg,
            "image_size": "1920x1080", "stages": len(cc.stageClassifiers), "weak_per_stage": [len(s.trees) for s in cc.stageClassifiers],
            "wall_ms_per_sweep": dt * 1e3, "device_ms_per_sweep": ms_dev / reps, "launches_per_sweep": k / reps,
-           "windows_per_s_device": win.value / (ms_dev / reps * 1e-3)}
+           "windows_per_s_device": win.value / (ms_dev / reps * 1e-3), "n_gpus": world,
+           "sharding": "background images round-robin across ranks, survivor bitmap summed over NCCL" if world > 1 else "single GPU"}
     ctx.close()
     return res
 

@@ -477,18 +477,25 @@ k_precalc_hog(const float* __restrict__ planes, const HogTaps* __restrict__ taps
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: per-feature segmented sort.  One CTA sorts one row of N (value, sample index) pairs held in
-// shared memory: stable LSD radix sort, 4 passes of 8 bits over the order-preserving float->uint
-// transform.  Stability is kept by giving every warp a contiguous segment and ranking inside a warp
-// with __match_any_sync; ties therefore come out in ascending sample index, which is the canonical
-// order the oracle's stable mode produces (std::sort + LessThanIdx in the reference leaves tie order
-// unspecified, o_utils.h:18-23, test_o_utils.cpp:111-128).
+// K3: per-feature segmented sort.  One CTA sorts one row of N (value, sample index) pairs in shared memory: stable
+// LSD radix sort over the order-preserving float->uint transform, 8 passes of 4 bits.
+//
+// What moves through the passes is one 32-bit word per element, (16 key bits << 16) | sample index: passes 0-3 sort
+// by the low half of the 32-bit key, then every element swaps its key half for the high half (one gather from the
+// row's key array, which stays put in shared memory) and passes 4-7 finish the sort -- stable passes keep the order
+// of the first four inside equal high halves.  A thread owns 15 consecutive positions and keeps them in registers
+// from the load to the scatter of a pass, so the pass is in place; its digit histogram and its running ranks are
+// 4-bit fields of two 32-bit registers, so the only shared-memory traffic of a pass is: 15 loads, 16 counter stores,
+// the block scan of the [digit][thread] counters, 15 base loads and 15 scattered stores per thread.  Stability: the
+// scan order is (digit, thread), a thread walks its positions in order.  Ties therefore come out in ascending
+// sample index, which is the canonical order the oracle's stable mode produces (std::sort + LessThanIdx in the
+// reference leaves tie order unspecified, o_utils.h:18-23, test_o_utils.cpp:111-128).
 // ------------------------------------------------------------------------------------------------
-constexpr int SORT_THREADS = 512;
+constexpr int SORT_THREADS = 1024;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_RADIX = 16;      // 4-bit digits, 8 passes
-constexpr int SORT_CNT_STRIDE = SORT_THREADS + SORT_THREADS / 16;   // one pad word per 16 counters
-__device__ __forceinline__ int cnt_index(int d, int t) { return d * SORT_CNT_STRIDE + t + (t >> 4); }
+constexpr int SORT_KPT = 15;                          // positions per thread: counts fit 4-bit fields, odd stride = conflict-free
+constexpr int SORT_CAP = SORT_THREADS * SORT_KPT;     // 15360 elements per row
+constexpr size_t SORT_SMEM = (size_t)SORT_CAP * 4 * 2 + (size_t)16 * SORT_THREADS * 2;
 
 __device__ __forceinline__ uint32_t float_to_key(float v) {
   uint32_t u = __float_as_uint(v + 0.0f);          // -0 -> +0
@@ -498,69 +505,99 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
   return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
 }
 
-// Every thread owns a contiguous segment of the row and a private set of 16 digit counters, laid out
-// [digit][thread] so that the flattened exclusive scan yields, for (digit d, thread t), the first output
-// slot of t's elements with digit d: elements keep their relative order (stable) without any cross-lane
-// ranking.  Warp w of the scan owns digit w, so a digit total is one warp reduction; a pass in which a
-// single digit holds all N keys is the identity and is skipped.
 __global__ void __launch_bounds__(SORT_THREADS, 1)
 k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint16_t* __restrict__ sidx, float* __restrict__ sval) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* keyA = reinterpret_cast<uint32_t*>(smem_raw);
-  uint32_t* keyB = keyA + N;
-  uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + N);
-  uint16_t* idxB = idxA + ((N + 1) & ~1);
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(idxB + ((N + 1) & ~1));       // [16][SORT_THREADS]
+  uint32_t* fullkey = reinterpret_cast<uint32_t*>(smem_raw);               // [SORT_CAP] by sample index
+  uint32_t* pk = fullkey + SORT_CAP;                                        // [SORT_CAP] packed (key half << 16) | index, by position
+  uint16_t* cnt = reinterpret_cast<uint16_t*>(pk + SORT_CAP);               // [16][SORT_THREADS]
   __shared__ uint32_t warp_tot[SORT_WARPS];
 
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int seg = ((N + SORT_THREADS - 1) / SORT_THREADS) | 1;               // odd length: conflict-free strided reads
-  const int s_begin = min(t * seg, N), s_end = min(s_begin + seg, N);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  uint32_t* mine = pk + t * SORT_KPT;
 
   for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
     const float* src = fval + (size_t)row * n_stride;
-    for (int i = t; i < N; i += SORT_THREADS) { keyA[i] = float_to_key(src[i]); idxA[i] = (uint16_t)i; }
-    uint32_t* kin = keyA; uint32_t* kout = keyB; uint16_t* iin = idxA; uint16_t* iout = idxB;
+    __syncthreads();                                   // the previous row's output gathers are done
+    for (int i = t; i < SORT_CAP; i += SORT_THREADS) {
+      const uint32_t k = i < N ? float_to_key(__ldcs(src + i)) : 0xFFFFFFFFu;     // padding sorts behind every real element
+      fullkey[i] = k;
+      pk[i] = (k << 16) | (uint32_t)i;
+    }
     __syncthreads();
+#pragma unroll 1
     for (int pass = 0; pass < 8; ++pass) {
-      const int shift = pass * 4;
+      const int shift = 16 + 4 * (pass & 3);
+      uint32_t e[SORT_KPT];
+      uint32_t hlo = 0, hhi = 0;                       // per-digit counts of this thread, 4-bit fields (digits 0-7 | 8-15)
 #pragma unroll
-      for (int d = 0; d < SORT_RADIX; ++d) cnt[cnt_index(d, t)] = 0;
-      for (int i = s_begin; i < s_end; ++i) cnt[cnt_index((kin[i] >> shift) & 15u, t)] += 1;
-      __syncthreads();
-      // flattened exclusive scan of cnt[16*512]: thread t scans entries [16t, 16t+16) (all of digit `warp`)
-      uint32_t loc[16];
-      uint32_t sum = 0;
+      for (int k = 0; k < SORT_KPT; ++k) {
+        uint32_t w = mine[k];
+        if (pass == 4) w = (fullkey[w & 0xFFFFu] & 0xFFFF0000u) | (w & 0xFFFFu);     // switch to the high key half
+        e[k] = w;
+        const uint32_t d = (w >> shift) & 15u;
+        const uint32_t one = 1u << ((d & 7u) * 4u);
+        if (d & 8u) hhi += one; else hlo += one;
+      }
 #pragma unroll
-      for (int k = 0; k < 16; ++k) { loc[k] = cnt[cnt_index(warp, lane * 16 + k)]; sum += loc[k]; }   // 17*lane + k: conflict-free
-      uint32_t incl = sum;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += x; }
-      const uint32_t digit_total = __shfl_sync(0xffffffffu, incl, 31);
-      if (lane == 31) warp_tot[warp] = incl;
-      if (__syncthreads_or(digit_total == (uint32_t)N)) continue;            // identity pass
-      uint32_t run = incl - sum;
-      for (int w = 0; w < warp; ++w) run += warp_tot[w];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) { const uint32_t c = loc[k]; cnt[cnt_index(warp, lane * 16 + k)] = run; run += c; }
-      __syncthreads();
-      for (int i = s_begin; i < s_end; ++i) {
-        const uint32_t k = kin[i];
-        uint32_t* slot = cnt + cnt_index((k >> shift) & 15u, t);
-        const uint32_t pos = *slot;
-        *slot = pos + 1;
-        kout[pos] = k;
-        iout[pos] = iin[i];
+      for (int d = 0; d < 8; ++d) {
+        cnt[d * SORT_THREADS + t] = (uint16_t)((hlo >> (4 * d)) & 15u);
+        cnt[(d + 8) * SORT_THREADS + t] = (uint16_t)((hhi >> (4 * d)) & 15u);
       }
       __syncthreads();
-      { uint32_t* tk = kin; kin = kout; kout = tk; uint16_t* ti = iin; iin = iout; iout = ti; }
+      // exclusive scan of the counters in (digit, thread) order: thread t owns flattened entries [16t, 16t+16)
+      {
+        uint4* c16 = reinterpret_cast<uint4*>(cnt + 16 * t);
+        uint4 a = c16[0], b = c16[1];
+        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sum += (w[k] & 0xFFFFu) + (w[k] >> 16);
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += x; }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        uint32_t wt = warp_tot[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wt, d); if (lane >= d) wt += x; }
+        const uint32_t wbase = __shfl_sync(0xffffffffu, wt, (warp + 31) & 31);
+        uint32_t run = (warp ? wbase : 0u) + incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
+          w[k] = run | ((run + lo) << 16);
+          run += lo + hi;
+        }
+        c16[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        c16[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      __syncthreads();
+      // scatter in place: every thread holds its elements in registers; ranks inside the thread from running 4-bit fields
+      uint32_t rlo = 0, rhi = 0;
+#pragma unroll
+      for (int k = 0; k < SORT_KPT; ++k) {
+        const uint32_t w = e[k];
+        const uint32_t d = (w >> shift) & 15u;
+        const uint32_t sh = (d & 7u) * 4u;
+        const bool up = (d & 8u) != 0;
+        const uint32_t rank = ((up ? rhi : rlo) >> sh) & 15u;
+        const uint32_t one = 1u << sh;
+        if (up) rhi += one; else rlo += one;
+        pk[(uint32_t)cnt[d * SORT_THREADS + t] + rank] = w;
+      }
+      __syncthreads();
     }
+    // output: sorted sample indices and the values in sorted order
     uint16_t* drow = sidx + (size_t)row * n_stride;
     float* vrow = sval + (size_t)row * n_stride;
-    for (int i = t; i < N; i += SORT_THREADS) { drow[i] = iin[i]; vrow[i] = key_to_float(kin[i]); }
+    for (int i = t; i < N; i += SORT_THREADS) {
+      const uint32_t id = pk[i] & 0xFFFFu;
+      drow[i] = (uint16_t)id;
+      __stcs(vrow + i, key_to_float(fullkey[id]));
+    }
     // row padding up to the split-search tile: index N (an always-zero operand), value +max
     for (int i = N + t; i < n_stride; i += SORT_THREADS) { drow[i] = (uint16_t)N; vrow[i] = 3.402823466e+38f; }
-    __syncthreads();
   }
 }
 
@@ -839,13 +876,11 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
   }
 
   if (ctx->ftype != CC_FEATURE_LBP) {   // categorical variables are not sorted (numPrecalcIdx = 0, :267-273)
-    const size_t smem = (size_t)N * 8 + (size_t)((N + 1) & ~1) * 4 + (size_t)SORT_RADIX * SORT_CNT_STRIDE * 4 + 16;
-    CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED,
-               "sort: numSamples %d needs %zu B of shared memory per row (limit 227 KB, about 16600 samples)", N, smem);
+    CC_REQUIRE(N <= SORT_CAP, CC_ERR_UNSUPPORTED, "sort: numSamples %d exceeds the %d samples one CTA sorts in shared memory", N, SORT_CAP);
     ScopedTimer tm(ctx, "sort", 1);
-    CC_CUDA(cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = std::min(ctx->nrows, ctx->sm_count * std::max(1, (int)((227 * 1024) / (smem + 1024))));
-    k_sort_rows<<<blocks, SORT_THREADS, smem, ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx, ctx->d_sval);
+    CC_CUDA(cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM));
+    const int blocks = std::min(ctx->nrows, ctx->sm_count);
+    k_sort_rows<<<blocks, SORT_THREADS, SORT_SMEM, ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx, ctx->d_sval);
     CC_CUDA(cudaGetLastError());
   }
   ctx->precalc_valid = true;
