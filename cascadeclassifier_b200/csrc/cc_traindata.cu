@@ -530,14 +530,17 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
       const int shift = 16 + 4 * (pass & 3);
       uint32_t e[SORT_KPT];
       uint32_t hlo = 0, hhi = 0;                       // per-digit counts of this thread, 4-bit fields (digits 0-7 | 8-15)
+      const uint32_t sh_field = (uint32_t)(shift - 2), top_bit = 1u << (shift + 3);
 #pragma unroll
       for (int k = 0; k < SORT_KPT; ++k) {
         uint32_t w = mine[k];
         if (pass == 4) w = (fullkey[w & 0xFFFFu] & 0xFFFF0000u) | (w & 0xFFFFu);     // switch to the high key half
         e[k] = w;
-        const uint32_t d = (w >> shift) & 15u;
-        const uint32_t one = 1u << ((d & 7u) * 4u);
-        if (d & 8u) hhi += one; else hlo += one;
+        // field offset = (digit & 7) * 4 straight from the word; digit bit 3 picks the register (predicated adds)
+        asm("{\n\t.reg .pred p;\n\t.reg .b32 s, o;\n\t"
+            "shr.b32 s, %2, %3;\n\tand.b32 s, s, 28;\n\tand.b32 o, %2, %4;\n\tsetp.ne.b32 p, o, 0;\n\tshl.b32 o, 1, s;\n\t"
+            "@p add.u32 %1, %1, o;\n\t@!p add.u32 %0, %0, o;\n\t}"
+            : "+r"(hlo), "+r"(hhi) : "r"(w), "r"(sh_field), "r"(top_bit));
       }
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
@@ -573,18 +576,19 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
         c16[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
       __syncthreads();
-      // scatter in place: every thread holds its elements in registers; ranks inside the thread from running 4-bit fields
-      uint32_t rlo = 0, rhi = 0;
+      // scatter in place: every thread holds its elements in registers; its column of the counter array now holds the
+      // first free slot per digit and is advanced as the thread walks its elements in order (only thread t touches it)
+      {
+        unsigned char* col = reinterpret_cast<unsigned char*>(cnt + t);
+        const uint32_t sh_row = (uint32_t)(shift - 11);            // digit * (SORT_THREADS * 2 bytes) = digit << 11
 #pragma unroll
-      for (int k = 0; k < SORT_KPT; ++k) {
-        const uint32_t w = e[k];
-        const uint32_t d = (w >> shift) & 15u;
-        const uint32_t sh = (d & 7u) * 4u;
-        const bool up = (d & 8u) != 0;
-        const uint32_t rank = ((up ? rhi : rlo) >> sh) & 15u;
-        const uint32_t one = 1u << sh;
-        if (up) rhi += one; else rlo += one;
-        pk[(uint32_t)cnt[d * SORT_THREADS + t] + rank] = w;
+        for (int k = 0; k < SORT_KPT; ++k) {
+          const uint32_t w = e[k];
+          uint16_t* slot = reinterpret_cast<uint16_t*>(col + ((w >> sh_row) & (15u << 11)));
+          const uint32_t pos = *slot;
+          *slot = (uint16_t)(pos + 1);
+          pk[pos] = w;
+        }
       }
       __syncthreads();
     }
