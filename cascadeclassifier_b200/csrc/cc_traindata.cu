@@ -495,7 +495,9 @@ constexpr int SORT_THREADS = 1024;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 constexpr int SORT_KPT = 15;                          // positions per thread: counts fit 4-bit fields, odd stride = conflict-free
 constexpr int SORT_CAP = SORT_THREADS * SORT_KPT;     // 15360 elements per row
-constexpr size_t SORT_SMEM = (size_t)SORT_CAP * 4 * 2 + (size_t)16 * SORT_THREADS * 2;
+constexpr int SORT_CNT_WORDS = 16 * SORT_THREADS + 16 * SORT_THREADS / 32;     // [digit][thread] u32, one pad word per 32: both access patterns conflict-free
+constexpr size_t SORT_SMEM = (size_t)SORT_CAP * 4 * 2 + (size_t)SORT_CNT_WORDS * 4;
+__device__ __forceinline__ int sort_cnt_slot(int idx) { return idx + (idx >> 5); }
 
 __device__ __forceinline__ uint32_t float_to_key(float v) {
   uint32_t u = __float_as_uint(v + 0.0f);          // -0 -> +0
@@ -510,7 +512,7 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint32_t* fullkey = reinterpret_cast<uint32_t*>(smem_raw);               // [SORT_CAP] by sample index
   uint32_t* pk = fullkey + SORT_CAP;                                        // [SORT_CAP] packed (key half << 16) | index, by position
-  uint16_t* cnt = reinterpret_cast<uint16_t*>(pk + SORT_CAP);               // [16][SORT_THREADS]
+  uint32_t* cnt = pk + SORT_CAP;                                            // [16][SORT_THREADS], padded (sort_cnt_slot)
   __shared__ uint32_t warp_tot[SORT_WARPS];
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -542,20 +544,20 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
             "@p add.u32 %1, %1, o;\n\t@!p add.u32 %0, %0, o;\n\t}"
             : "+r"(hlo), "+r"(hhi) : "r"(w), "r"(sh_field), "r"(top_bit));
       }
+      uint32_t* col = cnt + t + (t >> 5);              // entry (d, t) at col[d * (SORT_THREADS + 32)]
 #pragma unroll
       for (int d = 0; d < 8; ++d) {
-        cnt[d * SORT_THREADS + t] = (uint16_t)((hlo >> (4 * d)) & 15u);
-        cnt[(d + 8) * SORT_THREADS + t] = (uint16_t)((hhi >> (4 * d)) & 15u);
+        col[d * (SORT_THREADS + 32)] = (hlo >> (4 * d)) & 15u;
+        col[(d + 8) * (SORT_THREADS + 32)] = (hhi >> (4 * d)) & 15u;
       }
       __syncthreads();
       // exclusive scan of the counters in (digit, thread) order: thread t owns flattened entries [16t, 16t+16)
       {
-        uint4* c16 = reinterpret_cast<uint4*>(cnt + 16 * t);
-        uint4 a = c16[0], b = c16[1];
-        uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        uint32_t* c16 = cnt + sort_cnt_slot(16 * t);   // 16 consecutive entries never straddle a pad word (16t is a multiple of 16)
+        uint32_t w[16];
         uint32_t sum = 0;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sum += (w[k] & 0xFFFFu) + (w[k] >> 16);
+        for (int k = 0; k < 16; ++k) { w[k] = c16[k]; sum += w[k]; }
         uint32_t incl = sum;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += x; }
@@ -567,26 +569,19 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
         const uint32_t wbase = __shfl_sync(0xffffffffu, wt, (warp + 31) & 31);
         uint32_t run = (warp ? wbase : 0u) + incl - sum;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const uint32_t lo = w[k] & 0xFFFFu, hi = w[k] >> 16;
-          w[k] = run | ((run + lo) << 16);
-          run += lo + hi;
-        }
-        c16[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        c16[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        for (int k = 0; k < 16; ++k) { const uint32_t c = w[k]; c16[k] = run; run += c; }
       }
       __syncthreads();
       // scatter in place: every thread holds its elements in registers; its column of the counter array now holds the
       // first free slot per digit and is advanced as the thread walks its elements in order (only thread t touches it)
       {
-        unsigned char* col = reinterpret_cast<unsigned char*>(cnt + t);
-        const uint32_t sh_row = (uint32_t)(shift - 11);            // digit * (SORT_THREADS * 2 bytes) = digit << 11
+        const uint32_t sh_d = (uint32_t)shift;
 #pragma unroll
         for (int k = 0; k < SORT_KPT; ++k) {
           const uint32_t w = e[k];
-          uint16_t* slot = reinterpret_cast<uint16_t*>(col + ((w >> sh_row) & (15u << 11)));
+          uint32_t* slot = col + ((w >> sh_d) & 15u) * (SORT_THREADS + 32);
           const uint32_t pos = *slot;
-          *slot = (uint16_t)(pos + 1);
+          *slot = pos + 1;
           pk[pos] = w;
         }
       }
