@@ -700,18 +700,20 @@ __global__ void k_finalize_best(const SearchCtl* __restrict__ ctl, const RowBest
 // and the prefix scan over the ranked categories is done sequentially by lane 0 with un-fused f64
 // operations.
 // ------------------------------------------------------------------------------------------------
-constexpr int CAT_THREADS = 256;
-constexpr int CAT_WARPS = CAT_THREADS / 32;
+constexpr int CAT_THREADS_MAX = 1024;      // the launch picks as many warps as shared memory allows (per-warp state: 10.5 KB)
 
-__global__ void __launch_bounds__(CAT_THREADS, 1)
+__global__ void __launch_bounds__(CAT_THREADS_MAX, 1)
 k_split_search_cat(const uint8_t* __restrict__ codes, int n_stride, int N, int nrows, const double* __restrict__ wnode,
                    const float* __restrict__ ynode, int is_classifier, int crit, int has_y, RowBestCat* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int CAT_THREADS = blockDim.x, CAT_WARPS = blockDim.x >> 5;
   double* sw = reinterpret_cast<double*>(smem_raw);                   // [N]
-  float* sy = reinterpret_cast<float*>(sw + N);                        // [N] (LB only, else unused but allocated)
-  double* bins = reinterpret_cast<double*>(sy + ((N + 1) & ~1));       // [CAT_WARPS][3][256]: s0, s1, key
+  float* sy = reinterpret_cast<float*>(sw + N);                        // [N] (LogitBoost only)
+  double* bins = reinterpret_cast<double*>(sy + (has_y ? ((N + 1) & ~1) : 0));   // [CAT_WARPS][3][256]: s0, s1, key
   int* order_all = reinterpret_cast<int*>(bins + CAT_WARPS * 3 * 256); // [CAT_WARPS][256]
-  for (int i = threadIdx.x; i < N; i += CAT_THREADS) { sw[i] = wnode[i]; sy[i] = has_y ? ynode[i] : 0.f; }
+  double* steps_all = reinterpret_cast<double*>(order_all + CAT_WARPS * 256);   // [CAT_WARPS][6][32]
+  double* s_ikey_all = steps_all + CAT_WARPS * 6 * 32;                          // [CAT_WARPS][256] u64
+  for (int i = threadIdx.x; i < N; i += CAT_THREADS) { sw[i] = wnode[i]; if (has_y) sy[i] = ynode[i]; }
   __syncthreads();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   double* s0 = bins + warp * 3 * 256;     // regression: sum of y*w ; classification: class-0 weight
@@ -726,15 +728,28 @@ k_split_search_cat(const uint8_t* __restrict__ codes, int n_stride, int N, int n
     for (int base = 0; base < N; base += 32) {
       const int i = base + lane;
       const int mycode = i < N ? rc[i] : 0;
-      const int lim = min(32, N - base);
-      for (int j = 0; j < lim; ++j) {
-        const int code = __shfl_sync(0xffffffffu, mycode, j);
-        const double w = sw[base + j];
-        if (w != 0.0 && (code & 31) == lane) {
+      const double myw = i < N ? sw[i] : 0.0;
+      const float myy = (has_y && i < N) ? sy[i] : 0.f;
+      // route every node sample of this group of 32 to the lane that owns its bin ((code & 31) == lane): owner masks from
+      // 5 ballots; every owner then walks its samples in ascending sample order, so the additions inside a bin happen in
+      // the reference's sequential order while different bins proceed in parallel (about 3 rounds instead of 32)
+      unsigned mine = __ballot_sync(0xffffffffu, myw != 0.0);
+#pragma unroll
+      for (int bit = 0; bit < 5; ++bit) {
+        const unsigned b = __ballot_sync(0xffffffffu, (mycode >> bit) & 1);
+        mine &= ((lane >> bit) & 1) ? b : ~b;
+      }
+      while (__any_sync(0xffffffffu, mine != 0u)) {
+        const int src = mine ? __ffs(mine) - 1 : lane;
+        const int code = __shfl_sync(0xffffffffu, mycode, src);
+        const double w = __shfl_sync(0xffffffffu, myw, src);
+        const float y = has_y ? __shfl_sync(0xffffffffu, myy, src) : 0.f;
+        if (mine) {
+          mine &= mine - 1u;
           if (is_classifier) {
             if (w > 0.0) s1[code] = __dadd_rn(s1[code], w); else s0[code] = __dadd_rn(s0[code], -w);
           } else if (has_y) {
-            s0[code] = __dadd_rn(s0[code], __dmul_rn((double)sy[base + j], w));
+            s0[code] = __dadd_rn(s0[code], __dmul_rn((double)y, w));
             s1[code] = __dadd_rn(s1[code], w);
           } else {
             s0[code] = __dadd_rn(s0[code], w);            // w already carries the +-1 target
@@ -744,70 +759,101 @@ k_split_search_cat(const uint8_t* __restrict__ codes, int n_stride, int N, int n
       }
     }
     __syncwarp();
-    // sort key per category, totals (sequential over categories, as the reference)
+    // totals: sequential over the categories like the reference (o_cvboostree.cpp:459-467, every lane redundantly, same
+    // order); sort keys: one division per category, 8 categories per lane
     double R = 0, rsum = 0, rc0 = 0, rc1 = 0;
-    if (lane == 0) {
-      if (!is_classifier) {
-        for (int i = 0; i < 256; ++i) {
-          R = __dadd_rn(R, s1[i]);
-          rsum = __dadd_rn(rsum, s0[i]);
-          key[i] = fabs(s1[i]) > DBL_EPSILON ? __ddiv_rn(s0[i], s1[i]) : 0.0;
-        }
-      } else {
-        for (int i = 0; i < 256; ++i) { rc0 = __dadd_rn(rc0, s0[i]); rc1 = __dadd_rn(rc1, s1[i]); key[i] = s1[i]; }
-      }
+    if (!is_classifier) {
+      for (int i = 0; i < 256; ++i) { R = __dadd_rn(R, s1[i]); rsum = __dadd_rn(rsum, s0[i]); }
+      for (int i = lane; i < 256; i += 32) key[i] = fabs(s1[i]) > DBL_EPSILON ? __ddiv_rn(s0[i], s1[i]) : 0.0;
+    } else {
+      for (int i = 0; i < 256; ++i) { rc0 = __dadd_rn(rc0, s0[i]); rc1 = __dadd_rn(rc1, s1[i]); }
+      for (int i = lane; i < 256; i += 32) key[i] = s1[i];
     }
     __syncwarp();
-    // stable rank by counting
+    // stable rank by counting, on order-preserving 64-bit integer images of the keys (the FP64 pipe is narrow; 65536
+    // compares per variable belong on the integer pipe).  
+    unsigned long long* ikey = reinterpret_cast<unsigned long long*>(s_ikey_all) + warp * 256;
+    for (int i = lane; i < 256; i += 32) {
+      const unsigned long long u = (unsigned long long)__double_as_longlong(key[i] + 0.0);      // -0 -> +0
+      ikey[i] = u ^ ((u >> 63) ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+    }
+    __syncwarp();
     for (int j = lane; j < 256; j += 32) {
-      const double kj = key[j];
+      const unsigned long long kj = ikey[j];
       int rank = 0;
-      for (int k = 0; k < 256; ++k) { const double kk = key[k]; rank += (kk < kj) || (kk == kj && k < j); }
+#pragma unroll 8
+      for (int k = 0; k < 256; ++k) { const unsigned long long kk = ikey[k]; rank += (kk < kj) || (kk == kj && k < j); }
       order[rank] = j;
     }
     __syncwarp();
-    if (lane == 0) {
-      double best_val = -1.0;
-      int best_subset = -1;
-      if (!is_classifier) {
-        double L = 0, lsum = 0;
-        for (int si = 0; si < 255; ++si) {
-          const int idx = order[si];
-          const double ni = s1[idx];
-          if (ni > FLT_EPSILON) {
-            const double s = __dmul_rn(key[idx], ni);       // "revert back to unnormalized sums"
-            lsum = __dadd_rn(lsum, s); L = __dadd_rn(L, ni);
-            rsum = __dsub_rn(rsum, s); R = __dsub_rn(R, ni);
-            if (L > FLT_EPSILON && R > FLT_EPSILON) {
-              const double num = __dadd_rn(__dmul_rn(__dmul_rn(lsum, lsum), R), __dmul_rn(__dmul_rn(rsum, rsum), L));
-              const double val = __ddiv_rn(num, __dmul_rn(L, R));
-              if (best_val < val) { best_val = val; best_subset = si; }
+    // Prefix scan over the ranked categories.  The running sums are a sequential chain (lane 0, the reference's order of
+    // un-fused f64 operations, 32 positions at a time); the criterion at a position only reads them, so all lanes
+    // evaluate one position each and keep their first maximum -- same values and same winner as the sequential loop.
+    double* stp = steps_all + warp * 6 * 32;        // [6][32]: per-position running sums; stp[0][k] < 0 marks "no candidate here"
+    double best_val = -1.0;
+    int best_subset = -1;
+    double L = 0, lsum = 0, lcw0 = 0, lcw1 = 0;
+    if (is_classifier) R = __dadd_rn(rc0, rc1);
+    for (int blk = 0; blk < 255; blk += 32) {
+      if (lane == 0) {
+        const int lim = min(32, 255 - blk);
+        for (int k = 0; k < lim; ++k) {
+          const int idx = order[blk + k];
+          bool valid = false;
+          if (!is_classifier) {
+            const double ni = s1[idx];
+            if (ni > FLT_EPSILON) {
+              const double sv = __dmul_rn(key[idx], ni);       // "revert back to unnormalized sums"
+              lsum = __dadd_rn(lsum, sv); L = __dadd_rn(L, ni);
+              rsum = __dsub_rn(rsum, sv); R = __dsub_rn(R, ni);
+              valid = L > FLT_EPSILON && R > FLT_EPSILON;
             }
-          }
-        }
-      } else {
-        double lcw0 = 0, lcw1 = 0, L = 0;
-        R = __dadd_rn(rc0, rc1);
-        for (int si = 0; si < 255; ++si) {
-          const int idx = order[si];
-          const double w0 = s0[idx], w1 = s1[idx];
-          const double weight = __dadd_rn(w0, w1);
-          if (weight < FLT_EPSILON) continue;
-          lcw0 = __dadd_rn(lcw0, w0); rc0 = __dsub_rn(rc0, w0); lcw1 = __dadd_rn(lcw1, w1); rc1 = __dsub_rn(rc1, w1);
-          if (crit == CRIT_GINI) {
-            const double lsum2 = __dadd_rn(__dmul_rn(lcw0, lcw0), __dmul_rn(lcw1, lcw1));
-            const double rsum2 = __dadd_rn(__dmul_rn(rc0, rc0), __dmul_rn(rc1, rc1));
-            L = __dadd_rn(L, weight); R = __dsub_rn(R, weight);
-            if (L > FLT_EPSILON && R > FLT_EPSILON) {
-              const double val = __ddiv_rn(__dadd_rn(__dmul_rn(lsum2, R), __dmul_rn(rsum2, L)), __dmul_rn(L, R));
-              if (best_val < val) { best_val = val; best_subset = si; }
-            }
+            stp[0 * 32 + k] = valid ? L : -1.0; stp[1 * 32 + k] = R; stp[2 * 32 + k] = lsum; stp[3 * 32 + k] = rsum;
           } else {
-            const double val = fmax(__dadd_rn(lcw0, rc1), __dadd_rn(lcw1, rc0));
-            if (best_val < val) { best_val = val; best_subset = si; }
+            const double w0 = s0[idx], w1 = s1[idx];
+            const double weight = __dadd_rn(w0, w1);
+            if (!(weight < FLT_EPSILON)) {
+              lcw0 = __dadd_rn(lcw0, w0); rc0 = __dsub_rn(rc0, w0); lcw1 = __dadd_rn(lcw1, w1); rc1 = __dsub_rn(rc1, w1);
+              if (crit == CRIT_GINI) {
+                L = __dadd_rn(L, weight); R = __dsub_rn(R, weight);
+                valid = L > FLT_EPSILON && R > FLT_EPSILON;
+              } else valid = true;
+            }
+            stp[0 * 32 + k] = valid ? (crit == CRIT_GINI ? L : 1.0) : -1.0; stp[1 * 32 + k] = R;
+            stp[2 * 32 + k] = lcw0; stp[3 * 32 + k] = lcw1; stp[4 * 32 + k] = rc0; stp[5 * 32 + k] = rc1;
           }
         }
+        for (int k = lim; k < 32; ++k) stp[k] = -1.0;
       }
+      __syncwarp();
+      const double a0 = stp[lane];
+      if (a0 > 0.0) {
+        double val;
+        if (!is_classifier) {
+          const double Rr = stp[32 + lane], ls = stp[64 + lane], rs = stp[96 + lane];
+          const double num = __dadd_rn(__dmul_rn(__dmul_rn(ls, ls), Rr), __dmul_rn(__dmul_rn(rs, rs), a0));
+          val = __ddiv_rn(num, __dmul_rn(a0, Rr));
+        } else {
+          const double l0 = stp[64 + lane], l1 = stp[96 + lane], r0 = stp[128 + lane], r1 = stp[160 + lane];
+          if (crit == CRIT_GINI) {
+            const double Rr = stp[32 + lane];
+            const double lsum2 = __dadd_rn(__dmul_rn(l0, l0), __dmul_rn(l1, l1));
+            const double rsum2 = __dadd_rn(__dmul_rn(r0, r0), __dmul_rn(r1, r1));
+            val = __ddiv_rn(__dadd_rn(__dmul_rn(lsum2, Rr), __dmul_rn(rsum2, a0)), __dmul_rn(a0, Rr));
+          } else val = fmax(__dadd_rn(l0, r1), __dadd_rn(l1, r0));
+        }
+        if (best_val < val) { best_val = val; best_subset = blk + lane; }     // positions ascend per lane: first maximum
+      }
+      __syncwarp();
+    }
+    // warp argmax: larger value, then smaller position (the sequential loop keeps the first maximum)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best_val, d);
+      const int os = __shfl_xor_sync(0xffffffffu, best_subset, d);
+      if (os >= 0 && (best_subset < 0 || ov > best_val || (ov == best_val && os < best_subset))) { best_val = ov; best_subset = os; }
+    }
+    if (lane == 0) {
       RowBestCat rb;
       rb.q = best_subset >= 0 ? (float)best_val : -1.f;
       for (int k = 0; k < 8; ++k) rb.subset[k] = 0;
@@ -1111,10 +1157,15 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
   const int N = ctx->N;
   ScopedTimer tm(ctx, "split_search", 2);
   if (ctx->ftype == CC_FEATURE_LBP) {
-    const size_t smem = (size_t)N * 8 + (size_t)((N + 1) & ~1) * 4 + (size_t)CAT_WARPS * 3 * 256 * 8 + CAT_WARPS * 256 * 4;
-    CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED, "split search: numSamples %d needs %zu B of shared memory (limit 227 KB)", N, smem);
+    const bool cat_has_y = b->boost_type == CC_BOOST_LOGIT;
+    const size_t smem_fixed = (size_t)N * 8 + (cat_has_y ? (size_t)((N + 1) & ~1) * 4 : 0);
+    const size_t smem_warp = (size_t)3 * 256 * 8 + 256 * 4 + (size_t)6 * 32 * 8 + (size_t)256 * 8;
+    CC_REQUIRE(smem_fixed + 2 * smem_warp <= 227 * 1024, CC_ERR_UNSUPPORTED, "split search: numSamples %d needs %zu B of shared memory (limit 227 KB)", N, smem_fixed + 2 * smem_warp);
+    const int CAT_WARPS = (int)std::min<size_t>(CAT_THREADS_MAX / 32, (227 * 1024 - smem_fixed) / smem_warp);
+    const int CAT_THREADS = CAT_WARPS * 32;
+    const size_t smem = smem_fixed + CAT_WARPS * smem_warp;
     CC_CUDA(cudaFuncSetAttribute(k_split_search_cat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int blocks = std::min((ctx->nrows + CAT_WARPS - 1) / CAT_WARPS, ctx->sm_count * std::max(1, (int)((220 * 1024) / smem)));
+    const int blocks = std::min((ctx->nrows + CAT_WARPS - 1) / CAT_WARPS, ctx->sm_count);
     k_split_search_cat<<<blocks, CAT_THREADS, smem, ctx->stream>>>(ctx->d_fcode, ctx->n_stride, N, ctx->nrows, b->wnode, b->ynode,
                                                                    b->is_classifier, b->crit, b->boost_type == CC_BOOST_LOGIT, b->rowbest_cat);
     CC_CUDA(cudaGetLastError());

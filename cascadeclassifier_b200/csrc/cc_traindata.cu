@@ -493,10 +493,10 @@ k_precalc_hog(const float* __restrict__ planes, const HogTaps* __restrict__ taps
 // ------------------------------------------------------------------------------------------------
 constexpr int SORT_THREADS = 1024;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_KPT = 15;                          // positions per thread: counts fit 4-bit fields, odd stride = conflict-free
-constexpr int SORT_CAP = SORT_THREADS * SORT_KPT;     // 15360 elements per row
+constexpr int SORT_KPT_MAX = 15;                      // positions per thread: counts fit 4-bit fields, odd stride = conflict-free
+constexpr int SORT_CAP = SORT_THREADS * SORT_KPT_MAX; // 15360 elements per row (smaller rows use 3 / 7 / 11 positions per thread)
 constexpr int SORT_CNT_WORDS = 16 * SORT_THREADS + 16 * SORT_THREADS / 32;     // [digit][thread] u32, one pad word per 32: both access patterns conflict-free
-constexpr size_t SORT_SMEM = (size_t)SORT_CAP * 4 * 2 + (size_t)SORT_CNT_WORDS * 4;
+static size_t sort_smem(int kpt) { return (size_t)SORT_THREADS * kpt * 4 * 2 + (size_t)SORT_CNT_WORDS * 4; }
 __device__ __forceinline__ int sort_cnt_slot(int idx) { return idx + (idx >> 5); }
 
 __device__ __forceinline__ uint32_t float_to_key(float v) {
@@ -507,12 +507,14 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
   return __uint_as_float(k ^ ((k >> 31) ? 0x80000000u : 0xFFFFFFFFu));
 }
 
+template <int SORT_KPT>
 __global__ void __launch_bounds__(SORT_THREADS, 1)
 k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint16_t* __restrict__ sidx, float* __restrict__ sval) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint32_t* fullkey = reinterpret_cast<uint32_t*>(smem_raw);               // [SORT_CAP] by sample index
-  uint32_t* pk = fullkey + SORT_CAP;                                        // [SORT_CAP] packed (key half << 16) | index, by position
-  uint32_t* cnt = pk + SORT_CAP;                                            // [16][SORT_THREADS], padded (sort_cnt_slot)
+  constexpr int CAP = SORT_THREADS * SORT_KPT;
+  uint32_t* fullkey = reinterpret_cast<uint32_t*>(smem_raw);               // [CAP] by sample index
+  uint32_t* pk = fullkey + CAP;                                             // [CAP] packed (key half << 16) | index, by position
+  uint32_t* cnt = pk + CAP;                                            // [16][SORT_THREADS], padded (sort_cnt_slot)
   __shared__ uint32_t warp_tot[SORT_WARPS];
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -521,7 +523,7 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
   for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
     const float* src = fval + (size_t)row * n_stride;
     __syncthreads();                                   // the previous row's output gathers are done
-    for (int i = t; i < SORT_CAP; i += SORT_THREADS) {
+    for (int i = t; i < CAP; i += SORT_THREADS) {
       const uint32_t k = i < N ? float_to_key(__ldcs(src + i)) : 0xFFFFFFFFu;     // padding sorts behind every real element
       fullkey[i] = k;
       pk[i] = (k << 16) | (uint32_t)i;
@@ -877,9 +879,17 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
   if (ctx->ftype != CC_FEATURE_LBP) {   // categorical variables are not sorted (numPrecalcIdx = 0, :267-273)
     CC_REQUIRE(N <= SORT_CAP, CC_ERR_UNSUPPORTED, "sort: numSamples %d exceeds the %d samples one CTA sorts in shared memory", N, SORT_CAP);
     ScopedTimer tm(ctx, "sort", 1);
-    CC_CUDA(cudaFuncSetAttribute(k_sort_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SORT_SMEM));
     const int blocks = std::min(ctx->nrows, ctx->sm_count);
-    k_sort_rows<<<blocks, SORT_THREADS, SORT_SMEM, ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx, ctx->d_sval);
+#define LAUNCH_SORT(KPT)                                                                                                     \
+  {                                                                                                                          \
+    CC_CUDA(cudaFuncSetAttribute(k_sort_rows<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(KPT)));       \
+    k_sort_rows<KPT><<<blocks, SORT_THREADS, sort_smem(KPT), ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx, ctx->d_sval); \
+  }
+    if (N <= SORT_THREADS * 3) LAUNCH_SORT(3)
+    else if (N <= SORT_THREADS * 7) LAUNCH_SORT(7)
+    else if (N <= SORT_THREADS * 11) LAUNCH_SORT(11)
+    else LAUNCH_SORT(15)
+#undef LAUNCH_SORT
     CC_CUDA(cudaGetLastError());
   }
   ctx->precalc_valid = true;
