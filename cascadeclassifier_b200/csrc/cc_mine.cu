@@ -84,6 +84,10 @@ struct LevelDesc {
   long long ip_off;
   int rows_base, cols_base, diag_base;
   int owned;               // image-sharded mining: this rank builds and evaluates the level (1) or skips it (0)
+  int row0;                // fast path: this entry is a horizontal strip of its level starting at level row row0 (0: whole level)
+  int pitch;               // row pitch of the integral planes (>= lw + 1; the fast path pads it to a multiple of 4)
+  int ppitch;              // row pitch of the level pixels in the pool (>= lw)
+  int pad1;
 };
 
 // cv::resize(src, dst, INTER_LINEAR_EXACT), 8-bit single channel: 8.8 fixed-point coefficients per axis,
@@ -104,10 +108,11 @@ __global__ void k_resize_levels(const LevelDesc* __restrict__ levels, int nlevel
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].px_off <= p) lo = mid; else hi = mid - 1; }
     const LevelDesc& L = levels[lo];
     const int q = (int)(p - L.px_off);
-    const int y = q / L.lw, x = q - y * L.lw;
+    const int y = q / L.ppitch, x = q - y * L.ppitch;
+    if (x >= L.lw) continue;                       // row padding of the pool
     int ox, cx0, cx1, mx, oy, cy0, cy1, my;
     lin_coef(L.scale_x, x, L.sw, ox, cx0, cx1, mx);
-    lin_coef(L.scale_y, y, L.sh, oy, cy0, cy1, my);
+    lin_coef(L.scale_y, L.row0 + y, L.sh, oy, cy0, cy1, my);
     auto hrow = [&](int row) -> uint32_t {
       const uint8_t* s = L.src + (size_t)row * L.sw;
       if (mx == 1) return (uint32_t)s[0] * 256u;
@@ -136,7 +141,7 @@ __global__ void k_gather_windows(const LevelDesc* __restrict__ levels, int nleve
     const long long k = b - L.w_base + L.w_skip;
     const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
     const int wy = r / W, wx = r - wy * W;
-    dst[t] = pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.lw + (L.x0 + ix * L.step_x + wx)];
+    dst[t] = pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.ppitch + (L.x0 + ix * L.step_x + wx)];
   }
 }
 
@@ -223,116 +228,136 @@ __device__ __forceinline__ int level_of_line(const LevelDesc* __restrict__ level
 // owns pixel columns 2t, 2t+1 and plane columns 2t, 2t+1; one __syncthreads per row (all per-row shared
 // buffers are double-buffered).  Levels wider or taller than 2047 take the multi-kernel path below.
 // ------------------------------------------------------------------------------------------------
-constexpr int LB_THREADS = 1024;
-constexpr int LB_MAXDIM = 2 * LB_THREADS - 1;      // lw + 1 <= 2048 plane columns, lh <= 2047 rows of y coefficients
+constexpr int LB_MAX_THREADS = 512;
+constexpr int LB_PPT = 4;                               // pixels / plane columns per thread
+constexpr int LB_MAXDIM = LB_PPT * LB_MAX_THREADS - 1;  // lw + 1 <= 2048 plane columns, lh <= 2047 rows of y coefficients
 
-__global__ void __launch_bounds__(LB_THREADS, 1)
+// THREADS = 128 / 256 / 512 for levels up to 511 / 1023 / 2047 pixels wide: narrow levels get small CTAs, several per SM.
+// Thread t owns pixels x = 4t .. 4t+3 and plane columns j = 4t .. 4t+3 (plane column j <-> apex pixel x = j - 1); plane and
+// pool rows are padded to multiples of 4, so every row leaves as one 128-bit store per plane and one 32-bit pixel store.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
 k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order, uint8_t* __restrict__ pool, uint32_t* __restrict__ sum,
             uint32_t* __restrict__ sq, uint32_t* __restrict__ tilted) {
-  __shared__ uint8_t s_pix[2][2 * LB_THREADS + 8];         // pixel row, index j = x + 1 (j = 0: virtual column x = -1)
-  __shared__ uint32_t s_d1[2][2 * LB_THREADS + 2], s_d2[2][2 * LB_THREADS + 2];
-  __shared__ int s_yo[LB_MAXDIM + 1];                       // source row | c1 << 16
+  constexpr int NW = THREADS / 32;
+  __shared__ uint32_t s_bpix[2][THREADS];       // a thread's last pixel of the row (the left neighbour's apex pixel)
+  __shared__ uint32_t s_bd1[2][THREADS];        // D1 of the previous row at the thread's last plane column
+  __shared__ uint32_t s_bd2[2][THREADS + 1];    // D2 of the previous row at the thread's first plane column
+  __shared__ int s_yo[LB_MAXDIM + 1];           // source row | c1 << 16
   __shared__ uint32_t s_wt[2][2][32];
-  const LevelDesc L = levels[order[blockIdx.x]];      // tallest levels first: a level is one serial chain of rows
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int lw = L.lw, lh = L.lh, sw = L.sw, sh = L.sh, pitch = lw + 1;
+  const LevelDesc L = levels[order[blockIdx.x]];      // tallest strips first: a strip is one serial chain of rows
+  const int t = threadIdx.x, lane = t & 31;
+  const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
+  const int lw = L.lw, lh = L.lh, sw = L.sw, sh = L.sh, pitch = L.pitch;
   const uint8_t* __restrict__ src = L.src;
-  // per-column x coefficients (registers), per-row y coefficients (shared)
-  int xo[2], xc1[2];
+  const int x0 = LB_PPT * t;
+  // per-column x coefficients (registers: source column | c1 << 16), per-row y coefficients (shared)
+  int xc[LB_PPT];
 #pragma unroll
-  for (int k = 0; k < 2; ++k) {
+  for (int k = 0; k < LB_PPT; ++k) {
     int o = 0, c0 = 256, c1 = 0, md = 0;
-    const int x = 2 * t + k;
-    if (x < lw) lin_coef(L.scale_x, x, sw, o, c0, c1, md);
-    xo[k] = o; xc1[k] = c1;
+    if (x0 + k < lw) lin_coef(L.scale_x, x0 + k, sw, o, c0, c1, md);
+    xc[k] = o | (c1 << 16);
   }
-  for (int y = t; y < lh; y += LB_THREADS) {
+  for (int y = t; y < lh; y += THREADS) {
     int o, c0, c1, md;
-    lin_coef(L.scale_y, y, sh, o, c0, c1, md);
+    lin_coef(L.scale_y, L.row0 + y, sh, o, c0, c1, md);
     s_yo[y] = o | (c1 << 16);
   }
-  for (int j = t; j < 2 * LB_THREADS + 2; j += LB_THREADS) { s_pix[0][j] = s_pix[1][j] = 0; s_d1[0][j] = s_d1[1][j] = 0; s_d2[0][j] = s_d2[1][j] = 0; }
+  s_bpix[0][t] = s_bpix[1][t] = 0; s_bd1[0][t] = s_bd1[1][t] = 0; s_bd2[0][t] = s_bd2[1][t] = 0;
+  if (t == 0) { s_bd2[0][THREADS] = 0; s_bd2[1][THREADS] = 0; }
+  if (t < 32) { s_wt[0][0][t] = s_wt[0][1][t] = s_wt[1][0][t] = s_wt[1][1][t] = 0; }
   uint32_t* S = sum + L.ip_off;
   uint32_t* Q = sq ? sq + L.ip_off : nullptr;
   uint32_t* T = tilted ? tilted + L.ip_off : nullptr;
-  for (int j = t; j < pitch; j += LB_THREADS) { S[j] = 0; if (Q) Q[j] = 0; if (T) T[j] = 0; }
+  for (int j = t; j < pitch; j += THREADS) { S[j] = 0; if (Q) Q[j] = 0; if (T) T[j] = 0; }
   __syncthreads();
-  uint8_t* dst = pool + L.px_off;
-  uint32_t colS[2] = {0, 0}, colQ[2] = {0, 0}, Tprev[2] = {0, 0};
-  const int x0 = 2 * t, x1 = 2 * t + 1;
-  const int xa0 = xo[0], xb0 = min(xo[0] + 1, sw - 1), xa1 = xo[1], xb1 = min(xo[1] + 1, sw - 1);
+  const bool on = x0 <= lw;                          // this thread owns at least one plane column
+  const bool warp_on = warp * 32 * LB_PPT <= lw;     // warp-uniform
+  uint32_t colS[LB_PPT] = {0, 0, 0, 0}, colQ[LB_PPT] = {0, 0, 0, 0}, Tp[LB_PPT] = {0, 0, 0, 0};
+  uint32_t d1[LB_PPT] = {0, 0, 0, 0}, d2[LB_PPT] = {0, 0, 0, 0};
+  int xa[LB_PPT], xb[LB_PPT];
+  bool in[LB_PPT];
+#pragma unroll
+  for (int k = 0; k < LB_PPT; ++k) { in[k] = x0 + k < lw; xa[k] = xc[k] & 0xFFFF; xb[k] = min(xa[k] + 1, sw - 1); }
   // source bytes of row y are fetched one row ahead
-  auto fetch = [&](int y, uint32_t (&p)[8]) {
+  uint32_t nb[4 * LB_PPT];
+#pragma unroll
+  for (int k = 0; k < 4 * LB_PPT; ++k) nb[k] = 0;
+  auto fetch = [&](int y) {
     const int yo = s_yo[y];
     const int r0 = yo & 0xFFFF, r1 = min(r0 + 1, sh - 1);
     const uint8_t* a = src + (size_t)r0 * sw;
     const uint8_t* b = src + (size_t)r1 * sw;
-    if (x0 < lw) { p[0] = a[xa0]; p[1] = a[xb0]; p[2] = b[xa0]; p[3] = b[xb0]; }
-    if (x1 < lw) { p[4] = a[xa1]; p[5] = a[xb1]; p[6] = b[xa1]; p[7] = b[xb1]; }
+#pragma unroll
+    for (int k = 0; k < LB_PPT; ++k)
+      if (in[k]) { nb[4 * k] = a[xa[k]]; nb[4 * k + 1] = a[xb[k]]; nb[4 * k + 2] = b[xa[k]]; nb[4 * k + 3] = b[xb[k]]; }
   };
-  uint32_t nxt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (lh > 0) fetch(0, nxt);
+  if (lh > 0 && warp_on) fetch(0);
+  uint32_t* Srow = S + x0;
+  uint32_t* Qrow = Q ? Q + x0 : nullptr;
+  uint32_t* Trow = T ? T + x0 : nullptr;
+  uint8_t* drow = pool + L.px_off + x0;
   for (int y = 0; y < lh; ++y) {
     const int buf = y & 1;
-    uint32_t cur[8];
+    uint32_t v[LB_PPT] = {0, 0, 0, 0};
+    uint32_t i1 = 0, i2 = 0, tot1 = 0, tot2 = 0;
+    Srow += pitch; if (Q) Qrow += pitch; if (T) Trow += pitch;
+    if (warp_on) {
+      const uint32_t cy1 = (uint32_t)(s_yo[y] >> 16), cy0 = 256u - cy1;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) cur[k] = nxt[k];
-    const uint32_t cy1 = (uint32_t)(s_yo[y] >> 16), cy0 = 256u - cy1;
-    if (y + 1 < lh) fetch(y + 1, nxt);
-    uint32_t v[2] = {0, 0};
+      for (int k = 0; k < LB_PPT; ++k) {
+        const uint32_t c1 = (uint32_t)xc[k] >> 16, c0 = 256u - c1;
+        const uint32_t val = ((nb[4 * k] * c0 + nb[4 * k + 1] * c1) * cy0 + (nb[4 * k + 2] * c0 + nb[4 * k + 3] * c1) * cy1 + 32768u) >> 16;
+        v[k] = in[k] ? val : 0u;
+      }
+      if (y + 1 < lh) fetch(y + 1);
+      if (in[0]) *reinterpret_cast<uint32_t*>(drow) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);    // pool rows are padded to 4
+      s_bpix[buf][t] = v[3];
+      // block-wide exclusive scan of the per-thread row totals (pixels and squares)
+      tot1 = (v[0] + v[1]) + (v[2] + v[3]);
+      tot2 = (v[0] * v[0] + v[1] * v[1]) + (v[2] * v[2] + v[3] * v[3]);
+      i1 = tot1; i2 = tot2;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const uint32_t c1 = (uint32_t)xc1[k], c0 = 256u - c1;
-      const uint32_t h0 = cur[4 * k] * c0 + cur[4 * k + 1] * c1, h1 = cur[4 * k + 2] * c0 + cur[4 * k + 3] * c1;
-      v[k] = (h0 * cy0 + h1 * cy1 + 32768u) >> 16;
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, i1, d), b = __shfl_up_sync(0xffffffffu, i2, d);
+        if (lane >= d) { i1 += a; i2 += b; }
+      }
+      if (lane == 31) { s_wt[buf][0][warp] = i1; s_wt[buf][1][warp] = i2; }
     }
-    if (x0 < lw) { dst[(size_t)y * lw + x0] = (uint8_t)v[0]; s_pix[buf][x0 + 1] = (uint8_t)v[0]; }
-    if (x1 < lw) { dst[(size_t)y * lw + x1] = (uint8_t)v[1]; s_pix[buf][x1 + 1] = (uint8_t)v[1]; } else v[1] = 0;
-    if (x0 >= lw) v[0] = 0;
-    // block-wide exclusive scan of the per-thread row totals (pixels and squares)
-    const uint32_t tot1 = v[0] + v[1], tot2 = v[0] * v[0] + v[1] * v[1];
-    uint32_t i1 = tot1, i2 = tot2;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t a = __shfl_up_sync(0xffffffffu, i1, d), b = __shfl_up_sync(0xffffffffu, i2, d);
-      if (lane >= d) { i1 += a; i2 += b; }
-    }
-    if (lane == 31) { s_wt[buf][0][warp] = i1; s_wt[buf][1][warp] = i2; }
+    drow += L.ppitch;
     __syncthreads();
-    uint32_t w1 = s_wt[buf][0][lane], w2 = s_wt[buf][1][lane];
+    if (!warp_on) continue;
+    uint32_t w1 = (lane < NW && lane < warp) ? s_wt[buf][0][lane] : 0u, w2 = (lane < NW && lane < warp) ? s_wt[buf][1][lane] : 0u;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t a = __shfl_up_sync(0xffffffffu, w1, d), b = __shfl_up_sync(0xffffffffu, w2, d);
-      if (lane >= d) { w1 += a; w2 += b; }
+    for (int d = 16; d > 0; d >>= 1) { w1 += __shfl_xor_sync(0xffffffffu, w1, d); w2 += __shfl_xor_sync(0xffffffffu, w2, d); }
+    if (!on) continue;
+    // exclusive row prefixes at the thread's plane columns, accumulated down the columns
+    {
+      uint32_t e = w1 + i1 - tot1;
+#pragma unroll
+      for (int k = 0; k < LB_PPT; ++k) { colS[k] += e; e += v[k]; }
+      *reinterpret_cast<uint4*>(Srow) = make_uint4(colS[0], colS[1], colS[2], colS[3]);
     }
-    const uint32_t b1 = __shfl_sync(0xffffffffu, w1, (warp + 31) & 31), b2 = __shfl_sync(0xffffffffu, w2, (warp + 31) & 31);
-    const uint32_t e1 = (warp ? b1 : 0u) + i1 - tot1, e2 = (warp ? b2 : 0u) + i2 - tot2;    // row sums left of this thread's columns
-    uint32_t* Srow = S + (size_t)(y + 1) * pitch;
-    if (t == 0) Srow[0] = 0;
-    if (x0 < lw) { colS[0] += e1 + v[0]; Srow[x0 + 1] = colS[0]; }
-    if (x1 < lw) { colS[1] += e1 + v[0] + v[1]; Srow[x1 + 1] = colS[1]; }
     if (Q) {
-      uint32_t* Qrow = Q + (size_t)(y + 1) * pitch;
-      if (t == 0) Qrow[0] = 0;
-      if (x0 < lw) { colQ[0] += e2 + v[0] * v[0]; Qrow[x0 + 1] = colQ[0]; }
-      if (x1 < lw) { colQ[1] += e2 + tot2; Qrow[x1 + 1] = colQ[1]; }
+      uint32_t e = w2 + i2 - tot2;
+#pragma unroll
+      for (int k = 0; k < LB_PPT; ++k) { colQ[k] += e; e += v[k] * v[k]; }
+      *reinterpret_cast<uint4*>(Qrow) = make_uint4(colQ[0], colQ[1], colQ[2], colQ[3]);
     }
     if (T) {
-      uint32_t* Trow = T + (size_t)(y + 1) * pitch;
+      // apex pixels of the plane columns 4t..4t+3 are x = 4t-1 .. 4t+2; D1(y,x) = I + D1(y-1,x-1), D2(y,x) = I + D2(y-1,x+1)
+      const uint32_t ivl = t ? s_bpix[buf][t - 1] : 0u;
+      const uint32_t d1l = t ? s_bd1[buf ^ 1][t - 1] : 0u;          // D1 of the previous row at column 4t-1
+      const uint32_t d2r = s_bd2[buf ^ 1][t + 1];                   // D2 of the previous row at column 4t+4
+      const uint32_t iv[LB_PPT] = {ivl, v[0], v[1], v[2]};
+      const uint32_t n1[LB_PPT] = {iv[0] + d1l, iv[1] + d1[0], iv[2] + d1[1], iv[3] + d1[2]};
+      const uint32_t n2[LB_PPT] = {iv[0] + d2[1], iv[1] + d2[2], iv[2] + d2[3], iv[3] + d2r};
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int j = 2 * t + k;              // plane column X = j, pixel x = j - 1
-        if (j <= lw) {
-          const int x = j - 1;
-          const uint32_t iv = s_pix[buf][j];
-          const uint32_t a = (x >= 1) ? s_d1[buf ^ 1][j - 1] : 0u;           // D1(y-1, x-1)
-          const uint32_t b = (x + 1 <= lw - 1) ? s_d2[buf ^ 1][j + 1] : 0u;   // D2(y-1, x+1)
-          const uint32_t nd1 = a + iv, nd2 = b + iv;
-          s_d1[buf][j] = nd1; s_d2[buf][j] = nd2;
-          Tprev[k] += nd1 + nd2 - iv;
-          Trow[j] = Tprev[k];
-        }
-      }
+      for (int k = 0; k < LB_PPT; ++k) { d1[k] = n1[k]; d2[k] = n2[k]; Tp[k] += n1[k] + n2[k] - iv[k]; }
+      s_bd1[buf][t] = d1[3];
+      s_bd2[buf][t] = d2[0];
+      *reinterpret_cast<uint4*>(Trow) = make_uint4(Tp[0], Tp[1], Tp[2], Tp[3]);
     }
   }
 }
@@ -345,8 +370,8 @@ k_lvl_rows(const LevelDesc* __restrict__ levels, int nlevels, int total_rows, co
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   for (int gr = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; gr < total_rows; gr += nwarps) {
     const LevelDesc& L = levels[level_of_line(levels, nlevels, gr, 0)];
-    const int y = gr - L.rows_base, pitch = L.lw + 1;
-    const uint8_t* src = pool + L.px_off + (size_t)y * L.lw;
+    const int y = gr - L.rows_base, pitch = L.pitch;
+    const uint8_t* src = pool + L.px_off + (size_t)y * L.ppitch;
     uint32_t* S = sum + L.ip_off + (size_t)(y + 1) * pitch;
     uint32_t* Q = sq ? sq + L.ip_off + (size_t)(y + 1) * pitch : nullptr;
     if (y == 0) for (int x = lane; x < pitch; x += 32) { S[x - pitch] = 0; if (Q) Q[x - pitch] = 0; }
@@ -376,7 +401,7 @@ k_lvl_diag(const LevelDesc* __restrict__ levels, int nlevels, int total_diag, co
            uint32_t* __restrict__ tilted, int pass) {
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_diag; g += gridDim.x * blockDim.x) {
     const LevelDesc& L = levels[level_of_line(levels, nlevels, g, 2)];
-    const int k = g - L.diag_base, lw = L.lw, lh = L.lh, pitch = lw + 1;
+    const int k = g - L.diag_base, lw = L.lw, lh = L.lh, pitch = L.pitch, pp = L.ppitch;
     const uint8_t* img = pool + L.px_off;
     uint32_t* T = tilted + L.ip_off;
     // diagonals start on the top row (k < lw: column k) or on a side column (k >= lw: row k - lw + 1)
@@ -384,11 +409,11 @@ k_lvl_diag(const LevelDesc* __restrict__ levels, int nlevels, int total_diag, co
     uint32_t run = 0;
     if (pass == 0) {
       int x = k < lw ? k : 0;
-      for (; y < lh && x < lw; ++y, ++x) { run += img[(size_t)y * lw + x]; T[(size_t)(y + 1) * pitch + x + 1] = run; }
+      for (; y < lh && x < lw; ++y, ++x) { run += img[(size_t)y * pp + x]; T[(size_t)(y + 1) * pitch + x + 1] = run; }
     } else {
       int x = k < lw ? k : lw - 1;
       for (; y < lh && x >= 0; ++y, --x) {
-        const uint32_t v = img[(size_t)y * lw + x];
+        const uint32_t v = img[(size_t)y * pp + x];
         run += v;
         T[(size_t)(y + 1) * pitch + x + 1] += run - v;
       }
@@ -406,7 +431,7 @@ k_lvl_cols(const LevelDesc* __restrict__ levels, int nlevels, int total_cols, ui
   if (!plane) return;
   for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < total_cols; g += gridDim.x * blockDim.x) {
     const LevelDesc& L = levels[level_of_line(levels, nlevels, g, 1)];
-    const int j = g - L.cols_base, pitch = L.lw + 1;
+    const int j = g - L.cols_base, pitch = L.pitch;
     uint32_t* c = plane + L.ip_off + j;
     uint32_t acc = 0;
     int y = 1;
@@ -449,7 +474,7 @@ k_lvl_cascade(const LevelDesc* __restrict__ levels, int nlevels, LvlPlanes pl, i
       if (!L.owned) pass = false;          // another rank evaluates this level (image-sharded mining)
       const long long k = (long long)b - L.w_base + L.w_skip;
       const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
-      const int pitch = L.lw + 1;
+      const int pitch = L.pitch;
       const size_t org = (size_t)L.ip_off + (size_t)(L.y0 + iy * L.step_y) * pitch + (L.x0 + ix * L.step_x);
       const uint32_t* S = pl.sum + org;
       float nf = 0.f;
@@ -528,7 +553,7 @@ __global__ void k_gather_list(const LevelDesc* __restrict__ levels, int nlevels,
     const long long k = b - L.w_base + L.w_skip;
     const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
     const int wy = r / W, wx = r - wy * W;
-    dst[t] = L.owned ? pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.lw + (L.x0 + ix * L.step_x + wx)] : (uint8_t)0;
+    dst[t] = L.owned ? pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.ppitch + (L.x0 + ix * L.step_x + wx)] : (uint8_t)0;
     if (r == 0) labels[i] = (uint8_t)label;
   }
 }
@@ -581,6 +606,7 @@ struct MineState {
   unsigned int* h_bitmap = nullptr;
   size_t bitmap_cap = 0;
   bool shard_images = true;            // when an NCCL communicator is attached
+  std::vector<LevelDesc> dev_levels;   // fast path: the batch's levels cut into strips, as uploaded to d_levels
 };
 
 static void free_cascade(MineState* m) {
@@ -718,6 +744,7 @@ static void fill_level(const NegStream& ns, LevelDesc& L) {
   L.scale_y = 1.0 / ((double)ns.lh / (double)im.h);
   L.x0 = ns.offX; L.y0 = ns.offY; L.step_x = ns.stepX(); L.step_y = ns.stepY();
   L.nx = ns.countX(); L.ny = ns.countY();
+  L.row0 = 0; L.pad1 = 0; L.owned = 1; L.pitch = L.lw + 1; L.ppitch = L.lw;
 }
 
 // upload the cascade as flat arrays
@@ -846,30 +873,59 @@ static bool use_level_path(const cc_ctx* ctx, const MineState* m) {
 // list, return the sorted surviving batch ordinals.  The level pixels stay in m->d_pool for gather_accepted().
 static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigned>& survivors) {
   survivors.clear();
-  const int nlv = (int)bt.levels.size();
   if (bt.nwin == 0) return CC_OK;
-  size_t plane_elems = 0;
-  int rows = 0, cols = 0, diag = 0;
-  for (LevelDesc& L : bt.levels) {
-    L.ip_off = (long long)plane_elems; L.rows_base = rows; L.cols_base = cols; L.diag_base = diag;
-    plane_elems += (size_t)(L.lw + 1) * (L.lh + 1);
-    rows += L.lh; cols += L.lw + 1; diag += L.lw + L.lh - 1;
-  }
-  // image-sharded mining: the background images of the batch go round-robin to the ranks; every rank
-  // builds and evaluates only the levels of its images, the survivor bitmaps are summed over NVLink, and every rank
-  // then applies the same serial stopping rule to the same ordered survivor list
-  const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
+  // Tall levels are cut into horizontal strips of STRIP_WIN_ROWS window rows (consecutive strips overlap by H - step
+  // pixel rows): window sums are differences, so every strip can carry its own integral planes, and a strip is a
+  // much shorter serial chain of rows for k_lvl_build than the whole level.  The window ordinals of a strip are a
+  // contiguous range of its level's, so a strip is described like a level (the device code does not distinguish).
+  constexpr int STRIP_WIN_ROWS = 8;
+  std::vector<LevelDesc>& dl = m->dev_levels;
+  dl.clear();
+  size_t pool_px = 0;
   {
     int img_ord = -1;
     const uint8_t* prev = nullptr;
-    for (LevelDesc& L : bt.levels) {
+    // image-sharded mining: the background images of the batch go round-robin to the ranks; every rank
+    // builds and evaluates only the levels of its images, the survivor bitmaps are summed over NVLink, and every rank
+    // then applies the same serial stopping rule to the same ordered survivor list
+    const bool sharded_ = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
+    for (const LevelDesc& L : bt.levels) {
       if (L.src != prev) { ++img_ord; prev = L.src; }
-      L.owned = sharded ? ((img_ord % ctx->comm_world) == ctx->comm_rank) : 1;
+      const int owned = sharded_ ? ((img_ord % ctx->comm_world) == ctx->comm_rank) : 1;
+      const long long k_lo = L.w_skip, k_hi = L.w_skip + L.w_count;          // window indices of this level taken by the batch
+      for (int a = 0; a < L.ny; a += STRIP_WIN_ROWS) {
+        const int b = std::min(L.ny, a + STRIP_WIN_ROWS);
+        const long long s_lo = std::max<long long>(k_lo, (long long)a * L.nx), s_hi = std::min<long long>(k_hi, (long long)b * L.nx);
+        if (s_lo >= s_hi) continue;
+        LevelDesc S = L;
+        S.row0 = L.y0 + a * L.step_y;
+        S.y0 = 0;
+        S.lh = (b - a - 1) * L.step_y + ctx->H;
+        S.ny = b - a;
+        S.w_skip = s_lo - (long long)a * L.nx;
+        S.w_count = s_hi - s_lo;
+        S.w_base = L.w_base + (s_lo - k_lo);
+        S.px_off = (long long)pool_px;
+        S.owned = owned;
+        S.pitch = (S.lw + 1 + 3) & ~3;
+        S.ppitch = (S.lw + 3) & ~3;
+        pool_px += (size_t)S.ppitch * S.lh;
+        dl.push_back(S);
+      }
     }
   }
+  const int nlv = (int)dl.size();
+  size_t plane_elems = 0;
+  int rows = 0, cols = 0, diag = 0;
+  for (LevelDesc& L : dl) {
+    L.ip_off = (long long)plane_elems; L.rows_base = rows; L.cols_base = cols; L.diag_base = diag;
+    plane_elems += (size_t)L.pitch * (L.lh + 1);
+    rows += L.lh; cols += L.lw + 1; diag += L.lw + L.lh - 1;
+  }
+  const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
   const bool haar = ctx->ftype == CC_FEATURE_HAAR;
   const bool tilted = haar && m->cascade_tilted;
-  if (bt.pool_px > m->pool_cap) { cudaFree(m->d_pool); CC_CUDA(cudaMalloc(&m->d_pool, bt.pool_px)); m->pool_cap = bt.pool_px; }
+  if (pool_px > m->pool_cap) { cudaFree(m->d_pool); CC_CUDA(cudaMalloc(&m->d_pool, pool_px + pool_px / 4)); m->pool_cap = pool_px + pool_px / 4; }
   if (nlv > m->levels_cap) { cudaFree(m->d_levels); CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * nlv)); m->levels_cap = nlv; }
   if (plane_elems > m->plane_cap) {
     cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
@@ -889,26 +945,35 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
   }
   if (!m->h_surv) CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (m->list_cap + 1)));
   if (!m->d_counts) CC_CUDA(cudaMalloc(&m->d_counts, sizeof(unsigned) * 16));
-  CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * nlv, cudaMemcpyHostToDevice, ctx->stream));
+  CC_CUDA(cudaMemcpyAsync(m->d_levels, dl.data(), sizeof(LevelDesc) * nlv, cudaMemcpyHostToDevice, ctx->stream));
   int ngroups = 0;
   {
     ScopedTimer tm(ctx, "mine", 0);
     int launches = 0;
     bool fused = !m->force_unfused;
-    for (const LevelDesc& L : bt.levels) fused = fused && L.lw <= LB_MAXDIM && L.lh <= LB_MAXDIM && L.sh <= 65535;
+    for (const LevelDesc& L : dl) fused = fused && L.lw <= LB_MAXDIM && L.lh <= LB_MAXDIM && L.sh <= 65535;
     if (fused) {
-      std::vector<int> order;
-      for (int i = 0; i < nlv; ++i) if (bt.levels[i].owned) order.push_back(i);
-      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bt.levels[a].lh > bt.levels[b].lh; });
+      // three width classes (CTA of 128 / 256 / 512 threads, 4 columns per thread), each tallest-first
+      std::vector<int> order[3];
+      for (int i = 0; i < nlv; ++i)
+        if (dl[i].owned) order[dl[i].lw <= 511 ? 0 : dl[i].lw <= 1023 ? 1 : 2].push_back(i);
       if (nlv > m->order_cap) { cudaFree(m->d_order); CC_CUDA(cudaMalloc(&m->d_order, sizeof(int) * nlv * 2)); m->order_cap = nlv * 2; }
-      if (!order.empty()) {
-        CC_CUDA(cudaMemcpyAsync(m->d_order, order.data(), sizeof(int) * order.size(), cudaMemcpyHostToDevice, ctx->stream));
-        k_lvl_build<<<(int)order.size(), LB_THREADS, 0, ctx->stream>>>(m->d_levels, m->d_order, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr,
-                                                                       tilted ? m->d_ptilt : nullptr);
-        launches += 1;
+      std::vector<int> flat;
+      int off[4] = {0, 0, 0, 0};
+      for (int c = 0; c < 3; ++c) {
+        std::stable_sort(order[c].begin(), order[c].end(), [&](int a, int b) { return dl[a].lh > dl[b].lh; });
+        flat.insert(flat.end(), order[c].begin(), order[c].end());
+        off[c + 1] = (int)flat.size();
       }
+      if (!flat.empty()) CC_CUDA(cudaMemcpyAsync(m->d_order, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, ctx->stream));
+      uint32_t* psq = haar ? m->d_psq : nullptr;
+      uint32_t* ptl = tilted ? m->d_ptilt : nullptr;
+      // widest class first: its levels are the longest chains
+      if (off[3] > off[2]) { k_lvl_build<512><<<off[3] - off[2], 512, 0, ctx->stream>>>(m->d_levels, m->d_order + off[2], m->d_pool, m->d_psum, psq, ptl); ++launches; }
+      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, 0, ctx->stream>>>(m->d_levels, m->d_order + off[1], m->d_pool, m->d_psum, psq, ptl); ++launches; }
+      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, 0, ctx->stream>>>(m->d_levels, m->d_order + off[0], m->d_pool, m->d_psum, psq, ptl); ++launches; }
     } else {
-      k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, (long long)bt.pool_px, m->d_pool);
+      k_resize_levels<<<grid_for(ctx, (long long)pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, (long long)pool_px, m->d_pool);
       k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
       launches += 2;
       if (tilted) {
@@ -983,7 +1048,7 @@ static int gather_accepted(cc_ctx* ctx, MineState* m, const Batch& bt, const uns
   CC_CUDA(cudaMemcpyAsync(m->d_list[0], which, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
   {
     ScopedTimer tm(ctx, "mine", 1);
-    k_gather_list<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, ctx->W, ctx->H,
+    k_gather_list<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)m->dev_levels.size(), m->d_pool, ctx->W, ctx->H,
                                                                                   m->d_list[0], n, ctx->d_imgs + (size_t)first * npx,
                                                                                   ctx->d_labels + first, label);
     CC_CUDA(cudaGetLastError());

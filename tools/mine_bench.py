@@ -28,7 +28,7 @@ for i in range(nimg):
     _lib.check(lib.cc_bg_register(h, b.ctypes.data_as(C.c_void_p), b.shape[1], b.shape[0]))
 cc._sync_cascade()
 win, surv = C.c_int64(0), C.c_int64(0)
-_lib.check(lib.cc_mine_scan(h, 0, min(nimg, 4), C.byref(win), C.byref(surv)))      # warm-up
+_lib.check(lib.cc_mine_scan(h, 0, nimg, C.byref(win), C.byref(surv)))      # warm-up (same size: allocations)
 ctx.timing_reset()
 ctx.synchronize()
 t0 = time.time()
