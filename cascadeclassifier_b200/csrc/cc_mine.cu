@@ -451,90 +451,120 @@ struct LvlFeat { uint32_t hdr; uint32_t tap[16]; };      // hdr = ntaps | tilted
 
 struct LvlPlanes { const uint32_t* sum; const uint32_t* sq; const uint32_t* tilted; };
 
-// CvCascadeClassifier::predict over the windows of the batch, stages [s_begin, s_end), early exit; the survivors'
-// batch ordinals are appended to out_list (warp-ballot compaction, one atomic per warp).  in_list == nullptr:
-// every window of the batch; otherwise the survivors of the previous stage group (count read on the device).
+// CvCascadeClassifier::predict for window k of level (strip) L, stages [s_begin, s_end), early exit.
+struct CascadeArgs {
+  LvlPlanes pl;
+  int ftype, W, H;
+  const DevNode* nodes;
+  const LvlFeat* feats;
+  const int* tree_first;
+  const DevStageRef* stages;
+  int s_begin, s_end;
+};
+
+__device__ __forceinline__ bool lvl_eval_window(const LevelDesc& L, long long k, const CascadeArgs& A) {
+  const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
+  const int pitch = L.pitch, W = A.W, H = A.H;
+  const size_t org = (size_t)L.ip_off + (size_t)(L.y0 + iy * L.step_y) * pitch + (L.x0 + ix * L.step_x);
+  const uint32_t* S = A.pl.sum + org;
+  float nf = 0.f;
+  if (A.ftype == CC_FEATURE_HAAR) {
+    const uint32_t* Q = A.pl.sq + org;
+    const int o0 = pitch + 1, o1 = pitch + (W - 1), o2 = (H - 1) * pitch + 1, o3 = (H - 1) * pitch + (W - 1);
+    const uint32_t vs = __ldg(S + o0) - __ldg(S + o1) - __ldg(S + o2) + __ldg(S + o3);
+    const uint32_t vq = __ldg(Q + o0) - __ldg(Q + o1) - __ldg(Q + o2) + __ldg(Q + o3);
+    const double area = (double)((W - 2) * (H - 2));
+    const double dvs = (double)(int)vs;
+    nf = (float)sqrt(area * (double)vq - dvs * dvs);
+  }
+  const uint32_t* Tt = A.pl.tilted ? A.pl.tilted + org : nullptr;
+  for (int st = A.s_begin; st < A.s_end; ++st) {
+    const DevStageRef sr = A.stages[st];
+    double sum = 0;
+    for (int t = 0; t < sr.num_trees; ++t) {
+      const int first = A.tree_first[sr.first_tree + t];
+      int nd = 0;
+      while (A.nodes[first + nd].left >= 0) {
+        const DevNode& node = A.nodes[first + nd];
+        const LvlFeat& f = A.feats[first + nd];
+        bool left;
+        if (A.ftype == CC_FEATURE_HAAR) {
+          const uint32_t hdr = f.hdr;
+          const uint32_t* P = (hdr >> 8) ? Tt : S;
+          const int nt = (int)(hdr & 0xFFu);
+          int acc = 0;
+          for (int q = 0; q < nt; ++q) {
+            const uint32_t tp = f.tap[q];
+            acc += (int)(int8_t)(tp >> 16) * (int)__ldg(P + (int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu));
+          }
+          const float val = nf == 0.f ? 0.f : __fdiv_rn((float)acc, nf);
+          left = val <= node.c;
+        } else {
+          int v[16];
+#pragma unroll
+          for (int q = 0; q < 16; ++q) { const uint32_t tp = f.tap[q]; v[q] = (int)__ldg(S + (int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)); }
+          auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
+          const int c = cell(1, 1);
+          const int code = (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
+                           (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
+                           (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
+          left = (node.subset[code >> 5] & (1 << (code & 31))) != 0;
+        }
+        nd = left ? node.left : node.right;
+      }
+      sum += A.nodes[first + nd].value;
+    }
+    if (sum < (double)(sr.threshold - 0.00001F)) return false;
+  }
+  return true;
+}
+
+// ordered-in-warp compaction of the survivors (warp ballot, one atomic per warp); the host sorts the short final list
+__device__ __forceinline__ void lvl_append(bool pass, unsigned int b, unsigned int* __restrict__ out_count, unsigned int* __restrict__ out_list) {
+  const unsigned m = __ballot_sync(0xffffffffu, pass);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned base = 0;
+    if (lane == leader) base = atomicAdd(out_count, (unsigned)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pass) out_list[base + __popc(m & ((1u << lane) - 1u))] = b;
+  }
+}
+
+// first stage group: every window of the batch.  One CTA per level strip (grid-stride), threads over its windows.
 __global__ void __launch_bounds__(256)
-k_lvl_cascade(const LevelDesc* __restrict__ levels, int nlevels, LvlPlanes pl, int ftype, int W, int H,
-              const DevNode* __restrict__ nodes, const LvlFeat* __restrict__ feats, const int* __restrict__ tree_first,
-              const DevStageRef* __restrict__ stages, int s_begin, int s_end, const unsigned int* __restrict__ in_list,
-              const unsigned int* __restrict__ in_count, long long nwin_all, unsigned int* __restrict__ out_count,
-              unsigned int* __restrict__ out_list) {
-  const long long n = in_list ? (long long)*in_count : nwin_all;
-  const int lane = threadIdx.x & 31;
+k_lvl_cascade_all(const LevelDesc* __restrict__ levels, int nlevels, CascadeArgs A, unsigned int* __restrict__ out_count,
+                  unsigned int* __restrict__ out_list) {
+  for (int lv = blockIdx.x; lv < nlevels; lv += gridDim.x) {
+    const LevelDesc& L = levels[lv];
+    if (!L.owned) continue;              // another rank evaluates this level (image-sharded mining)
+    const int n = (int)L.w_count;
+    const int nround = (n + 31) & ~31;
+    for (int i = threadIdx.x; i < nround; i += blockDim.x) {
+      const bool pass = i < n && lvl_eval_window(L, L.w_skip + i, A);
+      lvl_append(pass, (unsigned int)(L.w_base + i), out_count, out_list);
+    }
+  }
+}
+
+// later stage groups: the survivors of the previous group (count read on the device)
+__global__ void __launch_bounds__(256)
+k_lvl_cascade(const LevelDesc* __restrict__ levels, int nlevels, CascadeArgs A, const unsigned int* __restrict__ in_list,
+              const unsigned int* __restrict__ in_count, unsigned int* __restrict__ out_count, unsigned int* __restrict__ out_list) {
+  const long long n = (long long)*in_count;
   const long long nround = (n + 31) & ~31ll;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nround; i += (long long)gridDim.x * blockDim.x) {
     bool pass = i < n;
     unsigned int b = 0;
     if (pass) {
-      b = in_list ? in_list[i] : (unsigned int)i;
+      b = in_list[i];
       int lo = 0, hi = nlevels - 1;
       while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= (long long)b) lo = mid; else hi = mid - 1; }
       const LevelDesc& L = levels[lo];
-      if (!L.owned) pass = false;          // another rank evaluates this level (image-sharded mining)
-      const long long k = (long long)b - L.w_base + L.w_skip;
-      const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
-      const int pitch = L.pitch;
-      const size_t org = (size_t)L.ip_off + (size_t)(L.y0 + iy * L.step_y) * pitch + (L.x0 + ix * L.step_x);
-      const uint32_t* S = pl.sum + org;
-      float nf = 0.f;
-      if (ftype == CC_FEATURE_HAAR && pass) {
-        const uint32_t* Q = pl.sq + org;
-        const int o0 = pitch + 1, o1 = pitch + (W - 1), o2 = (H - 1) * pitch + 1, o3 = (H - 1) * pitch + (W - 1);
-        const uint32_t vs = __ldg(S + o0) - __ldg(S + o1) - __ldg(S + o2) + __ldg(S + o3);
-        const uint32_t vq = __ldg(Q + o0) - __ldg(Q + o1) - __ldg(Q + o2) + __ldg(Q + o3);
-        const double area = (double)((W - 2) * (H - 2));
-        const double dvs = (double)(int)vs;
-        nf = (float)sqrt(area * (double)vq - dvs * dvs);
-      }
-      const uint32_t* Tt = pl.tilted ? pl.tilted + org : nullptr;
-      for (int st = s_begin; st < s_end && pass; ++st) {
-        const DevStageRef sr = stages[st];
-        double sum = 0;
-        for (int t = 0; t < sr.num_trees; ++t) {
-          const int first = tree_first[sr.first_tree + t];
-          int nd = 0;
-          while (nodes[first + nd].left >= 0) {
-            const DevNode& node = nodes[first + nd];
-            const LvlFeat& f = feats[first + nd];
-            bool left;
-            if (ftype == CC_FEATURE_HAAR) {
-              const uint32_t hdr = f.hdr;
-              const uint32_t* P = (hdr >> 8) ? Tt : S;
-              const int nt = (int)(hdr & 0xFFu);
-              int acc = 0;
-              for (int q = 0; q < nt; ++q) {
-                const uint32_t tp = f.tap[q];
-                acc += (int)(int8_t)(tp >> 16) * (int)__ldg(P + (int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu));
-              }
-              const float val = nf == 0.f ? 0.f : __fdiv_rn((float)acc, nf);
-              left = val <= node.c;
-            } else {
-              int v[16];
-#pragma unroll
-              for (int q = 0; q < 16; ++q) { const uint32_t tp = f.tap[q]; v[q] = (int)__ldg(S + (int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)); }
-              auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
-              const int c = cell(1, 1);
-              const int code = (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
-                               (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
-                               (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
-              left = (node.subset[code >> 5] & (1 << (code & 31))) != 0;
-            }
-            nd = left ? node.left : node.right;
-          }
-          sum += nodes[first + nd].value;
-        }
-        if (sum < (double)(sr.threshold - 0.00001F)) pass = false;
-      }
+      pass = lvl_eval_window(L, (long long)b - L.w_base + L.w_skip, A);
     }
-    const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (m) {
-      const int leader = __ffs(m) - 1;
-      unsigned base = 0;
-      if (lane == leader) base = atomicAdd(out_count, (unsigned)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, leader);
-      if (pass) out_list[base + __popc(m & ((1u << lane) - 1u))] = b;
-    }
+    lvl_append(pass, b, out_count, out_list);
   }
 }
 
@@ -988,21 +1018,23 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
     }
     CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaMemsetAsync(m->d_counts, 0, sizeof(unsigned) * 16, ctx->stream));
-    // stage groups [0,2) [2,4) [4,8) [8,16) ...: each group runs on the survivors of the previous one
+    // stage groups [0,2) [2,6) [6,end): each group runs on the survivors of the previous one
     const int ns = (int)m->stages.size();
-    LvlPlanes pl{m->d_psum, m->d_psq, tilted ? m->d_ptilt : nullptr};
-    int s0 = 0, width = 2;
+    CascadeArgs A;
+    A.pl = LvlPlanes{m->d_psum, m->d_psq, tilted ? m->d_ptilt : nullptr};
+    A.ftype = ctx->ftype; A.W = ctx->W; A.H = ctx->H;
+    A.nodes = m->d_nodes; A.feats = m->d_lfeats; A.tree_first = m->d_tree_first; A.stages = m->d_stages;
+    int s0 = 0;
     while (s0 < ns) {
-      const int s1 = std::min(ns, s0 + width);
-      const unsigned* in_list = ngroups == 0 ? nullptr : m->d_list[(ngroups - 1) & 1];
-      const int grid = ngroups == 0 ? grid_for(ctx, bt.nwin, 256) : ctx->sm_count * 8;
-      k_lvl_cascade<<<grid, 256, 0, ctx->stream>>>(m->d_levels, nlv, pl, ctx->ftype, ctx->W, ctx->H, m->d_nodes, m->d_lfeats, m->d_tree_first,
-                                                    m->d_stages, s0, s1, in_list, ngroups == 0 ? nullptr : m->d_counts + ngroups - 1, bt.nwin,
-                                                    m->d_counts + ngroups, m->d_list[ngroups & 1]);
+      const int s1 = ngroups == 0 ? std::min(ns, 2) : ngroups == 1 ? std::min(ns, 6) : ns;
+      A.s_begin = s0; A.s_end = s1;
+      if (ngroups == 0)
+        k_lvl_cascade_all<<<std::min(nlv, ctx->sm_count * 32), 256, 0, ctx->stream>>>(m->d_levels, nlv, A, m->d_counts, m->d_list[0]);
+      else
+        k_lvl_cascade<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(m->d_levels, nlv, A, m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1,
+                                                                   m->d_counts + ngroups, m->d_list[ngroups & 1]);
       ++ngroups; ++launches;
       s0 = s1;
-      if (ngroups >= 2) width *= 2;
-      if (ngroups == 15) { width = ns; }
     }
     CC_CUDA(cudaGetLastError());
     ctx->launches += launches;
