@@ -576,6 +576,8 @@ __global__ void k_gather_list(const LevelDesc* __restrict__ levels, int nlevels,
   for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(t / npx);
     const int r = (int)(t - (long long)i * npx);
+    if (r == 0) labels[i] = (uint8_t)label;
+    if (nlevels == 0) { dst[t] = 0; continue; }      // this rank owns no strip of the batch
     const long long b = which[i];
     int lo = 0, hi = nlevels - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= b) lo = mid; else hi = mid - 1; }
@@ -583,8 +585,9 @@ __global__ void k_gather_list(const LevelDesc* __restrict__ levels, int nlevels,
     const long long k = b - L.w_base + L.w_skip;
     const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
     const int wy = r / W, wx = r - wy * W;
-    dst[t] = L.owned ? pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.ppitch + (L.x0 + ix * L.step_x + wx)] : (uint8_t)0;
-    if (r == 0) labels[i] = (uint8_t)label;
+    // only the strips this rank owns are in the table: a window of another rank's strip falls outside [w_base, w_base + w_count)
+    const bool mine = b >= L.w_base && b < L.w_base + L.w_count;
+    dst[t] = mine ? pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.ppitch + (L.x0 + ix * L.step_x + wx)] : (uint8_t)0;
   }
 }
 
@@ -893,7 +896,13 @@ struct Batch {
 };
 
 // windows the fast path may put in one batch (pyramid pixels ~ 154 per window at 1920x1080 -> ~2 GB of planes)
-constexpr long long LEVEL_PATH_MAX_BATCH = 1 << 20;
+constexpr long long LEVEL_PATH_MAX_BATCH = 1 << 20;     // per rank: image-sharded mining scales the batch with the number of ranks
+static long long level_path_max_batch(const cc_ctx* ctx, const MineState* m);
+
+static long long level_path_max_batch(const cc_ctx* ctx, const MineState* m) {
+  const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
+  return LEVEL_PATH_MAX_BATCH * (sharded ? std::min(ctx->comm_world, 16) : 1);
+}
 
 static bool use_level_path(const cc_ctx* ctx, const MineState* m) {
   return !m->force_slots && !m->stages.empty() && (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) && ctx->W <= 255 && ctx->H <= 255;
@@ -922,6 +931,7 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
     for (const LevelDesc& L : bt.levels) {
       if (L.src != prev) { ++img_ord; prev = L.src; }
       const int owned = sharded_ ? ((img_ord % ctx->comm_world) == ctx->comm_rank) : 1;
+      if (!owned) continue;              // the owner builds, evaluates and (if accepted) supplies the pixels of these windows
       const long long k_lo = L.w_skip, k_hi = L.w_skip + L.w_count;          // window indices of this level taken by the batch
       for (int a = 0; a < L.ny; a += STRIP_WIN_ROWS) {
         const int b = std::min(L.ny, a + STRIP_WIN_ROWS);
@@ -1028,8 +1038,9 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
     while (s0 < ns) {
       const int s1 = ngroups == 0 ? std::min(ns, 2) : ngroups == 1 ? std::min(ns, 6) : ns;
       A.s_begin = s0; A.s_end = s1;
-      if (ngroups == 0)
-        k_lvl_cascade_all<<<std::min(nlv, ctx->sm_count * 32), 256, 0, ctx->stream>>>(m->d_levels, nlv, A, m->d_counts, m->d_list[0]);
+      if (ngroups == 0) {
+        if (nlv > 0) k_lvl_cascade_all<<<std::min(nlv, ctx->sm_count * 32), 256, 0, ctx->stream>>>(m->d_levels, nlv, A, m->d_counts, m->d_list[0]);
+      }
       else
         k_lvl_cascade<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(m->d_levels, nlv, A, m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1,
                                                                    m->d_counts + ngroups, m->d_list[ngroups & 1]);
@@ -1201,7 +1212,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   int got = 0;
   double accept_rate = m->stages.empty() ? 1.0 : 0.0;   // running estimate
   const bool level_path = use_level_path(ctx, m);
-  const long long max_batch = level_path ? LEVEL_PATH_MAX_BATCH : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
   bool stream_ok = true;
   if (ns.lw == 0) stream_ok = ns.nextImg();             // first get(): img.empty() -> nextImg()
   std::vector<unsigned> survivors, accepted;
@@ -1413,7 +1424,7 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
   CC_CUDA(cudaSetDevice(ctx->device));
   const int W = ctx->W, H = ctx->H, npx = W * H;
   const bool level_path = use_level_path(ctx, m);
-  const long long max_batch = level_path ? LEVEL_PATH_MAX_BATCH : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
   long long total = 0, surv = 0;
   std::vector<unsigned> survivors;
   // every image from its first level (round 0 offsets), independent of the reader state
