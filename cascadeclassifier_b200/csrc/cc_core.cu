@@ -34,10 +34,11 @@ ScopedTimer::ScopedTimer(cc_ctx* c, const char* nm, int launches) : ctx(c), name
   PendingEvent pe{get_event(ctx), get_event(ctx), nm, launches};
   cudaEventRecord(pe.a, ctx->stream);
   g_pending[ctx].push_back(pe);
+  idx = (int)g_pending[ctx].size() - 1;
 }
 ScopedTimer::~ScopedTimer() {
-  if (!ctx->timing_enabled) return;
-  cudaEventRecord(g_pending[ctx].back().b, ctx->stream);
+  if (!ctx->timing_enabled || idx < 0 || idx >= (int)g_pending[ctx].size()) return;
+  cudaEventRecord(g_pending[ctx][idx].b, ctx->stream);
 }
 
 static void resolve_timers(cc_ctx* ctx) {

@@ -178,10 +178,11 @@ struct cc_ctx {
 
 namespace cc {
 // timing helpers: bracket a kernel family with events on ctx->stream
-struct ScopedTimer {
+struct ScopedTimer {      // do not nest (the inner interval would be counted twice)
   cc_ctx* ctx;
   const char* name;
   int n;
+  int idx = -1;             // position of this timer's event pair in the pending list
   ScopedTimer(cc_ctx* c, const char* nm, int launches);
   ~ScopedTimer();
 };
