@@ -966,7 +966,7 @@ k_tree_finish(EvalView e, int N, int boost_type, int have_subsample, double trim
               const DevNode* __restrict__ tree, const uint8_t* __restrict__ labels, const int* __restrict__ orig_response,
               double* weights, double* weak_eval, double* treeval, double* stage_sum, double* sum_response, float* responses,
               uint8_t* mask, TreeSummary* summary) {
-  __shared__ double scratch[32];
+  __shared__ double scratch[32], scratch2[32], scratch3[32];
   __shared__ unsigned long long s_u64;
   // (a) responses of the samples that did not take part in the tree, and the threshold-rule output for everyone
   for (int s = threadIdx.x; s < N; s += blockDim.x) {
@@ -1053,19 +1053,27 @@ k_tree_finish(EvalView e, int N, int boost_type, int have_subsample, double trim
     if (any) {
       // Q(x) = [ sum{w <= x} - max{w <= x} >= target ] is a monotone step function of x whose first
       // true point is the wanted weight value (the sorted prefix before the last copy of that value).
+      // Q only changes at actual weight values, so after testing x = mid both ends snap to weights: true -> hi = largest
+      // weight <= mid, false -> lo = smallest weight > mid.  The interval then empties after ~log2(N) + a few steps
+      // instead of the 63 halvings of the bit space.
       while (lo < hi) {
         const unsigned long long mid = lo + ((hi - lo) >> 1);
         const double v = __longlong_as_double((long long)mid);
-        double acc = 0, top = 0;
-        for (int s = threadIdx.x; s < N; s += blockDim.x) { const double w = weights[s]; if (w <= v) { acc += w; top = fmax(top, w); } }
-        acc = block_sum(acc, scratch);
-        for (int d = 16; d > 0; d >>= 1) top = fmax(top, __shfl_xor_sync(0xffffffffu, top, d));
+        double acc = 0, top = 0, nxt = DBL_MAX;
+        for (int s = threadIdx.x; s < N; s += blockDim.x) {
+          const double w = weights[s];
+          if (w <= v) { acc += w; top = fmax(top, w); } else nxt = fmin(nxt, w);
+        }
+        acc = warp_sum(acc);
+        for (int d = 16; d > 0; d >>= 1) { top = fmax(top, __shfl_xor_sync(0xffffffffu, top, d)); nxt = fmin(nxt, __shfl_xor_sync(0xffffffffu, nxt, d)); }
         __syncthreads();
-        if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = top;
+        if ((threadIdx.x & 31) == 0) { scratch[threadIdx.x >> 5] = acc; scratch2[threadIdx.x >> 5] = top; scratch3[threadIdx.x >> 5] = nxt; }
         __syncthreads();
-        top = scratch[threadIdx.x & 31];
-        for (int d = 16; d > 0; d >>= 1) top = fmax(top, __shfl_xor_sync(0xffffffffu, top, d));
-        if (acc - top >= target) hi = mid; else lo = mid + 1;
+        acc = scratch[threadIdx.x & 31]; top = scratch2[threadIdx.x & 31]; nxt = scratch3[threadIdx.x & 31];
+        acc = warp_sum(acc);
+        for (int d = 16; d > 0; d >>= 1) { top = fmax(top, __shfl_xor_sync(0xffffffffu, top, d)); nxt = fmin(nxt, __shfl_xor_sync(0xffffffffu, nxt, d)); }
+        if (acc - top >= target) hi = (unsigned long long)__double_as_longlong(top);
+        else lo = (unsigned long long)__double_as_longlong(nxt);
       }
       // snap to the smallest actual weight >= bound
       const double bound = __longlong_as_double((long long)lo);
@@ -1102,13 +1110,26 @@ k_tree_finish(EvalView e, int N, int boost_type, int have_subsample, double trim
   const int thresholdIdx = (int)((1.0F - min_hit_rate) * numPos);
   // k-th smallest (k = thresholdIdx) of the float stage sums of the positives
   uint32_t klo = 0, khi = 0xFFFFFFFFu;
-  while (klo < khi) {
+  while (klo < khi) {       // same snapping: the count only changes at actual keys
     const uint32_t mid = klo + ((khi - klo) >> 1);
     long long c = 0;
+    uint32_t top = 0u, nxt = 0xFFFFFFFFu;
     for (int s = threadIdx.x; s < N; s += blockDim.x)
-      if (labels[s] == 1 && f2key((float)stage_sum[s]) <= mid) c++;
-    c = block_sum_ll(c, scratch);
-    if (c >= thresholdIdx + 1) khi = mid; else klo = mid + 1;
+      if (labels[s] == 1) {
+        const uint32_t k = f2key((float)stage_sum[s]);
+        if (k <= mid) { c++; top = max(top, k); } else nxt = min(nxt, k);
+      }
+    for (int d = 16; d > 0; d >>= 1) {
+      c += __shfl_xor_sync(0xffffffffu, c, d);
+      top = max(top, __shfl_xor_sync(0xffffffffu, top, d)); nxt = min(nxt, __shfl_xor_sync(0xffffffffu, nxt, d));
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { scratch[threadIdx.x >> 5] = (double)c; scratch2[threadIdx.x >> 5] = (double)top; scratch3[threadIdx.x >> 5] = (double)nxt; }
+    __syncthreads();
+    double dc = scratch[threadIdx.x & 31], dt = scratch2[threadIdx.x & 31], dn = scratch3[threadIdx.x & 31];      // counts and 32-bit keys are exact in f64
+    dc = warp_sum(dc);
+    for (int d = 16; d > 0; d >>= 1) { dt = fmax(dt, __shfl_xor_sync(0xffffffffu, dt, d)); dn = fmin(dn, __shfl_xor_sync(0xffffffffu, dn, d)); }
+    if ((long long)dc >= thresholdIdx + 1) khi = (uint32_t)dt; else klo = (uint32_t)dn;
   }
   const float thr = key2f(klo);
   long long below = 0, nfalse = 0;
