@@ -85,6 +85,8 @@ def _signatures():
         "cc_boost_get_weights": (i32, [vp, vp, vp]),
         "cc_boost_get_row_quality": (i32, [vp, i32, i32, vp]),
         "cc_boost_set_search_mode": (i32, [vp, i32]),
+        "cc_boost_set_sort_mode": (i32, [vp, i32]),
+        "cc_boost_get_sort_stats": (i32, [vp, P(i64)]),
         "cc_boost_get_search_stats": (i32, [vp, P(i64), P(i64), P(i64)]),
         "cc_stage_predict": (i32, [vp, P(Stage), i32, i32, i32, vp]),
         "cc_bg_clear": (i32, [vp]),

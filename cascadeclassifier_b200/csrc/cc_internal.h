@@ -163,6 +163,8 @@ struct cc_ctx {
   uint8_t* d_fcode = nullptr;      // [nrows][n_stride] (LBP)
   uint16_t* d_sidx = nullptr;      // [nrows][n_stride]
   float* d_sval = nullptr;         // [nrows][n_stride] values in sorted order
+  int* d_hard_rows = nullptr;      // [1 + nrows]: count, then the rows the bucket sort deferred to the radix kernel
+  int sort_mode = 0;               // cc_boost_set_sort_mode
   size_t cap_rows = 0, cap_stride = 0;
 
   // ---- boosting state (device) ----

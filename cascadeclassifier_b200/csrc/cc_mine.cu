@@ -462,22 +462,20 @@ struct CascadeArgs {
   int s_begin, s_end;
 };
 
-__device__ __forceinline__ bool lvl_eval_window(const LevelDesc& L, long long k, const CascadeArgs& A) {
-  const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
-  const int pitch = L.pitch, W = A.W, H = A.H;
-  const size_t org = (size_t)L.ip_off + (size_t)(L.y0 + iy * L.step_y) * pitch + (L.x0 + ix * L.step_x);
-  const uint32_t* S = A.pl.sum + org;
+// S / Q / Tt point at the window's origin inside planes of row pitch `pitch` (global memory: whole-level planes; shared
+// memory: the planes of one tile).  Same arithmetic as setImage + operator() + predict of the reference.
+__device__ __forceinline__ bool eval_window_at(const uint32_t* __restrict__ S, const uint32_t* __restrict__ Q, const uint32_t* __restrict__ Tt,
+                                               int pitch, const CascadeArgs& A) {
+  const int W = A.W, H = A.H;
   float nf = 0.f;
   if (A.ftype == CC_FEATURE_HAAR) {
-    const uint32_t* Q = A.pl.sq + org;
     const int o0 = pitch + 1, o1 = pitch + (W - 1), o2 = (H - 1) * pitch + 1, o3 = (H - 1) * pitch + (W - 1);
-    const uint32_t vs = __ldg(S + o0) - __ldg(S + o1) - __ldg(S + o2) + __ldg(S + o3);
-    const uint32_t vq = __ldg(Q + o0) - __ldg(Q + o1) - __ldg(Q + o2) + __ldg(Q + o3);
+    const uint32_t vs = S[o0] - S[o1] - S[o2] + S[o3];
+    const uint32_t vq = Q[o0] - Q[o1] - Q[o2] + Q[o3];
     const double area = (double)((W - 2) * (H - 2));
     const double dvs = (double)(int)vs;
     nf = (float)sqrt(area * (double)vq - dvs * dvs);
   }
-  const uint32_t* Tt = A.pl.tilted ? A.pl.tilted + org : nullptr;
   for (int st = A.s_begin; st < A.s_end; ++st) {
     const DevStageRef sr = A.stages[st];
     double sum = 0;
@@ -495,14 +493,14 @@ __device__ __forceinline__ bool lvl_eval_window(const LevelDesc& L, long long k,
           int acc = 0;
           for (int q = 0; q < nt; ++q) {
             const uint32_t tp = f.tap[q];
-            acc += (int)(int8_t)(tp >> 16) * (int)__ldg(P + (int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu));
+            acc += (int)(int8_t)(tp >> 16) * (int)P[(int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)];
           }
           const float val = nf == 0.f ? 0.f : __fdiv_rn((float)acc, nf);
           left = val <= node.c;
         } else {
           int v[16];
 #pragma unroll
-          for (int q = 0; q < 16; ++q) { const uint32_t tp = f.tap[q]; v[q] = (int)__ldg(S + (int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)); }
+          for (int q = 0; q < 16; ++q) { const uint32_t tp = f.tap[q]; v[q] = (int)S[(int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)]; }
           auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
           const int c = cell(1, 1);
           const int code = (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
@@ -517,6 +515,12 @@ __device__ __forceinline__ bool lvl_eval_window(const LevelDesc& L, long long k,
     if (sum < (double)(sr.threshold - 0.00001F)) return false;
   }
   return true;
+}
+
+__device__ __forceinline__ bool lvl_eval_window(const LevelDesc& L, long long k, const CascadeArgs& A) {
+  const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
+  const size_t org = (size_t)L.ip_off + (size_t)(L.y0 + iy * L.step_y) * L.pitch + (L.x0 + ix * L.step_x);
+  return eval_window_at(A.pl.sum + org, A.pl.sq ? A.pl.sq + org : nullptr, A.pl.tilted ? A.pl.tilted + org : nullptr, L.pitch, A);
 }
 
 // ordered-in-warp compaction of the survivors (warp ballot, one atomic per warp); the host sorts the short final list
@@ -565,6 +569,157 @@ k_lvl_cascade(const LevelDesc* __restrict__ levels, int nlevels, CascadeArgs A, 
       pass = lvl_eval_window(L, (long long)b - L.w_base + L.w_skip, A);
     }
     lvl_append(pass, b, out_count, out_list);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused tile miner (cc_mine_set_mode 3, Haar / LBP): one CTA takes a tile of TW x TH windows of one pyramid level, builds the tile's
+// pixels (INTER_LINEAR_EXACT from the source image) and its sum / sqsum / tilted integral planes in shared memory, runs
+// the whole cascade on the tile's windows and appends the survivors.  Window sums are differences, so tile-local planes
+// (zero outside the tile) give the same integers as the per-crop cv::integral of setImage; nothing but the survivor
+// ordinals leaves the SM.  No phase has a barrier inside a loop: rows are scanned by warps (independent rows), columns
+// and diagonals are walked by one thread each.
+// ------------------------------------------------------------------------------------------------
+struct TileDesc { int level; int tx, ty; };
+
+__global__ void __launch_bounds__(256)
+k_tile_cascade(const LevelDesc* __restrict__ levels, const TileDesc* __restrict__ tiles, int TW, int TH, int tpw, int tph, int pp,
+               int want_sq, int want_tilted, CascadeArgs A, unsigned int* __restrict__ out_count, unsigned int* __restrict__ out_list) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int plane_words = pp * (tph + 1);
+  uint32_t* S = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* Q = S + plane_words;
+  uint32_t* T = Q + (want_sq ? plane_words : 0);
+  uint8_t* pix = reinterpret_cast<uint8_t*>(T + (want_tilted ? plane_words : 0));      // [tph][tpw]
+  int* xcoef = reinterpret_cast<int*>(pix + ((tpw * tph + 3) & ~3));                    // [tpw] source column | c1 << 16
+  int* ycoef = xcoef + tpw;                                                             // [tph]
+  const TileDesc td = tiles[blockIdx.x];
+  const LevelDesc& L = levels[td.level];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int W = A.W, H = A.H, sx = L.step_x, sy = L.step_y;
+  const int ix0 = td.tx * TW, iy0 = td.ty * TH;
+  const int nwx = min(TW, L.nx - ix0), nwy = min(TH, L.ny - iy0);
+  const int aw = (nwx - 1) * sx + W, ah = (nwy - 1) * sy + H;                 // pixels of this tile
+  const int lx0 = L.x0 + ix0 * sx, ly0 = L.y0 + iy0 * sy;                     // tile origin in level coordinates
+  const int sw = L.sw, sh = L.sh;
+  const uint8_t* __restrict__ src = L.src;
+  // ---- phase 0: resize coefficients, zero borders of the planes ----
+  for (int i = t; i < aw + ah; i += 256) {
+    int o, c0, c1, md;
+    if (i < aw) { lin_coef(L.scale_x, lx0 + i, sw, o, c0, c1, md); xcoef[i] = o | (c1 << 16); }
+    else { lin_coef(L.scale_y, ly0 + (i - aw), sh, o, c0, c1, md); ycoef[i - aw] = o | (c1 << 16); }
+  }
+  for (int i = t; i <= aw; i += 256) { S[i] = 0; if (want_sq) Q[i] = 0; if (want_tilted) T[i] = 0; }
+  for (int i = t; i <= ah; i += 256) { S[i * pp] = 0; if (want_sq) Q[i * pp] = 0; if (want_tilted) T[i * pp] = 0; }
+  __syncthreads();
+  // ---- phase 1: pixels + row prefixes (one warp per row) ----
+  for (int y = warp; y < ah; y += 8) {
+    const int yo = ycoef[y];
+    const int r0 = yo & 0xFFFF, r1 = min(r0 + 1, sh - 1);
+    const uint32_t cy1 = (uint32_t)yo >> 16, cy0 = 256u - cy1;
+    const uint8_t* a = src + (size_t)r0 * sw;
+    const uint8_t* b = src + (size_t)r1 * sw;
+    uint32_t c1s = 0, c2s = 0;
+    for (int xb = 0; xb < aw; xb += 32) {
+      const int x = xb + lane;
+      uint32_t v = 0;
+      if (x < aw) {
+        const int xo = xcoef[x];
+        const int xa = xo & 0xFFFF, xn = min(xa + 1, sw - 1);
+        const uint32_t cx1 = (uint32_t)xo >> 16, cx0 = 256u - cx1;
+        v = (((uint32_t)a[xa] * cx0 + (uint32_t)a[xn] * cx1) * cy0 + ((uint32_t)b[xa] * cx0 + (uint32_t)b[xn] * cx1) * cy1 + 32768u) >> 16;
+        pix[y * tpw + x] = (uint8_t)v;
+      }
+      uint32_t p1 = v, p2 = v * v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t u1 = __shfl_up_sync(0xffffffffu, p1, d), u2 = __shfl_up_sync(0xffffffffu, p2, d);
+        if (lane >= d) { p1 += u1; p2 += u2; }
+      }
+      p1 += c1s; p2 += c2s;
+      if (x < aw) { S[(y + 1) * pp + x + 1] = p1; if (want_sq) Q[(y + 1) * pp + x + 1] = p2; }
+      c1s = __shfl_sync(0xffffffffu, p1, 31); c2s = __shfl_sync(0xffffffffu, p2, 31);
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: column prefixes of S (and Q); tilted step 1: D1 along the down-right diagonals ----
+  {
+    const int ncol = want_sq ? 2 * aw : aw;
+    if (t < ncol) {
+      uint32_t* c = (t < aw ? S : Q) + (t < aw ? t : t - aw) + 1;
+      uint32_t acc = 0;
+      for (int y = 1; y <= ah; ++y) { acc += c[y * pp]; c[y * pp] = acc; }
+    }
+  }
+  if (want_tilted) {
+    // cells T[y+1][x+1] (x = -1 .. aw-1): E(y,x) = D1(y,x) + D2(y,x) - I(y,x), then a column prefix gives the tilted integral
+    for (int k = t; k < aw + ah - 1; k += 256) {
+      int y = k < aw ? 0 : k - aw + 1, x = k < aw ? k : 0;
+      uint32_t run = 0;
+      for (; y < ah && x < aw; ++y, ++x) { run += pix[y * tpw + x]; T[(y + 1) * pp + x + 1] = run; }
+    }
+    __syncthreads();
+    for (int k = t; k < aw + ah - 1; k += 256) {
+      int y = k < aw ? 0 : k - aw + 1, x = k < aw ? k : aw - 1;
+      uint32_t run = 0;
+      for (; y < ah && x >= 0; ++y, --x) { const uint32_t v = pix[y * tpw + x]; run += v; T[(y + 1) * pp + x + 1] += run - v; }
+      if (y < ah) T[(y + 1) * pp] += run;                // virtual column x = -1
+    }
+    __syncthreads();
+    if (t <= aw) {
+      uint32_t* c = T + t;
+      uint32_t acc = 0;
+      for (int y = 1; y <= ah; ++y) { acc += c[y * pp]; c[y * pp] = acc; }
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: the cascade on the tile's windows ----
+  const int nw = nwx * nwy;
+  for (int i0 = 0; i0 < nw; i0 += 256) {
+    const int i = i0 + t;
+    bool pass = false;
+    unsigned int b = 0;
+    if (i < nw) {
+      const int wy = i / nwx, wx = i - wy * nwx;
+      const long long k = (long long)(iy0 + wy) * L.nx + (ix0 + wx);
+      if (k >= L.w_skip && k < L.w_skip + L.w_count) {
+        const int org = (wy * sy) * pp + wx * sx;
+        pass = eval_window_at(S + org, Q + org, T + org, pp, A);
+        b = (unsigned int)(L.w_base + (k - L.w_skip));
+      }
+    }
+    lvl_append(pass, b, out_count, out_list);
+  }
+}
+
+// accepted windows (batch ordinals) recomputed from the source images: INTER_LINEAR_EXACT pixel by pixel (the tile miner
+// keeps no level pixels).  Ordinals outside this rank's levels give zeros (image-sharded mining sums the ranks' outputs).
+__global__ void k_gather_resize(const LevelDesc* __restrict__ levels, int nlevels, int W, int H, const unsigned int* __restrict__ which, int n,
+                                uint8_t* __restrict__ dst, uint8_t* __restrict__ labels, int label) {
+  const int npx = W * H;
+  const long long total = (long long)n * npx;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(t / npx);
+    const int r = (int)(t - (long long)i * npx);
+    if (r == 0) labels[i] = (uint8_t)label;
+    if (nlevels == 0) { dst[t] = 0; continue; }
+    const long long b = which[i];
+    int lo = 0, hi = nlevels - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= b) lo = mid; else hi = mid - 1; }
+    const LevelDesc& L = levels[lo];
+    if (b < L.w_base || b >= L.w_base + L.w_count) { dst[t] = 0; continue; }
+    const long long k = b - L.w_base + L.w_skip;
+    const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
+    const int wy = r / W, wx = r - wy * W;
+    const int x = L.x0 + ix * L.step_x + wx, y = L.row0 + L.y0 + iy * L.step_y + wy;
+    int ox, cx0, cx1, mx, oy, cy0, cy1, my;
+    lin_coef(L.scale_x, x, L.sw, ox, cx0, cx1, mx);
+    lin_coef(L.scale_y, y, L.sh, oy, cy0, cy1, my);
+    const uint8_t* a = L.src + (size_t)oy * L.sw;
+    const uint8_t* bb = L.src + (size_t)min(oy + 1, L.sh - 1) * L.sw;
+    const int xn = min(ox + 1, L.sw - 1);
+    const uint32_t val = ((uint32_t)a[ox] * cx0 + (uint32_t)a[xn] * cx1) * (uint32_t)cy0 + ((uint32_t)bb[ox] * cx0 + (uint32_t)bb[xn] * cx1) * (uint32_t)cy1;
+    dst[t] = (uint8_t)((val + 32768u) >> 16);
   }
 }
 
@@ -639,7 +794,11 @@ struct MineState {
   unsigned int* h_bitmap = nullptr;
   size_t bitmap_cap = 0;
   bool shard_images = true;            // when an NCCL communicator is attached
-  std::vector<LevelDesc> dev_levels;   // fast path: the batch's levels cut into strips, as uploaded to d_levels
+  std::vector<LevelDesc> dev_levels;   // fast path: the batch's levels (tile miner) or their strips (plane path), as uploaded to d_levels
+  std::vector<TileDesc> tiles;
+  TileDesc* d_tiles = nullptr;
+  int tiles_cap = 0;
+  int mode = 0;                        // cc_mine_set_mode
 };
 
 static void free_cascade(MineState* m) {
@@ -660,6 +819,7 @@ static void free_scratch(MineState* m) {
   cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts); cudaFree(m->d_order);
   m->d_list[0] = m->d_list[1] = m->d_counts = nullptr; m->list_cap = 0; m->d_order = nullptr; m->order_cap = 0;
   cudaFree(m->d_bitmap); cudaFreeHost(m->h_bitmap); m->d_bitmap = nullptr; m->h_bitmap = nullptr; m->bitmap_cap = 0;
+  cudaFree(m->d_tiles); m->d_tiles = nullptr; m->tiles_cap = 0;
 }
 
 int mine_free(cc_ctx* ctx) {
@@ -908,6 +1068,138 @@ static bool use_level_path(const cc_ctx* ctx, const MineState* m) {
   return !m->force_slots && !m->stages.empty() && (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) && ctx->W <= 255 && ctx->H <= 255;
 }
 
+// survivors of a batch -> ascending ordinals on the host.  Image-sharded: the ranks' (disjoint) survivor sets are merged
+// as bitmaps summed over NCCL, so every rank ends up with the same ordered list.
+static int collect_survivors(cc_ctx* ctx, MineState* m, bool sharded, long long nwin, const unsigned int* d_count, const unsigned int* d_list,
+                             std::vector<unsigned>& survivors) {
+  if (sharded) {
+    const size_t words = ((size_t)nwin + 31) / 32;
+    if (words > m->bitmap_cap) {
+      cudaFree(m->d_bitmap); cudaFreeHost(m->h_bitmap);
+      const size_t cap = words + words / 4 + 64;
+      CC_CUDA(cudaMalloc(&m->d_bitmap, cap * 4)); CC_CUDA(cudaMallocHost(&m->h_bitmap, cap * 4));
+      m->bitmap_cap = cap;
+    }
+    CC_CUDA(cudaMemsetAsync(m->d_bitmap, 0, words * 4, ctx->stream));
+    k_list_to_bitmap<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(d_list, d_count, m->d_bitmap);
+    CC_CUDA(cudaGetLastError());
+    ctx->launches += 1;
+    CC_CHECK(allreduce_sum(ctx, m->d_bitmap, words, /*uint32*/ 4));
+    CC_CUDA(cudaMemcpyAsync(m->h_bitmap, m->d_bitmap, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t w = 0; w < words; ++w) {
+      unsigned int bits = m->h_bitmap[w];
+      while (bits) { const int k = __builtin_ctz(bits); bits &= bits - 1; survivors.push_back((unsigned)(w * 32 + k)); }
+    }
+    return CC_OK;
+  }
+  CC_CUDA(cudaMemcpyAsync(m->h_surv, d_count, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const unsigned cnt = m->h_surv[0];
+  if (cnt) {
+    CC_CUDA(cudaMemcpyAsync(m->h_surv + 1, d_list, sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    survivors.assign(m->h_surv + 1, m->h_surv + 1 + cnt);
+    std::sort(survivors.begin(), survivors.end());
+  }
+  return CC_OK;
+}
+
+static int ensure_lists(cc_ctx* ctx, MineState* m, long long nwin) {
+  if ((size_t)nwin > m->list_cap) {
+    cudaFree(m->d_list[0]); cudaFree(m->d_list[1]);
+    const size_t cap = (size_t)nwin + (size_t)nwin / 4;
+    CC_CUDA(cudaMalloc(&m->d_list[0], cap * 4)); CC_CUDA(cudaMalloc(&m->d_list[1], cap * 4));
+    m->list_cap = cap;
+    cudaFreeHost(m->h_surv); m->h_surv = nullptr;
+    CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (cap + 1)));
+  }
+  if (!m->h_surv) CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (m->list_cap + 1)));
+  if (!m->d_counts) CC_CUDA(cudaMalloc(&m->d_counts, sizeof(unsigned) * 16));
+  return CC_OK;
+}
+
+// Tile geometry of the fused miner: TW x TH windows per CTA such that the tile's planes fit ~100 KB (two CTAs per SM)
+struct TileGeom { int TW, TH, tpw, tph, pp; size_t smem; bool ok; };
+static TileGeom tile_geometry(const cc_ctx* ctx, bool want_sq, bool want_tilted) {
+  TileGeom g{};
+  const int sx = std::max(1, (int)(0.5F * ctx->W)), sy = std::max(1, (int)(0.5F * ctx->H));
+  const int nplanes = 1 + (want_sq ? 1 : 0) + (want_tilted ? 1 : 0);
+  for (int t = 8; t >= 1; --t) {
+    const int tpw = (t - 1) * sx + ctx->W, tph = (t - 1) * sy + ctx->H;
+    const int pp = (tpw + 1) | 1;                  // odd pitch: column, row and diagonal walks are bank-conflict-free
+    const size_t smem = (size_t)nplanes * pp * (tph + 1) * 4 + (size_t)((tpw * tph + 3) & ~3) + (size_t)(tpw + tph) * 4;
+    if (smem <= 100 * 1024 || (t == 1 && smem <= 200 * 1024)) { g = TileGeom{t, t, tpw, tph, pp, smem, true}; return g; }
+  }
+  return g;
+}
+
+// Fused tile miner: levels of the batch -> tiles -> k_tile_cascade; returns the sorted surviving batch ordinals
+static int eval_tiles(cc_ctx* ctx, MineState* m, Batch& bt, const TileGeom& g, std::vector<unsigned>& survivors) {
+  survivors.clear();
+  if (bt.nwin == 0) return CC_OK;
+  const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
+  const bool haar = ctx->ftype == CC_FEATURE_HAAR;
+  const bool tilted = haar && m->cascade_tilted;
+  std::vector<LevelDesc>& dl = m->dev_levels;
+  std::vector<TileDesc>& tiles = m->tiles;
+  dl.clear(); tiles.clear();
+  {
+    int img_ord = -1;
+    const uint8_t* prev = nullptr;
+    for (const LevelDesc& L : bt.levels) {
+      if (L.src != prev) { ++img_ord; prev = L.src; }
+      if (sharded && (img_ord % ctx->comm_world) != ctx->comm_rank) continue;      // image-sharded mining: another rank's image
+      const int li = (int)dl.size();
+      dl.push_back(L);
+      const long long k_lo = L.w_skip, k_hi = L.w_skip + L.w_count;
+      for (int ty = 0; ty * g.TH < L.ny; ++ty) {
+        const long long r_lo = (long long)ty * g.TH * L.nx, r_hi = (long long)std::min(L.ny, (ty + 1) * g.TH) * L.nx;
+        if (r_hi <= k_lo || r_lo >= k_hi) continue;                               // tile row outside the part of the level taken by the batch
+        for (int tx = 0; tx * g.TW < L.nx; ++tx) tiles.push_back(TileDesc{li, tx, ty});
+      }
+    }
+  }
+  const int nlv = (int)dl.size(), ntiles = (int)tiles.size();
+  if (nlv > m->levels_cap) { cudaFree(m->d_levels); CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * nlv * 2)); m->levels_cap = nlv * 2; }
+  if (ntiles > m->tiles_cap) { cudaFree(m->d_tiles); CC_CUDA(cudaMalloc(&m->d_tiles, sizeof(TileDesc) * ntiles * 2)); m->tiles_cap = ntiles * 2; }
+  CC_CHECK(ensure_lists(ctx, m, bt.nwin));
+  if (nlv) CC_CUDA(cudaMemcpyAsync(m->d_levels, dl.data(), sizeof(LevelDesc) * nlv, cudaMemcpyHostToDevice, ctx->stream));
+  if (ntiles) CC_CUDA(cudaMemcpyAsync(m->d_tiles, tiles.data(), sizeof(TileDesc) * ntiles, cudaMemcpyHostToDevice, ctx->stream));
+  CC_CUDA(cudaMemsetAsync(m->d_counts, 0, sizeof(unsigned) * 16, ctx->stream));
+  if (ntiles) {
+    ScopedTimer tm(ctx, "mine", 1);
+    CascadeArgs A;
+    A.pl = LvlPlanes{nullptr, nullptr, nullptr};
+    A.ftype = ctx->ftype; A.W = ctx->W; A.H = ctx->H;
+    A.nodes = m->d_nodes; A.feats = m->d_lfeats; A.tree_first = m->d_tree_first; A.stages = m->d_stages;
+    A.s_begin = 0; A.s_end = (int)m->stages.size();
+    CC_CUDA(cudaFuncSetAttribute(k_tile_cascade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    k_tile_cascade<<<ntiles, 256, g.smem, ctx->stream>>>(m->d_levels, m->d_tiles, g.TW, g.TH, g.tpw, g.tph, g.pp, haar ? 1 : 0, tilted ? 1 : 0, A,
+                                                          m->d_counts, m->d_list[0]);
+    CC_CUDA(cudaGetLastError());
+  }
+  return collect_survivors(ctx, m, sharded, bt.nwin, m->d_counts, m->d_list[0], survivors);
+}
+
+// fused tile miner: accepted windows recomputed from the source images into training slots [first, first+n)
+static int gather_accepted_resize(cc_ctx* ctx, MineState* m, const unsigned* which, int n, int first, int label) {
+  if (n == 0) return CC_OK;
+  const int npx = ctx->W * ctx->H;
+  CC_CUDA(cudaMemcpyAsync(m->d_list[1], which, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
+  {
+    ScopedTimer tm(ctx, "mine", 1);
+    k_gather_resize<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)m->dev_levels.size(), ctx->W, ctx->H, m->d_list[1], n,
+                                                                                    ctx->d_imgs + (size_t)first * npx, ctx->d_labels + first, label);
+    CC_CUDA(cudaGetLastError());
+  }
+  if (ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images) CC_CHECK(allreduce_sum(ctx, ctx->d_imgs + (size_t)first * npx, (size_t)n * npx, /*uint8*/ 1));
+  ctx->precalc_valid = false;
+  CC_CHECK(launch_integrals(ctx, main_store(ctx), first, n));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  return CC_OK;
+}
+
 // Fast path: build the levels and their integral planes, run the cascade in stage groups over the shrinking survivor
 // list, return the sorted surviving batch ordinals.  The level pixels stay in m->d_pool for gather_accepted().
 static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigned>& survivors) {
@@ -1051,37 +1343,7 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
     ctx->launches += launches;
     if (ctx->timing_enabled) ctx->timers["mine"].launches += launches;
   }
-  if (sharded) {
-    const size_t words = ((size_t)bt.nwin + 31) / 32;
-    if (words > m->bitmap_cap) {
-      cudaFree(m->d_bitmap); cudaFreeHost(m->h_bitmap);
-      const size_t cap = words + words / 4 + 64;
-      CC_CUDA(cudaMalloc(&m->d_bitmap, cap * 4)); CC_CUDA(cudaMallocHost(&m->h_bitmap, cap * 4));
-      m->bitmap_cap = cap;
-    }
-    CC_CUDA(cudaMemsetAsync(m->d_bitmap, 0, words * 4, ctx->stream));
-    k_list_to_bitmap<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1, m->d_bitmap);
-    CC_CUDA(cudaGetLastError());
-    ctx->launches += 1;
-    CC_CHECK(allreduce_sum(ctx, m->d_bitmap, words, /*uint32*/ 4));
-    CC_CUDA(cudaMemcpyAsync(m->h_bitmap, m->d_bitmap, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CC_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (size_t w = 0; w < words; ++w) {
-      unsigned int bits = m->h_bitmap[w];
-      while (bits) { const int k = __builtin_ctz(bits); bits &= bits - 1; survivors.push_back((unsigned)(w * 32 + k)); }
-    }
-    return CC_OK;
-  }
-  CC_CUDA(cudaMemcpyAsync(m->h_surv, m->d_counts + ngroups - 1, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-  CC_CUDA(cudaStreamSynchronize(ctx->stream));
-  const unsigned cnt = m->h_surv[0];
-  if (cnt) {
-    CC_CUDA(cudaMemcpyAsync(m->h_surv + 1, m->d_list[(ngroups - 1) & 1], sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    CC_CUDA(cudaStreamSynchronize(ctx->stream));
-    survivors.assign(m->h_surv + 1, m->h_surv + 1 + cnt);
-    std::sort(survivors.begin(), survivors.end());
-  }
-  return CC_OK;
+  return collect_survivors(ctx, m, sharded, bt.nwin, m->d_counts + ngroups - 1, m->d_list[(ngroups - 1) & 1], survivors);
 }
 
 // fast path: copy accepted windows (batch ordinals) from the level pool into training slots [first, first+n), build integrals
@@ -1177,8 +1439,9 @@ int cc_bg_register(cc_ctx* ctx, const uint8_t* host_gray, int w, int h) {
 }
 
 int cc_mine_set_mode(cc_ctx* ctx, int mode) {
-  CC_REQUIRE(ctx && mode >= 0 && mode <= 2, CC_ERR_BAD_ARG, "cc_mine_set_mode: mode must be 0 (auto), 1 (level planes, unfused kernels) or 2 (per-window slots)");
+  CC_REQUIRE(ctx && mode >= 0 && mode <= 3, CC_ERR_BAD_ARG, "cc_mine_set_mode: mode must be 0 (auto: level planes, fused builder), 1 (level planes, separate kernels), 2 (per-window slots) or 3 (fused tile miner)");
   MineState* m = mine_state(ctx);
+  m->mode = mode;
   m->force_unfused = mode == 1;
   m->force_slots = mode == 2;
   return CC_OK;
@@ -1212,6 +1475,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   int got = 0;
   double accept_rate = m->stages.empty() ? 1.0 : 0.0;   // running estimate
   const bool level_path = use_level_path(ctx, m);
+  const TileGeom tgeom = tile_geometry(ctx, ctx->ftype == CC_FEATURE_HAAR, ctx->ftype == CC_FEATURE_HAAR && m->cascade_tilted);
+  const bool tile_path = level_path && m->mode == 3 && tgeom.ok;
   const long long max_batch = level_path ? level_path_max_batch(ctx, m) : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
   bool stream_ok = true;
   if (ns.lw == 0) stream_ok = ns.nextImg();             // first get(): img.empty() -> nextImg()
@@ -1290,13 +1555,15 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       if (taken < take_direct) { /* ratio rule fired */ }
       if (got < count && taken == nwin) { ns = bt.after.back(); stream_ok = more; continue; }
     } else {
-      if (level_path) CC_CHECK(eval_levels(ctx, m, bt, survivors));
+      if (level_path && tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
+      else if (level_path) CC_CHECK(eval_levels(ctx, m, bt, survivors));
       else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
       // ---- serial stopping rule over the ordered survivors ----
       bool stopped = false;
       const long long pos = serial_cut(survivors.data(), survivors.size(), nwin, count, min_ratio, consumed, got, accepted, stopped);
       stop_after = pos - 1;
-      if (level_path) CC_CHECK(gather_accepted(ctx, m, bt, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
+      if (level_path && tile_path) CC_CHECK(gather_accepted_resize(ctx, m, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
+      else if (level_path) CC_CHECK(gather_accepted(ctx, m, bt, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
       else CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
       if (nwin > 0) accept_rate = std::max((double)survivors.size() / (double)nwin, 1e-9);
       if (!stopped) { ns = bt.after.back(); stream_ok = more; continue; }
@@ -1424,6 +1691,8 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
   CC_CUDA(cudaSetDevice(ctx->device));
   const int W = ctx->W, H = ctx->H, npx = W * H;
   const bool level_path = use_level_path(ctx, m);
+  const TileGeom tgeom = tile_geometry(ctx, ctx->ftype == CC_FEATURE_HAAR, ctx->ftype == CC_FEATURE_HAAR && m->cascade_tilted);
+  const bool tile_path = level_path && m->mode == 3 && tgeom.ok;
   const long long max_batch = level_path ? level_path_max_batch(ctx, m) : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
   long long total = 0, surv = 0;
   std::vector<unsigned> survivors;
@@ -1434,7 +1703,8 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
     if (bt.nwin == 0) return CC_OK;
     const int nwin = (int)bt.nwin;
     if (level_path) {
-      CC_CHECK(eval_levels(ctx, m, bt, survivors));
+      if (tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
+      else CC_CHECK(eval_levels(ctx, m, bt, survivors));
       total += nwin; surv += (long long)survivors.size();
       bt = Batch();
       return CC_OK;

@@ -509,9 +509,11 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
 
 template <int SORT_KPT>
 __global__ void __launch_bounds__(SORT_THREADS, 1)
-k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint16_t* __restrict__ sidx, float* __restrict__ sval) {
+k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint16_t* __restrict__ sidx, float* __restrict__ sval,
+            const int* __restrict__ row_list, const unsigned int* __restrict__ row_count) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CAP = SORT_THREADS * SORT_KPT;
+  if (row_list) nrows = (int)*row_count;               // second pass of the bucket sort: only the rows it deferred
   uint32_t* fullkey = reinterpret_cast<uint32_t*>(smem_raw);               // [CAP] by sample index
   uint32_t* pk = fullkey + CAP;                                             // [CAP] packed (key half << 16) | index, by position
   uint32_t* cnt = pk + CAP;                                            // [16][SORT_THREADS], padded (sort_cnt_slot)
@@ -520,7 +522,8 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   uint32_t* mine = pk + t * SORT_KPT;
 
-  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+  for (int r = blockIdx.x; r < nrows; r += gridDim.x) {
+    const int row = row_list ? row_list[r] : r;
     const float* src = fval + (size_t)row * n_stride;
     __syncthreads();                                   // the previous row's output gathers are done
     for (int i = t; i < CAP; i += SORT_THREADS) {
@@ -602,6 +605,166 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// K3, first pass for Haar rows: bucket + rank sort.  The canonical order (value ascending, ties by ascending sample
+// index) is the order of the 48-bit composites (key << 16) | index, which are all distinct -- so nothing has to be
+// stable, and one distribution pass into many value buckets followed by an exact ranking inside each bucket replaces
+// the eight stable radix passes:
+//   A  load the row (registers), row statistics -> a monotone linear bucket map  b(v) = clamp((v - lo) * scale)
+//      over [mean - 3.5 sd, mean + 3.5 sd] ∩ [min, max]  (any lo / scale gives a correct sort; float subtraction,
+//      multiplication by a positive constant and truncation are monotone, so b is non-decreasing in v);
+//   B  bucket histogram (shared-memory atomics);   C  exclusive scan of the B counters + the cost sum(k^2);
+//   D  distribution: slot = atomicAdd(cursor[b]), composite stored there (order inside a bucket is arbitrary);
+//   E  rank: position = bucket start + #(composites of the bucket smaller than mine); the index and the value go
+//      straight to their final place in HBM (a warp writes a permutation of 32 consecutive positions).
+// With B ~ N / 2 buckets a row costs ~ N * (k_avg + const) compares instead of 8 passes over N.  Rows where the map
+// is poor (sum(k^2) above a limit: long runs of equal values, outliers far beyond 3.5 sd) are appended to a list and
+// sorted by k_sort_rows afterwards.  Output is bit-identical to k_sort_rows (test_sort_paths_agree).
+// ------------------------------------------------------------------------------------------------
+template <int KPT> struct BucketCfg { static constexpr int B = KPT <= 7 ? 4096 : 8192; };     // a multiple of 4 * SORT_THREADS (uint4 scan)
+template <int KPT> static size_t bsort_smem() { return (size_t)SORT_THREADS * KPT * 8 + (size_t)BucketCfg<KPT>::B * 4; }
+
+template <int KPT>
+__global__ void __launch_bounds__(SORT_THREADS, 1)
+k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrows, uint16_t* __restrict__ sidx, float* __restrict__ sval,
+                   int* __restrict__ hard_rows, unsigned int* __restrict__ hard_count, float hard_limit) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int CAP = SORT_THREADS * KPT;
+  constexpr int B = BucketCfg<KPT>::B;
+  constexpr int CPT = B / SORT_THREADS;                                   // counters per thread in the scan
+  unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw);     // [CAP] composites, by bucket after phase D
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(comp + CAP);                         // [B] counts -> cursors -> bucket ends
+  __shared__ float red[4][SORT_WARPS];
+  __shared__ uint32_t warp_tot[SORT_WARPS];
+  __shared__ float warp_cost[SORT_WARPS];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const float* src = fval + (size_t)row * n_stride;
+    // ---- A: load, statistics ----
+    float v[KPT];
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f, sm = 0.f, sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int i = t + k * SORT_THREADS;
+      v[k] = i < N ? __ldcs(src + i) + 0.0f : 0.f;                          // -0 -> +0 (as float_to_key)
+    }
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      if (t + k * SORT_THREADS < N) { mn = fminf(mn, v[k]); mx = fmaxf(mx, v[k]); sm += v[k]; sq = fmaf(v[k], v[k], sq); }
+    }
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      sm += __shfl_xor_sync(0xffffffffu, sm, d); sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    }
+    __syncthreads();                                   // the previous row's ranking has finished reading comp / cnt
+    if (lane == 0) { red[0][warp] = mn; red[1][warp] = mx; red[2][warp] = sm; red[3][warp] = sq; }
+    {
+      uint4* c4 = reinterpret_cast<uint4*>(cnt);
+      for (int i = t; i < B / 4; i += SORT_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    mn = red[0][lane]; mx = red[1][lane]; sm = red[2][lane]; sq = red[3][lane];
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+      mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, d)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+      sm += __shfl_xor_sync(0xffffffffu, sm, d); sq += __shfl_xor_sync(0xffffffffu, sq, d);
+    }
+    float lo, scale;
+    {
+      const float inv_n = 1.0f / (float)N;
+      const float mean = sm * inv_n;
+      const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
+      const float sd = sqrtf(var);
+      float a = mean - 3.5f * sd, b = mean + 3.5f * sd;
+      if (!(a > mn)) a = mn;                           // also taken when the statistics overflowed (inf / nan)
+      if (!(b < mx)) b = mx;
+      const float w = b - a;
+      lo = a;
+      scale = (w > 0.f && w < 3.0e38f) ? (float)B / w : 0.f;
+      if (!(scale < 3.0e38f)) scale = 0.f;
+    }
+    auto bucket_of = [&](float x) -> int {
+      const int b = __float2int_rz((x - lo) * scale);
+      return min(max(b, 0), B - 1);
+    };
+    // ---- B: histogram ----
+#pragma unroll
+    for (int k = 0; k < KPT; ++k)
+      if (t + k * SORT_THREADS < N) atomicAdd(&cnt[bucket_of(v[k])], 1u);
+    __syncthreads();
+    // ---- C: exclusive scan of the counters (thread t owns [CPT*t, CPT*t + CPT)), cost = sum k^2 ----
+    float cost;
+    {
+      uint32_t w[CPT];
+      uint32_t sum = 0;
+      float c2 = 0.f;
+      const uint4* c4 = reinterpret_cast<const uint4*>(cnt + CPT * t);
+#pragma unroll
+      for (int q = 0; q < CPT / 4; ++q) { const uint4 x = c4[q]; w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w; }
+#pragma unroll
+      for (int k = 0; k < CPT; ++k) { sum += w[k]; c2 = fmaf((float)w[k], (float)w[k], c2); }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += x; }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, d);
+      if (lane == 31) warp_tot[warp] = incl;
+      if (lane == 0) warp_cost[warp] = c2;
+      __syncthreads();
+      uint32_t wt = warp_tot[lane];
+      cost = warp_cost[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wt, d); if (lane >= d) wt += x; }
+#pragma unroll
+      for (int d = 16; d; d >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, d);
+      const uint32_t wbase = __shfl_sync(0xffffffffu, wt, (warp + 31) & 31);
+      uint32_t run = (warp ? wbase : 0u) + incl - sum;
+      uint4* o4 = reinterpret_cast<uint4*>(cnt + CPT * t);
+#pragma unroll
+      for (int q = 0; q < CPT / 4; ++q) {
+        uint4 x;
+        x.x = run; run += w[4 * q]; x.y = run; run += w[4 * q + 1]; x.z = run; run += w[4 * q + 2]; x.w = run; run += w[4 * q + 3];
+        o4[q] = x;
+      }
+    }
+    if (cost > hard_limit) {                           // uniform over the CTA: defer the row to the radix kernel
+      if (t == 0) hard_rows[atomicAdd(hard_count, 1u)] = row;
+      continue;
+    }
+    __syncthreads();
+    // ---- D: distribution ----
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) {
+      const int i = t + k * SORT_THREADS;
+      if (i < N) {
+        const uint32_t p = atomicAdd(&cnt[bucket_of(v[k])], 1u);
+        comp[p] = ((unsigned long long)float_to_key(v[k]) << 16) | (unsigned long long)i;
+      }
+    }
+    __syncthreads();
+    // ---- E: rank inside the bucket, write out ----
+    uint16_t* drow = sidx + (size_t)row * n_stride;
+    float* vrow = sval + (size_t)row * n_stride;
+#pragma unroll 1
+    for (int p = t; p < N; p += SORT_THREADS) {
+      const unsigned long long c = comp[p];
+      const float x = key_to_float((uint32_t)(c >> 16));
+      const int b = bucket_of(x);
+      const int e = (int)cnt[b];
+      const int s = b ? (int)cnt[b - 1] : 0;
+      int r = s;
+      for (int j = s; j < e; ++j) r += comp[j] < c ? 1 : 0;
+      drow[r] = (uint16_t)(c & 0xFFFFull);
+      __stcs(vrow + r, x);
+    }
+    // row padding up to the split-search tile: index N (an always-zero operand), value +max
+    for (int i = N + t; i < n_stride; i += SORT_THREADS) { drow[i] = (uint16_t)N; vrow[i] = 3.402823466e+38f; }
+  }
+}
+
 __global__ void k_div_check(int steps, unsigned long long seed, long long n, unsigned long long* mismatches) {
   unsigned long long bad = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -633,8 +796,8 @@ __global__ void k_codes_to_float(const uint8_t* __restrict__ codes, int n_stride
 }
 
 int traindata_free(cc_ctx* ctx) {
-  cudaFree(ctx->d_fval); cudaFree(ctx->d_fcode); cudaFree(ctx->d_sidx); cudaFree(ctx->d_sval);
-  ctx->d_fval = nullptr; ctx->d_fcode = nullptr; ctx->d_sidx = nullptr; ctx->d_sval = nullptr;
+  cudaFree(ctx->d_fval); cudaFree(ctx->d_fcode); cudaFree(ctx->d_sidx); cudaFree(ctx->d_sval); cudaFree(ctx->d_hard_rows);
+  ctx->d_fval = nullptr; ctx->d_fcode = nullptr; ctx->d_sidx = nullptr; ctx->d_sval = nullptr; ctx->d_hard_rows = nullptr;
   ctx->cap_rows = ctx->cap_stride = 0;
   ctx->precalc_valid = false;
   return CC_OK;
@@ -650,6 +813,7 @@ static int ensure_traindata(cc_ctx* ctx, int nrows, int n_stride) {
     CC_CUDA(cudaMalloc(&ctx->d_fval, cells * sizeof(float)));
     CC_CUDA(cudaMalloc(&ctx->d_sidx, cells * sizeof(uint16_t)));
     CC_CUDA(cudaMalloc(&ctx->d_sval, cells * sizeof(float)));
+    CC_CUDA(cudaMalloc(&ctx->d_hard_rows, ((size_t)nrows + 1) * sizeof(int)));      // [0] = count, [1..] = rows deferred by the bucket sort
   }
   ctx->cap_rows = nrows; ctx->cap_stride = n_stride;
   return CC_OK;
@@ -878,12 +1042,25 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
 
   if (ctx->ftype != CC_FEATURE_LBP) {   // categorical variables are not sorted (numPrecalcIdx = 0, :267-273)
     CC_REQUIRE(N <= SORT_CAP, CC_ERR_UNSUPPORTED, "sort: numSamples %d exceeds the %d samples one CTA sorts in shared memory", N, SORT_CAP);
-    ScopedTimer tm(ctx, "sort", 1);
     const int blocks = std::min(ctx->nrows, ctx->sm_count);
+    // Haar rows: bucket + rank sort, then the radix kernel on the rows it deferred.  HOG rows (long runs of exact zeros)
+    // and cc_boost_set_sort_mode(ctx, 1): radix kernel on every row.
+    const bool bucket = ctx->sort_mode == 2 || (ctx->sort_mode == 0 && ctx->ftype == CC_FEATURE_HAAR);
+    ScopedTimer tm(ctx, "sort", bucket ? 2 : 1);
+    unsigned int* hard_count = reinterpret_cast<unsigned int*>(ctx->d_hard_rows);
+    int* hard_rows = ctx->d_hard_rows + 1;
+    const float hard_limit = 96.0f * (float)N;        // sum k^2 > 96 N: the ranking would cost more than the radix passes
+    if (bucket) CC_CUDA(cudaMemsetAsync(hard_count, 0, sizeof(unsigned int), ctx->stream));
 #define LAUNCH_SORT(KPT)                                                                                                     \
   {                                                                                                                          \
+    if (bucket) {                                                                                                            \
+      CC_CUDA(cudaFuncSetAttribute(k_sort_rows_bucket<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsort_smem<KPT>())); \
+      k_sort_rows_bucket<KPT><<<blocks, SORT_THREADS, bsort_smem<KPT>(), ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx, ctx->d_sval, \
+                                                                                      hard_rows, hard_count, hard_limit);   \
+    }                                                                                                                        \
     CC_CUDA(cudaFuncSetAttribute(k_sort_rows<KPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sort_smem(KPT)));       \
-    k_sort_rows<KPT><<<blocks, SORT_THREADS, sort_smem(KPT), ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx, ctx->d_sval); \
+    k_sort_rows<KPT><<<blocks, SORT_THREADS, sort_smem(KPT), ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx, ctx->d_sval, \
+                                                                            bucket ? hard_rows : nullptr, bucket ? hard_count : nullptr);   \
   }
     if (N <= SORT_THREADS * 3) LAUNCH_SORT(3)
     else if (N <= SORT_THREADS * 7) LAUNCH_SORT(7)
@@ -893,6 +1070,26 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
     CC_CUDA(cudaGetLastError());
   }
   ctx->precalc_valid = true;
+  return CC_OK;
+}
+
+int cc_boost_set_sort_mode(cc_ctx* ctx, int mode) {
+  CC_REQUIRE(ctx && mode >= 0 && mode <= 2, CC_ERR_BAD_ARG, "cc_boost_set_sort_mode: mode must be 0 (auto), 1 (radix passes) or 2 (bucket + rank)");
+  ctx->sort_mode = mode;
+  return CC_OK;
+}
+
+int cc_boost_get_sort_stats(cc_ctx* ctx, int64_t* deferred_rows) {
+  CC_REQUIRE(ctx && deferred_rows, CC_ERR_BAD_ARG, "cc_boost_get_sort_stats: null argument");
+  CC_REQUIRE(ctx->precalc_valid && ctx->d_hard_rows, CC_ERR_STATE, "cc_boost_get_sort_stats: no sorted rows (precalc not run, or categorical features)");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  const bool bucket = ctx->sort_mode == 2 || (ctx->sort_mode == 0 && ctx->ftype == CC_FEATURE_HAAR);
+  unsigned int h = 0;
+  if (bucket) {
+    CC_CUDA(cudaMemcpyAsync(&h, ctx->d_hard_rows, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  *deferred_rows = (int64_t)h;
   return CC_OK;
 }
 

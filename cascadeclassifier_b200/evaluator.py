@@ -53,6 +53,16 @@ class Context:
         """0 = pruned split search (default), 1 = exhaustive (every variable searched exactly)."""
         check(self.lib.cc_boost_set_search_mode(self.h, int(mode)), "cc_boost_set_search_mode")
 
+    def set_sort_mode(self, mode):
+        """0 = auto (Haar: bucket + rank sort, HOG: radix passes), 1 = radix passes, 2 = bucket + rank."""
+        check(self.lib.cc_boost_set_sort_mode(self.h, int(mode)), "cc_boost_set_sort_mode")
+
+    def sort_deferred_rows(self):
+        """Rows of the last precalc that the bucket sort handed to the radix kernel."""
+        a = C.c_int64(0)
+        check(self.lib.cc_boost_get_sort_stats(self.h, C.byref(a)), "cc_boost_get_sort_stats")
+        return a.value
+
     def search_stats(self):
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
         check(self.lib.cc_boost_get_search_stats(self.h, C.byref(a), C.byref(b), C.byref(c)), "cc_boost_get_search_stats")

@@ -147,6 +147,13 @@ int cc_boost_get_weights(cc_ctx* ctx, double* weights, uint8_t* mask);
  * serial loop of DTreeBestSplitFinder (src/o_cvdtree.cpp:313-357), whose init_quality threading prunes in the
  * same spirit.  1 = exhaustive: every variable searched exactly (keeps per-variable qualities for the getter). */
 int cc_boost_set_search_mode(cc_ctx* ctx, int mode);
+/* How the sorted-index rows (std::sort + LessThanIdx per feature, src/o_cvcascadeboosttraindata.cpp:490-563) are built.
+ * 0 (default) = Haar: bucket + rank sort (one distribution pass into value buckets, exact ranking inside a bucket) with
+ * the radix kernel on the rows it defers; HOG: radix kernel.  1 = stable LSD radix passes on every row.  2 = bucket +
+ * rank for every ordered feature type.  All modes give the same rows: ascending value, ties by ascending sample index. */
+int cc_boost_set_sort_mode(cc_ctx* ctx, int mode);
+/* rows of the last cc_boost_precalc that the bucket sort deferred to the radix kernel (local slice) */
+int cc_boost_get_sort_stats(cc_ctx* ctx, int64_t* deferred_rows);
 /* counters since cc_create: pruned searches run, rows searched exactly as seeds, rows flagged by the bound pass */
 int cc_boost_get_search_stats(cc_ctx* ctx, int64_t* searches, int64_t* seed_rows, int64_t* flagged_rows);
 /* per-variable best split quality of the LAST root-node search (0 where no split), local rows; exhaustive mode only */
@@ -184,7 +191,10 @@ int cc_mine_positives(cc_ctx* ctx, const uint8_t* host_vec, int vec_count, int c
 /* How predict() is evaluated over the window stream.  0 (default): Haar / LBP windows are evaluated from integral
  * planes of whole pyramid levels built by one fused kernel (same integers as the per-crop cv::integral of setImage,
  * src/haarfeatures.cpp:100-114), HOG from per-window slots.  1: same planes, built by separate row / diagonal /
- * column kernels.  2: per-window slots for every feature type (literal setImage + predict per window). */
+ * column kernels.  2: per-window slots for every feature type (literal setImage + predict per window).  3: fused tile
+ * miner -- a CTA builds a tile of a pyramid level (INTER_LINEAR_EXACT pixels, sum / sqsum / tilted integrals) in shared
+ * memory and runs the cascade on its windows; nothing but survivor ordinals leaves the SM (measured 2.5x slower than
+ * mode 0 on B200: 16 resident warps per SM cannot hide the serial column / diagonal walks). */
 int cc_mine_set_mode(cc_ctx* ctx, int mode);
 /* NegReader::get() x nwindows without pixels (host only, no GPU needed): advances *state over images of
  * the given sizes; window5 (optional) = x, y, level_w, level_h, source image of the last consumed window. */

@@ -123,9 +123,9 @@ def test_cascade_training_matches_oracle(gpu_ctx, tmp_path, ftype, mode):
 
 @pytest.mark.parametrize("ftype,mode", [(orc.HAAR, orc.ALL), (orc.LBP, 0)])
 def test_mining_paths_agree(gpu_ctx, tmp_path, ftype, mode):
-    """The whole-level integral planes (fused builder, and the separate row/diagonal/column kernels) must select
-    exactly the windows the literal per-window path (setImage + predict on a scratch slot) selects: same consumed
-    count, same reader state, same accepted pixels, same integrals."""
+    """The fused tile miner and the whole-level integral planes (fused builder, and the separate row/diagonal/column
+    kernels) must select exactly the windows the literal per-window path (setImage + predict on a scratch slot) selects:
+    same consumed count, same reader state, same accepted pixels, same integrals."""
     import copy
     import cascadeclassifier_b200 as ccb
     from cascadeclassifier_b200 import _lib
@@ -151,7 +151,7 @@ def test_mining_paths_agree(gpu_ctx, tmp_path, ftype, mode):
     lib, h = gpu_ctx.lib, gpu_ctx.h
     start = copy.copy(cc._reader)
     results = []
-    for m in (2, 1, 0):
+    for m in (2, 1, 3, 0):      # slots (literal), level planes by separate kernels, fused tile miner, level planes by the fused builder
         check(lib.cc_mine_set_mode(h, m), "cc_mine_set_mode")
         st = _lib.ReaderState.from_buffer_copy(bytes(start))
         consumed, got = C.c_int64(0), C.c_int32(0)

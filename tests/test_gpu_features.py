@@ -149,6 +149,58 @@ def test_precalc_and_sort_match_oracle(gpu_ctx, ftype, mode, W, H, npos, nneg):
             assert np.array_equal(gv, np.take_along_axis(td.fval(), td.sidx().astype(np.int64), axis=1))
 
 
+@pytest.mark.parametrize("ftype,mode,W,H,npos,nneg,flat", [(orc.HAAR, orc.ALL, 24, 24, 700, 1500, 0), (orc.HAAR, orc.BASIC, 24, 24, 1200, 2500, 900),
+                                                           (orc.HAAR, orc.CORE, 24, 24, 2500, 5200, 3), (orc.HOG, 0, 48, 96, 300, 500, 0)])
+def test_sort_paths_agree(gpu_ctx, ftype, mode, W, H, npos, nneg, flat):
+    """The bucket + rank sort (with the rows it defers to the radix kernel) writes exactly the rows the stable radix
+    passes write.  `flat` constant windows (norm factor 0 -> value 0 in every row) make long runs of equal values: every
+    row is deferred; a few of them make a tie group inside one bucket; HOG rows hold many exact zeros."""
+    import ctypes as C
+    from cascadeclassifier_b200._lib import check
+    imgs, labels = make_samples(npos, nneg, W, H)
+    imgs = imgs.copy()
+    rng = np.random.default_rng(11)
+    for i in rng.choice(len(imgs), flat, replace=False):
+        imgs[i] = rng.integers(0, 256)
+    n = len(imgs)
+    ev = _gpu_eval(ftype, mode, W, H, n, gpu_ctx)
+    ev.setImages(imgs, labels)
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    F = ev.getNumFeatures() * (36 if ftype == orc.HOG else 1)
+    rows = sorted(set([0, F - 256] + [int(x) for x in rng.integers(0, F - 256, 8)]))
+    out = {}
+    try:
+        for sm in (1, 2):
+            gpu_ctx.set_sort_mode(sm)
+            check(lib.cc_boost_precalc(h, n), "precalc")
+            if sm == 2:
+                deferred = gpu_ctx.sort_deferred_rows()
+                assert 0 <= deferred <= F
+                if flat >= 900:
+                    assert deferred == F          # 900 equal values: sum k^2 >= 810000 > 96 N
+                if ftype == orc.HAAR and flat <= 3:
+                    assert deferred < F // 4      # the bucket path is the one under test
+            got = []
+            for r0 in rows:
+                gi = np.zeros((256, n), np.uint16)
+                gv = np.zeros((256, n), np.float32)
+                check(lib.cc_boost_get_sorted_idx(h, r0, 256, gi.ctypes.data_as(C.c_void_p)), "get_sidx")
+                check(lib.cc_boost_get_sorted_val(h, r0, 256, gv.ctypes.data_as(C.c_void_p)), "get_sval")
+                got.append((gi, gv))
+            out[sm] = got
+    finally:
+        gpu_ctx.set_sort_mode(0)
+    for (ai, av), (bi, bv) in zip(out[1], out[2]):
+        assert np.array_equal(ai, bi)
+        assert np.array_equal(av.view(np.uint32), bv.view(np.uint32))
+    # and both are the canonical order
+    gi, gv = out[2][0]
+    fv = np.zeros((256, n), np.float32)
+    check(lib.cc_boost_get_fval(h, rows[0], 256, fv.ctypes.data_as(C.c_void_p)), "get_fval")
+    for k in range(0, 256, 17):
+        assert np.array_equal(gi[k].astype(np.int64), np.argsort(fv[k], kind="stable"))
+
+
 def test_fast_division_is_exact(gpu_ctx):
     """The reciprocal-based Haar division of K2 equals IEEE division on 2e9 (integer, norm-factor) pairs."""
     import ctypes as C

@@ -17,6 +17,8 @@ ev = ccb.CvFeatureEvaluator.create(0, ctx)
 fp = ccb.CvHaarFeatureParams(mode)
 n = len(imgs)
 ev.init(fp, n, (24, 24))
+if os.environ.get("CC_SORT_MODE"):
+    ctx.set_sort_mode(int(os.environ["CC_SORT_MODE"]))
 for rep in range(3):
     ctx.timing_reset()
     st0 = ctx.search_stats() if rep else dict(searches=0, seed_rows=0, flagged_rows=0)
@@ -35,7 +37,7 @@ for rep in range(3):
         if name == "precalc":
             extra = " -> %.3g evals/s, %.1f%% of 6547.8 GB/s" % (F * n / (ms * 1e-3), F * n * 4 / (ms * 1e-3) / 6547.8e9 * 100)
         if name == "sort":
-            extra = " -> %.1f%% of HBM roofline (6 B/elem)" % (F * n * 6 / (ms * 1e-3) / 6547.8e9 * 100)
+            extra = " -> %.1f%% of HBM roofline (6 B/elem), %d rows deferred to the radix kernel" % (F * n * 6 / (ms * 1e-3) / 6547.8e9 * 100, ctx.sort_deferred_rows())
         if name == "split_search" and k:
             st1 = ctx.search_stats()
             ns = max(1, st1["searches"] - st0["searches"])
