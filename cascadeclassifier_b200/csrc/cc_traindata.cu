@@ -622,8 +622,8 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
 // is poor (sum(k^2) above a limit: long runs of equal values, outliers far beyond 3.5 sd) are appended to a list and
 // sorted by k_sort_rows afterwards.  Output is bit-identical to k_sort_rows (test_sort_paths_agree).
 // ------------------------------------------------------------------------------------------------
-template <int KPT> struct BucketCfg { static constexpr int B = KPT <= 7 ? 4096 : 8192; };     // a multiple of 4 * SORT_THREADS (uint4 scan)
-template <int KPT> static size_t bsort_smem() { return (size_t)SORT_THREADS * KPT * 8 + (size_t)BucketCfg<KPT>::B * 4; }
+template <int KPT> struct BucketCfg { static constexpr int B = KPT <= 3 ? 4096 : KPT <= 7 ? 8192 : 16384; };     // a multiple of 4 * SORT_THREADS (uint4 scan)
+template <int KPT> static size_t bsort_smem() { return (size_t)(SORT_THREADS * KPT + 8) * 8 + (size_t)BucketCfg<KPT>::B * 4; }
 
 template <int KPT>
 __global__ void __launch_bounds__(SORT_THREADS, 1)
@@ -634,25 +634,29 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
   constexpr int B = BucketCfg<KPT>::B;
   constexpr int CPT = B / SORT_THREADS;                                   // counters per thread in the scan
   unsigned long long* comp = reinterpret_cast<unsigned long long*>(smem_raw);     // [CAP] composites, by bucket after phase D
-  uint32_t* cnt = reinterpret_cast<uint32_t*>(comp + CAP);                         // [B] counts -> cursors -> bucket ends
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(comp + CAP + 8);                     // [B] counts -> cursors -> bucket ends
   __shared__ float red[4][SORT_WARPS];
   __shared__ uint32_t warp_tot[SORT_WARPS];
   __shared__ float warp_cost[SORT_WARPS];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
-  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+  // every position k < KPT - 1 of a thread is a real element when N covers KPT - 1 full strides (uniform)
+  const bool full = N >= (KPT - 1) * SORT_THREADS;
+  auto valid = [&](int k) -> bool { return (k < KPT - 1 && full) || t + k * SORT_THREADS < N; };
+  float v[KPT];
+  auto load_row = [&](int row) {
     const float* src = fval + (size_t)row * n_stride;
-    // ---- A: load, statistics ----
-    float v[KPT];
+#pragma unroll
+    for (int k = 0; k < KPT; ++k) v[k] = valid(k) ? __ldcs(src + t + k * SORT_THREADS) : 0.f;
+  };
+  if ((int)blockIdx.x < nrows) load_row(blockIdx.x);
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    // ---- A: statistics of the row loaded during the previous row's ranking ----
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f, sm = 0.f, sq = 0.f;
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
-      const int i = t + k * SORT_THREADS;
-      v[k] = i < N ? __ldcs(src + i) + 0.0f : 0.f;                          // -0 -> +0 (as float_to_key)
-    }
-#pragma unroll
-    for (int k = 0; k < KPT; ++k) {
-      if (t + k * SORT_THREADS < N) { mn = fminf(mn, v[k]); mx = fmaxf(mx, v[k]); sm += v[k]; sq = fmaf(v[k], v[k], sq); }
+      v[k] += 0.0f;                                                         // -0 -> +0 (as float_to_key)
+      if (valid(k)) { mn = fminf(mn, v[k]); mx = fmaxf(mx, v[k]); sm += v[k]; sq = fmaf(v[k], v[k], sq); }
     }
 #pragma unroll
     for (int d = 16; d; d >>= 1) {
@@ -693,26 +697,37 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
     // ---- B: histogram ----
 #pragma unroll
     for (int k = 0; k < KPT; ++k)
-      if (t + k * SORT_THREADS < N) atomicAdd(&cnt[bucket_of(v[k])], 1u);
+      if (valid(k)) atomicAdd(&cnt[bucket_of(v[k])], 1u);
     __syncthreads();
-    // ---- C: exclusive scan of the counters (thread t owns [CPT*t, CPT*t + CPT)), cost = sum k^2 ----
+    // ---- C: exclusive scan of the counters, cost = sum k^2.  Warp w owns the CPT * 32 consecutive counters behind
+    // cnt + w * CPT * 32, as Q = CPT / 4 groups of 128; lane l holds counters [4l, 4l + 4) of every group (consecutive
+    // lanes read consecutive 16-byte words: conflict-free). ----
     float cost;
     {
-      uint32_t w[CPT];
-      uint32_t sum = 0;
+      constexpr int Q = CPT / 4;
+      uint4* c4 = reinterpret_cast<uint4*>(cnt + warp * (CPT * 32)) + lane;
+      uint4 g[Q];
+      uint32_t incl[Q], gs[Q], base[Q];
       float c2 = 0.f;
-      const uint4* c4 = reinterpret_cast<const uint4*>(cnt + CPT * t);
 #pragma unroll
-      for (int q = 0; q < CPT / 4; ++q) { const uint4 x = c4[q]; w[4 * q] = x.x; w[4 * q + 1] = x.y; w[4 * q + 2] = x.z; w[4 * q + 3] = x.w; }
+      for (int q = 0; q < Q; ++q) {
+        g[q] = c4[q * 32];
+        gs[q] = g[q].x + g[q].y + g[q].z + g[q].w;
+        incl[q] = gs[q];
+        c2 = fmaf((float)g[q].x, (float)g[q].x, c2); c2 = fmaf((float)g[q].y, (float)g[q].y, c2);
+        c2 = fmaf((float)g[q].z, (float)g[q].z, c2); c2 = fmaf((float)g[q].w, (float)g[q].w, c2);
+      }
 #pragma unroll
-      for (int k = 0; k < CPT; ++k) { sum += w[k]; c2 = fmaf((float)w[k], (float)w[k], c2); }
-      uint32_t incl = sum;
+      for (int d = 1; d < 32; d <<= 1) {
 #pragma unroll
-      for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += x; }
+        for (int q = 0; q < Q; ++q) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl[q], d); if (lane >= d) incl[q] += x; }
+      }
+      uint32_t wsum = 0;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) { base[q] = wsum; wsum += __shfl_sync(0xffffffffu, incl[q], 31); }
 #pragma unroll
       for (int d = 16; d; d >>= 1) c2 += __shfl_xor_sync(0xffffffffu, c2, d);
-      if (lane == 31) warp_tot[warp] = incl;
-      if (lane == 0) warp_cost[warp] = c2;
+      if (lane == 0) { warp_tot[warp] = wsum; warp_cost[warp] = c2; }
       __syncthreads();
       uint32_t wt = warp_tot[lane];
       cost = warp_cost[lane];
@@ -720,32 +735,36 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
       for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, wt, d); if (lane >= d) wt += x; }
 #pragma unroll
       for (int d = 16; d; d >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, d);
-      const uint32_t wbase = __shfl_sync(0xffffffffu, wt, (warp + 31) & 31);
-      uint32_t run = (warp ? wbase : 0u) + incl - sum;
-      uint4* o4 = reinterpret_cast<uint4*>(cnt + CPT * t);
+      const uint32_t wbase = warp ? __shfl_sync(0xffffffffu, wt, (warp + 31) & 31) : 0u;
 #pragma unroll
-      for (int q = 0; q < CPT / 4; ++q) {
+      for (int q = 0; q < Q; ++q) {
+        uint32_t run = wbase + base[q] + incl[q] - gs[q];
         uint4 x;
-        x.x = run; run += w[4 * q]; x.y = run; run += w[4 * q + 1]; x.z = run; run += w[4 * q + 2]; x.w = run; run += w[4 * q + 3];
-        o4[q] = x;
+        x.x = run; run += g[q].x; x.y = run; run += g[q].y; x.z = run; run += g[q].z; x.w = run;
+        c4[q * 32] = x;
       }
     }
     if (cost > hard_limit) {                           // uniform over the CTA: defer the row to the radix kernel
       if (t == 0) hard_rows[atomicAdd(hard_count, 1u)] = row;
+      if (row + (int)gridDim.x < nrows) load_row(row + gridDim.x);
       continue;
     }
     __syncthreads();
     // ---- D: distribution ----
+    if (t < 8) comp[N + t] = 0x7FFFFFFFFFFFFFFFull;      // sentinel behind the last bucket (composites are 48-bit, differences stay in int64)
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
-      const int i = t + k * SORT_THREADS;
-      if (i < N) {
+      if (valid(k)) {
         const uint32_t p = atomicAdd(&cnt[bucket_of(v[k])], 1u);
-        comp[p] = ((unsigned long long)float_to_key(v[k]) << 16) | (unsigned long long)i;
+        comp[p] = ((unsigned long long)float_to_key(v[k]) << 16) | (unsigned long long)(t + k * SORT_THREADS);
       }
     }
+    if (row + (int)gridDim.x < nrows) load_row(row + gridDim.x);      // the next row's loads fly during the ranking
     __syncthreads();
-    // ---- E: rank inside the bucket, write out ----
+    // ---- E: rank, write out.  The buckets are in value order, so every composite left of my bucket is smaller than
+    // mine and every one right of it is larger: my final position is w0 + #(smaller composites in [w0, w1)) for ANY
+    // window [w0, w1) that covers the bucket -- the window is widened to 16-byte alignment and whole groups of four
+    // (comp[N .. N+8) holds a sentinel), so there is neither a remainder loop nor a mask. ----
     uint16_t* drow = sidx + (size_t)row * n_stride;
     float* vrow = sval + (size_t)row * n_stride;
 #pragma unroll 1
@@ -754,9 +773,14 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
       const float x = key_to_float((uint32_t)(c >> 16));
       const int b = bucket_of(x);
       const int e = (int)cnt[b];
-      const int s = b ? (int)cnt[b - 1] : 0;
-      int r = s;
-      for (int j = s; j < e; ++j) r += comp[j] < c ? 1 : 0;
+      int j = (b ? (int)cnt[b - 1] : 0) & ~1;
+      uint32_t r = (uint32_t)j;
+#pragma unroll 1
+      for (; j < e; j += 4) {
+        const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(comp + j);
+        const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(comp + j + 2);
+        r += (uint32_t)((q0.x - c) >> 63) + (uint32_t)((q0.y - c) >> 63) + (uint32_t)((q1.x - c) >> 63) + (uint32_t)((q1.y - c) >> 63);
+      }
       drow[r] = (uint16_t)(c & 0xFFFFull);
       __stcs(vrow + r, x);
     }
