@@ -244,9 +244,9 @@ def run_ours(args):
     def roof(kernel, bytes_per_cell, ms, tkey):
         ach = bytes_per_cell * cells / (ms * 1e-3) / 1e9
         return {"kernel": kernel, "bound": "hbm", "achieved": ach, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic.get(tkey), "algorithmic_bytes_per_launch": bytes_per_cell * cells, "ms_per_launch": ms}
+                "traffic": (traffic[tkey] * rows_local / F) if tkey in traffic else None, "algorithmic_bytes_per_launch": bytes_per_cell * cells, "ms_per_launch": ms}
     rooflines = {"precalc": roof("k_precalc_haar_sep + k_precalc_haar", 4.0, pre_ms, "precalc_dram_bytes_per_step"),
-                 "sort": roof("k_sort_rows", 6.0, sort_ms, "sort_dram_bytes_per_launch"),
+                 "sort": roof("k_sort_rows_bucket (+ k_sort_rows on the rows it defers)", 6.0, sort_ms, "sort_dram_bytes_per_launch"),
                  "split_search": roof("k_ss_bound (+ exact search of seed / flagged rows)", 2.0, ss_ms, "split_search_dram_bytes_per_search")}
     dominant = max(("precalc", pre_ms), ("sort", sort_ms), ("split_search", fam["split_search"]["ms_per_step"]), key=lambda kv: kv[1])[0]
     out = {
@@ -258,7 +258,7 @@ def run_ours(args):
                    "parallelism": "feature-sharded x%d" % world},
         "stage_train_s": ms_step * 1e-3,
         "kernels": {"precalc_evals_per_s": cells / (pre_ms * 1e-3), "precalc_frac_of_hbm": rooflines["precalc"]["frac"],
-                    "sort_ms": sort_ms, "split_search_ms_per_node": ss_ms, "split_searches_per_step": searches_per_step,
+                    "sort_ms": sort_ms, "sort_rows_deferred_to_radix": int(ctx.sort_deferred_rows()), "split_search_ms_per_node": ss_ms, "split_searches_per_step": searches_per_step,
                     "rows_searched_exactly_per_node": exact_rows_per_search, "families": fam, "rooflines": rooflines},
         "roofline": rooflines[dominant],
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": int(imgs.nbytes + labels.nbytes),

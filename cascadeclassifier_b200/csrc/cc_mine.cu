@@ -12,6 +12,7 @@
 // copies the accepted windows into the training slots and leaves the reader state right behind the last
 // consumed window.  Evaluating windows past the stopping point is harmless: they are simply not consumed.
 #include <algorithm>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstring>
@@ -1056,13 +1057,29 @@ struct Batch {
 };
 
 // windows the fast path may put in one batch (pyramid pixels ~ 154 per window at 1920x1080 -> ~2 GB of planes)
-constexpr long long LEVEL_PATH_MAX_BATCH = 1 << 20;     // per rank: image-sharded mining scales the batch with the number of ranks
+// per rank (image-sharded mining scales the batch with the number of ranks): 4 M windows = ~8 GB of level pixels + planes.
+// Large batches keep every SM busy through the tail of the builder and amortise the per-batch host round trip.
+constexpr long long LEVEL_PATH_MAX_BATCH = 4 << 20;
 static long long level_path_max_batch(const cc_ctx* ctx, const MineState* m);
 
 static long long level_path_max_batch(const cc_ctx* ctx, const MineState* m) {
   const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
+  static const long long override_batch = [] { const char* e = getenv("CC_MINE_BATCH"); return e ? atoll(e) : 0ll; }();   // experiments only
+  if (override_batch > 0) return override_batch;
   return LEVEL_PATH_MAX_BATCH * (sharded ? std::min(ctx->comm_world, 16) : 1);
 }
+
+// host wall time of the batch loop by phase (cc_timing_get "mine_host_assemble" / "mine_host_eval" / "mine_host_cut"; launches = batches)
+struct HostTimer {
+  cc_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
+  HostTimer(cc_ctx* c, const char* n) : ctx(c), name(n), t0(std::chrono::steady_clock::now()) {}
+  ~HostTimer() {
+    if (!ctx->timing_enabled) return;
+    TimerSlot& s = ctx->timers[name];
+    s.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    s.launches += 1;
+  }
+};
 
 static bool use_level_path(const cc_ctx* ctx, const MineState* m) {
   return !m->force_slots && !m->stages.empty() && (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) && ctx->W <= 255 && ctx->H <= 255;
@@ -1108,7 +1125,7 @@ static int collect_survivors(cc_ctx* ctx, MineState* m, bool sharded, long long 
 static int ensure_lists(cc_ctx* ctx, MineState* m, long long nwin) {
   if ((size_t)nwin > m->list_cap) {
     cudaFree(m->d_list[0]); cudaFree(m->d_list[1]);
-    const size_t cap = (size_t)nwin + (size_t)nwin / 4;
+    const size_t cap = (size_t)nwin + (size_t)nwin / 2;
     CC_CUDA(cudaMalloc(&m->d_list[0], cap * 4)); CC_CUDA(cudaMalloc(&m->d_list[1], cap * 4));
     m->list_cap = cap;
     cudaFreeHost(m->h_surv); m->h_surv = nullptr;
@@ -1257,19 +1274,19 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
   const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
   const bool haar = ctx->ftype == CC_FEATURE_HAAR;
   const bool tilted = haar && m->cascade_tilted;
-  if (pool_px > m->pool_cap) { cudaFree(m->d_pool); CC_CUDA(cudaMalloc(&m->d_pool, pool_px + pool_px / 4)); m->pool_cap = pool_px + pool_px / 4; }
+  if (pool_px > m->pool_cap) { cudaFree(m->d_pool); CC_CUDA(cudaMalloc(&m->d_pool, pool_px + pool_px / 2)); m->pool_cap = pool_px + pool_px / 2; }
   if (nlv > m->levels_cap) { cudaFree(m->d_levels); CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * nlv)); m->levels_cap = nlv; }
   if (plane_elems > m->plane_cap) {
     cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
     m->d_psum = m->d_psq = m->d_ptilt = nullptr;
-    const size_t cap = plane_elems + plane_elems / 4;
+    const size_t cap = plane_elems + plane_elems / 2;
     CC_CUDA(cudaMalloc(&m->d_psum, cap * 4));
     if (haar) { CC_CUDA(cudaMalloc(&m->d_psq, cap * 4)); CC_CUDA(cudaMalloc(&m->d_ptilt, cap * 4)); }
     m->plane_cap = cap;
   }
   if ((size_t)bt.nwin > m->list_cap) {
     cudaFree(m->d_list[0]); cudaFree(m->d_list[1]);
-    const size_t cap = (size_t)bt.nwin + (size_t)bt.nwin / 4;
+    const size_t cap = (size_t)bt.nwin + (size_t)bt.nwin / 2;
     CC_CUDA(cudaMalloc(&m->d_list[0], cap * 4)); CC_CUDA(cudaMalloc(&m->d_list[1], cap * 4));
     m->list_cap = cap;
     cudaFreeHost(m->h_surv); m->h_surv = nullptr;
@@ -1493,6 +1510,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     Batch bt;
     NegStream cur = ns;
     bool more = true;
+    HostTimer* ht = new HostTimer(ctx, "mine_host_assemble");
     while (bt.nwin < want && more) {
       LevelDesc L;
       fill_level(cur, L);
@@ -1517,6 +1535,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       cur = nxt;
       if (L.w_count < avail) break;
     }
+    delete ht;
     const int nwin = (int)bt.nwin;
     // ---- GPU: levels, gather, integrals, cascade ----
     const bool direct = m->stages.empty();       // stage 0: every window passes, gather straight into the training slots
@@ -1555,9 +1574,13 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       if (taken < take_direct) { /* ratio rule fired */ }
       if (got < count && taken == nwin) { ns = bt.after.back(); stream_ok = more; continue; }
     } else {
-      if (level_path && tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
-      else if (level_path) CC_CHECK(eval_levels(ctx, m, bt, survivors));
-      else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
+      {
+        HostTimer he(ctx, "mine_host_eval");
+        if (level_path && tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
+        else if (level_path) CC_CHECK(eval_levels(ctx, m, bt, survivors));
+        else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
+      }
+      HostTimer hc(ctx, "mine_host_cut");
       // ---- serial stopping rule over the ordered survivors ----
       bool stopped = false;
       const long long pos = serial_cut(survivors.data(), survivors.size(), nwin, count, min_ratio, consumed, got, accepted, stopped);

@@ -40,6 +40,9 @@ if rank == 0:
     for t, r in zip(cc.timings, cc.reports):
         print("  stage %2d: weak %3d  mine %7.3f s  train %6.3f s  neg consumed %12d  acceptanceRatio %.3g" %
               (t["stage"], t["weak"], t["mine_s"], t["train_s"], r["neg_consumed"], r["acceptance_ratio"]))
+    for nm in ("mine", "mine_host_assemble", "mine_host_eval", "mine_host_cut"):
+        ms, k = ctx.timing(nm)
+        print("  timer %-20s %10.1f ms over %d" % (nm, ms, k))
     print("files:", sorted(os.listdir(d))[:6], "...")
     print(json.dumps(dict(stages=len(cc.stageClassifiers), total_s=t_train, mining_s=mine, train_s=train, weak=[t["weak"] for t in cc.timings],
                           neg_consumed=[r["neg_consumed"] for r in cc.reports], world=world)))
