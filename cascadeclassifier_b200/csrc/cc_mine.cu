@@ -724,29 +724,6 @@ __global__ void k_gather_resize(const LevelDesc* __restrict__ levels, int nlevel
   }
 }
 
-// copy the listed windows (batch ordinals) out of their pyramid levels into consecutive slots
-__global__ void k_gather_list(const LevelDesc* __restrict__ levels, int nlevels, const uint8_t* __restrict__ pool, int W, int H,
-                              const unsigned int* __restrict__ which, int n, uint8_t* __restrict__ dst, uint8_t* __restrict__ labels, int label) {
-  const int npx = W * H;
-  const long long total = (long long)n * npx;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(t / npx);
-    const int r = (int)(t - (long long)i * npx);
-    if (r == 0) labels[i] = (uint8_t)label;
-    if (nlevels == 0) { dst[t] = 0; continue; }      // this rank owns no strip of the batch
-    const long long b = which[i];
-    int lo = 0, hi = nlevels - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= b) lo = mid; else hi = mid - 1; }
-    const LevelDesc& L = levels[lo];
-    const long long k = b - L.w_base + L.w_skip;
-    const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
-    const int wy = r / W, wx = r - wy * W;
-    // only the strips this rank owns are in the table: a window of another rank's strip falls outside [w_base, w_base + w_count)
-    const bool mine = b >= L.w_base && b < L.w_base + L.w_count;
-    dst[t] = mine ? pool[L.px_off + (size_t)(L.y0 + iy * L.step_y + wy) * L.ppitch + (L.x0 + ix * L.step_x + wx)] : (uint8_t)0;
-  }
-}
-
 // survivor list -> bitmap over the batch ordinals (image-sharded mining: the bitmaps of the ranks are disjoint, so
 // their element-wise sum is their union)
 __global__ void k_list_to_bitmap(const unsigned int* __restrict__ list, const unsigned int* __restrict__ count, unsigned int* __restrict__ bitmap) {
@@ -778,7 +755,8 @@ struct MineState {
   int levels_cap = 0;
   unsigned int* d_surv = nullptr;      // [0] = counter, [1..cap] = list
   unsigned int surv_cap = 0;
-  unsigned int* h_surv = nullptr;      // pinned mirror
+  unsigned int* h_surv = nullptr;      // pinned mirror (count + list) shared by the slot path and the tile miner
+  size_t h_surv_cap = 0;               // entries
   // whole-level fast path (Haar / LBP)
   std::vector<LvlFeat> lfeats;         // parallel to `nodes`
   LvlFeat* d_lfeats = nullptr;
@@ -800,6 +778,16 @@ struct MineState {
   TileDesc* d_tiles = nullptr;
   int tiles_cap = 0;
   int mode = 0;                        // cc_mine_set_mode
+  // plane path, two batches in flight: strips of batch k stay resident for its gather while batch k+1 is evaluated
+  LevelDesc* d_strips[2] = {nullptr, nullptr};
+  int strips_cap[2] = {0, 0};
+  LevelDesc* h_strips[2] = {nullptr, nullptr};       // pinned staging: the upload must not wait for the batch in flight
+  std::vector<LevelDesc> strips[2];
+  unsigned int* h_bits[2] = {nullptr, nullptr};      // pinned survivor bitmaps
+  size_t h_bits_cap[2] = {0, 0};
+  cudaEvent_t ev_done[2] = {nullptr, nullptr};
+  unsigned int* d_which = nullptr;     // accepted ordinals of a batch
+  int which_cap = 0;
 };
 
 static void free_cascade(MineState* m) {
@@ -814,13 +802,20 @@ static void free_scratch(MineState* m) {
   cudaFree(m->d_pool); m->d_pool = nullptr; m->pool_cap = 0;
   cudaFree(m->d_levels); m->d_levels = nullptr; m->levels_cap = 0;
   cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
-  cudaFreeHost(m->h_surv); m->h_surv = nullptr;
+  cudaFreeHost(m->h_surv); m->h_surv = nullptr; m->h_surv_cap = 0;
   cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
   m->d_psum = m->d_psq = m->d_ptilt = nullptr; m->plane_cap = 0;
   cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts); cudaFree(m->d_order);
   m->d_list[0] = m->d_list[1] = m->d_counts = nullptr; m->list_cap = 0; m->d_order = nullptr; m->order_cap = 0;
   cudaFree(m->d_bitmap); cudaFreeHost(m->h_bitmap); m->d_bitmap = nullptr; m->h_bitmap = nullptr; m->bitmap_cap = 0;
   cudaFree(m->d_tiles); m->d_tiles = nullptr; m->tiles_cap = 0;
+  for (int s = 0; s < 2; ++s) {
+    cudaFree(m->d_strips[s]); m->d_strips[s] = nullptr; m->strips_cap[s] = 0;
+    cudaFreeHost(m->h_strips[s]); m->h_strips[s] = nullptr;
+    cudaFreeHost(m->h_bits[s]); m->h_bits[s] = nullptr; m->h_bits_cap[s] = 0;
+    if (m->ev_done[s]) { cudaEventDestroy(m->ev_done[s]); m->ev_done[s] = nullptr; }
+  }
+  cudaFree(m->d_which); m->d_which = nullptr; m->which_cap = 0;
 }
 
 int mine_free(cc_ctx* ctx) {
@@ -837,6 +832,14 @@ int mine_free(cc_ctx* ctx) {
 static MineState* mine_state(cc_ctx* ctx) {
   if (!ctx->mine) ctx->mine = new MineState();
   return ctx->mine;
+}
+
+static int ensure_h_surv(MineState* m, size_t entries) {
+  if (entries <= m->h_surv_cap) return CC_OK;
+  cudaFreeHost(m->h_surv); m->h_surv = nullptr; m->h_surv_cap = 0;
+  CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * entries));
+  m->h_surv_cap = entries;
+  return CC_OK;
 }
 
 static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, int nlevels) {
@@ -856,12 +859,11 @@ static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, i
     m->levels_cap = nlevels;
   }
   if ((unsigned)nwin > m->surv_cap) {
-    cudaFree(m->d_surv); cudaFreeHost(m->h_surv);
+    cudaFree(m->d_surv);
     CC_CUDA(cudaMalloc(&m->d_surv, sizeof(unsigned) * ((size_t)nwin + 1)));
-    CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * ((size_t)nwin + 1)));
     m->surv_cap = (unsigned)nwin;
   }
-  return CC_OK;
+  return ensure_h_surv(m, (size_t)m->surv_cap + 1);
 }
 
 // ---- NegReader state machine without the pixels (src/imagestorage.cpp:57-126) -------------------------
@@ -1128,10 +1130,8 @@ static int ensure_lists(cc_ctx* ctx, MineState* m, long long nwin) {
     const size_t cap = (size_t)nwin + (size_t)nwin / 2;
     CC_CUDA(cudaMalloc(&m->d_list[0], cap * 4)); CC_CUDA(cudaMalloc(&m->d_list[1], cap * 4));
     m->list_cap = cap;
-    cudaFreeHost(m->h_surv); m->h_surv = nullptr;
-    CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (cap + 1)));
   }
-  if (!m->h_surv) CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (m->list_cap + 1)));
+  CC_CHECK(ensure_h_surv(m, m->list_cap + 1));
   if (!m->d_counts) CC_CUDA(cudaMalloc(&m->d_counts, sizeof(unsigned) * 16));
   return CC_OK;
 }
@@ -1199,35 +1199,38 @@ static int eval_tiles(cc_ctx* ctx, MineState* m, Batch& bt, const TileGeom& g, s
   return collect_survivors(ctx, m, sharded, bt.nwin, m->d_counts, m->d_list[0], survivors);
 }
 
-// fused tile miner: accepted windows recomputed from the source images into training slots [first, first+n)
-static int gather_accepted_resize(cc_ctx* ctx, MineState* m, const unsigned* which, int n, int first, int label) {
+// accepted windows recomputed from the source images into training slots [first, first+n) (the level pixels of the batch
+// may already have been overwritten by the next batch); d_levels = the batch's descriptors as uploaded for its evaluation
+static int gather_accepted_resize(cc_ctx* ctx, MineState* m, const LevelDesc* d_levels, int nlevels, const unsigned* which, int n, int first, int label) {
   if (n == 0) return CC_OK;
   const int npx = ctx->W * ctx->H;
-  CC_CUDA(cudaMemcpyAsync(m->d_list[1], which, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
+  if (n > m->which_cap) { cudaFree(m->d_which); CC_CUDA(cudaMalloc(&m->d_which, sizeof(unsigned) * (size_t)ctx->max_samples)); m->which_cap = ctx->max_samples; }
+  CC_CUDA(cudaMemcpyAsync(m->d_which, which, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
   {
     ScopedTimer tm(ctx, "mine", 1);
-    k_gather_resize<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)m->dev_levels.size(), ctx->W, ctx->H, m->d_list[1], n,
+    k_gather_resize<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(d_levels, nlevels, ctx->W, ctx->H, m->d_which, n,
                                                                                     ctx->d_imgs + (size_t)first * npx, ctx->d_labels + first, label);
     CC_CUDA(cudaGetLastError());
   }
   if (ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images) CC_CHECK(allreduce_sum(ctx, ctx->d_imgs + (size_t)first * npx, (size_t)n * npx, /*uint8*/ 1));
   ctx->precalc_valid = false;
   CC_CHECK(launch_integrals(ctx, main_store(ctx), first, n));
-  CC_CUDA(cudaStreamSynchronize(ctx->stream));
   return CC_OK;
 }
 
-// Fast path: build the levels and their integral planes, run the cascade in stage groups over the shrinking survivor
-// list, return the sorted surviving batch ordinals.  The level pixels stay in m->d_pool for gather_accepted().
-static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigned>& survivors) {
-  survivors.clear();
+// Fast path, asynchronous half: build the levels and their integral planes, run the cascade in stage groups over the
+// shrinking survivor list, turn the survivors into a bitmap (summed over the ranks when the images are sharded) and
+// start its copy to the host.  Nothing here waits for the GPU, so the host assembles and launches batch k+1 while
+// batch k is evaluated; finish_levels(slot) waits for the bitmap and returns the ascending surviving ordinals.
+// The strips of the batch stay in m->d_strips[slot] for gather_accepted_resize().
+static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
   if (bt.nwin == 0) return CC_OK;
   // Tall levels are cut into horizontal strips of STRIP_WIN_ROWS window rows (consecutive strips overlap by H - step
   // pixel rows): window sums are differences, so every strip can carry its own integral planes, and a strip is a
   // much shorter serial chain of rows for k_lvl_build than the whole level.  The window ordinals of a strip are a
   // contiguous range of its level's, so a strip is described like a level (the device code does not distinguish).
   constexpr int STRIP_WIN_ROWS = 8;
-  std::vector<LevelDesc>& dl = m->dev_levels;
+  std::vector<LevelDesc>& dl = m->strips[slot];
   dl.clear();
   size_t pool_px = 0;
   {
@@ -1275,7 +1278,15 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
   const bool haar = ctx->ftype == CC_FEATURE_HAAR;
   const bool tilted = haar && m->cascade_tilted;
   if (pool_px > m->pool_cap) { cudaFree(m->d_pool); CC_CUDA(cudaMalloc(&m->d_pool, pool_px + pool_px / 2)); m->pool_cap = pool_px + pool_px / 2; }
-  if (nlv > m->levels_cap) { cudaFree(m->d_levels); CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * nlv)); m->levels_cap = nlv; }
+  if (nlv > m->strips_cap[slot]) {
+    cudaFree(m->d_strips[slot]); cudaFreeHost(m->h_strips[slot]);
+    m->d_strips[slot] = nullptr; m->h_strips[slot] = nullptr; m->strips_cap[slot] = 0;
+    const int cap = nlv + nlv / 2 + 64;
+    CC_CUDA(cudaMalloc(&m->d_strips[slot], sizeof(LevelDesc) * cap));
+    CC_CUDA(cudaMallocHost(&m->h_strips[slot], sizeof(LevelDesc) * cap));
+    m->strips_cap[slot] = cap;
+  }
+  LevelDesc* d_levels = m->d_strips[slot];
   if (plane_elems > m->plane_cap) {
     cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
     m->d_psum = m->d_psq = m->d_ptilt = nullptr;
@@ -1289,12 +1300,12 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
     const size_t cap = (size_t)bt.nwin + (size_t)bt.nwin / 2;
     CC_CUDA(cudaMalloc(&m->d_list[0], cap * 4)); CC_CUDA(cudaMalloc(&m->d_list[1], cap * 4));
     m->list_cap = cap;
-    cudaFreeHost(m->h_surv); m->h_surv = nullptr;
-    CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (cap + 1)));
   }
-  if (!m->h_surv) CC_CUDA(cudaMallocHost(&m->h_surv, sizeof(unsigned) * (m->list_cap + 1)));
   if (!m->d_counts) CC_CUDA(cudaMalloc(&m->d_counts, sizeof(unsigned) * 16));
-  CC_CUDA(cudaMemcpyAsync(m->d_levels, dl.data(), sizeof(LevelDesc) * nlv, cudaMemcpyHostToDevice, ctx->stream));
+  if (nlv) {
+    memcpy(m->h_strips[slot], dl.data(), sizeof(LevelDesc) * nlv);
+    CC_CUDA(cudaMemcpyAsync(d_levels, m->h_strips[slot], sizeof(LevelDesc) * nlv, cudaMemcpyHostToDevice, ctx->stream));
+  }
   int ngroups = 0;
   {
     ScopedTimer tm(ctx, "mine", 0);
@@ -1318,21 +1329,21 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
       uint32_t* psq = haar ? m->d_psq : nullptr;
       uint32_t* ptl = tilted ? m->d_ptilt : nullptr;
       // widest class first: its levels are the longest chains
-      if (off[3] > off[2]) { k_lvl_build<512><<<off[3] - off[2], 512, 0, ctx->stream>>>(m->d_levels, m->d_order + off[2], m->d_pool, m->d_psum, psq, ptl); ++launches; }
-      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, 0, ctx->stream>>>(m->d_levels, m->d_order + off[1], m->d_pool, m->d_psum, psq, ptl); ++launches; }
-      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, 0, ctx->stream>>>(m->d_levels, m->d_order + off[0], m->d_pool, m->d_psum, psq, ptl); ++launches; }
+      if (off[3] > off[2]) { k_lvl_build<512><<<off[3] - off[2], 512, 0, ctx->stream>>>(d_levels, m->d_order + off[2], m->d_pool, m->d_psum, psq, ptl); ++launches; }
+      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, 0, ctx->stream>>>(d_levels, m->d_order + off[1], m->d_pool, m->d_psum, psq, ptl); ++launches; }
+      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, 0, ctx->stream>>>(d_levels, m->d_order + off[0], m->d_pool, m->d_psum, psq, ptl); ++launches; }
     } else {
-      k_resize_levels<<<grid_for(ctx, (long long)pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, (long long)pool_px, m->d_pool);
-      k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
+      k_resize_levels<<<grid_for(ctx, (long long)pool_px, 256), 256, 0, ctx->stream>>>(d_levels, nlv, (long long)pool_px, m->d_pool);
+      k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
       launches += 2;
       if (tilted) {
         CC_CUDA(cudaMemsetAsync(m->d_ptilt, 0, plane_elems * 4, ctx->stream));
-        k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, diag, m->d_pool, m->d_ptilt, 0);
-        k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(m->d_levels, nlv, diag, m->d_pool, m->d_ptilt, 1);
+        k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(d_levels, nlv, diag, m->d_pool, m->d_ptilt, 0);
+        k_lvl_diag<<<grid_for(ctx, diag, 256), 256, 0, ctx->stream>>>(d_levels, nlv, diag, m->d_pool, m->d_ptilt, 1);
         launches += 2;
       }
       dim3 cgrid(grid_for(ctx, cols, 256), 3);
-      k_lvl_cols<<<cgrid, 256, 0, ctx->stream>>>(m->d_levels, nlv, cols, m->d_psum, haar ? m->d_psq : nullptr, tilted ? m->d_ptilt : nullptr);
+      k_lvl_cols<<<cgrid, 256, 0, ctx->stream>>>(d_levels, nlv, cols, m->d_psum, haar ? m->d_psq : nullptr, tilted ? m->d_ptilt : nullptr);
       launches += 1;
     }
     CC_CUDA(cudaGetLastError());
@@ -1348,10 +1359,10 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
       const int s1 = ngroups == 0 ? std::min(ns, 2) : ngroups == 1 ? std::min(ns, 6) : ns;
       A.s_begin = s0; A.s_end = s1;
       if (ngroups == 0) {
-        if (nlv > 0) k_lvl_cascade_all<<<std::min(nlv, ctx->sm_count * 32), 256, 0, ctx->stream>>>(m->d_levels, nlv, A, m->d_counts, m->d_list[0]);
+        if (nlv > 0) k_lvl_cascade_all<<<std::min(nlv, ctx->sm_count * 32), 256, 0, ctx->stream>>>(d_levels, nlv, A, m->d_counts, m->d_list[0]);
       }
       else
-        k_lvl_cascade<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(m->d_levels, nlv, A, m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1,
+        k_lvl_cascade<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_levels, nlv, A, m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1,
                                                                    m->d_counts + ngroups, m->d_list[ngroups & 1]);
       ++ngroups; ++launches;
       s0 = s1;
@@ -1360,26 +1371,42 @@ static int eval_levels(cc_ctx* ctx, MineState* m, Batch& bt, std::vector<unsigne
     ctx->launches += launches;
     if (ctx->timing_enabled) ctx->timers["mine"].launches += launches;
   }
-  return collect_survivors(ctx, m, sharded, bt.nwin, m->d_counts + ngroups - 1, m->d_list[(ngroups - 1) & 1], survivors);
+  // survivors -> bitmap (1 bit per batch ordinal) -> pinned host memory, asynchronously
+  const size_t words = ((size_t)bt.nwin + 31) / 32;
+  if (words > m->bitmap_cap) {
+    cudaFree(m->d_bitmap);
+    const size_t cap = words + words / 2 + 64;
+    CC_CUDA(cudaMalloc(&m->d_bitmap, cap * 4));
+    m->bitmap_cap = cap;
+  }
+  if (words > m->h_bits_cap[slot]) {
+    cudaFreeHost(m->h_bits[slot]);
+    const size_t cap = words + words / 2 + 64;
+    CC_CUDA(cudaMallocHost(&m->h_bits[slot], cap * 4));
+    m->h_bits_cap[slot] = cap;
+  }
+  if (!m->ev_done[slot]) CC_CUDA(cudaEventCreateWithFlags(&m->ev_done[slot], cudaEventDisableTiming));
+  CC_CUDA(cudaMemsetAsync(m->d_bitmap, 0, words * 4, ctx->stream));
+  k_list_to_bitmap<<<ctx->sm_count * 2, 256, 0, ctx->stream>>>(m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1, m->d_bitmap);
+  CC_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  if (sharded) CC_CHECK(allreduce_sum(ctx, m->d_bitmap, words, /*uint32*/ 4));
+  CC_CUDA(cudaMemcpyAsync(m->h_bits[slot], m->d_bitmap, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaEventRecord(m->ev_done[slot], ctx->stream));
+  return CC_OK;
 }
 
-// fast path: copy accepted windows (batch ordinals) from the level pool into training slots [first, first+n), build integrals
-static int gather_accepted(cc_ctx* ctx, MineState* m, const Batch& bt, const unsigned* which, int n, int first, int label) {
-  if (n == 0) return CC_OK;
-  const int npx = ctx->W * ctx->H;
-  CC_CUDA(cudaMemcpyAsync(m->d_list[0], which, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
-  {
-    ScopedTimer tm(ctx, "mine", 1);
-    k_gather_list<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)m->dev_levels.size(), m->d_pool, ctx->W, ctx->H,
-                                                                                  m->d_list[0], n, ctx->d_imgs + (size_t)first * npx,
-                                                                                  ctx->d_labels + first, label);
-    CC_CUDA(cudaGetLastError());
+// second half: wait for the batch's bitmap, list the surviving ordinals in ascending order
+static int finish_levels(cc_ctx* ctx, MineState* m, int slot, long long nwin, std::vector<unsigned>& survivors) {
+  survivors.clear();
+  if (nwin == 0) return CC_OK;
+  CC_CUDA(cudaEventSynchronize(m->ev_done[slot]));
+  const size_t words = ((size_t)nwin + 31) / 32;
+  const unsigned int* hb = m->h_bits[slot];
+  for (size_t w = 0; w < words; ++w) {
+    unsigned int bits = hb[w];
+    while (bits) { const int k = __builtin_ctz(bits); bits &= bits - 1; survivors.push_back((unsigned)(w * 32 + k)); }
   }
-  // image-sharded mining: only the owner of a level holds its pixels; the others wrote zeros
-  if (ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images) CC_CHECK(allreduce_sum(ctx, ctx->d_imgs + (size_t)first * npx, (size_t)n * npx, /*uint8*/ 1));
-  ctx->precalc_valid = false;
-  CC_CHECK(launch_integrals(ctx, main_store(ctx), first, n));
-  CC_CUDA(cudaStreamSynchronize(ctx->stream));
   return CC_OK;
 }
 
@@ -1499,18 +1526,15 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   if (ns.lw == 0) stream_ok = ns.nextImg();             // first get(): img.empty() -> nextImg()
   std::vector<unsigned> survivors, accepted;
 
-  while (got < count && stream_ok) {
-    // serial rule, checked before every window: stop when (getcount+1)/consumed <= minRatio
-    if (consumed != 0 && ((double)got + 1) / (double)consumed <= min_ratio) break;
-    // ---- assemble a batch ----
+  // ---- assemble a batch: levels (or parts of levels) of the stream starting at `from` ----
+  auto assemble = [&](const NegStream& from, Batch& bt, bool& more) {
+    HostTimer ht(ctx, "mine_host_assemble");
     long long want = 32768;
     if (accept_rate > 0) want = (long long)std::min<double>((double)max_batch, std::max(4096.0, 1.25 * (count - got) / accept_rate + 1024));
     else want = std::min<long long>(max_batch, 65536);
     want = std::min(want, max_batch);
-    Batch bt;
-    NegStream cur = ns;
-    bool more = true;
-    HostTimer* ht = new HostTimer(ctx, "mine_host_assemble");
+    NegStream cur = from;
+    more = true;
     while (bt.nwin < want && more) {
       LevelDesc L;
       fill_level(cur, L);
@@ -1535,7 +1559,26 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       cur = nxt;
       if (L.w_count < avail) break;
     }
-    delete ht;
+  };
+  // Plane path: two batches in flight.  While batch k is evaluated the host assembles and launches batch k+1 -- when
+  // the running acceptance rate says that batch k will not complete the stage -- and only then waits for batch k's
+  // survivor bitmap; a speculative batch that turns out not to be needed is dropped (its windows count as not read).
+  const bool pipelined = level_path && !tile_path;
+  Batch pre;
+  bool pre_valid = false, pre_more = false;
+  int slot = 0;
+
+  while (got < count && stream_ok) {
+    // serial rule, checked before every window: stop when (getcount+1)/consumed <= minRatio
+    if (consumed != 0 && ((double)got + 1) / (double)consumed <= min_ratio) break;
+    Batch bt;
+    bool more = true;
+    if (pre_valid) {
+      bt = std::move(pre); pre = Batch(); more = pre_more; pre_valid = false; slot ^= 1;
+    } else {
+      assemble(ns, bt, more);
+      if (pipelined) { HostTimer he(ctx, "mine_host_eval"); CC_CHECK(launch_levels(ctx, m, bt, slot)); }
+    }
     const int nwin = (int)bt.nwin;
     // ---- GPU: levels, gather, integrals, cascade ----
     const bool direct = m->stages.empty();       // stage 0: every window passes, gather straight into the training slots
@@ -1574,10 +1617,18 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       if (taken < take_direct) { /* ratio rule fired */ }
       if (got < count && taken == nwin) { ns = bt.after.back(); stream_ok = more; continue; }
     } else {
-      {
+      if (pipelined) {
+        if (more && accept_rate > 0 && accept_rate * (double)bt.nwin < 0.5 * (double)(count - got)) {
+          assemble(bt.after.back(), pre, pre_more);
+          HostTimer he(ctx, "mine_host_eval");
+          CC_CHECK(launch_levels(ctx, m, pre, slot ^ 1));
+          pre_valid = true;
+        }
+        HostTimer hw(ctx, "mine_host_wait");
+        CC_CHECK(finish_levels(ctx, m, slot, bt.nwin, survivors));
+      } else {
         HostTimer he(ctx, "mine_host_eval");
-        if (level_path && tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
-        else if (level_path) CC_CHECK(eval_levels(ctx, m, bt, survivors));
+        if (tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
         else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
       }
       HostTimer hc(ctx, "mine_host_cut");
@@ -1585,9 +1636,10 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       bool stopped = false;
       const long long pos = serial_cut(survivors.data(), survivors.size(), nwin, count, min_ratio, consumed, got, accepted, stopped);
       stop_after = pos - 1;
-      if (level_path && tile_path) CC_CHECK(gather_accepted_resize(ctx, m, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
-      else if (level_path) CC_CHECK(gather_accepted(ctx, m, bt, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
-      else CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), first_slot + got - (int)accepted.size(), 0));
+      const int first_acc = first_slot + got - (int)accepted.size();
+      if (pipelined) CC_CHECK(gather_accepted_resize(ctx, m, m->d_strips[slot], (int)m->strips[slot].size(), accepted.data(), (int)accepted.size(), first_acc, 0));
+      else if (tile_path) CC_CHECK(gather_accepted_resize(ctx, m, m->d_levels, (int)m->dev_levels.size(), accepted.data(), (int)accepted.size(), first_acc, 0));
+      else CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), first_acc, 0));
       if (nwin > 0) accept_rate = std::max((double)survivors.size() / (double)nwin, 1e-9);
       if (!stopped) { ns = bt.after.back(); stream_ok = more; continue; }
     }
@@ -1613,6 +1665,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     }
     break;
   }
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));          // gathers / integrals of the last batches; a dropped speculative batch
   state_from_stream(ns, state);
   *consumed_out = consumed;
   *got_out = got;
@@ -1722,12 +1775,22 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
   // every image from its first level (round 0 offsets), independent of the reader state
   std::vector<BgImage> one(1);
   Batch bt;
+  int slot = 0;
+  long long pend_nwin = 0;             // windows of the batch in flight in slot ^ 1
   auto flush = [&]() -> int {
     if (bt.nwin == 0) return CC_OK;
     const int nwin = (int)bt.nwin;
+    if (level_path && !tile_path) {
+      // two batches in flight, as in cc_mine_negatives: launch this one, then collect the previous one
+      CC_CHECK(launch_levels(ctx, m, bt, slot));
+      if (pend_nwin) { CC_CHECK(finish_levels(ctx, m, slot ^ 1, pend_nwin, survivors)); surv += (long long)survivors.size(); }
+      pend_nwin = nwin; slot ^= 1;
+      total += nwin;
+      bt = Batch();
+      return CC_OK;
+    }
     if (level_path) {
-      if (tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
-      else CC_CHECK(eval_levels(ctx, m, bt, survivors));
+      CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
       total += nwin; surv += (long long)survivors.size();
       bt = Batch();
       return CC_OK;
@@ -1774,6 +1837,7 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
     }
   }
   CC_CHECK(flush());
+  if (pend_nwin) { CC_CHECK(finish_levels(ctx, m, slot ^ 1, pend_nwin, survivors)); surv += (long long)survivors.size(); }
   if (windows) *windows = total;
   if (survivors_out) *survivors_out = surv;
   return CC_OK;
