@@ -622,6 +622,7 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
 // is poor (sum(k^2) above a limit: long runs of equal values, outliers far beyond 3.5 sd) are appended to a list and
 // sorted by k_sort_rows afterwards.  Output is bit-identical to k_sort_rows (test_sort_paths_agree).
 // ------------------------------------------------------------------------------------------------
+constexpr unsigned long long BSORT_ONE = 0x3FF0000000000000ull;     // composites are stored as doubles in [1, 2)
 template <int KPT> struct BucketCfg { static constexpr int B = KPT <= 3 ? 4096 : KPT <= 7 ? 8192 : 16384; };     // a multiple of 4 * SORT_THREADS (uint4 scan)
 template <int KPT> static size_t bsort_smem() { return (size_t)(SORT_THREADS * KPT + 8) * 8 + (size_t)BucketCfg<KPT>::B * 4; }
 
@@ -639,6 +640,8 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
   __shared__ uint32_t warp_tot[SORT_WARPS];
   __shared__ float warp_cost[SORT_WARPS];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  uint32_t comp_s = (uint32_t)__cvta_generic_to_shared(comp), cnt_s = (uint32_t)__cvta_generic_to_shared(cnt);
+  asm volatile("" : "+r"(comp_s), "+r"(cnt_s));          // opaque: kept in registers instead of being re-derived from SR_CgaCtaId in the loops
 
   // every position k < KPT - 1 of a thread is a real element when N covers KPT - 1 full strides (uniform)
   const bool full = N >= (KPT - 1) * SORT_THREADS;
@@ -751,12 +754,12 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
     }
     __syncthreads();
     // ---- D: distribution ----
-    if (t < 8) comp[N + t] = 0x7FFFFFFFFFFFFFFFull;      // sentinel behind the last bucket (composites are 48-bit, differences stay in int64)
+    if (t < 8) comp[N + t] = 0x4000000000000000ull;      // sentinel behind the last bucket: 2.0, above every composite
 #pragma unroll
     for (int k = 0; k < KPT; ++k) {
       if (valid(k)) {
         const uint32_t p = atomicAdd(&cnt[bucket_of(v[k])], 1u);
-        comp[p] = ((unsigned long long)float_to_key(v[k]) << 16) | (unsigned long long)(t + k * SORT_THREADS);
+        comp[p] = BSORT_ONE | ((unsigned long long)float_to_key(v[k]) << 16) | (unsigned long long)(t + k * SORT_THREADS);
       }
     }
     if (row + (int)gridDim.x < nrows) load_row(row + gridDim.x);      // the next row's loads fly during the ranking
@@ -764,22 +767,32 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
     // ---- E: rank, write out.  The buckets are in value order, so every composite left of my bucket is smaller than
     // mine and every one right of it is larger: my final position is w0 + #(smaller composites in [w0, w1)) for ANY
     // window [w0, w1) that covers the bucket -- the window is widened to 16-byte alignment and whole groups of four
-    // (comp[N .. N+8) holds a sentinel), so there is neither a remainder loop nor a mask. ----
+    // (comp[N .. N+8) holds a sentinel), so there is neither a remainder loop nor a mask.  Composites carry the
+    // exponent of 1.0, i.e. they are doubles in [1, 2) whose order is the order of the 48-bit integers: one DSETP per
+    // comparison on the otherwise idle FP64 pipe.  Shared memory is addressed through 32-bit shared-window addresses. ----
     uint16_t* drow = sidx + (size_t)row * n_stride;
     float* vrow = sval + (size_t)row * n_stride;
 #pragma unroll 1
     for (int p = t; p < N; p += SORT_THREADS) {
-      const unsigned long long c = comp[p];
+      double cd;
+      asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cd) : "r"(comp_s + 8u * (uint32_t)p));
+      const unsigned long long c = (unsigned long long)__double_as_longlong(cd);
       const float x = key_to_float((uint32_t)(c >> 16));
       const int b = bucket_of(x);
-      const int e = (int)cnt[b];
-      int j = (b ? (int)cnt[b - 1] : 0) & ~1;
-      uint32_t r = (uint32_t)j;
+      uint32_t e, j = 0;
+      asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(cnt_s + 4u * (uint32_t)b));
+      if (b) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(j) : "r"(cnt_s + 4u * (uint32_t)b - 4u));
+      j &= ~1u;
+      uint32_t r = j;
 #pragma unroll 1
       for (; j < e; j += 4) {
-        const ulonglong2 q0 = *reinterpret_cast<const ulonglong2*>(comp + j);
-        const ulonglong2 q1 = *reinterpret_cast<const ulonglong2*>(comp + j + 2);
-        r += (uint32_t)((q0.x - c) >> 63) + (uint32_t)((q0.y - c) >> 63) + (uint32_t)((q1.x - c) >> 63) + (uint32_t)((q1.y - c) >> 63);
+        double q0, q1, q2, q3;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q0), "=d"(q1) : "r"(comp_s + 8u * j));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(q2), "=d"(q3) : "r"(comp_s + 8u * j + 16u));
+        asm("{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+            "setp.lt.f64 p0, %1, %5;\n\tsetp.lt.f64 p1, %2, %5;\n\tsetp.lt.f64 p2, %3, %5;\n\tsetp.lt.f64 p3, %4, %5;\n\t"
+            "@p0 add.u32 %0, %0, 1;\n\t@p1 add.u32 %0, %0, 1;\n\t@p2 add.u32 %0, %0, 1;\n\t@p3 add.u32 %0, %0, 1;\n\t}"
+            : "+r"(r) : "d"(q0), "d"(q1), "d"(q2), "d"(q3), "d"(cd));
       }
       drow[r] = (uint16_t)(c & 0xFFFFull);
       __stcs(vrow + r, x);
