@@ -290,7 +290,8 @@ def mining_leg(device, dist=None, dev=None, world=1):
     pos = synth.make_positives(1400, WIN, WIN)
     small = synth.make_backgrounds(12, 480, 360, seed0=500, clutter=2.5)
     cc = CvCascadeClassifier(ctx, out=io.StringIO())
-    cc.train("/tmp/bench_mining_cascade_r%d" % device, "pos.vec", "bg.txt", 1000, 2000, 1024, 1024, 8, CvCascadeParams(0, 0, (WIN, WIN)),
+    import tempfile
+    cc.train(tempfile.mkdtemp(prefix="bench_mining_cascade_r%d_" % device), "pos.vec", "bg.txt", 1000, 2000, 1024, 1024, 8, CvCascadeParams(0, 0, (WIN, WIN)),
              ccb.CvHaarFeatureParams(HAAR_MODE_ALL), ccb.CvCascadeBoostParams(), positives=pos, backgrounds=small)
     nimg = 256
     big = [synth.make_background(1920, 1080, 9000 + i, clutter=0.3) for i in range(4)]

@@ -85,6 +85,46 @@ class CvCascadeBoost:
         s._build_c()
         return s
 
+    # bool read(const FileNode&, const CvFeatureEvaluator*, const CvCascadeBoostParams&), src/boost.cpp:543-565 +
+    # CvCascadeBoostTree::read, src/o_cvcascadeboosttree.cpp:95-165 (resume: leaf values and thresholds come back as f32)
+    @staticmethod
+    def read(node, maxCatCount):
+        """node = cv2.FileNode of one stage (stage<i>.xml top level, or an element of cascade.xml's `stages`)."""
+        subsetN = (maxCatCount + 31) // 32
+        step = 3 + (subsetN if maxCatCount > 0 else 1)
+        threshold = float(np.float32(node.getNode("stageThreshold").real()))
+        trees = []
+        weak = node.getNode("weakClassifiers")
+        for wi in range(weak.size()):
+            wn = weak.at(wi)
+            inn, lvn = wn.getNode("internalNodes"), wn.getNode("leafValues")
+            vals = [inn.at(i).real() for i in range(inn.size())]
+            leaves = [float(np.float32(lvn.at(i).real())) for i in range(lvn.size())]
+            n_int = len(vals) // step
+            if n_int == 0 or len(vals) != n_int * step:
+                raise CascadeCudaError("malformed internalNodes in stage file")
+            nodes = [None] * n_int
+            for i in range(n_int):
+                rec = vals[i * step:(i + 1) * step]
+                nd = dict(left=-1, right=-1, var_idx=int(rec[2]), split_point=-1, c=0.0, quality=0.0, subset=[0] * 8, value=0.0,
+                          depth=0, sample_count=0)
+                if maxCatCount > 0:
+                    sub = [int(v) for v in rec[3:3 + subsetN]]
+                    nd["subset"] = (sub + [0] * 8)[:8]
+                else:
+                    nd["c"] = float(np.float32(rec[3]))
+                nodes[i] = nd
+            for i in range(n_int):
+                for side, ref in (("left", int(vals[i * step])), ("right", int(vals[i * step + 1]))):
+                    if ref <= 0:            # leaf: index -ref into leafValues
+                        nodes.append(dict(left=-1, right=-1, var_idx=-1, split_point=-1, c=0.0, quality=0.0, subset=[0] * 8,
+                                          value=leaves[-ref], depth=0, sample_count=0))
+                        nodes[i][side] = len(nodes) - 1
+                    else:
+                        nodes[i][side] = ref
+            trees.append(nodes)
+        return CvCascadeBoost.from_trees(threshold, trees)
+
     def _build_c(self):
         cap = max(len(self.trees), 1)
         trees = (_lib.Tree * cap)()

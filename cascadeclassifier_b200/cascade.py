@@ -167,10 +167,20 @@ class CvCascadeClassifier:
         except (IOError, OSError, ValueError):
             out.write("Image reader can not be created from -vec %s and -bg %s.\n" % (posFilename, negFilename))
             return False
-        self.featureEvaluator = CvFeatureEvaluator.create(cascadeParams.featureType, self.ctx)
-        self.featureEvaluator.init(featureParams, numPos + numNeg, cascadeParams.winSize)
-        self._create_readers(positives, backgrounds)
         self.stageClassifiers = []
+        if not self.load(dirName):
+            self.cascadeParams, self.featureParams, self.stageParams = cascadeParams, featureParams, stageParams
+            self.featureEvaluator = CvFeatureEvaluator.create(cascadeParams.featureType, self.ctx)
+            self.featureEvaluator.init(featureParams, numPos + numNeg, cascadeParams.winSize)
+        else:
+            # src/cascadeclassifier.cpp:179-186
+            out.write("---------------------------------------------------------------------------------\n"
+                      "Training parameters are pre-loaded from the parameter file in data folder!\n"
+                      "Please empty this folder if you want to use a NEW set of training parameters.\n"
+                      "---------------------------------------------------------------------------------\n")
+            cascadeParams, featureParams, stageParams = self.cascadeParams, self.featureParams, self.stageParams
+            W, H = cascadeParams.winSize
+        self._create_readers(positives, backgrounds)
         out.write("PARAMETERS:\ncascadeDirName: %s\nvecFileName: %s\nbgFileName: %s\n" % (cascadeDirName, posFilename, negFilename))
         out.write("numPos: %d\nnumNeg: %d\nnumStages: %d\n" % (numPos, numNeg, numStages))
         out.write("precalcValBufSize[Mb] : %d\nprecalcIdxBufSize[Mb] : %d\n" % (precalcValBufSize, precalcIdxBufSize))
@@ -183,8 +193,13 @@ class CvCascadeClassifier:
             out.write("mode: %s\n" % featureParams.modeStr())
         out.write("Number of unique features given windowSize [%d,%d] : %d\n" % (W, H, self.featureEvaluator.getNumFeatures()))
 
+        startNumStages = len(self.stageClassifiers)
+        if startNumStages > 1:
+            out.write("\nStages 0-%d are loaded\n" % (startNumStages - 1))
+        elif startNumStages == 1:
+            out.write("\nStage 0 is loaded\n")
         requiredLeafFARate = math.pow(float(stageParams.maxFalseAlarm), float(numStages)) / float(stageParams.max_depth)
-        for i in range(numStages):
+        for i in range(startNumStages, numStages):
             out.write("\n===== TRAINING %d-stage =====\n<BEGIN\n" % i)
             t0 = time.time()
             ok, tempLeafFARate, rep = self.updateTrainingSet(requiredLeafFARate)
@@ -232,6 +247,59 @@ class CvCascadeClassifier:
             out.write("Cascade classifier can't be trained. Check the used training parameters.\n")
             return False
         self.save(dirName + "cascade.xml", baseFormatSave)
+        return True
+
+    # bool load(const string& cascadeDirName), src/cascadeclassifier.cpp:534-564 (+ readParams :388-404): resume from
+    # params.xml and the stage<i>.xml files already in the directory; the NegReader state is not persisted (as in the reference)
+    def load(self, cascadeDirName):
+        import cv2
+        from .evaluator import CvLBPFeatureParams, CvHOGFeatureParams
+        ppath = cascadeDirName + "params.xml"
+        if not os.path.exists(ppath):
+            return False
+        fs = cv2.FileStorage(ppath, cv2.FILE_STORAGE_READ)
+        if not fs.isOpened():
+            return False
+        node = fs.getFirstTopLevelNode()
+        try:
+            ft = {"HAAR": 0, "LBP": 1, "HOG": 2}[node.getNode("featureType").string()]
+            if node.getNode("stageType").string() != "BOOST":
+                return False
+            self.cascadeParams = CvCascadeParams(0, ft, (int(node.getNode("width").real()), int(node.getNode("height").real())))
+            sp = node.getNode("stageParams")
+            bt = {"DAB": 0, "RAB": 1, "LB": 2, "GAB": 3}[sp.getNode("boostType").string()]
+            self.stageParams = CvCascadeBoostParams(bt, float(np.float32(sp.getNode("minHitRate").real())),
+                                                    float(np.float32(sp.getNode("maxFalseAlarm").real())), sp.getNode("weightTrimRate").real(),
+                                                    int(sp.getNode("maxDepth").real()), int(sp.getNode("maxWeakCount").real()))
+            fp = node.getNode("featureParams")
+            if ft == 0:
+                self.featureParams = CvHaarFeatureParams({"BASIC": 0, "CORE": 1, "ALL": 2}[fp.getNode("mode").string()])
+            elif ft == 1:
+                self.featureParams = CvLBPFeatureParams()
+            else:
+                self.featureParams = CvHOGFeatureParams()
+        except KeyError:
+            fs.release()
+            return False
+        fs.release()
+        if self.ctx is None:
+            self.ctx = Context(0)
+        self.featureEvaluator = CvFeatureEvaluator.create(self.cascadeParams.featureType, self.ctx)
+        self.featureEvaluator.init(self.featureParams, self.numPos + self.numNeg, self.cascadeParams.winSize)
+        for si in range(self.numStages):
+            spath = cascadeDirName + "stage%d.xml" % si
+            if not os.path.exists(spath):
+                break
+            fs = cv2.FileStorage(spath, cv2.FILE_STORAGE_READ)
+            if not fs.isOpened():
+                break
+            try:
+                st = CvCascadeBoost.read(fs.getFirstTopLevelNode(), self.featureEvaluator.getMaxCatCount())
+            except (CascadeCudaError, cv2.error):
+                fs.release()
+                break
+            fs.release()
+            self.stageClassifiers.append(st)
         return True
 
     def predict(self, sampleIdx):

@@ -131,3 +131,57 @@ def test_tree_xml_encoding(tmp_path):
     assert inn == [1.0, 0.0, 1.0, 0.5, -1.0, -2.0, 2.0, -0.25]  # root: child node 1, leaf 0; node 1: leaves -1,-2
     lv = [t1.getNode("leafValues").at(i).real() for i in range(3)]
     assert lv == [np.float32(0.3), np.float32(-0.7), np.float32(0.9)]
+
+
+def test_stage_xml_write_read_round_trip(tmp_path):
+    """CvCascadeBoost::write -> stage<i>.xml -> CvCascadeBoost::read (the resume path of CvCascadeClassifier::load,
+    src/cascadeclassifier.cpp:534-564): tree structure, variable indices, thresholds / category subsets survive; leaf
+    values and the stage threshold come back rounded to f32, exactly what the reference's reader yields."""
+    import cv2
+    from cascadeclassifier_b200.boost import CvCascadeBoost
+    from cascadeclassifier_b200.xml_io import XmlWriter
+    rng = np.random.default_rng(3)
+
+    def leaf(v):
+        return dict(left=-1, right=-1, var_idx=-1, split_point=-1, c=0.0, quality=0.0, subset=[0] * 8, value=float(v), depth=0, sample_count=0)
+
+    def inner(l, r, var, cat):
+        nd = dict(left=l, right=r, var_idx=int(var), split_point=5, c=0.0, quality=1.0, subset=[0] * 8, value=0.0, depth=0, sample_count=0)
+        if cat:
+            nd["subset"] = [int(x) for x in rng.integers(-2**31, 2**31 - 1, 8)]
+        else:
+            nd["c"] = float(rng.normal())
+        return nd
+
+    for cat, max_cat in ((False, 0), (True, 256)):
+        trees = []
+        for t in range(5):
+            if t % 2 == 0:       # stump
+                trees.append([inner(1, 2, rng.integers(0, 5000), cat), leaf(rng.normal()), leaf(rng.normal())])
+            else:                # depth 2, right child internal: root, leaf, inner, leaf, leaf
+                trees.append([inner(1, 2, rng.integers(0, 5000), cat), leaf(rng.normal()), inner(3, 4, rng.integers(0, 5000), cat),
+                              leaf(rng.normal()), leaf(rng.normal())])
+        st = CvCascadeBoost.from_trees(-0.73251, trees)
+        path = str(tmp_path / ("stage_%d.xml" % max_cat))
+        fs = XmlWriter(path)
+        fs.start_map("stage0")
+        st.write(fs, None, max_cat)
+        fs.end_map()
+        fs.release()
+        rd = cv2.FileStorage(path, cv2.FILE_STORAGE_READ)
+        back = CvCascadeBoost.read(rd.getFirstTopLevelNode(), max_cat)
+        rd.release()
+        assert back.threshold == float(np.float32(-0.73251))
+        assert len(back.trees) == len(trees)
+
+        def walk(tr, i):
+            nd = tr[i]
+            if nd["left"] < 0:
+                return ("leaf", float(np.float32(nd["value"])))
+            key = tuple(nd["subset"]) if cat else float(np.float32(nd["c"]))
+            return (nd["var_idx"], key, walk(tr, nd["left"]), walk(tr, nd["right"]))
+
+        for a, b in zip(trees, back.trees):
+            assert walk(a, 0) == walk(b, 0)
+        # and the C-side stage built from the read trees is what cc_cascade_set_stages consumes
+        assert back.c_stage().num_weak == len(trees)

@@ -169,3 +169,51 @@ def test_mining_paths_agree(gpu_ctx, tmp_path, ftype, mode):
             assert (a[0] == b[0]).all() and np.float32(a[2]) == np.float32(b[2])
             if a[1] is not None and b[1] is not None:
                 assert (np.asarray(a[1]) == np.asarray(b[1])).all()
+
+
+@pytest.mark.parametrize("ftype,mode", [(orc.HAAR, orc.ALL), (orc.LBP, 0)])
+def test_resume_from_stage_files(gpu_ctx, tmp_path, ftype, mode):
+    """CvCascadeClassifier::load (src/cascadeclassifier.cpp:534-564): a second train() on a directory that holds
+    params.xml + stage<i>.xml keeps those stages (leaf values / thresholds as the f32 the XML holds), announces them
+    like the reference, trains only the missing stages and writes a cascade.xml OpenCV's detector loads."""
+    import cv2
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    pos, bgs = _data(260, 6)
+    fp = ccb.CvFeatureParams.create(ftype)
+    if ftype == orc.HAAR:
+        fp.mode = mode
+    d = str(tmp_path)
+    a = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
+    assert a.train(d, "pos.vec", "bg.txt", 200, 300, 1024, 1024, 2, CvCascadeParams(0, ftype, (24, 24)), fp, ccb.CvCascadeBoostParams(),
+                   positives=pos, backgrounds=bgs)
+    assert len(a.stageClassifiers) == 2
+    out = io.StringIO()
+    b = CvCascadeClassifier(gpu_ctx, out=out)
+    # other parameters on the command line are ignored in favour of params.xml, as in the reference
+    assert b.train(d, "pos.vec", "bg.txt", 200, 300, 1024, 1024, 4, CvCascadeParams(0, ftype, (24, 24)), fp,
+                   ccb.CvCascadeBoostParams(maxFalseAlarm=0.4), positives=pos, backgrounds=bgs)
+    log = out.getvalue()
+    assert "Training parameters are pre-loaded from the parameter file in data folder!" in log
+    assert "Stages 0-1 are loaded" in log
+    assert "===== TRAINING 0-stage =====" not in log and "===== TRAINING 2-stage =====" in log
+    assert b.stageParams.maxFalseAlarm == pytest.approx(0.5)
+    assert len(b.stageClassifiers) >= 3
+    for sa, sb in zip(a.stageClassifiers, b.stageClassifiers[:2]):
+        assert sb.threshold == float(np.float32(sa.threshold))
+        assert len(sa.trees) == len(sb.trees)
+        for ta, tb in zip(sa.trees, sb.trees):
+            assert ta[0]["var_idx"] == tb[0]["var_idx"]
+            if ftype == orc.HAAR:
+                assert float(np.float32(ta[0]["c"])) == tb[0]["c"]
+            else:
+                assert list(ta[0]["subset"]) == list(tb[0]["subset"])
+            assert float(np.float32(ta[ta[0]["left"]]["value"])) == tb[tb[0]["left"]]["value"]
+    # the loaded stages really are in the mining cascade: every mined negative passes them
+    st = b.stageClassifiers[0]
+    n = b.curNumSamples
+    preds = st.predict(b.featureEvaluator, 0, False, n)
+    assert (preds == 1.0).all()
+    assert os.path.exists(os.path.join(d, "stage2.xml"))
+    det = cv2.CascadeClassifier(os.path.join(d, "cascade.xml"))
+    assert not det.empty()

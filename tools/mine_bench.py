@@ -15,7 +15,8 @@ pos = synth.make_positives(1400, 24, 24)
 small = synth.make_backgrounds(12, 480, 360, seed0=500, clutter=2.5)
 ctx = ccb.Context(0)
 cc = CvCascadeClassifier(ctx, out=io.StringIO())
-ok = cc.train("/tmp/mine_bench_cascade", "pos.vec", "bg.txt", 1000, 2000, 1024, 1024, nstages, CvCascadeParams(0, 0, (24, 24)),
+import tempfile
+ok = cc.train(tempfile.mkdtemp(prefix="mine_bench_cascade_"), "pos.vec", "bg.txt", 1000, 2000, 1024, 1024, nstages, CvCascadeParams(0, 0, (24, 24)),
               ccb.CvHaarFeatureParams(mode), ccb.CvCascadeBoostParams(), positives=pos, backgrounds=small)
 print("trained %d stages in %.1fs: weak per stage %s" % (len(cc.stageClassifiers), time.time() - t0, [len(s.trees) for s in cc.stageClassifiers]))
 for t in cc.timings:
