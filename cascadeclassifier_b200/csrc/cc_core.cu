@@ -84,6 +84,16 @@ int cc_create(int device, cc_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   CC_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   ctx->own_stream = true;
+  {
+    // temporaries come from the stream-ordered pool (cudaMallocAsync); keep freed blocks in the pool across
+    // synchronisations instead of returning them to the driver every time (the default release threshold is 0)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    cudaGetLastError();
+  }
   *out = ctx;
   return CC_OK;
 }

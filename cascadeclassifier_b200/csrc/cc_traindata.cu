@@ -612,14 +612,14 @@ k_sort_rows(const float* __restrict__ fval, int n_stride, int N, int nrows, uint
 // stable, and one distribution pass into many value buckets followed by an exact ranking inside each bucket replaces
 // the eight stable radix passes:
 //   A  load the row (registers), row statistics -> a monotone linear bucket map  b(v) = clamp((v - lo) * scale)
-//      over [mean - 3.5 sd, mean + 3.5 sd] ∩ [min, max]  (any lo / scale gives a correct sort; float subtraction,
+//      over [mean - 4.5 sd, mean + 4.5 sd] ∩ [min, max]  (any lo / scale gives a correct sort; float subtraction,
 //      multiplication by a positive constant and truncation are monotone, so b is non-decreasing in v);
 //   B  bucket histogram (shared-memory atomics);   C  exclusive scan of the B counters + the cost sum(k^2);
 //   D  distribution: slot = atomicAdd(cursor[b]), composite stored there (order inside a bucket is arbitrary);
 //   E  rank: position = bucket start + #(composites of the bucket smaller than mine); the index and the value go
 //      straight to their final place in HBM (a warp writes a permutation of 32 consecutive positions).
 // With B ~ N / 2 buckets a row costs ~ N * (k_avg + const) compares instead of 8 passes over N.  Rows where the map
-// is poor (sum(k^2) above a limit: long runs of equal values, outliers far beyond 3.5 sd) are appended to a list and
+// is poor (sum(k^2) above a limit: long runs of equal values, outliers far beyond 4.5 sd) are appended to a list and
 // sorted by k_sort_rows afterwards.  Output is bit-identical to k_sort_rows (test_sort_paths_agree).
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned long long BSORT_ONE = 0x3FF0000000000000ull;     // composites are stored as doubles in [1, 2)
@@ -685,7 +685,7 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
       const float mean = sm * inv_n;
       const float var = fmaxf(sq * inv_n - mean * mean, 0.f);
       const float sd = sqrtf(var);
-      float a = mean - 3.5f * sd, b = mean + 3.5f * sd;
+      float a = mean - 4.5f * sd, b = mean + 4.5f * sd;
       if (!(a > mn)) a = mn;                           // also taken when the statistics overflowed (inf / nan)
       if (!(b < mx)) b = mx;
       const float w = b - a;

@@ -185,21 +185,26 @@ def test_resume_from_stage_files(gpu_ctx, tmp_path, ftype, mode):
         fp.mode = mode
     d = str(tmp_path)
     a = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
-    assert a.train(d, "pos.vec", "bg.txt", 200, 300, 1024, 1024, 2, CvCascadeParams(0, ftype, (24, 24)), fp, ccb.CvCascadeBoostParams(),
-                   positives=pos, backgrounds=bgs)
-    assert len(a.stageClassifiers) == 2
+    assert a.train(d, "pos.vec", "bg.txt", 200, 300, 1024, 1024, 2, CvCascadeParams(0, ftype, (24, 24)), fp,
+                   ccb.CvCascadeBoostParams(maxFalseAlarm=0.7), positives=pos, backgrounds=bgs)
+    assert len(a.stageClassifiers) >= 1
+    # an interrupted run: only params.xml and stage0.xml are left in the directory
+    for f in os.listdir(d):
+        if f not in ("params.xml", "stage0.xml"):
+            os.remove(os.path.join(d, f))
     out = io.StringIO()
     b = CvCascadeClassifier(gpu_ctx, out=out)
-    # other parameters on the command line are ignored in favour of params.xml, as in the reference
-    assert b.train(d, "pos.vec", "bg.txt", 200, 300, 1024, 1024, 4, CvCascadeParams(0, ftype, (24, 24)), fp,
+    # other parameters on the command line are ignored in favour of params.xml, as in the reference; numStages is not
+    # part of params.xml (20 stages: the acceptance-ratio rule does not fire on the first rejected windows)
+    assert b.train(d, "pos.vec", "bg.txt", 200, 300, 1024, 1024, 20, CvCascadeParams(0, ftype, (24, 24)), fp,
                    ccb.CvCascadeBoostParams(maxFalseAlarm=0.4), positives=pos, backgrounds=bgs)
     log = out.getvalue()
     assert "Training parameters are pre-loaded from the parameter file in data folder!" in log
-    assert "Stages 0-1 are loaded" in log
-    assert "===== TRAINING 0-stage =====" not in log and "===== TRAINING 2-stage =====" in log
-    assert b.stageParams.maxFalseAlarm == pytest.approx(0.5)
-    assert len(b.stageClassifiers) >= 3
-    for sa, sb in zip(a.stageClassifiers, b.stageClassifiers[:2]):
+    assert "Stage 0 is loaded" in log
+    assert "===== TRAINING 0-stage =====" not in log and "===== TRAINING 1-stage =====" in log
+    assert b.stageParams.maxFalseAlarm == pytest.approx(0.7)
+    assert len(b.stageClassifiers) >= 2, log[-1500:]
+    for sa, sb in zip(a.stageClassifiers[:1], b.stageClassifiers[:1]):
         assert sb.threshold == float(np.float32(sa.threshold))
         assert len(sa.trees) == len(sb.trees)
         for ta, tb in zip(sa.trees, sb.trees):
@@ -214,6 +219,6 @@ def test_resume_from_stage_files(gpu_ctx, tmp_path, ftype, mode):
     n = b.curNumSamples
     preds = st.predict(b.featureEvaluator, 0, False, n)
     assert (preds == 1.0).all()
-    assert os.path.exists(os.path.join(d, "stage2.xml"))
+    assert os.path.exists(os.path.join(d, "stage1.xml"))
     det = cv2.CascadeClassifier(os.path.join(d, "cascade.xml"))
     assert not det.empty()
