@@ -88,7 +88,7 @@ struct LevelDesc {
   int row0;                // fast path: this entry is a horizontal strip of its level starting at level row row0 (0: whole level)
   int pitch;               // row pitch of the integral planes (>= lw + 1; the fast path pads it to a multiple of 4)
   int ppitch;              // row pitch of the level pixels in the pool (>= lw)
-  int pad1;
+  int spitch;              // row pitch of the source image in HBM (>= sw, a multiple of 16: rows can be staged with 16-byte copies)
 };
 
 // cv::resize(src, dst, INTER_LINEAR_EXACT), 8-bit single channel: 8.8 fixed-point coefficients per axis,
@@ -115,7 +115,7 @@ __global__ void k_resize_levels(const LevelDesc* __restrict__ levels, int nlevel
     lin_coef(L.scale_x, x, L.sw, ox, cx0, cx1, mx);
     lin_coef(L.scale_y, L.row0 + y, L.sh, oy, cy0, cy1, my);
     auto hrow = [&](int row) -> uint32_t {
-      const uint8_t* s = L.src + (size_t)row * L.sw;
+      const uint8_t* s = L.src + (size_t)row * L.spitch;
       if (mx == 1) return (uint32_t)s[0] * 256u;
       if (mx == 2) return (uint32_t)s[L.sw - 1] * 256u;
       return (uint32_t)s[ox] * cx0 + (uint32_t)s[ox + 1] * cx1;
@@ -239,8 +239,10 @@ constexpr int LB_MAXDIM = LB_PPT * LB_MAX_THREADS - 1;  // lw + 1 <= 2048 plane 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS)
 k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order, uint8_t* __restrict__ pool, uint32_t* __restrict__ sum,
-            uint32_t* __restrict__ sq, uint32_t* __restrict__ tilted) {
+            uint32_t* __restrict__ sq, uint32_t* __restrict__ tilted, int sp) {
   constexpr int NW = THREADS / 32;
+  // the two source rows of a level row, staged four level rows ahead with 16-byte cp.async copies: [y & 3][row][sp]
+  extern __shared__ __align__(16) uint8_t s_src[];
   __shared__ uint32_t s_bpix[2][THREADS];       // a thread's last pixel of the row (the left neighbour's apex pixel)
   __shared__ uint32_t s_bd1[2][THREADS];        // D1 of the previous row at the thread's last plane column
   __shared__ uint32_t s_bd2[2][THREADS + 1];    // D2 of the previous row at the thread's first plane column
@@ -249,7 +251,7 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
   const LevelDesc L = levels[order[blockIdx.x]];      // tallest strips first: a strip is one serial chain of rows
   const int t = threadIdx.x, lane = t & 31;
   const int warp = __shfl_sync(0xffffffffu, t >> 5, 0);
-  const int lw = L.lw, lh = L.lh, sw = L.sw, sh = L.sh, pitch = L.pitch;
+  const int lw = L.lw, lh = L.lh, sw = L.sw, sh = L.sh, pitch = L.pitch, spitch = L.spitch;
   const uint8_t* __restrict__ src = L.src;
   const int x0 = LB_PPT * t;
   // per-column x coefficients (registers: source column | c1 << 16), per-row y coefficients (shared)
@@ -280,20 +282,41 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
   int xa[LB_PPT], xb[LB_PPT];
   bool in[LB_PPT];
 #pragma unroll
-  for (int k = 0; k < LB_PPT; ++k) { in[k] = x0 + k < lw; xa[k] = xc[k] & 0xFFFF; xb[k] = min(xa[k] + 1, sw - 1); }
+  uint32_t cx0[LB_PPT], cx1[LB_PPT];                  // horizontal weights of the thread's columns (row-invariant)
+  for (int k = 0; k < LB_PPT; ++k) {
+    in[k] = x0 + k < lw; xa[k] = xc[k] & 0xFFFF; xb[k] = min(xa[k] + 1, sw - 1);
+    cx1[k] = (uint32_t)xc[k] >> 16; cx0[k] = 256u - cx1[k];
+  }
   // source bytes of row y are fetched one row ahead
   uint32_t nb[4 * LB_PPT];
 #pragma unroll
   for (int k = 0; k < 4 * LB_PPT; ++k) nb[k] = 0;
-  auto fetch = [&](int y) {
-    const int yo = s_yo[y];
+  const uint32_t s_src_addr = (uint32_t)__cvta_generic_to_shared(s_src);
+  const int chunks = spitch >> 4;                     // 16-byte chunks per source row (the pitch is a multiple of 16)
+  auto stage = [&](int y) {                           // all threads: source rows of level row y -> buffer y & 1
+    const int yo = s_yo[min(y, lh - 1)];
     const int r0 = yo & 0xFFFF, r1 = min(r0 + 1, sh - 1);
-    const uint8_t* a = src + (size_t)r0 * sw;
-    const uint8_t* b = src + (size_t)r1 * sw;
+    const uint32_t dst = s_src_addr + (uint32_t)((y & 3) * 2 * sp);
+    for (int i = t; i < 2 * chunks; i += THREADS) {
+      const int rr = i >= chunks ? 1 : 0, c = i - rr * chunks;
+      const uint8_t* g = src + (size_t)(rr ? r1 : r0) * spitch + (size_t)c * 16;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst + (uint32_t)(rr * sp + c * 16)), "l"(g) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto fetch = [&](int y) {                           // this thread's 16 source bytes of level row y, from the staged rows
+    const uint8_t* a = s_src + (y & 3) * 2 * sp;
+    const uint8_t* b = a + sp;
 #pragma unroll
     for (int k = 0; k < LB_PPT; ++k)
       if (in[k]) { nb[4 * k] = a[xa[k]]; nb[4 * k + 1] = a[xb[k]]; nb[4 * k + 2] = b[xa[k]]; nb[4 * k + 3] = b[xb[k]]; }
   };
+  stage(0);                                           // (row indices beyond the level are clamped: every thread commits
+  stage(1);                                           //  the same number of groups)
+  stage(2);
+  stage(3);
+  asm volatile("cp.async.wait_group 2;" ::: "memory");   // rows 0 and 1 have landed
+  __syncthreads();
   if (lh > 0 && warp_on) fetch(0);
   uint32_t* Srow = S + x0;
   uint32_t* Qrow = Q ? Q + x0 : nullptr;
@@ -304,16 +327,17 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
     uint32_t v[LB_PPT] = {0, 0, 0, 0};
     uint32_t i1 = 0, i2 = 0, tot1 = 0, tot2 = 0;
     Srow += pitch; if (Q) Qrow += pitch; if (T) Trow += pitch;
+    stage(y + 4);                                     // buffer y & 3 was consumed by fetch(y) before the previous barrier
     if (warp_on) {
       const uint32_t cy1 = (uint32_t)(s_yo[y] >> 16), cy0 = 256u - cy1;
 #pragma unroll
       for (int k = 0; k < LB_PPT; ++k) {
-        const uint32_t c1 = (uint32_t)xc[k] >> 16, c0 = 256u - c1;
+        const uint32_t c1 = cx1[k], c0 = cx0[k];
         const uint32_t val = ((nb[4 * k] * c0 + nb[4 * k + 1] * c1) * cy0 + (nb[4 * k + 2] * c0 + nb[4 * k + 3] * c1) * cy1 + 32768u) >> 16;
         v[k] = in[k] ? val : 0u;
       }
       if (y + 1 < lh) fetch(y + 1);
-      if (in[0]) *reinterpret_cast<uint32_t*>(drow) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);    // pool rows are padded to 4
+      if (pool && in[0]) *reinterpret_cast<uint32_t*>(drow) = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);    // pool rows are padded to 4
       s_bpix[buf][t] = v[3];
       // block-wide exclusive scan of the per-thread row totals (pixels and squares)
       tot1 = (v[0] + v[1]) + (v[2] + v[3]);
@@ -327,11 +351,11 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
       if (lane == 31) { s_wt[buf][0][warp] = i1; s_wt[buf][1][warp] = i2; }
     }
     drow += L.ppitch;
+    asm volatile("cp.async.wait_group 2;" ::: "memory");   // this thread's copies for row y + 2 have landed (rows y + 3, y + 4 may be in flight)
     __syncthreads();
     if (!warp_on) continue;
     uint32_t w1 = (lane < NW && lane < warp) ? s_wt[buf][0][lane] : 0u, w2 = (lane < NW && lane < warp) ? s_wt[buf][1][lane] : 0u;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) { w1 += __shfl_xor_sync(0xffffffffu, w1, d); w2 += __shfl_xor_sync(0xffffffffu, w2, d); }
+    w1 = __reduce_add_sync(0xffffffffu, w1); w2 = __reduce_add_sync(0xffffffffu, w2);       // REDUX: totals of the warps to the left
     if (!on) continue;
     // exclusive row prefixes at the thread's plane columns, accumulated down the columns
     {
@@ -602,7 +626,7 @@ k_tile_cascade(const LevelDesc* __restrict__ levels, const TileDesc* __restrict_
   const int nwx = min(TW, L.nx - ix0), nwy = min(TH, L.ny - iy0);
   const int aw = (nwx - 1) * sx + W, ah = (nwy - 1) * sy + H;                 // pixels of this tile
   const int lx0 = L.x0 + ix0 * sx, ly0 = L.y0 + iy0 * sy;                     // tile origin in level coordinates
-  const int sw = L.sw, sh = L.sh;
+  const int sw = L.sw, sh = L.sh, spitch = L.spitch;
   const uint8_t* __restrict__ src = L.src;
   // ---- phase 0: resize coefficients, zero borders of the planes ----
   for (int i = t; i < aw + ah; i += 256) {
@@ -618,8 +642,8 @@ k_tile_cascade(const LevelDesc* __restrict__ levels, const TileDesc* __restrict_
     const int yo = ycoef[y];
     const int r0 = yo & 0xFFFF, r1 = min(r0 + 1, sh - 1);
     const uint32_t cy1 = (uint32_t)yo >> 16, cy0 = 256u - cy1;
-    const uint8_t* a = src + (size_t)r0 * sw;
-    const uint8_t* b = src + (size_t)r1 * sw;
+    const uint8_t* a = src + (size_t)r0 * spitch;
+    const uint8_t* b = src + (size_t)r1 * spitch;
     uint32_t c1s = 0, c2s = 0;
     for (int xb = 0; xb < aw; xb += 32) {
       const int x = xb + lane;
@@ -716,8 +740,8 @@ __global__ void k_gather_resize(const LevelDesc* __restrict__ levels, int nlevel
     int ox, cx0, cx1, mx, oy, cy0, cy1, my;
     lin_coef(L.scale_x, x, L.sw, ox, cx0, cx1, mx);
     lin_coef(L.scale_y, y, L.sh, oy, cy0, cy1, my);
-    const uint8_t* a = L.src + (size_t)oy * L.sw;
-    const uint8_t* bb = L.src + (size_t)min(oy + 1, L.sh - 1) * L.sw;
+    const uint8_t* a = L.src + (size_t)oy * L.spitch;
+    const uint8_t* bb = L.src + (size_t)min(oy + 1, L.sh - 1) * L.spitch;
     const int xn = min(ox + 1, L.sw - 1);
     const uint32_t val = ((uint32_t)a[ox] * cx0 + (uint32_t)a[xn] * cx1) * (uint32_t)cy0 + ((uint32_t)bb[ox] * cx0 + (uint32_t)bb[xn] * cx1) * (uint32_t)cy1;
     dst[t] = (uint8_t)((val + 32768u) >> 16);
@@ -735,7 +759,7 @@ __global__ void k_list_to_bitmap(const unsigned int* __restrict__ list, const un
 }
 
 // ---- host-side state ----------------------------------------------------------------------------------
-struct BgImage { int w = 0, h = 0; uint8_t* d_px = nullptr; };
+struct BgImage { int w = 0, h = 0, pitch = 0; uint8_t* d_px = nullptr; };      // pitch: multiple of 16 bytes
 
 struct MineState {
   std::vector<BgImage> bgs;
@@ -940,7 +964,7 @@ static void fill_level(const NegStream& ns, LevelDesc& L) {
   L.scale_y = 1.0 / ((double)ns.lh / (double)im.h);
   L.x0 = ns.offX; L.y0 = ns.offY; L.step_x = ns.stepX(); L.step_y = ns.stepY();
   L.nx = ns.countX(); L.ny = ns.countY();
-  L.row0 = 0; L.pad1 = 0; L.owned = 1; L.pitch = L.lw + 1; L.ppitch = L.lw;
+  L.row0 = 0; L.spitch = im.pitch; L.owned = 1; L.pitch = L.lw + 1; L.ppitch = L.lw;
 }
 
 // upload the cascade as flat arrays
@@ -1311,7 +1335,8 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
     ScopedTimer tm(ctx, "mine", 0);
     int launches = 0;
     bool fused = !m->force_unfused;
-    for (const LevelDesc& L : dl) fused = fused && L.lw <= LB_MAXDIM && L.lh <= LB_MAXDIM && L.sh <= 65535;
+    int src_pitch_max = 16;
+    for (const LevelDesc& L : dl) { fused = fused && L.lw <= LB_MAXDIM && L.lh <= LB_MAXDIM && L.sh <= 65535 && L.spitch <= 8192; src_pitch_max = std::max(src_pitch_max, L.spitch); }
     if (fused) {
       // three width classes (CTA of 128 / 256 / 512 threads, 4 columns per thread), each tallest-first
       std::vector<int> order[3];
@@ -1329,9 +1354,17 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
       uint32_t* psq = haar ? m->d_psq : nullptr;
       uint32_t* ptl = tilted ? m->d_ptilt : nullptr;
       // widest class first: its levels are the longest chains
-      if (off[3] > off[2]) { k_lvl_build<512><<<off[3] - off[2], 512, 0, ctx->stream>>>(d_levels, m->d_order + off[2], m->d_pool, m->d_psum, psq, ptl); ++launches; }
-      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, 0, ctx->stream>>>(d_levels, m->d_order + off[1], m->d_pool, m->d_psum, psq, ptl); ++launches; }
-      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, 0, ctx->stream>>>(d_levels, m->d_order + off[0], m->d_pool, m->d_psum, psq, ptl); ++launches; }
+      // the accepted windows are recomputed from the source images (k_gather_resize), so the fused builder keeps no level pixels
+      uint8_t* pool = nullptr;
+      const size_t ssm = (size_t)8 * src_pitch_max;
+      if (ssm > 24 * 1024) {                          // static + dynamic beyond 48 KB needs the opt-in (images wider than 3072 pixels)
+        CC_CUDA(cudaFuncSetAttribute(k_lvl_build<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        CC_CUDA(cudaFuncSetAttribute(k_lvl_build<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+        CC_CUDA(cudaFuncSetAttribute(k_lvl_build<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
+      }
+      if (off[3] > off[2]) { k_lvl_build<512><<<off[3] - off[2], 512, ssm, ctx->stream>>>(d_levels, m->d_order + off[2], pool, m->d_psum, psq, ptl, src_pitch_max); ++launches; }
+      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, ssm, ctx->stream>>>(d_levels, m->d_order + off[1], pool, m->d_psum, psq, ptl, src_pitch_max); ++launches; }
+      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, ssm, ctx->stream>>>(d_levels, m->d_order + off[0], pool, m->d_psum, psq, ptl, src_pitch_max); ++launches; }
     } else {
       k_resize_levels<<<grid_for(ctx, (long long)pool_px, 256), 256, 0, ctx->stream>>>(d_levels, nlv, (long long)pool_px, m->d_pool);
       k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
@@ -1474,9 +1507,9 @@ int cc_bg_register(cc_ctx* ctx, const uint8_t* host_gray, int w, int h) {
   MineState* m = mine_state(ctx);
   CC_CUDA(cudaSetDevice(ctx->device));
   BgImage b;
-  b.w = w; b.h = h;
-  CC_CUDA(cudaMalloc(&b.d_px, (size_t)w * h));
-  CC_CUDA(cudaMemcpyAsync(b.d_px, host_gray, (size_t)w * h, cudaMemcpyHostToDevice, ctx->stream));
+  b.w = w; b.h = h; b.pitch = (w + 15) & ~15;
+  CC_CUDA(cudaMalloc(&b.d_px, (size_t)b.pitch * h));
+  CC_CUDA(cudaMemcpy2DAsync(b.d_px, (size_t)b.pitch, host_gray, (size_t)w, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
   m->bgs.push_back(b);
   return CC_OK;

@@ -169,6 +169,27 @@ def test_mining_paths_agree(gpu_ctx, tmp_path, ftype, mode):
             assert (a[0] == b[0]).all() and np.float32(a[2]) == np.float32(b[2])
             if a[1] is not None and b[1] is not None:
                 assert (np.asarray(a[1]) == np.asarray(b[1])).all()
+    # images whose width is not a multiple of the 16-byte row pitch, and one wider than 3072 pixels (the fused builder stages
+    # source rows in shared memory; wide rows take the opt-in shared-memory size): literal path vs planes vs tiles again
+    from cascadeclassifier_b200 import synth
+    odd = [synth.make_background(3500, 60, 77, clutter=1.0), synth.make_background(333, 77, 78, clutter=2.0),
+           synth.make_background(57, 33, 79), synth.make_background(1001, 99, 80, clutter=2.0)]
+    check(lib.cc_bg_clear(h), "cc_bg_clear")
+    for im in odd:
+        im = np.ascontiguousarray(im)
+        check(lib.cc_bg_register(h, im.ctypes.data_as(C.c_void_p), im.shape[1], im.shape[0]), "cc_bg_register")
+    results = []
+    for m in (2, 3, 0):
+        check(lib.cc_mine_set_mode(h, m), "cc_mine_set_mode")
+        st = _lib.ReaderState()
+        consumed, got = C.c_int64(0), C.c_int32(0)
+        check(lib.cc_mine_negatives(h, 200, 120, 1e-7, C.byref(st), C.byref(consumed), C.byref(got)), "cc_mine_negatives")
+        results.append((got.value, consumed.value, _state_dict(st), cc.featureEvaluator.images(200, got.value)))
+    check(lib.cc_mine_set_mode(h, 0), "cc_mine_set_mode")
+    assert results[0][0] > 0
+    for r in results[1:]:
+        assert r[:3] == results[0][:3]
+        assert np.array_equal(r[3], results[0][3])
 
 
 @pytest.mark.parametrize("ftype,mode", [(orc.HAAR, orc.ALL), (orc.LBP, 0)])
