@@ -293,7 +293,7 @@ def mining_leg(device, dist=None, dev=None, world=1):
     import tempfile
     cc.train(tempfile.mkdtemp(prefix="bench_mining_cascade_r%d_" % device), "pos.vec", "bg.txt", 1000, 2000, 1024, 1024, 8, CvCascadeParams(0, 0, (WIN, WIN)),
              ccb.CvHaarFeatureParams(HAAR_MODE_ALL), ccb.CvCascadeBoostParams(), positives=pos, backgrounds=small)
-    nimg = 256
+    nimg = 1024                     # 4 batches of 4 M windows per rank at N = 1: the two-deep batch pipeline is in steady state
     big = [synth.make_background(1920, 1080, 9000 + i, clutter=0.3) for i in range(4)]
     _lib.check(lib.cc_bg_clear(h), "cc_bg_clear")
     for i in range(nimg):
