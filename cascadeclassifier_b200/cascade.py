@@ -302,6 +302,54 @@ class CvCascadeClassifier:
             self.stageClassifiers.append(st)
         return True
 
+    # -baseFormatSave: the legacy "opencv-haar-classifier" layout, Haar only (src/cascadeclassifier.cpp:457-531)
+    def _save_base_format(self, filename):
+        if self.cascadeParams.featureType != CvFeatureParams.HAAR:
+            raise CascadeCudaError("old file format is used for Haar-like features only")
+        fs = XmlWriter(filename)
+        fs.start_map("cascade", type_name="opencv-haar-classifier", flow=True)
+        fs.write_flow_seq("size", [int(self.cascadeParams.winSize[0]), int(self.cascadeParams.winSize[1])])
+        fs.start_seq("stages")
+        for si, st in enumerate(self.stageClassifiers):
+            fs.start_map(None)
+            fs.start_seq("trees")
+            for tr in st.trees:
+                fs.start_seq(None)
+                queue = [0]
+                total_inner = 0
+                while queue:
+                    nd = tr[queue.pop(0)]
+                    fs.start_map(None)
+                    fs.start_map("feature")
+                    rects, wts, tilted = self.featureEvaluator.feature(nd["var_idx"])
+                    fs.start_seq("rects")
+                    for ri in range(3):
+                        if rects[ri][2] == 0:
+                            break
+                        fs.write_flow_seq(None, [int(rects[ri][0]), int(rects[ri][1]), int(rects[ri][2]), int(rects[ri][3]), float(wts[ri])])
+                    fs.end_seq()
+                    fs.write("tilted", int(tilted))
+                    fs.end_map()
+                    fs.write("threshold", float(np.float32(nd["c"])))
+                    for side, node_key, val_key in (("left", "left_node", "left_val"), ("right", "right_node", "right_val")):
+                        ch = tr[nd[side]]
+                        if ch["left"] >= 0:
+                            queue.append(nd[side])
+                            total_inner += 1
+                            fs.write(node_key, total_inner)
+                        else:
+                            fs.write(val_key, float(ch["value"]))
+                    fs.end_map()
+                fs.end_seq()
+            fs.end_seq()
+            fs.write("stage_threshold", float(np.float32(st.threshold)))
+            fs.write("parent", si - 1)
+            fs.write("next", -1)
+            fs.end_map()
+        fs.end_seq()
+        fs.end_map()
+        fs.release()
+
     def predict(self, sampleIdx):
         for st in self.stageClassifiers:
             if st.predict(self.featureEvaluator, sampleIdx) == 0.0:
@@ -342,8 +390,7 @@ class CvCascadeClassifier:
 
     def save(self, filename, baseFormat=False):
         if baseFormat:
-            raise CascadeCudaError("old file format (-baseFormatSave) is written by the unchanged reference host code; "
-                                   "not part of the GPU path")
+            return self._save_base_format(filename)
         fs = XmlWriter(filename)
         fmap = self.getUsedFeaturesIdxMap()
         fs.start_map("cascade")

@@ -17,8 +17,12 @@ class XmlWriter:
         if not self.fs.isOpened():
             raise IOError("file %s can not be opened" % path)
 
-    def start_map(self, name):
-        self.fs.startWriteStruct(name or "", self.cv2.FILE_NODE_MAP)
+    def start_map(self, name, type_name=None, flow=False):
+        flags = self.cv2.FILE_NODE_MAP | (self.cv2.FILE_NODE_FLOW if flow else 0)
+        if type_name:
+            self.fs.startWriteStruct(name or "", flags, type_name)       # `fs << "{:" "type_id"`
+        else:
+            self.fs.startWriteStruct(name or "", flags)
 
     def end_map(self):
         self.fs.endWriteStruct()

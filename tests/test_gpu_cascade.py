@@ -243,3 +243,30 @@ def test_resume_from_stage_files(gpu_ctx, tmp_path, ftype, mode):
     assert os.path.exists(os.path.join(d, "stage1.xml"))
     det = cv2.CascadeClassifier(os.path.join(d, "cascade.xml"))
     assert not det.empty()
+
+
+def test_base_format_save_is_loadable(gpu_ctx, tmp_path):
+    """-baseFormatSave (src/cascadeclassifier.cpp:457-531): the legacy opencv-haar-classifier XML is written for Haar
+    cascades and OpenCV's detector loads it (the reference's own integration test checks exactly that,
+    test_integration.cpp:287-343); other feature types are refused with the reference's message."""
+    import cv2
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    pos, bgs = _data(260, 6)
+    cc = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
+    assert cc.train(str(tmp_path), "pos.vec", "bg.txt", 200, 300, 1024, 1024, 3, CvCascadeParams(0, orc.HAAR, (24, 24)),
+                    ccb.CvHaarFeatureParams(orc.ALL), ccb.CvCascadeBoostParams(maxDepth=2), baseFormatSave=True, positives=pos, backgrounds=bgs)
+    path = os.path.join(str(tmp_path), "cascade.xml")
+    text = open(path).read()
+    assert 'type_id="opencv-haar-classifier"' in text and "<stage_threshold>" in text and "<left_val>" in text
+    det = cv2.CascadeClassifier(path)
+    assert not det.empty()
+    # the detector built from the legacy file fires on a positive sample pasted into a flat scene
+    scene = np.full((96, 96), 128, np.uint8)
+    scene[30:54, 40:64] = pos[0]
+    hits = det.detectMultiScale(scene, scaleFactor=1.1, minNeighbors=0, minSize=(24, 24), maxSize=(24, 24))
+    assert len(hits) >= 1
+    lbp = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
+    with pytest.raises(ccb.CascadeCudaError, match="Haar-like features only"):
+        lbp.train(str(tmp_path / "lbp"), "pos.vec", "bg.txt", 200, 300, 1024, 1024, 1, CvCascadeParams(0, orc.LBP, (24, 24)),
+                  ccb.CvFeatureParams.create(orc.LBP), ccb.CvCascadeBoostParams(), baseFormatSave=True, positives=pos, backgrounds=bgs)
