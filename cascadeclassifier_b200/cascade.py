@@ -156,10 +156,8 @@ class CvCascadeClassifier:
         dirName = cascadeDirName if cascadeDirName[-1] in "/\\" else cascadeDirName + "/"
         self.numPos, self.numNeg, self.numStages = numPos, numNeg, numStages
         self.cascadeParams, self.featureParams, self.stageParams = cascadeParams, featureParams, stageParams
-        if self.ctx is None:
-            self.ctx = Context(0)
         W, H = cascadeParams.winSize
-        try:
+        try:        # imgReader.create comes first in the reference too (src/cascadeclassifier.cpp:163-168)
             if positives is None:
                 positives = synth.read_vec(posFilename, W, H)
             if backgrounds is None:
@@ -167,6 +165,8 @@ class CvCascadeClassifier:
         except (IOError, OSError, ValueError):
             out.write("Image reader can not be created from -vec %s and -bg %s.\n" % (posFilename, negFilename))
             return False
+        if self.ctx is None:
+            self.ctx = Context(0)
         self.stageClassifiers = []
         if not self.load(dirName):
             self.cascadeParams, self.featureParams, self.stageParams = cascadeParams, featureParams, stageParams

@@ -185,3 +185,25 @@ def test_stage_xml_write_read_round_trip(tmp_path):
             assert walk(a, 0) == walk(b, 0)
         # and the C-side stage built from the read trees is what cc_cascade_set_stages consumes
         assert back.c_stage().num_weak == len(trees)
+
+
+def test_train_error_paths_of_the_reference(tmp_path):
+    """test_integration.cpp:221-281: a missing .vec makes train() return false (message as the reference prints it, no
+    cascade.xml), an empty cascade directory name is rejected up front.  Both fail before any GPU work."""
+    import io
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    bg = tmp_path / "bg.txt"
+    bg.write_text("")
+    data = tmp_path / "data"
+    data.mkdir()
+    out = io.StringIO()
+    cc = CvCascadeClassifier(None, out=out)
+    ok = cc.train(str(data), str(tmp_path / "no_such.vec"), str(bg), 10, 1, 64, 64, 1, CvCascadeParams(), ccb.CvHaarFeatureParams(),
+                  ccb.CvCascadeBoostParams())
+    assert ok is False
+    assert "Image reader can not be created from -vec" in out.getvalue()
+    assert not (data / "cascade.xml").exists()
+    with pytest.raises(ccb.CascadeCudaError):
+        CvCascadeClassifier(None, out=io.StringIO()).train("", "x.vec", str(bg), 10, 1, 64, 64, 1, CvCascadeParams(1 * 0, 1, (75, 32)),
+                                                           ccb.CvFeatureParams.create(1), ccb.CvCascadeBoostParams())
