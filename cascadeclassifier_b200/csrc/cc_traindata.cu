@@ -54,24 +54,28 @@ __device__ __forceinline__ int haar_acc(const uint32_t (&w)[HAAR_MAX_TAPS], cons
 constexpr int PRECALC_THREADS = 1024;
 
 // taps: compact list of this launch (one plane), w[11] of every entry = global feature index
-template <int TILES_PER_CTA>
+// IN_GLOBAL: windows whose 32-sample tile (P * 128 bytes) does not fit in shared memory (beyond ~41x41; the reference's
+// own end-to-end tests use 75x32) read the taps straight from the tiles in HBM / L2 -- same addresses, same coalescing.
+template <int TILES_PER_CTA, bool IN_GLOBAL>
 __global__ void __launch_bounds__(PRECALC_THREADS, 1)
 k_precalc_haar(const int32_t* __restrict__ plane_tiles, const float* __restrict__ nf, const HaarTaps* __restrict__ taps,
                int nrows_launch, int rows_per_chunk, int row_base, float* __restrict__ fval, int n_stride, int P, int ntiles_used) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  int32_t* stile = reinterpret_cast<int32_t*>(smem_raw);                      // [TILES][P][32]
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TILES_PER_CTA * P * TILE * sizeof(int32_t));
-
   const int tile0 = blockIdx.x * TILES_PER_CTA;
   const int ntl = min(TILES_PER_CTA, ntiles_used - tile0);
-  const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar, tile_bytes * ntl);
-    for (int k = 0; k < ntl; ++k) bulk_g2s(stile + (size_t)k * P * TILE, plane_tiles + (size_t)(tile0 + k) * P * TILE, tile_bytes, bar);
+  const int32_t* stile = IN_GLOBAL ? plane_tiles + (size_t)tile0 * P * TILE : reinterpret_cast<const int32_t*>(smem_raw);   // [TILES][P][32]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TILES_PER_CTA * P * TILE * sizeof(int32_t));
+  if (!IN_GLOBAL) {
+    const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
+    if (threadIdx.x == 0) {
+      int32_t* dst = reinterpret_cast<int32_t*>(smem_raw);
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, tile_bytes * ntl);
+      for (int k = 0; k < ntl; ++k) bulk_g2s(dst + (size_t)k * P * TILE, plane_tiles + (size_t)(tile0 + k) * P * TILE, tile_bytes, bar);
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = PRECALC_THREADS / 32;
   const int r_begin = blockIdx.y * rows_per_chunk;
@@ -83,7 +87,7 @@ k_precalc_haar(const int32_t* __restrict__ plane_tiles, const float* __restrict_
   float nfv[TILES_PER_CTA];
 #pragma unroll
   for (int k = 0; k < TILES_PER_CTA; ++k) nfv[k] = (k < ntl) ? nf[(tile0 + k) * TILE + lane] : 0.f;
-  mbar_wait(bar, 0);
+  if (!IN_GLOBAL) mbar_wait(bar, 0);
 
   for (; r < r_end; r += nwarps) {
     const uint32_t w[HAAR_MAX_TAPS] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
@@ -397,24 +401,27 @@ k_precalc_haar_sep(const int32_t* __restrict__ sum_tiles, const float* __restric
 
 // K2 / LBP: same tiling; 16 corner taps -> 9 cell sums -> 8-bit code (lbpfeatures.h:70-83).
 constexpr int LBP_THREADS = 512;
-template <int TILES_PER_CTA>
+template <int TILES_PER_CTA, bool IN_GLOBAL>
 __global__ void __launch_bounds__(LBP_THREADS, 1)
 k_precalc_lbp(const int32_t* __restrict__ sum_tiles, const LbpTaps* __restrict__ taps, int row_first, int nrows_launch,
               int rows_per_chunk, uint8_t* __restrict__ fcode, int n_stride, int P, int ntiles_used) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  int32_t* stile = reinterpret_cast<int32_t*>(smem_raw);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TILES_PER_CTA * P * TILE * sizeof(int32_t));
   const int tile0 = blockIdx.x * TILES_PER_CTA;
   const int ntl = min(TILES_PER_CTA, ntiles_used - tile0);
-  const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
-  if (threadIdx.x == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    mbar_expect_tx(bar, tile_bytes * ntl);
-    for (int k = 0; k < ntl; ++k) bulk_g2s(stile + (size_t)k * P * TILE, sum_tiles + (size_t)(tile0 + k) * P * TILE, tile_bytes, bar);
+  const int32_t* stile = IN_GLOBAL ? sum_tiles + (size_t)tile0 * P * TILE : reinterpret_cast<const int32_t*>(smem_raw);
+  if (!IN_GLOBAL) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw + (size_t)TILES_PER_CTA * P * TILE * sizeof(int32_t));
+    const uint32_t tile_bytes = (uint32_t)P * TILE * sizeof(int32_t);
+    if (threadIdx.x == 0) {
+      int32_t* dst = reinterpret_cast<int32_t*>(smem_raw);
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      mbar_expect_tx(bar, tile_bytes * ntl);
+      for (int k = 0; k < ntl; ++k) bulk_g2s(dst + (size_t)k * P * TILE, sum_tiles + (size_t)(tile0 + k) * P * TILE, tile_bytes, bar);
+    }
+    __syncthreads();
+    mbar_wait(bar, 0);
   }
-  __syncthreads();
-  mbar_wait(bar, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = LBP_THREADS / 32;
   const int r_begin = blockIdx.y * rows_per_chunk;
   const int r_end = min(r_begin + rows_per_chunk, nrows_launch);
@@ -999,10 +1006,9 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
 
   if (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) {
     const size_t tile_bytes = (size_t)P * TILE * sizeof(int32_t);
-    const int tiles_per_cta = (2 * tile_bytes + 64 <= 200 * 1024) ? 2 : 1;
-    CC_REQUIRE(tile_bytes + 64 <= 227 * 1024, CC_ERR_UNSUPPORTED,
-               "precalc: one 32-sample integral tile of a %dx%d window (%zu B) exceeds shared memory", ctx->W, ctx->H, tile_bytes);
-    const size_t smem = tiles_per_cta * tile_bytes + 64;
+    const bool in_global = tile_bytes + 64 > 227 * 1024;         // big windows: taps read from the tiles in HBM / L2
+    const int tiles_per_cta = (in_global || 2 * tile_bytes + 64 <= 200 * 1024) ? 2 : 1;
+    const size_t smem = in_global ? 0 : tiles_per_cta * tile_bytes + 64;
     const int gx = (ntiles_used + tiles_per_cta - 1) / tiles_per_cta;
     auto chunks_for = [&](int nrows_launch) {
       // enough CTAs for >= ~8 waves, but >= 4096 rows (128 per warp) per CTA so the tile load is amortised
@@ -1042,14 +1048,17 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
         const int chunks = chunks_for(l.n);
         const int rpc = (l.n + chunks - 1) / chunks;
         dim3 grid(gx, (l.n + rpc - 1) / rpc);
-        if (tiles_per_cta == 2) {
-          CC_CUDA(cudaFuncSetAttribute(k_precalc_haar<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_precalc_haar<2><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, l.taps, l.n, rpc, ctx->row0,
-                                                                          ctx->d_fval, n_stride, P, ntiles_used);
+        if (in_global) {
+          k_precalc_haar<2, true><<<grid, PRECALC_THREADS, 0, ctx->stream>>>(l.plane, ctx->d_nf, l.taps, l.n, rpc, ctx->row0,
+                                                                            ctx->d_fval, n_stride, P, ntiles_used);
+        } else if (tiles_per_cta == 2) {
+          CC_CUDA(cudaFuncSetAttribute(k_precalc_haar<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_precalc_haar<2, false><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, l.taps, l.n, rpc, ctx->row0,
+                                                                                 ctx->d_fval, n_stride, P, ntiles_used);
         } else {
-          CC_CUDA(cudaFuncSetAttribute(k_precalc_haar<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          k_precalc_haar<1><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, l.taps, l.n, rpc, ctx->row0,
-                                                                          ctx->d_fval, n_stride, P, ntiles_used);
+          CC_CUDA(cudaFuncSetAttribute(k_precalc_haar<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          k_precalc_haar<1, false><<<grid, PRECALC_THREADS, smem, ctx->stream>>>(l.plane, ctx->d_nf, l.taps, l.n, rpc, ctx->row0,
+                                                                                 ctx->d_fval, n_stride, P, ntiles_used);
         }
         CC_CUDA(cudaGetLastError());
       }
@@ -1058,14 +1067,17 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
       const int chunks = chunks_for(ctx->nrows);
       const int rpc = (ctx->nrows + chunks - 1) / chunks;
       dim3 grid(gx, (ctx->nrows + rpc - 1) / rpc);
-      if (tiles_per_cta == 2) {
-        CC_CUDA(cudaFuncSetAttribute(k_precalc_lbp<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_precalc_lbp<2><<<grid, LBP_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
-                                                                       n_stride, P, ntiles_used);
+      if (in_global) {
+        k_precalc_lbp<2, true><<<grid, LBP_THREADS, 0, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
+                                                                     n_stride, P, ntiles_used);
+      } else if (tiles_per_cta == 2) {
+        CC_CUDA(cudaFuncSetAttribute(k_precalc_lbp<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_precalc_lbp<2, false><<<grid, LBP_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
+                                                                          n_stride, P, ntiles_used);
       } else {
-        CC_CUDA(cudaFuncSetAttribute(k_precalc_lbp<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_precalc_lbp<1><<<grid, LBP_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
-                                                                       n_stride, P, ntiles_used);
+        CC_CUDA(cudaFuncSetAttribute(k_precalc_lbp<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_precalc_lbp<1, false><<<grid, LBP_THREADS, smem, ctx->stream>>>(ctx->d_sum, ctx->d_lbp_taps, ctx->row0, ctx->nrows, rpc, ctx->d_fcode,
+                                                                          n_stride, P, ntiles_used);
       }
       CC_CUDA(cudaGetLastError());
     }

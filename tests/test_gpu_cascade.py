@@ -270,3 +270,50 @@ def test_base_format_save_is_loadable(gpu_ctx, tmp_path):
     with pytest.raises(ccb.CascadeCudaError, match="Haar-like features only"):
         lbp.train(str(tmp_path / "lbp"), "pos.vec", "bg.txt", 200, 300, 1024, 1024, 1, CvCascadeParams(0, orc.LBP, (24, 24)),
                   ccb.CvFeatureParams.create(orc.LBP), ccb.CvCascadeBoostParams(), baseFormatSave=True, positives=pos, backgrounds=bgs)
+
+
+@pytest.mark.parametrize("ftype,mode,depth,stages", [(orc.LBP, 0, 1, 1), (orc.HAAR, orc.BASIC, 1, 2), (orc.HAAR, orc.ALL, 1, 1),
+                                                     (orc.HAAR, orc.CORE, 2, 1)])
+def test_reference_integration_scenarios(gpu_ctx, tmp_path, ftype, mode, depth, stages):
+    """The shape of the reference's own end-to-end tests (test_integration.cpp:84-174,287-433): a 75x32 window, numPos=20,
+    numNeg=1, 64 MB buffers, the synthetic negative image (r*7 + c*13) & 0xFF of 256x128 (test_integration.cpp:59-64),
+    LBP / Haar BASIC / CORE / ALL, depth-2 trees.  The reference only asserts that the files exist and that
+    cv::CascadeClassifier loads cascade.xml; here the run must also equal the oracle's (21 samples, up to 2.8 M features)."""
+    import cv2
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import synth
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    W, H = 75, 32
+    pos = synth.make_positives(40, W, H, seed=5)
+    r, c = np.mgrid[0:128, 0:256]
+    bgs = [((r * 7 + c * 13) & 0xFF).astype(np.uint8)]
+    out = io.StringIO()
+    cc = CvCascadeClassifier(gpu_ctx, out=out)
+    fp = ccb.CvFeatureParams.create(ftype)
+    if ftype == orc.HAAR:
+        fp.mode = mode
+    ok = cc.train(str(tmp_path), "pos.vec", "bg.txt", 20, 1, 64, 64, stages, CvCascadeParams(0, ftype, (W, H)), fp,
+                  ccb.CvCascadeBoostParams(maxDepth=depth), positives=pos, backgrounds=bgs)
+    o = orc.Cascade(ftype, mode, W, H, 20, 1, stages, orc.boost_params(max_depth=depth), sort_mode=orc.SORT_STABLE, threads=8)
+    o.set_pos(pos)
+    o.add_bg(bgs[0])
+    o.train()
+    ref_stages = o.stages()
+    assert ok == (len(ref_stages) > 0)
+    assert len(cc.stageClassifiers) == len(ref_stages), out.getvalue()
+    from test_gpu_boost import compare_stage
+
+    class _R:
+        pass
+    for g, rs in zip(cc.stageClassifiers, ref_stages):
+        rr = _R()
+        rr.trees = rs["trees"]
+        assert compare_stage(g, rr) == len(rs["trees"])
+        assert g.threshold == pytest.approx(rs["threshold"], rel=1e-6, abs=1e-7)
+    for g, rs in zip(cc.reports, o.reports()):
+        for k in ("pos_count", "pos_consumed", "neg_count", "neg_consumed"):
+            assert g[k] == rs[k], (k, g, rs)
+    if ok:
+        for f in ("params.xml", "stage0.xml", "cascade.xml"):
+            assert os.path.exists(os.path.join(str(tmp_path), f))
+        assert not cv2.CascadeClassifier(os.path.join(str(tmp_path), "cascade.xml")).empty()

@@ -118,7 +118,9 @@ def test_hog_planes_match_oracle(gpu_ctx):
 
 
 @pytest.mark.parametrize("ftype,mode,W,H,npos,nneg", [(orc.HAAR, orc.BASIC, 24, 24, 150, 317), (orc.HAAR, orc.ALL, 24, 24, 90, 200),
-                                                      (orc.LBP, 0, 24, 24, 100, 233), (orc.HOG, 0, 48, 96, 40, 60)])
+                                                      (orc.LBP, 0, 24, 24, 100, 233), (orc.HOG, 0, 48, 96, 40, 60),
+                                                      # windows whose 32-sample integral tile exceeds shared memory (taps read from HBM / L2)
+                                                      (orc.HAAR, orc.ALL, 52, 44, 20, 45), (orc.LBP, 0, 75, 32, 30, 40)])
 def test_precalc_and_sort_match_oracle(gpu_ctx, ftype, mode, W, H, npos, nneg):
     import ctypes as C
     from cascadeclassifier_b200._lib import check
