@@ -157,3 +157,38 @@ def test_pruned_search_equals_exhaustive(gpu_ctx, bt, depth):
     F = ev.getNumFeatures()
     # far fewer rows searched exactly than an exhaustive search would touch
     assert stats["flagged_rows"] + stats["seed_rows"] < 0.25 * F * stats["searches"], stats
+
+
+_MATRIX = [
+    # ftype, mode, W, H, npos, nneg, boost parameters                                                what the case adds
+    (orc.LBP, 0, 24, 24, 150, 250, dict(boost_type=orc.DAB, weak_count=5, max_false_alarm=0.05)),   # categorical x classification (misclass)
+    (orc.LBP, 0, 24, 24, 150, 250, dict(boost_type=orc.RAB, weak_count=5, max_false_alarm=0.05)),   # categorical x classification (Gini)
+    (orc.LBP, 0, 24, 24, 150, 250, dict(boost_type=orc.LB, weak_count=4, max_false_alarm=0.05)),    # categorical x LogitBoost targets
+    (orc.LBP, 0, 32, 20, 120, 200, dict(max_depth=2, weak_count=4, max_false_alarm=0.05)),          # categorical, depth 2, non-square window
+    (orc.HAAR, orc.CORE, 20, 20, 120, 260, dict(max_depth=3, weak_count=3, max_false_alarm=0.05)),  # depth 3
+    (orc.HAAR, orc.BASIC, 24, 24, 130, 270, dict(weight_trim_rate=1.0, weak_count=6, max_false_alarm=0.02)),   # trimming off
+    (orc.HAAR, orc.BASIC, 24, 24, 130, 270, dict(weight_trim_rate=0.5, weak_count=6, max_false_alarm=0.02)),   # aggressive trimming
+    (orc.HAAR, orc.ALL, 24, 24, 130, 270, dict(min_hit_rate=0.9, max_false_alarm=0.3, weak_count=8)),          # loose hit rate: threshold index > 0
+    (orc.HAAR, orc.BASIC, 64, 48, 40, 70, dict(weak_count=3, max_false_alarm=0.05)),                # big window: tiles beyond shared memory
+    (orc.HOG, 0, 64, 64, 50, 90, dict(boost_type=orc.RAB, weak_count=4, max_false_alarm=0.05)),     # HOG x classification, square window
+    (orc.HAAR, orc.BASIC, 24, 24, 9, 14, dict(weak_count=3)),                                       # fewer samples than one 32-sample tile
+]
+
+
+@pytest.mark.parametrize("case", range(len(_MATRIX)))
+def test_stage_configuration_matrix(gpu_ctx, case):
+    """Flag combinations the CLI accepts (-bt, -maxDepth, -weightTrimRate, -minHitRate, -w / -h, feature types) that the
+    BASELINE configs do not exercise: one stage each, trees / thresholds / log rows against the oracle (trees are compared
+    up to the first float-level tie, which must not come before the first tree)."""
+    ftype, mode, W, H, npos, nneg, bp = _MATRIX[case]
+    ok, stage, ref, ev = run_pair(gpu_ctx, ftype, mode, W, H, npos, nneg, **bp)
+    assert ok == ref.ok
+    if not ref.ok:
+        return
+    agreed = compare_stage(stage, ref)
+    assert agreed >= 1
+    if agreed == len(ref.trees):
+        assert stage.threshold == pytest.approx(ref.threshold, rel=1e-6, abs=1e-7)
+        assert [r[0] for r in stage.log] == [r[0] for r in ref.log]
+        for a, b in zip(stage.log, ref.log):
+            assert a[1] == pytest.approx(b[1]) and a[2] == pytest.approx(b[2])
