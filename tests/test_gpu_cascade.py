@@ -74,12 +74,14 @@ def _run_cascade(gpu_ctx, tmp_path, ftype, mode, W, H, numPos, numNeg, numStages
     fp = ccb.CvFeatureParams.create(ftype)
     if ftype == orc.HAAR:
         fp.mode = mode
-    sp = ccb.CvCascadeBoostParams(maxFalseAlarm=kw.get("max_false_alarm", 0.5), minHitRate=kw.get("min_hit_rate", 0.995),
+    sp = ccb.CvCascadeBoostParams(boostType=kw.get("boost_type", 3), maxFalseAlarm=kw.get("max_false_alarm", 0.5),
+                                  minHitRate=kw.get("min_hit_rate", 0.995), maxDepth=kw.get("max_depth", 1),
                                   maxWeakCount=kw.get("weak_count", 100))
     ok = cc.train(str(tmp_path), "pos.vec", "bg.txt", numPos, numNeg, 1024, 1024, numStages,
                   CvCascadeParams(0, ftype, (W, H)), fp, sp, positives=pos, backgrounds=bgs)
     o = orc.Cascade(ftype, mode, W, H, numPos, numNeg, numStages,
-                    orc.boost_params(max_false_alarm=kw.get("max_false_alarm", 0.5), min_hit_rate=kw.get("min_hit_rate", 0.995),
+                    orc.boost_params(boost_type=kw.get("boost_type", orc.GAB), max_false_alarm=kw.get("max_false_alarm", 0.5),
+                                     min_hit_rate=kw.get("min_hit_rate", 0.995), max_depth=kw.get("max_depth", 1),
                                      weak_count=kw.get("weak_count", 100)), sort_mode=orc.SORT_STABLE, threads=8)
     o.set_pos(pos)
     for b in bgs:
@@ -317,3 +319,42 @@ def test_reference_integration_scenarios(gpu_ctx, tmp_path, ftype, mode, depth, 
         for f in ("params.xml", "stage0.xml", "cascade.xml"):
             assert os.path.exists(os.path.join(str(tmp_path), f))
         assert not cv2.CascadeClassifier(os.path.join(str(tmp_path), "cascade.xml")).empty()
+
+
+_CASCADES = [
+    # ftype, mode, W, H, numPos, numNeg, stages, backgrounds (w, h), parameters
+    (orc.LBP, 0, 32, 20, 150, 250, 3, (210, 150), dict()),                                   # non-square window through the level planes
+    (orc.HAAR, orc.CORE, 20, 28, 150, 250, 3, (190, 170), dict(max_depth=2)),                # depth-2 trees in the mining cascade
+    (orc.HAAR, orc.ALL, 24, 24, 150, 250, 3, (200, 160), dict(min_hit_rate=0.95, max_false_alarm=0.4)),
+    (orc.HAAR, orc.BASIC, 24, 24, 150, 250, 3, (200, 160), dict(boost_type=orc.RAB)),        # Real AdaBoost leaf values in predict()
+    (orc.HOG, 0, 48, 96, 80, 120, 2, (260, 300), dict(weak_count=6)),                        # HOG: per-window slots
+]
+
+
+@pytest.mark.parametrize("case", range(len(_CASCADES)))
+def test_cascade_configuration_matrix(gpu_ctx, tmp_path, case):
+    """Mining + stage training over several stages for flag combinations the BASELINE configs do not cover, against the
+    oracle: stages, consumed counts and the final NegReader state (comparison stops at the first float-level tie)."""
+    ftype, mode, W, H, npos, nneg, nst, (bw, bh), kw = _CASCADES[case]
+    pos, bgs = _data(npos + 60, 6, W=W, H=H, bw=bw, bh=bh, seed=11 + case)
+    ok, cc, o, log = _run_cascade(gpu_ctx, tmp_path, ftype, mode, W, H, npos, nneg, nst, pos, bgs, **kw)
+    ref_stages, ref_reports = o.stages(), o.reports()
+    from test_gpu_boost import compare_stage
+
+    class _R:
+        pass
+    exact = True
+    for s, (g, r) in enumerate(zip(cc.stageClassifiers, ref_stages)):
+        rr = _R()
+        rr.trees = r["trees"]
+        if compare_stage(g, rr) != len(r["trees"]):
+            exact = False           # a tie inside stage s: later stages legitimately differ
+            assert s >= 1 or len(r["trees"]) > 1
+            break
+        assert g.threshold == pytest.approx(r["threshold"], rel=1e-6, abs=1e-7)
+    if exact:
+        assert len(cc.stageClassifiers) == len(ref_stages), log
+        for g, r in zip(cc.reports, ref_reports):
+            for k in ("pos_count", "pos_consumed", "neg_count", "neg_consumed"):
+                assert g[k] == r[k], (k, g, r)
+        assert _state_dict(cc._reader) == o.neg_state()
