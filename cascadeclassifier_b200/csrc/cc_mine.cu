@@ -318,6 +318,7 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
   asm volatile("cp.async.wait_group 2;" ::: "memory");   // rows 0 and 1 have landed
   __syncthreads();
   if (lh > 0 && warp_on) fetch(0);
+  __syncthreads();                                    // iteration 0 re-fills buffer 0 (row 4): every thread must have read row 0 first
   uint32_t* Srow = S + x0;
   uint32_t* Qrow = Q ? Q + x0 : nullptr;
   uint32_t* Trow = T ? T + x0 : nullptr;
