@@ -293,7 +293,7 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
   for (int k = 0; k < 4 * LB_PPT; ++k) nb[k] = 0;
   const uint32_t s_src_addr = (uint32_t)__cvta_generic_to_shared(s_src);
   const int chunks = spitch >> 4;                     // 16-byte chunks per source row (the pitch is a multiple of 16)
-  auto stage = [&](int y) {                           // all threads: source rows of level row y -> buffer y & 1
+  auto stage = [&](int y) {                           // all threads: source rows of level row y -> buffer y & 3
     const int yo = s_yo[min(y, lh - 1)];
     const int r0 = yo & 0xFFFF, r1 = min(r0 + 1, sh - 1);
     const uint32_t dst = s_src_addr + (uint32_t)((y & 3) * 2 * sp);
