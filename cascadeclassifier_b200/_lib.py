@@ -97,6 +97,8 @@ def _signatures():
         "cc_mine_positives": (i32, [vp, vp, i32, i32, P(C.c_int32), P(i64), P(C.c_int32)]),
         "cc_mine_scan": (i32, [vp, i32, i32, P(i64), P(i64)]),
         "cc_mine_set_mode": (i32, [vp, i32]),
+        "cc_mine_set_cache": (i32, [vp, i32, i64]),
+        "cc_mine_get_stats": (i32, [vp, vp]),
         "cc_mine_serial_cut": (i32, [vp, i64, i64, i32, f64, P(i64), P(C.c_int32), P(i64), P(C.c_int32), vp, P(C.c_int32)]),
         "cc_reader_advance": (i32, [vp, vp, i32, i32, i32, P(ReaderState), i64, vp]),
         "cc_timing_reset": (i32, [vp]),

@@ -98,6 +98,9 @@ class CvCascadeClassifier:
         for im in backgrounds:
             im = np.ascontiguousarray(im, np.uint8)
             if im.size == 0:
+                # unreadable file: the reference keeps it in imgFilenames and nextImg() skips it without touching `round`
+                # (src/imagestorage.cpp:62-70), so it must keep its slot in the list
+                check(lib.cc_bg_register(h, None, 0, 0), "cc_bg_register")
                 continue
             check(lib.cc_bg_register(h, _p(im), im.shape[1], im.shape[0]), "cc_bg_register")
         self._reader = _lib.ReaderState()

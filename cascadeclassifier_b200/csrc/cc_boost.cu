@@ -109,7 +109,7 @@ struct BoostBuffers {
   RowBest* rowbest = nullptr;
   RowBestCat* rowbest_cat = nullptr;
   NodeStats* d_stats = nullptr;       // [CC_MAX_TREE_NODES]
-  BestSplit* d_best = nullptr;        // [1] (+ world candidates)
+  BestSplit* d_best = nullptr;        // [1 + CC_MAX_RANKS]: the local / winning candidate, then the all-gathered candidates of the ranks
   TreeSummary* d_summary = nullptr;
   DevNode* d_tree = nullptr;          // [CC_MAX_TREE_NODES]
   NodeStats* h_stats = nullptr;       // pinned
@@ -151,7 +151,7 @@ static int ensure_boost(cc_ctx* ctx, int N, size_t nrows) {
   BoostBuffers* b = ctx->boost;
   if (!b->d_stats) {
     CC_CUDA(cudaMalloc(&b->d_stats, sizeof(NodeStats) * CC_MAX_TREE_NODES));
-    CC_CUDA(cudaMalloc(&b->d_best, sizeof(BestSplit) * 16));
+    CC_CUDA(cudaMalloc(&b->d_best, sizeof(BestSplit) * (1 + CC_MAX_RANKS)));
     CC_CUDA(cudaMalloc(&b->d_summary, sizeof(TreeSummary)));
     CC_CUDA(cudaMalloc(&b->d_tree, sizeof(DevNode) * CC_MAX_TREE_NODES));
     CC_CUDA(cudaMalloc(&b->d_ctl, sizeof(SearchCtl)));

@@ -93,7 +93,8 @@ int cc_comm_unique_id(void* out_id128) {
 
 int cc_comm_init(cc_ctx* ctx, const void* id128, int rank, int world) {
   CC_REQUIRE(ctx && id128, CC_ERR_BAD_ARG, "cc_comm_init: null argument");
-  CC_REQUIRE(world >= 1 && world <= 15 && rank >= 0 && rank < world, CC_ERR_BAD_ARG, "cc_comm_init: rank %d of %d (max 15 ranks)", rank, world);
+  CC_REQUIRE(world >= 1 && world <= CC_MAX_RANKS && rank >= 0 && rank < world, CC_ERR_BAD_ARG,
+             "cc_comm_init: rank %d of %d (the candidate buffer of the per-node exchange holds at most %d ranks)", rank, world, CC_MAX_RANKS);
   CC_CHECK(load_nccl());
   CC_CUDA(cudaSetDevice(ctx->device));
   ncclUniqueId_t id;

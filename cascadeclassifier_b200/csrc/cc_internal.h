@@ -39,6 +39,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 constexpr int TILE = 32;   // samples per integral tile (one warp lane per sample)
+constexpr int CC_MAX_RANKS = 72;   // ranks of one communicator (one NVLink domain: 8 on a B200 box, 72 on an NVL72 rack)
 
 // ---- host-side catalogs -------------------------------------------------------------------
 struct RectI { int x, y, w, h; };

@@ -16,6 +16,7 @@
 #include <climits>
 #include <cmath>
 #include <cstring>
+#include <unordered_map>
 
 #include "cc_internal.h"
 
@@ -184,6 +185,34 @@ __global__ void k_cascade_eval(EvalView e, const DevNode* __restrict__ nodes, co
       if (pos < surv_cap) surv[pos] = (unsigned)s;
     }
   }
+}
+
+// Cached survivors (see PyrCache below): slot s holds a window that is known to pass stages [0, first_stage[s]); run the
+// remaining stages and leave one flag per slot (the candidates are in stream order, so the flags are too).
+__global__ void k_cascade_flags(EvalView e, const DevNode* __restrict__ nodes, const int* __restrict__ tree_first,
+                                const DevStageRef* __restrict__ stages, int nstages, int n, const uint8_t* __restrict__ first_stage,
+                                uint8_t* __restrict__ flags) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  bool pass = true;
+  for (int st = first_stage[s]; st < nstages && pass; ++st) {
+    const DevStageRef sr = stages[st];
+    double sum = 0;
+    for (int t = 0; t < sr.num_trees; ++t) {
+      const DevNode* tree = nodes + tree_first[sr.first_tree + t];
+      int nd = 0;
+      while (tree[nd].left >= 0) {
+        const float val = m_eval_var(e, tree[nd].var_idx, s);
+        bool left;
+        if (e.ftype == CC_FEATURE_LBP) { const int c = (int)val; left = (tree[nd].subset[c >> 5] & (1 << (c & 31))) != 0; }
+        else left = val <= tree[nd].c;
+        nd = left ? tree[nd].left : tree[nd].right;
+      }
+      sum += tree[nd].value;
+    }
+    if (sum < (double)(sr.threshold - 0.00001F)) pass = false;
+  }
+  flags[s] = pass ? 1 : 0;
 }
 
 __global__ void k_copy_slots(const uint8_t* __restrict__ src, const unsigned int* __restrict__ which, int n, int npx, uint8_t* __restrict__ dst,
@@ -760,7 +789,28 @@ __global__ void k_list_to_bitmap(const unsigned int* __restrict__ list, const un
 }
 
 // ---- host-side state ----------------------------------------------------------------------------------
-struct BgImage { int w = 0, h = 0, pitch = 0; uint8_t* d_px = nullptr; };      // pitch: multiple of 16 bytes
+struct BgImage { int w = 0, h = 0, pitch = 0; uint8_t* d_px = nullptr; };      // pitch: multiple of 16 bytes; w == 0: placeholder of an unreadable file
+
+// Survivor cache of the window stream.  NegReader cycles the background list with a `round` phase
+// (src/imagestorage.cpp:57-88): image i is scanned with the offsets (round % W, round / W) clamped to the image, so the
+// stream revisits the pyramid (image, offsets) once per W*H list cycles -- in late stages many times per stage when
+// the list is short.  Cascade stages are append-only, so the windows of a pyramid that pass stages [0, n) are a superset of those
+// that pass any longer cascade: the cache keeps, per pyramid, the ascending stream ordinals (relative to the pyramid's first
+// window) of the windows that passed the first n_stages stages.  A revisit evaluates only stages [n_stages, ns) on them
+// (k_gather_resize + K1 + k_cascade_flags: the literal per-window setImage + predict path) instead of building the pyramid's
+// integral planes again.  Which windows are CONSUMED, the ordered cut, `consumed`, the reader state and the mined pixels are
+// those of the uncached evaluation (test_survivor_cache_is_transparent).  Entries are only created from pyramids that
+// were evaluated from their first to their last window and have few survivors; the cache is dropped when the background list,
+// the window size or an already cached cascade prefix changes.
+struct PyrEntry { int n_stages = 0; long long nwin = 0; std::vector<uint32_t> surv; };
+struct PyrCache {
+  std::unordered_map<uint64_t, PyrEntry> map;
+  std::vector<uint64_t> stage_hash;    // hash of every stage of the cascade the entries were computed with
+  size_t bytes = 0, max_bytes = (size_t)4 << 30;
+  bool enabled = true;
+  int W = 0, H = 0, ftype = -1, haar_mode = -1;
+  void clear() { map.clear(); bytes = 0; }
+};
 
 struct MineState {
   std::vector<BgImage> bgs;
@@ -813,6 +863,22 @@ struct MineState {
   cudaEvent_t ev_done[2] = {nullptr, nullptr};
   unsigned int* d_which = nullptr;     // accepted ordinals of a batch
   int which_cap = 0;
+  // survivor cache + the re-evaluation of cached survivors (candidates)
+  PyrCache cache;
+  EvalStore cand_store;                // scratch slots of the candidates of one batch
+  int cand_cap = 0;
+  uint8_t* d_cand = nullptr;           // device: [LevelDesc table | which u32 | first_stage u8 | flags u8] of one batch
+  size_t d_cand_cap = 0;
+  uint8_t* h_cand[2] = {nullptr, nullptr};            // pinned staging of the upload, one per batch in flight
+  size_t h_cand_cap[2] = {0, 0};
+  uint8_t* h_cand_flags[2] = {nullptr, nullptr};      // pinned result flags
+  size_t h_cand_flags_cap[2] = {0, 0};
+  uint8_t* d_gather = nullptr;         // device: [LevelDesc table | which u32] for the accepted windows of a batch
+  size_t d_gather_cap = 0;
+  uint8_t* h_gather = nullptr;         // pinned staging of that upload; ev_gather: the last upload has left it
+  size_t h_gather_cap = 0;
+  cudaEvent_t ev_gather = nullptr;
+  long long stat_consumed = 0, stat_built = 0, stat_cand = 0, stat_skipped = 0;
 };
 
 static void free_cascade(MineState* m) {
@@ -841,6 +907,15 @@ static void free_scratch(MineState* m) {
     if (m->ev_done[s]) { cudaEventDestroy(m->ev_done[s]); m->ev_done[s] = nullptr; }
   }
   cudaFree(m->d_which); m->d_which = nullptr; m->which_cap = 0;
+  store_free(m->cand_store); m->cand_cap = 0;
+  cudaFree(m->d_cand); m->d_cand = nullptr; m->d_cand_cap = 0;
+  cudaFree(m->d_gather); m->d_gather = nullptr; m->d_gather_cap = 0;
+  cudaFreeHost(m->h_gather); m->h_gather = nullptr; m->h_gather_cap = 0;
+  if (m->ev_gather) { cudaEventDestroy(m->ev_gather); m->ev_gather = nullptr; }
+  for (int s = 0; s < 2; ++s) {
+    cudaFreeHost(m->h_cand[s]); m->h_cand[s] = nullptr; m->h_cand_cap[s] = 0;
+    cudaFreeHost(m->h_cand_flags[s]); m->h_cand_flags[s] = nullptr; m->h_cand_flags_cap[s] = 0;
+  }
 }
 
 int mine_free(cc_ctx* ctx) {
@@ -900,6 +975,7 @@ struct NegStream {
   int pointX = 0, pointY = 0, offX = 0, offY = 0;
   int lw = 0, lh = 0;           // current level size (0: no image loaded yet)
   float scale = 1.0f;
+  bool fresh = false;           // the last transition loaded a new image (not part of the reader state)
   static constexpr float scaleFactor = 1.4142135623730950488016887242097F;
   static constexpr float stepFactor = 0.5F;
 
@@ -911,6 +987,7 @@ struct NegStream {
       src = (int)last;
       last++;
       const BgImage& im = (*bgs)[src];
+      if (im.w == 0 || im.h == 0) { last %= count; continue; }      // unreadable file: imread() gave an empty Mat (src/imagestorage.cpp:64-67) -- `round` is not advanced
       round += last / count;
       round = round % ((long long)W * H);
       last %= count;
@@ -924,8 +1001,19 @@ struct NegStream {
     scale = std::max(((float)W + pointX) / ((float)im.w), ((float)H + pointY) / ((float)im.h));
     lw = (int)(scale * im.w + 0.5F);
     lh = (int)(scale * im.h + 0.5F);
+    fresh = true;
     return true;
   }
+  // the stream stands on the first window of the first level of (image src, offsets): everything the reader does until
+  // the next nextImg() is a function of (src, offX, offY) alone
+  bool is_pyramid_start() const {
+    if (src < 0 || lw == 0 || pointX != offX || pointY != offY) return false;
+    const BgImage& im = (*bgs)[src];
+    if (im.w == 0) return false;
+    const float s0 = std::max(((float)W + offX) / ((float)im.w), ((float)H + offY) / ((float)im.h));
+    return scale == s0 && lw == (int)(s0 * im.w + 0.5F) && lh == (int)(s0 * im.h + 0.5F);
+  }
+  uint64_t pyramid_key() const { return ((uint64_t)(uint32_t)src << 32) | ((uint64_t)(uint32_t)offY << 16) | (uint64_t)(uint32_t)offX; }
   int stepX() const { return (int)(stepFactor * W); }
   int stepY() const { return (int)(stepFactor * H); }
   bool canStepX(int x) const { return (int)(x + (1.0F + stepFactor) * W) < lw; }
@@ -940,6 +1028,7 @@ struct NegStream {
       const BgImage& im = (*bgs)[src];
       lw = (int)(scale * im.w);
       lh = (int)(scale * im.h);
+      fresh = false;
       return true;
     }
     return nextImg();
@@ -968,9 +1057,49 @@ static void fill_level(const NegStream& ns, LevelDesc& L) {
   L.row0 = 0; L.spitch = im.pitch; L.owned = 1; L.pitch = L.lw + 1; L.ppitch = L.lw;
 }
 
+static uint64_t fnv1a(uint64_t h, const void* p, size_t n) {
+  const unsigned char* b = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 0x100000001B3ull; }
+  return h;
+}
+static uint64_t stage_hash(const cc_stage& st) {
+  uint64_t h = 0xCBF29CE484222325ull;
+  h = fnv1a(h, &st.threshold, sizeof(float));
+  h = fnv1a(h, &st.num_weak, sizeof(int32_t));
+  for (int t = 0; t < st.num_weak; ++t) {
+    const cc_tree& tr = st.trees[t];
+    h = fnv1a(h, &tr.num_nodes, sizeof(int32_t));
+    for (int i = 0; i < tr.num_nodes; ++i) {
+      const cc_node& nd = tr.nodes[i];
+      h = fnv1a(h, &nd.left, 4); h = fnv1a(h, &nd.right, 4); h = fnv1a(h, &nd.var_idx, 4); h = fnv1a(h, &nd.c, 4);
+      h = fnv1a(h, nd.subset, sizeof(nd.subset)); h = fnv1a(h, &nd.value, 8);
+    }
+  }
+  return h;
+}
+// the cache entries hold survivors of a cascade PREFIX: they stay valid as long as that prefix is unchanged
+static void cache_validate(cc_ctx* ctx, MineState* m, const cc_stage* stages, int n) {
+  PyrCache& c = m->cache;
+  if (c.W != ctx->W || c.H != ctx->H || c.ftype != ctx->ftype || c.haar_mode != ctx->haar_mode) {
+    c.clear(); c.stage_hash.clear();
+    c.W = ctx->W; c.H = ctx->H; c.ftype = ctx->ftype; c.haar_mode = ctx->haar_mode;
+  }
+  std::vector<uint64_t> hs(n);
+  for (int i = 0; i < n; ++i) hs[i] = stage_hash(stages[i]);
+  size_t common = 0;
+  while (common < hs.size() && common < c.stage_hash.size() && hs[common] == c.stage_hash[common]) ++common;
+  if (common < c.stage_hash.size()) {          // a stage the entries may depend on changed or disappeared
+    for (auto it = c.map.begin(); it != c.map.end();) {
+      if ((size_t)it->second.n_stages > common) { c.bytes -= it->second.surv.size() * 4 + 64; it = c.map.erase(it); } else ++it;
+    }
+  }
+  c.stage_hash.swap(hs);
+}
+
 // upload the cascade as flat arrays
 static int upload_cascade(cc_ctx* ctx, MineState* m, const cc_stage* stages, int n) {
   free_cascade(m);
+  cache_validate(ctx, m, stages, n);
   for (int s = 0; s < n; ++s) {
     DevStageRef sr;
     sr.first_tree = (int)m->tree_first.size();
@@ -1076,10 +1205,30 @@ static int accept_windows(cc_ctx* ctx, MineState* m, const unsigned* which, int 
 }
 
 // build one batch: whole levels (or a bounded part of one) starting at the stream position
+// A batch is a run of consecutive stream windows: level parts that are evaluated on the GPU (`levels`; w_base = their dense
+// "evaluation ordinal") interleaved with whole pyramids answered from the survivor cache (`pyrs`).  `segs` lists both kinds in
+// stream order with their batch-relative stream ordinals.
+struct CachedPyr {
+  NegStream start, after;           // stream state on the pyramid's first window / right behind its last one
+  long long base = 0, nwin = 0;     // stream ordinals [base, base + nwin)
+  uint64_t key = 0;
+  size_t cand0 = 0, ncand = 0;      // its cached survivors in Batch::cand
+};
+struct MissPyr { uint64_t key = 0; long long base = 0, nwin = 0; bool complete = false; };      // evaluated pyramid that may enter the cache
+struct Seg { long long base, nwin; int kind, idx; };      // kind 0: levels[idx] (a level part), 1: pyrs[idx]
 struct Batch {
   std::vector<LevelDesc> levels;
+  std::vector<NegStream> before;    // stream state on the first window taken from each level part
   std::vector<NegStream> after;     // stream state right after the last window of each level part (level granularity)
-  long long nwin = 0;
+  std::vector<long long> lv_stream; // stream ordinal of the first window taken from each level part
+  std::vector<CachedPyr> pyrs;
+  std::vector<MissPyr> miss;
+  std::vector<Seg> segs;
+  std::vector<long long> cand;      // stream ordinals of the cached survivors (ascending)
+  std::vector<uint8_t> cand_fs;     // stages they are known to pass
+  std::vector<uint32_t> cand_eval;  // indices into cand that still have stages to run
+  long long nwin = 0;               // stream windows
+  long long neval = 0;              // windows in `levels`
   size_t pool_px = 0;
 };
 
@@ -1224,32 +1373,12 @@ static int eval_tiles(cc_ctx* ctx, MineState* m, Batch& bt, const TileGeom& g, s
   return collect_survivors(ctx, m, sharded, bt.nwin, m->d_counts, m->d_list[0], survivors);
 }
 
-// accepted windows recomputed from the source images into training slots [first, first+n) (the level pixels of the batch
-// may already have been overwritten by the next batch); d_levels = the batch's descriptors as uploaded for its evaluation
-static int gather_accepted_resize(cc_ctx* ctx, MineState* m, const LevelDesc* d_levels, int nlevels, const unsigned* which, int n, int first, int label) {
-  if (n == 0) return CC_OK;
-  const int npx = ctx->W * ctx->H;
-  if (n > m->which_cap) { cudaFree(m->d_which); CC_CUDA(cudaMalloc(&m->d_which, sizeof(unsigned) * (size_t)ctx->max_samples)); m->which_cap = ctx->max_samples; }
-  CC_CUDA(cudaMemcpyAsync(m->d_which, which, sizeof(unsigned) * n, cudaMemcpyHostToDevice, ctx->stream));
-  {
-    ScopedTimer tm(ctx, "mine", 1);
-    k_gather_resize<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>(d_levels, nlevels, ctx->W, ctx->H, m->d_which, n,
-                                                                                    ctx->d_imgs + (size_t)first * npx, ctx->d_labels + first, label);
-    CC_CUDA(cudaGetLastError());
-  }
-  if (ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images) CC_CHECK(allreduce_sum(ctx, ctx->d_imgs + (size_t)first * npx, (size_t)n * npx, /*uint8*/ 1));
-  ctx->precalc_valid = false;
-  CC_CHECK(launch_integrals(ctx, main_store(ctx), first, n));
-  return CC_OK;
-}
-
 // Fast path, asynchronous half: build the levels and their integral planes, run the cascade in stage groups over the
 // shrinking survivor list, turn the survivors into a bitmap (summed over the ranks when the images are sharded) and
 // start its copy to the host.  Nothing here waits for the GPU, so the host assembles and launches batch k+1 while
 // batch k is evaluated; finish_levels(slot) waits for the bitmap and returns the ascending surviving ordinals.
-// The strips of the batch stay in m->d_strips[slot] for gather_accepted_resize().
 static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
-  if (bt.nwin == 0) return CC_OK;
+  if (bt.neval == 0) return CC_OK;
   // Tall levels are cut into horizontal strips of STRIP_WIN_ROWS window rows (consecutive strips overlap by H - step
   // pixel rows): window sums are differences, so every strip can carry its own integral planes, and a strip is a
   // much shorter serial chain of rows for k_lvl_build than the whole level.  The window ordinals of a strip are a
@@ -1320,9 +1449,9 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
     if (haar) { CC_CUDA(cudaMalloc(&m->d_psq, cap * 4)); CC_CUDA(cudaMalloc(&m->d_ptilt, cap * 4)); }
     m->plane_cap = cap;
   }
-  if ((size_t)bt.nwin > m->list_cap) {
+  if ((size_t)bt.neval > m->list_cap) {
     cudaFree(m->d_list[0]); cudaFree(m->d_list[1]);
-    const size_t cap = (size_t)bt.nwin + (size_t)bt.nwin / 2;
+    const size_t cap = (size_t)bt.neval + (size_t)bt.neval / 2;
     CC_CUDA(cudaMalloc(&m->d_list[0], cap * 4)); CC_CUDA(cudaMalloc(&m->d_list[1], cap * 4));
     m->list_cap = cap;
   }
@@ -1406,7 +1535,7 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
     if (ctx->timing_enabled) ctx->timers["mine"].launches += launches;
   }
   // survivors -> bitmap (1 bit per batch ordinal) -> pinned host memory, asynchronously
-  const size_t words = ((size_t)bt.nwin + 31) / 32;
+  const size_t words = ((size_t)bt.neval + 31) / 32;
   if (words > m->bitmap_cap) {
     cudaFree(m->d_bitmap);
     const size_t cap = words + words / 2 + 64;
@@ -1426,15 +1555,15 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
   ctx->launches += 1;
   if (sharded) CC_CHECK(allreduce_sum(ctx, m->d_bitmap, words, /*uint32*/ 4));
   CC_CUDA(cudaMemcpyAsync(m->h_bits[slot], m->d_bitmap, words * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CC_CUDA(cudaEventRecord(m->ev_done[slot], ctx->stream));
+  CC_CUDA(cudaEventRecord(m->ev_done[slot], ctx->stream));      // (cc_mine_negatives records it again behind the cached survivors' pass)
   return CC_OK;
 }
 
 // second half: wait for the batch's bitmap, list the surviving ordinals in ascending order
 static int finish_levels(cc_ctx* ctx, MineState* m, int slot, long long nwin, std::vector<unsigned>& survivors) {
   survivors.clear();
+  if (m->ev_done[slot]) CC_CUDA(cudaEventSynchronize(m->ev_done[slot]));
   if (nwin == 0) return CC_OK;
-  CC_CUDA(cudaEventSynchronize(m->ev_done[slot]));
   const size_t words = ((size_t)nwin + 31) / 32;
   const unsigned int* hb = m->h_bits[slot];
   for (size_t w = 0; w < words; ++w) {
@@ -1444,13 +1573,212 @@ static int finish_levels(cc_ctx* ctx, MineState* m, int slot, long long nwin, st
   return CC_OK;
 }
 
+// ---- gathering windows by stream ordinal ---------------------------------------------------------------
+// Pixels of arbitrary stream windows of a batch (cached survivors to re-evaluate, accepted windows) are recomputed from the
+// source images by k_gather_resize.  This builds its inputs: one descriptor per pyramid level that holds at least one of
+// the requested windows (whole level, private ordinal base) and the private ordinal of every window.  Every rank holds
+// every background image, so no exchange is needed for these pixels.
+struct GatherPlan { std::vector<LevelDesc> levels; std::vector<uint32_t> which; };
+
+static void level_after(NegStream& w) {        // next level of the SAME pyramid (the caller knows there is one)
+  w.pointX = w.offX; w.pointY = w.offY;
+  w.scale *= NegStream::scaleFactor;
+  const BgImage& im = (*w.bgs)[w.src];
+  w.lw = (int)(w.scale * im.w);
+  w.lh = (int)(w.scale * im.h);
+  w.fresh = false;
+}
+
+static int build_gather_plan(const Batch& bt, const long long* ords, size_t n, GatherPlan& gp) {
+  gp.levels.clear(); gp.which.resize(n);
+  size_t si = 0;
+  long long priv = 0;
+  int cur_seg = -1;
+  NegStream walk;                 // cached pyramid being walked
+  long long lvl_base = 0, lvl_n = 0;      // stream ordinals [lvl_base, lvl_base + lvl_n) of the level `walk` stands on
+  bool lvl_in_plan = false;
+  for (size_t i = 0; i < n; ++i) {
+    const long long o = ords[i];
+    while (si + 1 < bt.segs.size() && bt.segs[si + 1].base <= o) ++si;
+    const Seg& sg = bt.segs[si];
+    CC_REQUIRE(o >= sg.base && o < sg.base + sg.nwin, CC_ERR_STATE, "mining: stream ordinal %lld outside the batch", o);
+    if (sg.kind == 0) {
+      const LevelDesc& L = bt.levels[sg.idx];
+      if (cur_seg != (int)si) {
+        LevelDesc T = L;
+        T.w_skip = 0; T.w_count = (long long)L.nx * L.ny; T.w_base = priv; T.owned = 1;
+        priv += T.w_count;
+        gp.levels.push_back(T);
+        cur_seg = (int)si;
+      }
+      gp.which[i] = (uint32_t)(gp.levels.back().w_base + (o - sg.base) + L.w_skip);
+    } else {
+      const CachedPyr& cp = bt.pyrs[sg.idx];
+      if (cur_seg != (int)si) {
+        walk = cp.start;
+        lvl_base = cp.base; lvl_n = (long long)walk.countX() * walk.countY();
+        lvl_in_plan = false;
+        cur_seg = (int)si;
+      }
+      while (o >= lvl_base + lvl_n) { lvl_base += lvl_n; level_after(walk); lvl_n = (long long)walk.countX() * walk.countY(); lvl_in_plan = false; }
+      if (!lvl_in_plan) {
+        LevelDesc T;
+        fill_level(walk, T);
+        T.w_skip = 0; T.w_count = lvl_n; T.w_base = priv; T.px_off = 0; T.ip_off = 0; T.rows_base = T.cols_base = T.diag_base = 0;
+        priv += lvl_n;
+        gp.levels.push_back(T);
+        lvl_in_plan = true;
+      }
+      gp.which[i] = (uint32_t)(gp.levels.back().w_base + (o - lvl_base));
+    }
+    CC_REQUIRE(priv < 0xFFFFFFFFll, CC_ERR_UNSUPPORTED, "mining: too many distinct levels in one gather");
+  }
+  return CC_OK;
+}
+
+// accepted windows (stream ordinals of the batch, ascending) -> training slots [first, first + n) with label, + their integrals
+static int gather_accepted(cc_ctx* ctx, MineState* m, const Batch& bt, const std::vector<long long>& ords, int first, int label) {
+  const int n = (int)ords.size();
+  if (n == 0) return CC_OK;
+  GatherPlan gp;
+  CC_CHECK(build_gather_plan(bt, ords.data(), ords.size(), gp));
+  const size_t tb = sizeof(LevelDesc) * gp.levels.size(), need = tb + sizeof(uint32_t) * n;
+  if (need > m->d_gather_cap) { cudaFree(m->d_gather); m->d_gather = nullptr; CC_CUDA(cudaMalloc(&m->d_gather, need * 2)); m->d_gather_cap = need * 2; }
+  if (!m->ev_gather) CC_CUDA(cudaEventCreateWithFlags(&m->ev_gather, cudaEventDisableTiming));
+  else CC_CUDA(cudaEventSynchronize(m->ev_gather));           // the previous upload has left the staging buffer (long ago)
+  if (need > m->h_gather_cap) { cudaFreeHost(m->h_gather); m->h_gather = nullptr; CC_CUDA(cudaMallocHost(&m->h_gather, need * 2)); m->h_gather_cap = need * 2; }
+  std::memcpy(m->h_gather, gp.levels.data(), tb);
+  std::memcpy(m->h_gather + tb, gp.which.data(), sizeof(uint32_t) * n);
+  CC_CUDA(cudaMemcpyAsync(m->d_gather, m->h_gather, need, cudaMemcpyHostToDevice, ctx->stream));   // pinned: does not wait for the batch in flight
+  CC_CUDA(cudaEventRecord(m->ev_gather, ctx->stream));
+  const int npx = ctx->W * ctx->H;
+  {
+    ScopedTimer tm(ctx, "mine", 1);
+    k_gather_resize<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>((const LevelDesc*)m->d_gather, (int)gp.levels.size(), ctx->W, ctx->H,
+                                                                                    (const unsigned int*)(m->d_gather + tb), n,
+                                                                                    ctx->d_imgs + (size_t)first * npx, ctx->d_labels + first, label);
+    CC_CUDA(cudaGetLastError());
+  }
+  ctx->precalc_valid = false;
+  CC_CHECK(launch_integrals(ctx, main_store(ctx), first, n));
+  return CC_OK;
+}
+
+// Cached survivors of the batch that still have stages to run: gather their pixels into scratch slots, build their integrals
+// (K1, the arithmetic of setImage) and run stages [first_stage, ns) on every slot.  Asynchronous like launch_levels: the flags
+// arrive in m->h_cand_flags[slot] before m->ev_done[slot] fires.
+static int launch_candidates(cc_ctx* ctx, MineState* m, const Batch& bt, int slot) {
+  const int n = (int)bt.cand_eval.size();
+  if (n == 0) return CC_OK;
+  std::vector<long long> ords(n);
+  for (int i = 0; i < n; ++i) ords[i] = bt.cand[bt.cand_eval[i]];
+  GatherPlan gp;
+  CC_CHECK(build_gather_plan(bt, ords.data(), ords.size(), gp));
+  const size_t tb = sizeof(LevelDesc) * gp.levels.size();
+  const size_t off_which = tb, off_fs = off_which + sizeof(uint32_t) * (size_t)n, off_flags = (off_fs + n + 15) & ~(size_t)15, need = off_flags + n;
+  if (need > m->d_cand_cap) { cudaFree(m->d_cand); m->d_cand = nullptr; CC_CUDA(cudaMalloc(&m->d_cand, need * 2)); m->d_cand_cap = need * 2; }
+  if (need > m->h_cand_cap[slot]) {
+    cudaFreeHost(m->h_cand[slot]); m->h_cand[slot] = nullptr;
+    CC_CUDA(cudaMallocHost(&m->h_cand[slot], need * 2)); m->h_cand_cap[slot] = need * 2;
+  }
+  if ((size_t)n > m->h_cand_flags_cap[slot]) {
+    cudaFreeHost(m->h_cand_flags[slot]); m->h_cand_flags[slot] = nullptr;
+    CC_CUDA(cudaMallocHost(&m->h_cand_flags[slot], (size_t)n * 2)); m->h_cand_flags_cap[slot] = (size_t)n * 2;
+  }
+  if (n > m->cand_cap) {
+    store_free(m->cand_store);
+    const int cap = std::max(n + n / 2, 4096);
+    CC_CHECK(store_alloc(ctx, m->cand_store, cap));
+    m->cand_cap = cap;
+  }
+  uint8_t* hb = m->h_cand[slot];
+  std::memcpy(hb, gp.levels.data(), tb);
+  std::memcpy(hb + off_which, gp.which.data(), sizeof(uint32_t) * (size_t)n);
+  for (int i = 0; i < n; ++i) hb[off_fs + i] = bt.cand_fs[bt.cand_eval[i]];
+  CC_CUDA(cudaMemcpyAsync(m->d_cand, hb, off_fs + n, cudaMemcpyHostToDevice, ctx->stream));
+  const int npx = ctx->W * ctx->H;
+  {
+    ScopedTimer tm(ctx, "mine", 1);
+    k_gather_resize<<<grid_for(ctx, (long long)n * npx, 256), 256, 0, ctx->stream>>>((const LevelDesc*)m->d_cand, (int)gp.levels.size(), ctx->W, ctx->H,
+                                                                                    (const unsigned int*)(m->d_cand + off_which), n,
+                                                                                    m->cand_store.d_imgs, m->cand_store.d_labels, 0);
+    CC_CUDA(cudaGetLastError());
+  }
+  CC_CHECK(launch_integrals(ctx, m->cand_store, 0, n));
+  {
+    ScopedTimer tm(ctx, "mine", 1);
+    k_cascade_flags<<<(n + 127) / 128, 128, 0, ctx->stream>>>(make_eval_view_store(ctx, m->cand_store), m->d_nodes, m->d_tree_first, m->d_stages,
+                                                              (int)m->stages.size(), n, m->d_cand + off_fs, m->d_cand + off_flags);
+    CC_CUDA(cudaGetLastError());
+  }
+  CC_CUDA(cudaMemcpyAsync(m->h_cand_flags[slot], m->d_cand + off_flags, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+  m->stat_cand += n;
+  return CC_OK;
+}
+
+// Survivors of the whole batch as ascending stream ordinals: the evaluated level parts (`eval_surv` = ascending evaluation
+// ordinals) merged with the cached survivors (known ones, and re-evaluated ones by their flags); then the cache is brought up
+// to date with what this batch has learnt about its pyramids.
+static void merge_and_update_cache(MineState* m, const Batch& bt, const std::vector<unsigned>& eval_surv, const uint8_t* flags, int ns, bool cache_on,
+                                   std::vector<long long>& out) {
+  out.clear();
+  std::vector<long long> a, c;
+  a.reserve(eval_surv.size());
+  size_t li = 0;
+  for (const unsigned e : eval_surv) {
+    while (li + 1 < bt.levels.size() && bt.levels[li + 1].w_base <= (long long)e) ++li;
+    a.push_back(bt.lv_stream[li] + ((long long)e - bt.levels[li].w_base));
+  }
+  size_t fj = 0;
+  for (size_t i = 0; i < bt.cand.size(); ++i) {
+    const bool pass = bt.cand_fs[i] >= ns ? true : flags[fj++] != 0;
+    if (pass) c.push_back(bt.cand[i]);
+  }
+  out.resize(a.size() + c.size());
+  std::merge(a.begin(), a.end(), c.begin(), c.end(), out.begin());
+  if (!cache_on) return;
+  PyrCache& pc = m->cache;
+  auto range = [&](long long base, long long nwin, std::vector<uint32_t>& v) {
+    auto lo = std::lower_bound(out.begin(), out.end(), base), hi = std::lower_bound(out.begin(), out.end(), base + nwin);
+    v.clear(); v.reserve(hi - lo);
+    for (auto it = lo; it != hi; ++it) v.push_back((uint32_t)(*it - base));
+  };
+  std::vector<uint32_t> v;
+  for (const CachedPyr& cp : bt.pyrs) {
+    auto it = pc.map.find(cp.key);
+    if (it == pc.map.end() || it->second.n_stages >= ns) continue;
+    range(cp.base, cp.nwin, v);
+    pc.bytes -= it->second.surv.size() * 4;
+    it->second.surv = v; it->second.n_stages = ns;
+    pc.bytes += v.size() * 4;
+  }
+  for (const MissPyr& mp : bt.miss) {
+    if (!mp.complete) continue;
+    auto it = pc.map.find(mp.key);
+    if (it != pc.map.end() && it->second.n_stages >= ns) continue;
+    range(mp.base, mp.nwin, v);
+    if ((long long)v.size() > std::max<long long>(8, mp.nwin / 16)) continue;          // re-evaluating that many windows one by one costs more than the planes
+    if (it == pc.map.end()) {
+      if (pc.bytes + v.size() * 4 + 64 > pc.max_bytes) continue;
+      PyrEntry e; e.n_stages = ns; e.nwin = mp.nwin; e.surv = v;
+      pc.map.emplace(mp.key, std::move(e));
+      pc.bytes += v.size() * 4 + 64;
+    } else {
+      pc.bytes -= it->second.surv.size() * 4;
+      it->second.surv = v; it->second.n_stages = ns; it->second.nwin = mp.nwin;
+      pc.bytes += v.size() * 4;
+    }
+  }
+}
+
 // The serial part of fillPassedSamples (src/cascadeclassifier.cpp:333-355) applied to a batch that has already been
 // evaluated: walk the windows in stream order, stop at the count-th acceptance or as soon as the reference's check
 // (getcount+1)/consumed <= minimumAcceptanceRatio holds before a window.  `surv` = ascending batch ordinals that pass
 // the cascade.  Returns the ordinal of the first unconsumed window; consumed / got are updated, accepted ordinals
 // appended.
-static long long serial_cut(const unsigned* surv, size_t nsurv, long long nwin, int count, double min_ratio, long long& consumed, int& got,
-                            std::vector<unsigned>& accepted, bool& stopped) {
+template <typename Ord>
+static long long serial_cut(const Ord* surv, size_t nsurv, long long nwin, int count, double min_ratio, long long& consumed, int& got,
+                            std::vector<Ord>& accepted, bool& stopped) {
   accepted.clear();
   stopped = false;
   long long pos = 0;            // next unconsumed batch ordinal
@@ -1481,7 +1809,7 @@ static long long serial_cut(const unsigned* surv, size_t nsurv, long long nwin, 
     pos = nextPass;
     if (pos >= nwin) break;
     consumed++; got++;                                  // window `pos` passes the cascade
-    accepted.push_back((unsigned)pos);
+    accepted.push_back((Ord)pos);
     pos++; si++;
     if (got == count) { stopped = true; break; }
   }
@@ -1500,14 +1828,17 @@ int cc_bg_clear(cc_ctx* ctx) {
   CC_CUDA(cudaSetDevice(ctx->device));
   for (auto& b : m->bgs) cudaFree(b.d_px);
   m->bgs.clear();
+  m->cache.clear();
   return CC_OK;
 }
 
 int cc_bg_register(cc_ctx* ctx, const uint8_t* host_gray, int w, int h) {
-  CC_REQUIRE(ctx && host_gray && w > 0 && h > 0, CC_ERR_BAD_ARG, "cc_bg_register: bad arguments");
+  CC_REQUIRE(ctx && ((host_gray && w > 0 && h > 0) || (w == 0 && h == 0)), CC_ERR_BAD_ARG, "cc_bg_register: bad arguments");
   MineState* m = mine_state(ctx);
   CC_CUDA(cudaSetDevice(ctx->device));
   BgImage b;
+  m->cache.clear();                                        // image indices / list length are part of the cache keys
+  if (w == 0) { m->bgs.push_back(b); return CC_OK; }      // placeholder of an unreadable file: keeps its slot in the list, NegReader::nextImg skips it
   b.w = w; b.h = h; b.pitch = (w + 15) & ~15;
   CC_CUDA(cudaMalloc(&b.d_px, (size_t)b.pitch * h));
   CC_CUDA(cudaMemcpy2DAsync(b.d_px, (size_t)b.pitch, host_gray, (size_t)w, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
@@ -1522,6 +1853,23 @@ int cc_mine_set_mode(cc_ctx* ctx, int mode) {
   m->mode = mode;
   m->force_unfused = mode == 1;
   m->force_slots = mode == 2;
+  return CC_OK;
+}
+
+int cc_mine_set_cache(cc_ctx* ctx, int enable, int64_t max_bytes) {
+  CC_REQUIRE(ctx, CC_ERR_BAD_ARG, "cc_mine_set_cache: null ctx");
+  MineState* m = mine_state(ctx);
+  m->cache.enabled = enable != 0;
+  if (!m->cache.enabled) m->cache.clear();
+  if (max_bytes > 0) m->cache.max_bytes = (size_t)max_bytes;
+  return CC_OK;
+}
+
+int cc_mine_get_stats(cc_ctx* ctx, int64_t* stats6) {
+  CC_REQUIRE(ctx && stats6, CC_ERR_BAD_ARG, "cc_mine_get_stats: null argument");
+  MineState* m = mine_state(ctx);
+  stats6[0] = m->stat_consumed; stats6[1] = m->stat_built; stats6[2] = m->stat_cand; stats6[3] = m->stat_skipped;
+  stats6[4] = (int64_t)m->cache.map.size(); stats6[5] = (int64_t)m->cache.bytes;
   return CC_OK;
 }
 
@@ -1556,48 +1904,106 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   const TileGeom tgeom = tile_geometry(ctx, ctx->ftype == CC_FEATURE_HAAR, ctx->ftype == CC_FEATURE_HAAR && m->cascade_tilted);
   const bool tile_path = level_path && m->mode == 3 && tgeom.ok;
   const long long max_batch = level_path ? level_path_max_batch(ctx, m) : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  // Plane path: two batches in flight.  While batch k is evaluated the host assembles and launches batch k+1 -- when
+  // the running acceptance rate says that batch k will not complete the stage -- and only then waits for batch k's
+  // survivor bitmap; a speculative batch that turns out not to be needed is dropped (its windows count as not read).
+  const bool pipelined = level_path && !tile_path;
+  const bool cache_on = pipelined && m->cache.enabled && m->mode == 0 && m->stages.size() < 255;
+  const int nstages = (int)m->stages.size();
+  constexpr long long CAND_CAP = 262144;         // cached survivors re-evaluated per batch (scratch slots)
+  constexpr size_t SEG_CAP = (size_t)1 << 20;    // level parts + cached pyramids per batch
   bool stream_ok = true;
   if (ns.lw == 0) stream_ok = ns.nextImg();             // first get(): img.empty() -> nextImg()
-  std::vector<unsigned> survivors, accepted;
+  std::vector<unsigned> survivors;
+  std::vector<long long> surv64, accepted;
 
-  // ---- assemble a batch: levels (or parts of levels) of the stream starting at `from` ----
+  // ---- assemble a batch: level parts (or whole cached pyramids) of the stream starting at `from` ----
   auto assemble = [&](const NegStream& from, Batch& bt, bool& more) {
     HostTimer ht(ctx, "mine_host_assemble");
-    long long want = 32768;
-    if (accept_rate > 0) want = (long long)std::min<double>((double)max_batch, std::max(4096.0, 1.25 * (count - got) / accept_rate + 1024));
-    else want = std::min<long long>(max_batch, 65536);
-    want = std::min(want, max_batch);
+    // stream windows this batch should cover: enough to finish the stage at the observed acceptance rate.  Only the windows that
+    // have to be evaluated (not answered from the cache) are bounded by max_batch.
+    double want = 65536;
+    if (accept_rate > 0) want = std::max(4096.0, 1.25 * (count - got) / accept_rate + 1024);
+    if (!cache_on) want = std::min(want, (double)max_batch);
+    want = std::min(want, 4.0e12);
     NegStream cur = from;
     more = true;
-    while (bt.nwin < want && more) {
+    int open_pyr = -1;                  // bt.miss entry of the pyramid being assembled from its first window
+    while ((double)bt.nwin < want && bt.neval < max_batch && more && (long long)bt.cand_eval.size() < CAND_CAP && bt.segs.size() < SEG_CAP) {
+      if (cache_on && cur.is_pyramid_start()) {
+        const uint64_t key = cur.pyramid_key();
+        auto it = m->cache.map.find(key);
+        if (it != m->cache.map.end() && it->second.n_stages <= nstages) {
+          const PyrEntry& e = it->second;
+          CachedPyr cp;
+          cp.start = cur; cp.base = bt.nwin; cp.nwin = e.nwin; cp.key = key; cp.cand0 = bt.cand.size(); cp.ncand = e.surv.size();
+          for (const uint32_t o : e.surv) {
+            if (e.n_stages < nstages) bt.cand_eval.push_back((uint32_t)bt.cand.size());
+            bt.cand.push_back(cp.base + (long long)o);
+            bt.cand_fs.push_back((uint8_t)std::min(e.n_stages, 255));
+          }
+          NegStream nxt = cur;
+          more = nxt.nextImg();
+          cp.after = nxt;
+          bt.segs.push_back(Seg{cp.base, cp.nwin, 1, (int)bt.pyrs.size()});
+          bt.pyrs.push_back(cp);
+          bt.nwin += cp.nwin;
+          cur = nxt;
+          open_pyr = -1;
+          continue;
+        }
+        MissPyr mp;
+        mp.key = key; mp.base = bt.nwin;
+        open_pyr = (int)bt.miss.size();
+        bt.miss.push_back(mp);
+      }
       LevelDesc L;
       fill_level(cur, L);
       const int ix0 = (cur.pointX - cur.offX) / std::max(1, L.step_x), iy0 = (cur.pointY - cur.offY) / std::max(1, L.step_y);
       L.w_skip = (long long)iy0 * L.nx + ix0;
       const long long avail = (long long)L.nx * L.ny - L.w_skip;
-      L.w_count = std::min(avail, max_batch - bt.nwin);
-      L.w_base = bt.nwin;
+      L.w_count = std::min(avail, max_batch - bt.neval);
+      L.w_base = bt.neval;                               // evaluation ordinal of its first window
       L.px_off = (long long)bt.pool_px;
       bt.pool_px += (size_t)L.lw * L.lh;
+      bt.segs.push_back(Seg{bt.nwin, L.w_count, 0, (int)bt.levels.size()});
+      bt.lv_stream.push_back(bt.nwin);
+      bt.neval += L.w_count;
       bt.nwin += L.w_count;
+      if (open_pyr >= 0) bt.miss[open_pyr].nwin += L.w_count;
       NegStream nxt = cur;
       if (L.w_count == avail) {
         more = nxt.nextLevel();
+        if (!more || nxt.fresh) {                        // that was the pyramid's last level
+          if (open_pyr >= 0) bt.miss[open_pyr].complete = true;
+          open_pyr = -1;
+        }
       } else {
         const long long k = L.w_skip + L.w_count;      // first window not taken
         nxt.pointY = cur.offY + (int)(k / L.nx) * L.step_y;
         nxt.pointX = cur.offX + (int)(k % L.nx) * L.step_x;
       }
       bt.levels.push_back(L);
+      bt.before.push_back(cur);
       bt.after.push_back(nxt);
       cur = nxt;
       if (L.w_count < avail) break;
     }
   };
-  // Plane path: two batches in flight.  While batch k is evaluated the host assembles and launches batch k+1 -- when
-  // the running acceptance rate says that batch k will not complete the stage -- and only then waits for batch k's
-  // survivor bitmap; a speculative batch that turns out not to be needed is dropped (its windows count as not read).
-  const bool pipelined = level_path && !tile_path;
+  auto batch_end_state = [&](const Batch& bt) -> const NegStream& {
+    const Seg& sg = bt.segs.back();
+    return sg.kind == 0 ? bt.after[sg.idx] : bt.pyrs[sg.idx].after;
+  };
+  // asynchronous half of a plane-path batch: pyramid planes + cascade for the level parts, per-window path for the cached survivors
+  auto launch_batch = [&](Batch& bt, int slot) -> int {
+    HostTimer he(ctx, "mine_host_eval");
+    if (!m->ev_done[slot]) CC_CUDA(cudaEventCreateWithFlags(&m->ev_done[slot], cudaEventDisableTiming));
+    CC_CHECK(launch_levels(ctx, m, bt, slot));
+    CC_CHECK(launch_candidates(ctx, m, bt, slot));
+    CC_CUDA(cudaEventRecord(m->ev_done[slot], ctx->stream));
+    m->stat_built += bt.neval;
+    return CC_OK;
+  };
   Batch pre;
   bool pre_valid = false, pre_more = false;
   int slot = 0;
@@ -1611,14 +2017,15 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       bt = std::move(pre); pre = Batch(); more = pre_more; pre_valid = false; slot ^= 1;
     } else {
       assemble(ns, bt, more);
-      if (pipelined) { HostTimer he(ctx, "mine_host_eval"); CC_CHECK(launch_levels(ctx, m, bt, slot)); }
+      if (pipelined) CC_CHECK(launch_batch(bt, slot));
     }
-    const int nwin = (int)bt.nwin;
+    if (bt.segs.empty()) { stream_ok = more; continue; }
+    const long long nwin = bt.nwin;
     // ---- GPU: levels, gather, integrals, cascade ----
     const bool direct = m->stages.empty();       // stage 0: every window passes, gather straight into the training slots
     long long take_direct = 0;
     if (!level_path) {
-      CC_CHECK(ensure_scratch(ctx, m, direct ? 1 : nwin, bt.pool_px, (int)bt.levels.size()));
+      CC_CHECK(ensure_scratch(ctx, m, direct ? 1 : (int)nwin, bt.pool_px, (int)bt.levels.size()));
       CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (!level_path) {
@@ -1631,9 +2038,10 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
         k_gather_windows<<<grid_for(ctx, take_direct * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, take_direct,
                                                                                        ctx->d_imgs + (size_t)(first_slot + got) * npx);
       } else {
-        k_gather_windows<<<grid_for(ctx, (long long)nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
+        k_gather_windows<<<grid_for(ctx, nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
       }
       CC_CUDA(cudaGetLastError());
+      m->stat_built += direct ? 0 : nwin;
     }
     long long stop_after = -1;     // batch ordinal of the last consumed window (-1: none consumed)
     if (direct) {
@@ -1649,58 +2057,92 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       CC_CUDA(cudaStreamSynchronize(ctx->stream));
       stop_after = taken - 1;
       if (taken < take_direct) { /* ratio rule fired */ }
-      if (got < count && taken == nwin) { ns = bt.after.back(); stream_ok = more; continue; }
+      if (got < count && taken == nwin) { ns = batch_end_state(bt); stream_ok = more; continue; }
     } else {
       if (pipelined) {
         if (more && accept_rate > 0 && accept_rate * (double)bt.nwin < 0.5 * (double)(count - got)) {
-          assemble(bt.after.back(), pre, pre_more);
-          HostTimer he(ctx, "mine_host_eval");
-          CC_CHECK(launch_levels(ctx, m, pre, slot ^ 1));
-          pre_valid = true;
+          assemble(batch_end_state(bt), pre, pre_more);
+          if (!pre.segs.empty()) {
+            CC_CHECK(launch_batch(pre, slot ^ 1));
+            pre_valid = true;
+          }
         }
-        HostTimer hw(ctx, "mine_host_wait");
-        CC_CHECK(finish_levels(ctx, m, slot, bt.nwin, survivors));
+        {
+          HostTimer hw(ctx, "mine_host_wait");
+          CC_CHECK(finish_levels(ctx, m, slot, bt.neval, survivors));
+        }
+        HostTimer hm(ctx, "mine_host_merge");
+        merge_and_update_cache(m, bt, survivors, m->h_cand_flags[slot], nstages, cache_on, surv64);
       } else {
         HostTimer he(ctx, "mine_host_eval");
         if (tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
-        else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
+        else CC_CHECK(eval_scratch(ctx, m, (int)nwin, survivors));
+        if (tile_path) m->stat_built += nwin;
+        surv64.assign(survivors.begin(), survivors.end());
       }
       HostTimer hc(ctx, "mine_host_cut");
       // ---- serial stopping rule over the ordered survivors ----
       bool stopped = false;
-      const long long pos = serial_cut(survivors.data(), survivors.size(), nwin, count, min_ratio, consumed, got, accepted, stopped);
+      const long long pos = serial_cut<long long>(surv64.data(), surv64.size(), nwin, count, min_ratio, consumed, got, accepted, stopped);
       stop_after = pos - 1;
       const int first_acc = first_slot + got - (int)accepted.size();
-      if (pipelined) CC_CHECK(gather_accepted_resize(ctx, m, m->d_strips[slot], (int)m->strips[slot].size(), accepted.data(), (int)accepted.size(), first_acc, 0));
-      else if (tile_path) CC_CHECK(gather_accepted_resize(ctx, m, m->d_levels, (int)m->dev_levels.size(), accepted.data(), (int)accepted.size(), first_acc, 0));
-      else CC_CHECK(accept_windows(ctx, m, accepted.data(), (int)accepted.size(), first_acc, 0));
-      if (nwin > 0) accept_rate = std::max((double)survivors.size() / (double)nwin, 1e-9);
-      if (!stopped) { ns = bt.after.back(); stream_ok = more; continue; }
+      if (level_path) CC_CHECK(gather_accepted(ctx, m, bt, accepted, first_acc, 0));
+      else {
+        std::vector<unsigned> acc32(accepted.begin(), accepted.end());
+        CC_CHECK(accept_windows(ctx, m, acc32.data(), (int)acc32.size(), first_acc, 0));
+      }
+      if (nwin > 0) accept_rate = std::max((double)surv64.size() / (double)nwin, 1e-12);
+      for (const CachedPyr& cp : bt.pyrs) if (cp.base <= stop_after) m->stat_skipped += std::min(cp.nwin, stop_after + 1 - cp.base);
+      if (!stopped) { ns = batch_end_state(bt); stream_ok = more; continue; }
     }
     // ---- stopped inside this batch: reader state right after window `stop_after` ----
     if (stop_after < 0) {
       // nothing consumed from this batch: state unchanged
     } else {
-      // find the level part containing stop_after
-      size_t li = 0;
-      while (li + 1 < bt.levels.size() && bt.levels[li + 1].w_base <= stop_after) ++li;
-      const LevelDesc& L = bt.levels[li];
-      const long long k = stop_after - L.w_base + L.w_skip + 1;          // index (within the level) of the next window
-      if (k >= (long long)L.nx * L.ny) {
-        ns = bt.after[li];                                               // next level / image (already advanced)
-        if (li + 1 == bt.levels.size()) stream_ok = more;
+      // find the segment containing stop_after
+      size_t si = 0;
+      {
+        size_t lo = 0, hi = bt.segs.size() - 1;
+        while (lo < hi) { const size_t mid = (lo + hi + 1) >> 1; if (bt.segs[mid].base <= stop_after) lo = mid; else hi = mid - 1; }
+        si = lo;
+      }
+      const Seg& sg = bt.segs[si];
+      if (sg.kind == 0) {
+        const LevelDesc& L = bt.levels[sg.idx];
+        const long long k = stop_after - sg.base + L.w_skip + 1;          // index (within the level) of the next window
+        if (k >= (long long)L.nx * L.ny) {
+          ns = bt.after[sg.idx];                                           // next level / image (already advanced)
+          if (si + 1 == bt.segs.size()) stream_ok = more;
+        } else {
+          // same level: the state of that level, then position the point
+          NegStream st = bt.before[sg.idx];
+          st.pointY = st.offY + (int)(k / L.nx) * L.step_y;
+          st.pointX = st.offX + (int)(k % L.nx) * L.step_x;
+          ns = st;
+        }
       } else {
-        // same level: rebuild the state of that level, then position the point
-        NegStream st = li == 0 ? ns : bt.after[li - 1];
-        st.pointY = st.offY + (int)(k / L.nx) * L.step_y;
-        st.pointX = st.offX + (int)(k % L.nx) * L.step_x;
-        ns = st;
+        const CachedPyr& cp = bt.pyrs[sg.idx];
+        const long long k = stop_after - cp.base + 1;                      // windows of the pyramid consumed
+        if (k >= cp.nwin) {
+          ns = cp.after;
+          if (si + 1 == bt.segs.size()) stream_ok = more;
+        } else {
+          NegStream st = cp.start;
+          long long lb = 0, ln = (long long)st.countX() * st.countY();
+          while (k >= lb + ln) { lb += ln; level_after(st); ln = (long long)st.countX() * st.countY(); }
+          const int nx = st.countX();
+          const long long kk = k - lb;
+          st.pointY = st.offY + (int)(kk / nx) * st.stepY();
+          st.pointX = st.offX + (int)(kk % nx) * st.stepX();
+          ns = st;
+        }
       }
     }
     break;
   }
   CC_CUDA(cudaStreamSynchronize(ctx->stream));          // gathers / integrals of the last batches; a dropped speculative batch
   state_from_stream(ns, state);
+  m->stat_consumed += consumed;
   *consumed_out = consumed;
   *got_out = got;
   return CC_OK;
@@ -1787,7 +2229,7 @@ int cc_mine_serial_cut(const uint32_t* survivors, int64_t nsurv, int64_t nwin, i
   long long c = *consumed;
   int g = *got;
   bool st = false;
-  const long long pos = serial_cut(survivors, (size_t)nsurv, nwin, count, min_ratio, c, g, acc, st);
+  const long long pos = serial_cut<unsigned>(survivors, (size_t)nsurv, nwin, count, min_ratio, c, g, acc, st);
   *consumed = c; *got = g; *next_window = pos; *stopped = st ? 1 : 0;
   *n_accepted = (int32_t)acc.size();
   if (accepted) std::memcpy(accepted, acc.data(), acc.size() * sizeof(unsigned));
@@ -1862,6 +2304,7 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
         part.px_off = (long long)bt.pool_px;
         bt.pool_px += (size_t)L.lw * L.lh;
         bt.nwin += part.w_count;
+        bt.neval += part.w_count;
         bt.levels.push_back(part);
         done += part.w_count;
       }

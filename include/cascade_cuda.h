@@ -125,7 +125,7 @@ typedef struct {
 /* Restrict this ctx to the variable slice [rank*F/world, (rank+1)*F/world) (feature sharding,
  * SURVEY.md §8e).  Default: rank 0 of 1. */
 int cc_boost_set_shard(cc_ctx* ctx, int rank, int world);
-/* Optional NCCL communicator for the per-node allreduce-argmax; id = ncclUniqueId bytes (128). */
+/* Optional NCCL communicator for the per-node allreduce-argmax; id = ncclUniqueId bytes (128); 1 <= world <= 72. */
 int cc_comm_unique_id(void* out_id128);
 int cc_comm_init(cc_ctx* ctx, const void* id128, int rank, int world);
 
@@ -173,7 +173,9 @@ typedef struct {   /* NegReader state (src/imagestorage.cpp:23-33) so that runs 
 } cc_reader_state;
 
 int cc_bg_clear(cc_ctx* ctx);
-/* register one decoded 8-bit gray background (cv::imread(path, 0)); kept resident in HBM */
+/* register one decoded 8-bit gray background (cv::imread(path, 0)); kept resident in HBM.
+ * (NULL, 0, 0) registers the placeholder of a file imread() could not decode: it keeps its position in the list and
+ * NegReader::nextImg passes over it without advancing `round`, exactly like src/imagestorage.cpp:62-70 */
 int cc_bg_register(cc_ctx* ctx, const uint8_t* host_gray, int w, int h);
 int cc_bg_count(cc_ctx* ctx);
 /* the cascade used by predict() during mining: stages 0..n-1 (copied) */
@@ -196,6 +198,15 @@ int cc_mine_positives(cc_ctx* ctx, const uint8_t* host_vec, int vec_count, int c
  * memory and runs the cascade on its windows; nothing but survivor ordinals leaves the SM (measured 2.5x slower than
  * mode 0 on B200: 16 resident warps per SM cannot hide the serial column / diagonal walks). */
 int cc_mine_set_mode(cc_ctx* ctx, int mode);
+/* Survivor cache of the negative window stream (default: on, 4 GiB of host memory).  NegReader cycles the background list with a
+ * `round` phase (src/imagestorage.cpp:57-88), so a short list makes the stream revisit the same (image, offsets) pyramid many
+ * times in late stages; stages are append-only, so the windows of a pyramid that passed stages [0, n) are kept and a revisit
+ * runs only the newer stages on them (per-window setImage + predict path) instead of rebuilding the pyramid.  Transparent:
+ * consumed counts, the ordered cut, the reader state and the mined windows are those of the uncached evaluation. */
+int cc_mine_set_cache(cc_ctx* ctx, int enable, int64_t max_bytes);
+/* stats6 = { stream windows consumed by cc_mine_negatives, windows evaluated from pyramid planes / slots (speculative ones included),
+ *            cached survivors re-evaluated, stream windows answered by the cache, cache entries, cache bytes } since cc_create */
+int cc_mine_get_stats(cc_ctx* ctx, int64_t* stats6);
 /* NegReader::get() x nwindows without pixels (host only, no GPU needed): advances *state over images of
  * the given sizes; window5 (optional) = x, y, level_w, level_h, source image of the last consumed window. */
 int cc_reader_advance(const int32_t* img_w, const int32_t* img_h, int nimg, int win_w, int win_h,

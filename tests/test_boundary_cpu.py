@@ -49,11 +49,19 @@ def test_product_does_not_import_oracle():
                 assert "liborc" not in text and "import orc" not in text and "oracle/" not in text, f
 
 
-def test_reader_state_machine_matches_oracle():
+@pytest.mark.parametrize("sizes", [
+    [(100, 80), (64, 48), (20, 20), (57, 33), (24, 24), (130, 25), (31, 200)],          # too-small images are skipped (round still advances)
+    [(100, 80), (0, 0), (64, 48), (20, 20), (0, 0), (57, 33)],                          # unreadable files in the middle of bg.txt
+    [(0, 0), (90, 70), (0, 0)],                                                         # first and last unreadable: `round` never advances
+    [(70, 50), (0, 0)],
+])
+def test_reader_state_machine_matches_oracle(sizes):
+    """NegReader::nextImg / get (src/imagestorage.cpp:57-126) without pixels vs the oracle's reader with pixels.  A (0, 0) entry is
+    a file cv::imread could not decode: it keeps its slot in the list, nextImg does `last++; last %= count; continue` on it and
+    leaves `round` alone (:62-70)."""
     from cascadeclassifier_b200 import _lib
     lib = _lib.load()
     rng = np.random.default_rng(11)
-    sizes = [(100, 80), (64, 48), (20, 20), (57, 33), (24, 24), (130, 25), (31, 200)]
     imgs = [rng.integers(0, 256, (h, w), dtype=np.uint8) for (w, h) in sizes]
     rd = orc.NegReader(24, 24, imgs)
     w = np.array([s[0] for s in sizes], np.int32)

@@ -8,15 +8,33 @@ from conftest import make_samples
 pytestmark = pytest.mark.gpu
 
 
-def compare_stage(gpu_stage, ref, rel=1e-6):
-    """Trees must agree in (feature, threshold, leaf values).  A divergence is tolerated only where the
-    oracle itself sees a tie within float tolerance (north_star), after which the comparison stops."""
+def prove_tie(ev, labels, weights, mask, g_root, r_root, rel=2e-6):
+    """A divergence between the GPU and the oracle is accepted only as a float-level tie that is re-derived here, independently
+    of both: the squared-error criterion of find_split_ord_reg (src/o_cvboostree.cpp:361-426) is evaluated in numpy for the two
+    chosen (variable, threshold) pairs on the boosting state in force before the tree (oracle snapshot), and must agree to `rel`."""
+    act = np.flatnonzero(mask)
+    y = 2.0 * labels[act].astype(np.float64) - 1.0
+    w = weights[act]
+    quals = []
+    for root in (g_root, r_root):
+        f = ev.values([root["var_idx"]], 0, len(labels))[0][act]
+        left = f <= np.float32(root["c"])
+        L, R = w[left].sum(), w[~left].sum()
+        ls, rs = (w * y)[left].sum(), (w * y)[~left].sum()
+        quals.append((ls * ls * R + rs * rs * L) / (L * R))
+    assert abs(quals[0] - quals[1]) <= rel * abs(quals[1]), "not a tie: GPU %s -> %.12g, oracle %s -> %.12g" % (g_root, quals[0], r_root, quals[1])
+
+
+def compare_stage(gpu_stage, ref, tie=None):
+    """Trees must agree in (feature, threshold, leaf values, structure) -- all of them.  The one tolerated divergence (north_star:
+    "wherever split criteria are not tied within float tolerance") has to be PROVEN by the caller-supplied `tie(t, g_root, r_root)`
+    check; without it any difference fails.  Returns the number of identical trees."""
     n = min(len(gpu_stage.trees), len(ref.trees))
     for t in range(n):
         g, r = gpu_stage.trees[t], ref.trees[t]
-        if g[0]["var_idx"] != r[0]["var_idx"]:
-            assert abs(g[0]["quality"] - r[0]["quality"]) <= rel * abs(r[0]["quality"]), \
-                "tree %d: different feature without a quality tie: %s vs %s" % (t, g[0], r[0])
+        if g[0]["var_idx"] != r[0]["var_idx"] or g[0]["c"] != r[0]["c"]:
+            assert tie is not None, "tree %d differs: %s vs %s" % (t, g[0], r[0])
+            tie(t, g[0], r[0])
             return t
         assert len(g) == len(r)
         for a, b in zip(g, r):
@@ -28,6 +46,15 @@ def compare_stage(gpu_stage, ref, rel=1e-6):
             assert a["value"] == pytest.approx(b["value"], rel=1e-9, abs=1e-12)
     assert len(gpu_stage.trees) == len(ref.trees)
     return n
+
+
+def assert_full_stage(stage, ref):
+    """every tree, the stage threshold and every (N, HR, FA) row of the stdout table"""
+    assert compare_stage(stage, ref) == len(ref.trees)
+    assert stage.threshold == pytest.approx(ref.threshold, rel=1e-6, abs=1e-7)
+    assert [r[0] for r in stage.log] == [r[0] for r in ref.log]
+    for a, b in zip(stage.log, ref.log):
+        assert a[1] == pytest.approx(b[1]) and a[2] == pytest.approx(b[2])
 
 
 def run_pair(gpu_ctx, ftype, mode, W, H, npos, nneg, **bp):
@@ -57,19 +84,13 @@ def run_pair(gpu_ctx, ftype, mode, W, H, npos, nneg, **bp):
 def test_gab_stump_stage_matches_oracle(gpu_ctx, ftype, mode):
     ok, stage, ref, ev = run_pair(gpu_ctx, ftype, mode, 24, 24, 200, 400, max_false_alarm=0.05, weak_count=12)
     assert ok == ref.ok
-    agreed = compare_stage(stage, ref)
-    assert agreed >= 1
-    if agreed == len(ref.trees):
-        assert stage.threshold == pytest.approx(ref.threshold, rel=1e-6, abs=1e-7)
-        assert [r[0] for r in stage.log] == [r[0] for r in ref.log]
-        for a, b in zip(stage.log, ref.log):
-            assert a[1] == pytest.approx(b[1]) and a[2] == pytest.approx(b[2])
+    assert_full_stage(stage, ref)
 
 
 def test_hog_stage_matches_oracle(gpu_ctx):
     ok, stage, ref, ev = run_pair(gpu_ctx, orc.HOG, 0, 48, 96, 60, 120, max_false_alarm=0.05, weak_count=6)
     assert ok == ref.ok
-    assert compare_stage(stage, ref) >= 1
+    assert_full_stage(stage, ref)
 
 
 @pytest.mark.parametrize("bt", [orc.DAB, orc.RAB, orc.LB])
@@ -77,14 +98,14 @@ def test_other_boost_types(gpu_ctx, bt):
     ok, stage, ref, ev = run_pair(gpu_ctx, orc.HAAR, orc.BASIC, 24, 24, 120, 240, boost_type=bt, max_false_alarm=0.05,
                                   weak_count=6)
     assert ok == ref.ok
-    assert compare_stage(stage, ref) >= 1
+    assert_full_stage(stage, ref)
 
 
 def test_depth2_trees(gpu_ctx):
     ok, stage, ref, ev = run_pair(gpu_ctx, orc.HAAR, orc.BASIC, 24, 24, 150, 300, max_depth=2, max_false_alarm=0.05,
                                   weak_count=5)
     assert ok == ref.ok
-    assert compare_stage(stage, ref) >= 1
+    assert_full_stage(stage, ref)
 
 
 def test_stage_predict_matches_training_decision(gpu_ctx):
@@ -93,7 +114,10 @@ def test_stage_predict_matches_training_decision(gpu_ctx):
     sums = stage.predict(ev, 0, returnSum=True, count=n)
     dec = stage.predict(ev, 0, returnSum=False, count=n)
     thr = np.float32(stage.threshold) - np.float32(0.00001)
-    assert ((sums >= thr) == (dec == 1.0)).all() or True   # f32 rounding of sums can flip exact ties only
+    # the decision is taken on the f64 stage sum (src/boost.cpp:461-477); the returned f32 sum can only disagree at the threshold itself
+    bad = (sums >= thr) != (dec == 1.0)
+    assert (np.abs(sums[bad] - thr) <= 4e-7 * max(1.0, abs(float(thr)))).all(), (sums[bad], thr)
+    assert bad.sum() <= 2
     pos = sums[:100]
     assert (dec[:100] == 1).mean() >= 0.99
     assert np.isfinite(pos).all()
@@ -179,16 +203,63 @@ _MATRIX = [
 def test_stage_configuration_matrix(gpu_ctx, case):
     """Flag combinations the CLI accepts (-bt, -maxDepth, -weightTrimRate, -minHitRate, -w / -h, feature types) that the
     BASELINE configs do not exercise: one stage each, trees / thresholds / log rows against the oracle (trees are compared
-    up to the first float-level tie, which must not come before the first tree)."""
+    in full: every tree, threshold and log row)."""
     ftype, mode, W, H, npos, nneg, bp = _MATRIX[case]
     ok, stage, ref, ev = run_pair(gpu_ctx, ftype, mode, W, H, npos, nneg, **bp)
     assert ok == ref.ok
     if not ref.ok:
         return
-    agreed = compare_stage(stage, ref)
-    assert agreed >= 1
-    if agreed == len(ref.trees):
-        assert stage.threshold == pytest.approx(ref.threshold, rel=1e-6, abs=1e-7)
-        assert [r[0] for r in stage.log] == [r[0] for r in ref.log]
-        for a, b in zip(stage.log, ref.log):
-            assert a[1] == pytest.approx(b[1]) and a[2] == pytest.approx(b[2])
+    assert_full_stage(stage, ref)
+
+
+@pytest.mark.parametrize("bt", [orc.GAB, orc.DAB, orc.RAB, orc.LB])
+@pytest.mark.parametrize("ftype", [orc.HAAR, orc.LBP])
+def test_weights_and_mask_after_training_match_oracle(gpu_ctx, bt, ftype):
+    """update_weights (src/boost.cpp:168-407) + trim_weights (src/o_cvboost.cpp:101-139), checked directly: the AdaBoost
+    weights and the subsample mask the library holds after the last weak tree against the oracle's snapshot after the same
+    tree.  Weights: f64, relative 1e-12 (cvExp / reassociated sums); mask: identical."""
+    import ctypes as C
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200._lib import check
+    k = 4
+    imgs, labels = make_samples(140, 260)
+    n = len(imgs)
+    ev = ccb.CvFeatureEvaluator.create(ftype, gpu_ctx)
+    fp = ccb.CvFeatureParams.create(ftype)
+    ev.init(fp, n, (24, 24))
+    ev.setImages(imgs, labels)
+    stage = ccb.CvCascadeBoost()
+    # maxFalseAlarm ~ 0: the stage cannot stop before weak_count trees unless the training set is separated
+    assert stage.train(ev, n, 1024, 1024, ccb.CvCascadeBoostParams(boostType=bt, maxFalseAlarm=1e-6, minHitRate=0.999999, maxWeakCount=k))
+    w = np.zeros(n, np.float64)
+    m = np.zeros(n, np.uint8)
+    check(gpu_ctx.lib.cc_boost_get_weights(gpu_ctx.h, w.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)), "cc_boost_get_weights")
+    o = orc.Evaluator(ftype, 0, 24, 24, n)
+    o.set_images(imgs, labels)
+    td = orc.TrainData(o, n, orc.SORT_STABLE, 8)
+    ref = orc.boost_train(td, orc.boost_params(boost_type=bt, weak_count=k, max_false_alarm=1e-6, min_hit_rate=0.999999), cat_sort=orc.SORT_STABLE, record=True)
+    assert compare_stage(stage, ref) == len(ref.trees)
+    ow, om = ref.snapshot(len(ref.trees) - 1)
+    assert abs(w.sum() - 1.0) < 1e-9 and abs(ow.sum() - 1.0) < 1e-9
+    np.testing.assert_allclose(w, ow, rtol=1e-12, atol=1e-300)
+    assert ((m != 0) == (om != 0)).all()
+    assert 0 < int((m != 0).sum()) <= n
+
+
+def test_gpu_stumps_match_cv2_boost(gpu_ctx):
+    """Independent pin of the CUDA trainer itself (not through the oracle): cv2.ml.Boost GENTLE stumps on the fval matrix the
+    library computed -- variable, f32 threshold, quality, leaf values of every weak tree (tests/cv2_boost_ref.py)."""
+    import cascadeclassifier_b200 as ccb
+    from cv2_boost_ref import assert_stumps_match, cv2_boost_stumps
+    imgs, labels = make_samples(120, 200, 12, 12)
+    n = len(imgs)
+    ev = ccb.CvFeatureEvaluator.create(orc.HAAR, gpu_ctx)
+    ev.init(ccb.CvHaarFeatureParams(orc.ALL), n, (12, 12))
+    ev.setImages(imgs, labels)
+    F = ev.getNumFeatures()
+    X = np.concatenate([ev.values(list(range(a, min(F, a + 4096))), 0, n) for a in range(0, F, 4096)]).T.copy()
+    for bt, name in ((orc.GAB, "GAB"), (orc.LB, "LB"), (orc.RAB, "RAB")):
+        stage = ccb.CvCascadeBoost()
+        assert stage.train(ev, n, 1024, 1024, ccb.CvCascadeBoostParams(boostType=bt, maxFalseAlarm=1e-6, minHitRate=0.999999, maxWeakCount=8))
+        k = assert_stumps_match(stage.trees, cv2_boost_stumps(X, labels, name, 8, 0.95), 3, check_quality=(name != "RAB"), what="gpu " + name)
+        assert k >= 3
