@@ -86,16 +86,19 @@ def _signatures():
         "cc_boost_get_row_quality": (i32, [vp, i32, i32, vp]),
         "cc_boost_set_search_mode": (i32, [vp, i32]),
         "cc_boost_set_sort_mode": (i32, [vp, i32]),
+        "cc_boost_set_tree_path": (i32, [vp, i32]),
         "cc_boost_get_sort_stats": (i32, [vp, P(i64)]),
         "cc_boost_get_search_stats": (i32, [vp, P(i64), P(i64), P(i64)]),
         "cc_stage_predict": (i32, [vp, P(Stage), i32, i32, i32, vp]),
         "cc_bg_clear": (i32, [vp]),
         "cc_bg_register": (i32, [vp, vp, i32, i32]),
+        "cc_bg_register_device": (i32, [vp, vp, i32, i32, i32]),
         "cc_bg_count": (i32, [vp]),
         "cc_cascade_set_stages": (i32, [vp, P(Stage), i32]),
         "cc_mine_negatives": (i32, [vp, i32, i32, f64, P(ReaderState), P(i64), P(C.c_int32)]),
         "cc_mine_positives": (i32, [vp, vp, i32, i32, P(C.c_int32), P(i64), P(C.c_int32)]),
         "cc_mine_scan": (i32, [vp, i32, i32, P(i64), P(i64)]),
+        "cc_mine_scan_digest": (i32, [vp, i32, i32, P(i64), P(i64), P(C.c_uint64)]),
         "cc_mine_set_mode": (i32, [vp, i32]),
         "cc_mine_set_cache": (i32, [vp, i32, i64]),
         "cc_mine_get_stats": (i32, [vp, vp]),

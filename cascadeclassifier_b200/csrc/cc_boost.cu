@@ -115,6 +115,8 @@ struct BoostBuffers {
   NodeStats* h_stats = nullptr;       // pinned
   BestSplit* h_best = nullptr;
   TreeSummary* h_summary = nullptr;
+  int* d_tree_ok = nullptr;           // stump path
+  int* h_tree_ok = nullptr;
   // stage state
   int boost_type = CC_BOOST_GENTLE, crit = CRIT_SQERR, is_classifier = 0, have_subsample = 0;
   cc_boost_params params;
@@ -126,6 +128,7 @@ struct BoostBuffers {
   std::vector<int> seed_rows;         // strided sample of the local rows + the winners of this stage so far
   int seed_cap = 0, n_seed_static = 0;
   int search_mode = 0;                // 0 = pruned (default), 1 = exhaustive (every row evaluated exactly)
+  int tree_path = 0;                  // 0 = stumps grown without a host round trip inside the tree (default), 1 = general node-by-node path
   long long stat_searches = 0, stat_seed_rows = 0, stat_flag_rows = 0;
 };
 
@@ -137,6 +140,7 @@ int boost_free(cc_ctx* ctx) {
     cudaFree(b->node_of); cudaFree(b->rowbest); cudaFree(b->rowbest_cat); cudaFree(b->d_stats); cudaFree(b->d_best);
     cudaFree(b->d_summary); cudaFree(b->d_tree); cudaFree(b->d_ctl); cudaFree(b->d_seed_rows); cudaFree(b->d_flag_rows);
     cudaFreeHost(b->h_stats); cudaFreeHost(b->h_best); cudaFreeHost(b->h_summary);
+    cudaFree(b->d_tree_ok); cudaFreeHost(b->h_tree_ok);
     delete b;
     ctx->boost = nullptr;
   }
@@ -158,6 +162,8 @@ static int ensure_boost(cc_ctx* ctx, int N, size_t nrows) {
     CC_CUDA(cudaMallocHost(&b->h_stats, sizeof(NodeStats) * CC_MAX_TREE_NODES));
     CC_CUDA(cudaMallocHost(&b->h_best, sizeof(BestSplit) * 16));
     CC_CUDA(cudaMallocHost(&b->h_summary, sizeof(TreeSummary)));
+    CC_CUDA(cudaMalloc(&b->d_tree_ok, sizeof(int)));
+    CC_CUDA(cudaMallocHost(&b->h_tree_ok, sizeof(int)));
   }
   if (N > b->cap_n) {
     cudaFree(b->weights); cudaFree(b->weak_eval); cudaFree(b->stage_sum); cudaFree(b->sum_response); cudaFree(b->wnode);
@@ -480,7 +486,7 @@ template <int CRIT, bool HAS_Y>
 __global__ void __launch_bounds__(SS_THREADS, 1)
 k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ sval, int n_stride, int N, int nrows,
                    const double* __restrict__ wnode, const float* __restrict__ ynode, const NodeStats* __restrict__ stats,
-                   float filter_abs, RowBest* __restrict__ out, const int* __restrict__ row_list,
+                   double filter_ymax2, RowBest* __restrict__ out, const int* __restrict__ row_list,
                    const unsigned int* __restrict__ list_count, SearchCtl* __restrict__ ctl) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   // rows to search: all local rows, or the entries of row_list (seed rows / rows flagged by k_ss_bound)
@@ -500,6 +506,10 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
   const double totA = st.rcw[0];
   const double totB = (CRIT == CRIT_SQERR) ? st.rsum0 : st.rcw[1];
   const float ftotA = (float)totA, ftotB = (float)totB;
+  // absolute slack of the f32 pre-filter: the f32 prefix sums carry ~1e-6 * (node weight) * |y|max^2 of absolute error
+  // (see criterion32); LogitBoost targets are clipped to |z| <= 10 (boost.cpp:347).  Taken from the node statistics on the
+  // device, so that the host does not have to read them back before it launches the search.
+  const float filter_abs = (float)(4e-6 * (st.rcw[0] + st.rcw[1]) * filter_ymax2 + 1e-30);
   // broadcast from lane 0 so that the compiler knows the row loop is warp-uniform (no collective-sync
   // wrappers around the shuffles inside it)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -927,6 +937,7 @@ __global__ void k_apply_split(EvalView e, int N, int nid, int lid, int rid, cons
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= N || node_of[s] != nid) return;
   const BestSplit b = *best;
+  if (!b.valid) return;                    // speculative launch of the stump path: no split was found
   const float val = d_eval_var(e, b.var, s);
   bool left;
   if (e.ftype == CC_FEATURE_LBP) { const int c = (int)val; left = (b.subset[c >> 5] & (1 << (c & 31))) != 0; }
@@ -965,9 +976,10 @@ __global__ void __launch_bounds__(ONE_CTA, 1)
 k_tree_finish(EvalView e, int N, int boost_type, int have_subsample, double trim_rate, float min_hit_rate,
               const DevNode* __restrict__ tree, const uint8_t* __restrict__ labels, const int* __restrict__ orig_response,
               double* weights, double* weak_eval, double* treeval, double* stage_sum, double* sum_response, float* responses,
-              uint8_t* mask, TreeSummary* summary) {
+              uint8_t* mask, TreeSummary* summary, const int* __restrict__ tree_ok) {
   __shared__ double scratch[32], scratch2[32], scratch3[32];
   __shared__ unsigned long long s_u64;
+  if (tree_ok && !*tree_ok) return;        // stump path: the root was not split (tree->train() failed, src/boost.cpp:436-440): nothing is updated
   // (a) responses of the samples that did not take part in the tree, and the threshold-rule output for everyone
   for (int s = threadIdx.x; s < N; s += blockDim.x) {
     const double tv = d_tree_predict(e, tree, s);
@@ -1157,6 +1169,25 @@ k_tree_finish(EvalView e, int N, int boost_type, int have_subsample, double trim
   (void)s_u64;
 }
 
+// Stump path (max_depth == 1): the tree is assembled on the device so that k_tree_finish can follow without a host round trip.
+// ok = the root may be split (CvDTree::try_split_node, src/o_cvdtree.cpp:122-187 -- same tests as grow_node()) and a split was found.
+__global__ void k_build_stump(const NodeStats* __restrict__ stats, const BestSplit* __restrict__ best, int min_sample_count,
+                              float regression_accuracy, int is_classifier, DevNode* __restrict__ tree, int* __restrict__ tree_ok) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const NodeStats st = stats[0];
+  bool can_split = st.n > min_sample_count;
+  if (can_split && is_classifier) { if (((st.cls_count[0] != 0) + (st.cls_count[1] != 0)) == 1) can_split = false; }
+  else if (can_split) { if (sqrt(st.risk) / st.n < (double)regression_accuracy) can_split = false; }
+  const BestSplit b = *best;
+  DevNode root, l, r;
+  root.left = 1; root.right = 2; root.var_idx = b.var; root.c = b.c; root.value = st.value;
+  for (int i = 0; i < 8; ++i) { root.subset[i] = b.subset[i]; l.subset[i] = 0; r.subset[i] = 0; }
+  l.left = l.right = -1; l.var_idx = -1; l.c = 0.f; l.value = stats[1].value;
+  r.left = r.right = -1; r.var_idx = -1; r.c = 0.f; r.value = stats[2].value;
+  tree[0] = root; tree[1] = l; tree[2] = r;
+  *tree_ok = (can_split && b.valid) ? 1 : 0;
+}
+
 __global__ void k_row_quality(const RowBest* rows, const RowBestCat* rows_cat, int nrows, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nrows) { const float q = rows ? rows[i].q : rows_cat[i].q; out[i] = q > 0.f ? q : 0.f; }
@@ -1197,10 +1228,7 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
     const size_t smem = (size_t)(N + 1) * 8 + (size_t)SS_WARPS * ntile * (sizeof(TileCarry) + 4) + (has_y ? (size_t)(N + 1) * 4 : 0) + 16;
     CC_REQUIRE(smem <= 227 * 1024, CC_ERR_UNSUPPORTED, "split search: numSamples %d needs %zu B of shared memory (limit 227 KB)", N, smem);
     const int per_sm = std::max(1, std::min(4, (int)((220 * 1024) / (smem + 1024))));
-    // absolute slack of the f32 pre-filter: the f32 prefix sums carry ~1e-6 * (node weight) * |y|max^2
-    // of absolute error (see criterion32); LogitBoost targets are clipped to |z| <= 10 (boost.cpp:347).
-    const double ymax2 = has_y ? 100.0 : 1.0;
-    const float filter_abs = (float)(4e-6 * (b->h_stats[nid].rcw[0] + b->h_stats[nid].rcw[1]) * ymax2 + 1e-30);
+    const double ymax2 = has_y ? 100.0 : 1.0;      // slack of the f32 pre-filter, see k_split_search_ord
     const int blocks = std::min((ctx->nrows + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
     const bool pruned = b->search_mode == 0 && !has_y && ctx->nrows >= 4 * SEED_TARGET;
     CC_CUDA(cudaMemsetAsync(b->d_ctl, 0, sizeof(SearchCtl), ctx->stream));
@@ -1208,7 +1236,7 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
   {                                                                                                                         \
     CC_CUDA(cudaFuncSetAttribute(k_split_search_ord<CR, HY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
     k_split_search_ord<CR, HY><<<BLOCKS, SS_THREADS, smem, ctx->stream>>>(ctx->d_sidx, ctx->d_sval, ctx->n_stride, N, NWORK, \
-                                                                          b->wnode, b->ynode, b->d_stats + nid, filter_abs, b->rowbest, \
+                                                                          b->wnode, b->ynode, b->d_stats + nid, ymax2, b->rowbest, \
                                                                           LIST, COUNT, b->d_ctl);                           \
   }
 #define LAUNCH_SS_CRIT(BLOCKS, NWORK, LIST, COUNT)                                                             \
@@ -1323,6 +1351,64 @@ static int grow_node(cc_ctx* ctx, BoostBuffers* b, std::vector<HostNode>& nodes,
   return CC_OK;
 }
 
+// One weak tree of depth 1 without a host round trip inside: root statistics, split search (+ the exchange between the ranks),
+// the split, both leaves, the tree record and everything that follows a finished tree (k_tree_finish) are queued back to back;
+// the host reads statistics, winner and summary ONCE per tree.  The launches that depend on "can the root be split / was a split
+// found" are speculative: k_apply_split ignores an invalid winner and k_tree_finish returns at once when the tree failed.
+// Same results as grow_node() + the tail of cc_boost_train's loop (test_stump_path_equals_general_path).
+static int grow_stump_and_finish(cc_ctx* ctx, BoostBuffers* b, const EvalView& ev, float min_hit_rate, std::vector<HostNode>& nodes, bool& ok) {
+  const int N = ctx->N;
+  {
+    ScopedTimer tm(ctx, "boost_small", 1);
+    k_node_prepare<<<1, ONE_CTA, 0, ctx->stream>>>(N, 0, b->is_classifier, b->boost_type, b->node_of, b->weights, b->responses,
+                                                   b->wnode, b->ynode, b->weak_eval, b->d_stats);
+    CC_CUDA(cudaGetLastError());
+  }
+  CC_CHECK(launch_split_search(ctx, b, 0));
+  CC_CHECK(exchange_candidates(ctx, b->d_best));
+  {
+    ScopedTimer tm(ctx, "boost_small", 5);
+    k_apply_split<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ev, N, 0, 1, 2, b->d_best, b->node_of);
+    // the leaves: wnode / ynode are no longer needed (no further search), only the node values and weak_eval
+    k_node_prepare<<<1, ONE_CTA, 0, ctx->stream>>>(N, 1, b->is_classifier, b->boost_type, b->node_of, b->weights, b->responses,
+                                                   b->wnode, b->ynode, b->weak_eval, b->d_stats);
+    k_node_prepare<<<1, ONE_CTA, 0, ctx->stream>>>(N, 2, b->is_classifier, b->boost_type, b->node_of, b->weights, b->responses,
+                                                   b->wnode, b->ynode, b->weak_eval, b->d_stats);
+    k_build_stump<<<1, 32, 0, ctx->stream>>>(b->d_stats, b->d_best, b->params.min_sample_count, b->params.regression_accuracy, b->is_classifier,
+                                             b->d_tree, b->d_tree_ok);
+    k_tree_finish<<<1, ONE_CTA, 0, ctx->stream>>>(ev, N, b->boost_type, b->have_subsample, b->params.weight_trim_rate, min_hit_rate,
+                                                  b->d_tree, ctx->d_labels, b->orig_response, b->weights, b->weak_eval, b->treeval,
+                                                  b->stage_sum, b->sum_response, b->responses, b->mask, b->d_summary, b->d_tree_ok);
+    CC_CUDA(cudaGetLastError());
+  }
+  CC_CUDA(cudaMemcpyAsync(b->h_stats, b->d_stats, sizeof(NodeStats) * 3, cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaMemcpyAsync(b->h_best, b->d_best, sizeof(BestSplit), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaMemcpyAsync(b->h_tree_ok, b->d_tree_ok, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaMemcpyAsync(b->h_summary, b->d_summary, sizeof(TreeSummary), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const BestSplit bs = *b->h_best;
+  if (b->d_seed_rows && !b->row_quality_valid) b->stat_flag_rows += bs.pad[0];
+  nodes[0].value = b->h_stats[0].value; nodes[0].n = b->h_stats[0].n;
+  ok = *b->h_tree_ok != 0;
+  if (!ok) return CC_OK;
+  if (b->d_seed_rows && bs.var >= ctx->row0 && bs.var < ctx->row0 + ctx->nrows && (int)b->seed_rows.size() < b->seed_cap) {
+    const int lr = bs.var - ctx->row0;
+    if (std::find(b->seed_rows.begin(), b->seed_rows.end(), lr) == b->seed_rows.end()) {
+      b->seed_rows.push_back(lr);
+      CC_CUDA(cudaMemcpyAsync(b->d_seed_rows + b->seed_rows.size() - 1, &b->seed_rows.back(), sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  HostNode l, r;
+  l.depth = r.depth = 1;
+  l.value = b->h_stats[1].value; l.n = b->h_stats[1].n;
+  r.value = b->h_stats[2].value; r.n = b->h_stats[2].n;
+  nodes.push_back(l); nodes.push_back(r);
+  nodes[0].left = 1; nodes[0].right = 2;
+  nodes[0].var = bs.var; nodes[0].c = bs.c; nodes[0].q = bs.q; nodes[0].pos = bs.pos;
+  std::memcpy(nodes[0].subset, bs.subset, sizeof(bs.subset));
+  return CC_OK;
+}
+
 }  // namespace cc
 
 using namespace cc;
@@ -1375,6 +1461,11 @@ int cc_boost_train(cc_ctx* ctx, int num_samples, const cc_boost_params* p, cc_st
       CC_CUDA(cudaGetLastError());
     }
     std::vector<HostNode> nodes(1);
+    if (b->params.max_depth == 1 && b->tree_path == 0) {
+      bool ok = false;
+      CC_CHECK(grow_stump_and_finish(ctx, b, ev, p->min_hit_rate, nodes, ok));
+      if (!ok) break;                  // tree->train() returned false (root not split), boost.cpp:436-440
+    } else {
     CC_CHECK(grow_node(ctx, b, nodes, 0));
     if (nodes[0].left < 0) break;      // tree->train() returned false (root not split), boost.cpp:436-440
     // upload the tree for the threshold-rule pass
@@ -1389,11 +1480,12 @@ int cc_boost_train(cc_ctx* ctx, int num_samples, const cc_boost_params* p, cc_st
       ScopedTimer tm(ctx, "boost_small", 1);
       k_tree_finish<<<1, ONE_CTA, 0, ctx->stream>>>(ev, N, b->boost_type, b->have_subsample, b->params.weight_trim_rate, p->min_hit_rate,
                                                     b->d_tree, ctx->d_labels, b->orig_response, b->weights, b->weak_eval, b->treeval,
-                                                    b->stage_sum, b->sum_response, b->responses, b->mask, b->d_summary);
+                                                    b->stage_sum, b->sum_response, b->responses, b->mask, b->d_summary, nullptr);
       CC_CUDA(cudaGetLastError());
     }
     CC_CUDA(cudaMemcpyAsync(b->h_summary, b->d_summary, sizeof(TreeSummary), cudaMemcpyDeviceToHost, ctx->stream));
     CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     const TreeSummary ts = *b->h_summary;
     b->have_subsample = ts.have_subsample;
     // record the tree (DAB: tree->scale(C), src/boost.cpp:316)
@@ -1433,6 +1525,13 @@ int cc_boost_set_search_mode(cc_ctx* ctx, int mode) {
   CC_REQUIRE(ctx && (mode == 0 || mode == 1), CC_ERR_BAD_ARG, "cc_boost_set_search_mode: mode must be 0 (pruned) or 1 (exhaustive)");
   if (!ctx->boost) ctx->boost = new BoostBuffers();
   ctx->boost->search_mode = mode;
+  return CC_OK;
+}
+
+int cc_boost_set_tree_path(cc_ctx* ctx, int mode) {
+  CC_REQUIRE(ctx && (mode == 0 || mode == 1), CC_ERR_BAD_ARG, "cc_boost_set_tree_path: mode must be 0 (stump fast path) or 1 (general path)");
+  if (!ctx->boost) ctx->boost = new BoostBuffers();
+  ctx->boost->tree_path = mode;
   return CC_OK;
 }
 

@@ -805,11 +805,28 @@ struct BgImage { int w = 0, h = 0, pitch = 0; uint8_t* d_px = nullptr; };      /
 struct PyrEntry { int n_stages = 0; long long nwin = 0; std::vector<uint32_t> surv; };
 struct PyrCache {
   std::unordered_map<uint64_t, PyrEntry> map;
+  std::vector<PyrEntry*> table;        // [image][offY][offX] -> entry (nullptr: none); rebuilt lazily, see lookup()
+  int table_imgs = 0;
+  bool table_valid = false;
   std::vector<uint64_t> stage_hash;    // hash of every stage of the cascade the entries were computed with
   size_t bytes = 0, max_bytes = (size_t)4 << 30;
   bool enabled = true;
   int W = 0, H = 0, ftype = -1, haar_mode = -1;
-  void clear() { map.clear(); bytes = 0; }
+  void clear() { map.clear(); bytes = 0; table_valid = false; }
+  // assemble() looks a pyramid up about a million times per late stage: a flat table instead of the hash map (entries are
+  // stable in an unordered_map until erased; every insert / erase invalidates the table)
+  const PyrEntry* lookup(int src, int offX, int offY, int nimg) {
+    if (!table_valid) {
+      table.assign((size_t)nimg * W * H, nullptr);
+      table_imgs = nimg;
+      for (auto& kv : map) {
+        const int s = (int)(kv.first >> 32), oy = (int)((kv.first >> 16) & 0xFFFF), ox = (int)(kv.first & 0xFFFF);
+        if (s < nimg && oy < H && ox < W) table[((size_t)s * H + oy) * W + ox] = &kv.second;
+      }
+      table_valid = true;
+    }
+    return table[((size_t)src * H + offY) * W + offX];
+  }
 };
 
 struct MineState {
@@ -1092,6 +1109,7 @@ static void cache_validate(cc_ctx* ctx, MineState* m, const cc_stage* stages, in
     for (auto it = c.map.begin(); it != c.map.end();) {
       if ((size_t)it->second.n_stages > common) { c.bytes -= it->second.surv.size() * 4 + 64; it = c.map.erase(it); } else ++it;
     }
+    c.table_valid = false;
   }
   c.stage_hash.swap(hs);
 }
@@ -1762,6 +1780,7 @@ static void merge_and_update_cache(MineState* m, const Batch& bt, const std::vec
       if (pc.bytes + v.size() * 4 + 64 > pc.max_bytes) continue;
       PyrEntry e; e.n_stages = ns; e.nwin = mp.nwin; e.surv = v;
       pc.map.emplace(mp.key, std::move(e));
+      pc.table_valid = false;
       pc.bytes += v.size() * 4 + 64;
     } else {
       pc.bytes -= it->second.surv.size() * 4;
@@ -1843,6 +1862,19 @@ int cc_bg_register(cc_ctx* ctx, const uint8_t* host_gray, int w, int h) {
   CC_CUDA(cudaMalloc(&b.d_px, (size_t)b.pitch * h));
   CC_CUDA(cudaMemcpy2DAsync(b.d_px, (size_t)b.pitch, host_gray, (size_t)w, (size_t)w, (size_t)h, cudaMemcpyHostToDevice, ctx->stream));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  m->bgs.push_back(b);
+  return CC_OK;
+}
+
+int cc_bg_register_device(cc_ctx* ctx, const uint8_t* dev_gray, int w, int h, int pitch) {
+  CC_REQUIRE(ctx && dev_gray && w > 0 && h > 0 && pitch >= w, CC_ERR_BAD_ARG, "cc_bg_register_device: bad arguments");
+  MineState* m = mine_state(ctx);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  BgImage b;
+  m->cache.clear();
+  b.w = w; b.h = h; b.pitch = (w + 15) & ~15;
+  CC_CUDA(cudaMalloc(&b.d_px, (size_t)b.pitch * h));
+  CC_CUDA(cudaMemcpy2DAsync(b.d_px, (size_t)b.pitch, dev_gray, (size_t)pitch, (size_t)w, (size_t)h, cudaMemcpyDeviceToDevice, ctx->stream));
   m->bgs.push_back(b);
   return CC_OK;
 }
@@ -1930,11 +1962,11 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     more = true;
     int open_pyr = -1;                  // bt.miss entry of the pyramid being assembled from its first window
     while ((double)bt.nwin < want && bt.neval < max_batch && more && (long long)bt.cand_eval.size() < CAND_CAP && bt.segs.size() < SEG_CAP) {
-      if (cache_on && cur.is_pyramid_start()) {
+      if (cache_on && ((cur.fresh && cur.pointX == cur.offX && cur.pointY == cur.offY) || cur.is_pyramid_start())) {
         const uint64_t key = cur.pyramid_key();
-        auto it = m->cache.map.find(key);
-        if (it != m->cache.map.end() && it->second.n_stages <= nstages) {
-          const PyrEntry& e = it->second;
+        const PyrEntry* ep = m->cache.lookup(cur.src, cur.offX, cur.offY, (int)m->bgs.size());
+        if (ep && ep->n_stages <= nstages) {
+          const PyrEntry& e = *ep;
           CachedPyr cp;
           cp.start = cur; cp.base = bt.nwin; cp.nwin = e.nwin; cp.key = key; cp.cand0 = bt.cand.size(); cp.ncand = e.surv.size();
           for (const uint32_t o : e.surv) {
@@ -2237,6 +2269,10 @@ int cc_mine_serial_cut(const uint32_t* survivors, int64_t nsurv, int64_t nwin, i
 }
 
 int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* survivors_out) {
+  return cc_mine_scan_digest(ctx, img0, nimg, windows, survivors_out, nullptr);
+}
+
+int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* survivors_out, uint64_t* digest_out) {
   CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_mine_scan: evaluator not initialised");
   MineState* m = mine_state(ctx);
   CC_REQUIRE(img0 >= 0 && nimg > 0 && img0 + nimg <= (int)m->bgs.size(), CC_ERR_BAD_ARG, "cc_mine_scan: image range out of bounds");
@@ -2247,27 +2283,36 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
   const bool tile_path = level_path && m->mode == 3 && tgeom.ok;
   const long long max_batch = level_path ? level_path_max_batch(ctx, m) : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
   long long total = 0, surv = 0;
+  uint64_t digest = 0;                 // order-independent digest of the surviving windows' scan ordinals
   std::vector<unsigned> survivors;
+  auto account = [&](long long base) {
+    surv += (long long)survivors.size();
+    for (const unsigned o : survivors) {
+      uint64_t z = (uint64_t)(base + (long long)o) + 0x9E3779B97F4A7C15ull;
+      z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+      digest += z;
+    }
+  };
   // every image from its first level (round 0 offsets), independent of the reader state
   std::vector<BgImage> one(1);
   Batch bt;
   int slot = 0;
-  long long pend_nwin = 0;             // windows of the batch in flight in slot ^ 1
+  long long pend_nwin = 0, pend_base = 0;      // windows / first scan ordinal of the batch in flight in slot ^ 1
   auto flush = [&]() -> int {
     if (bt.nwin == 0) return CC_OK;
     const int nwin = (int)bt.nwin;
     if (level_path && !tile_path) {
       // two batches in flight, as in cc_mine_negatives: launch this one, then collect the previous one
       CC_CHECK(launch_levels(ctx, m, bt, slot));
-      if (pend_nwin) { CC_CHECK(finish_levels(ctx, m, slot ^ 1, pend_nwin, survivors)); surv += (long long)survivors.size(); }
-      pend_nwin = nwin; slot ^= 1;
+      if (pend_nwin) { CC_CHECK(finish_levels(ctx, m, slot ^ 1, pend_nwin, survivors)); account(pend_base); }
+      pend_nwin = nwin; pend_base = total; slot ^= 1;
       total += nwin;
       bt = Batch();
       return CC_OK;
     }
     if (level_path) {
       CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
-      total += nwin; surv += (long long)survivors.size();
+      account(total); total += nwin;
       bt = Batch();
       return CC_OK;
     }
@@ -2280,7 +2325,7 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
       CC_CUDA(cudaGetLastError());
     }
     CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
-    total += nwin; surv += (long long)survivors.size();
+    account(total); total += nwin;
     bt = Batch();
     return CC_OK;
   };
@@ -2314,9 +2359,10 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
     }
   }
   CC_CHECK(flush());
-  if (pend_nwin) { CC_CHECK(finish_levels(ctx, m, slot ^ 1, pend_nwin, survivors)); surv += (long long)survivors.size(); }
+  if (pend_nwin) { CC_CHECK(finish_levels(ctx, m, slot ^ 1, pend_nwin, survivors)); account(pend_base); }
   if (windows) *windows = total;
   if (survivors_out) *survivors_out = surv;
+  if (digest_out) *digest_out = digest;
   return CC_OK;
 }
 

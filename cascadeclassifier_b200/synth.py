@@ -142,6 +142,48 @@ def make_backgrounds(count, w, h, seed0=1000, clutter=0.0):
     return [make_background(w, h, seed0 + i, clutter) for i in range(count)]
 
 
+def make_backgrounds_device(count, w, h, seed, device, chunk=64):
+    """`count` distinct 8-bit gray backgrounds generated ON the GPU (plumbing for benchmarks at BASELINE configs[4] size: 4096
+    images of 1920x1080 would take the numpy generator above the better part of an hour).  Multi-octave value noise (bilinear
+    upsampling of seeded random grids), random flat / ramp rectangles and per-pixel noise, so that window variance is never zero.
+    Returns a uint8 torch tensor [count, h, w] on `device`; deterministic for (count, w, h, seed) on a given GPU model."""
+    import torch
+    import torch.nn.functional as Fn
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    out = torch.empty((count, h, w), dtype=torch.uint8, device=device)
+    ys = torch.arange(h, device=device, dtype=torch.float32)[None, :, None]
+    xs = torch.arange(w, device=device, dtype=torch.float32)[None, None, :]
+    for c0 in range(0, count, chunk):
+        n = min(chunk, count - c0)
+        img = torch.zeros((n, 1, h, w), device=device)
+        amp = 1.0
+        for octave in range(5):
+            gh, gw = max(2, h >> (7 - octave)), max(2, w >> (7 - octave))
+            grid = torch.rand((n, 1, gh + 1, gw + 1), generator=g, device=device)
+            img += amp * Fn.interpolate(grid, size=(h, w), mode="bilinear", align_corners=True)
+            amp *= 0.6
+        img = img[:, 0]
+        lo = img.amin(dim=(1, 2), keepdim=True)
+        hi = img.amax(dim=(1, 2), keepdim=True)
+        img = (img - lo) / (hi - lo).clamp_min(1e-6) * 255.0
+        for _ in range(12):
+            r = torch.rand((n, 6), generator=g, device=device)
+            x0 = (r[:, 0] * (w - 8))[:, None, None]
+            y0 = (r[:, 1] * (h - 8))[:, None, None]
+            x1 = x0 + 8 + r[:, 2][:, None, None] * (w / 3)
+            y1 = y0 + 8 + r[:, 3][:, None, None] * (h / 3)
+            inside = (xs >= x0) & (xs < x1) & (ys >= y0) & (ys < y1)
+            level = (r[:, 4] * 255.0)[:, None, None]
+            ramp = (xs - x0) / (x1 - x0) * 120.0 - 60.0
+            flat = img * 0.3 + level * 0.7
+            grad = img + ramp * (r[:, 5][:, None, None] * 2 - 1)
+            img = torch.where(inside, torch.where((r[:, 5] < 0.5)[:, None, None], flat, grad), img)
+        img += torch.randn((n, h, w), generator=g, device=device) * 3.0
+        out[c0:c0 + n] = img.round().clamp(0, 255).to(torch.uint8)
+    return out
+
+
 # ---- on-disk formats -------------------------------------------------------------------------
 def write_vec(path, samples):
     """.vec: int32 count, int32 vecSize, int16 0, int16 0; per sample 1 pad byte + vecSize int16."""

@@ -147,6 +147,11 @@ int cc_boost_get_weights(cc_ctx* ctx, double* weights, uint8_t* mask);
  * serial loop of DTreeBestSplitFinder (src/o_cvdtree.cpp:313-357), whose init_quality threading prunes in the
  * same spirit.  1 = exhaustive: every variable searched exactly (keeps per-variable qualities for the getter). */
 int cc_boost_set_search_mode(cc_ctx* ctx, int mode);
+/* How a weak tree of depth 1 is grown.  0 (default): root statistics, split search, exchange between the ranks, the split, both
+ * leaves and the weight update / trimming / isErrDesired pass are queued back to back and the host reads the result once per
+ * tree.  1: the general node-by-node path that deeper trees always take (CvDTree::try_split_node recursion, src/o_cvdtree.cpp:122-187),
+ * with a host decision after every node.  Same trees. */
+int cc_boost_set_tree_path(cc_ctx* ctx, int mode);
 /* How the sorted-index rows (std::sort + LessThanIdx per feature, src/o_cvcascadeboosttraindata.cpp:490-563) are built.
  * 0 (default) = Haar: bucket + rank sort (one distribution pass into value buckets, exact ranking inside a bucket) with
  * the radix kernel on the rows it defers; HOG: radix kernel.  1 = stable LSD radix passes on every row.  2 = bucket +
@@ -177,6 +182,9 @@ int cc_bg_clear(cc_ctx* ctx);
  * (NULL, 0, 0) registers the placeholder of a file imread() could not decode: it keeps its position in the list and
  * NegReader::nextImg passes over it without advancing `round`, exactly like src/imagestorage.cpp:62-70 */
 int cc_bg_register(cc_ctx* ctx, const uint8_t* host_gray, int w, int h);
+/* same for an image that is already in device memory (decoded on the GPU / generated there); row pitch in bytes.  The copy is
+ * ordered on the ctx's stream: the source may be reused after cc_synchronize */
+int cc_bg_register_device(cc_ctx* ctx, const uint8_t* dev_gray, int w, int h, int pitch);
 int cc_bg_count(cc_ctx* ctx);
 /* the cascade used by predict() during mining: stages 0..n-1 (copied) */
 int cc_cascade_set_stages(cc_ctx* ctx, const cc_stage* stages, int n);
@@ -222,6 +230,9 @@ int cc_mine_serial_cut(const uint32_t* survivors, int64_t nsurv, int64_t nwin, i
 /* throughput probe used by bench.py: evaluate the cascade on every window of backgrounds
  * [img0, img0+nimg) at round 0 without touching evaluator slots; returns windows and survivors */
 int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* survivors);
+/* same, plus an order-independent 64-bit digest of the scan ordinals of the surviving windows: two miners (cc_mine_set_mode)
+ * or two runs agree on WHICH windows pass iff their digests agree */
+int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* survivors, uint64_t* digest);
 
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* CUDA-event time (ms) and launch count accumulated per kernel family since the last reset.

@@ -30,7 +30,33 @@ def make_samples(n_pos, n_neg, W=24, H=24, seed=7):
     return imgs, labels
 
 
+def pytest_collection_modifyitems(config, items):
+    """Everything under tests/test_gpu_*.py needs a CUDA device: make sure it carries the `gpu` marker (so `-m "not gpu"` never
+    collects it), and when no device is visible skip those tests instead of reporting errors."""
+    gpu_mark = pytest.mark.gpu
+    have_gpu = None
+    for item in items:
+        if os.path.basename(str(item.fspath)).startswith("test_gpu_") and "gpu" not in item.keywords:
+            item.add_marker(gpu_mark)
+        if "gpu" in item.keywords:
+            if have_gpu is None:
+                have_gpu = _cuda_device_present()
+            if not have_gpu:
+                item.add_marker(pytest.mark.skip(reason="no CUDA device (run on the B200 box with -m gpu)"))
+
+
+def _cuda_device_present():
+    try:
+        import torch
+        return bool(torch.cuda.is_available())
+    except Exception:
+        return os.path.exists("/dev/nvidia0")
+
+
 @pytest.fixture(scope="session")
 def gpu_ctx():
     import cascadeclassifier_b200 as ccb
-    return ccb.Context(0)
+    try:
+        return ccb.Context(0)
+    except ccb.CascadeCudaError as e:      # the library itself has no CPU fallback; only the TEST is skipped
+        pytest.skip("no CUDA device: %s" % e)

@@ -263,3 +263,38 @@ def test_gpu_stumps_match_cv2_boost(gpu_ctx):
         assert stage.train(ev, n, 1024, 1024, ccb.CvCascadeBoostParams(boostType=bt, maxFalseAlarm=1e-6, minHitRate=0.999999, maxWeakCount=8))
         k = assert_stumps_match(stage.trees, cv2_boost_stumps(X, labels, name, 8, 0.95), 3, check_quality=(name != "RAB"), what="gpu " + name)
         assert k >= 3
+
+
+@pytest.mark.parametrize("ftype,mode,bt", [(orc.HAAR, orc.ALL, orc.GAB), (orc.HAAR, orc.BASIC, orc.DAB), (orc.HAAR, orc.CORE, orc.RAB),
+                                           (orc.HAAR, orc.BASIC, orc.LB), (orc.LBP, 0, orc.GAB), (orc.LBP, 0, orc.RAB)])
+def test_stump_path_equals_general_path(gpu_ctx, ftype, mode, bt):
+    """cc_boost_set_tree_path: stumps grown with one host read per tree (speculative launches, tree assembled on the device) must be
+    the trees of the general node-by-node path, bit for bit -- trees, leaf values, threshold, (N, HR, FA) rows, final weights and mask."""
+    import ctypes as C
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200._lib import check
+    imgs, labels = make_samples(180, 320)
+    n = len(imgs)
+    ev = ccb.CvFeatureEvaluator.create(ftype, gpu_ctx)
+    fp = ccb.CvFeatureParams.create(ftype)
+    if ftype == orc.HAAR:
+        fp.mode = mode
+    ev.init(fp, n, (24, 24))
+    ev.setImages(imgs, labels)
+    params = ccb.CvCascadeBoostParams(boostType=bt, maxFalseAlarm=0.02, maxWeakCount=9)
+    runs = []
+    try:
+        for path in (1, 0):
+            check(gpu_ctx.lib.cc_boost_set_tree_path(gpu_ctx.h, path), "cc_boost_set_tree_path")
+            st = ccb.CvCascadeBoost()
+            assert st.train(ev, n, 1024, 1024, params)
+            w = np.zeros(n, np.float64)
+            m = np.zeros(n, np.uint8)
+            check(gpu_ctx.lib.cc_boost_get_weights(gpu_ctx.h, w.ctypes.data_as(C.c_void_p), m.ctypes.data_as(C.c_void_p)), "cc_boost_get_weights")
+            runs.append((st.trees, st.threshold, st.log, w, m))
+    finally:
+        check(gpu_ctx.lib.cc_boost_set_tree_path(gpu_ctx.h, 0), "cc_boost_set_tree_path")
+    a, b = runs
+    assert len(a[0]) >= 2
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])

@@ -353,3 +353,123 @@ def test_cascade_configuration_matrix(gpu_ctx, tmp_path, case):
         for k in ("pos_count", "pos_consumed", "neg_count", "neg_consumed"):
             assert g[k] == r[k], (k, g, r)
     assert _state_dict(cc._reader) == o.neg_state()
+
+
+def _mine_sequence(gpu_ctx, cc, bgs, plan, cache, first=200):
+    """(re)register `bgs`, then mine with growing cascade prefixes from a fresh reader: [(n_stages, count), ...]"""
+    import copy
+    from cascadeclassifier_b200 import _lib
+    from cascadeclassifier_b200._lib import check
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    check(lib.cc_mine_set_cache(h, cache, 0), "cc_mine_set_cache")
+    check(lib.cc_bg_clear(h), "cc_bg_clear")
+    for im in bgs:
+        im = np.ascontiguousarray(im)
+        check(lib.cc_bg_register(h, im.ctypes.data_as(C.c_void_p), im.shape[1], im.shape[0]), "cc_bg_register")
+    stats0 = np.zeros(6, np.int64)
+    check(lib.cc_mine_get_stats(h, stats0.ctypes.data_as(C.c_void_p)), "cc_mine_get_stats")
+    st = _lib.ReaderState()
+    all_stages = cc.stageClassifiers
+    out = []
+    for nst, count in plan:
+        cc.stageClassifiers = all_stages[:nst]
+        cc._sync_cascade()
+        consumed, got = C.c_int64(0), C.c_int32(0)
+        check(lib.cc_mine_negatives(h, first, count, 1e-9, C.byref(st), C.byref(consumed), C.byref(got)), "cc_mine_negatives")
+        out.append((got.value, consumed.value, _state_dict(st), cc.featureEvaluator.images(first, got.value).copy(),
+                    cc.featureEvaluator.integrals(first + got.value - 1)[0].copy()))
+    cc.stageClassifiers = all_stages
+    stats = np.zeros(6, np.int64)
+    check(lib.cc_mine_get_stats(h, stats.ctypes.data_as(C.c_void_p)), "cc_mine_get_stats")
+    return out, stats - stats0
+
+
+@pytest.mark.parametrize("ftype,mode", [(orc.HAAR, orc.ALL), (orc.LBP, 0)])
+def test_survivor_cache_is_transparent(gpu_ctx, tmp_path, ftype, mode):
+    """The survivor cache (cc_mine_set_cache) must not change a single bit of what mining produces: got, consumed, the reader
+    state after every call, the accepted pixels and their integrals -- over a stream that wraps the background list's round cycle
+    several times (short list of small images), with a cascade that grows between the calls (stale entries are brought up to
+    date by running only the new stages) and repeated calls with the same cascade (entries answer without any evaluation)."""
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import synth
+    from cascadeclassifier_b200._lib import check
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    pos, bgs = _data(300, 5, bw=230, bh=170)
+    cc = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
+    fp = ccb.CvFeatureParams.create(ftype)
+    if ftype == orc.HAAR:
+        fp.mode = mode
+    cc.train(str(tmp_path), "pos.vec", "bg.txt", 200, 300, 1024, 1024, 3, CvCascadeParams(0, ftype, (24, 24)), fp,
+             ccb.CvCascadeBoostParams(maxFalseAlarm=0.35), positives=pos, backgrounds=bgs)
+    assert len(cc.stageClassifiers) == 3
+    # 3 images x 576 round phases, a handful of windows per pyramid: one full cycle of distinct pyramids is a few thousand windows
+    small = [synth.make_background(44, 38, 301, clutter=2.0), synth.make_background(31, 52, 302, clutter=2.0),
+             synth.make_background(60, 27, 303, clutter=1.0)]
+    plan = [(1, 300), (2, 300), (2, 250), (3, 300), (3, 300), (3, 120)]
+    ref, s_off = _mine_sequence(gpu_ctx, cc, small, plan, cache=0)
+    got, s_on = _mine_sequence(gpu_ctx, cc, small, plan, cache=1)
+    check(gpu_ctx.lib.cc_mine_set_cache(gpu_ctx.h, 1, 0), "cc_mine_set_cache")
+    assert sum(r[1] for r in ref) > 3 * 576 * 3 * 4, [r[1] for r in ref]      # the stream really wrapped the cycle
+    for a, b in zip(ref, got):
+        assert a[0] == b[0] and a[1] == b[1], (a[:3], b[:3])
+        assert a[2] == b[2]
+        assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+    assert s_off[3] == 0 and s_off[2] == 0
+    assert s_on[0] == s_off[0]                       # same windows consumed
+    assert s_on[3] > 0 and s_on[2] > 0, s_on         # windows answered by the cache, survivors re-evaluated with newer stages
+    assert s_on[1] < s_off[1], (s_on, s_off)         # fewer windows evaluated from pyramid planes
+    # a larger list: cache on vs off over full-size-like pyramids that are never revisited must also agree (pure insert path)
+    ref2, _ = _mine_sequence(gpu_ctx, cc, bgs, [(3, 200)], cache=0)
+    got2, _ = _mine_sequence(gpu_ctx, cc, bgs, [(3, 200)], cache=1)
+    assert ref2[0][:3] == got2[0][:3] and np.array_equal(ref2[0][3], got2[0][3])
+
+
+def test_fused_builder_stress_full_hd(gpu_ctx, tmp_path):
+    """Race / determinism stress for the fused pyramid builder (k_lvl_build: cp.async staging ring, one barrier per level row):
+    > 10^8 windows of 1920x1080 backgrounds through mode 0, three passes, every pass must select exactly the same windows
+    (digest of the surviving scan ordinals) as the builder made of separate row / diagonal / column kernels (mode 1, no shared
+    staging, no intra-CTA pipeline) on the whole set and as the literal per-window path (mode 2: setImage + predict per slot)
+    and the fused tile miner (mode 3) on a subset.  compute-sanitizer is not available on the GPU pool
+    (profiles/r02_compute_sanitizer_closed.log), so this is the check that would have caught the round-1 prologue race."""
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import synth
+    from cascadeclassifier_b200._lib import check
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    pos, bgs = _data(300, 5, bw=230, bh=170)
+    cc = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
+    cc.train(str(tmp_path), "pos.vec", "bg.txt", 200, 300, 1024, 1024, 3, CvCascadeParams(0, orc.HAAR, (24, 24)),
+             ccb.CvHaarFeatureParams(orc.ALL), ccb.CvCascadeBoostParams(), positives=pos, backgrounds=bgs)
+    # a stage of tilted stumps so that the tilted plane of the builder is exercised as well
+    tilted = [fi for fi in range(0, cc.featureEvaluator.getNumFeatures(), 997) if cc.featureEvaluator.feature(fi)[2]][:2]
+    trees = [[dict(left=1, right=2, var_idx=fi, c=0.02 * k, value=0.0), dict(left=-1, right=-1, var_idx=-1, value=1.0),
+              dict(left=-1, right=-1, var_idx=-1, value=-1.0)] for k, fi in enumerate(tilted)]
+    cc.stageClassifiers.append(ccb.CvCascadeBoost.from_trees(-1.5, trees))
+    cc._sync_cascade()
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    check(lib.cc_bg_clear(h), "cc_bg_clear")
+    distinct = [np.ascontiguousarray(synth.make_background(1920, 1080, 8800 + i, clutter=1.0)) for i in range(6)]
+    NIMG = 2560                                   # 3.5e7 windows per pass
+    for i in range(NIMG):
+        b = distinct[i % len(distinct)]
+        check(lib.cc_bg_register(h, b.ctypes.data_as(C.c_void_p), b.shape[1], b.shape[0]), "cc_bg_register")
+
+    def scan(mode, nimg):
+        check(lib.cc_mine_set_mode(h, mode), "cc_mine_set_mode")
+        win, surv, dig = C.c_int64(0), C.c_int64(0), C.c_uint64(0)
+        check(lib.cc_mine_scan_digest(h, 0, nimg, C.byref(win), C.byref(surv), C.byref(dig)), "cc_mine_scan_digest")
+        return win.value, surv.value, dig.value
+    try:
+        fused = [scan(0, NIMG) for _ in range(3)]
+        assert fused[0][0] > NIMG * 13000 and 3 * fused[0][0] > 10 ** 8       # ~13.6e3 windows per 1920x1080 pyramid
+        assert fused[0][1] > 0
+        assert fused[0] == fused[1] == fused[2], fused
+        assert scan(1, NIMG) == fused[0]
+        sub = scan(0, 96)
+        assert scan(2, 96) == sub
+        assert scan(3, 96) == sub
+        # every registration of the same image must give the same survivors: the per-image survivor count is periodic
+        per = [scan(0, k)[1] for k in (6, 12)]
+        assert per[1] == 2 * per[0]
+    finally:
+        check(lib.cc_mine_set_mode(h, 0), "cc_mine_set_mode")
+        check(lib.cc_bg_clear(h), "cc_bg_clear")
