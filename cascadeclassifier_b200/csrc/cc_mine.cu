@@ -268,7 +268,7 @@ constexpr int LB_MAXDIM = LB_PPT * LB_MAX_THREADS - 1;  // lw + 1 <= 2048 plane 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS)
 k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order, uint8_t* __restrict__ pool, uint32_t* __restrict__ sum,
-            uint32_t* __restrict__ sq, uint32_t* __restrict__ tilted, int sp) {
+            uint32_t* __restrict__ sq, uint32_t* __restrict__ tilted, int sp, int winH) {
   constexpr int NW = THREADS / 32;
   // the two source rows of a level row, staged four level rows ahead with 16-byte cp.async copies: [y & 3][row][sp]
   extern __shared__ __align__(16) uint8_t s_src[];
@@ -294,7 +294,12 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
   for (int y = t; y < lh; y += THREADS) {
     int o, c0, c1, md;
     lin_coef(L.scale_y, L.row0 + y, sh, o, c0, c1, md);
-    s_yo[y] = o | (c1 << 16);
+    // The sqsum plane is only read by calcNormFactor's four corners (src/features.cpp:13-25): plane rows 1 and winH - 1 below a window's
+    // origin row.  Level row y produces plane row y + 1; bit 31 marks the rows some window needs -- the others are not stored
+    // (5 of 6 rows for 24-pixel windows at step 12), which takes a third off the builder's write traffic.
+    const int a = y - L.y0, b = y + 2 - winH - L.y0, sy = max(1, L.step_y);
+    const bool need = (a >= 0 && a % sy == 0 && a / sy < L.ny) || (b >= 0 && b % sy == 0 && b / sy < L.ny);
+    s_yo[y] = o | (c1 << 16) | (need ? (int)0x80000000u : 0);
   }
   s_bpix[0][t] = s_bpix[1][t] = 0; s_bd1[0][t] = s_bd1[1][t] = 0; s_bd2[0][t] = s_bd2[1][t] = 0;
   if (t == 0) { s_bd2[0][THREADS] = 0; s_bd2[1][THREADS] = 0; }
@@ -359,7 +364,7 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
     Srow += pitch; if (Q) Qrow += pitch; if (T) Trow += pitch;
     stage(y + 4);                                     // buffer y & 3 was consumed by fetch(y) before the previous barrier
     if (warp_on) {
-      const uint32_t cy1 = (uint32_t)(s_yo[y] >> 16), cy0 = 256u - cy1;
+      const uint32_t cy1 = ((uint32_t)s_yo[y] >> 16) & 0x7FFFu, cy0 = 256u - cy1;
 #pragma unroll
       for (int k = 0; k < LB_PPT; ++k) {
         const uint32_t c1 = cx1[k], c0 = cx0[k];
@@ -398,7 +403,7 @@ k_lvl_build(const LevelDesc* __restrict__ levels, const int* __restrict__ order,
       uint32_t e = w2 + i2 - tot2;
 #pragma unroll
       for (int k = 0; k < LB_PPT; ++k) { colQ[k] += e; e += v[k] * v[k]; }
-      *reinterpret_cast<uint4*>(Qrow) = make_uint4(colQ[0], colQ[1], colQ[2], colQ[3]);
+      if (s_yo[y] < 0) *reinterpret_cast<uint4*>(Qrow) = make_uint4(colQ[0], colQ[1], colQ[2], colQ[3]);
     }
     if (T) {
       // apex pixels of the plane columns 4t..4t+3 are x = 4t-1 .. 4t+2; D1(y,x) = I + D1(y-1,x-1), D2(y,x) = I + D2(y-1,x+1)
@@ -1510,9 +1515,9 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
         CC_CUDA(cudaFuncSetAttribute(k_lvl_build<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         CC_CUDA(cudaFuncSetAttribute(k_lvl_build<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
       }
-      if (off[3] > off[2]) { k_lvl_build<512><<<off[3] - off[2], 512, ssm, ctx->stream>>>(d_levels, m->d_order + off[2], pool, m->d_psum, psq, ptl, src_pitch_max); ++launches; }
-      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, ssm, ctx->stream>>>(d_levels, m->d_order + off[1], pool, m->d_psum, psq, ptl, src_pitch_max); ++launches; }
-      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, ssm, ctx->stream>>>(d_levels, m->d_order + off[0], pool, m->d_psum, psq, ptl, src_pitch_max); ++launches; }
+      if (off[3] > off[2]) { k_lvl_build<512><<<off[3] - off[2], 512, ssm, ctx->stream>>>(d_levels, m->d_order + off[2], pool, m->d_psum, psq, ptl, src_pitch_max, ctx->H); ++launches; }
+      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, ssm, ctx->stream>>>(d_levels, m->d_order + off[1], pool, m->d_psum, psq, ptl, src_pitch_max, ctx->H); ++launches; }
+      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, ssm, ctx->stream>>>(d_levels, m->d_order + off[0], pool, m->d_psum, psq, ptl, src_pitch_max, ctx->H); ++launches; }
     } else {
       k_resize_levels<<<grid_for(ctx, (long long)pool_px, 256), 256, 0, ctx->stream>>>(d_levels, nlv, (long long)pool_px, m->d_pool);
       k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);

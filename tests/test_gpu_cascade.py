@@ -399,28 +399,30 @@ def test_survivor_cache_is_transparent(gpu_ctx, tmp_path, ftype, mode):
     fp = ccb.CvFeatureParams.create(ftype)
     if ftype == orc.HAAR:
         fp.mode = mode
-    cc.train(str(tmp_path), "pos.vec", "bg.txt", 200, 300, 1024, 1024, 3, CvCascadeParams(0, ftype, (24, 24)), fp,
-             ccb.CvCascadeBoostParams(maxFalseAlarm=0.35), positives=pos, backgrounds=bgs)
-    assert len(cc.stageClassifiers) == 3
-    # 3 images x 576 round phases, a handful of windows per pyramid: one full cycle of distinct pyramids is a few thousand windows
+    cc.train(str(tmp_path), "pos.vec", "bg.txt", 200, 300, 1024, 1024, 4, CvCascadeParams(0, ftype, (24, 24)), fp,
+             ccb.CvCascadeBoostParams(), positives=pos, backgrounds=bgs)
+    ns = len(cc.stageClassifiers)
+    assert ns >= 2
+    # three tiny images: a pyramid is one to a few windows, the round offsets are clamped to a few dozen distinct values per
+    # image -> the stream returns to the same (image, offsets) pyramid again and again, within a call and across calls
     small = [synth.make_background(44, 38, 301, clutter=2.0), synth.make_background(31, 52, 302, clutter=2.0),
-             synth.make_background(60, 27, 303, clutter=1.0)]
-    plan = [(1, 300), (2, 300), (2, 250), (3, 300), (3, 300), (3, 120)]
+             synth.make_background(30, 28, 303, clutter=1.0)]
+    plan = [(1, 300)] * 2 + [(2, 300)] * 3 + [(min(3, ns), 300)] * 4 + [(ns, 300)] * 4 + [(ns, 77)]
     ref, s_off = _mine_sequence(gpu_ctx, cc, small, plan, cache=0)
     got, s_on = _mine_sequence(gpu_ctx, cc, small, plan, cache=1)
     check(gpu_ctx.lib.cc_mine_set_cache(gpu_ctx.h, 1, 0), "cc_mine_set_cache")
-    assert sum(r[1] for r in ref) > 3 * 576 * 3 * 4, [r[1] for r in ref]      # the stream really wrapped the cycle
     for a, b in zip(ref, got):
         assert a[0] == b[0] and a[1] == b[1], (a[:3], b[:3])
         assert a[2] == b[2]
         assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
     assert s_off[3] == 0 and s_off[2] == 0
-    assert s_on[0] == s_off[0]                       # same windows consumed
-    assert s_on[3] > 0 and s_on[2] > 0, s_on         # windows answered by the cache, survivors re-evaluated with newer stages
+    assert s_on[0] == s_off[0] > 3000                # same windows consumed
+    assert s_on[3] > s_on[0] // 4, s_on              # a good part of the stream was answered by the cache ...
+    assert s_on[2] > 0, s_on                         # ... and stale entries were brought up to date with the newer stages
     assert s_on[1] < s_off[1], (s_on, s_off)         # fewer windows evaluated from pyramid planes
     # a larger list: cache on vs off over full-size-like pyramids that are never revisited must also agree (pure insert path)
-    ref2, _ = _mine_sequence(gpu_ctx, cc, bgs, [(3, 200)], cache=0)
-    got2, _ = _mine_sequence(gpu_ctx, cc, bgs, [(3, 200)], cache=1)
+    ref2, _ = _mine_sequence(gpu_ctx, cc, bgs, [(ns, 200)], cache=0)
+    got2, _ = _mine_sequence(gpu_ctx, cc, bgs, [(ns, 200)], cache=1)
     assert ref2[0][:3] == got2[0][:3] and np.array_equal(ref2[0][3], got2[0][3])
 
 
