@@ -40,7 +40,7 @@ bool CvCudaCascadeBoost::train(const CvFeatureEvaluator* featureEvaluator, int n
   }
   threshold = st.threshold;
   for (int t = 0; t < st.num_weak; ++t) {
-    auto* tree = new CvCascadeBoostTree();
+    auto* tree = new CvCudaCascadeBoostTree();
     buildTree(trees[t], tree);
     cvSeqPush(weak, &tree);
   }
@@ -49,7 +49,7 @@ bool CvCudaCascadeBoost::train(const CvFeatureEvaluator* featureEvaluator, int n
   return false;
 }
 
-void CvCudaCascadeBoost::buildTree(const cc_tree& t, CvCascadeBoostTree* tree) {
+void CvCudaCascadeBoost::buildTree(const cc_tree& t, CvCudaCascadeBoostTree* tree) {
   const int maxCat = (dynamic_cast<CvCascadeBoostTrainData*>(data))->featureEvaluator->getMaxCatCount();
   const int subsetN = (maxCat + 31) / 32;
   std::vector<CvDTreeNode*> nodes(t.num_nodes, nullptr);
@@ -66,5 +66,5 @@ void CvCudaCascadeBoost::buildTree(const cc_tree& t, CvCascadeBoostTree* tree) {
       nodes[i]->right = nodes[n.right]; nodes[n.right]->parent = nodes[i];
     }
   }
-  tree->setRoot(nodes[0], data, this);   // one-line accessor added to CvCascadeBoostTree: root = r; data = d; ensemble = e;
+  tree->adopt(nodes[0], data, this);
 }

@@ -81,6 +81,7 @@ def _signatures():
         "cc_boost_get_fval": (i32, [vp, i32, i32, vp]),
         "cc_boost_get_sorted_idx": (i32, [vp, i32, i32, vp]),
         "cc_boost_get_sorted_val": (i32, [vp, i32, i32, vp]),
+        "cc_boost_get_sorted_idx32": (i32, [vp, i32, i32, vp]),
         "cc_boost_train": (i32, [vp, i32, P(BoostParams), P(Stage)]),
         "cc_boost_get_weights": (i32, [vp, vp, vp]),
         "cc_boost_get_row_quality": (i32, [vp, i32, i32, vp]),

@@ -594,6 +594,103 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Ordered split search, wide path (numSamples beyond the shared-memory kernels above; 32-bit sorted-index rows): one warp per
+// row, 32 sorted positions per step, per-sample operands and feature values gathered from global memory (operands: L1 / L2
+// resident, N * 8 bytes; values: fval[row][index]).  Same arithmetic and same selection as ss_tile<EXACT>: operand 0 = not in
+// the node, a split between consecutive node samples p < j is admissible iff v[p] + 2 * FLT_EPSILON < v[j], candidates are
+// compared as exact fractions, first maximum wins.  Every row is searched exactly (no pruning pass).
+// ------------------------------------------------------------------------------------------------
+constexpr int SW_THREADS = 256;
+template <int CRIT, bool HAS_Y>
+__global__ void __launch_bounds__(SW_THREADS)
+k_split_search_ord_wide(const uint32_t* __restrict__ sidx32, const float* __restrict__ fval, int n_stride, int N, int nrows,
+                        const double* __restrict__ wnode, const float* __restrict__ ynode, const NodeStats* __restrict__ stats,
+                        RowBest* __restrict__ out) {
+  const NodeStats st = *stats;
+  const double totA = st.rcw[0];
+  const double totB = (CRIT == CRIT_SQERR) ? st.rsum0 : st.rcw[1];
+  const int lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const float eps = FLT_EPSILON * 2;
+  const int nwarps = (gridDim.x * SW_THREADS) >> 5;
+  for (int row = (blockIdx.x * SW_THREADS + threadIdx.x) >> 5; row < nrows; row += nwarps) {
+    const uint32_t* ri = sidx32 + (size_t)row * n_stride;
+    const float* fv = fval + (size_t)row * n_stride;
+    double carryA = 0, carryB = 0;
+    float carryV = 0.f;
+    bool carryHas = false;
+    int carryCnt = 0;
+    double bestNum = -1.0, bestDen = 1.0;
+    int bestPos = -1;
+    float bestVl = 0.f, bestVr = 0.f;
+    for (int base = 0; base < N; base += 32) {
+      const int p = base + lane;
+      double w = 0.0;
+      float v = 0.f, y = 0.f;
+      if (p < N) {
+        const uint32_t idx = ri[p];
+        w = __ldg(wnode + idx);
+        if (w != 0.0) { v = __ldg(fv + idx); if (HAS_Y) y = __ldg(ynode + idx); }
+      }
+      const bool on = w != 0.0;
+      double a, b;
+      if (CRIT == CRIT_SQERR) {
+        if (HAS_Y) { a = w; b = (double)y * w; } else { a = fabs(w); b = w; }
+      } else { a = w < 0.0 ? -w : 0.0; b = w > 0.0 ? w : 0.0; }
+      double ia = a, ib = b;
+      int ic = on ? 1 : 0;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const double xa = __shfl_up_sync(0xffffffffu, ia, d), xb = __shfl_up_sync(0xffffffffu, ib, d);
+        const int xc = __shfl_up_sync(0xffffffffu, ic, d);
+        if (lane >= d) { ia += xa; ib += xb; ic += xc; }
+      }
+      const double pa = carryA + (ia - a), pb = carryB + (ib - b);          // sums over the node samples before this one
+      const int pc = carryCnt + (ic - (on ? 1 : 0));
+      const uint32_t onmask = __ballot_sync(0xffffffffu, on);
+      const uint32_t before = onmask & lt_mask;
+      const int src = before ? (31 - __clz(before)) : 0;
+      const float pv_other = __shfl_sync(0xffffffffu, v, src);
+      const float pv = before ? pv_other : carryV;
+      const bool pHas = before ? true : carryHas;
+      if (on && pHas && __fadd_rn(pv, eps) < v) {
+        double num, den;
+        if (criterion_frac<CRIT>(pa, pb, totA, totB, num, den) && num * bestDen > bestNum * den) {
+          bestNum = num; bestDen = den; bestPos = pc - 1; bestVl = pv; bestVr = v;
+        }
+      }
+      carryA += __shfl_sync(0xffffffffu, ia, 31);
+      carryB += __shfl_sync(0xffffffffu, ib, 31);
+      carryCnt += __shfl_sync(0xffffffffu, ic, 31);
+      if (onmask) {
+        const int lastl = 31 - __clz(onmask);
+        carryV = __shfl_sync(0xffffffffu, v, lastl);
+        carryHas = true;
+      }
+    }
+    double bestVal = bestPos >= 0 ? bestNum / bestDen : -1.0;
+    int owner = lane;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bestVal, d);
+      const int op = __shfl_xor_sync(0xffffffffu, bestPos, d);
+      const int oo = __shfl_xor_sync(0xffffffffu, owner, d);
+      const bool take = op >= 0 && (bestPos < 0 || ov > bestVal || (ov == bestVal && op < bestPos));
+      if (take) { bestVal = ov; bestPos = op; owner = oo; }
+    }
+    const float vl = __shfl_sync(0xffffffffu, bestVl, owner), vr = __shfl_sync(0xffffffffu, bestVr, owner);
+    if (lane == 0) {
+      RowBest rb;
+      rb.q = bestPos >= 0 ? (float)bestVal : -1.f;
+      rb.c = __fmul_rn(__fadd_rn(vl, vr), 0.5f);
+      rb.vleft = vl;
+      rb.pos = bestPos;
+      out[row] = rb;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pruning pass of the ordered split search (all criteria over two class weights: GAB squared error with
 // +-1 targets, Gini, misclassification).
 //
@@ -714,16 +811,21 @@ constexpr int CAT_THREADS_MAX = 1024;      // the launch picks as many warps as 
 
 __global__ void __launch_bounds__(CAT_THREADS_MAX, 1)
 k_split_search_cat(const uint8_t* __restrict__ codes, int n_stride, int N, int nrows, const double* __restrict__ wnode,
-                   const float* __restrict__ ynode, int is_classifier, int crit, int has_y, RowBestCat* __restrict__ out) {
+                   const float* __restrict__ ynode, int is_classifier, int crit, int has_y, int ops_global, RowBestCat* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int CAT_THREADS = blockDim.x, CAT_WARPS = blockDim.x >> 5;
-  double* sw = reinterpret_cast<double*>(smem_raw);                   // [N]
-  float* sy = reinterpret_cast<float*>(sw + N);                        // [N] (LogitBoost only)
-  double* bins = reinterpret_cast<double*>(sy + (has_y ? ((N + 1) & ~1) : 0));   // [CAT_WARPS][3][256]: s0, s1, key
+  // per-sample operands: staged in shared memory, or -- when numSamples is too large for that -- read from global memory
+  // (they are read linearly, one coalesced line per 32 samples, and stay in L1 / L2 across the rows of a CTA)
+  const int NS = ops_global ? 0 : N;
+  double* sw_s = reinterpret_cast<double*>(smem_raw);                 // [NS]
+  float* sy_s = reinterpret_cast<float*>(sw_s + NS);                   // [NS] (LogitBoost only)
+  double* bins = reinterpret_cast<double*>(sy_s + (has_y ? ((NS + 1) & ~1) : 0));   // [CAT_WARPS][3][256]: s0, s1, key
+  const double* sw = ops_global ? wnode : sw_s;
+  const float* sy = ops_global ? ynode : sy_s;
   int* order_all = reinterpret_cast<int*>(bins + CAT_WARPS * 3 * 256); // [CAT_WARPS][256]
   double* steps_all = reinterpret_cast<double*>(order_all + CAT_WARPS * 256);   // [CAT_WARPS][6][32]
   double* s_ikey_all = steps_all + CAT_WARPS * 6 * 32;                          // [CAT_WARPS][256] u64
-  for (int i = threadIdx.x; i < N; i += CAT_THREADS) { sw[i] = wnode[i]; if (has_y) sy[i] = ynode[i]; }
+  for (int i = threadIdx.x; i < NS; i += CAT_THREADS) { sw_s[i] = wnode[i]; if (has_y) sy_s[i] = ynode[i]; }
   __syncthreads();
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   double* s0 = bins + warp * 3 * 256;     // regression: sum of y*w ; classification: class-0 weight
@@ -1210,18 +1312,33 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
   ScopedTimer tm(ctx, "split_search", 2);
   if (ctx->ftype == CC_FEATURE_LBP) {
     const bool cat_has_y = b->boost_type == CC_BOOST_LOGIT;
-    const size_t smem_fixed = (size_t)N * 8 + (cat_has_y ? (size_t)((N + 1) & ~1) * 4 : 0);
+    size_t smem_fixed = (size_t)N * 8 + (cat_has_y ? (size_t)((N + 1) & ~1) * 4 : 0);
     const size_t smem_warp = (size_t)3 * 256 * 8 + 256 * 4 + (size_t)6 * 32 * 8 + (size_t)256 * 8;
-    CC_REQUIRE(smem_fixed + 2 * smem_warp <= 227 * 1024, CC_ERR_UNSUPPORTED, "split search: numSamples %d needs %zu B of shared memory (limit 227 KB)", N, smem_fixed + 2 * smem_warp);
+    // operands in shared memory as long as at least 8 warps still fit next to them; beyond that (numSamples > ~17000) they are
+    // read from global memory
+    const int ops_global = (smem_fixed + 8 * smem_warp > 227 * 1024 || b->search_mode == 2) ? 1 : 0;
+    if (ops_global) smem_fixed = 0;
     const int CAT_WARPS = (int)std::min<size_t>(CAT_THREADS_MAX / 32, (227 * 1024 - smem_fixed) / smem_warp);
     const int CAT_THREADS = CAT_WARPS * 32;
     const size_t smem = smem_fixed + CAT_WARPS * smem_warp;
     CC_CUDA(cudaFuncSetAttribute(k_split_search_cat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int blocks = std::min((ctx->nrows + CAT_WARPS - 1) / CAT_WARPS, ctx->sm_count);
     k_split_search_cat<<<blocks, CAT_THREADS, smem, ctx->stream>>>(ctx->d_fcode, ctx->n_stride, N, ctx->nrows, b->wnode, b->ynode,
-                                                                   b->is_classifier, b->crit, b->boost_type == CC_BOOST_LOGIT, b->rowbest_cat);
+                                                                   b->is_classifier, b->crit, b->boost_type == CC_BOOST_LOGIT, ops_global, b->rowbest_cat);
     CC_CUDA(cudaGetLastError());
     k_argmax_rows<<<1, ONE_CTA, 0, ctx->stream>>>(nullptr, b->rowbest_cat, ctx->nrows, ctx->row0, b->d_best);
+  } else if (ctx->wide) {
+    const bool has_y = b->boost_type == CC_BOOST_LOGIT;
+    const int blocks = std::min((ctx->nrows + SW_THREADS / 32 - 1) / (SW_THREADS / 32), ctx->sm_count * 8);
+#define LAUNCH_SW(CR, HY) k_split_search_ord_wide<CR, HY><<<blocks, SW_THREADS, 0, ctx->stream>>>(ctx->d_sidx32, ctx->d_fval, ctx->n_stride, N, ctx->nrows, \
+                                                                                                  b->wnode, b->ynode, b->d_stats + nid, b->rowbest);
+    if (b->crit == CRIT_SQERR) { if (has_y) LAUNCH_SW(CRIT_SQERR, true) else LAUNCH_SW(CRIT_SQERR, false) }
+    else if (b->crit == CRIT_GINI) LAUNCH_SW(CRIT_GINI, false)
+    else LAUNCH_SW(CRIT_MISCLASS, false)
+#undef LAUNCH_SW
+    CC_CUDA(cudaGetLastError());
+    k_argmax_rows<<<1, ONE_CTA, 0, ctx->stream>>>(b->rowbest, nullptr, ctx->nrows, ctx->row0, b->d_best);
+    b->row_quality_valid = true;
   } else {
     const bool has_y = b->boost_type == CC_BOOST_LOGIT;
     const int ntile = (N + SS_TILE - 1) / SS_TILE;
@@ -1522,9 +1639,11 @@ int cc_boost_get_weights(cc_ctx* ctx, double* weights, uint8_t* mask) {
 }
 
 int cc_boost_set_search_mode(cc_ctx* ctx, int mode) {
-  CC_REQUIRE(ctx && (mode == 0 || mode == 1), CC_ERR_BAD_ARG, "cc_boost_set_search_mode: mode must be 0 (pruned) or 1 (exhaustive)");
+  CC_REQUIRE(ctx && mode >= 0 && mode <= 2, CC_ERR_BAD_ARG, "cc_boost_set_search_mode: mode must be 0 (pruned), 1 (exhaustive) or 2 (wide kernels)");
   if (!ctx->boost) ctx->boost = new BoostBuffers();
   ctx->boost->search_mode = mode;
+  if ((mode == 2) != (ctx->force_wide != 0)) ctx->precalc_valid = false;      // the sorted rows have another layout on the wide path
+  ctx->force_wide = mode == 2 ? 1 : 0;
   return CC_OK;
 }
 

@@ -164,6 +164,10 @@ struct cc_ctx {
   uint8_t* d_fcode = nullptr;      // [nrows][n_stride] (LBP)
   uint16_t* d_sidx = nullptr;      // [nrows][n_stride]
   float* d_sval = nullptr;         // [nrows][n_stride] values in sorted order
+  uint32_t* d_sidx32 = nullptr;    // wide path (numSamples beyond what one CTA sorts in shared memory): 32-bit sorted-index rows, no d_sidx / d_sval
+  bool wide = false;               // the current stage uses the wide path
+  bool cap_wide = false;           // what the buffers were allocated for
+  int force_wide = 0;              // cc_boost_set_search_mode(ctx, 2): wide kernels regardless of numSamples (tests)
   int* d_hard_rows = nullptr;      // [1 + nrows]: count, then the rows the bucket sort deferred to the radix kernel
   int sort_mode = 0;               // cc_boost_set_sort_mode
   size_t cap_rows = 0, cap_stride = 0;

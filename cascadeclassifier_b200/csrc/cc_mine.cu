@@ -1040,8 +1040,17 @@ struct NegStream {
   int stepY() const { return (int)(stepFactor * H); }
   bool canStepX(int x) const { return (int)(x + (1.0F + stepFactor) * W) < lw; }
   bool canStepY(int y) const { return (int)(y + (1.0F + stepFactor) * H) < lh; }
-  int countX() const { int n = 1, x = offX; while (canStepX(x)) { x += stepX(); ++n; } return n; }
-  int countY() const { int n = 1, y = offY; while (canStepY(y)) { y += stepY(); ++n; } return n; }
+  // windows per level row / column: 1 + the number of steps NegReader::get takes before canStep fails.  (int)(x + 1.5f * W) ==
+  // x + (int)(1.5f * W) for the non-negative integers x that occur (1.5f * W is a multiple of 0.5, everything is exact in f32),
+  // so the loop `while (canStepX(x)) x += stepX()` has a closed form; steps of 0 pixels (W == 1) never advance in the reference
+  // either and are treated as a single position.
+  static int count1(int off, int step, int reach, int len) {
+    if (step <= 0) return 1;
+    const int room = len - reach - off - 1;          // largest x - off (x = position before a step) that still may step
+    return room < 0 ? 1 : 2 + room / step;
+  }
+  int countX() const { return count1(offX, stepX(), (int)((1.0F + stepFactor) * W), lw); }
+  int countY() const { return count1(offY, stepY(), (int)((1.0F + stepFactor) * H), lh); }
   // after the last window of the current level: next level of the same image or the next image
   bool nextLevel() {
     pointX = offX; pointY = offY;
@@ -1232,7 +1241,7 @@ static int accept_windows(cc_ctx* ctx, MineState* m, const unsigned* which, int 
 // "evaluation ordinal") interleaved with whole pyramids answered from the survivor cache (`pyrs`).  `segs` lists both kinds in
 // stream order with their batch-relative stream ordinals.
 struct CachedPyr {
-  NegStream start, after;           // stream state on the pyramid's first window / right behind its last one
+  NegStream start;                  // stream state on the pyramid's first window (right behind its last one: start.nextImg())
   long long base = 0, nwin = 0;     // stream ordinals [base, base + nwin)
   uint64_t key = 0;
   size_t cand0 = 0, ncand = 0;      // its cached survivors in Batch::cand
@@ -1965,6 +1974,10 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     want = std::min(want, 4.0e12);
     NegStream cur = from;
     more = true;
+    if (cache_on && !m->cache.map.empty()) {
+      const size_t guess = (size_t)std::min<double>((double)SEG_CAP, want / 8000.0 + 64);
+      bt.pyrs.reserve(guess); bt.segs.reserve(guess);
+    }
     int open_pyr = -1;                  // bt.miss entry of the pyramid being assembled from its first window
     while ((double)bt.nwin < want && bt.neval < max_batch && more && (long long)bt.cand_eval.size() < CAND_CAP && bt.segs.size() < SEG_CAP) {
       if (cache_on && ((cur.fresh && cur.pointX == cur.offX && cur.pointY == cur.offY) || cur.is_pyramid_start())) {
@@ -1979,13 +1992,10 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
             bt.cand.push_back(cp.base + (long long)o);
             bt.cand_fs.push_back((uint8_t)std::min(e.n_stages, 255));
           }
-          NegStream nxt = cur;
-          more = nxt.nextImg();
-          cp.after = nxt;
           bt.segs.push_back(Seg{cp.base, cp.nwin, 1, (int)bt.pyrs.size()});
           bt.pyrs.push_back(cp);
           bt.nwin += cp.nwin;
-          cur = nxt;
+          more = cur.nextImg();
           open_pyr = -1;
           continue;
         }
@@ -2027,9 +2037,12 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       if (L.w_count < avail) break;
     }
   };
-  auto batch_end_state = [&](const Batch& bt) -> const NegStream& {
+  auto batch_end_state = [&](const Batch& bt) -> NegStream {
     const Seg& sg = bt.segs.back();
-    return sg.kind == 0 ? bt.after[sg.idx] : bt.pyrs[sg.idx].after;
+    if (sg.kind == 0) return bt.after[sg.idx];
+    NegStream a = bt.pyrs[sg.idx].start;
+    a.nextImg();
+    return a;
   };
   // asynchronous half of a plane-path batch: pyramid planes + cascade for the level parts, per-window path for the cached survivors
   auto launch_batch = [&](Batch& bt, int slot) -> int {
@@ -2161,8 +2174,9 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
         const CachedPyr& cp = bt.pyrs[sg.idx];
         const long long k = stop_after - cp.base + 1;                      // windows of the pyramid consumed
         if (k >= cp.nwin) {
-          ns = cp.after;
-          if (si + 1 == bt.segs.size()) stream_ok = more;
+          ns = cp.start;
+          const bool has_next = ns.nextImg();
+          if (si + 1 == bt.segs.size()) stream_ok = more; else (void)has_next;
         } else {
           NegStream st = cp.start;
           long long lb = 0, ln = (long long)st.countX() * st.countY();

@@ -809,6 +809,76 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// K3, wide path: rows longer than one CTA can hold in shared memory (numSamples > 15360, including the reference's
+// is_buf_16u == false case numSamples >= 65536).  Stable LSD radix sort, 4 passes of 8 bits, one CTA per row, keys and
+// indices ping-pong between two global scratch rows per CTA (L2-resident).  A pass = digit histogram, exclusive scan, then a
+// stable scatter chunk by chunk in position order: inside a chunk of 1024 positions a thread's rank among the equal digits
+// is (equal digits in earlier warps) + (equal digits in earlier lanes of its warp, by __match_any_sync).  Ties therefore come out
+// in ascending sample index, the canonical order of the other sort kernels.  Output: 32-bit sorted-index rows.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SORT_THREADS, 1)
+k_sort_rows_wide(const float* __restrict__ fval, int n_stride, int N, int nrows, uint32_t* __restrict__ sidx32, uint32_t* __restrict__ scratch) {
+  __shared__ uint32_t s_base[256];                 // running first free slot per digit
+  __shared__ uint32_t s_wcnt[SORT_WARPS][256];     // per chunk: equal digits per warp -> exclusive offsets over the warps
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const size_t npad = (size_t)n_stride;
+  uint32_t* kbuf[2] = {scratch + (size_t)blockIdx.x * 4 * npad, scratch + (size_t)blockIdx.x * 4 * npad + npad};
+  uint32_t* ibuf[2] = {scratch + (size_t)blockIdx.x * 4 * npad + 2 * npad, scratch + (size_t)blockIdx.x * 4 * npad + 3 * npad};
+  for (int row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const float* src = fval + (size_t)row * n_stride;
+    for (int i = t; i < N; i += SORT_THREADS) { kbuf[0][i] = float_to_key(src[i]); ibuf[0][i] = (uint32_t)i; }
+    __syncthreads();
+    for (int pass = 0; pass < 4; ++pass) {
+      const uint32_t* kin = kbuf[pass & 1];
+      const uint32_t* iin = ibuf[pass & 1];
+      uint32_t* kout = kbuf[(pass & 1) ^ 1];
+      uint32_t* iout = ibuf[(pass & 1) ^ 1];
+      const int shift = 8 * pass;
+      if (t < 256) s_base[t] = 0;
+      __syncthreads();
+      for (int i = t; i < N; i += SORT_THREADS) atomicAdd(&s_base[(kin[i] >> shift) & 255u], 1u);
+      __syncthreads();
+      if (warp == 0) {                               // exclusive scan of the 256 counters
+        uint32_t c[8], sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { c[k] = s_base[lane * 8 + k]; sum += c[k]; }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += x; }
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s_base[lane * 8 + k] = run; run += c[k]; }
+      }
+      __syncthreads();
+      for (int c0 = 0; c0 < N; c0 += SORT_THREADS) {
+        for (int i = t; i < SORT_WARPS * 256; i += SORT_THREADS) (&s_wcnt[0][0])[i] = 0;
+        __syncthreads();
+        const int i = c0 + t;
+        const bool on = i < N;
+        const uint32_t key = on ? kin[i] : 0u, id = on ? iin[i] : 0u;
+        const uint32_t d = on ? ((key >> shift) & 255u) : 256u;          // 256: not a digit, matches only other idle lanes
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const uint32_t rank_in_warp = __popc(peers & ((1u << lane) - 1u));
+        if (on && rank_in_warp == 0) s_wcnt[warp][d] = __popc(peers);
+        __syncthreads();
+        if (t < 256) {                                 // exclusive offsets over the warps, and the digit's base moves on
+          uint32_t run = s_base[t];
+          for (int w = 0; w < SORT_WARPS; ++w) { const uint32_t c = s_wcnt[w][t]; s_wcnt[w][t] = run; run += c; }
+          s_base[t] = run;
+        }
+        __syncthreads();
+        if (on) { const uint32_t p = s_wcnt[warp][d] + rank_in_warp; kout[p] = key; iout[p] = id; }
+        __syncthreads();
+      }
+    }
+    // 4 passes: the result is back in buffer 0
+    uint32_t* drow = sidx32 + (size_t)row * n_stride;
+    for (int i = t; i < n_stride; i += SORT_THREADS) drow[i] = i < N ? ibuf[0][i] : (uint32_t)N;
+    __syncthreads();
+  }
+}
+
 __global__ void k_div_check(int steps, unsigned long long seed, long long n, unsigned long long* mismatches) {
   unsigned long long bad = 0;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -840,19 +910,25 @@ __global__ void k_codes_to_float(const uint8_t* __restrict__ codes, int n_stride
 }
 
 int traindata_free(cc_ctx* ctx) {
-  cudaFree(ctx->d_fval); cudaFree(ctx->d_fcode); cudaFree(ctx->d_sidx); cudaFree(ctx->d_sval); cudaFree(ctx->d_hard_rows);
-  ctx->d_fval = nullptr; ctx->d_fcode = nullptr; ctx->d_sidx = nullptr; ctx->d_sval = nullptr; ctx->d_hard_rows = nullptr;
+  cudaFree(ctx->d_fval); cudaFree(ctx->d_fcode); cudaFree(ctx->d_sidx); cudaFree(ctx->d_sval); cudaFree(ctx->d_hard_rows); cudaFree(ctx->d_sidx32);
+  ctx->d_fval = nullptr; ctx->d_fcode = nullptr; ctx->d_sidx = nullptr; ctx->d_sval = nullptr; ctx->d_hard_rows = nullptr; ctx->d_sidx32 = nullptr;
   ctx->cap_rows = ctx->cap_stride = 0;
   ctx->precalc_valid = false;
   return CC_OK;
 }
 
-static int ensure_traindata(cc_ctx* ctx, int nrows, int n_stride) {
-  if ((size_t)nrows <= ctx->cap_rows && (size_t)n_stride <= ctx->cap_stride) return CC_OK;
+static int ensure_traindata(cc_ctx* ctx, int nrows, int n_stride, bool wide) {
+  if ((size_t)nrows <= ctx->cap_rows && (size_t)n_stride <= ctx->cap_stride && wide == ctx->cap_wide) return CC_OK;
   traindata_free(ctx);
   const size_t cells = (size_t)nrows * n_stride;
+  ctx->cap_wide = wide;
   if (ctx->ftype == CC_FEATURE_LBP) {
     CC_CUDA(cudaMalloc(&ctx->d_fcode, cells));
+  } else if (wide) {
+    // CvCascadeBoostTrainData::setData with is_buf_16u == false (src/o_cvcascadeboosttraindata.cpp:250-251,283-309): 32-bit index
+    // rows.  Sorted values are not kept: the wide search gathers them from the fval row
+    CC_CUDA(cudaMalloc(&ctx->d_fval, cells * sizeof(float)));
+    CC_CUDA(cudaMalloc(&ctx->d_sidx32, cells * sizeof(uint32_t)));
   } else {
     CC_CUDA(cudaMalloc(&ctx->d_fval, cells * sizeof(float)));
     CC_CUDA(cudaMalloc(&ctx->d_sidx, cells * sizeof(uint16_t)));
@@ -995,11 +1071,13 @@ int cc_boost_set_shard(cc_ctx* ctx, int rank, int world) {
 int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
   CC_REQUIRE(ctx && ctx->ftype >= 0, CC_ERR_STATE, "cc_boost_precalc: evaluator not initialised");
   CC_REQUIRE(num_samples > 0 && num_samples <= ctx->max_samples, CC_ERR_BAD_ARG, "cc_boost_precalc: numSamples %d not in (0, %d]", num_samples, ctx->max_samples);
-  CC_REQUIRE(num_samples < 65536, CC_ERR_UNSUPPORTED, "cc_boost_precalc: numSamples %d >= 65536 needs 32-bit sorted indices (is_buf_16u == false), not implemented", num_samples);
   CC_CUDA(cudaSetDevice(ctx->device));
   const int N = num_samples;
   const int n_stride = (N + 255) & ~255;   // rows padded to the split-search tile (256 elements)
-  CC_CHECK(ensure_traindata(ctx, ctx->nrows, n_stride));
+  // ordered variables: rows of more than SORT_CAP samples (and cc_boost_set_search_mode(ctx, 2)) take the wide path
+  const bool wide = ctx->ftype != CC_FEATURE_LBP && (N > SORT_CAP || ctx->force_wide);
+  CC_CHECK(ensure_traindata(ctx, ctx->nrows, n_stride, wide));
+  ctx->wide = wide;
   ctx->N = N; ctx->n_stride = n_stride;
   const int ntiles_used = (N + TILE - 1) / TILE;
   const int P = ctx->P;
@@ -1089,8 +1167,15 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
     CC_CUDA(cudaGetLastError());
   }
 
-  if (ctx->ftype != CC_FEATURE_LBP) {   // categorical variables are not sorted (numPrecalcIdx = 0, :267-273)
-    CC_REQUIRE(N <= SORT_CAP, CC_ERR_UNSUPPORTED, "sort: numSamples %d exceeds the %d samples one CTA sorts in shared memory", N, SORT_CAP);
+  if (wide) {
+    ScopedTimer tm(ctx, "sort", 1);
+    const int blocks = std::min(ctx->nrows, ctx->sm_count * 2);
+    uint32_t* scratch = nullptr;
+    CC_CUDA(cudaMallocAsync(&scratch, (size_t)blocks * 4 * n_stride * sizeof(uint32_t), ctx->stream));
+    k_sort_rows_wide<<<blocks, SORT_THREADS, 0, ctx->stream>>>(ctx->d_fval, n_stride, N, ctx->nrows, ctx->d_sidx32, scratch);
+    CC_CUDA(cudaGetLastError());
+    CC_CUDA(cudaFreeAsync(scratch, ctx->stream));
+  } else if (ctx->ftype != CC_FEATURE_LBP) {   // categorical variables are not sorted (numPrecalcIdx = 0, :267-273)
     const int blocks = std::min(ctx->nrows, ctx->sm_count);
     // Haar rows: bucket + rank sort, then the radix kernel on the rows it deferred.  HOG rows (long runs of exact zeros)
     // and cc_boost_set_sort_mode(ctx, 1): radix kernel on every row.
@@ -1179,6 +1264,14 @@ int cc_boost_get_fval(cc_ctx* ctx, int row0, int nrows, float* out) {
 }
 
 int cc_boost_get_sorted_idx(cc_ctx* ctx, int row0, int nrows, uint16_t* out) {
+  if (ctx && ctx->precalc_valid && ctx->wide) {      // wide path: narrow the 32-bit rows (numSamples < 65536 only)
+    CC_REQUIRE(ctx->N < 65536, CC_ERR_BAD_ARG, "cc_boost_get_sorted_idx: numSamples %d needs cc_boost_get_sorted_idx32", ctx->N);
+    CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows, CC_ERR_BAD_ARG, "cc_boost_get_sorted_idx: rows outside the local slice");
+    std::vector<uint32_t> tmp((size_t)nrows * ctx->N);
+    CC_CHECK(cc_boost_get_sorted_idx32(ctx, row0, nrows, tmp.data()));
+    for (size_t i = 0; i < tmp.size(); ++i) out[i] = (uint16_t)tmp[i];
+    return CC_OK;
+  }
   CC_REQUIRE(ctx && ctx->precalc_valid && ctx->d_sidx, CC_ERR_STATE, "cc_boost_get_sorted_idx: no sorted-index buffer (precalc not run, or categorical features)");
   CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows, CC_ERR_BAD_ARG, "cc_boost_get_sorted_idx: rows out of range");
   CC_CUDA(cudaSetDevice(ctx->device));
@@ -1188,7 +1281,32 @@ int cc_boost_get_sorted_idx(cc_ctx* ctx, int row0, int nrows, uint16_t* out) {
   return CC_OK;
 }
 
+int cc_boost_get_sorted_idx32(cc_ctx* ctx, int row0, int nrows, uint32_t* out) {
+  CC_REQUIRE(ctx && ctx->precalc_valid && (ctx->d_sidx32 || ctx->d_sidx), CC_ERR_STATE, "cc_boost_get_sorted_idx32: no sorted-index buffer (precalc not run, or categorical features)");
+  CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows && out, CC_ERR_BAD_ARG, "cc_boost_get_sorted_idx32: rows outside the local slice");
+  CC_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->wide) {
+    CC_CUDA(cudaMemcpy2DAsync(out, (size_t)ctx->N * sizeof(uint32_t), ctx->d_sidx32 + (size_t)row0 * ctx->n_stride, (size_t)ctx->n_stride * sizeof(uint32_t),
+                              (size_t)ctx->N * sizeof(uint32_t), nrows, cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    return CC_OK;
+  }
+  std::vector<uint16_t> tmp((size_t)nrows * ctx->N);
+  CC_CHECK(cc_boost_get_sorted_idx(ctx, row0, nrows, tmp.data()));
+  for (size_t i = 0; i < tmp.size(); ++i) out[i] = tmp[i];
+  return CC_OK;
+}
+
 int cc_boost_get_sorted_val(cc_ctx* ctx, int row0, int nrows, float* out) {
+  if (ctx && ctx->precalc_valid && ctx->wide) {        // wide path keeps no sorted-value rows: gather them
+    std::vector<uint32_t> idx((size_t)nrows * ctx->N);
+    std::vector<float> fv((size_t)nrows * ctx->N);
+    CC_CHECK(cc_boost_get_sorted_idx32(ctx, row0, nrows, idx.data()));
+    CC_CHECK(cc_boost_get_fval(ctx, row0, nrows, fv.data()));
+    for (int r = 0; r < nrows; ++r)
+      for (int i = 0; i < ctx->N; ++i) out[(size_t)r * ctx->N + i] = fv[(size_t)r * ctx->N + idx[(size_t)r * ctx->N + i]];
+    return CC_OK;
+  }
   CC_REQUIRE(ctx && ctx->precalc_valid && ctx->d_sval, CC_ERR_STATE, "cc_boost_get_sorted_val: no sorted-value buffer");
   CC_REQUIRE(row0 >= 0 && nrows > 0 && row0 + nrows <= ctx->nrows, CC_ERR_BAD_ARG, "cc_boost_get_sorted_val: rows out of range");
   CC_CUDA(cudaSetDevice(ctx->device));

@@ -136,6 +136,9 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples);
 int cc_boost_get_fval(cc_ctx* ctx, int row0, int nrows, float* out);          /* out[nrows][num_samples] */
 int cc_boost_get_sorted_idx(cc_ctx* ctx, int row0, int nrows, uint16_t* out); /* out[nrows][num_samples] */
 int cc_boost_get_sorted_val(cc_ctx* ctx, int row0, int nrows, float* out);
+/* same rows as 32-bit indices: the only form that exists when numSamples >= 65536 (is_buf_16u == false,
+ * src/o_cvcascadeboosttraindata.cpp:250-251) */
+int cc_boost_get_sorted_idx32(cc_ctx* ctx, int row0, int nrows, uint32_t* out);
 
 /* The whole stage: precalc (if not done for this sample set) + boosting loop; fills `out`. */
 int cc_boost_train(cc_ctx* ctx, int num_samples, const cc_boost_params* params, cc_stage* out);
@@ -145,7 +148,10 @@ int cc_boost_get_weights(cc_ctx* ctx, double* weights, uint8_t* mask);
 /* Ordered-variable split search strategy.  0 (default) = pruned: a bound pass over the u16 index rows drops every
  * variable that cannot beat the best split already known, the rest is searched exactly -- same winner as the
  * serial loop of DTreeBestSplitFinder (src/o_cvdtree.cpp:313-357), whose init_quality threading prunes in the
- * same spirit.  1 = exhaustive: every variable searched exactly (keeps per-variable qualities for the getter). */
+ * same spirit.  1 = exhaustive: every variable searched exactly (keeps per-variable qualities for the getter).
+ * 2 = wide kernels: the path stages with more than 15360 samples always take (rows sorted by a global-memory radix sort into
+ * 32-bit index rows, per-sample operands read from global memory, every variable searched exactly) forced for any numSamples;
+ * there is no upper limit on numSamples other than device memory.  All modes grow the same trees. */
 int cc_boost_set_search_mode(cc_ctx* ctx, int mode);
 /* How a weak tree of depth 1 is grown.  0 (default): root statistics, split search, exchange between the ranks, the split, both
  * leaves and the weight update / trimming / isErrDesired pass are queued back to back and the host reads the result once per

@@ -89,6 +89,9 @@ struct TrainData {
   bool categorical = false;
   std::vector<float> fval;          // F x N, feature-major ("valCache")
   std::vector<uint16_t> sidx;       // F x N sorted sample indices (ordered variables only), is_buf_16u
+  std::vector<uint32_t> sidx32;     // the same buffer when is_buf_16u == false: N >= 65536 (o_cvcascadeboosttraindata.cpp:250-251,283-309)
+  bool is_buf_16u = true;
+  uint32_t sorted_at(int row, int i) const { return is_buf_16u ? (uint32_t)sidx[(size_t)row * N + i] : sidx32[(size_t)row * N + i]; }
   std::vector<int> feat_subset;     // optional: evaluate only these variables (bench sampling); empty = all
 
   int var(int row) const { return feat_subset.empty() ? row : feat_subset[row]; }
@@ -100,19 +103,28 @@ struct TrainData {
     if (subset) feat_subset.assign(subset, subset + nsubset); else feat_subset.clear();
     F = subset ? nsubset : e->varCount();
     fval.assign((size_t)F * N, 0.f);
-    if (!categorical) sidx.assign((size_t)F * N, 0);
+    is_buf_16u = N < 65536;
+    sidx.clear(); sidx32.clear();
+    if (!categorical) { if (is_buf_16u) sidx.assign((size_t)F * N, 0); else sidx32.assign((size_t)F * N, 0); }
     parallel_rows(0, F, threads, [&](int b, int en) {
       for (int fi = b; fi < en; ++fi) {
         float* row = &fval[(size_t)fi * N];
         const int vi = var(fi);
         for (int si = 0; si < N; ++si) row[si] = (*ev)(vi, si);
-        if (!categorical) {
+        if (!categorical && is_buf_16u) {
           uint16_t* idx = &sidx[(size_t)fi * N];
           for (int si = 0; si < N; ++si) idx[si] = (uint16_t)si;
           if (sortMode == SORT_STD)
             std::sort(idx, idx + N, [row](uint16_t a, uint16_t b2) { return row[a] < row[b2]; });   // LessThanIdx, o_utils.h:18-23
           else
             std::stable_sort(idx, idx + N, [row](uint16_t a, uint16_t b2) { return row[a] < row[b2]; });
+        } else if (!categorical) {
+          uint32_t* idx = &sidx32[(size_t)fi * N];
+          for (int si = 0; si < N; ++si) idx[si] = (uint32_t)si;
+          if (sortMode == SORT_STD)
+            std::sort(idx, idx + N, [row](uint32_t a, uint32_t b2) { return row[a] < row[b2]; });
+          else
+            std::stable_sort(idx, idx + N, [row](uint32_t a, uint32_t b2) { return row[a] < row[b2]; });
         }
       }
     });
@@ -364,12 +376,12 @@ struct BoostTrainer {
 
   // node-local sorted order of ordered variable vi (values in sorted order, node-local positions)
   void node_sorted(int vi, const std::vector<int>& members, std::vector<int>& sorted, std::vector<float>& values) {
-    const uint16_t* g = &data->sidx[(size_t)vi * N];
     const float* row = &data->fval[(size_t)vi * N];
     sorted.clear(); values.clear();
     for (int i = 0; i < N; ++i) {
-      int p = pos_in_node[g[i]];
-      if (p >= 0) { sorted.push_back(p); values.push_back(row[g[i]]); }
+      const uint32_t gi = data->sorted_at(vi, i);
+      int p = pos_in_node[gi];
+      if (p >= 0) { sorted.push_back(p); values.push_back(row[gi]); }
     }
     (void)members;
   }

@@ -144,6 +144,7 @@ void orc_td_destroy(void* h) { delete (TrainData*)h; }
 int orc_td_rows(void* h) { return ((TrainData*)h)->F; }
 const float* orc_td_fval(void* h) { return ((TrainData*)h)->fval.data(); }
 const uint16_t* orc_td_sidx(void* h) { auto* t = (TrainData*)h; return t->sidx.empty() ? nullptr : t->sidx.data(); }
+const uint32_t* orc_td_sidx32(void* h) { auto* t = (TrainData*)h; return t->sidx32.empty() ? nullptr : t->sidx32.data(); }
 
 // ---- stage training ----------------------------------------------------------------------
 struct StageResult {

@@ -88,6 +88,7 @@ def lib():
         "orc_td_rows": (i32, [vp]),
         "orc_td_fval": (vp, [vp]),
         "orc_td_sidx": (vp, [vp]),
+        "orc_td_sidx32": (vp, [vp]),
         "orc_boost_train": (vp, [vp, P(BoostParams), i32, i32]),
         "orc_stage_destroy": (None, [vp]),
         "orc_stage_ok": (i32, [vp]),
@@ -263,7 +264,10 @@ class TrainData:
     def sidx(self):
         ptr = lib().orc_td_sidx(self.h)
         if not ptr:
-            return None
+            ptr32 = lib().orc_td_sidx32(self.h)          # is_buf_16u == false (N >= 65536)
+            if not ptr32:
+                return None
+            return np.ctypeslib.as_array(C.cast(ptr32, C.POINTER(C.c_uint32)), shape=(self.F, self.N))
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint16)), shape=(self.F, self.N))
 
 

@@ -298,3 +298,79 @@ def test_stump_path_equals_general_path(gpu_ctx, ftype, mode, bt):
     assert len(a[0]) >= 2
     assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
     assert np.array_equal(a[3], b[3]) and np.array_equal(a[4], b[4])
+
+
+# ---- wide path: numSamples beyond one CTA's shared memory (a9: CvCascadeBoostTrainData::setData takes any N) ---------------------
+def _train_gpu(gpu_ctx, ftype, mode, W, H, imgs, labels, **kw):
+    import cascadeclassifier_b200 as ccb
+    n = len(imgs)
+    ev = ccb.CvFeatureEvaluator.create(ftype, gpu_ctx)
+    fp = ccb.CvFeatureParams.create(ftype)
+    if ftype == orc.HAAR:
+        fp.mode = mode
+    ev.init(fp, n, (W, H))
+    ev.setImages(imgs, labels)
+    st = ccb.CvCascadeBoost()
+    ok = st.train(ev, n, 1024, 1024, ccb.CvCascadeBoostParams(**kw))
+    return ok, st, ev
+
+
+@pytest.mark.parametrize("ftype,mode,bt,depth", [(orc.HAAR, orc.ALL, orc.GAB, 1), (orc.HAAR, orc.BASIC, orc.RAB, 1), (orc.HAAR, orc.BASIC, orc.DAB, 2),
+                                                 (orc.HAAR, orc.CORE, orc.LB, 1), (orc.HOG, 0, orc.GAB, 1), (orc.LBP, 0, orc.GAB, 2)])
+def test_wide_kernels_equal_shared_memory_kernels(gpu_ctx, ftype, mode, bt, depth):
+    """cc_boost_set_search_mode(ctx, 2) forces the kernels that stages with more than 15360 samples take (global-memory radix sort
+    into 32-bit index rows, operands and values gathered from global memory, categorical operands from global memory) on a small
+    stage: sorted rows and trees must be bit-identical to the shared-memory kernels'."""
+    import ctypes as C
+    from cascadeclassifier_b200._lib import check
+    W, H = (32, 32) if ftype == orc.HOG else (16, 16)
+    imgs, labels = make_samples(170, 290, W, H)
+    n = len(imgs)
+    runs = []
+    try:
+        for sm in (1, 2):
+            gpu_ctx.set_search_mode(sm)
+            ok, st, ev = _train_gpu(gpu_ctx, ftype, mode, W, H, imgs, labels, boostType=bt, maxDepth=depth, maxFalseAlarm=0.05, maxWeakCount=6)
+            assert ok
+            rows = None
+            if ftype != orc.LBP:
+                nr = min(64, ev.getNumFeatures() * ev.getFeatureSize())
+                rows = np.zeros((nr, n), np.uint32)
+                check(gpu_ctx.lib.cc_boost_get_sorted_idx32(gpu_ctx.h, 0, nr, rows.ctypes.data_as(C.c_void_p)), "cc_boost_get_sorted_idx32")
+                vals = np.zeros((nr, n), np.float32)
+                check(gpu_ctx.lib.cc_boost_get_sorted_val(gpu_ctx.h, 0, nr, vals.ctypes.data_as(C.c_void_p)), "cc_boost_get_sorted_val")
+                rows = (rows, vals)
+            runs.append((st.trees, st.threshold, st.log, rows))
+    finally:
+        gpu_ctx.set_search_mode(0)
+    a, b = runs
+    assert a[0] == b[0] and a[1] == b[1] and a[2] == b[2]
+    if a[3] is not None:
+        assert np.array_equal(a[3][0], b[3][0]) and np.array_equal(a[3][1].view(np.uint32), b[3][1].view(np.uint32))
+
+
+@pytest.mark.parametrize("ftype,mode,W,npos,nneg,bt", [(orc.HAAR, orc.ALL, 12, 6000, 14000, orc.GAB),       # 20000 > 15360: u16 range, wide kernels
+                                                       (orc.HAAR, orc.BASIC, 10, 16000, 50000, orc.GAB),    # 66000 >= 65536: is_buf_16u == false in the reference
+                                                       (orc.HAAR, orc.BASIC, 10, 9000, 21000, orc.RAB),
+                                                       (orc.LBP, 0, 12, 9000, 21000, orc.GAB)])              # categorical operands no longer fit in shared memory
+def test_large_sample_counts_match_oracle(gpu_ctx, ftype, mode, W, npos, nneg, bt):
+    """CvCascadeBoostTrainData::setData accepts any sample count (32-bit index buffers from 65536 on,
+    src/o_cvcascadeboosttraindata.cpp:250-251,283-309): stages with 20000 / 30000 / 66000 samples against the oracle -- sorted index
+    rows (stable order) and every weak tree."""
+    import ctypes as C
+    from cascadeclassifier_b200._lib import check
+    imgs, labels = make_samples(npos, nneg, W, W)
+    n = len(imgs)
+    kw = dict(boostType=bt, maxFalseAlarm=0.3, maxWeakCount=4)
+    ok, st, ev = _train_gpu(gpu_ctx, ftype, mode, W, W, imgs, labels, **kw)
+    o = orc.Evaluator(ftype, mode, W, W, n)
+    o.set_images(imgs, labels)
+    td = orc.TrainData(o, n, orc.SORT_STABLE, 16)
+    ref = orc.boost_train(td, orc.boost_params(boost_type=bt, max_false_alarm=0.3, weak_count=4), cat_sort=orc.SORT_STABLE)
+    assert ok == ref.ok
+    assert_full_stage(st, ref)
+    if ftype != orc.LBP:
+        nr = 48
+        rows = np.zeros((nr, n), np.uint32)
+        check(gpu_ctx.lib.cc_boost_get_sorted_idx32(gpu_ctx.h, 0, nr, rows.ctypes.data_as(C.c_void_p)), "cc_boost_get_sorted_idx32")
+        assert np.array_equal(rows, td.sidx()[:nr].astype(np.uint32))
