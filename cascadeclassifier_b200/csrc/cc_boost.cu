@@ -261,22 +261,24 @@ __global__ void k_tree_begin(int N, const uint8_t* __restrict__ mask, int* node_
 // and weak_eval[s] = node value for every member (leaf assignment of CvBoostTree::try_split_node,
 // :74-84; children overwrite it when the node is split).
 __global__ void __launch_bounds__(ONE_CTA, 1)
-k_node_prepare(int N, int nid, int is_classifier, int boost_type, const int* __restrict__ node_of, const double* __restrict__ weights,
+k_node_prepare(int N, int nid0, int is_classifier, int boost_type, const int* __restrict__ node_of, const double* __restrict__ weights,
                const float* __restrict__ responses, double* wnode, float* ynode, double* weak_eval, NodeStats* stats) {
   __shared__ double scratch[32];
+  const int nid = nid0 + blockIdx.x;      // one CTA per node: the two leaves of a stump are prepared by one launch
+  const bool write_ops = gridDim.x == 1;  // sibling CTAs would overwrite each other's operands; leaves need none (no further search)
   double a0 = 0, a1 = 0, a2 = 0;
   long long c0 = 0, c1 = 0;
   for (int s = threadIdx.x; s < N; s += blockDim.x) {
-    if (node_of[s] != nid) { wnode[s] = 0.0; continue; }
+    if (node_of[s] != nid) { if (write_ops) wnode[s] = 0.0; continue; }
     const double w = weights[s];
     const float y = responses[s];
     if (is_classifier) {
       const int r = (int)y;
-      if (r) { a1 += w; c1++; wnode[s] = w; } else { a0 += w; c0++; wnode[s] = -w; }
+      if (r) { a1 += w; c1++; if (write_ops) wnode[s] = w; } else { a0 += w; c0++; if (write_ops) wnode[s] = -w; }
     } else {
       const double t = (double)y;
       a0 += w; a1 += t * w; a2 += t * t * w; c0++;
-      if (boost_type == CC_BOOST_LOGIT) { wnode[s] = w; ynode[s] = y; } else wnode[s] = t * w;
+      if (write_ops) { if (boost_type == CC_BOOST_LOGIT) { wnode[s] = w; ynode[s] = y; } else wnode[s] = t * w; }
     }
   }
   a0 = block_sum(a0, scratch); a1 = block_sum(a1, scratch); a2 = block_sum(a2, scratch);
@@ -1484,12 +1486,10 @@ static int grow_stump_and_finish(cc_ctx* ctx, BoostBuffers* b, const EvalView& e
   CC_CHECK(launch_split_search(ctx, b, 0));
   CC_CHECK(exchange_candidates(ctx, b->d_best));
   {
-    ScopedTimer tm(ctx, "boost_small", 5);
+    ScopedTimer tm(ctx, "boost_small", 4);
     k_apply_split<<<(N + 255) / 256, 256, 0, ctx->stream>>>(ev, N, 0, 1, 2, b->d_best, b->node_of);
     // the leaves: wnode / ynode are no longer needed (no further search), only the node values and weak_eval
-    k_node_prepare<<<1, ONE_CTA, 0, ctx->stream>>>(N, 1, b->is_classifier, b->boost_type, b->node_of, b->weights, b->responses,
-                                                   b->wnode, b->ynode, b->weak_eval, b->d_stats);
-    k_node_prepare<<<1, ONE_CTA, 0, ctx->stream>>>(N, 2, b->is_classifier, b->boost_type, b->node_of, b->weights, b->responses,
+    k_node_prepare<<<2, ONE_CTA, 0, ctx->stream>>>(N, 1, b->is_classifier, b->boost_type, b->node_of, b->weights, b->responses,
                                                    b->wnode, b->ynode, b->weak_eval, b->d_stats);
     k_build_stump<<<1, 32, 0, ctx->stream>>>(b->d_stats, b->d_best, b->params.min_sample_count, b->params.regression_accuracy, b->is_classifier,
                                              b->d_tree, b->d_tree_ok);

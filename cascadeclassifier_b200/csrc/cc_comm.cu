@@ -105,6 +105,18 @@ int cc_comm_init(cc_ctx* ctx, const void* id128, int rank, int world) {
   ctx->nccl_comm = comm;
   ctx->comm_rank = rank;
   ctx->comm_world = world;
+  // NCCL sets its channels up lazily at the first collective of each kind (hundreds of ms on 8 ranks): do that here, not
+  // inside the first stage training / the first mining batch
+  {
+    unsigned char* warm = nullptr;
+    CC_CUDA(cudaMalloc(&warm, (size_t)64 * (world + 1) + 4096));
+    CC_CUDA(cudaMemsetAsync(warm, 0, (size_t)64 * (world + 1) + 4096, ctx->stream));
+    int r1 = g_nccl.AllGather(warm, warm + 64, 64, /*ncclChar*/ 0, comm, ctx->stream);
+    int r2 = g_nccl.AllReduce(warm, warm, 1024, /*ncclUint32*/ 3, /*ncclSum*/ 0, comm, ctx->stream);
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(warm);
+    CC_REQUIRE(r1 == 0 && r2 == 0, CC_ERR_NCCL, "NCCL warm-up collectives failed");
+  }
   return cc_boost_set_shard(ctx, rank, world);
 }
 
