@@ -238,7 +238,7 @@ def run_ours(args):
     ss_ms = fam["split_search"]["ms_per_step"] / n_search
     pre_ms, sort_ms = fam["precalc"]["ms_per_step"], fam["sort"]["ms_per_step"]
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f)

@@ -105,6 +105,8 @@ def _signatures():
         "cc_mine_get_stats": (i32, [vp, vp]),
         "cc_mine_serial_cut": (i32, [vp, i64, i64, i32, f64, P(i64), P(C.c_int32), P(i64), P(C.c_int32), vp, P(C.c_int32)]),
         "cc_reader_advance": (i32, [vp, vp, i32, i32, i32, P(ReaderState), i64, vp]),
+        "cc_createsamples": (i32, [vp, vp, i32, i32, i32, i32, i32, i32, i32, f64, f64, f64, i32, i32, i32, vp]),
+        "cc_createsamples_plan": (i32, [i32, i32, i32, i32, i32, f64, f64, f64, i32, i32, i32, vp, vp, vp]),
         "cc_timing_reset": (i32, [vp]),
         "cc_timing_get": (i32, [vp, C.c_char_p, P(f64), P(i64)]),
         "cc_launch_count": (i64, [vp]),

@@ -522,56 +522,62 @@ struct CascadeArgs {
   int s_begin, s_end;
 };
 
+// window normalisation factor: calcNormFactor (src/features.cpp:13-25) from the level planes
+__device__ __forceinline__ float window_nf(const uint32_t* __restrict__ S, const uint32_t* __restrict__ Q, int pitch, const CascadeArgs& A) {
+  if (A.ftype != CC_FEATURE_HAAR) return 0.f;
+  const int W = A.W, H = A.H;
+  const int o0 = pitch + 1, o1 = pitch + (W - 1), o2 = (H - 1) * pitch + 1, o3 = (H - 1) * pitch + (W - 1);
+  const uint32_t vs = S[o0] - S[o1] - S[o2] + S[o3];
+  const uint32_t vq = Q[o0] - Q[o1] - Q[o2] + Q[o3];
+  const double area = (double)((W - 2) * (H - 2));
+  const double dvs = (double)(int)vs;
+  return (float)sqrt(area * (double)vq - dvs * dvs);
+}
+
+// CvCascadeBoostTree::predict (src/o_cvcascadeboosttree.cpp:16-39) of the tree whose nodes start at `first`, on the window at S / Tt
+__device__ __forceinline__ double window_tree_value(const uint32_t* __restrict__ S, const uint32_t* __restrict__ Tt, int pitch, const CascadeArgs& A,
+                                                    int first, float nf) {
+  int nd = 0;
+  while (A.nodes[first + nd].left >= 0) {
+    const DevNode& node = A.nodes[first + nd];
+    const LvlFeat& f = A.feats[first + nd];
+    bool left;
+    if (A.ftype == CC_FEATURE_HAAR) {
+      const uint32_t hdr = f.hdr;
+      const uint32_t* P = (hdr >> 8) ? Tt : S;
+      const int nt = (int)(hdr & 0xFFu);
+      int acc = 0;
+      for (int q = 0; q < nt; ++q) {
+        const uint32_t tp = f.tap[q];
+        acc += (int)(int8_t)(tp >> 16) * (int)P[(int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)];
+      }
+      const float val = nf == 0.f ? 0.f : __fdiv_rn((float)acc, nf);
+      left = val <= node.c;
+    } else {
+      int v[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) { const uint32_t tp = f.tap[q]; v[q] = (int)S[(int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)]; }
+      auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
+      const int c = cell(1, 1);
+      const int code = (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
+                       (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
+                       (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
+      left = (node.subset[code >> 5] & (1 << (code & 31))) != 0;
+    }
+    nd = left ? node.left : node.right;
+  }
+  return A.nodes[first + nd].value;
+}
+
 // S / Q / Tt point at the window's origin inside planes of row pitch `pitch` (global memory: whole-level planes; shared
 // memory: the planes of one tile).  Same arithmetic as setImage + operator() + predict of the reference.
 __device__ __forceinline__ bool eval_window_at(const uint32_t* __restrict__ S, const uint32_t* __restrict__ Q, const uint32_t* __restrict__ Tt,
                                                int pitch, const CascadeArgs& A) {
-  const int W = A.W, H = A.H;
-  float nf = 0.f;
-  if (A.ftype == CC_FEATURE_HAAR) {
-    const int o0 = pitch + 1, o1 = pitch + (W - 1), o2 = (H - 1) * pitch + 1, o3 = (H - 1) * pitch + (W - 1);
-    const uint32_t vs = S[o0] - S[o1] - S[o2] + S[o3];
-    const uint32_t vq = Q[o0] - Q[o1] - Q[o2] + Q[o3];
-    const double area = (double)((W - 2) * (H - 2));
-    const double dvs = (double)(int)vs;
-    nf = (float)sqrt(area * (double)vq - dvs * dvs);
-  }
+  const float nf = window_nf(S, Q, pitch, A);
   for (int st = A.s_begin; st < A.s_end; ++st) {
     const DevStageRef sr = A.stages[st];
     double sum = 0;
-    for (int t = 0; t < sr.num_trees; ++t) {
-      const int first = A.tree_first[sr.first_tree + t];
-      int nd = 0;
-      while (A.nodes[first + nd].left >= 0) {
-        const DevNode& node = A.nodes[first + nd];
-        const LvlFeat& f = A.feats[first + nd];
-        bool left;
-        if (A.ftype == CC_FEATURE_HAAR) {
-          const uint32_t hdr = f.hdr;
-          const uint32_t* P = (hdr >> 8) ? Tt : S;
-          const int nt = (int)(hdr & 0xFFu);
-          int acc = 0;
-          for (int q = 0; q < nt; ++q) {
-            const uint32_t tp = f.tap[q];
-            acc += (int)(int8_t)(tp >> 16) * (int)P[(int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)];
-          }
-          const float val = nf == 0.f ? 0.f : __fdiv_rn((float)acc, nf);
-          left = val <= node.c;
-        } else {
-          int v[16];
-#pragma unroll
-          for (int q = 0; q < 16; ++q) { const uint32_t tp = f.tap[q]; v[q] = (int)S[(int)((tp >> 8) & 0xFFu) * pitch + (int)(tp & 0xFFu)]; }
-          auto cell = [&](int gx, int gy) { const int a = gy * 4 + gx; return v[a] - v[a + 1] - v[a + 4] + v[a + 5]; };
-          const int c = cell(1, 1);
-          const int code = (cell(0, 0) >= c ? 128 : 0) | (cell(1, 0) >= c ? 64 : 0) | (cell(2, 0) >= c ? 32 : 0) |
-                           (cell(2, 1) >= c ? 16 : 0) | (cell(2, 2) >= c ? 8 : 0) | (cell(1, 2) >= c ? 4 : 0) |
-                           (cell(0, 2) >= c ? 2 : 0) | (cell(0, 1) >= c ? 1 : 0);
-          left = (node.subset[code >> 5] & (1 << (code & 31))) != 0;
-        }
-        nd = left ? node.left : node.right;
-      }
-      sum += A.nodes[first + nd].value;
-    }
+    for (int t = 0; t < sr.num_trees; ++t) sum += window_tree_value(S, Tt, pitch, A, A.tree_first[sr.first_tree + t], nf);
     if (sum < (double)(sr.threshold - 0.00001F)) return false;
   }
   return true;
@@ -629,6 +635,45 @@ k_lvl_cascade(const LevelDesc* __restrict__ levels, int nlevels, CascadeArgs A, 
       pass = lvl_eval_window(L, (long long)b - L.w_base + L.w_skip, A);
     }
     lvl_append(pass, b, out_count, out_list);
+  }
+}
+
+// Deep stage groups: few survivors, many trees per stage.  One thread per window would walk ~150 trees one after the other,
+// a chain of dependent loads of ~1 us each that no amount of parallelism across the handful of surviving windows hides.  Here a
+// WARP takes a window: the lanes evaluate the trees of a stage in parallel, the stage sum is then accumulated in tree order
+// (lane k's leaf value broadcast to all lanes, k = 0, 1, ...), i.e. with the additions of CvCascadeBoost::predict
+// (src/boost.cpp:461-477) in the reference's order -- same f64 sum, same decision.
+__global__ void __launch_bounds__(256)
+k_lvl_cascade_warp(const LevelDesc* __restrict__ levels, int nlevels, CascadeArgs A, const unsigned int* __restrict__ in_list,
+                   const unsigned int* __restrict__ in_count, unsigned int* __restrict__ out_count, unsigned int* __restrict__ out_list) {
+  const long long n = (long long)*in_count;
+  const int lane = threadIdx.x & 31;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += nwarps) {
+    const unsigned int b = in_list[i];
+    int lo = 0, hi = nlevels - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= (long long)b) lo = mid; else hi = mid - 1; }
+    const LevelDesc& L = levels[lo];
+    const long long k = (long long)b - L.w_base + L.w_skip;
+    const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
+    const size_t org = (size_t)L.ip_off + (size_t)(L.y0 + iy * L.step_y) * L.pitch + (L.x0 + ix * L.step_x);
+    const uint32_t* S = A.pl.sum + org;
+    const uint32_t* Q = A.pl.sq ? A.pl.sq + org : nullptr;
+    const uint32_t* Tt = A.pl.tilted ? A.pl.tilted + org : nullptr;
+    const float nf = window_nf(S, Q, L.pitch, A);
+    bool pass = true;
+    for (int st = A.s_begin; st < A.s_end && pass; ++st) {
+      const DevStageRef sr = A.stages[st];
+      double sum = 0;
+      for (int t0 = 0; t0 < sr.num_trees; t0 += 32) {
+        const int t = t0 + lane;
+        const double val = t < sr.num_trees ? window_tree_value(S, Tt, L.pitch, A, A.tree_first[sr.first_tree + t], nf) : 0.0;
+        const int cnt = min(32, sr.num_trees - t0);
+        for (int q = 0; q < cnt; ++q) sum += __shfl_sync(0xffffffffu, val, q);
+      }
+      if (sum < (double)(sr.threshold - 0.00001F)) pass = false;
+    }
+    if (pass && lane == 0) out_list[atomicAdd(out_count, 1u)] = b;
   }
 }
 
@@ -901,6 +946,9 @@ struct MineState {
   size_t h_gather_cap = 0;
   cudaEvent_t ev_gather = nullptr;
   long long stat_consumed = 0, stat_built = 0, stat_cand = 0, stat_skipped = 0;
+  // the three width classes of the pyramid builder run side by side (their tails overlap): two helper streams forked from / joined to ctx->stream
+  cudaStream_t side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 };
 
 static void free_cascade(MineState* m) {
@@ -933,6 +981,11 @@ static void free_scratch(MineState* m) {
   cudaFree(m->d_cand); m->d_cand = nullptr; m->d_cand_cap = 0;
   cudaFree(m->d_gather); m->d_gather = nullptr; m->d_gather_cap = 0;
   cudaFreeHost(m->h_gather); m->h_gather = nullptr; m->h_gather_cap = 0;
+  for (int s = 0; s < 2; ++s) {
+    if (m->side[s]) { cudaStreamDestroy(m->side[s]); m->side[s] = nullptr; }
+    if (m->ev_join[s]) { cudaEventDestroy(m->ev_join[s]); m->ev_join[s] = nullptr; }
+  }
+  if (m->ev_fork) { cudaEventDestroy(m->ev_fork); m->ev_fork = nullptr; }
   if (m->ev_gather) { cudaEventDestroy(m->ev_gather); m->ev_gather = nullptr; }
   for (int s = 0; s < 2; ++s) {
     cudaFreeHost(m->h_cand[s]); m->h_cand[s] = nullptr; m->h_cand_cap[s] = 0;
@@ -1524,9 +1577,24 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
         CC_CUDA(cudaFuncSetAttribute(k_lvl_build<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
         CC_CUDA(cudaFuncSetAttribute(k_lvl_build<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536));
       }
+      // the classes write disjoint strips: run them side by side so that the tail of one overlaps the others
+      if (!m->ev_fork) {
+        CC_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+        for (int k = 0; k < 2; ++k) {
+          CC_CUDA(cudaStreamCreateWithFlags(&m->side[k], cudaStreamNonBlocking));
+          CC_CUDA(cudaEventCreateWithFlags(&m->ev_join[k], cudaEventDisableTiming));
+        }
+      }
+      CC_CUDA(cudaEventRecord(m->ev_fork, ctx->stream));
+      CC_CUDA(cudaStreamWaitEvent(m->side[0], m->ev_fork, 0));
+      CC_CUDA(cudaStreamWaitEvent(m->side[1], m->ev_fork, 0));
       if (off[3] > off[2]) { k_lvl_build<512><<<off[3] - off[2], 512, ssm, ctx->stream>>>(d_levels, m->d_order + off[2], pool, m->d_psum, psq, ptl, src_pitch_max, ctx->H); ++launches; }
-      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, ssm, ctx->stream>>>(d_levels, m->d_order + off[1], pool, m->d_psum, psq, ptl, src_pitch_max, ctx->H); ++launches; }
-      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, ssm, ctx->stream>>>(d_levels, m->d_order + off[0], pool, m->d_psum, psq, ptl, src_pitch_max, ctx->H); ++launches; }
+      if (off[2] > off[1]) { k_lvl_build<256><<<off[2] - off[1], 256, ssm, m->side[0]>>>(d_levels, m->d_order + off[1], pool, m->d_psum, psq, ptl, src_pitch_max, ctx->H); ++launches; }
+      if (off[1] > off[0]) { k_lvl_build<128><<<off[1] - off[0], 128, ssm, m->side[1]>>>(d_levels, m->d_order + off[0], pool, m->d_psum, psq, ptl, src_pitch_max, ctx->H); ++launches; }
+      CC_CUDA(cudaEventRecord(m->ev_join[0], m->side[0]));
+      CC_CUDA(cudaEventRecord(m->ev_join[1], m->side[1]));
+      CC_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_join[0], 0));
+      CC_CUDA(cudaStreamWaitEvent(ctx->stream, m->ev_join[1], 0));
     } else {
       k_resize_levels<<<grid_for(ctx, (long long)pool_px, 256), 256, 0, ctx->stream>>>(d_levels, nlv, (long long)pool_px, m->d_pool);
       k_lvl_rows<<<grid_for(ctx, (long long)rows * 32, 256), 256, 0, ctx->stream>>>(d_levels, nlv, rows, m->d_pool, m->d_psum, haar ? m->d_psq : nullptr);
@@ -1556,9 +1624,12 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
       if (ngroups == 0) {
         if (nlv > 0) k_lvl_cascade_all<<<std::min(nlv, ctx->sm_count * 32), 256, 0, ctx->stream>>>(d_levels, nlv, A, m->d_counts, m->d_list[0]);
       }
-      else
+      else if (ngroups == 1)
         k_lvl_cascade<<<ctx->sm_count * 4, 256, 0, ctx->stream>>>(d_levels, nlv, A, m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1,
                                                                    m->d_counts + ngroups, m->d_list[ngroups & 1]);
+      else      // deep stages on the few windows left: a warp per window, lanes across the trees of a stage
+        k_lvl_cascade_warp<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_levels, nlv, A, m->d_list[(ngroups - 1) & 1], m->d_counts + ngroups - 1,
+                                                                        m->d_counts + ngroups, m->d_list[ngroups & 1]);
       ++ngroups; ++launches;
       s0 = s1;
     }

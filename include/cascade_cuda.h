@@ -240,6 +240,22 @@ int cc_mine_scan(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* sur
  * or two runs agree on WHICH windows pass iff their digests agree */
 int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64_t* survivors, uint64_t* digest);
 
+/* ---- training-sample generation: opencv_createsamples -img <image> -num <count> -vec <out> (no -bg),
+ *      tools/createsamples/utility.cpp:952-1029 cvCreateTrainingSamples + :419-672 (icvRandomQuad, the tool's own scan-line
+ *      cvWarpPerspective, icvStartSampleDistortion, icvPlaceDistortedSample), flags of tools/createsamples/createsamples.cpp:60-166 --- */
+#define CC_RANDOM_INVERT 0x7FFFFFFF   /* -randinv (CV_RANDOM_INVERT) */
+/* host_gray = the source image (imread(path, IMREAD_GRAYSCALE)), w x h.  out_samples receives count windows of win_h * win_w bytes:
+ * the payload of the .vec file (header / record layout: utility.cpp:128-153).  The cv::RNG stream (cv::setRNGSeed(rngseed)), the
+ * rotations, the perspective systems and the edge walks are computed on the host in f64 exactly in the reference's order; the
+ * warps, the mask blur, the INTER_LINEAR_EXACT resizes and the blend run on the GPU. */
+int cc_createsamples(cc_ctx* ctx, const uint8_t* host_gray, int w, int h, int bgcolor, int bgthreshold, int count, int invert,
+                     int maxintensitydev, double maxxangle, double maxyangle, double maxzangle, int win_w, int win_h, int rngseed,
+                     uint8_t* out_samples);
+/* the host half alone (no GPU needed; parity tests): per sample quads[8] (the distorted quadrangle in the enlarged image),
+ * coeffs[9] (perspective transform), misc[8] = crop x, y, w, h, forecolordev, inverse, warp rows, warp pixels */
+int cc_createsamples_plan(int w, int h, int count, int invert, int maxintensitydev, double maxxangle, double maxyangle, double maxzangle,
+                          int win_w, int win_h, int rngseed, double* quads, double* coeffs, int32_t* misc);
+
 /* ---- instrumentation ------------------------------------------------------------------------ */
 /* CUDA-event time (ms) and launch count accumulated per kernel family since the last reset.
  * names: "integral", "precalc", "sort", "split_search", "boost_small", "mine" */
