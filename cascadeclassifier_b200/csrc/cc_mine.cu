@@ -1330,11 +1330,20 @@ static long long level_path_max_batch(const cc_ctx* ctx, const MineState* m) {
   return LEVEL_PATH_MAX_BATCH * (sharded ? std::min(ctx->comm_world, 16) : 1);
 }
 
+// image-sharded mining: a rank builds 1 / world of a batch
+static double sharded_alloc_div(const cc_ctx* ctx, const MineState* m) {
+  return (ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images) ? (double)std::min(ctx->comm_world, 16) : 1.0;
+}
+
 // host wall time of the batch loop by phase (cc_timing_get "mine_host_assemble" / "mine_host_eval" / "mine_host_cut"; launches = batches)
 struct HostTimer {
   cc_ctx* ctx; const char* name; std::chrono::steady_clock::time_point t0;
+  bool done = false;
   HostTimer(cc_ctx* c, const char* n) : ctx(c), name(n), t0(std::chrono::steady_clock::now()) {}
-  ~HostTimer() {
+  ~HostTimer() { stop(); }
+  void stop() {
+    if (done) return;
+    done = true;
     if (!ctx->timing_enabled) return;
     TimerSlot& s = ctx->timers[name];
     s.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -1516,11 +1525,24 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
   const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
   const bool haar = ctx->ftype == CC_FEATURE_HAAR;
   const bool tilted = haar && m->cascade_tilted;
-  if (pool_px > m->pool_cap) { cudaFree(m->d_pool); CC_CUDA(cudaMalloc(&m->d_pool, pool_px + pool_px / 2)); m->pool_cap = pool_px + pool_px / 2; }
+  // Buffers grow with the batches (which grow from stage to stage as the acceptance rate falls): grow by 4x, but not beyond what
+  // a full batch will need, so that a cascade reallocates two or three times instead of once per stage (cudaFree / cudaMalloc /
+  // cudaMallocHost of gigabytes synchronise the device and take milliseconds each).
+  HostTimer halloc(ctx, "mine_host_alloc");
+  const double full_batch = std::max(1.0, (double)level_path_max_batch(ctx, m) / (double)std::max<long long>(1, bt.neval) / (sharded_alloc_div(ctx, m)));
+  auto grown = [&](size_t need) -> size_t { return (size_t)((double)need * std::min(4.0, std::max(1.1, 1.1 * full_batch))); };
+  bool fused = !m->force_unfused;
+  int src_pitch_max = 16;
+  for (const LevelDesc& L : dl) { fused = fused && L.lw <= LB_MAXDIM && L.lh <= LB_MAXDIM && L.sh <= 65535 && L.spitch <= 8192; src_pitch_max = std::max(src_pitch_max, L.spitch); }
+  if (!fused && pool_px > m->pool_cap) {      // (the fused builder keeps no level pixels)
+    cudaFree(m->d_pool); m->d_pool = nullptr;
+    const size_t cap = grown(pool_px);
+    CC_CUDA(cudaMalloc(&m->d_pool, cap)); m->pool_cap = cap;
+  }
   if (nlv > m->strips_cap[slot]) {
     cudaFree(m->d_strips[slot]); cudaFreeHost(m->h_strips[slot]);
     m->d_strips[slot] = nullptr; m->h_strips[slot] = nullptr; m->strips_cap[slot] = 0;
-    const int cap = nlv + nlv / 2 + 64;
+    const int cap = (int)grown((size_t)nlv) + 64;
     CC_CUDA(cudaMalloc(&m->d_strips[slot], sizeof(LevelDesc) * cap));
     CC_CUDA(cudaMallocHost(&m->h_strips[slot], sizeof(LevelDesc) * cap));
     m->strips_cap[slot] = cap;
@@ -1529,18 +1551,34 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
   if (plane_elems > m->plane_cap) {
     cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
     m->d_psum = m->d_psq = m->d_ptilt = nullptr;
-    const size_t cap = plane_elems + plane_elems / 2;
+    const size_t cap = grown(plane_elems);
     CC_CUDA(cudaMalloc(&m->d_psum, cap * 4));
     if (haar) { CC_CUDA(cudaMalloc(&m->d_psq, cap * 4)); CC_CUDA(cudaMalloc(&m->d_ptilt, cap * 4)); }
     m->plane_cap = cap;
   }
   if ((size_t)bt.neval > m->list_cap) {
     cudaFree(m->d_list[0]); cudaFree(m->d_list[1]);
-    const size_t cap = (size_t)bt.neval + (size_t)bt.neval / 2;
+    const size_t cap = grown((size_t)bt.neval);
     CC_CUDA(cudaMalloc(&m->d_list[0], cap * 4)); CC_CUDA(cudaMalloc(&m->d_list[1], cap * 4));
     m->list_cap = cap;
   }
   if (!m->d_counts) CC_CUDA(cudaMalloc(&m->d_counts, sizeof(unsigned) * 16));
+  {
+    const size_t words = ((size_t)bt.neval + 31) / 32;
+    if (words > m->bitmap_cap) {
+      cudaFree(m->d_bitmap);
+      const size_t cap = grown(words) + 64;
+      CC_CUDA(cudaMalloc(&m->d_bitmap, cap * 4));
+      m->bitmap_cap = cap;
+    }
+    if (words > m->h_bits_cap[slot]) {
+      cudaFreeHost(m->h_bits[slot]);
+      const size_t cap = grown(words) + 64;
+      CC_CUDA(cudaMallocHost(&m->h_bits[slot], cap * 4));
+      m->h_bits_cap[slot] = cap;
+    }
+  }
+  halloc.stop();
   if (nlv) {
     memcpy(m->h_strips[slot], dl.data(), sizeof(LevelDesc) * nlv);
     CC_CUDA(cudaMemcpyAsync(d_levels, m->h_strips[slot], sizeof(LevelDesc) * nlv, cudaMemcpyHostToDevice, ctx->stream));
@@ -1549,9 +1587,6 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
   {
     ScopedTimer tm(ctx, "mine", 0);
     int launches = 0;
-    bool fused = !m->force_unfused;
-    int src_pitch_max = 16;
-    for (const LevelDesc& L : dl) { fused = fused && L.lw <= LB_MAXDIM && L.lh <= LB_MAXDIM && L.sh <= 65535 && L.spitch <= 8192; src_pitch_max = std::max(src_pitch_max, L.spitch); }
     if (fused) {
       // three width classes (CTA of 128 / 256 / 512 threads, 4 columns per thread), each tallest-first
       std::vector<int> order[3];
