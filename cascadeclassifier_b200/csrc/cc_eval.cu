@@ -175,63 +175,82 @@ __device__ __forceinline__ float cv_atan2_rad(float y, float x) {
 }
 
 // gradient magnitude + orientation bin per pixel; outputs are [pixel][ns_pad] (sample-fastest)
-__global__ void k_hog_gradient(const uint8_t* __restrict__ imgs, int W, int H, int first, int n, int ns_pad,
-                               float* __restrict__ grad, uint8_t* __restrict__ qangle) {
-  const long long total = (long long)n * W * H;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int s = (int)(t % n);
-    const int px = (int)(t / n);
-    const int y = px / W, x = px - y * W;
-    const uint8_t* img = imgs + (size_t)(first + s) * W * H;
-    const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
-    const float dx = (float)((int)img[y * W + xp] - (int)img[y * W + xm]);
-    const float dy = (float)((int)img[yp * W + x] - (int)img[ym * W + x]);
-    const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-    float angle = cv_atan2_rad(dy, dx);
-    angle = __fsub_rn(__fmul_rn(angle, (float)(9 / 3.14159265358979323846)), 0.5f);
-    int b = (int)floorf(angle);
-    if (b < 0) b += 9; else if (b >= 9) b -= 9;
-    grad[(size_t)px * ns_pad + first + s] = mag;
-    qangle[(size_t)px * ns_pad + first + s] = (uint8_t)b;
-  }
-}
-
-// row pass: thread per (plane, y, sample); sequential float prefix along x, same order as the reference
-__global__ void k_hog_rows(const float* __restrict__ grad, const uint8_t* __restrict__ qangle, int W, int H,
-                           int first, int n, int ns_pad, float* __restrict__ planes) {
-  const int S = W + 1, P = S * (H + 1);
-  const long long total = (long long)10 * H * n;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int s = first + (int)(t % n);
-    const int y = (int)((t / n) % H);
-    const int b = (int)(t / ((long long)n * H));
-    float* out = planes + (size_t)b * P * ns_pad;
-    float run = 0.f;
-    out[(size_t)((y + 1) * S) * ns_pad + s] = 0.f;
-    for (int x = 0; x < W; ++x) {
-      const size_t px = (size_t)(y * W + x) * ns_pad + s;
-      if (b == 9 || qangle[px] == b) run = __fadd_rn(run, grad[px]);
-      out[(size_t)((y + 1) * S + x + 1) * ns_pad + s] = run;
+// Gradient magnitude + orientation bin of every pixel of every window (src/HOGfeatures.cpp:163-224: central differences with
+// BORDER_REPLICATE at the crop border, cartToPolar, bin = floor(angle * 9 / pi - 0.5) wrapped).  Windows are stored sample-major
+// (u8 [sample][H][W]) while the outputs are sample-fastest, so a CTA stages a block of rows (+ one halo row on either side) of 32
+// windows in shared memory with coalesced reads -- a warp reads the contiguous bytes of one window at a time -- and computes with
+// lane == sample: shared reads are conflict-free (window stride = 1 mod 32 words), global writes are 128-byte lines.  (One thread
+// per (pixel, sample) reading the windows directly costs four 32-byte sectors per thread: it was 85 % of the HOG K1 time.)
+constexpr int HOG_G_THREADS = 256;
+constexpr int HOG_G_ROWS = 8;             // image rows per staged block
+__global__ void __launch_bounds__(HOG_G_THREADS)
+k_hog_gradient(const uint8_t* __restrict__ imgs, int W, int H, int first, int n, int ns_pad, int wstride /* bytes per staged window, = 4 mod 128 */,
+               float* __restrict__ grad, uint8_t* __restrict__ qangle) {
+  extern __shared__ __align__(16) uint8_t s_px[];          // [32][wstride]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = HOG_G_THREADS / 32;
+  for (int s0 = blockIdx.x * 32; s0 < n; s0 += gridDim.x * 32) {
+    const int ns = min(32, n - s0);
+    for (int y0 = 0; y0 < H; y0 += HOG_G_ROWS) {
+      const int r_lo = max(y0 - 1, 0), r_hi = min(y0 + HOG_G_ROWS + 1, H);      // staged rows [r_lo, r_hi)
+      const int nbytes = (r_hi - r_lo) * W;
+      __syncthreads();
+      for (int k = warp; k < ns; k += nwarps) {
+        const uint8_t* src = imgs + (size_t)(first + s0 + k) * W * H + (size_t)r_lo * W;
+        uint8_t* dst = s_px + (size_t)k * wstride;
+        for (int i = lane; i < nbytes; i += 32) dst[i] = src[i];
+      }
+      __syncthreads();
+      const int rows = min(HOG_G_ROWS, H - y0);
+      if (lane < ns) {
+        const uint8_t* img = s_px + (size_t)lane * wstride;
+        const int s = first + s0 + lane;
+        for (int p = warp; p < rows * W; p += nwarps) {
+          const int yy = p / W, x = p - yy * W, y = y0 + yy;
+          const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+          const float dx = (float)((int)img[(y - r_lo) * W + xp] - (int)img[(y - r_lo) * W + xm]);
+          const float dy = (float)((int)img[(yp - r_lo) * W + x] - (int)img[(ym - r_lo) * W + x]);
+          const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+          float angle = cv_atan2_rad(dy, dx);
+          angle = __fsub_rn(__fmul_rn(angle, (float)(9 / 3.14159265358979323846)), 0.5f);
+          int b = (int)floorf(angle);
+          if (b < 0) b += 9; else if (b >= 9) b -= 9;
+          const size_t o = (size_t)(y * W + x) * ns_pad + s;
+          grad[o] = mag;
+          qangle[o] = (uint8_t)b;
+        }
+      }
     }
   }
 }
 
-// column pass: thread per (plane, x, sample); plane[y+1][x+1] = plane[y][x+1] + rowprefix
-__global__ void k_hog_cols(int W, int H, int first, int n, int ns_pad, float* __restrict__ planes) {
+// Integral histograms (src/HOGfeatures.cpp:226-255: per row a sequential prefix strSum along x, plane[y+1][x+1] = plane[y][x+1] +
+// strSum -- the same f32 additions in the same order) in ONE pass over the planes.  A warp = 32 consecutive samples of one
+// plane (coalesced: the planes are sample-fastest), a CTA = the 10 planes of those samples, so the nine re-reads of a gradient
+// line come from L1; the previous plane row is read back from L2 (written one row earlier by the same thread).  HBM traffic per
+// window: the planes once (190 KB for 48x96) + the gradients once, against 4 plane passes + 10 gradient passes of a separate row
+// and column kernel.
+constexpr int HOG_INT_THREADS = 320;
+__global__ void __launch_bounds__(HOG_INT_THREADS)
+k_hog_integrals(const float* __restrict__ grad, const uint8_t* __restrict__ qangle, int W, int H, int first, int n, int ns_pad,
+                float* __restrict__ planes) {
   const int S = W + 1, P = S * (H + 1);
-  const long long total = (long long)10 * S * n;
-  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
-    const int s = first + (int)(t % n);
-    const int X = (int)((t / n) % S);
-    const int b = (int)(t / ((long long)n * S));
-    float* out = planes + (size_t)b * P * ns_pad;
-    out[(size_t)X * ns_pad + s] = 0.f;
-    if (X == 0) continue;
-    float prev = 0.f;
+  const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
+  for (int s0 = blockIdx.x * 32; s0 < n; s0 += gridDim.x * 32) {
+    const int si = s0 + lane;
+    if (si >= n) continue;
+    const int s = first + si;
+    float* out = planes + (size_t)b * P * ns_pad + s;
+    for (int X = 0; X <= W; ++X) out[(size_t)X * ns_pad] = 0.f;
     for (int y = 0; y < H; ++y) {
-      const size_t o = (size_t)((y + 1) * S + X) * ns_pad + s;
-      prev = __fadd_rn(prev, out[o]);
-      out[o] = prev;
+      const float* prevrow = out + (size_t)(y * S) * ns_pad;
+      float* currow = out + (size_t)((y + 1) * S) * ns_pad;
+      currow[0] = 0.f;
+      float run = 0.f;
+      for (int x = 0; x < W; ++x) {
+        const size_t px = (size_t)(y * W + x) * ns_pad + s;
+        if (b == 9 || qangle[px] == b) run = __fadd_rn(run, grad[px]);
+        currow[(size_t)(x + 1) * ns_pad] = __fadd_rn(prevrow[(size_t)(x + 1) * ns_pad], run);
+      }
     }
   }
 }
@@ -367,16 +386,18 @@ int launch_integrals(cc_ctx* ctx, const EvalStore& st, int first, int n) {
   if (n <= 0) return CC_OK;
   const int last = first + n;
   if (ctx->ftype == CC_FEATURE_HOG) {
-    ScopedTimer tm(ctx, "integral", 3);
+    // bytes per staged window: a multiple of 128 plus 4, so that the 32 windows of a CTA start in 32 different banks
+    const int wstride = ((((HOG_G_ROWS + 2) * ctx->W) + 127) & ~127) + 4;
+    CC_REQUIRE((size_t)32 * wstride <= 200 * 1024, CC_ERR_UNSUPPORTED, "HOG windows wider than %d pixels are not supported", (200 * 1024 / 32 - 132) / (HOG_G_ROWS + 2));
+    ScopedTimer tm(ctx, "integral", 2);
     const size_t npx = (size_t)ctx->W * ctx->H;
     float* grad = nullptr; uint8_t* qa = nullptr;
     CC_CUDA(cudaMallocAsync(&grad, npx * st.ns_pad * sizeof(float), ctx->stream));
     CC_CUDA(cudaMallocAsync(&qa, npx * st.ns_pad, ctx->stream));
-    const int threads = 256;
-    auto blocks = [&](long long total) { return (int)std::min<long long>((total + threads - 1) / threads, (long long)ctx->sm_count * 32); };
-    k_hog_gradient<<<blocks((long long)n * npx), threads, 0, ctx->stream>>>(st.d_imgs, ctx->W, ctx->H, first, n, st.ns_pad, grad, qa);
-    k_hog_rows<<<blocks((long long)10 * ctx->H * n), threads, 0, ctx->stream>>>(grad, qa, ctx->W, ctx->H, first, n, st.ns_pad, st.d_hog);
-    k_hog_cols<<<blocks((long long)10 * (ctx->W + 1) * n), threads, 0, ctx->stream>>>(ctx->W, ctx->H, first, n, st.ns_pad, st.d_hog);
+    CC_CUDA(cudaFuncSetAttribute(k_hog_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * wstride));
+    k_hog_gradient<<<std::max(1, std::min((n + 31) / 32, ctx->sm_count * 8)), HOG_G_THREADS, (size_t)32 * wstride, ctx->stream>>>(
+        st.d_imgs, ctx->W, ctx->H, first, n, st.ns_pad, wstride, grad, qa);
+    k_hog_integrals<<<std::max(1, std::min((n + 31) / 32, ctx->sm_count * 16)), HOG_INT_THREADS, 0, ctx->stream>>>(grad, qa, ctx->W, ctx->H, first, n, st.ns_pad, st.d_hog);
     CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaFreeAsync(grad, ctx->stream));
     CC_CUDA(cudaFreeAsync(qa, ctx->stream));

@@ -1351,6 +1351,14 @@ struct HostTimer {
   }
 };
 
+// windows per batch of the per-window slot path: HOG keeps 10 f32 integral planes per slot (190 KB for 48x96 windows), so the
+// batch is sized to ~8 GB of scratch -- large batches amortise the launches and the host round trip of a batch
+static long long slot_path_max_batch(const cc_ctx* ctx) {
+  if (ctx->ftype != CC_FEATURE_HOG) return 262144;
+  const double slot_bytes = 10.0 * ctx->P * 4 + 6.0 * ctx->W * ctx->H;
+  return (long long)std::min(65536.0, std::max(4096.0, 8.0e9 / slot_bytes));
+}
+
 static bool use_level_path(const cc_ctx* ctx, const MineState* m) {
   return !m->force_slots && !m->stages.empty() && (ctx->ftype == CC_FEATURE_HAAR || ctx->ftype == CC_FEATURE_LBP) && ctx->W <= 255 && ctx->H <= 255;
 }
@@ -1478,6 +1486,7 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
   // much shorter serial chain of rows for k_lvl_build than the whole level.  The window ordinals of a strip are a
   // contiguous range of its level's, so a strip is described like a level (the device code does not distinguish).
   constexpr int STRIP_WIN_ROWS = 8;
+  HostTimer hstrips(ctx, "mine_host_strips");
   std::vector<LevelDesc>& dl = m->strips[slot];
   dl.clear();
   size_t pool_px = 0;
@@ -1525,6 +1534,7 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
   const bool sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
   const bool haar = ctx->ftype == CC_FEATURE_HAAR;
   const bool tilted = haar && m->cascade_tilted;
+  hstrips.stop();
   // Buffers grow with the batches (which grow from stage to stage as the acceptance rate falls): grow by 4x, but not beyond what
   // a full batch will need, so that a cascade reallocates two or three times instead of once per stage (cudaFree / cudaMalloc /
   // cudaMallocHost of gigabytes synchronise the device and take milliseconds each).
@@ -1544,7 +1554,7 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
     m->d_strips[slot] = nullptr; m->h_strips[slot] = nullptr; m->strips_cap[slot] = 0;
     const int cap = (int)grown((size_t)nlv) + 64;
     CC_CUDA(cudaMalloc(&m->d_strips[slot], sizeof(LevelDesc) * cap));
-    CC_CUDA(cudaMallocHost(&m->h_strips[slot], sizeof(LevelDesc) * cap));
+    CC_CUDA(cudaMallocHost(&m->h_strips[slot], (sizeof(LevelDesc) + sizeof(int)) * cap));      // strips, then the builder's launch order
     m->strips_cap[slot] = cap;
   }
   LevelDesc* d_levels = m->d_strips[slot];
@@ -1589,6 +1599,7 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
     int launches = 0;
     if (fused) {
       // three width classes (CTA of 128 / 256 / 512 threads, 4 columns per thread), each tallest-first
+      HostTimer horder(ctx, "mine_host_order");
       std::vector<int> order[3];
       for (int i = 0; i < nlv; ++i)
         if (dl[i].owned) order[dl[i].lw <= 511 ? 0 : dl[i].lw <= 1023 ? 1 : 2].push_back(i);
@@ -1600,7 +1611,14 @@ static int launch_levels(cc_ctx* ctx, MineState* m, Batch& bt, int slot) {
         flat.insert(flat.end(), order[c].begin(), order[c].end());
         off[c + 1] = (int)flat.size();
       }
-      if (!flat.empty()) CC_CUDA(cudaMemcpyAsync(m->d_order, flat.data(), sizeof(int) * flat.size(), cudaMemcpyHostToDevice, ctx->stream));
+      horder.stop();
+      if (!flat.empty()) {
+        // through the pinned staging buffer: an async copy from pageable memory of this size waits for the stream to drain, i.e.
+        // for the batch in flight -- the host would stall for a whole batch and the two-batch pipeline would run in lock step
+        int* h_order = reinterpret_cast<int*>(m->h_strips[slot] + m->strips_cap[slot]);
+        std::memcpy(h_order, flat.data(), sizeof(int) * flat.size());
+        CC_CUDA(cudaMemcpyAsync(m->d_order, h_order, sizeof(int) * flat.size(), cudaMemcpyHostToDevice, ctx->stream));
+      }
       uint32_t* psq = haar ? m->d_psq : nullptr;
       uint32_t* ptl = tilted ? m->d_ptilt : nullptr;
       // widest class first: its levels are the longest chains
@@ -2055,7 +2073,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   const bool level_path = use_level_path(ctx, m);
   const TileGeom tgeom = tile_geometry(ctx, ctx->ftype == CC_FEATURE_HAAR, ctx->ftype == CC_FEATURE_HAAR && m->cascade_tilted);
   const bool tile_path = level_path && m->mode == 3 && tgeom.ok;
-  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : slot_path_max_batch(ctx);
   // Plane path: two batches in flight.  While batch k is evaluated the host assembles and launches batch k+1 -- when
   // the running acceptance rate says that batch k will not complete the stage -- and only then waits for batch k's
   // survivor bitmap; a speculative batch that turns out not to be needed is dropped (its windows count as not read).
@@ -2154,8 +2172,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   auto launch_batch = [&](Batch& bt, int slot) -> int {
     HostTimer he(ctx, "mine_host_eval");
     if (!m->ev_done[slot]) CC_CUDA(cudaEventCreateWithFlags(&m->ev_done[slot], cudaEventDisableTiming));
-    CC_CHECK(launch_levels(ctx, m, bt, slot));
-    CC_CHECK(launch_candidates(ctx, m, bt, slot));
+    { HostTimer h1(ctx, "mine_host_eval_levels"); CC_CHECK(launch_levels(ctx, m, bt, slot)); }
+    { HostTimer h2(ctx, "mine_host_eval_cand"); CC_CHECK(launch_candidates(ctx, m, bt, slot)); }
     CC_CUDA(cudaEventRecord(m->ev_done[slot], ctx->stream));
     m->stat_built += bt.neval;
     return CC_OK;
@@ -2315,7 +2333,7 @@ int cc_mine_positives(cc_ctx* ctx, const uint8_t* host_vec, int vec_count, int c
   long long consumed = 0;
   int got = 0;
   int pos = *vec_pos;
-  const int max_batch = ctx->ftype == CC_FEATURE_HOG ? 8192 : 65536;
+  const int max_batch = (int)std::min<long long>(65536, slot_path_max_batch(ctx));
   std::vector<unsigned> survivors, accepted;
   while (got < count) {
     if (pos >= vec_count) {
@@ -2406,7 +2424,7 @@ int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64
   const bool level_path = use_level_path(ctx, m);
   const TileGeom tgeom = tile_geometry(ctx, ctx->ftype == CC_FEATURE_HAAR, ctx->ftype == CC_FEATURE_HAAR && m->cascade_tilted);
   const bool tile_path = level_path && m->mode == 3 && tgeom.ok;
-  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : ctx->ftype == CC_FEATURE_HOG ? 8192 : 262144;
+  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : slot_path_max_batch(ctx);
   long long total = 0, surv = 0;
   uint64_t digest = 0;                 // order-independent digest of the surviving windows' scan ordinals
   std::vector<unsigned> survivors;

@@ -53,7 +53,7 @@ if rank == 0:
     ccb._lib.check(ctx.lib.cc_mine_get_stats(ctx.h, st6.ctypes.data_as(__import__("ctypes").c_void_p)), "cc_mine_get_stats")
     print("  mining: %d stream windows consumed, %d windows evaluated from pyramid planes, %d cached survivors re-evaluated, %d windows answered by the cache "
           "(%d entries, %.1f MB)" % (st6[0], st6[1], st6[2], st6[3], st6[4], st6[5] / 1e6))
-    for nm in ("mine", "mine_host_assemble", "mine_host_eval", "mine_host_alloc", "mine_host_wait", "mine_host_merge", "mine_host_cut"):
+    for nm in ("mine", "mine_host_assemble", "mine_host_eval", "mine_host_eval_levels", "mine_host_strips", "mine_host_order", "mine_host_alloc", "mine_host_eval_cand", "mine_host_wait", "mine_host_merge", "mine_host_cut"):
         ms, k = ctx.timing(nm)
         print("  timer %-20s %10.1f ms over %d" % (nm, ms, k))
     print("files:", sorted(os.listdir(d))[:6], "...")
