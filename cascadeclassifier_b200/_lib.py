@@ -72,6 +72,7 @@ def _signatures():
         "cc_eval_values": (i32, [vp, vp, i32, i32, i32, vp]),
         "cc_eval_get_integrals": (i32, [vp, i32, vp, vp, vp]),
         "cc_eval_get_hog_planes": (i32, [vp, i32, vp]),
+        "cc_eval_get_hog_planes_compact": (i32, [vp, i32, vp]),
         "cc_eval_get_labels": (i32, [vp, i32, i32, vp]),
         "cc_eval_get_images": (i32, [vp, i32, i32, vp]),
         "cc_boost_set_shard": (i32, [vp, i32, i32]),

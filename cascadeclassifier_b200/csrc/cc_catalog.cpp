@@ -168,9 +168,9 @@ LbpTaps make_lbp_taps(const LbpFeatureH& f, int S) {
   return t;
 }
 
-HogTaps make_hog_taps(const HogFeatureH& f, int S) {
+HogTaps make_hog_taps(const HogFeatureH& f, int S, int G) {
   HogTaps t;
-  const RectI& c0 = f.cell0;
+  const RectI c0 = {f.cell0.x / G, f.cell0.y / G, f.cell0.w / G, f.cell0.h / G};     // exact: all four are multiples of G
   const RectI cells[4] = {{c0.x, c0.y, c0.w, c0.h}, {c0.x + c0.w, c0.y, c0.w, c0.h},
                           {c0.x, c0.y + c0.h, c0.w, c0.h}, {c0.x + c0.w, c0.y + c0.h, c0.w, c0.h}};
   for (int i = 0; i < 4; ++i) {

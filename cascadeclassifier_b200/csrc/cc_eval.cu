@@ -224,33 +224,66 @@ k_hog_gradient(const uint8_t* __restrict__ imgs, int W, int H, int first, int n,
 }
 
 // Integral histograms (src/HOGfeatures.cpp:226-255: per row a sequential prefix strSum along x, plane[y+1][x+1] = plane[y][x+1] +
-// strSum -- the same f32 additions in the same order) in ONE pass over the planes.  A warp = 32 consecutive samples of one
-// plane (coalesced: the planes are sample-fastest), a CTA = the 10 planes of those samples, so the nine re-reads of a gradient
-// line come from L1; the previous plane row is read back from L2 (written one row earlier by the same thread).  HBM traffic per
-// window: the planes once (190 KB for 48x96) + the gradients once, against 4 plane passes + 10 gradient passes of a separate row
-// and column kernel.
+// strSum -- the same f32 additions in the same order), kept COMPACT: every cell corner of the catalog is a multiple of HOG_GRID = 4
+// pixels (block step 4, cell sizes multiples of 8), so only plane entries (4i, 4j) are ever read and only they are stored --
+// 325 instead of 4753 floats per plane for a 48x96 window.  A thread owns one plane of one sample: it carries the running
+// integral of the kept columns (I(y, 4c) for the current y) in a small local array, adds the row prefix when it passes a kept
+// column and writes the array out at every 4th row.  A warp = 32 consecutive samples of one plane (coalesced: the planes are
+// sample-fastest), a CTA = the 10 planes of those samples, so the nine re-reads of a gradient line come from L1.
 constexpr int HOG_INT_THREADS = 320;
+constexpr int HOG_MAX_COLS = 64;          // kept columns: windows up to 252 pixels wide
 __global__ void __launch_bounds__(HOG_INT_THREADS)
 k_hog_integrals(const float* __restrict__ grad, const uint8_t* __restrict__ qangle, int W, int H, int first, int n, int ns_pad,
                 float* __restrict__ planes) {
-  const int S = W + 1, P = S * (H + 1);
+  const int Sc = W / HOG_GRID + 1, Pc = Sc * (H / HOG_GRID + 1);
   const int lane = threadIdx.x & 31, b = threadIdx.x >> 5;
   for (int s0 = blockIdx.x * 32; s0 < n; s0 += gridDim.x * 32) {
     const int si = s0 + lane;
     if (si >= n) continue;
     const int s = first + si;
-    float* out = planes + (size_t)b * P * ns_pad + s;
-    for (int X = 0; X <= W; ++X) out[(size_t)X * ns_pad] = 0.f;
-    for (int y = 0; y < H; ++y) {
-      const float* prevrow = out + (size_t)(y * S) * ns_pad;
-      float* currow = out + (size_t)((y + 1) * S) * ns_pad;
-      currow[0] = 0.f;
+    float* out = planes + (size_t)b * Pc * ns_pad + s;
+    float col[HOG_MAX_COLS];
+    for (int c = 0; c < Sc; ++c) { col[c] = 0.f; out[(size_t)c * ns_pad] = 0.f; }
+    const int rows = (H / HOG_GRID) * HOG_GRID, groups = W / HOG_GRID;
+    for (int y = 0; y < rows; ++y) {
       float run = 0.f;
-      for (int x = 0; x < W; ++x) {
-        const size_t px = (size_t)(y * W + x) * ns_pad + s;
-        if (b == 9 || qangle[px] == b) run = __fadd_rn(run, grad[px]);
-        currow[(size_t)(x + 1) * ns_pad] = __fadd_rn(prevrow[(size_t)(x + 1) * ns_pad], run);
+      for (int c = 0; c < groups; ++c) {
+        float g[HOG_GRID];
+        int q[HOG_GRID];
+#pragma unroll
+        for (int k = 0; k < HOG_GRID; ++k) {
+          const size_t px = (size_t)(y * W + c * HOG_GRID + k) * ns_pad + s;
+          g[k] = grad[px];
+          q[k] = qangle[px];
+        }
+#pragma unroll
+        for (int k = 0; k < HOG_GRID; ++k)
+          if (b == 9 || q[k] == b) run = __fadd_rn(run, g[k]);
+        col[c + 1] = __fadd_rn(col[c + 1], run);                 // plane[y + 1][4 (c + 1)] = plane[y][4 (c + 1)] + strSum
       }
+      if (((y + 1) & (HOG_GRID - 1)) == 0) {
+        float* row = out + (size_t)((y + 1) / HOG_GRID) * Sc * ns_pad;
+        for (int c = 0; c < Sc; ++c) row[(size_t)c * ns_pad] = col[c];
+      }
+    }
+  }
+}
+
+// the full (H + 1) x (W + 1) planes of ONE sample in the reference's layout, for the parity getter (one thread per plane)
+__global__ void k_hog_planes_full(const float* __restrict__ grad, const uint8_t* __restrict__ qangle, int W, int H, int s, int ns_pad,
+                                  float* __restrict__ out10) {
+  const int b = threadIdx.x;
+  if (b >= 10) return;
+  const int S = W + 1, P = S * (H + 1);
+  float* out = out10 + (size_t)b * P;
+  for (int X = 0; X <= W; ++X) out[X] = 0.f;
+  for (int y = 0; y < H; ++y) {
+    float run = 0.f;
+    out[(y + 1) * S] = 0.f;
+    for (int x = 0; x < W; ++x) {
+      const size_t px = (size_t)(y * W + x) * ns_pad + s;
+      if (b == 9 || qangle[px] == b) run = __fadd_rn(run, grad[px]);
+      out[(y + 1) * S + x + 1] = __fadd_rn(out[y * S + x + 1], run);
     }
   }
 }
@@ -320,7 +353,7 @@ __global__ void k_eval_values(EvalView e, const int* __restrict__ vars, int nv, 
 
 EvalView make_eval_view_store(const cc_ctx* ctx, const EvalStore& st) {
   EvalView e;
-  e.ftype = ctx->ftype; e.P = ctx->P; e.ns_pad = st.ns_pad;
+  e.ftype = ctx->ftype; e.P = ctx->ftype == CC_FEATURE_HOG ? ctx->hogP : ctx->P; e.ns_pad = st.ns_pad;
   e.sum = st.d_sum; e.tilted = st.d_tilted; e.nf = st.d_nf; e.hog = st.d_hog;
   e.haar_taps = ctx->d_haar_taps; e.lbp_taps = ctx->d_lbp_taps; e.hog_taps = ctx->d_hog_taps;
   return e;
@@ -363,7 +396,7 @@ int store_alloc(cc_ctx* ctx, EvalStore& st, int max_samples) {
     CC_CUDA(cudaMemsetAsync(st.d_nf, 0, st.ns_pad * sizeof(float), ctx->stream));
   }
   if (ctx->ftype == CC_FEATURE_HOG) {
-    const size_t bytes = (size_t)10 * ctx->P * st.ns_pad * sizeof(float);
+    const size_t bytes = (size_t)10 * ctx->hogP * st.ns_pad * sizeof(float);
     CC_CUDA(cudaMalloc(&st.d_hog, bytes));
     CC_CUDA(cudaMemsetAsync(st.d_hog, 0, bytes, ctx->stream));
   }
@@ -388,7 +421,8 @@ int launch_integrals(cc_ctx* ctx, const EvalStore& st, int first, int n) {
   if (ctx->ftype == CC_FEATURE_HOG) {
     // bytes per staged window: a multiple of 128 plus 4, so that the 32 windows of a CTA start in 32 different banks
     const int wstride = ((((HOG_G_ROWS + 2) * ctx->W) + 127) & ~127) + 4;
-    CC_REQUIRE((size_t)32 * wstride <= 200 * 1024, CC_ERR_UNSUPPORTED, "HOG windows wider than %d pixels are not supported", (200 * 1024 / 32 - 132) / (HOG_G_ROWS + 2));
+    CC_REQUIRE((size_t)32 * wstride <= 200 * 1024 && ctx->hogS <= HOG_MAX_COLS, CC_ERR_UNSUPPORTED, "HOG windows wider than %d pixels are not supported",
+               std::min((200 * 1024 / 32 - 132) / (HOG_G_ROWS + 2), (HOG_MAX_COLS - 1) * HOG_GRID + HOG_GRID - 1));
     ScopedTimer tm(ctx, "integral", 2);
     const size_t npx = (size_t)ctx->W * ctx->H;
     float* grad = nullptr; uint8_t* qa = nullptr;
@@ -448,6 +482,7 @@ int cc_eval_init(cc_ctx* ctx, int feature_type, int haar_mode, int win_w, int wi
   cc::eval_free(ctx);
   ctx->ftype = feature_type; ctx->haar_mode = haar_mode; ctx->W = win_w; ctx->H = win_h;
   ctx->P = (win_w + 1) * (win_h + 1);
+  ctx->hogS = win_w / HOG_GRID + 1; ctx->hogP = ctx->hogS * (win_h / HOG_GRID + 1);
   ctx->max_samples = max_samples;
   ctx->ntiles = (max_samples + TILE - 1) / TILE;
   ctx->ns_pad = ctx->ntiles * TILE;
@@ -472,8 +507,11 @@ int cc_eval_init(cc_ctx* ctx, int feature_type, int haar_mode, int win_w, int wi
   } else {
     ctx->hog = make_hog_catalog(win_w, win_h);
     ctx->num_features = (int)ctx->hog.size(); ctx->feat_size = 36; ctx->max_cat = 0;
+    for (const HogFeatureH& f : ctx->hog)
+      CC_REQUIRE(f.cell0.x % HOG_GRID == 0 && f.cell0.y % HOG_GRID == 0 && f.cell0.w % HOG_GRID == 0 && f.cell0.h % HOG_GRID == 0, CC_ERR_STATE,
+                 "cc_eval_init: HOG cell (%d,%d,%d,%d) is not aligned to the plane grid", f.cell0.x, f.cell0.y, f.cell0.w, f.cell0.h);
     std::vector<HogTaps> taps(ctx->hog.size());
-    for (size_t i = 0; i < ctx->hog.size(); ++i) taps[i] = make_hog_taps(ctx->hog[i], S);
+    for (size_t i = 0; i < ctx->hog.size(); ++i) taps[i] = make_hog_taps(ctx->hog[i], ctx->hogS, HOG_GRID);
     CC_CUDA(cudaMalloc(&ctx->d_hog_taps, std::max<size_t>(1, taps.size()) * sizeof(HogTaps)));
     CC_CUDA(cudaMemcpyAsync(ctx->d_hog_taps, taps.data(), taps.size() * sizeof(HogTaps), cudaMemcpyHostToDevice, ctx->stream));
     CC_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -588,10 +626,34 @@ int cc_eval_get_integrals(cc_ctx* ctx, int si, int32_t* sum, int32_t* tilted, fl
 
 int cc_eval_get_hog_planes(cc_ctx* ctx, int si, float* planes10) {
   CC_REQUIRE(ctx && ctx->ftype == CC_FEATURE_HOG, CC_ERR_STATE, "cc_eval_get_hog_planes: not a HOG evaluator");
-  CC_REQUIRE(si >= 0 && si < ctx->max_samples, CC_ERR_BAD_ARG, "cc_eval_get_hog_planes: sample %d out of range", si);
+  CC_REQUIRE(si >= 0 && si < ctx->max_samples && planes10, CC_ERR_BAD_ARG, "cc_eval_get_hog_planes: sample %d out of range", si);
   CC_CUDA(cudaSetDevice(ctx->device));
-  CC_CUDA(cudaMemcpy2DAsync(planes10, sizeof(float), ctx->d_hog + si, (size_t)ctx->ns_pad * sizeof(float), sizeof(float),
-                            (size_t)10 * ctx->P, cudaMemcpyDeviceToHost, ctx->stream));
+  // the resident planes are compact (every HOG_GRID-th row / column); the getter returns the reference's full layout, computed
+  // here for this one sample with the same gradient kernel and the same order of additions
+  const size_t npx = (size_t)ctx->W * ctx->H;
+  const int wstride = ((((HOG_G_ROWS + 2) * ctx->W) + 127) & ~127) + 4;
+  float *grad = nullptr, *full = nullptr;
+  uint8_t* qa = nullptr;
+  CC_CUDA(cudaMallocAsync(&grad, npx * ctx->ns_pad * sizeof(float), ctx->stream));
+  CC_CUDA(cudaMallocAsync(&qa, npx * ctx->ns_pad, ctx->stream));
+  CC_CUDA(cudaMallocAsync(&full, (size_t)10 * ctx->P * sizeof(float), ctx->stream));
+  CC_CUDA(cudaFuncSetAttribute(k_hog_gradient, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * wstride));
+  k_hog_gradient<<<1, HOG_G_THREADS, (size_t)32 * wstride, ctx->stream>>>(ctx->d_imgs, ctx->W, ctx->H, si, 1, ctx->ns_pad, wstride, grad, qa);
+  k_hog_planes_full<<<1, 32, 0, ctx->stream>>>(grad, qa, ctx->W, ctx->H, si, ctx->ns_pad, full);
+  CC_CUDA(cudaGetLastError());
+  CC_CUDA(cudaMemcpyAsync(planes10, full, (size_t)10 * ctx->P * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  CC_CUDA(cudaFreeAsync(grad, ctx->stream)); CC_CUDA(cudaFreeAsync(qa, ctx->stream)); CC_CUDA(cudaFreeAsync(full, ctx->stream));
+  return CC_OK;
+}
+
+/* the resident compact planes of one sample: 10 planes of (H / 4 + 1) x (W / 4 + 1) entries = the reference's planes at rows / columns 0, 4, 8, ... */
+int cc_eval_get_hog_planes_compact(cc_ctx* ctx, int si, float* planes10c) {
+  CC_REQUIRE(ctx && ctx->ftype == CC_FEATURE_HOG, CC_ERR_STATE, "cc_eval_get_hog_planes_compact: not a HOG evaluator");
+  CC_REQUIRE(si >= 0 && si < ctx->max_samples && planes10c, CC_ERR_BAD_ARG, "cc_eval_get_hog_planes_compact: sample %d out of range", si);
+  CC_CUDA(cudaSetDevice(ctx->device));
+  CC_CUDA(cudaMemcpy2DAsync(planes10c, sizeof(float), ctx->d_hog + si, (size_t)ctx->ns_pad * sizeof(float), sizeof(float),
+                            (size_t)10 * ctx->hogP, cudaMemcpyDeviceToHost, ctx->stream));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
   return CC_OK;
 }

@@ -39,6 +39,7 @@ void set_error(const char* fmt, ...);
   } while (0)
 
 constexpr int TILE = 32;   // samples per integral tile (one warp lane per sample)
+constexpr int HOG_GRID = 4;  // HOG block step: every cell corner of the catalog is a multiple of it (src/HOGfeatures.cpp:67-106)
 constexpr int CC_MAX_RANKS = 72;   // ranks of one communicator (one NVLink domain: 8 on a B200 box, 72 on an NVL72 rack)
 
 // ---- host-side catalogs -------------------------------------------------------------------
@@ -85,7 +86,7 @@ std::vector<LbpFeatureH> make_lbp_catalog(int W, int H);
 std::vector<HogFeatureH> make_hog_catalog(int W, int H);
 HaarTaps make_haar_taps(const HaarFeatureH& f, int stride);
 LbpTaps make_lbp_taps(const LbpFeatureH& f, int stride);
-HogTaps make_hog_taps(const HogFeatureH& f, int stride);
+HogTaps make_hog_taps(const HogFeatureH& f, int stride, int grid);      // grid: the planes keep every grid-th row / column (coordinates are divided by it)
 
 // ---- timing -------------------------------------------------------------------------------
 struct TimerSlot { double ms = 0; int64_t launches = 0; };
@@ -137,7 +138,8 @@ struct cc_ctx {
   int32_t* d_sum = nullptr;        // tiles [ntiles][P][32]
   int32_t* d_tilted = nullptr;     // tiles (Haar ALL only)
   float* d_nf = nullptr;           // [ntiles*32]
-  float* d_hog = nullptr;          // [10][P][ns_pad]  sample-fastest
+  float* d_hog = nullptr;          // [10][hogP][ns_pad]  sample-fastest; HOG planes keep only the rows / columns features can touch (multiples of HOG_GRID)
+  int hogS = 0, hogP = 0;          // compact plane: row stride W / HOG_GRID + 1, entries hogS * (H / HOG_GRID + 1)
   int ns_pad = 0;                  // ntiles*32
   cc::HaarTaps* d_haar_taps = nullptr;   // [num_features]
   cc::LbpTaps* d_lbp_taps = nullptr;

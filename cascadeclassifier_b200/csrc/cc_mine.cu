@@ -1351,12 +1351,13 @@ struct HostTimer {
   }
 };
 
-// windows per batch of the per-window slot path: HOG keeps 10 f32 integral planes per slot (190 KB for 48x96 windows), so the
-// batch is sized to ~8 GB of scratch -- large batches amortise the launches and the host round trip of a batch
+// windows per batch of the per-window slot path: HOG keeps 10 compact f32 integral planes per slot + 5 bytes of gradient scratch per
+// pixel (36 KB for 48x96 windows), so the batch is sized to ~8 GB of scratch, at most 256 K windows -- large batches amortise the
+// launches and the host round trip of a batch
 static long long slot_path_max_batch(const cc_ctx* ctx) {
   if (ctx->ftype != CC_FEATURE_HOG) return 262144;
-  const double slot_bytes = 10.0 * ctx->P * 4 + 6.0 * ctx->W * ctx->H;
-  return (long long)std::min(65536.0, std::max(4096.0, 8.0e9 / slot_bytes));
+  const double slot_bytes = 10.0 * ctx->hogP * 4 + 6.0 * ctx->W * ctx->H;
+  return (long long)std::min(262144.0, std::max(4096.0, 8.0e9 / slot_bytes));
 }
 
 static bool use_level_path(const cc_ctx* ctx, const MineState* m) {
@@ -2333,7 +2334,7 @@ int cc_mine_positives(cc_ctx* ctx, const uint8_t* host_vec, int vec_count, int c
   long long consumed = 0;
   int got = 0;
   int pos = *vec_pos;
-  const int max_batch = (int)std::min<long long>(65536, slot_path_max_batch(ctx));
+  const int max_batch = (int)std::min<long long>(65536, slot_path_max_batch(ctx));      // positives: the .vec block is small
   std::vector<unsigned> survivors, accepted;
   while (got < count) {
     if (pos >= vec_count) {

@@ -1162,7 +1162,7 @@ int cc_boost_precalc(cc_ctx* ctx, int num_samples) {
   } else {
     ScopedTimer tm(ctx, "precalc", 1);
     const int blocks = ctx->sm_count * 8;
-    k_precalc_hog<<<blocks, 256, 0, ctx->stream>>>(ctx->d_hog, ctx->d_hog_taps, ctx->row0, ctx->nrows, ctx->d_fval, n_stride, P, ctx->ns_pad,
+    k_precalc_hog<<<blocks, 256, 0, ctx->stream>>>(ctx->d_hog, ctx->d_hog_taps, ctx->row0, ctx->nrows, ctx->d_fval, n_stride, ctx->hogP, ctx->ns_pad,
                                                    ntiles_used);
     CC_CUDA(cudaGetLastError());
   }

@@ -228,6 +228,13 @@ class CvFeatureEvaluator:
         check(self.ctx.lib.cc_eval_get_hog_planes(self.ctx.h, int(si), _p(out)), "cc_eval_get_hog_planes")
         return out
 
+    def hogPlanesCompact(self, si):
+        """the resident HOG planes: rows / columns 0, 4, 8, ... of hogPlanes() -> [10][H // 4 + 1][W // 4 + 1]"""
+        W, H = self.winSize
+        out = np.zeros((10, H // 4 + 1, W // 4 + 1), np.float32)
+        check(self.ctx.lib.cc_eval_get_hog_planes_compact(self.ctx.h, int(si), _p(out)), "cc_eval_get_hog_planes_compact")
+        return out
+
     def images(self, first, n):
         W, H = self.winSize
         out = np.zeros((n, H, W), np.uint8)

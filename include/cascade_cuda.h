@@ -74,7 +74,10 @@ int cc_eval_value(cc_ctx* ctx, int var_idx, int sample_idx, float* out);
 int cc_eval_values(cc_ctx* ctx, const int32_t* var_idx, int nv, int s0, int ns, float* out);
 /* debug / parity getters in the reference's own layout: one (H+1)*(W+1) row per sample */
 int cc_eval_get_integrals(cc_ctx* ctx, int sample_idx, int32_t* sum, int32_t* tilted, float* norm_factor);
-int cc_eval_get_hog_planes(cc_ctx* ctx, int sample_idx, float* planes10);   /* 9 hist planes + norm */
+int cc_eval_get_hog_planes(cc_ctx* ctx, int sample_idx, float* planes10);   /* 9 hist planes + norm, (H+1) x (W+1) each as in the reference */
+/* what is resident: the same planes at rows / columns 0, 4, 8, ... only ((H/4+1) x (W/4+1) each) -- every cell corner of the HOG
+ * catalog is a multiple of the block step 4 (src/HOGfeatures.cpp:67-106) */
+int cc_eval_get_hog_planes_compact(cc_ctx* ctx, int sample_idx, float* planes10c);
 int cc_eval_get_labels(cc_ctx* ctx, int first_idx, int n, float* cls);      /* getCls() */
 int cc_eval_get_images(cc_ctx* ctx, int first_idx, int n, uint8_t* imgs);   /* the cached u8 windows */
 

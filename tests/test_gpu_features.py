@@ -107,14 +107,20 @@ def test_flat_image_invariants(gpu_ctx):
     assert isinstance(ev, ccb.CvFeatureEvaluator)
 
 
-def test_hog_planes_match_oracle(gpu_ctx):
-    imgs, labels = make_samples(3, 4, 48, 96)
-    ev = _gpu_eval(orc.HOG, 0, 48, 96, 7, gpu_ctx)
+@pytest.mark.parametrize("W,H", [(48, 96), (64, 64), (50, 38)])
+def test_hog_planes_match_oracle(gpu_ctx, W, H):
+    """the 9 integral histograms + the norm plane, bit for bit: in the reference's full layout (parity getter) and as they are
+    resident -- only rows / columns that are multiples of the block step 4, the only entries a HOG feature can touch"""
+    imgs, labels = make_samples(20, 30, W, H)
+    ev = _gpu_eval(orc.HOG, 0, W, H, 50, gpu_ctx)
     ev.setImages(imgs, labels)
-    for si in (0, 6):
+    for si in (0, 6, 31, 32, 49):
         g = ev.hogPlanes(si)
         r = orc.hog_planes(imgs[si]).reshape(10, -1)
         assert np.array_equal(g, r)
+        c = ev.hogPlanesCompact(si)
+        full = r.reshape(10, H + 1, W + 1)
+        assert np.array_equal(c, full[:, ::4, ::4][:, :H // 4 + 1, :W // 4 + 1])
 
 
 @pytest.mark.parametrize("ftype,mode,W,H,npos,nneg", [(orc.HAAR, orc.BASIC, 24, 24, 150, 317), (orc.HAAR, orc.ALL, 24, 24, 90, 200),
