@@ -1300,13 +1300,17 @@ struct CachedPyr {
   size_t cand0 = 0, ncand = 0;      // its cached survivors in Batch::cand
 };
 struct MissPyr { uint64_t key = 0; long long base = 0, nwin = 0; bool complete = false; };      // evaluated pyramid that may enter the cache
-struct Seg { long long base, nwin; int kind, idx; };      // kind 0: levels[idx] (a level part), 1: pyrs[idx]
+// A run of consecutive cached pyramids WITHOUT survivors (most pyramids in late stages): only its extent matters -- no window of it
+// can be accepted or re-evaluated -- so the run is one record however long it is; a stop position inside it is found by walking.
+struct EmptyRun { NegStream start, after; long long base = 0, nwin = 0; int count = 0; };
+struct Seg { long long base, nwin; int kind, idx; };      // kind 0: levels[idx] (a level part), 1: pyrs[idx], 2: runs[idx]
 struct Batch {
   std::vector<LevelDesc> levels;
   std::vector<NegStream> before;    // stream state on the first window taken from each level part
   std::vector<NegStream> after;     // stream state right after the last window of each level part (level granularity)
   std::vector<long long> lv_stream; // stream ordinal of the first window taken from each level part
   std::vector<CachedPyr> pyrs;
+  std::vector<EmptyRun> runs;
   std::vector<MissPyr> miss;
   std::vector<Seg> segs;
   std::vector<long long> cand;      // stream ordinals of the cached survivors (ascending)
@@ -1759,6 +1763,7 @@ static int build_gather_plan(const Batch& bt, const long long* ords, size_t n, G
     while (si + 1 < bt.segs.size() && bt.segs[si + 1].base <= o) ++si;
     const Seg& sg = bt.segs[si];
     CC_REQUIRE(o >= sg.base && o < sg.base + sg.nwin, CC_ERR_STATE, "mining: stream ordinal %lld outside the batch", o);
+    CC_REQUIRE(sg.kind != 2, CC_ERR_STATE, "mining: a window of a survivor-free cached pyramid was requested");
     if (sg.kind == 0) {
       const LevelDesc& L = bt.levels[sg.idx];
       if (cur_seg != (int)si) {
@@ -2110,6 +2115,22 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
         const PyrEntry* ep = m->cache.lookup(cur.src, cur.offX, cur.offY, (int)m->bgs.size());
         if (ep && ep->n_stages <= nstages) {
           const PyrEntry& e = *ep;
+          if (e.surv.empty()) {
+            if (bt.segs.empty() || bt.segs.back().kind != 2) {
+              EmptyRun r;
+              r.start = cur; r.base = bt.nwin;
+              bt.segs.push_back(Seg{bt.nwin, 0, 2, (int)bt.runs.size()});
+              bt.runs.push_back(r);
+            }
+            EmptyRun& r = bt.runs.back();
+            r.nwin += e.nwin; r.count += 1;
+            bt.segs.back().nwin = r.nwin;
+            bt.nwin += e.nwin;
+            more = cur.nextImg();
+            r.after = cur;
+            open_pyr = -1;
+            continue;
+          }
           CachedPyr cp;
           cp.start = cur; cp.base = bt.nwin; cp.nwin = e.nwin; cp.key = key; cp.cand0 = bt.cand.size(); cp.ncand = e.surv.size();
           for (const uint32_t o : e.surv) {
@@ -2165,6 +2186,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   auto batch_end_state = [&](const Batch& bt) -> NegStream {
     const Seg& sg = bt.segs.back();
     if (sg.kind == 0) return bt.after[sg.idx];
+    if (sg.kind == 2) return bt.runs[sg.idx].after;
     NegStream a = bt.pyrs[sg.idx].start;
     a.nextImg();
     return a;
@@ -2268,6 +2290,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       }
       if (nwin > 0) accept_rate = std::max((double)surv64.size() / (double)nwin, 1e-12);
       for (const CachedPyr& cp : bt.pyrs) if (cp.base <= stop_after) m->stat_skipped += std::min(cp.nwin, stop_after + 1 - cp.base);
+      for (const EmptyRun& r : bt.runs) if (r.base <= stop_after) m->stat_skipped += std::min(r.nwin, stop_after + 1 - r.base);
       if (!stopped) { ns = batch_end_state(bt); stream_ok = more; continue; }
     }
     // ---- stopped inside this batch: reader state right after window `stop_after` ----
@@ -2293,6 +2316,30 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
           NegStream st = bt.before[sg.idx];
           st.pointY = st.offY + (int)(k / L.nx) * L.step_y;
           st.pointX = st.offX + (int)(k % L.nx) * L.step_x;
+          ns = st;
+        }
+      } else if (sg.kind == 2) {
+        // inside a run of survivor-free cached pyramids: walk to the pyramid that holds the stop position, then to its level
+        const EmptyRun& r = bt.runs[sg.idx];
+        long long k = stop_after - r.base + 1;                             // windows of the run consumed
+        if (k >= r.nwin) {
+          ns = r.after;
+          if (si + 1 == bt.segs.size()) stream_ok = more;
+        } else {
+          NegStream st = r.start;
+          for (;;) {
+            const PyrEntry* e = m->cache.lookup(st.src, st.offX, st.offY, (int)m->bgs.size());
+            CC_REQUIRE(e, CC_ERR_STATE, "mining: cached pyramid vanished while a batch was in flight");
+            if (k < e->nwin) break;
+            k -= e->nwin;
+            CC_REQUIRE(st.nextImg(), CC_ERR_STATE, "mining: stream ended inside a cached run");
+          }
+          long long lb = 0, ln = (long long)st.countX() * st.countY();
+          while (k >= lb + ln) { lb += ln; level_after(st); ln = (long long)st.countX() * st.countY(); }
+          const int nx = st.countX();
+          const long long kk = k - lb;
+          st.pointY = st.offY + (int)(kk / nx) * st.stepY();
+          st.pointX = st.offX + (int)(kk % nx) * st.stepX();
           ns = st;
         }
       } else {
