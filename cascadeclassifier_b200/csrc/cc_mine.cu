@@ -1319,6 +1319,8 @@ struct Batch {
   long long nwin = 0;               // stream windows
   long long neval = 0;              // windows in `levels`
   size_t pool_px = 0;
+  bool has_stale = false;           // some cached pyramid of the batch has stages to run on its survivors ...
+  uint64_t first_stale_key = 0;     // ... the first of them: the batch ends before the stream returns to it (see assemble)
 };
 
 // windows the fast path may put in one batch (pyramid pixels ~ 154 per window at 1920x1080 -> ~2 GB of planes)
@@ -2131,6 +2133,13 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
             open_pyr = -1;
             continue;
           }
+          if (e.n_stages < nstages) {
+            // A stale entry is brought up to date when the batch that re-evaluates it has finished.  The stream returns to the
+            // same pyramids in the same order, so a batch that ran on past its first stale pyramid would re-evaluate the same
+            // stale lists once per list cycle it spans: end the batch there instead -- the next one finds the entries fresh.
+            if (bt.has_stale && key == bt.first_stale_key) break;
+            if (!bt.has_stale) { bt.has_stale = true; bt.first_stale_key = key; }
+          }
           CachedPyr cp;
           cp.start = cur; cp.base = bt.nwin; cp.nwin = e.nwin; cp.key = key; cp.cand0 = bt.cand.size(); cp.ncand = e.surv.size();
           for (const uint32_t o : e.surv) {
@@ -2257,7 +2266,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       if (got < count && taken == nwin) { ns = batch_end_state(bt); stream_ok = more; continue; }
     } else {
       if (pipelined) {
-        if (more && accept_rate > 0 && accept_rate * (double)bt.nwin < 0.5 * (double)(count - got)) {
+        // (no speculation while this batch is bringing stale cache entries up to date: the next batch would re-evaluate the same lists)
+        if (more && accept_rate > 0 && accept_rate * (double)bt.nwin < 0.5 * (double)(count - got) && !bt.has_stale) {
           assemble(batch_end_state(bt), pre, pre_more);
           if (!pre.segs.empty()) {
             CC_CHECK(launch_batch(pre, slot ^ 1));
