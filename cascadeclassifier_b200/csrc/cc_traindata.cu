@@ -646,7 +646,6 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
   __shared__ float red[4][SORT_WARPS];
   __shared__ uint32_t warp_tot[SORT_WARPS];
   __shared__ float warp_cost[SORT_WARPS];
-  __shared__ int s_chunk;                                // next 32-position chunk of the ranking phase (claimed by whole warps)
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
   uint32_t comp_s = (uint32_t)__cvta_generic_to_shared(comp), cnt_s = (uint32_t)__cvta_generic_to_shared(cnt);
   asm volatile("" : "+r"(comp_s), "+r"(cnt_s));          // opaque: kept in registers instead of being re-derived from SR_CgaCtaId in the loops
@@ -676,7 +675,6 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
     }
     __syncthreads();                                   // the previous row's ranking has finished reading comp / cnt
     if (lane == 0) { red[0][warp] = mn; red[1][warp] = mx; red[2][warp] = sm; red[3][warp] = sq; }
-    if (t == 0) s_chunk = 0;
     {
       uint4* c4 = reinterpret_cast<uint4*>(cnt);
       for (int i = t; i < B / 4; i += SORT_THREADS) c4[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -781,17 +779,8 @@ k_sort_rows_bucket(const float* __restrict__ fval, int n_stride, int N, int nrow
     // comparison on the otherwise idle FP64 pipe.  Shared memory is addressed through 32-bit shared-window addresses. ----
     uint16_t* drow = sidx + (size_t)row * n_stride;
     float* vrow = sval + (size_t)row * n_stride;
-    // chunks of 32 consecutive positions are claimed by whole warps from a shared counter: the ranking time of a chunk depends
-    // on the bucket sizes it meets, and a static assignment leaves the CTA waiting at the next barrier for its unluckiest warp
-    const int nchunks = (N + 31) >> 5;
 #pragma unroll 1
-    for (;;) {
-      int chunk = 0;
-      if (lane == 0) chunk = atomicAdd(&s_chunk, 1);
-      chunk = __shfl_sync(0xffffffffu, chunk, 0);
-      if (chunk >= nchunks) break;
-      const int p = chunk * 32 + lane;
-      if (p >= N) continue;
+    for (int p = t; p < N; p += SORT_THREADS) {
       double cd;
       asm volatile("ld.shared.f64 %0, [%1];" : "=d"(cd) : "r"(comp_s + 8u * (uint32_t)p));
       const unsigned long long c = (unsigned long long)__double_as_longlong(cd);
