@@ -152,28 +152,6 @@ k_integral_tiles(const uint8_t* __restrict__ imgs, int W, int H, int first, int 
 // ------------------------------------------------------------------------------------------------
 // HOG integral histograms (CvHOGEvaluator::integralHistogram, src/HOGfeatures.cpp:163-256)
 // ------------------------------------------------------------------------------------------------
-// cv::fastAtan32f polynomial (OpenCV 4.x core/mathfuncs_core.simd.hpp), radians; explicit _rn
-// intrinsics keep the operation order free of FMA contraction.
-__device__ __forceinline__ float cv_atan2_rad(float y, float x) {
-  const float deg = (float)(180.0 / 3.14159265358979323846);
-  const float p1 = 0.9997878412794807f * deg, p3 = -0.3258083974640975f * deg, p5 = 0.1555786518463281f * deg,
-              p7 = -0.04432655554792128f * deg;
-  float ax = fabsf(x), ay = fabsf(y), a, c, c2;
-  const float eps = (float)2.2204460492503131e-16;
-  if (ax >= ay) {
-    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
-  } else {
-    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
-    c2 = __fmul_rn(c, c);
-    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
-  }
-  if (x < 0) a = __fsub_rn(180.f, a);
-  if (y < 0) a = __fsub_rn(360.f, a);
-  return __fmul_rn(a, (float)(3.14159265358979323846 / 180.0));
-}
-
 // gradient magnitude + orientation bin per pixel; outputs are [pixel][ns_pad] (sample-fastest)
 // Gradient magnitude + orientation bin of every pixel of every window (src/HOGfeatures.cpp:163-224: central differences with
 // BORDER_REPLICATE at the crop border, cartToPolar, bin = floor(angle * 9 / pi - 0.5) wrapped).  Windows are stored sample-major
@@ -209,11 +187,9 @@ k_hog_gradient(const uint8_t* __restrict__ imgs, int W, int H, int first, int n,
           const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
           const float dx = (float)((int)img[(y - r_lo) * W + xp] - (int)img[(y - r_lo) * W + xm]);
           const float dy = (float)((int)img[(yp - r_lo) * W + x] - (int)img[(ym - r_lo) * W + x]);
-          const float mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
-          float angle = cv_atan2_rad(dy, dx);
-          angle = __fsub_rn(__fmul_rn(angle, (float)(9 / 3.14159265358979323846)), 0.5f);
-          int b = (int)floorf(angle);
-          if (b < 0) b += 9; else if (b >= 9) b -= 9;
+          float mag;
+          int b;
+          hog_mag_bin(dx, dy, mag, b);
           const size_t o = (size_t)(y * W + x) * ns_pad + s;
           grad[o] = mag;
           qangle[o] = (uint8_t)b;

@@ -185,6 +185,42 @@ struct cc_ctx {
   int comm_rank = 0, comm_world = 1;
 };
 
+#if defined(__CUDACC__)
+namespace cc {
+// cv::fastAtan32f polynomial (OpenCV 4.x core/mathfuncs_core.simd.hpp), radians; explicit _rn
+// intrinsics keep the operation order free of FMA contraction.
+__device__ __forceinline__ float cv_atan2_rad(float y, float x) {
+  const float deg = (float)(180.0 / 3.14159265358979323846);
+  const float p1 = 0.9997878412794807f * deg, p3 = -0.3258083974640975f * deg, p5 = 0.1555786518463281f * deg,
+              p7 = -0.04432655554792128f * deg;
+  float ax = fabsf(x), ay = fabsf(y), a, c, c2;
+  const float eps = (float)2.2204460492503131e-16;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, eps));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return __fmul_rn(a, (float)(3.14159265358979323846 / 180.0));
+}
+
+// gradient magnitude and orientation bin of one pixel from its central differences (src/HOGfeatures.cpp:187-222: cartToPolar,
+// bin = floor(angle * 9 / pi - 0.5) wrapped into [0, 9)); shared by K1 (k_hog_gradient) and the HOG miner (cc_mine.cu)
+__device__ __forceinline__ void hog_mag_bin(float dx, float dy, float& mag, int& b) {
+  mag = __fsqrt_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)));
+  float angle = cv_atan2_rad(dy, dx);
+  angle = __fsub_rn(__fmul_rn(angle, (float)(9 / 3.14159265358979323846)), 0.5f);
+  b = (int)floorf(angle);
+  if (b < 0) b += 9; else if (b >= 9) b -= 9;
+}
+}  // namespace cc
+#endif
+
 namespace cc {
 // timing helpers: bracket a kernel family with events on ctx->stream
 struct ScopedTimer {      // do not nest (the inner interval would be counted twice)

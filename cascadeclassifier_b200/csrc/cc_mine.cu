@@ -226,6 +226,225 @@ __global__ void k_copy_slots(const uint8_t* __restrict__ src, const unsigned int
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// HOG miner: gradients once per pyramid level, integral histograms and cascade per window inside one CTA.
+//
+// CvHOGEvaluator::integralHistogram works on the window crop (src/HOGfeatures.cpp:163-256): central differences with
+// BORDER_REPLICATE at the crop border, magnitude + orientation bin per pixel, then per bin an f32 integral image whose
+// additions run from the crop's first column / first row.  The integrals therefore cannot be shared between windows (f32 sums
+// depend on where they start), but the gradient of every pixel that is NOT on the window's 1-pixel ring is a function of the
+// level pixels alone: k_hog_level_grad computes it once per level pixel, and k_hog_window_cascade -- one CTA per window --
+// takes the interior of its window from those planes, recomputes the ring with the replicated border, builds the ten
+// compact integral planes in shared memory with the additions of k_hog_integrals in the same order (row prefix, then
+// column accumulation) and runs the cascade on them with early exit.  Nothing per window ever goes to HBM: the slot path
+// writes and re-reads ~70 KB per 48x96 window (pixels, gradients, planes).  Survivors == the slot path's
+// (test_hog_miner_matches_slot_path), which is the literal setImage + predict arithmetic.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_hog_level_grad(const LevelDesc* __restrict__ levels, int nlevels, long long total_px, const uint8_t* __restrict__ pool,
+                                 float* __restrict__ gmag, uint8_t* __restrict__ gbin) {
+  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total_px; p += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = nlevels - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].px_off <= p) lo = mid; else hi = mid - 1; }
+    const LevelDesc& L = levels[lo];
+    const int q = (int)(p - L.px_off);
+    const int y = q / L.ppitch, x = q - y * L.ppitch;
+    if (x >= L.lw) continue;
+    // pixels on the border of the level are only ever ring pixels of a window (recomputed there); clamped here to stay in bounds
+    const uint8_t* base = pool + L.px_off;
+    const int xm = max(x - 1, 0), xp = min(x + 1, L.lw - 1), ym = max(y - 1, 0), yp = min(y + 1, L.lh - 1);
+    const float dx = (float)((int)base[(size_t)y * L.ppitch + xp] - (int)base[(size_t)y * L.ppitch + xm]);
+    const float dy = (float)((int)base[(size_t)yp * L.ppitch + x] - (int)base[(size_t)ym * L.ppitch + x]);
+    float mag;
+    int b;
+    hog_mag_bin(dx, dy, mag, b);
+    gmag[p] = mag;
+    gbin[p] = (uint8_t)b;
+  }
+}
+
+// shared-memory geometry of k_hog_window_cascade (strides chosen odd in 32-bit words: a thread per row walks its row
+// without bank conflicts)
+struct HogWinGeom {
+  int W, H;
+  int ms;          // row stride of the magnitude tile, floats (odd)
+  int bs;          // row stride of the bin tile, bytes (a multiple of 4, odd in words)
+  int ss;          // row stride of the row-prefix array, floats (odd)
+  int Sc, Pc;      // compact plane: row stride W / HOG_GRID + 1, entries per plane
+  int groups, rows;
+  int off_bin, off_S;
+  size_t smem;
+};
+static HogWinGeom hog_win_geometry(int W, int H) {
+  HogWinGeom g;
+  g.W = W; g.H = H;
+  g.ms = W | 1;
+  g.bs = (((W + 3) / 4) | 1) * 4;
+  g.groups = W / HOG_GRID; g.rows = (H / HOG_GRID) * HOG_GRID;
+  g.ss = (g.groups * 10) | 1;
+  g.Sc = W / HOG_GRID + 1; g.Pc = g.Sc * (H / HOG_GRID + 1);
+  const size_t tile = std::max((size_t)H * g.ms * 4, (size_t)10 * g.Pc * 4);      // the planes reuse the magnitude tile
+  g.off_bin = (int)((tile + 15) & ~(size_t)15);
+  g.off_S = (int)(((size_t)g.off_bin + (size_t)H * g.bs + 15) & ~(size_t)15);
+  g.smem = (size_t)g.off_S + (size_t)g.rows * g.ss * 4;
+  return g;
+}
+
+constexpr int HOGW_THREADS = 256;
+constexpr int HOGW_LB = 4;            // rows per load batch of a warp
+constexpr int HOGW_RB = 2;            // ring pixels per load batch of a thread
+// run += g if the pixel's bin is `want` -- one predicated FADD (written in PTX: the compiler turns the C++ form of nine
+// mutually exclusive tests into a divergent decision tree)
+__device__ __forceinline__ void hog_add_if(float& run, uint32_t q, uint32_t want, float gg) {
+  asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.rn.f32 %0, %0, %3;\n\t}" : "+f"(run) : "r"(q), "r"(want), "f"(gg));
+}
+__global__ void __launch_bounds__(HOGW_THREADS, 3)
+k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const uint8_t* __restrict__ pool, const float* __restrict__ gmag,
+                     const uint8_t* __restrict__ gbin, HogWinGeom g, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
+                     const int* __restrict__ tree_first, const DevStageRef* __restrict__ stages, int nstages, long long nwin,
+                     unsigned int* __restrict__ surv_count, unsigned int* __restrict__ surv, unsigned int surv_cap) {
+  extern __shared__ __align__(16) unsigned char hw_smem[];
+  float* smag = reinterpret_cast<float*>(hw_smem);                  // [H][ms]
+  float* planes = smag;                                             // [10][Pc] once the row prefixes are taken
+  uint8_t* sbin = hw_smem + g.off_bin;                              // [H][bs]
+  float* S = reinterpret_cast<float*>(hw_smem + g.off_S);           // [rows][ss]: row prefix of plane b behind pixel group c at [c * 10 + b]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NW = HOGW_THREADS / 32;
+  const int W = g.W, H = g.H;
+  for (long long wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
+    int lo = 0, hi = nlevels - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= wi) lo = mid; else hi = mid - 1; }
+    const LevelDesc& L = levels[lo];
+    const long long k = wi - L.w_base + L.w_skip;
+    const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
+    const int pp = L.ppitch;
+    const long long org = L.px_off + (long long)(L.y0 + iy * L.step_y) * pp + (L.x0 + ix * L.step_x);
+    __syncthreads();                                   // the previous window's cascade has finished reading the planes
+    // ---- interior: the level gradient; ring: central differences with the window's replicated border ----
+    // (loads are issued in batches of HOGW_LB rows / ring pixels before their first use: one L2 round trip per batch, not per row)
+    for (int xc = 1; xc < W - 1; xc += 32) {
+      const int x = xc + lane;
+      for (int y0 = 1 + warp; y0 < H - 1; y0 += NW * HOGW_LB) {
+        float mv[HOGW_LB];
+        uint8_t bv[HOGW_LB];
+#pragma unroll
+        for (int r = 0; r < HOGW_LB; ++r) {
+          const int y = y0 + r * NW;
+          if (y < H - 1 && x < W - 1) { mv[r] = gmag[org + (long long)y * pp + x]; bv[r] = gbin[org + (long long)y * pp + x]; }
+        }
+#pragma unroll
+        for (int r = 0; r < HOGW_LB; ++r) {
+          const int y = y0 + r * NW;
+          if (y < H - 1 && x < W - 1) { smag[y * g.ms + x] = mv[r]; sbin[y * g.bs + x] = bv[r]; }
+        }
+      }
+    }
+    const int ring_n = 2 * W + 2 * (H - 2);
+    for (int r0 = tid; r0 < ring_n; r0 += HOGW_THREADS * HOGW_RB) {
+      int rx[HOGW_RB], ry[HOGW_RB], pa[HOGW_RB], pb[HOGW_RB], pc[HOGW_RB], pd[HOGW_RB];
+      const uint8_t* px = pool + org;
+#pragma unroll
+      for (int i = 0; i < HOGW_RB; ++i) {
+        const int r = r0 + i * HOGW_THREADS;
+        if (r < ring_n) {
+          int x, y;
+          if (r < W) { y = 0; x = r; }
+          else if (r < 2 * W) { y = H - 1; x = r - W; }
+          else { const int r2 = r - 2 * W; y = 1 + (r2 >> 1); x = (r2 & 1) ? W - 1 : 0; }
+          const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
+          rx[i] = x; ry[i] = y;
+          pa[i] = px[(long long)y * pp + xp]; pb[i] = px[(long long)y * pp + xm];
+          pc[i] = px[(long long)yp * pp + x]; pd[i] = px[(long long)ym * pp + x];
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < HOGW_RB; ++i) {
+        if (r0 + i * HOGW_THREADS < ring_n) {
+          float mag;
+          int b;
+          hog_mag_bin((float)(pa[i] - pb[i]), (float)(pc[i] - pd[i]), mag, b);
+          smag[ry[i] * g.ms + rx[i]] = mag;
+          sbin[ry[i] * g.bs + rx[i]] = (uint8_t)b;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- row prefixes (strSum of src/HOGfeatures.cpp:240-252): two threads walk one row, the first with bins 0..4, the second
+    // with bins 5..8 and the norm plane; only the matching bin and the norm plane change at a pixel (the other planes add +0,
+    // which leaves an f32 sum unchanged) ----
+    for (int t = tid; t < 2 * g.rows; t += HOGW_THREADS) {
+      const bool second = t >= g.rows;
+      const int y = second ? t - g.rows : t;
+      const uint32_t b0 = second ? 5u : 0u;
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f, r3 = 0.f, r4 = 0.f;
+      const float* mrow = smag + y * g.ms;
+      const uint32_t* brow = reinterpret_cast<const uint32_t*>(sbin + y * g.bs);
+      float* srow = S + y * g.ss + b0;
+      for (int c = 0; c < g.groups; ++c) {
+        const uint32_t q4 = brow[c];
+#pragma unroll
+        for (int kk = 0; kk < HOG_GRID; ++kk) {
+          const float gg = mrow[c * HOG_GRID + kk];
+          const uint32_t q = (q4 >> (8 * kk)) & 0xFFu;
+          hog_add_if(r0, q, b0, gg); hog_add_if(r1, q, b0 + 1u, gg); hog_add_if(r2, q, b0 + 2u, gg); hog_add_if(r3, q, b0 + 3u, gg);
+          hog_add_if(r4, q, second ? q : 4u, gg);          // second thread: the norm plane takes every pixel
+        }
+        srow[c * 10] = r0; srow[c * 10 + 1] = r1; srow[c * 10 + 2] = r2; srow[c * 10 + 3] = r3; srow[c * 10 + 4] = r4;
+      }
+    }
+    __syncthreads();
+    // ---- column accumulation: plane[y + 1][4 (c + 1)] = plane[y][4 (c + 1)] + strSum; only rows / columns that are multiples of
+    // HOG_GRID are kept (the compact planes of k_hog_integrals) ----
+    for (int j = tid; j < g.groups * 10; j += HOGW_THREADS) {
+      const int c = j / 10, b = j - c * 10;
+      float* pl = planes + b * g.Pc + (c + 1);
+      float col = 0.f;
+      for (int y = 0; y < g.rows; y += HOG_GRID) {
+#pragma unroll
+        for (int kk = 0; kk < HOG_GRID; ++kk) col = __fadd_rn(col, S[(y + kk) * g.ss + j]);
+        pl[(y / HOG_GRID + 1) * g.Sc] = col;
+      }
+    }
+    {
+      const int nr = H / HOG_GRID + 1;                 // first row and first column of every plane are zero
+      for (int i = tid; i < 10 * (g.Sc + nr); i += HOGW_THREADS) {
+        const int b = i / (g.Sc + nr), e = i - b * (g.Sc + nr);
+        planes[b * g.Pc + (e < g.Sc ? e : (e - g.Sc) * g.Sc)] = 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- cascade (warp 0): lane t walks weak tree t of the stage, the leaf values are added in tree order ----
+    if (warp == 0) {
+      EvalView e;
+      e.ftype = CC_FEATURE_HOG; e.P = g.Pc; e.ns_pad = 1;
+      e.sum = nullptr; e.tilted = nullptr; e.nf = nullptr; e.hog = planes;
+      e.haar_taps = nullptr; e.lbp_taps = nullptr; e.hog_taps = taps;
+      bool pass = true;
+      for (int st = 0; st < nstages && pass; ++st) {
+        const DevStageRef sr = stages[st];
+        double sum = 0;
+        for (int t0 = 0; t0 < sr.num_trees; t0 += 32) {
+          double v = 0;
+          if (t0 + lane < sr.num_trees) {
+            const DevNode* tree = nodes + tree_first[sr.first_tree + t0 + lane];
+            int nd = 0;
+            while (tree[nd].left >= 0) {
+              const float val = m_hog_value(taps[tree[nd].var_idx / 36], e, tree[nd].var_idx % 36, 0);
+              nd = val <= tree[nd].c ? tree[nd].left : tree[nd].right;
+            }
+            v = tree[nd].value;
+          }
+          const int cnt = min(32, sr.num_trees - t0);
+          for (int i = 0; i < cnt; ++i) sum += __shfl_sync(0xffffffffu, v, i);
+        }
+        if (sum < (double)(sr.threshold - 0.00001F)) pass = false;
+      }
+      if (pass && lane == 0) {
+        const unsigned pos = atomicAdd(surv_count, 1u);
+        if (pos < surv_cap) surv[pos] = (unsigned)wi;
+      }
+    }
+  }
+}
 
 // ------------------------------------------------------------------------------------------------
 // Haar / LBP fast path: integral images of whole pyramid levels instead of one per window.
@@ -899,6 +1118,9 @@ struct MineState {
   unsigned int surv_cap = 0;
   unsigned int* h_surv = nullptr;      // pinned mirror (count + list) shared by the slot path and the tile miner
   size_t h_surv_cap = 0;               // entries
+  float* d_gmag = nullptr;             // HOG miner: gradient magnitude / orientation bin of every level pixel of the batch
+  uint8_t* d_gbin = nullptr;
+  size_t grad_cap = 0;
   // whole-level fast path (Haar / LBP)
   std::vector<LvlFeat> lfeats;         // parallel to `nodes`
   LvlFeat* d_lfeats = nullptr;
@@ -964,6 +1186,7 @@ static void free_scratch(MineState* m) {
   cudaFree(m->d_levels); m->d_levels = nullptr; m->levels_cap = 0;
   cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
   cudaFreeHost(m->h_surv); m->h_surv = nullptr; m->h_surv_cap = 0;
+  cudaFree(m->d_gmag); cudaFree(m->d_gbin); m->d_gmag = nullptr; m->d_gbin = nullptr; m->grad_cap = 0;
   cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
   m->d_psum = m->d_psq = m->d_ptilt = nullptr; m->plane_cap = 0;
   cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts); cudaFree(m->d_order);
@@ -1017,7 +1240,8 @@ static int ensure_h_surv(MineState* m, size_t entries) {
   return CC_OK;
 }
 
-static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, int nlevels) {
+static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, int nlevels, long long surv_n = -1) {
+  if (surv_n < 0) surv_n = nwin;
   if (nwin > m->scratch_cap) {
     store_free(m->scratch);
     CC_CHECK(store_alloc(ctx, m->scratch, nwin));
@@ -1033,10 +1257,10 @@ static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, i
     CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * nlevels));
     m->levels_cap = nlevels;
   }
-  if ((unsigned)nwin > m->surv_cap) {
-    cudaFree(m->d_surv);
-    CC_CUDA(cudaMalloc(&m->d_surv, sizeof(unsigned) * ((size_t)nwin + 1)));
-    m->surv_cap = (unsigned)nwin;
+  if ((unsigned long long)surv_n > m->surv_cap) {
+    cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
+    CC_CUDA(cudaMalloc(&m->d_surv, sizeof(unsigned) * ((size_t)surv_n + 1)));
+    m->surv_cap = (unsigned)surv_n;
   }
   return ensure_h_surv(m, (size_t)m->surv_cap + 1);
 }
@@ -1257,6 +1481,48 @@ static int eval_scratch(cc_ctx* ctx, MineState* m, int n, std::vector<unsigned>&
     CC_CUDA(cudaMemsetAsync(m->d_surv, 0, sizeof(unsigned), ctx->stream));
     k_cascade_eval<<<(n + 127) / 128, 128, 0, ctx->stream>>>(make_eval_view_store(ctx, m->scratch), m->d_nodes, m->d_tree_first, m->d_stages,
                                                              (int)m->stages.size(), n, m->d_surv, m->d_surv + 1, m->surv_cap);
+    CC_CUDA(cudaGetLastError());
+  }
+  CC_CUDA(cudaMemcpyAsync(m->h_surv, m->d_surv, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  CC_CUDA(cudaStreamSynchronize(ctx->stream));
+  const unsigned cnt = std::min(m->h_surv[0], m->surv_cap);
+  if (cnt) {
+    CC_CUDA(cudaMemcpyAsync(m->h_surv + 1, m->d_surv + 1, sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+    CC_CUDA(cudaStreamSynchronize(ctx->stream));
+    survivors.assign(m->h_surv + 1, m->h_surv + 1 + cnt);
+    std::sort(survivors.begin(), survivors.end());
+  }
+  return CC_OK;
+}
+
+// HOG miner (see k_hog_window_cascade): the batch's levels are in m->d_pool / m->d_levels; returns sorted survivors
+constexpr long long HOG_WINDOW_MAX_BATCH = 8 << 20;
+static bool use_hog_window_path(const cc_ctx* ctx, const MineState* m) {
+  if (ctx->ftype != CC_FEATURE_HOG || m->force_slots || m->stages.empty() || ctx->W < 3 || ctx->H < 3) return false;
+  return hog_win_geometry(ctx->W, ctx->H).smem <= (size_t)200 * 1024;
+}
+static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, size_t pool_px, long long nwin, std::vector<unsigned>& survivors) {
+  survivors.clear();
+  if (nwin == 0) return CC_OK;
+  if (pool_px > m->grad_cap) {
+    cudaFree(m->d_gmag); cudaFree(m->d_gbin); m->d_gmag = nullptr; m->d_gbin = nullptr; m->grad_cap = 0;
+    const size_t cap = pool_px + pool_px / 4;
+    CC_CUDA(cudaMalloc(&m->d_gmag, cap * sizeof(float)));
+    CC_CUDA(cudaMalloc(&m->d_gbin, cap));
+    m->grad_cap = cap;
+  }
+  const HogWinGeom g = hog_win_geometry(ctx->W, ctx->H);
+  {
+    ScopedTimer tm(ctx, "mine", 2);
+    k_hog_level_grad<<<grid_for(ctx, (long long)pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlevels, (long long)pool_px, m->d_pool, m->d_gmag, m->d_gbin);
+    CC_CUDA(cudaGetLastError());
+    CC_CUDA(cudaMemsetAsync(m->d_surv, 0, sizeof(unsigned), ctx->stream));
+    CC_CUDA(cudaFuncSetAttribute(k_hog_window_cascade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
+    const int per_sm = std::max(1, (int)((size_t)227 * 1024 / (g.smem + 1024)));
+    const int grid = (int)std::min<long long>(nwin, (long long)ctx->sm_count * per_sm * 4);
+    k_hog_window_cascade<<<grid, HOGW_THREADS, g.smem, ctx->stream>>>(m->d_levels, nlevels, m->d_pool, m->d_gmag, m->d_gbin, g, ctx->d_hog_taps, m->d_nodes,
+                                                                       m->d_tree_first, m->d_stages, (int)m->stages.size(), nwin, m->d_surv, m->d_surv + 1,
+                                                                       m->surv_cap);
     CC_CUDA(cudaGetLastError());
   }
   CC_CUDA(cudaMemcpyAsync(m->h_surv, m->d_surv, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
@@ -2081,7 +2347,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
   const bool level_path = use_level_path(ctx, m);
   const TileGeom tgeom = tile_geometry(ctx, ctx->ftype == CC_FEATURE_HAAR, ctx->ftype == CC_FEATURE_HAAR && m->cascade_tilted);
   const bool tile_path = level_path && m->mode == 3 && tgeom.ok;
-  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : slot_path_max_batch(ctx);
+  const bool hog_win = !level_path && use_hog_window_path(ctx, m);      // HOG: level gradients + one CTA per window
+  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : hog_win ? HOG_WINDOW_MAX_BATCH : slot_path_max_batch(ctx);
   // Plane path: two batches in flight.  While batch k is evaluated the host assembles and launches batch k+1 -- when
   // the running acceptance rate says that batch k will not complete the stage -- and only then waits for batch k's
   // survivor bitmap; a speculative batch that turns out not to be needed is dropped (its windows count as not read).
@@ -2231,11 +2498,11 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     const bool direct = m->stages.empty();       // stage 0: every window passes, gather straight into the training slots
     long long take_direct = 0;
     if (!level_path) {
-      CC_CHECK(ensure_scratch(ctx, m, direct ? 1 : (int)nwin, bt.pool_px, (int)bt.levels.size()));
+      CC_CHECK(ensure_scratch(ctx, m, (direct || hog_win) ? 1 : (int)nwin, bt.pool_px, (int)bt.levels.size(), direct ? 1 : nwin));
       CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (!level_path) {
-      ScopedTimer tm(ctx, "mine", 2);
+      ScopedTimer tm(ctx, "mine", hog_win ? 1 : 2);
       k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
       CC_CUDA(cudaGetLastError());
       if (direct) {
@@ -2243,7 +2510,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
         take_direct = std::min<long long>(nwin, count - got);
         k_gather_windows<<<grid_for(ctx, take_direct * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, take_direct,
                                                                                        ctx->d_imgs + (size_t)(first_slot + got) * npx);
-      } else {
+      } else if (!hog_win) {
         k_gather_windows<<<grid_for(ctx, nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
       }
       CC_CUDA(cudaGetLastError());
@@ -2283,6 +2550,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       } else {
         HostTimer he(ctx, "mine_host_eval");
         if (tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
+        else if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), bt.pool_px, nwin, survivors));
         else CC_CHECK(eval_scratch(ctx, m, (int)nwin, survivors));
         if (tile_path) m->stat_built += nwin;
         surv64.assign(survivors.begin(), survivors.end());
@@ -2293,7 +2561,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       const long long pos = serial_cut<long long>(surv64.data(), surv64.size(), nwin, count, min_ratio, consumed, got, accepted, stopped);
       stop_after = pos - 1;
       const int first_acc = first_slot + got - (int)accepted.size();
-      if (level_path) CC_CHECK(gather_accepted(ctx, m, bt, accepted, first_acc, 0));
+      if (level_path || hog_win) CC_CHECK(gather_accepted(ctx, m, bt, accepted, first_acc, 0));      // (the levels of the batch, from the source images)
       else {
         std::vector<unsigned> acc32(accepted.begin(), accepted.end());
         CC_CHECK(accept_windows(ctx, m, acc32.data(), (int)acc32.size(), first_acc, 0));
@@ -2482,7 +2750,8 @@ int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64
   const bool level_path = use_level_path(ctx, m);
   const TileGeom tgeom = tile_geometry(ctx, ctx->ftype == CC_FEATURE_HAAR, ctx->ftype == CC_FEATURE_HAAR && m->cascade_tilted);
   const bool tile_path = level_path && m->mode == 3 && tgeom.ok;
-  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : slot_path_max_batch(ctx);
+  const bool hog_win = !level_path && use_hog_window_path(ctx, m);
+  const long long max_batch = level_path ? level_path_max_batch(ctx, m) : hog_win ? HOG_WINDOW_MAX_BATCH : slot_path_max_batch(ctx);
   long long total = 0, surv = 0;
   uint64_t digest = 0;                 // order-independent digest of the surviving windows' scan ordinals
   std::vector<unsigned> survivors;
@@ -2517,15 +2786,17 @@ int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64
       bt = Batch();
       return CC_OK;
     }
-    CC_CHECK(ensure_scratch(ctx, m, nwin, bt.pool_px, (int)bt.levels.size()));
+    CC_CHECK(ensure_scratch(ctx, m, hog_win ? 1 : nwin, bt.pool_px, (int)bt.levels.size(), nwin));
     CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     {
-      ScopedTimer tm(ctx, "mine", 2);
+      ScopedTimer tm(ctx, "mine", hog_win ? 1 : 2);
       k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
-      k_gather_windows<<<grid_for(ctx, (long long)nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
+      if (!hog_win)
+        k_gather_windows<<<grid_for(ctx, (long long)nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
       CC_CUDA(cudaGetLastError());
     }
-    CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
+    if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), bt.pool_px, nwin, survivors));
+    else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
     account(total); total += nwin;
     bt = Batch();
     return CC_OK;

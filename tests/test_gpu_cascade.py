@@ -194,6 +194,54 @@ def test_mining_paths_agree(gpu_ctx, tmp_path, ftype, mode):
         assert np.array_equal(r[3], results[0][3])
 
 
+@pytest.mark.parametrize("W,H,bw,bh", [(48, 96, 300, 330), (32, 40, 260, 200), (24, 24, 97, 61)])
+def test_hog_miner_matches_slot_path(gpu_ctx, tmp_path, W, H, bw, bh):
+    """HOG mining by level gradients + one CTA per window (k_hog_level_grad / k_hog_window_cascade, the default) must select
+    exactly the windows the literal per-window path (scratch slot: setImage + predict, cc_mine_set_mode 2) selects -- same
+    consumed count, reader state, accepted pixels and integral histograms -- over several images, pyramid levels and calls that
+    resume inside a level."""
+    import copy
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import _lib
+    from cascadeclassifier_b200._lib import check
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    pos, bgs = _data(220, 4, W=W, H=H, bw=bw, bh=bh, seed=21)
+    cc = CvCascadeClassifier(gpu_ctx, out=io.StringIO())
+    fp = ccb.CvFeatureParams.create(orc.HOG)
+    cc.train(str(tmp_path), "pos.vec", "bg.txt", 150, 200, 1024, 1024, 3, CvCascadeParams(0, orc.HOG, (W, H)), fp,
+             ccb.CvCascadeBoostParams(maxWeakCount=8), positives=pos, backgrounds=bgs)
+    assert len(cc.stageClassifiers) >= 1
+    cc._sync_cascade()
+    lib, h = gpu_ctx.lib, gpu_ctx.h
+    start = copy.copy(cc._reader)
+    results = []
+    for m in (2, 0):
+        check(lib.cc_mine_set_mode(h, m), "cc_mine_set_mode")
+        st = _lib.ReaderState.from_buffer_copy(bytes(start))
+        rec = []
+        for count in (90, 110):           # the second call resumes where the first one stopped (inside a level)
+            consumed, got = C.c_int64(0), C.c_int32(0)
+            check(lib.cc_mine_negatives(h, 150, count, 1e-7, C.byref(st), C.byref(consumed), C.byref(got)), "cc_mine_negatives")
+            planes = [cc.featureEvaluator.hogPlanesCompact(150 + k).copy() for k in (0, got.value - 1)]
+            rec.append((got.value, consumed.value, _state_dict(st), cc.featureEvaluator.images(150, got.value).copy(), planes))
+        results.append(rec)
+    # every window of every level of every image: same set of survivors (order-independent digest of their scan ordinals)
+    scans = []
+    for m in (2, 0):
+        check(lib.cc_mine_set_mode(h, m), "cc_mine_set_mode")
+        win, surv, dig = C.c_int64(0), C.c_int64(0), C.c_uint64(0)
+        check(lib.cc_mine_scan_digest(h, 0, len(bgs), C.byref(win), C.byref(surv), C.byref(dig)), "cc_mine_scan_digest")
+        scans.append((win.value, surv.value, dig.value))
+    check(lib.cc_mine_set_mode(h, 0), "cc_mine_set_mode")
+    assert scans[0] == scans[1] and 0 < scans[0][1] < scans[0][0], scans
+    for a, b in zip(results[0], results[1]):
+        assert a[0] == b[0] > 0 and a[1] == b[1] and a[2] == b[2], (a[:3], b[:3])
+        assert np.array_equal(a[3], b[3])
+        for pa, pb in zip(a[4], b[4]):
+            assert np.array_equal(pa, pb)
+    assert results[0][0][1] > results[0][0][0]          # the cascade rejected windows: the stages were really evaluated
+
+
 @pytest.mark.parametrize("ftype,mode", [(orc.HAAR, orc.ALL), (orc.LBP, 0)])
 def test_resume_from_stage_files(gpu_ctx, tmp_path, ftype, mode):
     """CvCascadeClassifier::load (src/cascadeclassifier.cpp:534-564): a second train() on a directory that holds
