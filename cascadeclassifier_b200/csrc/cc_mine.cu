@@ -227,39 +227,30 @@ __global__ void k_copy_slots(const uint8_t* __restrict__ src, const unsigned int
 }
 
 // ------------------------------------------------------------------------------------------------
-// HOG miner: gradients once per pyramid level, integral histograms and cascade per window inside one CTA.
+// HOG miner: one CTA per window, nothing per window in HBM.
 //
 // CvHOGEvaluator::integralHistogram works on the window crop (src/HOGfeatures.cpp:163-256): central differences with
 // BORDER_REPLICATE at the crop border, magnitude + orientation bin per pixel, then per bin an f32 integral image whose
-// additions run from the crop's first column / first row.  The integrals therefore cannot be shared between windows (f32 sums
-// depend on where they start), but the gradient of every pixel that is NOT on the window's 1-pixel ring is a function of the
-// level pixels alone: k_hog_level_grad computes it once per level pixel, and k_hog_window_cascade -- one CTA per window --
-// takes the interior of its window from those planes, recomputes the ring with the replicated border, builds the ten
-// compact integral planes in shared memory with the additions of k_hog_integrals in the same order (row prefix, then
-// column accumulation) and runs the cascade on them with early exit.  Nothing per window ever goes to HBM: the slot path
-// writes and re-reads ~70 KB per 48x96 window (pixels, gradients, planes).  Survivors == the slot path's
+// additions run from the crop's first column / first row -- so neither the gradients on the crop's 1-pixel ring nor the integrals
+// can be shared between windows.  k_hog_window_cascade copies the window's pixels from its pyramid level into shared memory,
+// takes magnitude and bin of every pixel from a table over all 511 x 511 (dx, dy) pairs (differences of 8-bit pixels; the
+// table is filled once by k_hog_lut_init with hog_mag_bin, the arithmetic of K1's k_hog_gradient, so the values are
+// bit-identical by construction and the division / square root / arctangent polynomial are not re-evaluated per pixel),
+// builds the ten compact integral planes in shared memory with the additions of k_hog_integrals in the same order (row
+// prefix, then column accumulation) and runs the cascade on them with early exit.  The slot path writes and re-reads ~70 KB
+// per 48x96 window (pixels, gradients, planes); this kernel reads the 4.6 KB of pixels.  Survivors == the slot path's
 // (test_hog_miner_matches_slot_path), which is the literal setImage + predict arithmetic.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_hog_level_grad(const LevelDesc* __restrict__ levels, int nlevels, long long total_px, const uint8_t* __restrict__ pool,
-                                 float* __restrict__ gmag, uint8_t* __restrict__ gbin) {
-  for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total_px; p += (long long)gridDim.x * blockDim.x) {
-    int lo = 0, hi = nlevels - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].px_off <= p) lo = mid; else hi = mid - 1; }
-    const LevelDesc& L = levels[lo];
-    const int q = (int)(p - L.px_off);
-    const int y = q / L.ppitch, x = q - y * L.ppitch;
-    if (x >= L.lw) continue;
-    // pixels on the border of the level are only ever ring pixels of a window (recomputed there); clamped here to stay in bounds
-    const uint8_t* base = pool + L.px_off;
-    const int xm = max(x - 1, 0), xp = min(x + 1, L.lw - 1), ym = max(y - 1, 0), yp = min(y + 1, L.lh - 1);
-    const float dx = (float)((int)base[(size_t)y * L.ppitch + xp] - (int)base[(size_t)y * L.ppitch + xm]);
-    const float dy = (float)((int)base[(size_t)yp * L.ppitch + x] - (int)base[(size_t)ym * L.ppitch + x]);
-    float mag;
-    int b;
-    hog_mag_bin(dx, dy, mag, b);
-    gmag[p] = mag;
-    gbin[p] = (uint8_t)b;
-  }
+constexpr int HOG_LUT_W = 512;                                    // row stride of the table; entry [(dy + 255) * 512 + dx + 255]
+constexpr int HOG_LUT_N = 511 * HOG_LUT_W;
+__global__ void k_hog_lut_init(float2* __restrict__ lut) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= HOG_LUT_N) return;
+  const int dy = i / HOG_LUT_W - 255, dx = i % HOG_LUT_W - 255;
+  float mag = 0.f;
+  int b = 0;
+  if (dx <= 255) hog_mag_bin((float)dx, (float)dy, mag, b);
+  lut[i] = make_float2(mag, __int_as_float(b));
 }
 
 // shared-memory geometry of k_hog_window_cascade (strides chosen odd in 32-bit words: a thread per row walks its row
@@ -285,21 +276,20 @@ static HogWinGeom hog_win_geometry(int W, int H) {
   const size_t tile = std::max((size_t)H * g.ms * 4, (size_t)10 * g.Pc * 4);      // the planes reuse the magnitude tile
   g.off_bin = (int)((tile + 15) & ~(size_t)15);
   g.off_S = (int)(((size_t)g.off_bin + (size_t)H * g.bs + 15) & ~(size_t)15);
-  g.smem = (size_t)g.off_S + (size_t)g.rows * g.ss * 4;
+  g.smem = (size_t)g.off_S + std::max((size_t)g.rows * g.ss * 4, (size_t)W * H);      // the pixel tile lives where S goes later
   return g;
 }
 
 constexpr int HOGW_THREADS = 256;
-constexpr int HOGW_LB = 4;            // rows per load batch of a warp
-constexpr int HOGW_RB = 2;            // ring pixels per load batch of a thread
+constexpr int HOGW_LB = 6;            // pixels per load batch of a thread
 // run += g if the pixel's bin is `want` -- one predicated FADD (written in PTX: the compiler turns the C++ form of nine
 // mutually exclusive tests into a divergent decision tree)
 __device__ __forceinline__ void hog_add_if(float& run, uint32_t q, uint32_t want, float gg) {
   asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.rn.f32 %0, %0, %3;\n\t}" : "+f"(run) : "r"(q), "r"(want), "f"(gg));
 }
 __global__ void __launch_bounds__(HOGW_THREADS, 3)
-k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const uint8_t* __restrict__ pool, const float* __restrict__ gmag,
-                     const uint8_t* __restrict__ gbin, HogWinGeom g, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
+k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const uint8_t* __restrict__ pool, const float2* __restrict__ lut,
+                     HogWinGeom g, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
                      const int* __restrict__ tree_first, const DevStageRef* __restrict__ stages, int nstages, long long nwin,
                      unsigned int* __restrict__ surv_count, unsigned int* __restrict__ surv, unsigned int surv_cap) {
   extern __shared__ __align__(16) unsigned char hw_smem[];
@@ -307,6 +297,7 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const ui
   float* planes = smag;                                             // [10][Pc] once the row prefixes are taken
   uint8_t* sbin = hw_smem + g.off_bin;                              // [H][bs]
   float* S = reinterpret_cast<float*>(hw_smem + g.off_S);           // [rows][ss]: row prefix of plane b behind pixel group c at [c * 10 + b]
+  uint8_t* spx = hw_smem + g.off_S;                                 // [H][W] window pixels, until the gradients are taken
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = HOGW_THREADS / 32;
   const int W = g.W, H = g.H;
@@ -319,52 +310,41 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const ui
     const int pp = L.ppitch;
     const long long org = L.px_off + (long long)(L.y0 + iy * L.step_y) * pp + (L.x0 + ix * L.step_x);
     __syncthreads();                                   // the previous window's cascade has finished reading the planes
-    // ---- interior: the level gradient; ring: central differences with the window's replicated border ----
-    // (loads are issued in batches of HOGW_LB rows / ring pixels before their first use: one L2 round trip per batch, not per row)
-    for (int xc = 1; xc < W - 1; xc += 32) {
-      const int x = xc + lane;
-      for (int y0 = 1 + warp; y0 < H - 1; y0 += NW * HOGW_LB) {
-        float mv[HOGW_LB];
-        uint8_t bv[HOGW_LB];
+    // ---- the window's pixels (loads issued in batches before their first use: one L2 round trip per batch) ----
+    {
+      const uint8_t* px = pool + org;
+      const int npx = W * H;
+      int y = tid / W, x = tid - y * W;
+      const int dyq = HOGW_THREADS / W, dxr = HOGW_THREADS - dyq * W;      // (y, x) of pixel i + HOGW_THREADS from those of pixel i
+      for (int i0 = tid; i0 < npx; i0 += HOGW_THREADS * HOGW_LB) {
+        uint8_t v[HOGW_LB];
+        int o[HOGW_LB];
 #pragma unroll
         for (int r = 0; r < HOGW_LB; ++r) {
-          const int y = y0 + r * NW;
-          if (y < H - 1 && x < W - 1) { mv[r] = gmag[org + (long long)y * pp + x]; bv[r] = gbin[org + (long long)y * pp + x]; }
+          o[r] = i0 + r * HOGW_THREADS;
+          if (o[r] < npx) v[r] = px[(long long)y * pp + x];
+          x += dxr; y += dyq;
+          if (x >= W) { x -= W; ++y; }
         }
 #pragma unroll
-        for (int r = 0; r < HOGW_LB; ++r) {
-          const int y = y0 + r * NW;
-          if (y < H - 1 && x < W - 1) { smag[y * g.ms + x] = mv[r]; sbin[y * g.bs + x] = bv[r]; }
-        }
+        for (int r = 0; r < HOGW_LB; ++r)
+          if (o[r] < npx) spx[o[r]] = v[r];
       }
     }
-    const int ring_n = 2 * W + 2 * (H - 2);
-    for (int r0 = tid; r0 < ring_n; r0 += HOGW_THREADS * HOGW_RB) {
-      int rx[HOGW_RB], ry[HOGW_RB], pa[HOGW_RB], pb[HOGW_RB], pc[HOGW_RB], pd[HOGW_RB];
-      const uint8_t* px = pool + org;
-#pragma unroll
-      for (int i = 0; i < HOGW_RB; ++i) {
-        const int r = r0 + i * HOGW_THREADS;
-        if (r < ring_n) {
-          int x, y;
-          if (r < W) { y = 0; x = r; }
-          else if (r < 2 * W) { y = H - 1; x = r - W; }
-          else { const int r2 = r - 2 * W; y = 1 + (r2 >> 1); x = (r2 & 1) ? W - 1 : 0; }
-          const int xm = max(x - 1, 0), xp = min(x + 1, W - 1), ym = max(y - 1, 0), yp = min(y + 1, H - 1);
-          rx[i] = x; ry[i] = y;
-          pa[i] = px[(long long)y * pp + xp]; pb[i] = px[(long long)y * pp + xm];
-          pc[i] = px[(long long)yp * pp + x]; pd[i] = px[(long long)ym * pp + x];
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < HOGW_RB; ++i) {
-        if (r0 + i * HOGW_THREADS < ring_n) {
-          float mag;
-          int b;
-          hog_mag_bin((float)(pa[i] - pb[i]), (float)(pc[i] - pd[i]), mag, b);
-          smag[ry[i] * g.ms + rx[i]] = mag;
-          sbin[ry[i] * g.bs + rx[i]] = (uint8_t)b;
-        }
+    __syncthreads();
+    // ---- magnitude and bin of every pixel: central differences with the window's replicated border, table lookup ----
+    {
+      int y = tid / W, x = tid - y * W;
+      const int dyq = HOGW_THREADS / W, dxr = HOGW_THREADS - dyq * W;
+      for (int i = tid; i < W * H; i += HOGW_THREADS) {
+        const uint8_t* rowp = spx + y * W;
+        const int dx = (int)rowp[min(x + 1, W - 1)] - (int)rowp[max(x - 1, 0)];
+        const int dy = (int)spx[min(y + 1, H - 1) * W + x] - (int)spx[max(y - 1, 0) * W + x];
+        const float2 e = __ldg(lut + (dy + 255) * HOG_LUT_W + (dx + 255));
+        smag[y * g.ms + x] = e.x;
+        sbin[y * g.bs + x] = (uint8_t)__float_as_int(e.y);
+        x += dxr; y += dyq;
+        if (x >= W) { x -= W; ++y; }
       }
     }
     __syncthreads();
@@ -1118,9 +1098,7 @@ struct MineState {
   unsigned int surv_cap = 0;
   unsigned int* h_surv = nullptr;      // pinned mirror (count + list) shared by the slot path and the tile miner
   size_t h_surv_cap = 0;               // entries
-  float* d_gmag = nullptr;             // HOG miner: gradient magnitude / orientation bin of every level pixel of the batch
-  uint8_t* d_gbin = nullptr;
-  size_t grad_cap = 0;
+  float2* d_hog_lut = nullptr;         // HOG miner: (magnitude, bin) of every (dx, dy) pair, see k_hog_lut_init
   // whole-level fast path (Haar / LBP)
   std::vector<LvlFeat> lfeats;         // parallel to `nodes`
   LvlFeat* d_lfeats = nullptr;
@@ -1186,7 +1164,7 @@ static void free_scratch(MineState* m) {
   cudaFree(m->d_levels); m->d_levels = nullptr; m->levels_cap = 0;
   cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
   cudaFreeHost(m->h_surv); m->h_surv = nullptr; m->h_surv_cap = 0;
-  cudaFree(m->d_gmag); cudaFree(m->d_gbin); m->d_gmag = nullptr; m->d_gbin = nullptr; m->grad_cap = 0;
+  cudaFree(m->d_hog_lut); m->d_hog_lut = nullptr;
   cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
   m->d_psum = m->d_psq = m->d_ptilt = nullptr; m->plane_cap = 0;
   cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts); cudaFree(m->d_order);
@@ -1501,26 +1479,22 @@ static bool use_hog_window_path(const cc_ctx* ctx, const MineState* m) {
   if (ctx->ftype != CC_FEATURE_HOG || m->force_slots || m->stages.empty() || ctx->W < 3 || ctx->H < 3) return false;
   return hog_win_geometry(ctx->W, ctx->H).smem <= (size_t)200 * 1024;
 }
-static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, size_t pool_px, long long nwin, std::vector<unsigned>& survivors) {
+static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nwin, std::vector<unsigned>& survivors) {
   survivors.clear();
   if (nwin == 0) return CC_OK;
-  if (pool_px > m->grad_cap) {
-    cudaFree(m->d_gmag); cudaFree(m->d_gbin); m->d_gmag = nullptr; m->d_gbin = nullptr; m->grad_cap = 0;
-    const size_t cap = pool_px + pool_px / 4;
-    CC_CUDA(cudaMalloc(&m->d_gmag, cap * sizeof(float)));
-    CC_CUDA(cudaMalloc(&m->d_gbin, cap));
-    m->grad_cap = cap;
+  if (!m->d_hog_lut) {
+    CC_CUDA(cudaMalloc(&m->d_hog_lut, sizeof(float2) * HOG_LUT_N));
+    k_hog_lut_init<<<(HOG_LUT_N + 255) / 256, 256, 0, ctx->stream>>>(m->d_hog_lut);
+    CC_CUDA(cudaGetLastError());
   }
   const HogWinGeom g = hog_win_geometry(ctx->W, ctx->H);
   {
-    ScopedTimer tm(ctx, "mine", 2);
-    k_hog_level_grad<<<grid_for(ctx, (long long)pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, nlevels, (long long)pool_px, m->d_pool, m->d_gmag, m->d_gbin);
-    CC_CUDA(cudaGetLastError());
+    ScopedTimer tm(ctx, "mine", 1);
     CC_CUDA(cudaMemsetAsync(m->d_surv, 0, sizeof(unsigned), ctx->stream));
     CC_CUDA(cudaFuncSetAttribute(k_hog_window_cascade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int per_sm = std::max(1, (int)((size_t)227 * 1024 / (g.smem + 1024)));
     const int grid = (int)std::min<long long>(nwin, (long long)ctx->sm_count * per_sm * 4);
-    k_hog_window_cascade<<<grid, HOGW_THREADS, g.smem, ctx->stream>>>(m->d_levels, nlevels, m->d_pool, m->d_gmag, m->d_gbin, g, ctx->d_hog_taps, m->d_nodes,
+    k_hog_window_cascade<<<grid, HOGW_THREADS, g.smem, ctx->stream>>>(m->d_levels, nlevels, m->d_pool, m->d_hog_lut, g, ctx->d_hog_taps, m->d_nodes,
                                                                        m->d_tree_first, m->d_stages, (int)m->stages.size(), nwin, m->d_surv, m->d_surv + 1,
                                                                        m->surv_cap);
     CC_CUDA(cudaGetLastError());
@@ -2550,7 +2524,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       } else {
         HostTimer he(ctx, "mine_host_eval");
         if (tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
-        else if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), bt.pool_px, nwin, survivors));
+        else if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), nwin, survivors));
         else CC_CHECK(eval_scratch(ctx, m, (int)nwin, survivors));
         if (tile_path) m->stat_built += nwin;
         surv64.assign(survivors.begin(), survivors.end());
@@ -2795,7 +2769,7 @@ int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64
         k_gather_windows<<<grid_for(ctx, (long long)nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
       CC_CUDA(cudaGetLastError());
     }
-    if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), bt.pool_px, nwin, survivors));
+    if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), nwin, survivors));
     else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
     account(total); total += nwin;
     bt = Batch();
