@@ -129,6 +129,55 @@ __global__ void k_resize_levels(const LevelDesc* __restrict__ levels, int nlevel
   }
 }
 
+// The same levels, tiled: a CTA takes RZ_ROWS rows x RZ_THREADS columns of one level, so the column coefficients (f64) are
+// computed once per column instead of once per pixel and the row coefficients once per row; LevelDesc::rows_base holds the
+// level's first tile (resize_tiles()).  Same fixed-point arithmetic, bit-identical pixels (test_hog_miner_matches_slot_path
+// compares a path that uses this kernel with one that uses k_resize_levels).
+constexpr int RZ_ROWS = 8, RZ_THREADS = 256;
+__global__ void __launch_bounds__(RZ_THREADS)
+k_resize_tiles(const LevelDesc* __restrict__ levels, int nlevels, int ntiles, uint8_t* __restrict__ pool) {
+  __shared__ int s_oy[RZ_ROWS], s_cy0[RZ_ROWS], s_cy1[RZ_ROWS], s_step[RZ_ROWS];
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    int lo = 0, hi = nlevels - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].rows_base <= tile) lo = mid; else hi = mid - 1; }
+    const LevelDesc& L = levels[lo];
+    const int t = tile - L.rows_base;
+    const int nxc = (L.lw + RZ_THREADS - 1) / RZ_THREADS;
+    const int rb = t / nxc, xc = t - rb * nxc;
+    const int y0 = rb * RZ_ROWS, ny = min(RZ_ROWS, L.lh - y0);
+    __syncthreads();                                   // the previous tile's row coefficients are no longer read
+    if ((int)threadIdx.x < ny) {
+      int oy, cy0, cy1, my;
+      lin_coef(L.scale_y, L.row0 + y0 + (int)threadIdx.x, L.sh, oy, cy0, cy1, my);
+      s_oy[threadIdx.x] = oy; s_cy0[threadIdx.x] = cy0; s_cy1[threadIdx.x] = cy1; s_step[threadIdx.x] = my == 0 ? 1 : 0;
+    }
+    __syncthreads();
+    const int x = xc * RZ_THREADS + (int)threadIdx.x;
+    if (x >= L.lw) continue;
+    int ox, cx0, cx1, mx;
+    lin_coef(L.scale_x, x, L.sw, ox, cx0, cx1, mx);
+    // outside the interpolating mode the coefficients are (256, 0) and the offset is the clamped tap: the second tap is read
+    // from the same place, which gives k_resize_levels' `tap * 256` without a branch
+    const int xb = ox + (mx == 0 ? 1 : 0);
+    uint8_t* dst = pool + L.px_off + (size_t)y0 * L.ppitch + x;
+    for (int r = 0; r < ny; ++r) {
+      const uint8_t* a = L.src + (size_t)s_oy[r] * L.spitch;
+      const uint8_t* b = a + (size_t)s_step[r] * L.spitch;
+      const uint32_t ha = (uint32_t)a[ox] * cx0 + (uint32_t)a[xb] * cx1, hb = (uint32_t)b[ox] * cx0 + (uint32_t)b[xb] * cx1;
+      dst[(size_t)r * L.ppitch] = (uint8_t)((ha * (uint32_t)s_cy0[r] + hb * (uint32_t)s_cy1[r] + 32768u) >> 16);
+    }
+  }
+}
+// fills LevelDesc::rows_base with the level's first tile of k_resize_tiles; returns the number of tiles
+static int resize_tiles(std::vector<LevelDesc>& levels) {
+  long long n = 0;
+  for (LevelDesc& L : levels) {
+    L.rows_base = (int)n;
+    n += (long long)((L.lh + RZ_ROWS - 1) / RZ_ROWS) * ((L.lw + RZ_THREADS - 1) / RZ_THREADS);
+  }
+  return (int)std::min<long long>(n, INT_MAX);
+}
+
 // copy every window of the batch out of its pyramid level into consecutive slots dst[first .. first+n)
 __global__ void k_gather_windows(const LevelDesc* __restrict__ levels, int nlevels, const uint8_t* __restrict__ pool, int W, int H,
                                  long long nwin, uint8_t* __restrict__ dst) {
@@ -2471,13 +2520,16 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     // ---- GPU: levels, gather, integrals, cascade ----
     const bool direct = m->stages.empty();       // stage 0: every window passes, gather straight into the training slots
     long long take_direct = 0;
+    int rz_tiles = 0;
     if (!level_path) {
       CC_CHECK(ensure_scratch(ctx, m, (direct || hog_win) ? 1 : (int)nwin, bt.pool_px, (int)bt.levels.size(), direct ? 1 : nwin));
+      if (hog_win) rz_tiles = resize_tiles(bt.levels);
       CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (!level_path) {
       ScopedTimer tm(ctx, "mine", hog_win ? 1 : 2);
-      k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
+      if (hog_win) k_resize_tiles<<<std::min(rz_tiles, ctx->sm_count * 64), RZ_THREADS, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), rz_tiles, m->d_pool);
+      else k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
       CC_CUDA(cudaGetLastError());
       if (direct) {
         // how many windows does the serial rule consume?  all pass, so got grows with consumed
@@ -2761,10 +2813,12 @@ int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64
       return CC_OK;
     }
     CC_CHECK(ensure_scratch(ctx, m, hog_win ? 1 : nwin, bt.pool_px, (int)bt.levels.size(), nwin));
+    const int rz_tiles = hog_win ? resize_tiles(bt.levels) : 0;
     CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     {
       ScopedTimer tm(ctx, "mine", hog_win ? 1 : 2);
-      k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
+      if (hog_win) k_resize_tiles<<<std::min(rz_tiles, ctx->sm_count * 64), RZ_THREADS, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), rz_tiles, m->d_pool);
+      else k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
       if (!hog_win)
         k_gather_windows<<<grid_for(ctx, (long long)nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
       CC_CUDA(cudaGetLastError());
