@@ -311,7 +311,8 @@ struct HogWinGeom {
   int ss;          // row stride of the row-prefix array, floats (odd)
   int Sc, Pc;      // compact plane: row stride W / HOG_GRID + 1, entries per plane
   int groups, rows;
-  int off_bin, off_S;
+  int spb;         // bytes per staged pixel row: the aligned 32-bit words that cover W bytes at any byte offset (odd in words)
+  int off_bin, off_S, off_px;
   size_t smem;
 };
 static HogWinGeom hog_win_geometry(int W, int H) {
@@ -325,78 +326,124 @@ static HogWinGeom hog_win_geometry(int W, int H) {
   const size_t tile = std::max((size_t)H * g.ms * 4, (size_t)10 * g.Pc * 4);      // the planes reuse the magnitude tile
   g.off_bin = (int)((tile + 15) & ~(size_t)15);
   g.off_S = (int)(((size_t)g.off_bin + (size_t)H * g.bs + 15) & ~(size_t)15);
-  g.smem = (size_t)g.off_S + std::max((size_t)g.rows * g.ss * 4, (size_t)W * H);      // the pixel tile lives where S goes later
+  g.spb = (((W + 6) / 4) | 1) * 4;
+  g.off_px = (int)(((size_t)g.off_S + (size_t)g.rows * g.ss * 4 + 15) & ~(size_t)15);
+  g.smem = (size_t)g.off_px + (size_t)H * g.spb;
   return g;
 }
 
 constexpr int HOGW_THREADS = 256;
-constexpr int HOGW_LB = 6;            // pixels per load batch of a thread
+constexpr int HOGW_GB = 4;            // rows per table-lookup batch of a column thread
+constexpr int HOGW_BLK = 64;          // windows per entry of the window -> level table
 // run += g if the pixel's bin is `want` -- one predicated FADD (written in PTX: the compiler turns the C++ form of nine
 // mutually exclusive tests into a divergent decision tree)
 __device__ __forceinline__ void hog_add_if(float& run, uint32_t q, uint32_t want, float gg) {
   asm("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, %2;\n\t@p add.rn.f32 %0, %0, %3;\n\t}" : "+f"(run) : "r"(q), "r"(want), "f"(gg));
 }
+// level of every HOGW_BLK-th window of the batch, so that a window finds its level with one load and a short forward walk
+__global__ void k_hog_block_levels(const LevelDesc* __restrict__ levels, int nlevels, long long nwin, int* __restrict__ blk) {
+  const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (b * HOGW_BLK >= nwin) return;
+  const long long wi = b * HOGW_BLK;
+  int lo = 0, hi = nlevels - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= wi) lo = mid; else hi = mid - 1; }
+  blk[b] = lo;
+}
+struct HogWinDesc { long long org; int pp, pad; };      // first pixel of the window in the level pool, row pitch of its level
+__device__ __forceinline__ HogWinDesc hog_win_locate(const LevelDesc* __restrict__ levels, int nlevels, const int* __restrict__ blk, long long wi) {
+  int lo = blk[wi / HOGW_BLK];
+  while (lo + 1 < nlevels && levels[lo + 1].w_base <= wi) ++lo;
+  const LevelDesc& L = levels[lo];
+  const int k = (int)(wi - L.w_base + L.w_skip);
+  const int iy = k / L.nx, ix = k - iy * L.nx;
+  HogWinDesc d;
+  d.pp = L.ppitch; d.pad = 0;
+  d.org = L.px_off + (long long)(L.y0 + iy * L.step_y) * L.ppitch + (L.x0 + ix * L.step_x);
+  return d;
+}
 __global__ void __launch_bounds__(HOGW_THREADS, 3)
-k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const uint8_t* __restrict__ pool, const float2* __restrict__ lut,
-                     HogWinGeom g, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
+k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const int* __restrict__ blk, const uint8_t* __restrict__ pool,
+                     const float2* __restrict__ lut, HogWinGeom g, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
                      const int* __restrict__ tree_first, const DevStageRef* __restrict__ stages, int nstages, long long nwin,
                      unsigned int* __restrict__ surv_count, unsigned int* __restrict__ surv, unsigned int surv_cap) {
   extern __shared__ __align__(16) unsigned char hw_smem[];
+  __shared__ HogWinDesc s_desc[4];                                  // ring: iteration it reads [it & 3], the idle warp fills [(it + 2) & 3]
   float* smag = reinterpret_cast<float*>(hw_smem);                  // [H][ms]
   float* planes = smag;                                             // [10][Pc] once the row prefixes are taken
   uint8_t* sbin = hw_smem + g.off_bin;                              // [H][bs]
   float* S = reinterpret_cast<float*>(hw_smem + g.off_S);           // [rows][ss]: row prefix of plane b behind pixel group c at [c * 10 + b]
-  uint8_t* spx = hw_smem + g.off_S;                                 // [H][W] window pixels, until the gradients are taken
+  uint8_t* spx = hw_smem + g.off_px;                                // [H][spb] pixel rows as the aligned words that hold them
+  const uint32_t spx_s = (uint32_t)__cvta_generic_to_shared(spx);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NW = HOGW_THREADS / 32;
   const int W = g.W, H = g.H;
-  for (long long wi = blockIdx.x; wi < nwin; wi += gridDim.x) {
-    int lo = 0, hi = nlevels - 1;
-    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= wi) lo = mid; else hi = mid - 1; }
-    const LevelDesc& L = levels[lo];
-    const long long k = wi - L.w_base + L.w_skip;
-    const int iy = (int)(k / L.nx), ix = (int)(k - (long long)iy * L.nx);
-    const int pp = L.ppitch;
-    const long long org = L.px_off + (long long)(L.y0 + iy * L.step_y) * pp + (L.x0 + ix * L.step_x);
-    __syncthreads();                                   // the previous window's cascade has finished reading the planes
-    // ---- the window's pixels (loads issued in batches before their first use: one L2 round trip per batch) ----
+  // asynchronous copy of a window's pixel rows into spx (4-byte cp.async: a row starts at any byte, so the words that hold it
+  // are copied and the row is read at offset (address & 3)); lands before the next cp.async.wait_group 0
+  auto prefetch = [&](const HogWinDesc d) {
+    const int nw = g.spb / 4, total = H * nw;
+    int row = tid / nw, w = tid - row * nw;
+    const int drow = HOGW_THREADS / nw, dw = HOGW_THREADS - drow * nw;
+    for (int i = tid; i < total; i += HOGW_THREADS) {
+      const long long a = (d.org + (long long)row * d.pp) & ~3ll;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(spx_s + (uint32_t)(row * g.spb + w * 4)), "l"(pool + a + w * 4) : "memory");
+      w += dw; row += drow;
+      if (w >= nw) { w -= nw; ++row; }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (tid == 0) {
+    s_desc[0] = hog_win_locate(levels, nlevels, blk, blockIdx.x);
+    if ((long long)blockIdx.x + gridDim.x < nwin) s_desc[1] = hog_win_locate(levels, nlevels, blk, (long long)blockIdx.x + gridDim.x);
+  }
+  __syncthreads();
+  prefetch(s_desc[0]);
+  int it = 0;
+  for (long long wi = blockIdx.x; wi < nwin; wi += gridDim.x, ++it) {
+    const HogWinDesc d = s_desc[it & 3];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                   // this window's pixels have landed; the previous window's cascade has finished reading the planes
+    // ---- magnitude and bin of every pixel: central differences with the window's replicated border, table lookup.  A thread
+    // walks down one column of a segment of rows (the pixel above / below slides through registers) ----
     {
-      const uint8_t* px = pool + org;
-      const int npx = W * H;
-      int y = tid / W, x = tid - y * W;
-      const int dyq = HOGW_THREADS / W, dxr = HOGW_THREADS - dyq * W;      // (y, x) of pixel i + HOGW_THREADS from those of pixel i
-      for (int i0 = tid; i0 < npx; i0 += HOGW_THREADS * HOGW_LB) {
-        uint8_t v[HOGW_LB];
-        int o[HOGW_LB];
+      const int nseg = HOGW_THREADS / W, seg = tid / W, x = tid - seg * W;
+      const int rs = (H + nseg - 1) / nseg;
+      const int ya = seg * rs, yb = min(H, ya + rs);
+      if (seg < nseg && ya < yb) {
+        const int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
+        const int o3 = (int)(d.org & 3), p3 = d.pp & 3;
+        auto rowp = [&](int y) -> const uint8_t* { return spx + y * g.spb + ((o3 + y * p3) & 3); };
+        int prev = rowp(max(ya - 1, 0))[x], cur = rowp(ya)[x];
+        for (int y0 = ya; y0 < yb; y0 += HOGW_GB) {
+          int idx[HOGW_GB];
 #pragma unroll
-        for (int r = 0; r < HOGW_LB; ++r) {
-          o[r] = i0 + r * HOGW_THREADS;
-          if (o[r] < npx) v[r] = px[(long long)y * pp + x];
-          x += dxr; y += dyq;
-          if (x >= W) { x -= W; ++y; }
+          for (int r = 0; r < HOGW_GB; ++r) {
+            const int y = y0 + r;
+            idx[r] = -1;
+            if (y < yb) {
+              const uint8_t* rc = rowp(y);
+              const int nxt = rowp(min(y + 1, H - 1))[x];
+              idx[r] = (nxt - prev + 255) * HOG_LUT_W + ((int)rc[xp] - (int)rc[xm] + 255);
+              prev = cur; cur = nxt;
+            }
+          }
+          float2 e[HOGW_GB];
+#pragma unroll
+          for (int r = 0; r < HOGW_GB; ++r)
+            if (idx[r] >= 0) e[r] = __ldg(lut + idx[r]);
+#pragma unroll
+          for (int r = 0; r < HOGW_GB; ++r)
+            if (idx[r] >= 0) { smag[(y0 + r) * g.ms + x] = e[r].x; sbin[(y0 + r) * g.bs + x] = (uint8_t)__float_as_int(e[r].y); }
         }
-#pragma unroll
-        for (int r = 0; r < HOGW_LB; ++r)
-          if (o[r] < npx) spx[o[r]] = v[r];
       }
     }
     __syncthreads();
-    // ---- magnitude and bin of every pixel: central differences with the window's replicated border, table lookup ----
+    // the pixel tile is free: start the copy of the next window; the last warp (idle in the row pass of windows up to 112 rows)
+    // looks up the window after that
     {
-      int y = tid / W, x = tid - y * W;
-      const int dyq = HOGW_THREADS / W, dxr = HOGW_THREADS - dyq * W;
-      for (int i = tid; i < W * H; i += HOGW_THREADS) {
-        const uint8_t* rowp = spx + y * W;
-        const int dx = (int)rowp[min(x + 1, W - 1)] - (int)rowp[max(x - 1, 0)];
-        const int dy = (int)spx[min(y + 1, H - 1) * W + x] - (int)spx[max(y - 1, 0) * W + x];
-        const float2 e = __ldg(lut + (dy + 255) * HOG_LUT_W + (dx + 255));
-        smag[y * g.ms + x] = e.x;
-        sbin[y * g.bs + x] = (uint8_t)__float_as_int(e.y);
-        x += dxr; y += dyq;
-        if (x >= W) { x -= W; ++y; }
-      }
+      const long long wn = wi + gridDim.x;
+      if (wn < nwin) prefetch(s_desc[(it + 1) & 3]);
+      if (tid == HOGW_THREADS - 1 && wn + gridDim.x < nwin) s_desc[(it + 2) & 3] = hog_win_locate(levels, nlevels, blk, wn + gridDim.x);
     }
-    __syncthreads();
     // ---- row prefixes (strSum of src/HOGfeatures.cpp:240-252): two threads walk one row, the first with bins 0..4, the second
     // with bins 5..8 and the norm plane; only the matching bin and the norm plane change at a pixel (the other planes add +0,
     // which leaves an f32 sum unchanged) ----
@@ -1148,6 +1195,8 @@ struct MineState {
   unsigned int* h_surv = nullptr;      // pinned mirror (count + list) shared by the slot path and the tile miner
   size_t h_surv_cap = 0;               // entries
   float2* d_hog_lut = nullptr;         // HOG miner: (magnitude, bin) of every (dx, dy) pair, see k_hog_lut_init
+  int* d_hog_blk = nullptr;            // HOG miner: level of every HOGW_BLK-th window of the batch
+  size_t hog_blk_cap = 0;
   // whole-level fast path (Haar / LBP)
   std::vector<LvlFeat> lfeats;         // parallel to `nodes`
   LvlFeat* d_lfeats = nullptr;
@@ -1214,6 +1263,7 @@ static void free_scratch(MineState* m) {
   cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
   cudaFreeHost(m->h_surv); m->h_surv = nullptr; m->h_surv_cap = 0;
   cudaFree(m->d_hog_lut); m->d_hog_lut = nullptr;
+  cudaFree(m->d_hog_blk); m->d_hog_blk = nullptr; m->hog_blk_cap = 0;
   cudaFree(m->d_psum); cudaFree(m->d_psq); cudaFree(m->d_ptilt);
   m->d_psum = m->d_psq = m->d_ptilt = nullptr; m->plane_cap = 0;
   cudaFree(m->d_list[0]); cudaFree(m->d_list[1]); cudaFree(m->d_counts); cudaFree(m->d_order);
@@ -1276,7 +1326,7 @@ static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, i
   }
   if (pool_px > m->pool_cap) {
     cudaFree(m->d_pool);
-    CC_CUDA(cudaMalloc(&m->d_pool, pool_px));
+    CC_CUDA(cudaMalloc(&m->d_pool, pool_px + 64));      // slack: the HOG miner copies the aligned words around a row
     m->pool_cap = pool_px;
   }
   if (nlevels > m->levels_cap) {
@@ -1525,7 +1575,7 @@ static int eval_scratch(cc_ctx* ctx, MineState* m, int n, std::vector<unsigned>&
 // HOG miner (see k_hog_window_cascade): the batch's levels are in m->d_pool / m->d_levels; returns sorted survivors
 constexpr long long HOG_WINDOW_MAX_BATCH = 8 << 20;
 static bool use_hog_window_path(const cc_ctx* ctx, const MineState* m) {
-  if (ctx->ftype != CC_FEATURE_HOG || m->force_slots || m->stages.empty() || ctx->W < 3 || ctx->H < 3) return false;
+  if (ctx->ftype != CC_FEATURE_HOG || m->force_slots || m->stages.empty() || ctx->W < 3 || ctx->H < 3 || ctx->W > HOGW_THREADS) return false;
   return hog_win_geometry(ctx->W, ctx->H).smem <= (size_t)200 * 1024;
 }
 static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nwin, std::vector<unsigned>& survivors) {
@@ -1536,14 +1586,22 @@ static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nw
     k_hog_lut_init<<<(HOG_LUT_N + 255) / 256, 256, 0, ctx->stream>>>(m->d_hog_lut);
     CC_CUDA(cudaGetLastError());
   }
+  const size_t nblk = (size_t)((nwin + HOGW_BLK - 1) / HOGW_BLK);
+  if (nblk > m->hog_blk_cap) {
+    cudaFree(m->d_hog_blk); m->d_hog_blk = nullptr; m->hog_blk_cap = 0;
+    CC_CUDA(cudaMalloc(&m->d_hog_blk, sizeof(int) * (nblk + nblk / 4)));
+    m->hog_blk_cap = nblk + nblk / 4;
+  }
   const HogWinGeom g = hog_win_geometry(ctx->W, ctx->H);
   {
-    ScopedTimer tm(ctx, "mine", 1);
+    ScopedTimer tm(ctx, "mine", 2);
+    k_hog_block_levels<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(m->d_levels, nlevels, nwin, m->d_hog_blk);
+    CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaMemsetAsync(m->d_surv, 0, sizeof(unsigned), ctx->stream));
     CC_CUDA(cudaFuncSetAttribute(k_hog_window_cascade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int per_sm = std::max(1, (int)((size_t)227 * 1024 / (g.smem + 1024)));
     const int grid = (int)std::min<long long>(nwin, (long long)ctx->sm_count * per_sm * 4);
-    k_hog_window_cascade<<<grid, HOGW_THREADS, g.smem, ctx->stream>>>(m->d_levels, nlevels, m->d_pool, m->d_hog_lut, g, ctx->d_hog_taps, m->d_nodes,
+    k_hog_window_cascade<<<grid, HOGW_THREADS, g.smem, ctx->stream>>>(m->d_levels, nlevels, m->d_hog_blk, m->d_pool, m->d_hog_lut, g, ctx->d_hog_taps, m->d_nodes,
                                                                        m->d_tree_first, m->d_stages, (int)m->stages.size(), nwin, m->d_surv, m->d_surv + 1,
                                                                        m->surv_cap);
     CC_CUDA(cudaGetLastError());

@@ -29,6 +29,6 @@ print("%s: %d stages in %.2f s" % (cfg, len(cc.stageClassifiers), time.time() - 
 for t, r in zip(cc.timings, cc.reports):
     print("  stage %2d: weak %3d  mine %7.3f s  train %6.3f s  neg consumed %10d  acceptanceRatio %.3g" %
           (t["stage"], t["weak"], t["mine_s"], t["train_s"], r["neg_consumed"], r["acceptance_ratio"]))
-for name in ["integral", "precalc", "sort", "split_search", "boost_small", "mine"]:
+for name in ["integral", "precalc", "sort", "split_search", "boost_small", "mine", "mine_host_assemble", "mine_host_eval", "mine_host_cut", "mine_host_alloc"]:
     ms, k = ctx.timing(name)
-    print("   %-13s %9.3f ms  launches %d" % (name, ms, k))
+    print("   %-18s %9.3f ms  launches %d" % (name, ms, k))
