@@ -361,21 +361,88 @@ __device__ __forceinline__ HogWinDesc hog_win_locate(const LevelDesc* __restrict
   d.org = L.px_off + (long long)(L.y0 + iy * L.step_y) * L.ppitch + (L.x0 + ix * L.step_x);
   return d;
 }
+// shared-memory accesses of the gradient pass through 32-bit shared-window addresses (plain LDS / STS with one address add)
+__device__ __forceinline__ int hog_lds_u8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return (int)v; }
+__device__ __forceinline__ void hog_sts_f32(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void hog_sts_u8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+// a column thread of the gradient pass: walks down column x of a segment of rows; the pixel above / below slides through registers
+struct HogGradCol {
+  uint32_t row;         // shared address of the current pixel row (before its byte shift)
+  int sh;               // byte shift of the current row: (address of its first pixel in the pool) & 3
+  int prev, cur;        // pixel (y - 1, x) with the border replicated, pixel (y, x)
+  uint32_t sm, sb;      // shared addresses of smag[y][x], sbin[y][x]
+  int y;
+};
+template <int GB>
+__device__ __forceinline__ void hog_grad_rows(HogGradCol& st, int x, int xm, int xp, int p3, int H, int spb, int ms4, int bs,
+                                              const float2* __restrict__ lut) {
+  int idx[GB];
+#pragma unroll
+  for (int r = 0; r < GB; ++r) {
+    const int lf = hog_lds_u8(st.row + st.sh + xm), rt = hog_lds_u8(st.row + st.sh + xp);
+    const bool last = st.y + 1 >= H;                                  // last row: the pixel below is the pixel itself
+    const int shn = (st.sh + p3) & 3;
+    const int nxt = hog_lds_u8(last ? st.row + st.sh + x : st.row + spb + shn + x);
+    idx[r] = (nxt - st.prev + 255) * HOG_LUT_W + (rt - lf + 255);
+    st.prev = st.cur; st.cur = nxt; st.row += spb; st.sh = shn; ++st.y;
+  }
+  float2 e[GB];
+#pragma unroll
+  for (int r = 0; r < GB; ++r) e[r] = __ldg(lut + idx[r]);
+#pragma unroll
+  for (int r = 0; r < GB; ++r) {
+    hog_sts_f32(st.sm, e[r].x);
+    hog_sts_u8(st.sb, (uint32_t)__float_as_int(e[r].y));
+    st.sm += ms4; st.sb += bs;
+  }
+}
+
+// cascade on the compact planes of one window (a warp): lane t walks weak tree t of the stage, the leaf values are added in tree order
+__device__ __forceinline__ bool hog_window_predict(const float* planes, int Pc, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
+                                                   const int* __restrict__ tree_first, const DevStageRef* __restrict__ stages, int nstages, int lane) {
+  EvalView e;
+  e.ftype = CC_FEATURE_HOG; e.P = Pc; e.ns_pad = 1;
+  e.sum = nullptr; e.tilted = nullptr; e.nf = nullptr; e.hog = planes;
+  e.haar_taps = nullptr; e.lbp_taps = nullptr; e.hog_taps = taps;
+  bool pass = true;
+  for (int st = 0; st < nstages && pass; ++st) {
+    const DevStageRef sr = stages[st];
+    double sum = 0;
+    for (int t0 = 0; t0 < sr.num_trees; t0 += 32) {
+      double v = 0;
+      if (t0 + lane < sr.num_trees) {
+        const DevNode* tree = nodes + tree_first[sr.first_tree + t0 + lane];
+        int nd = 0;
+        while (tree[nd].left >= 0) {
+          const float val = m_hog_value(taps[tree[nd].var_idx / 36], e, tree[nd].var_idx % 36, 0);
+          nd = val <= tree[nd].c ? tree[nd].left : tree[nd].right;
+        }
+        v = tree[nd].value;
+      }
+      const int cnt = min(32, sr.num_trees - t0);
+      for (int i = 0; i < cnt; ++i) sum += __shfl_sync(0xffffffffu, v, i);
+    }
+    if (sum < (double)(sr.threshold - 0.00001F)) pass = false;
+  }
+  return pass;
+}
+
+constexpr int HOGW_MAXQ = 32;         // kept plane rows per window (H / HOG_GRID) held in registers by the column pass
 __global__ void __launch_bounds__(HOGW_THREADS, 3)
 k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const int* __restrict__ blk, const uint8_t* __restrict__ pool,
                      const float2* __restrict__ lut, HogWinGeom g, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
                      const int* __restrict__ tree_first, const DevStageRef* __restrict__ stages, int nstages, long long nwin,
                      unsigned int* __restrict__ surv_count, unsigned int* __restrict__ surv, unsigned int surv_cap) {
   extern __shared__ __align__(16) unsigned char hw_smem[];
-  __shared__ HogWinDesc s_desc[4];                                  // ring: iteration it reads [it & 3], the idle warp fills [(it + 2) & 3]
+  __shared__ HogWinDesc s_desc[4];                                  // ring: iteration it reads [it & 3], the last thread fills [(it + 2) & 3]
   float* smag = reinterpret_cast<float*>(hw_smem);                  // [H][ms]
-  float* planes = smag;                                             // [10][Pc] once the row prefixes are taken
   uint8_t* sbin = hw_smem + g.off_bin;                              // [H][bs]
   float* S = reinterpret_cast<float*>(hw_smem + g.off_S);           // [rows][ss]: row prefix of plane b behind pixel group c at [c * 10 + b]
+  float* planes = S;                                                // [10][Pc] compact planes of the window, once the column pass has read S
   uint8_t* spx = hw_smem + g.off_px;                                // [H][spb] pixel rows as the aligned words that hold them
   const uint32_t spx_s = (uint32_t)__cvta_generic_to_shared(spx);
+  const uint32_t smag_s = (uint32_t)__cvta_generic_to_shared(smag), sbin_s = (uint32_t)__cvta_generic_to_shared(sbin);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = HOGW_THREADS / 32;
   const int W = g.W, H = g.H;
   // asynchronous copy of a window's pixel rows into spx (4-byte cp.async: a row starts at any byte, so the words that hold it
   // are copied and the row is read at offset (address & 3)); lands before the next cp.async.wait_group 0
@@ -391,6 +458,13 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const in
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  auto report = [&](long long wi) {      // warp 0: cascade on the planes of window wi
+    const bool pass = hog_window_predict(planes, g.Pc, taps, nodes, tree_first, stages, nstages, lane);
+    if (pass && lane == 0) {
+      const unsigned pos = atomicAdd(surv_count, 1u);
+      if (pos < surv_cap) surv[pos] = (unsigned)wi;
+    }
+  };
   if (tid == 0) {
     s_desc[0] = hog_win_locate(levels, nlevels, blk, blockIdx.x);
     if ((long long)blockIdx.x + gridDim.x < nwin) s_desc[1] = hog_win_locate(levels, nlevels, blk, (long long)blockIdx.x + gridDim.x);
@@ -398,47 +472,35 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const in
   __syncthreads();
   prefetch(s_desc[0]);
   int it = 0;
+  long long prev_wi = -1;
   for (long long wi = blockIdx.x; wi < nwin; wi += gridDim.x, ++it) {
     const HogWinDesc d = s_desc[it & 3];
     asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();                                   // this window's pixels have landed; the previous window's cascade has finished reading the planes
-    // ---- magnitude and bin of every pixel: central differences with the window's replicated border, table lookup.  A thread
-    // walks down one column of a segment of rows (the pixel above / below slides through registers) ----
-    {
-      const int nseg = HOGW_THREADS / W, seg = tid / W, x = tid - seg * W;
-      const int rs = (H + nseg - 1) / nseg;
+    __syncthreads();                                   // this window's pixels have landed; the previous window's planes are complete
+    if (warp == 0) {
+      // ---- the cascade of the PREVIOUS window runs beside this window's gradient pass ----
+      if (prev_wi >= 0) report(prev_wi);
+    } else {
+      // ---- magnitude and bin of every pixel: central differences with the window's replicated border, table lookup ----
+      const int gt = tid - 32, nseg = (HOGW_THREADS - 32) / W, seg = gt / W, x = gt - seg * W;
+      const int rs = (((H + nseg - 1) / nseg + HOGW_GB - 1) / HOGW_GB) * HOGW_GB;
       const int ya = seg * rs, yb = min(H, ya + rs);
       if (seg < nseg && ya < yb) {
         const int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
         const int o3 = (int)(d.org & 3), p3 = d.pp & 3;
-        auto rowp = [&](int y) -> const uint8_t* { return spx + y * g.spb + ((o3 + y * p3) & 3); };
-        int prev = rowp(max(ya - 1, 0))[x], cur = rowp(ya)[x];
-        for (int y0 = ya; y0 < yb; y0 += HOGW_GB) {
-          int idx[HOGW_GB];
-#pragma unroll
-          for (int r = 0; r < HOGW_GB; ++r) {
-            const int y = y0 + r;
-            idx[r] = -1;
-            if (y < yb) {
-              const uint8_t* rc = rowp(y);
-              const int nxt = rowp(min(y + 1, H - 1))[x];
-              idx[r] = (nxt - prev + 255) * HOG_LUT_W + ((int)rc[xp] - (int)rc[xm] + 255);
-              prev = cur; cur = nxt;
-            }
-          }
-          float2 e[HOGW_GB];
-#pragma unroll
-          for (int r = 0; r < HOGW_GB; ++r)
-            if (idx[r] >= 0) e[r] = __ldg(lut + idx[r]);
-#pragma unroll
-          for (int r = 0; r < HOGW_GB; ++r)
-            if (idx[r] >= 0) { smag[(y0 + r) * g.ms + x] = e[r].x; sbin[(y0 + r) * g.bs + x] = (uint8_t)__float_as_int(e[r].y); }
-        }
+        const int yp = max(ya - 1, 0);
+        HogGradCol st;
+        st.row = spx_s + (uint32_t)(ya * g.spb); st.sh = (o3 + ya * p3) & 3; st.y = ya;
+        st.prev = hog_lds_u8(spx_s + (uint32_t)(yp * g.spb + ((o3 + yp * p3) & 3) + x));
+        st.cur = hog_lds_u8(st.row + st.sh + x);
+        st.sm = smag_s + (uint32_t)((ya * g.ms + x) * 4); st.sb = sbin_s + (uint32_t)(ya * g.bs + x);
+        while (st.y + HOGW_GB <= yb) hog_grad_rows<HOGW_GB>(st, x, xm, xp, p3, H, g.spb, g.ms * 4, g.bs, lut);
+        while (st.y < yb) hog_grad_rows<1>(st, x, xm, xp, p3, H, g.spb, g.ms * 4, g.bs, lut);
       }
     }
     __syncthreads();
-    // the pixel tile is free: start the copy of the next window; the last warp (idle in the row pass of windows up to 112 rows)
-    // looks up the window after that
+    // the pixel tile and the planes are free: start the copy of the next window; the last thread (idle in the row pass of
+    // windows up to 112 rows) looks up the window after that
     {
       const long long wn = wi + gridDim.x;
       if (wn < nwin) prefetch(s_desc[(it + 1) & 3]);
@@ -469,16 +531,33 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const in
     }
     __syncthreads();
     // ---- column accumulation: plane[y + 1][4 (c + 1)] = plane[y][4 (c + 1)] + strSum; only rows / columns that are multiples of
-    // HOG_GRID are kept (the compact planes of k_hog_integrals) ----
-    for (int j = tid; j < g.groups * 10; j += HOGW_THREADS) {
-      const int c = j / 10, b = j - c * 10;
-      float* pl = planes + b * g.Pc + (c + 1);
-      float col = 0.f;
-      for (int y = 0; y < g.rows; y += HOG_GRID) {
+    // HOG_GRID are kept (the compact planes of k_hog_integrals).  The planes go where S is, so the kept values wait in registers
+    // until every thread has read its column of S ----
+    const int nq = g.rows / HOG_GRID;
+    for (int j0 = 0; j0 < g.groups * 10; j0 += HOGW_THREADS) {
+      const int j = j0 + tid;
+      const bool on = j < g.groups * 10;
+      float keep[HOGW_MAXQ];
+      if (on) {
+        float col = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < HOG_GRID; ++kk) col = __fadd_rn(col, S[(y + kk) * g.ss + j]);
-        pl[(y / HOG_GRID + 1) * g.Sc] = col;
+        for (int q = 0; q < HOGW_MAXQ; ++q) {
+          if (q < nq) {
+#pragma unroll
+            for (int kk = 0; kk < HOG_GRID; ++kk) col = __fadd_rn(col, S[(q * HOG_GRID + kk) * g.ss + j]);
+            keep[q] = col;
+          }
+        }
       }
+      __syncthreads();
+      if (on) {
+        const int c = j / 10, b = j - c * 10;
+        float* pl = planes + b * g.Pc + (c + 1);
+#pragma unroll
+        for (int q = 0; q < HOGW_MAXQ; ++q)
+          if (q < nq) pl[(q + 1) * g.Sc] = keep[q];
+      }
+      if (j0 + HOGW_THREADS < g.groups * 10) __syncthreads();      // (windows wider than 100 pixels: the next round of columns reads S)
     }
     {
       const int nr = H / HOG_GRID + 1;                 // first row and first column of every plane are zero
@@ -487,39 +566,10 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const in
         planes[b * g.Pc + (e < g.Sc ? e : (e - g.Sc) * g.Sc)] = 0.f;
       }
     }
-    __syncthreads();
-    // ---- cascade (warp 0): lane t walks weak tree t of the stage, the leaf values are added in tree order ----
-    if (warp == 0) {
-      EvalView e;
-      e.ftype = CC_FEATURE_HOG; e.P = g.Pc; e.ns_pad = 1;
-      e.sum = nullptr; e.tilted = nullptr; e.nf = nullptr; e.hog = planes;
-      e.haar_taps = nullptr; e.lbp_taps = nullptr; e.hog_taps = taps;
-      bool pass = true;
-      for (int st = 0; st < nstages && pass; ++st) {
-        const DevStageRef sr = stages[st];
-        double sum = 0;
-        for (int t0 = 0; t0 < sr.num_trees; t0 += 32) {
-          double v = 0;
-          if (t0 + lane < sr.num_trees) {
-            const DevNode* tree = nodes + tree_first[sr.first_tree + t0 + lane];
-            int nd = 0;
-            while (tree[nd].left >= 0) {
-              const float val = m_hog_value(taps[tree[nd].var_idx / 36], e, tree[nd].var_idx % 36, 0);
-              nd = val <= tree[nd].c ? tree[nd].left : tree[nd].right;
-            }
-            v = tree[nd].value;
-          }
-          const int cnt = min(32, sr.num_trees - t0);
-          for (int i = 0; i < cnt; ++i) sum += __shfl_sync(0xffffffffu, v, i);
-        }
-        if (sum < (double)(sr.threshold - 0.00001F)) pass = false;
-      }
-      if (pass && lane == 0) {
-        const unsigned pos = atomicAdd(surv_count, 1u);
-        if (pos < surv_cap) surv[pos] = (unsigned)wi;
-      }
-    }
+    prev_wi = wi;
   }
+  __syncthreads();
+  if (warp == 0 && prev_wi >= 0) report(prev_wi);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1324,20 +1374,25 @@ static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, i
     CC_CHECK(store_alloc(ctx, m->scratch, nwin));
     m->scratch_cap = nwin;
   }
+  // (capacities grow geometrically: batches grow with the falling acceptance rate, and a cudaFree + cudaMalloc of gigabytes per batch
+  // costs more than the batch)
   if (pool_px > m->pool_cap) {
-    cudaFree(m->d_pool);
-    CC_CUDA(cudaMalloc(&m->d_pool, pool_px + 64));      // slack: the HOG miner copies the aligned words around a row
-    m->pool_cap = pool_px;
+    cudaFree(m->d_pool); m->d_pool = nullptr; m->pool_cap = 0;
+    const size_t cap = pool_px + pool_px / 2;
+    CC_CUDA(cudaMalloc(&m->d_pool, cap + 64));          // slack: the HOG miner copies the aligned words around a row
+    m->pool_cap = cap;
   }
   if (nlevels > m->levels_cap) {
-    cudaFree(m->d_levels);
-    CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * nlevels));
-    m->levels_cap = nlevels;
+    cudaFree(m->d_levels); m->d_levels = nullptr; m->levels_cap = 0;
+    const int cap = nlevels + nlevels / 2 + 16;
+    CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * cap));
+    m->levels_cap = cap;
   }
   if ((unsigned long long)surv_n > m->surv_cap) {
     cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
-    CC_CUDA(cudaMalloc(&m->d_surv, sizeof(unsigned) * ((size_t)surv_n + 1)));
-    m->surv_cap = (unsigned)surv_n;
+    const size_t cap = (size_t)std::min<long long>(surv_n + surv_n / 2 + 1024, 0xFFFFFFF0ll);
+    CC_CUDA(cudaMalloc(&m->d_surv, sizeof(unsigned) * (cap + 1)));
+    m->surv_cap = (unsigned)cap;
   }
   return ensure_h_surv(m, (size_t)m->surv_cap + 1);
 }
@@ -1573,9 +1628,11 @@ static int eval_scratch(cc_ctx* ctx, MineState* m, int n, std::vector<unsigned>&
 }
 
 // HOG miner (see k_hog_window_cascade): the batch's levels are in m->d_pool / m->d_levels; returns sorted survivors
-constexpr long long HOG_WINDOW_MAX_BATCH = 8 << 20;
+constexpr long long HOG_WINDOW_MAX_BATCH = 2 << 20;      // ~1600 level pixels per 48x96 window: 3 GB of level pixels per batch
 static bool use_hog_window_path(const cc_ctx* ctx, const MineState* m) {
-  if (ctx->ftype != CC_FEATURE_HOG || m->force_slots || m->stages.empty() || ctx->W < 3 || ctx->H < 3 || ctx->W > HOGW_THREADS) return false;
+  if (ctx->ftype != CC_FEATURE_HOG || m->force_slots || m->stages.empty() || ctx->W < 3 || ctx->H < 3) return false;
+  // one round of the column pass (a thread per kept column and plane), kept rows in registers, a gradient segment per W threads
+  if ((ctx->W / HOG_GRID) * 10 > HOGW_THREADS || ctx->H / HOG_GRID > HOGW_MAXQ || ctx->W > HOGW_THREADS - 32) return false;
   return hog_win_geometry(ctx->W, ctx->H).smem <= (size_t)200 * 1024;
 }
 static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nwin, std::vector<unsigned>& survivors) {
@@ -2580,7 +2637,9 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     long long take_direct = 0;
     int rz_tiles = 0;
     if (!level_path) {
+      HostTimer halloc(ctx, "mine_host_alloc");
       CC_CHECK(ensure_scratch(ctx, m, (direct || hog_win) ? 1 : (int)nwin, bt.pool_px, (int)bt.levels.size(), direct ? 1 : nwin));
+      halloc.stop();
       if (hog_win) rz_tiles = resize_tiles(bt.levels);
       CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
