@@ -1252,7 +1252,7 @@ struct MineState {
   LvlFeat* d_lfeats = nullptr;
   bool cascade_tilted = false;         // some node uses a tilted feature
   bool force_unfused = false;          // cc_mine_set_mode 1: build the planes with the multi-kernel path (k_lvl_rows/diag/cols)
-  bool force_slots = false;            // cc_mine_set_mode 2: per-window scratch slots (the generic path HOG always takes)
+  bool force_slots = false;            // cc_mine_set_mode 2: per-window scratch slots (the literal setImage + predict path)
   uint32_t *d_psum = nullptr, *d_psq = nullptr, *d_ptilt = nullptr;
   size_t plane_cap = 0;
   unsigned int *d_list[2] = {nullptr, nullptr}, *d_counts = nullptr;

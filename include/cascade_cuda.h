@@ -209,8 +209,9 @@ int cc_mine_positives(cc_ctx* ctx, const uint8_t* host_vec, int vec_count, int c
                       int32_t* vec_pos, int64_t* consumed, int32_t* got);
 /* How predict() is evaluated over the window stream.  0 (default): Haar / LBP windows are evaluated from integral
  * planes of whole pyramid levels built by one fused kernel (same integers as the per-crop cv::integral of setImage,
- * src/haarfeatures.cpp:100-114), HOG from per-window slots.  1: same planes, built by separate row / diagonal /
- * column kernels.  2: per-window slots for every feature type (literal setImage + predict per window).  3: fused tile
+ * src/haarfeatures.cpp:100-114), HOG windows by the window miner (one CTA per window: gradients, integral histograms
+ * and cascade in shared memory; windows wider than 100 or taller than 128 pixels fall back to slots).  1: same planes,
+ * built by separate row / diagonal / column kernels.  2: per-window slots for every feature type (literal setImage + predict per window).  3: fused tile
  * miner -- a CTA builds a tile of a pyramid level (INTER_LINEAR_EXACT pixels, sum / sqsum / tilted integrals) in shared
  * memory and runs the cascade on its windows; nothing but survivor ordinals leaves the SM (measured 2.5x slower than
  * mode 0 on B200: 16 resident warps per SM cannot hide the serial column / diagonal walks). */

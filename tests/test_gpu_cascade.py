@@ -375,7 +375,7 @@ _CASCADES = [
     (orc.HAAR, orc.CORE, 20, 28, 150, 250, 3, (190, 170), dict(max_depth=2)),                # depth-2 trees in the mining cascade
     (orc.HAAR, orc.ALL, 24, 24, 150, 250, 3, (200, 160), dict(min_hit_rate=0.95, max_false_alarm=0.4)),
     (orc.HAAR, orc.BASIC, 24, 24, 150, 250, 3, (200, 160), dict(boost_type=orc.RAB)),        # Real AdaBoost leaf values in predict()
-    (orc.HOG, 0, 48, 96, 80, 120, 2, (260, 300), dict(weak_count=6)),                        # HOG: per-window slots
+    (orc.HOG, 0, 48, 96, 80, 120, 2, (260, 300), dict(weak_count=6)),                        # HOG: the window miner (k_hog_window_cascade)
 ]
 
 
