@@ -142,6 +142,9 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
 
+    # BASELINE's other configs first (N = 1): whole cascades in their own contexts, before the headline config takes its 40 GB
+    other = other_configs_leg(local) if world == 1 and not args.no_configs else None
+
     N = NUM_POS + NUM_NEG
     stream = torch.cuda.Stream(device=dev)
     ctx = ccb.Context(local, stream=stream.cuda_stream)
@@ -271,11 +274,64 @@ def run_ours(args):
     }
     if mining is not None:
         out["mining"] = mining
+    if other is not None:
+        out["other_configs"] = other
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(imgs, labels, F, budget_s=20.0, ref_trees=int(nweak))
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+OTHER_CONFIGS = {
+    # BASELINE configs[0], [1], [3]: whole cascades through the host mirror of CvCascadeClassifier::train, reference default flags
+    "configs[0]": dict(name="traincascade Haar BASIC 24x24, 2 stages, numPos=500 numNeg=1000", ft=0, haar_mode=0, W=24, H=24, npos=500, nneg=1000, nst=2),
+    "configs[1]": dict(name="traincascade LBP 24x24, 10 stages, numPos=2000 numNeg=4000", ft=1, haar_mode=None, W=24, H=24, npos=2000, nneg=4000, nst=10),
+    "configs[3]": dict(name="traincascade HOG 48x96, 15 stages, numPos=4000 numNeg=8000", ft=2, haar_mode=None, W=48, H=96, npos=4000, nneg=8000, nst=15),
+}
+
+
+def run_other_config(spec, device=0, nst=None):
+    """One of BASELINE's other configs, end to end on synthetic data: wall time of train() (every stage until numStages or the
+    required leaf false-alarm rate), split into mining and stage training, and the NegReader windows consumed."""
+    import io
+    import tempfile
+    import cascadeclassifier_b200 as ccb
+    from cascadeclassifier_b200 import synth
+    from cascadeclassifier_b200.cascade import CvCascadeClassifier, CvCascadeParams
+    W, H = spec["W"], spec["H"]
+    t0 = time.time()
+    pos = synth.make_positives(int(spec["npos"] * 1.2) + 64, W, H, seed=12345)
+    bgs = [synth.make_background(960, 720, 4000 + i, clutter=1.5) for i in range(24)]
+    t_data = time.time() - t0
+    ctx = ccb.Context(device)
+    cc = CvCascadeClassifier(ctx, out=io.StringIO())
+    fp = ccb.CvHaarFeatureParams(spec["haar_mode"]) if spec["ft"] == 0 else ccb.CvFeatureParams.create(spec["ft"])
+    t0 = time.time()
+    cc.train(tempfile.mkdtemp(), "pos.vec", "bg.txt", spec["npos"], spec["nneg"], 1024, 1024, nst or spec["nst"],
+             CvCascadeParams(0, spec["ft"], (W, H)), fp, ccb.CvCascadeBoostParams(), positives=pos, backgrounds=bgs)
+    ctx.synchronize()
+    wall = time.time() - t0
+    res = {"workload": spec["name"] + ", 24 generated 960x720 backgrounds", "stages_trained": len(cc.stageClassifiers),
+           "weak_per_stage": [int(t["weak"]) for t in cc.timings], "train_wall_s": wall, "mining_s": sum(t["mine_s"] for t in cc.timings),
+           "stage_training_s": sum(t["train_s"] for t in cc.timings), "neg_windows_consumed": int(sum(r["neg_consumed"] for r in cc.reports)),
+           "gpu_launches": int(ctx.launch_count()), "data_generation_s": t_data, "timings": cc.timings, "reports": cc.reports}
+    kern = {}
+    for name in ["integral", "precalc", "sort", "split_search", "boost_small", "mine", "mine_host_assemble", "mine_host_eval", "mine_host_cut", "mine_host_alloc"]:
+        ms, k = ctx.timing(name)
+        kern[name] = {"ms": ms, "launches": k}
+    res["families"] = kern
+    ctx.close()
+    return res
+
+
+def other_configs_leg(device):
+    out = {}
+    for key, spec in OTHER_CONFIGS.items():
+        r = run_other_config(spec, device)
+        r.pop("timings"); r.pop("reports")
+        out[key] = r
+    return out
 
 
 MINING_IMAGES, MINING_W, MINING_H = 4096, 1920, 1080
@@ -517,6 +573,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mining", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs[0] / [1] / [3] cascades (N = 1 only)")
     ap.add_argument("--mining-images", type=int, default=MINING_IMAGES)
     ap.add_argument("--ref-stride", type=int, default=0, help="--impl reference: every k-th feature (0 = chosen from the time budget, 1 = the full F)")
     args = ap.parse_args()

@@ -428,6 +428,8 @@ __device__ __forceinline__ bool hog_window_predict(const float* planes, int Pc, 
 }
 
 constexpr int HOGW_MAXQ = 32;         // kept plane rows per window (H / HOG_GRID) held in registers by the column pass
+// NQ: H / HOG_GRID at compile time (the column pass is fully unrolled), or 0 for any height up to HOG_GRID * HOGW_MAXQ
+template <int NQ>
 __global__ void __launch_bounds__(HOGW_THREADS, 3)
 k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const int* __restrict__ blk, const uint8_t* __restrict__ pool,
                      const float2* __restrict__ lut, HogWinGeom g, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
@@ -533,18 +535,20 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const in
     // ---- column accumulation: plane[y + 1][4 (c + 1)] = plane[y][4 (c + 1)] + strSum; only rows / columns that are multiples of
     // HOG_GRID are kept (the compact planes of k_hog_integrals).  The planes go where S is, so the kept values wait in registers
     // until every thread has read its column of S ----
-    const int nq = g.rows / HOG_GRID;
-    for (int j0 = 0; j0 < g.groups * 10; j0 += HOGW_THREADS) {
-      const int j = j0 + tid;
+    {
+      constexpr int QN = NQ ? NQ : HOGW_MAXQ;
+      const int nq = NQ ? NQ : g.rows / HOG_GRID;
+      const int j = tid;                                 // (use_hog_window_path: groups * 10 <= HOGW_THREADS, one round)
       const bool on = j < g.groups * 10;
-      float keep[HOGW_MAXQ];
+      float keep[QN];
       if (on) {
         float col = 0.f;
+        const float* sp = S + j;
 #pragma unroll
-        for (int q = 0; q < HOGW_MAXQ; ++q) {
-          if (q < nq) {
+        for (int q = 0; q < QN; ++q) {
+          if (NQ || q < nq) {
 #pragma unroll
-            for (int kk = 0; kk < HOG_GRID; ++kk) col = __fadd_rn(col, S[(q * HOG_GRID + kk) * g.ss + j]);
+            for (int kk = 0; kk < HOG_GRID; ++kk) { col = __fadd_rn(col, *sp); sp += g.ss; }
             keep[q] = col;
           }
         }
@@ -554,10 +558,9 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const in
         const int c = j / 10, b = j - c * 10;
         float* pl = planes + b * g.Pc + (c + 1);
 #pragma unroll
-        for (int q = 0; q < HOGW_MAXQ; ++q)
-          if (q < nq) pl[(q + 1) * g.Sc] = keep[q];
+        for (int q = 0; q < QN; ++q)
+          if (NQ || q < nq) { pl += g.Sc; *pl = keep[q]; }
       }
-      if (j0 + HOGW_THREADS < g.groups * 10) __syncthreads();      // (windows wider than 100 pixels: the next round of columns reads S)
     }
     {
       const int nr = H / HOG_GRID + 1;                 // first row and first column of every plane are zero
@@ -1655,12 +1658,22 @@ static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nw
     k_hog_block_levels<<<(unsigned)((nblk + 255) / 256), 256, 0, ctx->stream>>>(m->d_levels, nlevels, nwin, m->d_hog_blk);
     CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaMemsetAsync(m->d_surv, 0, sizeof(unsigned), ctx->stream));
-    CC_CUDA(cudaFuncSetAttribute(k_hog_window_cascade, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));
     const int per_sm = std::max(1, (int)((size_t)227 * 1024 / (g.smem + 1024)));
     const int grid = (int)std::min<long long>(nwin, (long long)ctx->sm_count * per_sm * 4);
-    k_hog_window_cascade<<<grid, HOGW_THREADS, g.smem, ctx->stream>>>(m->d_levels, nlevels, m->d_hog_blk, m->d_pool, m->d_hog_lut, g, ctx->d_hog_taps, m->d_nodes,
-                                                                       m->d_tree_first, m->d_stages, (int)m->stages.size(), nwin, m->d_surv, m->d_surv + 1,
-                                                                       m->surv_cap);
+#define HOGW_LAUNCH(NQ)                                                                                                                      \
+  {                                                                                                                                          \
+    CC_CUDA(cudaFuncSetAttribute(k_hog_window_cascade<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));                       \
+    k_hog_window_cascade<NQ><<<grid, HOGW_THREADS, g.smem, ctx->stream>>>(m->d_levels, nlevels, m->d_hog_blk, m->d_pool, m->d_hog_lut, g,    \
+                                                                           ctx->d_hog_taps, m->d_nodes, m->d_tree_first, m->d_stages,        \
+                                                                           (int)m->stages.size(), nwin, m->d_surv, m->d_surv + 1, m->surv_cap); \
+  }
+    switch (g.rows / HOG_GRID) {
+      case 24: HOGW_LAUNCH(24); break;      // 96 rows (BASELINE configs[3])
+      case 32: HOGW_LAUNCH(32); break;      // 128
+      case 16: HOGW_LAUNCH(16); break;      // 64
+      default: HOGW_LAUNCH(0); break;
+    }
+#undef HOGW_LAUNCH
     CC_CUDA(cudaGetLastError());
   }
   CC_CUDA(cudaMemcpyAsync(m->h_surv, m->d_surv, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));

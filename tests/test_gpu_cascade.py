@@ -194,7 +194,7 @@ def test_mining_paths_agree(gpu_ctx, tmp_path, ftype, mode):
         assert np.array_equal(r[3], results[0][3])
 
 
-@pytest.mark.parametrize("W,H,bw,bh", [(48, 96, 300, 330), (32, 40, 260, 200), (24, 24, 97, 61)])
+@pytest.mark.parametrize("W,H,bw,bh", [(48, 96, 300, 330), (32, 40, 260, 200), (24, 24, 97, 61), (32, 64, 210, 260), (64, 128, 330, 300)])
 def test_hog_miner_matches_slot_path(gpu_ctx, tmp_path, W, H, bw, bh):
     """HOG mining by level gradients + one CTA per window (k_hog_level_grad / k_hog_window_cascade, the default) must select
     exactly the windows the literal per-window path (scratch slot: setImage + predict, cc_mine_set_mode 2) selects -- same
