@@ -168,10 +168,12 @@ k_resize_tiles(const LevelDesc* __restrict__ levels, int nlevels, int ntiles, ui
     }
   }
 }
-// fills LevelDesc::rows_base with the level's first tile of k_resize_tiles; returns the number of tiles
-static int resize_tiles(std::vector<LevelDesc>& levels) {
+// fills LevelDesc::rows_base of levels [l0, l1] with the level's first tile of k_resize_tiles (launched on that range); returns the
+// number of tiles
+static int resize_tiles(std::vector<LevelDesc>& levels, int l0, int l1) {
   long long n = 0;
-  for (LevelDesc& L : levels) {
+  for (int l = l0; l <= l1; ++l) {
+    LevelDesc& L = levels[l];
     L.rows_base = (int)n;
     n += (long long)((L.lh + RZ_ROWS - 1) / RZ_ROWS) * ((L.lw + RZ_THREADS - 1) / RZ_THREADS);
   }
@@ -433,8 +435,9 @@ template <int NQ>
 __global__ void __launch_bounds__(HOGW_THREADS, 3)
 k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const int* __restrict__ blk, const uint8_t* __restrict__ pool,
                      const float2* __restrict__ lut, HogWinGeom g, const HogTaps* __restrict__ taps, const DevNode* __restrict__ nodes,
-                     const int* __restrict__ tree_first, const DevStageRef* __restrict__ stages, int nstages, long long nwin,
+                     const int* __restrict__ tree_first, const DevStageRef* __restrict__ stages, int nstages, long long w_begin, long long nwin,
                      unsigned int* __restrict__ surv_count, unsigned int* __restrict__ surv, unsigned int surv_cap) {
+  // windows [w_begin, nwin) of the batch (image-sharded mining gives every rank a contiguous slice)
   extern __shared__ __align__(16) unsigned char hw_smem[];
   __shared__ HogWinDesc s_desc[4];                                  // ring: iteration it reads [it & 3], the last thread fills [(it + 2) & 3]
   float* smag = reinterpret_cast<float*>(hw_smem);                  // [H][ms]
@@ -468,14 +471,14 @@ k_hog_window_cascade(const LevelDesc* __restrict__ levels, int nlevels, const in
     }
   };
   if (tid == 0) {
-    s_desc[0] = hog_win_locate(levels, nlevels, blk, blockIdx.x);
-    if ((long long)blockIdx.x + gridDim.x < nwin) s_desc[1] = hog_win_locate(levels, nlevels, blk, (long long)blockIdx.x + gridDim.x);
+    s_desc[0] = hog_win_locate(levels, nlevels, blk, w_begin + blockIdx.x);
+    if (w_begin + blockIdx.x + gridDim.x < nwin) s_desc[1] = hog_win_locate(levels, nlevels, blk, w_begin + blockIdx.x + gridDim.x);
   }
   __syncthreads();
   prefetch(s_desc[0]);
   int it = 0;
   long long prev_wi = -1;
-  for (long long wi = blockIdx.x; wi < nwin; wi += gridDim.x, ++it) {
+  for (long long wi = w_begin + blockIdx.x; wi < nwin; wi += gridDim.x, ++it) {
     const HogWinDesc d = s_desc[it & 3];
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                   // this window's pixels have landed; the previous window's planes are complete
@@ -1638,7 +1641,29 @@ static bool use_hog_window_path(const cc_ctx* ctx, const MineState* m) {
   if ((ctx->W / HOG_GRID) * 10 > HOGW_THREADS || ctx->H / HOG_GRID > HOGW_MAXQ || ctx->W > HOGW_THREADS - 32) return false;
   return hog_win_geometry(ctx->W, ctx->H).smem <= (size_t)200 * 1024;
 }
-static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nwin, std::vector<unsigned>& survivors) {
+// Image-sharded mining (an NCCL communicator is attached): every rank evaluates a contiguous slice [w0, w1) of the batch's windows
+// and builds only the levels [l0, l0 + nl) that hold them; the survivor sets are merged as bitmaps (collect_survivors).
+struct HogShard { long long w0 = 0, w1 = 0; int l0 = 0, nl = 0, tiles = 0; bool sharded = false; };
+static HogShard hog_shard(const cc_ctx* ctx, const MineState* m, std::vector<LevelDesc>& levels, long long nwin) {
+  HogShard h;
+  h.sharded = ctx->comm_world > 1 && ctx->nccl_comm && m->shard_images;
+  h.w0 = 0; h.w1 = nwin;
+  if (h.sharded) { h.w0 = nwin * ctx->comm_rank / ctx->comm_world; h.w1 = nwin * (ctx->comm_rank + 1) / ctx->comm_world; }
+  if (h.w1 <= h.w0 || levels.empty()) return h;
+  auto level_of = [&](long long wi) {
+    int lo = 0, hi = (int)levels.size() - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (levels[mid].w_base <= wi) lo = mid; else hi = mid - 1; }
+    return lo;
+  };
+  h.l0 = level_of(h.w0);
+  const int l1 = level_of(h.w1 - 1);
+  h.nl = l1 - h.l0 + 1;
+  h.tiles = resize_tiles(levels, h.l0, l1);
+  return h;
+}
+static int collect_survivors(cc_ctx* ctx, MineState* m, bool sharded, long long nwin, const unsigned int* d_count, const unsigned int* d_list,
+                             std::vector<unsigned>& survivors);
+static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nwin, const HogShard& hs, std::vector<unsigned>& survivors) {
   survivors.clear();
   if (nwin == 0) return CC_OK;
   if (!m->d_hog_lut) {
@@ -1659,15 +1684,15 @@ static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nw
     CC_CUDA(cudaGetLastError());
     CC_CUDA(cudaMemsetAsync(m->d_surv, 0, sizeof(unsigned), ctx->stream));
     const int per_sm = std::max(1, (int)((size_t)227 * 1024 / (g.smem + 1024)));
-    const int grid = (int)std::min<long long>(nwin, (long long)ctx->sm_count * per_sm * 4);
+    const int grid = (int)std::min<long long>(hs.w1 - hs.w0, (long long)ctx->sm_count * per_sm * 4);
 #define HOGW_LAUNCH(NQ)                                                                                                                      \
   {                                                                                                                                          \
     CC_CUDA(cudaFuncSetAttribute(k_hog_window_cascade<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.smem));                       \
     k_hog_window_cascade<NQ><<<grid, HOGW_THREADS, g.smem, ctx->stream>>>(m->d_levels, nlevels, m->d_hog_blk, m->d_pool, m->d_hog_lut, g,    \
                                                                            ctx->d_hog_taps, m->d_nodes, m->d_tree_first, m->d_stages,        \
-                                                                           (int)m->stages.size(), nwin, m->d_surv, m->d_surv + 1, m->surv_cap); \
+                                                                           (int)m->stages.size(), hs.w0, hs.w1, m->d_surv, m->d_surv + 1, m->surv_cap); \
   }
-    switch (g.rows / HOG_GRID) {
+    if (grid > 0) switch (g.rows / HOG_GRID) {
       case 24: HOGW_LAUNCH(24); break;      // 96 rows (BASELINE configs[3])
       case 32: HOGW_LAUNCH(32); break;      // 128
       case 16: HOGW_LAUNCH(16); break;      // 64
@@ -1676,16 +1701,7 @@ static int eval_hog_windows(cc_ctx* ctx, MineState* m, int nlevels, long long nw
 #undef HOGW_LAUNCH
     CC_CUDA(cudaGetLastError());
   }
-  CC_CUDA(cudaMemcpyAsync(m->h_surv, m->d_surv, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-  CC_CUDA(cudaStreamSynchronize(ctx->stream));
-  const unsigned cnt = std::min(m->h_surv[0], m->surv_cap);
-  if (cnt) {
-    CC_CUDA(cudaMemcpyAsync(m->h_surv + 1, m->d_surv + 1, sizeof(unsigned) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
-    CC_CUDA(cudaStreamSynchronize(ctx->stream));
-    survivors.assign(m->h_surv + 1, m->h_surv + 1 + cnt);
-    std::sort(survivors.begin(), survivors.end());
-  }
-  return CC_OK;
+  return collect_survivors(ctx, m, hs.sharded, nwin, m->d_surv, m->d_surv + 1, survivors);
 }
 
 // copy accepted scratch windows into training slots [first, first+n) and build their integrals
@@ -2648,17 +2664,17 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     // ---- GPU: levels, gather, integrals, cascade ----
     const bool direct = m->stages.empty();       // stage 0: every window passes, gather straight into the training slots
     long long take_direct = 0;
-    int rz_tiles = 0;
+    HogShard hshard;
     if (!level_path) {
       HostTimer halloc(ctx, "mine_host_alloc");
       CC_CHECK(ensure_scratch(ctx, m, (direct || hog_win) ? 1 : (int)nwin, bt.pool_px, (int)bt.levels.size(), direct ? 1 : nwin));
       halloc.stop();
-      if (hog_win) rz_tiles = resize_tiles(bt.levels);
+      if (hog_win) hshard = hog_shard(ctx, m, bt.levels, nwin);
       CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (!level_path) {
       ScopedTimer tm(ctx, "mine", hog_win ? 1 : 2);
-      if (hog_win) k_resize_tiles<<<std::min(rz_tiles, ctx->sm_count * 64), RZ_THREADS, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), rz_tiles, m->d_pool);
+      if (hog_win) { if (hshard.tiles > 0) k_resize_tiles<<<std::min(hshard.tiles, ctx->sm_count * 64), RZ_THREADS, 0, ctx->stream>>>(m->d_levels + hshard.l0, hshard.nl, hshard.tiles, m->d_pool); }
       else k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
       CC_CUDA(cudaGetLastError());
       if (direct) {
@@ -2706,7 +2722,7 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
       } else {
         HostTimer he(ctx, "mine_host_eval");
         if (tile_path) CC_CHECK(eval_tiles(ctx, m, bt, tgeom, survivors));
-        else if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), nwin, survivors));
+        else if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), nwin, hshard, survivors));
         else CC_CHECK(eval_scratch(ctx, m, (int)nwin, survivors));
         if (tile_path) m->stat_built += nwin;
         surv64.assign(survivors.begin(), survivors.end());
@@ -2943,17 +2959,18 @@ int cc_mine_scan_digest(cc_ctx* ctx, int img0, int nimg, int64_t* windows, int64
       return CC_OK;
     }
     CC_CHECK(ensure_scratch(ctx, m, hog_win ? 1 : nwin, bt.pool_px, (int)bt.levels.size(), nwin));
-    const int rz_tiles = hog_win ? resize_tiles(bt.levels) : 0;
+    HogShard hshard;
+    if (hog_win) hshard = hog_shard(ctx, m, bt.levels, nwin);
     CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
     {
       ScopedTimer tm(ctx, "mine", hog_win ? 1 : 2);
-      if (hog_win) k_resize_tiles<<<std::min(rz_tiles, ctx->sm_count * 64), RZ_THREADS, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), rz_tiles, m->d_pool);
+      if (hog_win) { if (hshard.tiles > 0) k_resize_tiles<<<std::min(hshard.tiles, ctx->sm_count * 64), RZ_THREADS, 0, ctx->stream>>>(m->d_levels + hshard.l0, hshard.nl, hshard.tiles, m->d_pool); }
       else k_resize_levels<<<grid_for(ctx, (long long)bt.pool_px, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), (long long)bt.pool_px, m->d_pool);
       if (!hog_win)
         k_gather_windows<<<grid_for(ctx, (long long)nwin * npx, 256), 256, 0, ctx->stream>>>(m->d_levels, (int)bt.levels.size(), m->d_pool, W, H, nwin, m->scratch.d_imgs);
       CC_CUDA(cudaGetLastError());
     }
-    if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), nwin, survivors));
+    if (hog_win) CC_CHECK(eval_hog_windows(ctx, m, (int)bt.levels.size(), nwin, hshard, survivors));
     else CC_CHECK(eval_scratch(ctx, m, nwin, survivors));
     account(total); total += nwin;
     bt = Batch();

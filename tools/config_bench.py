@@ -17,18 +17,30 @@ W, H = spec["W"], spec["H"]
 t0 = time.time()
 pos = synth.make_positives(int(spec["npos"] * 1.2) + 64, W, H, seed=12345)
 bgs = [synth.make_background(960, 720, 4000 + i, clutter=1.5) for i in range(24)]
-print("data %.1fs" % (time.time() - t0), flush=True)
-ctx = ccb.Context(0)
+
+rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+ctx = ccb.Context(local)
+if world > 1:          # under torchrun: feature-sharded stage training + image-sharded mining over NCCL
+    import torch
+    import torch.distributed as dist
+    from cascadeclassifier_b200.dist import init_comm
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    init_comm(ctx, dist, torch.device("cuda", local))
 out = io.StringIO()
 cc = CvCascadeClassifier(ctx, out=out)
 t0 = time.time()
 ok = cc.train(tempfile.mkdtemp(), "pos.vec", "bg.txt", spec["npos"], spec["nneg"], 1024, 1024, nst, CvCascadeParams(0, spec["ft"], (W, H)), spec["fp"],
               ccb.CvCascadeBoostParams(), positives=pos, backgrounds=bgs)
 ctx.synchronize()
-print("%s: %d stages in %.2f s" % (cfg, len(cc.stageClassifiers), time.time() - t0))
+if rank != 0:
+    dist.barrier(); dist.destroy_process_group(); sys.exit(0)
+print("%s: %d stages in %.2f s on %d GPU(s)" % (cfg, len(cc.stageClassifiers), time.time() - t0, world))
 for t, r in zip(cc.timings, cc.reports):
     print("  stage %2d: weak %3d  mine %7.3f s  train %6.3f s  neg consumed %10d  acceptanceRatio %.3g" %
           (t["stage"], t["weak"], t["mine_s"], t["train_s"], r["neg_consumed"], r["acceptance_ratio"]))
 for name in ["integral", "precalc", "sort", "split_search", "boost_small", "mine", "mine_host_assemble", "mine_host_eval", "mine_host_cut", "mine_host_alloc"]:
     ms, k = ctx.timing(name)
     print("   %-18s %9.3f ms  launches %d" % (name, ms, k))
+if world > 1:
+    dist.barrier(); dist.destroy_process_group()

@@ -20,7 +20,7 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 FT = int(sys.argv[1]) if len(sys.argv) > 1 else 0          # 0 Haar ALL (default), 1 LBP, 2 HOG 48x96
 W, H = (48, 96) if FT == 2 else (24, 24)
-pos = synth.make_positives(700 if FT != 2 else 300, W, H, seed=7)
+pos = synth.make_positives(700 if FT != 2 else 400, W, H, seed=7)
 bgs = synth.make_backgrounds(9, 400, 300, seed0=70, clutter=2.0)
 
 
@@ -28,7 +28,7 @@ def run(ctx):
     cc = CvCascadeClassifier(ctx, out=io.StringIO())
     d = tempfile.mkdtemp()
     fp = ccb.CvHaarFeatureParams(2) if FT == 0 else ccb.CvFeatureParams.create(FT)
-    npos, nneg, nst = (500, 900, 5) if FT != 2 else (200, 300, 3)
+    npos, nneg, nst = (500, 900, 5) if FT != 2 else (300, 600, 8)
     cc.train(d, "pos.vec", "bg.txt", npos, nneg, 1024, 1024, nst, CvCascadeParams(0, FT, (W, H)), fp,
              ccb.CvCascadeBoostParams(), positives=pos, backgrounds=bgs)
     imgs = cc.featureEvaluator.images(0, cc.curNumSamples)
