@@ -1373,8 +1373,12 @@ static int ensure_h_surv(MineState* m, size_t entries) {
   return CC_OK;
 }
 
-static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, int nlevels, long long surv_n = -1) {
+// `grow`: how much larger the largest batch of this call can be than this one (HOG window miner: batches grow with the falling
+// acceptance rate up to the batch limit) -- the buffers are sized for it at once, a cudaFree + cudaMalloc of gigabytes per growth step
+// costs more than a batch
+static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, int nlevels, long long surv_n = -1, double grow = 1.0) {
   if (surv_n < 0) surv_n = nwin;
+  grow = std::max(1.0, grow);
   if (nwin > m->scratch_cap) {
     store_free(m->scratch);
     CC_CHECK(store_alloc(ctx, m->scratch, nwin));
@@ -1384,19 +1388,23 @@ static int ensure_scratch(cc_ctx* ctx, MineState* m, int nwin, size_t pool_px, i
   // costs more than the batch)
   if (pool_px > m->pool_cap) {
     cudaFree(m->d_pool); m->d_pool = nullptr; m->pool_cap = 0;
-    const size_t cap = pool_px + pool_px / 2;
-    CC_CUDA(cudaMalloc(&m->d_pool, cap + 64));          // slack: the HOG miner copies the aligned words around a row
+    size_t cap = (size_t)std::min((double)pool_px * 1.25 * grow, std::max((double)pool_px * 1.5, 6.0e9));
+    if (cudaMalloc(&m->d_pool, cap + 64) != cudaSuccess) {      // slack: the HOG miner copies the aligned words around a row
+      (void)cudaGetLastError();
+      cap = pool_px + pool_px / 2;
+      CC_CUDA(cudaMalloc(&m->d_pool, cap + 64));
+    }
     m->pool_cap = cap;
   }
   if (nlevels > m->levels_cap) {
     cudaFree(m->d_levels); m->d_levels = nullptr; m->levels_cap = 0;
-    const int cap = nlevels + nlevels / 2 + 16;
+    const int cap = (int)std::min((double)nlevels * 1.25 * grow + 16, std::max((double)nlevels * 1.5 + 16, 4.0e6));
     CC_CUDA(cudaMalloc(&m->d_levels, sizeof(LevelDesc) * cap));
     m->levels_cap = cap;
   }
   if ((unsigned long long)surv_n > m->surv_cap) {
     cudaFree(m->d_surv); m->d_surv = nullptr; m->surv_cap = 0;
-    const size_t cap = (size_t)std::min<long long>(surv_n + surv_n / 2 + 1024, 0xFFFFFFF0ll);
+    const size_t cap = (size_t)std::min<double>(std::min((double)surv_n * 1.25 * grow, std::max((double)surv_n * 1.5, 4.0e7)) + 1024, 4294967280.0);
     CC_CUDA(cudaMalloc(&m->d_surv, sizeof(unsigned) * (cap + 1)));
     m->surv_cap = (unsigned)cap;
   }
@@ -2667,7 +2675,8 @@ int cc_mine_negatives(cc_ctx* ctx, int first_slot, int count, double min_ratio, 
     HogShard hshard;
     if (!level_path) {
       HostTimer halloc(ctx, "mine_host_alloc");
-      CC_CHECK(ensure_scratch(ctx, m, (direct || hog_win) ? 1 : (int)nwin, bt.pool_px, (int)bt.levels.size(), direct ? 1 : nwin));
+      CC_CHECK(ensure_scratch(ctx, m, (direct || hog_win) ? 1 : (int)nwin, bt.pool_px, (int)bt.levels.size(), direct ? 1 : nwin,
+                              hog_win ? (double)max_batch / (double)std::max<long long>(nwin, 1) : 1.0));
       halloc.stop();
       if (hog_win) hshard = hog_shard(ctx, m, bt.levels, nwin);
       CC_CUDA(cudaMemcpyAsync(m->d_levels, bt.levels.data(), sizeof(LevelDesc) * bt.levels.size(), cudaMemcpyHostToDevice, ctx->stream));
