@@ -11,6 +11,9 @@
 // surviving stream ordinals.  The host then applies the serial stopping rule to the ordered survivors,
 // copies the accepted windows into the training slots and leaves the reader state right behind the last
 // consumed window.  Evaluating windows past the stopping point is harmless: they are simply not consumed.
+// That literal form is kept as mode 2; by default Haar / LBP windows are evaluated from integral planes of whole pyramid
+// levels (k_lvl_build / k_lvl_cascade, with the survivor cache of the window stream) and HOG windows by one CTA per window
+// with everything in shared memory (k_hog_window_cascade).
 #include <algorithm>
 #include <chrono>
 #include <climits>
@@ -325,11 +328,12 @@ static HogWinGeom hog_win_geometry(int W, int H) {
   g.groups = W / HOG_GRID; g.rows = (H / HOG_GRID) * HOG_GRID;
   g.ss = (g.groups * 10) | 1;
   g.Sc = W / HOG_GRID + 1; g.Pc = g.Sc * (H / HOG_GRID + 1);
-  const size_t tile = std::max((size_t)H * g.ms * 4, (size_t)10 * g.Pc * 4);      // the planes reuse the magnitude tile
+  const size_t tile = (size_t)H * g.ms * 4;
   g.off_bin = (int)((tile + 15) & ~(size_t)15);
   g.off_S = (int)(((size_t)g.off_bin + (size_t)H * g.bs + 15) & ~(size_t)15);
   g.spb = (((W + 6) / 4) | 1) * 4;
-  g.off_px = (int)(((size_t)g.off_S + (size_t)g.rows * g.ss * 4 + 15) & ~(size_t)15);
+  // (the compact planes, 10 * Pc floats, later overwrite the row-prefix array: never larger than it, checked here)
+  g.off_px = (int)(((size_t)g.off_S + std::max((size_t)g.rows * g.ss * 4, (size_t)10 * g.Pc * 4) + 15) & ~(size_t)15);
   g.smem = (size_t)g.off_px + (size_t)H * g.spb;
   return g;
 }
