@@ -384,7 +384,8 @@ struct TileCarry { double a, b; float v; int cnt_has; };     // cnt_has = (count
 // One 256-position tile of one row.  EXACT == false: f32 estimate of every admissible split, returns the lane's
 // maximum.  EXACT == true: re-evaluates candidates whose estimate reaches `lim` with the reference's f64 formula,
 // in position order, keeping the first maximum (compared as exact fractions).
-template <int CRIT, bool HAS_Y, bool EXACT>
+// TOTALS (with EXACT == false): only the carries are advanced (the tile's totals when they come in as zero).
+template <int CRIT, bool HAS_Y, bool EXACT, bool TOTALS = false>
 __device__ __forceinline__ float ss_tile(const uint4 ci, const float4 cv0, const float4 cv1, uint32_t sw_addr, uint32_t sy_addr,
                                          int lane, uint32_t lt_mask, double totA, double totB, float ftotA, float ftotB,
                                          double& carryA, double& carryB, float& carryV, int& carryHas, int& carryCnt, float lim,
@@ -447,12 +448,14 @@ __device__ __forceinline__ float ss_tile(const uint4 ci, const float4 cv0, const
   float fa = (float)pa0, fb = (float)pb0;
   float tmax = -3.0e38f;
   unsigned pass = 0;
+  if (!TOTALS) {
 #pragma unroll
-  for (int j = 0; j < SS_EPT; ++j) {
-    const float est = criterion32<CRIT>(fa, fb, ftotA, ftotB);
-    if (EXACT) { if (!(est < lim)) pass |= 1u << j; }
-    else tmax = ((cand >> j) & 1u) ? fmaxf(tmax, est == est ? est : 3.0e38f) : tmax;     // NaN (0/0 at the ends) counts as "unknown, maybe large"
-    fa += af[j]; fb += bf[j];
+    for (int j = 0; j < SS_EPT; ++j) {
+      const float est = criterion32<CRIT>(fa, fb, ftotA, ftotB);
+      if (EXACT) { if (!(est < lim)) pass |= 1u << j; }
+      else tmax = ((cand >> j) & 1u) ? fmaxf(tmax, est == est ? est : 3.0e38f) : tmax;     // NaN (0/0 at the ends) counts as "unknown, maybe large"
+      fa += af[j]; fb += bf[j];
+    }
   }
   if (EXACT) {
     pass &= cand;
@@ -592,6 +595,159 @@ k_split_search_ord(const uint16_t* __restrict__ sidx, const float* __restrict__ 
         if (k > *reinterpret_cast<volatile unsigned long long*>(&ctl->key)) atomicMax(&ctl->key, k);
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The same search with one CTA per row, for the short row lists of the pruned search (seed rows of a feature shard, rows flagged
+// by k_ss_bound).  k_split_search_ord gives a row to one warp, which walks its 59 tiles one after the other: ~85 us whatever
+// the number of rows -- the floor of a tree node on a 1/8 feature shard.  Here the 16 warps of a CTA take contiguous segments
+// of the row's tiles: (0) every tile's totals (the carries of ss_tile, started from zero), (1) one thread chains them in tile
+// order -- the same additions in the same order as the running carries of the one-warp walk, so every tile sees bit-identical
+// carries --, (2) f32 estimates per tile and the row maximum, (3) exact evaluation of the tiles that can hold it, (4) arg max
+// over the warps with the rule of the warp-level arg max (larger quality, then smaller position).  Same result bits.
+// ------------------------------------------------------------------------------------------------
+template <int CRIT, bool HAS_Y>
+__global__ void __launch_bounds__(SS_THREADS, 1)
+k_split_search_ord_coop(const uint16_t* __restrict__ sidx, const float* __restrict__ sval, int n_stride, int N, int nrows,
+                        const double* __restrict__ wnode, const float* __restrict__ ynode, const NodeStats* __restrict__ stats,
+                        double filter_ymax2, RowBest* __restrict__ out, const int* __restrict__ row_list,
+                        const unsigned int* __restrict__ list_count, SearchCtl* __restrict__ ctl) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int nwork = list_count ? (int)min(*list_count, (unsigned int)nrows) : nrows;
+  if ((int)blockIdx.x >= nwork) return;
+  const int ntile = (N + SS_TILE - 1) / SS_TILE;
+  double* sw = reinterpret_cast<double*>(smem_raw);                      // [N+1]; entry N = 0 is what the row padding points at
+  TileCarry* carries = reinterpret_cast<TileCarry*>(sw + N + 1);         // [ntile]: carries INTO tile t
+  TileCarry* tot = carries + ntile;                                      // [ntile]: totals OF tile t
+  float* tilemax = reinterpret_cast<float*>(tot + ntile);                // [ntile]
+  float* sy = tilemax + ntile;                                           // [N+1] (LogitBoost only)
+  __shared__ float s_wmax[SS_WARPS], s_vl[SS_WARPS], s_vr[SS_WARPS];
+  __shared__ double s_bval[SS_WARPS];
+  __shared__ int s_bpos[SS_WARPS];
+  for (int i = threadIdx.x; i <= N; i += SS_THREADS) { sw[i] = i < N ? wnode[i] : 0.0; if (HAS_Y) sy[i] = i < N ? ynode[i] : 0.f; }
+  __syncthreads();
+  const uint32_t sw_addr = (uint32_t)__cvta_generic_to_shared(sw);
+  const uint32_t sy_addr = (uint32_t)__cvta_generic_to_shared(sy);
+  const NodeStats st = *stats;
+  const double totA = st.rcw[0];
+  const double totB = (CRIT == CRIT_SQERR) ? st.rsum0 : st.rcw[1];
+  const float ftotA = (float)totA, ftotB = (float)totB;
+  const float filter_abs = (float)(4e-6 * (st.rcw[0] + st.rcw[1]) * filter_ymax2 + 1e-30);       // as k_split_search_ord
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  const int per = (ntile + SS_WARPS - 1) / SS_WARPS;
+  const int t0 = min(ntile, warp * per), t1 = min(ntile, t0 + per);
+
+  for (int wi = blockIdx.x; wi < nwork; wi += gridDim.x) {
+    const int row = row_list ? row_list[wi] : wi;
+    const uint16_t* ri = sidx + (size_t)row * n_stride;
+    const float* rv = sval + (size_t)row * n_stride;
+    double bestNum = -1.0, bestDen = 1.0;
+    int bestPos = -1;
+    float bestVl = 0.f, bestVr = 0.f;
+    // ---------------- (0) totals of my tiles ----------------
+    for (int t = t0; t < t1; ++t) {
+      const int o = t * SS_TILE + lane * SS_EPT;
+      const uint4 ci = *reinterpret_cast<const uint4*>(ri + o);
+      const float4 cv0 = *reinterpret_cast<const float4*>(rv + o), cv1 = *reinterpret_cast<const float4*>(rv + o + 4);
+      double cA = 0, cB = 0;
+      float cV = 0.f;
+      int cH = 0, cC = 0;
+      ss_tile<CRIT, HAS_Y, false, true>(ci, cv0, cv1, sw_addr, sy_addr, lane, lt_mask, totA, totB, ftotA, ftotB, cA, cB, cV, cH, cC, 0.f, bestNum,
+                                        bestDen, bestPos, bestVl, bestVr);
+      if (lane == 0) { tot[t].a = cA; tot[t].b = cB; tot[t].v = cV; tot[t].cnt_has = (cC << 1) | cH; }
+    }
+    __syncthreads();
+    // ---------------- (1) carries into every tile: the totals chained in tile order ----------------
+    if (threadIdx.x == 0) {
+      double a = 0, b = 0;
+      float v = 0.f;
+      int has = 0, cnt = 0;
+      for (int t = 0; t < ntile; ++t) {
+        carries[t].a = a; carries[t].b = b; carries[t].v = v; carries[t].cnt_has = (cnt << 1) | has;
+        a += tot[t].a; b += tot[t].b; cnt += tot[t].cnt_has >> 1;
+        if (tot[t].cnt_has & 1) { v = tot[t].v; has = 1; }
+      }
+    }
+    __syncthreads();
+    // ---------------- (2) f32 estimates, per-tile maxima, row maximum ----------------
+    float rmax = -3.0e38f;
+    for (int t = t0; t < t1; ++t) {
+      const int o = t * SS_TILE + lane * SS_EPT;
+      const uint4 ci = *reinterpret_cast<const uint4*>(ri + o);
+      const float4 cv0 = *reinterpret_cast<const float4*>(rv + o), cv1 = *reinterpret_cast<const float4*>(rv + o + 4);
+      double cA = carries[t].a, cB = carries[t].b;
+      float cV = carries[t].v;
+      int cH = carries[t].cnt_has & 1, cC = carries[t].cnt_has >> 1;
+      float tm = ss_tile<CRIT, HAS_Y, false>(ci, cv0, cv1, sw_addr, sy_addr, lane, lt_mask, totA, totB, ftotA, ftotB, cA, cB, cV, cH, cC, 0.f,
+                                             bestNum, bestDen, bestPos, bestVl, bestVr);
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, d));
+      if (lane == 0) tilemax[t] = tm;
+      rmax = fmaxf(rmax, tm);
+    }
+    if (lane == 0) s_wmax[warp] = rmax;
+    __syncthreads();
+    rmax = s_wmax[lane & (SS_WARPS - 1)];
+#pragma unroll
+    for (int d = SS_WARPS / 2; d > 0; d >>= 1) rmax = fmaxf(rmax, __shfl_xor_sync(0xffffffffu, rmax, d));
+    // ---------------- (3) exact evaluation of my tiles that can hold the maximum ----------------
+    const float lim = rmax - (1e-5f * fabsf(rmax) + filter_abs);
+    for (int t = t0; t < t1; ++t) {
+      if (!(tilemax[t] >= lim)) continue;           // warp-uniform (shared memory broadcast)
+      const int o = t * SS_TILE + lane * SS_EPT;
+      const uint4 ci = *reinterpret_cast<const uint4*>(ri + o);
+      const float4 cv0 = *reinterpret_cast<const float4*>(rv + o), cv1 = *reinterpret_cast<const float4*>(rv + o + 4);
+      double cA = carries[t].a, cB = carries[t].b;
+      float cV = carries[t].v;
+      int cH = carries[t].cnt_has & 1, cC = carries[t].cnt_has >> 1;
+      ss_tile<CRIT, HAS_Y, true>(ci, cv0, cv1, sw_addr, sy_addr, lane, lt_mask, totA, totB, ftotA, ftotB, cA, cB, cV, cH, cC, lim, bestNum,
+                                 bestDen, bestPos, bestVl, bestVr);
+    }
+    // ---------------- (4) arg max: lanes, then warps (larger value first, then smaller position) ----------------
+    double bestVal = bestPos >= 0 ? bestNum / bestDen : -1.0;
+    {
+      int owner = lane;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bestVal, d);
+        const int op = __shfl_xor_sync(0xffffffffu, bestPos, d);
+        const int oo = __shfl_xor_sync(0xffffffffu, owner, d);
+        const bool take = op >= 0 && (bestPos < 0 || ov > bestVal || (ov == bestVal && op < bestPos));
+        if (take) { bestVal = ov; bestPos = op; owner = oo; }
+      }
+      const float vl = __shfl_sync(0xffffffffu, bestVl, owner), vr = __shfl_sync(0xffffffffu, bestVr, owner);
+      if (lane == 0) { s_bval[warp] = bestVal; s_bpos[warp] = bestPos; s_vl[warp] = vl; s_vr[warp] = vr; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const int src = lane & (SS_WARPS - 1);
+      double bv = s_bval[src];
+      int bp = s_bpos[src], owner = src;
+#pragma unroll
+      for (int d = SS_WARPS / 2; d > 0; d >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, bv, d);
+        const int op = __shfl_xor_sync(0xffffffffu, bp, d);
+        const int oo = __shfl_xor_sync(0xffffffffu, owner, d);
+        const bool take = op >= 0 && (bp < 0 || ov > bv || (ov == bv && op < bp));
+        if (take) { bv = ov; bp = op; owner = oo; }
+      }
+      if (lane == 0) {
+        const float vl = s_vl[owner], vr = s_vr[owner];
+        RowBest rb;
+        rb.q = bp >= 0 ? (float)bv : -1.f;
+        rb.c = __fmul_rn(__fadd_rn(vl, vr), 0.5f);
+        rb.vleft = vl;
+        rb.pos = bp;
+        out[row] = rb;
+        if (rb.q > 0.f) {
+          const unsigned long long k = ((unsigned long long)__float_as_uint(rb.q) << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned)row);
+          if (k > *reinterpret_cast<volatile unsigned long long*>(&ctl->key)) atomicMax(&ctl->key, k);
+        }
+      }
+    }
+    __syncthreads();                                 // tot / carries / tilemax / s_* are reused by the next row
   }
 }
 
@@ -1365,6 +1521,22 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
     else LAUNCH_SS(CRIT_MISCLASS, false, BLOCKS, NWORK, LIST, COUNT)                                           \
     CC_CUDA(cudaGetLastError());                                                                               \
   }
+    // one CTA per row (k_split_search_ord_coop) for the short row lists of the pruned search
+    const size_t csmem = (size_t)(N + 1) * 8 + (size_t)ntile * (2 * sizeof(TileCarry) + 4) + (has_y ? (size_t)(N + 1) * 4 : 0) + 16;
+#define LAUNCH_SC(CR, HY, BLOCKS, NWORK, LIST, COUNT)                                                                            \
+  {                                                                                                                              \
+    CC_CUDA(cudaFuncSetAttribute(k_split_search_ord_coop<CR, HY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));     \
+    k_split_search_ord_coop<CR, HY><<<BLOCKS, SS_THREADS, csmem, ctx->stream>>>(ctx->d_sidx, ctx->d_sval, ctx->n_stride, N, NWORK, \
+                                                                                b->wnode, b->ynode, b->d_stats + nid, ymax2, b->rowbest, \
+                                                                                LIST, COUNT, b->d_ctl);                           \
+  }
+#define LAUNCH_SC_CRIT(BLOCKS, NWORK, LIST, COUNT)                                                             \
+  {                                                                                                            \
+    if (b->crit == CRIT_SQERR) { if (has_y) LAUNCH_SC(CRIT_SQERR, true, BLOCKS, NWORK, LIST, COUNT) else LAUNCH_SC(CRIT_SQERR, false, BLOCKS, NWORK, LIST, COUNT) } \
+    else if (b->crit == CRIT_GINI) LAUNCH_SC(CRIT_GINI, false, BLOCKS, NWORK, LIST, COUNT)                     \
+    else LAUNCH_SC(CRIT_MISCLASS, false, BLOCKS, NWORK, LIST, COUNT)                                           \
+    CC_CUDA(cudaGetLastError());                                                                               \
+  }
     if (!pruned) {
       LAUNCH_SS_CRIT(blocks, ctx->nrows, (const int*)nullptr, (const unsigned int*)nullptr)
       k_argmax_rows<<<1, ONE_CTA, 0, ctx->stream>>>(b->rowbest, nullptr, ctx->nrows, ctx->row0, b->d_best);
@@ -1373,8 +1545,13 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
       // (1) exact search over the seed rows -> pruning threshold, (2) bound pass over every row, (3) exact search
       // over the flagged rows, (4) winner from the packed key
       const int nseed = (int)b->seed_rows.size();
-      const int seed_blocks = std::min((nseed + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
-      LAUNCH_SS_CRIT(seed_blocks, nseed, b->d_seed_rows, (const unsigned int*)nullptr)
+      const int coop_blocks = ctx->sm_count * std::max(1, std::min(2, (int)((220 * 1024) / (csmem + 1024))));
+      if (ctx->shard_world > 1) {      // a feature shard searches SEED_TARGET / world seed rows: a few per SM, one CTA each
+        LAUNCH_SC_CRIT(std::min(nseed, coop_blocks), nseed, b->d_seed_rows, (const unsigned int*)nullptr)
+      } else {
+        const int seed_blocks = std::min((nseed + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
+        LAUNCH_SS_CRIT(seed_blocks, nseed, b->d_seed_rows, (const unsigned int*)nullptr)
+      }
       const size_t bsmem = (size_t)(N + 1) * sizeof(float);
       const int bper_sm = std::max(1, std::min(3, (int)((220 * 1024) / (bsmem + 1024))));
       const int bblocks = std::min((ctx->nrows + SB_WARPS - 1) / SB_WARPS, ctx->sm_count * bper_sm);
@@ -1388,12 +1565,14 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
                                                                       b->d_ctl, b->d_flag_rows);
       }
       CC_CUDA(cudaGetLastError());
-      LAUNCH_SS_CRIT(blocks, ctx->nrows, b->d_flag_rows, &b->d_ctl->nflag)
+      LAUNCH_SC_CRIT(std::min(ctx->nrows, coop_blocks), ctx->nrows, b->d_flag_rows, &b->d_ctl->nflag)      // (a few hundred rows at most, typically)
       k_finalize_best<<<1, 32, 0, ctx->stream>>>(b->d_ctl, b->rowbest, ctx->row0, b->d_best);
       b->row_quality_valid = false;
       b->stat_searches++; b->stat_seed_rows += nseed;
       ctx->launches += 3;
     }
+#undef LAUNCH_SC_CRIT
+#undef LAUNCH_SC
 #undef LAUNCH_SS_CRIT
 #undef LAUNCH_SS
   }
@@ -1562,10 +1741,12 @@ int cc_boost_train(cc_ctx* ctx, int num_samples, const cc_boost_params* p, cc_st
     CC_CUDA(cudaGetLastError());
   }
   if (b->d_seed_rows) {     // seed rows of the pruned split search: a strided sample of the local rows
-    const int stride = std::max(1, ctx->nrows / SEED_TARGET);
+    // (a feature shard takes its share of the seed rows: the exact search of the seeds is latency-bound, see k_split_search_ord_coop)
+    const int seed_target = std::max(256, SEED_TARGET / std::max(1, ctx->shard_world));
+    const int stride = std::max(1, ctx->nrows / seed_target);
     b->seed_rows.clear();
     b->seed_rows.reserve(b->seed_cap);
-    for (int r = stride / 2; r < ctx->nrows && (int)b->seed_rows.size() < SEED_TARGET; r += stride) b->seed_rows.push_back(r);
+    for (int r = stride / 2; r < ctx->nrows && (int)b->seed_rows.size() < seed_target; r += stride) b->seed_rows.push_back(r);
     b->n_seed_static = (int)b->seed_rows.size();
     CC_CUDA(cudaMemcpyAsync(b->d_seed_rows, b->seed_rows.data(), sizeof(int) * b->seed_rows.size(), cudaMemcpyHostToDevice, ctx->stream));
   }
