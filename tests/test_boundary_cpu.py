@@ -215,3 +215,37 @@ def test_train_error_paths_of_the_reference(tmp_path):
     with pytest.raises(ccb.CascadeCudaError):
         CvCascadeClassifier(None, out=io.StringIO()).train("", "x.vec", str(bg), 10, 1, 64, 64, 1, CvCascadeParams(1 * 0, 1, (75, 32)),
                                                            ccb.CvFeatureParams.create(1), ccb.CvCascadeBoostParams())
+
+
+def test_createsamples_from_info_collection(tmp_path):
+    """`opencv_createsamples -info` (cvCreateTrainingSamplesFromInfo, tools/createsamples/utility.cpp:1125-1230): rectangles of the
+    collection file, image paths relative to it, INTER_AREA when shrinking in both directions else INTER_LINEAR_EXACT, `num` in the
+    header, a parse error ends the file."""
+    import struct
+    import cv2
+    from cascadeclassifier_b200 import synth
+    from cascadeclassifier_b200.createsamples import cvCreateTrainingSamplesFromInfo
+    rng = np.random.default_rng(5)
+    a = rng.integers(0, 256, (120, 160), dtype=np.uint8)
+    b = rng.integers(0, 256, (90, 70), dtype=np.uint8)
+    d = tmp_path / "set"
+    d.mkdir()
+    cv2.imwrite(str(d / "a.png"), a)
+    cv2.imwrite(str(d / "b.png"), b)
+    (d / "info.dat").write_text("a.png 2 10 12 48 60 0 0 20 30\nb.png 1 5 6 24 24\na.png 1 1 2 30 oops\n")
+    vec = tmp_path / "out" / "deep" / "s.vec"                     # icvMkDir: the directory hierarchy is created
+    n = cvCreateTrainingSamplesFromInfo(str(d / "info.dat"), str(vec), 10, 0, 24, 24)
+    assert n == 3                                                 # the 4th object has a parse error: the file ends there
+    with open(vec, "rb") as f:
+        count, vec_size, z0, z1 = struct.unpack("<iihh", f.read(12))
+    assert (count, vec_size, z0, z1) == (10, 576, 0, 0)           # the header carries the requested number
+    got = synth.read_vec(str(vec), 24, 24)
+    assert got.shape == (3, 24, 24)
+    assert np.array_equal(got[0], cv2.resize(a[12:72, 10:58], (24, 24), interpolation=cv2.INTER_AREA))
+    assert np.array_equal(got[1], cv2.resize(a[0:30, 0:20], (24, 24), interpolation=cv2.INTER_LINEAR_EXACT))
+    assert np.array_equal(got[2], b[6:30, 5:29])                  # same size: INTER_AREA of a 1:1 resize is the crop
+    # `num` smaller than the collection: stops after num objects
+    assert cvCreateTrainingSamplesFromInfo(str(d / "info.dat"), str(tmp_path / "two.vec"), 2, 0, 24, 24) == 2
+    assert synth.read_vec(str(tmp_path / "two.vec"), 24, 24).shape == (2, 24, 24)
+    # unreadable collection file: nothing written, 0 returned
+    assert cvCreateTrainingSamplesFromInfo(str(d / "missing.dat"), str(tmp_path / "none.vec"), 2, 0, 24, 24) == 0
