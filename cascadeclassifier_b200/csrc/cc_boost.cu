@@ -127,6 +127,7 @@ struct BoostBuffers {
   int* d_flag_rows = nullptr;
   std::vector<int> seed_rows;         // strided sample of the local rows + the winners of this stage so far
   int seed_cap = 0, n_seed_static = 0;
+  int last_nflag = -1;                // rows flagged by the bound pass of the last search read back (-1: none yet in this stage)
   int search_mode = 0;                // 0 = pruned (default), 1 = exhaustive (every row evaluated exactly)
   int tree_path = 0;                  // 0 = stumps grown without a host round trip inside the tree (default), 1 = general node-by-node path
   long long stat_searches = 0, stat_seed_rows = 0, stat_flag_rows = 0;
@@ -1565,7 +1566,13 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
                                                                       b->d_ctl, b->d_flag_rows);
       }
       CC_CUDA(cudaGetLastError());
-      LAUNCH_SC_CRIT(std::min(ctx->nrows, coop_blocks), ctx->nrows, b->d_flag_rows, &b->d_ctl->nflag)      // (a few hundred rows at most, typically)
+      // The number of flagged rows is only known on the device; the last search read back predicts it.  A few rows per SM:
+      // one CTA per row (~25 us per row); more (or nothing known yet): one warp per row (~85 us per wave of 16 rows per SM).
+      if (b->last_nflag >= 0 && b->last_nflag <= 3 * ctx->sm_count) {
+        LAUNCH_SC_CRIT(std::min(ctx->nrows, coop_blocks), ctx->nrows, b->d_flag_rows, &b->d_ctl->nflag)
+      } else {
+        LAUNCH_SS_CRIT(blocks, ctx->nrows, b->d_flag_rows, &b->d_ctl->nflag)
+      }
       k_finalize_best<<<1, 32, 0, ctx->stream>>>(b->d_ctl, b->rowbest, ctx->row0, b->d_best);
       b->row_quality_valid = false;
       b->stat_searches++; b->stat_seed_rows += nseed;
@@ -1621,7 +1628,7 @@ static int grow_node(cc_ctx* ctx, BoostBuffers* b, std::vector<HostNode>& nodes,
   CC_CUDA(cudaMemcpyAsync(b->h_best, b->d_best, sizeof(BestSplit), cudaMemcpyDeviceToHost, ctx->stream));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
   const BestSplit bs = *b->h_best;
-  if (b->d_seed_rows && !b->row_quality_valid) b->stat_flag_rows += bs.pad[0];
+  if (b->d_seed_rows && !b->row_quality_valid) { b->stat_flag_rows += bs.pad[0]; b->last_nflag = (int)bs.pad[0]; }
   if (!bs.valid) return CC_OK;
   if (b->d_seed_rows && bs.var >= ctx->row0 && bs.var < ctx->row0 + ctx->nrows && (int)b->seed_rows.size() < b->seed_cap) {
     // the winner of this search stays a strong candidate for the next ones: evaluate it exactly up front
@@ -1683,7 +1690,7 @@ static int grow_stump_and_finish(cc_ctx* ctx, BoostBuffers* b, const EvalView& e
   CC_CUDA(cudaMemcpyAsync(b->h_summary, b->d_summary, sizeof(TreeSummary), cudaMemcpyDeviceToHost, ctx->stream));
   CC_CUDA(cudaStreamSynchronize(ctx->stream));
   const BestSplit bs = *b->h_best;
-  if (b->d_seed_rows && !b->row_quality_valid) b->stat_flag_rows += bs.pad[0];
+  if (b->d_seed_rows && !b->row_quality_valid) { b->stat_flag_rows += bs.pad[0]; b->last_nflag = (int)bs.pad[0]; }
   nodes[0].value = b->h_stats[0].value; nodes[0].n = b->h_stats[0].n;
   ok = *b->h_tree_ok != 0;
   if (!ok) return CC_OK;
@@ -1741,6 +1748,7 @@ int cc_boost_train(cc_ctx* ctx, int num_samples, const cc_boost_params* p, cc_st
     CC_CUDA(cudaGetLastError());
   }
   if (b->d_seed_rows) {     // seed rows of the pruned split search: a strided sample of the local rows
+    b->last_nflag = -1;
     // (a feature shard takes its share of the seed rows: the exact search of the seeds is latency-bound, see k_split_search_ord_coop)
     const int seed_target = std::max(256, SEED_TARGET / std::max(1, ctx->shard_world));
     const int stride = std::max(1, ctx->nrows / seed_target);
