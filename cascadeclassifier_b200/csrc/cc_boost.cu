@@ -1547,7 +1547,7 @@ static int launch_split_search(cc_ctx* ctx, BoostBuffers* b, int nid) {
       // over the flagged rows, (4) winner from the packed key
       const int nseed = (int)b->seed_rows.size();
       const int coop_blocks = ctx->sm_count * std::max(1, std::min(2, (int)((220 * 1024) / (csmem + 1024))));
-      if (ctx->shard_world > 1) {      // a feature shard searches SEED_TARGET / world seed rows: a few per SM, one CTA each
+      if (ctx->shard_world > 1 && nseed <= 6 * ctx->sm_count) {      // a feature shard searches SEED_TARGET / world seed rows: a few per SM, one CTA each
         LAUNCH_SC_CRIT(std::min(nseed, coop_blocks), nseed, b->d_seed_rows, (const unsigned int*)nullptr)
       } else {
         const int seed_blocks = std::min((nseed + SS_WARPS - 1) / SS_WARPS, ctx->sm_count * per_sm);
